@@ -1,0 +1,823 @@
+/*
+ * femtech_oracle.c -- TEST INFRASTRUCTURE ONLY (see femtech_oracle.h).
+ *
+ * Plain-C restatement of the FemTech hex8 explicit-dynamics hot path.  Every
+ * function follows the reference's arithmetic operation by operation (same
+ * summation order, same divisions vs reciprocal multiplies, same quirks) so
+ * that, compiled with -ffp-contract=off, it reproduces a reference build made
+ * with the same flag BIT FOR BIT (tests/test_oracle_golden.py).
+ *
+ * Citations are relative to /root/reference.
+ */
+#include "femtech_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define NDIM 3
+static const double huge_dt = 1e20; /* include/GlobalVariables.h:16 */
+
+/* ------------------------------------------------------------------------ */
+/* tiny BLAS restatements: naive left-to-right sums, identical to            */
+/* oracle/ref/blas_shim.c (the definition of "reference result")  */
+/* ------------------------------------------------------------------------ */
+/* C(3x3) = alpha * op(A) * op(B), column-major, beta = 0 */
+static void mm3(int ta, int tb, double alpha, const double *a, const double *b,
+                double *c) {
+  for (int j = 0; j < 3; ++j)
+    for (int i = 0; i < 3; ++i) {
+      double s = 0.0;
+      for (int l = 0; l < 3; ++l) {
+        double av = ta ? a[l + 3 * i] : a[i + 3 * l];
+        double bv = tb ? b[j + 3 * l] : b[l + 3 * j];
+        s += av * bv;
+      }
+      c[i + 3 * j] = alpha * s;
+    }
+}
+
+/* src/math/math.cpp:8-28 */
+static void inverse3x3Matrix(const double *mat, double *invMat, double *det) {
+  double detLocal = mat[0] * (mat[4] * mat[8] - mat[5] * mat[7]) -
+                    mat[3] * (mat[1] * mat[8] - mat[7] * mat[2]) +
+                    mat[6] * (mat[1] * mat[5] - mat[4] * mat[2]);
+  double invdet = 1 / detLocal;
+  invMat[0] = (mat[4] * mat[8] - mat[5] * mat[7]) * invdet;
+  invMat[3] = (mat[6] * mat[5] - mat[3] * mat[8]) * invdet;
+  invMat[6] = (mat[3] * mat[7] - mat[6] * mat[4]) * invdet;
+  invMat[1] = (mat[7] * mat[2] - mat[1] * mat[8]) * invdet;
+  invMat[4] = (mat[0] * mat[8] - mat[6] * mat[2]) * invdet;
+  invMat[7] = (mat[1] * mat[6] - mat[0] * mat[7]) * invdet;
+  invMat[2] = (mat[1] * mat[5] - mat[2] * mat[4]) * invdet;
+  invMat[5] = (mat[2] * mat[3] - mat[0] * mat[5]) * invdet;
+  invMat[8] = (mat[0] * mat[4] - mat[1] * mat[3]) * invdet;
+  *det = detLocal;
+}
+
+/* src/math/math.cpp:30-41 (ndim == 3 branch) */
+static double normOfCrossProduct(const double *a, const double *b) {
+  double z = a[0] * b[1] - a[1] * b[0];
+  double x = a[1] * b[2] - a[2] * b[1];
+  double y = -a[0] * b[2] + a[2] * b[0];
+  return sqrt(x * x + y * y + z * z);
+}
+
+/* src/math/math.cpp:44-48 */
+static double tripleProduct(const double *s, const double *a, const double *b) {
+  return s[2] * (a[0] * b[1] - a[1] * b[0]) +
+         s[0] * (a[1] * b[2] - a[2] * b[1]) -
+         s[1] * (a[0] * b[2] - a[2] * b[0]);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Geometry (stable time step)                                               */
+/* ------------------------------------------------------------------------ */
+/* src/math/Geometry.cpp:3-27 */
+double oracle_volumeHexahedron(const double *L) {
+  double q0[3], q1[3], q2[3], q3[3], q4[3], q5[3];
+  for (int i = 0; i < 3; ++i) {
+    q0[i] = L[0 + i] - L[3 + i] + L[6 + i] - L[9 + i] + L[12 + i] - L[15 + i] +
+            L[18 + i] - L[21 + i];
+    q1[i] = L[0 + i] - L[3 + i] - L[6 + i] + L[9 + i] - L[12 + i] + L[15 + i] +
+            L[18 + i] - L[21 + i];
+    q2[i] = -L[0 + i] + L[3 + i] + L[6 + i] - L[9 + i] - L[12 + i] + L[15 + i] +
+            L[18 + i] - L[21 + i];
+    q3[i] = L[0 + i] + L[3 + i] - L[6 + i] - L[9 + i] - L[12 + i] - L[15 + i] +
+            L[18 + i] + L[21 + i];
+    q4[i] = -L[0 + i] - L[3 + i] + L[6 + i] + L[9 + i] - L[12 + i] - L[15 + i] +
+            L[18 + i] + L[21 + i];
+    q5[i] = -L[0 + i] - L[3 + i] - L[6 + i] - L[9 + i] + L[12 + i] + L[15 + i] +
+            L[18 + i] + L[21 + i];
+  }
+  return (tripleProduct(q0, q4, q3) + tripleProduct(q2, q0, q1) +
+          tripleProduct(q1, q3, q5)) / 192.0 +
+         tripleProduct(q2, q4, q5) / 64.0;
+}
+
+/* src/math/Geometry.cpp:29-64, including the signed (no fabs) parallelogram
+ * test of :46 */
+double oracle_areaHexahedronFace(const double *L, const int *index) {
+  const double *p1 = &L[3 * index[0]];
+  const double *p2 = &L[3 * index[1]];
+  const double *p3 = &L[3 * index[2]];
+  const double *p4 = &L[3 * index[3]];
+  double tol = 1e-6;
+  double centerD[3], c1[3], c2[3];
+  for (int i = 0; i < 3; ++i) {
+    centerD[i] = 0.25 * (p1[i] - p2[i] + p3[i] - p4[i]);
+    c1[i] = 0.25 * (-p1[i] + p2[i] + p3[i] - p4[i]);
+    c2[i] = 0.25 * (-p1[i] - p2[i] + p3[i] + p4[i]);
+  }
+  if ((centerD[0] < tol) && (centerD[1] < tol) && (centerD[2] < tol)) {
+    return 4.0 * normOfCrossProduct(c1, c2);
+  }
+  double t = sqrt(3.0) / 3.0;
+  const double q[2] = {-t, t};
+  double area = 0.0;
+  for (int i = 0; i < 2; ++i) {
+    for (int j = 0; j < 2; ++j) {
+      double v1[3], v2[3];
+      for (int k = 0; k < 3; ++k) {
+        v1[k] = q[j] * centerD[k] + c1[k];
+        v2[k] = q[i] * centerD[k] + c2[k];
+      }
+      area += normOfCrossProduct(v1, v2);
+    }
+  }
+  return area;
+}
+
+/* src/elements/CharacteristicLength/CalculateCharacteristicLength_C3D8.cpp:3-30 */
+static double characteristicLength_C3D8(const oracle_state *s, int e) {
+  double ec[24];
+  for (int j = 0; j < 8; ++j) {
+    int n = s->connectivity[8 * e + j];
+    for (int k = 0; k < 3; ++k) {
+      int index = NDIM * n + k;
+      ec[j * NDIM + k] = s->coordinates[index] + s->displacements[index];
+    }
+  }
+  static const int index[24] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 3, 7, 4,
+                                1, 2, 6, 5, 0, 1, 5, 4, 3, 2, 6, 7};
+  double cl = oracle_volumeHexahedron(ec);
+  double areaMax = 0.0, faceArea;
+  for (int i = 0; i < 6; ++i) {
+    faceArea = oracle_areaHexahedronFace(ec, &index[i * 4]);
+    if (faceArea > areaMax) areaMax = faceArea;
+  }
+  return cl / areaMax;
+}
+
+/* src/timestep/CalculateTimeStep.cpp:7-21 */
+double oracle_CalculateTimeStep(const oracle_state *s, int e) {
+  double le = characteristicLength_C3D8(s, e);
+  int pide = s->pid[e];
+  double mu = s->properties[ORACLE_MAXMATPARAMS * pide + 1];
+  double lambda = s->properties[ORACLE_MAXMATPARAMS * pide + 2];
+  double rho = s->properties[ORACLE_MAXMATPARAMS * pide + 0];
+  double nu = 0.5 * lambda / (lambda + mu);
+  double ce = sqrt(lambda * (1.0 / nu - 1.0) / rho);
+  return le / ce;
+}
+
+/* src/timestep/StableTimeStep.cpp:11-30 */
+double oracle_StableTimeStep_local(const oracle_state *s) {
+  double dtMin = huge_dt;
+  for (int i = 0; i < s->nElements; i++) {
+    int isNotRigid = 0;
+    for (int j = 8 * i; j < 8 * i + 8; ++j) {
+      int index = s->connectivity[j] * NDIM;
+      if (!(s->boundary[index] & s->boundary[index + 1] &
+            s->boundary[index + 2])) {
+        isNotRigid = 1;
+        break;
+      }
+    }
+    if (isNotRigid) {
+      double dtElem = oracle_CalculateTimeStep(s, i);
+      if (dtElem < dtMin) dtMin = dtElem;
+    }
+  }
+  return dtMin;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Shape functions (reference configuration, once)                           */
+/* ------------------------------------------------------------------------ */
+/* src/fem/ShapeFunctions/GaussQuadrature3D.cpp:17-58 */
+static const double GP_A = 0.577350269189626;
+static const double gp_sign[8][3] = {{-1, -1, 1}, {1, -1, 1}, {1, 1, 1},
+                                     {-1, 1, 1},  {-1, -1, -1}, {1, -1, -1},
+                                     {1, 1, -1},  {-1, 1, -1}};
+
+/* src/fem/ShapeFunctions/ShapeFunction_C3D8.cpp:4-128 */
+static void shapeFunction_C3D8(oracle_state *s, int e, int gp) {
+  const double chi = gp_sign[gp][0] * GP_A;
+  const double eta = gp_sign[gp][1] * GP_A;
+  const double iota = gp_sign[gp][2] * GP_A;
+  double *shp = &s->shp[64 * e + 8 * gp];
+  double *d = &s->dshp[192 * e + 24 * gp];
+  const double *X = s->coordinates;
+  const int *c = &s->connectivity[8 * e];
+
+  shp[0] = ((1 - chi) * (1 - eta) * (1 - iota)) / 8;
+  shp[1] = ((1 + chi) * (1 - eta) * (1 - iota)) / 8;
+  shp[2] = ((1 + chi) * (1 + eta) * (1 - iota)) / 8;
+  shp[3] = ((1 - chi) * (1 + eta) * (1 - iota)) / 8;
+  shp[4] = ((1 - chi) * (1 - eta) * (1 + iota)) / 8;
+  shp[5] = ((1 + chi) * (1 - eta) * (1 + iota)) / 8;
+  shp[6] = ((1 + chi) * (1 + eta) * (1 + iota)) / 8;
+  shp[7] = ((1 - chi) * (1 + eta) * (1 + iota)) / 8;
+
+  d[3 * 0 + 0] = -((eta - 1) * (iota - 1)) / 8;
+  d[3 * 1 + 0] = ((eta - 1) * (iota - 1)) / 8;
+  d[3 * 2 + 0] = -((eta + 1) * (iota - 1)) / 8;
+  d[3 * 3 + 0] = ((eta + 1) * (iota - 1)) / 8;
+  d[3 * 4 + 0] = ((eta - 1) * (iota + 1)) / 8;
+  d[3 * 5 + 0] = -((eta - 1) * (iota + 1)) / 8;
+  d[3 * 6 + 0] = ((eta + 1) * (iota + 1)) / 8;
+  d[3 * 7 + 0] = -((eta + 1) * (iota + 1)) / 8;
+
+  d[3 * 0 + 1] = -((chi - 1) * (iota - 1)) / 8;
+  d[3 * 1 + 1] = ((chi + 1) * (iota - 1)) / 8;
+  d[3 * 2 + 1] = -((chi + 1) * (iota - 1)) / 8;
+  d[3 * 3 + 1] = ((chi - 1) * (iota - 1)) / 8;
+  d[3 * 4 + 1] = ((chi - 1) * (iota + 1)) / 8;
+  d[3 * 5 + 1] = -((chi + 1) * (iota + 1)) / 8;
+  d[3 * 6 + 1] = ((chi + 1) * (iota + 1)) / 8;
+  d[3 * 7 + 1] = -((chi - 1) * (iota + 1)) / 8;
+
+  d[3 * 0 + 2] = -((chi - 1) * (eta - 1)) / 8;
+  d[3 * 1 + 2] = ((chi + 1) * (eta - 1)) / 8;
+  d[3 * 2 + 2] = -((chi + 1) * (eta + 1)) / 8;
+  d[3 * 3 + 2] = ((chi - 1) * (eta + 1)) / 8;
+  d[3 * 4 + 2] = ((chi - 1) * (eta - 1)) / 8;
+  d[3 * 5 + 2] = -((chi + 1) * (eta - 1)) / 8;
+  d[3 * 6 + 2] = ((chi + 1) * (eta + 1)) / 8;
+  d[3 * 7 + 2] = -((chi - 1) * (eta + 1)) / 8;
+
+  /* Jacobian from four paired differences per entry (:78-93) */
+  double xs[9];
+#define XC(n, j) X[NDIM * c[n] + (j)]
+  for (int j = 0; j < NDIM; j++) {
+    xs[0 + j * NDIM] = (XC(1, j) - XC(0, j)) * d[3 * 1 + 0] +
+                       (XC(2, j) - XC(3, j)) * d[3 * 2 + 0] +
+                       (XC(5, j) - XC(4, j)) * d[3 * 5 + 0] +
+                       (XC(6, j) - XC(7, j)) * d[3 * 6 + 0];
+    xs[1 + j * NDIM] = (XC(2, j) - XC(1, j)) * d[3 * 2 + 1] +
+                       (XC(3, j) - XC(0, j)) * d[3 * 3 + 1] +
+                       (XC(6, j) - XC(5, j)) * d[3 * 6 + 1] +
+                       (XC(7, j) - XC(4, j)) * d[3 * 7 + 1];
+    xs[2 + j * NDIM] = (XC(4, j) - XC(0, j)) * d[3 * 4 + 2] +
+                       (XC(5, j) - XC(1, j)) * d[3 * 5 + 2] +
+                       (XC(6, j) - XC(2, j)) * d[3 * 6 + 2] +
+                       (XC(7, j) - XC(3, j)) * d[3 * 7 + 2];
+  }
+#undef XC
+  double det, J_Inv[9];
+  inverse3x3Matrix(xs, J_Inv, &det);
+  s->detJacobian[8 * e + gp] = det;
+  /* dN/dX (:108-119) */
+  for (int i = 0; i < 8; ++i) {
+    double *b = &d[3 * i];
+    double c1 = b[0] * J_Inv[0] + b[1] * J_Inv[3] + b[2] * J_Inv[6];
+    double c2 = b[0] * J_Inv[1] + b[1] * J_Inv[4] + b[2] * J_Inv[7];
+    double c3 = b[0] * J_Inv[2] + b[1] * J_Inv[5] + b[2] * J_Inv[8];
+    b[0] = c1;
+    b[1] = c2;
+    b[2] = c3;
+  }
+}
+
+/* src/fem/ShapeFunctions/ShapeFunctions.cpp:181-252 */
+void oracle_ShapeFunctions(oracle_state *s) {
+  const int nE = s->nElements;
+  memset(s->shp, 0, sizeof(double) * 64 * (size_t)nE);
+  memset(s->dshp, 0, sizeof(double) * 192 * (size_t)nE);
+  memset(s->F, 0, sizeof(double) * 72 * (size_t)nE);
+  memset(s->pk2, 0, sizeof(double) * 48 * (size_t)nE);
+  for (size_t i = 0; i < 8 * (size_t)nE; ++i) {
+    s->F[i * 9] = 1.0;
+    s->F[i * 9 + 4] = 1.0;
+    s->F[i * 9 + 8] = 1.0;
+    s->detF[i] = 1.0;
+    s->gaussWeights[i] = 1.0;
+  }
+  for (int e = 0; e < nE; ++e)
+    for (int k = 0; k < 8; ++k) shapeFunction_C3D8(s, e, k);
+  if (s->Hn_1) memset(s->Hn_1, 0, sizeof(double) * 72 * (size_t)nE);
+  if (s->Hn_2) memset(s->Hn_2, 0, sizeof(double) * 72 * (size_t)nE);
+  if (s->S0n) memset(s->S0n, 0, sizeof(double) * 72 * (size_t)nE);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Lumped mass                                                               */
+/* ------------------------------------------------------------------------ */
+/* src/fem/Mass/Mass3D.cpp:5-67 + :127-157.  The 24x24 consistent matrix
+ * N^T N has the block form Me[(3n+a) + 24*(3m+b)] = delta_ab * N_n * N_m; the
+ * reference accumulates it with dgemm (k = 3 inner terms, two of which are
+ * exact zeros), scales by w*detJ per Gauss point, by rho at the end, and then
+ * lumps rows in ascending column-block order.  The exact zeros do not change
+ * any rounding, so only the non-zero entries are carried here. */
+void oracle_AssembleLumpedMass_local(oracle_state *s) {
+  for (int e = 0; e < s->nElements; ++e) {
+    double Me[8][8]; /* Me[n][m] = sum_gp (N_n N_m) * pre */
+    memset(Me, 0, sizeof(Me));
+    for (int k = 0; k < 8; ++k) {
+      const double *shp = &s->shp[64 * e + 8 * k];
+      int wIndex = 8 * e + k;
+      const double preFactor = s->gaussWeights[wIndex] * s->detJacobian[wIndex];
+      for (int n = 0; n < 8; ++n)
+        for (int m = 0; m < 8; ++m) {
+          /* dgemm inner sum: 0 + Nn*Nm + (exact zeros) ; alpha = 1 */
+          double MeGQ = shp[n] * shp[m];
+          Me[n][m] += MeGQ * preFactor;
+        }
+    }
+    double rho = s->properties[ORACLE_MAXMATPARAMS * s->pid[e]];
+    for (int n = 0; n < 8; ++n)
+      for (int m = 0; m < 8; ++m) Me[n][m] *= rho;
+    /* row-sum lumping: Me[j] += Me[j + i*24], i = 1..23 (:140-144).  For row
+     * j = 3n+a only columns i = 3m+a are non-zero; adding exact zeros is a
+     * no-op, so the sum runs over m = 0..7 in ascending order starting from
+     * the m = 0 column (i = a is the first non-zero column for row 3n+a:
+     * for a > 0 the row starts from the zero in column 0). */
+    for (int l = 0; l < 8; ++l) {
+      const int gIndex = s->connectivity[8 * e + l];
+      for (int a = 0; a < 3; ++a) {
+        double lumped = (a == 0) ? Me[l][0] : 0.0;
+        for (int m = (a == 0) ? 1 : 0; m < 8; ++m) lumped += Me[l][m];
+        s->mass[gIndex * NDIM + a] += lumped;
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* Materials                                                                 */
+/* ------------------------------------------------------------------------ */
+/* src/math/InverseF.cpp:38-66 (ndim == 3) */
+static void InverseF(const double *Fm, double detA, double *fInv) {
+  double A[3][3];
+  A[0][0] = Fm[0]; A[0][1] = Fm[1]; A[0][2] = Fm[2];
+  A[1][0] = Fm[3]; A[1][1] = Fm[4]; A[1][2] = Fm[5];
+  A[2][0] = Fm[6]; A[2][1] = Fm[7]; A[2][2] = Fm[8];
+  fInv[0] = (A[1][1] * A[2][2] - A[1][2] * A[2][1]) / detA;
+  fInv[1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) / detA;
+  fInv[2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) / detA;
+  fInv[3] = (A[1][2] * A[2][0] - A[1][0] * A[2][2]) / detA;
+  fInv[4] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) / detA;
+  fInv[5] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) / detA;
+  fInv[6] = (A[1][0] * A[2][1] - A[1][1] * A[2][0]) / detA;
+  fInv[7] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) / detA;
+  fInv[8] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) / detA;
+}
+
+static void storeVoigt(const double *S, double *pk2) {
+  pk2[0] = S[0]; pk2[1] = S[4]; pk2[2] = S[8];
+  pk2[3] = S[7]; pk2[4] = S[6]; pk2[5] = S[3];
+}
+
+/* src/materials/CompressibleNeoHookean.cpp:14-58 */
+static void CompressibleNeoHookean(const double *Fg, double J, const double *p,
+                                   double *pk2) {
+  double mu = p[1], lambda = p[2];
+  double Cmat[9], Cinv[9], Cdet;
+  mm3(1, 0, 1.0, Fg, Fg, Cmat);
+  inverse3x3Matrix(Cmat, Cinv, &Cdet);
+  double logJ = lambda * log(J);
+  pk2[0] = mu * (1.0 - Cinv[0]) + logJ * Cinv[0];
+  pk2[1] = mu * (1.0 - Cinv[4]) + logJ * Cinv[4];
+  pk2[2] = mu * (1.0 - Cinv[8]) + logJ * Cinv[8];
+  pk2[3] = -mu * Cinv[7] + logJ * Cinv[7];
+  pk2[4] = -mu * Cinv[6] + logJ * Cinv[6];
+  pk2[5] = -mu * Cinv[3] + logJ * Cinv[3];
+}
+
+/* src/materials/StVenantKirchhoff.cpp:25-48 */
+static void StVenantKirchhoff(const double *Fg, const double *p, double *pk2) {
+  double mu = p[1], lambda = p[2];
+  double E[9], S[9];
+  double half = 0.5;
+  mm3(1, 0, half, Fg, Fg, E);
+  E[0] -= half; E[4] -= half; E[8] -= half;
+  double traceE = E[0] + E[4] + E[8];
+  for (int i = 0; i < 9; ++i) S[i] = 2.0 * mu * E[i];
+  S[0] += lambda * traceE;
+  S[4] += lambda * traceE;
+  S[8] += lambda * traceE;
+  storeVoigt(S, pk2);
+}
+
+/* src/materials/LinearElastic.cpp:30-63 */
+static void LinearElastic(const double *Fg, double J, const double *p,
+                          double *pk2) {
+  double mu = p[1], lambda = p[2];
+  double eps[9], P[9], fInv[9], S[9];
+  const double trEps = Fg[0] + Fg[4] + Fg[8] - 3.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const int indexL = j + i * 3;
+      eps[indexL] = (Fg[indexL] + Fg[i + j * 3]);
+    }
+  eps[0] -= 2.0; eps[4] -= 2.0; eps[8] -= 2.0;
+  for (int i = 0; i < 9; ++i) P[i] = mu * eps[i];
+  P[0] += lambda * trEps;
+  P[4] += lambda * trEps;
+  P[8] += lambda * trEps;
+  InverseF(Fg, J, fInv);
+  mm3(0, 0, 1.0, fInv, P, S);
+  storeVoigt(S, pk2);
+}
+
+/* Shared front half of HGOIsotropic.cpp:44-90 and
+ * HGOIsotropicViscoelastic.cpp:54-100.  visco selects the rounding order of
+ * the prefactor (A.4 of SURVEY.md): material 4 scales by
+ * totalPrefactor = Jm23*(mu+fiber)/J, material 5 by Jm23*((mu+fiber)/J) one
+ * multiply at a time. */
+static void hgo_S(const double *Fg, double J, const double *p, int visco,
+                  double *fInv, double *S) {
+  const double mu = p[1], lambda = p[2], k1 = p[3], k2 = p[4];
+  const double kappa = 1.0 / 3.0;
+  const double K = lambda + 2.0 * mu / 3.0;
+  const double hydroDiag = 0.5 * K * (J * J - 1.0) / J;
+  double Bmat[9], STemp[9];
+  mm3(0, 1, 1.0, Fg, Fg, Bmat);
+  const double traceB = Bmat[0] + Bmat[4] + Bmat[8];
+  const double Jm23 = pow(J, -2.0 / 3.0);
+  const double I1 = Jm23 * traceB;
+  const double E_alpha = kappa * (I1 - 3.0);
+  double fiberPrefactor = 0.0;
+  if (E_alpha > 0.0) {
+    fiberPrefactor = 2.0 * k1 * exp(k2 * E_alpha * E_alpha) * E_alpha * kappa;
+  }
+  const double traceBby3 = traceB / 3.0;
+  Bmat[0] = Bmat[0] - traceBby3;
+  Bmat[4] = Bmat[4] - traceBby3;
+  Bmat[8] = Bmat[8] - traceBby3;
+  if (!visco) {
+    const double totalPrefactor = Jm23 * (mu + fiberPrefactor) / J;
+    for (int i = 0; i < 9; ++i) Bmat[i] = Bmat[i] * totalPrefactor;
+  } else {
+    const double totalPrefactor = (mu + fiberPrefactor) / J;
+    for (int i = 0; i < 9; ++i) Bmat[i] = Bmat[i] * Jm23 * totalPrefactor;
+  }
+  Bmat[0] += hydroDiag;
+  Bmat[4] += hydroDiag;
+  Bmat[8] += hydroDiag;
+  InverseF(Fg, J, fInv);
+  mm3(0, 0, 1.0, fInv, Bmat, STemp);
+  mm3(0, 1, J, STemp, fInv, S);
+}
+
+/* src/materials/HGOIsotropic.cpp:21-115 */
+static void HGOIsotropic(const double *Fg, double J, const double *p,
+                         double *pk2) {
+  double fInv[9], S[9];
+  hgo_S(Fg, J, p, 0, fInv, S);
+  storeVoigt(S, pk2);
+}
+
+/* src/materials/HGOIsotropicViscoelastic.cpp:27-168 */
+static void HGOIsotropicViscoelastic(const double *Fg, double J,
+                                     const double *p, double dt, double *Hn_1,
+                                     double *Hn_2, double *S0n, double *pk2) {
+  const double g1 = p[5], t1 = p[6], g2 = p[7], t2 = p[8];
+  double fInv[9], S[9], Cmat[9], Sic[9], Sdev[9];
+  hgo_S(Fg, J, p, 1, fInv, S);
+  mm3(1, 0, 1.0, Fg, Fg, Cmat);
+  double SddC = 0.0;
+  for (int i = 0; i < 9; ++i) SddC += Cmat[i] * S[i];
+  SddC = SddC / 3.0;
+  mm3(0, 1, SddC, fInv, fInv, Sic);
+  for (int i = 0; i < 9; ++i) Sdev[i] = S[i] - Sic[i];
+  const double rt1 = dt / t1;
+  const double rt2 = dt / t2;
+  const double c11 = exp(-rt1);
+  const double c12 = exp(-rt2);
+  const double c21 = g1 * (1 - c11) / rt1;
+  const double c22 = g2 * (1 - c12) / rt2;
+  for (int i = 0; i < 9; ++i) {
+    Hn_1[i] = c11 * Hn_1[i] + c21 * (Sdev[i] - S0n[i]);
+    Hn_2[i] = c12 * Hn_2[i] + c22 * (Sdev[i] - S0n[i]);
+    S[i] = S[i] + Hn_1[i] + Hn_2[i];
+  }
+  storeVoigt(S, pk2);
+  for (int i = 0; i < 9; ++i) S0n[i] = Sdev[i];
+}
+
+/* ------------------------------------------------------------------------ */
+/* GetForce                                                                  */
+/* ------------------------------------------------------------------------ */
+/* src/elements/ElementCalculations/StrainDisplacementMatrix.cpp:25-77 */
+static void StrainDisplacementMatrix(const double *dn, const double *Fg,
+                                     double *Bmat) {
+  double dnIdx = dn[0], dnIdy = dn[1], dnIdz = dn[2];
+  double F11 = Fg[0], F21 = Fg[1], F31 = Fg[2];
+  double F12 = Fg[3], F22 = Fg[4], F32 = Fg[5];
+  double F13 = Fg[6], F23 = Fg[7], F33 = Fg[8];
+  double B11 = dnIdx * F11, B12 = dnIdx * F21, B13 = dnIdx * F31;
+  double B21 = dnIdy * F12, B22 = dnIdy * F22, B23 = dnIdy * F32;
+  double B31 = dnIdz * F13, B32 = dnIdz * F23, B33 = dnIdz * F33;
+  double B41 = dnIdy * F13 + dnIdz * F12;
+  double B42 = dnIdy * F23 + dnIdz * F22;
+  double B43 = dnIdy * F33 + dnIdz * F32;
+  double B51 = dnIdx * F13 + dnIdz * F11;
+  double B52 = dnIdx * F23 + dnIdz * F21;
+  double B53 = dnIdx * F33 + dnIdz * F31;
+  double B61 = dnIdx * F12 + dnIdy * F11;
+  double B62 = dnIdx * F22 + dnIdy * F21;
+  double B63 = dnIdx * F32 + dnIdy * F31;
+  Bmat[0] = B11; Bmat[1] = B21; Bmat[2] = B31; Bmat[3] = B41; Bmat[4] = B51; Bmat[5] = B61;
+  Bmat[6] = B12; Bmat[7] = B22; Bmat[8] = B32; Bmat[9] = B42; Bmat[10] = B52; Bmat[11] = B62;
+  Bmat[12] = B13; Bmat[13] = B23; Bmat[14] = B33; Bmat[15] = B43; Bmat[16] = B53; Bmat[17] = B63;
+}
+
+/* src/fem/SolidMechanics/GetForce_3D.cpp:11-46 */
+int oracle_GetForce_local(oracle_state *s) {
+  const int nDOF = NDIM * s->nNodes;
+  memcpy(s->f_net, s->fe, nDOF * sizeof(double));
+  memset(s->fi, 0, nDOF * sizeof(double));
+  int bad = 0;
+  for (int e = 0; e < s->nElements; e++) {
+    double fintLocal[24];
+    memset(fintLocal, 0, sizeof(fintLocal));
+    const int *conn = &s->connectivity[8 * e];
+    const int pide = s->pid[e];
+    const double *props = &s->properties[ORACLE_MAXMATPARAMS * pide];
+    for (int gp = 0; gp < 8; gp++) {
+      double *Fg = &s->F[72 * e + 9 * gp];
+      const double *dshp = &s->dshp[192 * e + 24 * gp];
+      /* CalculateDeformationGradient.cpp:11-25 */
+      for (int i = 0; i < NDIM; i++)
+        for (int j = 0; j < NDIM; j++) {
+          double theSum = 0.0;
+          for (int k = 0; k < 8; k++) {
+            int node_a = conn[k];
+            theSum = theSum + (s->coordinates[NDIM * node_a + i] +
+                               s->displacements[NDIM * node_a + i]) *
+                                  dshp[k * NDIM + j];
+          }
+          Fg[NDIM * j + i] = theSum;
+        }
+      /* DeterminateF.cpp:43-56 */
+      {
+        double da = Fg[0], db = Fg[3], dc = Fg[6];
+        double dd = Fg[1], de = Fg[4], df = Fg[7];
+        double dg = Fg[2], dh = Fg[5], di = Fg[8];
+        s->detF[8 * e + gp] = da * (de * di - df * dh) -
+                              db * (dd * di - df * dg) +
+                              dc * (dd * dh - de * dg);
+      }
+      const double J = s->detF[8 * e + gp];
+      double *pk2 = &s->pk2[48 * e + 6 * gp];
+      /* StressUpdate.cpp:7-27 */
+      switch (s->materialID[pide]) {
+        case 0: break;
+        case 1: CompressibleNeoHookean(Fg, J, props, pk2); break;
+        case 2: StVenantKirchhoff(Fg, props, pk2); break;
+        case 3: LinearElastic(Fg, J, props, pk2); break;
+        case 4: HGOIsotropic(Fg, J, props, pk2); break;
+        case 5:
+          HGOIsotropicViscoelastic(Fg, J, props, s->dt,
+                                   &s->Hn_1[72 * e + 9 * gp],
+                                   &s->Hn_2[72 * e + 9 * gp],
+                                   &s->S0n[72 * e + 9 * gp], pk2);
+          break;
+        default: bad = 1; break;
+      }
+      /* InternalForceUpdate.cpp:4-28: B (6x24), fintGQ = B^T sigma via the
+       * naive dgemv ('T', m=6, n=24, alpha=1, beta=0), then the weighted add */
+      double B[144];
+      for (int k = 0; k < 8; ++k)
+        StrainDisplacementMatrix(&dshp[3 * k], Fg, &B[18 * k]);
+      const int wIndex = 8 * e + gp;
+      const double preFactor = s->gaussWeights[wIndex] * s->detJacobian[wIndex];
+      for (int k = 0; k < 24; ++k) {
+        double sum = 0.0;
+        for (int j = 0; j < 6; ++j) sum += B[j + 6 * k] * pk2[j];
+        double fintGQ = 1.0 * sum;
+        fintLocal[k] += preFactor * fintGQ;
+      }
+    }
+    /* scatter (:39-44) */
+    for (int k = 0; k < 8; ++k) {
+      int dIndex = conn[k];
+      for (int l = 0; l < NDIM; ++l)
+        s->fi[dIndex * NDIM + l] += fintLocal[k * NDIM + l];
+    }
+  }
+  return bad;
+}
+
+/* src/fem/SolidMechanics/GetForce_3D.cpp:49-51 */
+void oracle_GetForce_finish(oracle_state *s) {
+  const int nDOF = NDIM * s->nNodes;
+  for (int i = 0; i < nDOF; ++i) s->f_net[i] -= s->fi[i];
+}
+
+/* src/fem/SolidMechanics/CalculateAcclerations.cpp:7-11 */
+void oracle_CalculateAccelerations(oracle_state *s) {
+  const int nDOF = NDIM * s->nNodes;
+  for (int i = 0; i < nDOF; ++i)
+    if (!s->boundary[i]) s->accelerations[i] = s->f_net[i] / s->mass[i];
+}
+
+/* src/fem/SolidMechanics/GetForce_3D.cpp:54-102 and src/fem/Mass/Mass3D.cpp:
+ * 77-125 for ranks emulated in one process.  Every rank packs first (the
+ * reference posts all sends before any add), then every rank adds what its
+ * neighbours packed, neighbour by neighbour in its own list order. */
+void oracle_halo_sum(oracle_state **ranks, int nranks, int field) {
+  double **sendbuf = (double **)calloc(nranks, sizeof(double *));
+  for (int r = 0; r < nranks; ++r) {
+    oracle_state *s = ranks[r];
+    double *a = field == 0 ? s->fi : s->mass;
+    int total = s->sendProcessCount ? s->sendNeighbourCountCum[s->sendProcessCount] : 0;
+    sendbuf[r] = (double *)malloc(sizeof(double) * (NDIM * (size_t)total + 1));
+    for (int i = 0; i < total; ++i)
+      memcpy(&sendbuf[r][NDIM * i], &a[NDIM * s->sendNodeIndex[i]],
+             sizeof(double) * NDIM);
+  }
+  for (int r = 0; r < nranks; ++r) {
+    oracle_state *s = ranks[r];
+    double *a = field == 0 ? s->fi : s->mass;
+    for (int p = 0; p < s->sendProcessCount; ++p) {
+      int q = s->sendProcessID[p];
+      oracle_state *o = ranks[q];
+      /* find this rank in the neighbour's list */
+      int po = -1;
+      for (int k = 0; k < o->sendProcessCount; ++k)
+        if (o->sendProcessID[k] == r) po = k;
+      if (po < 0) abort();
+      int cnt = s->sendNeighbourCountCum[p + 1] - s->sendNeighbourCountCum[p];
+      if (cnt != o->sendNeighbourCountCum[po + 1] - o->sendNeighbourCountCum[po])
+        abort();
+      const double *recv = &sendbuf[q][NDIM * o->sendNeighbourCountCum[po]];
+      for (int i = 0; i < cnt; ++i) {
+        int nodeIndex = NDIM * s->sendNodeIndex[s->sendNeighbourCountCum[p] + i];
+        for (int l = 0; l < NDIM; ++l) a[nodeIndex + l] += recv[NDIM * i + l];
+      }
+    }
+  }
+  for (int r = 0; r < nranks; ++r) free(sendbuf[r]);
+  free(sendbuf);
+}
+
+/* src/fem/SolidMechanics/CheckEnergy.cpp:19-52 */
+void oracle_CheckEnergy_local(const oracle_state *s, double out[3]) {
+  double sum_Wint_n = 0.0, sum_Wext_n = 0.0, delta_d = 0.0, WKE = 0.0;
+  /* ownership scan (:21-33), done once instead of per node: O(shared) */
+  char *skip = (char *)calloc(s->nNodes > 0 ? s->nNodes : 1, 1);
+  for (int j = 0; j < s->sendProcessCount; ++j)
+    if (s->sendProcessID[j] < s->world_rank)
+      for (int k = s->sendNeighbourCountCum[j]; k < s->sendNeighbourCountCum[j + 1]; ++k)
+        skip[s->sendNodeIndex[k]] = 1;
+  for (int i = 0; i < s->nNodes; ++i) {
+    if (skip[i]) continue;
+    int index = i * NDIM;
+    for (int j = 0; j < NDIM; ++j) {
+      int indexJ = index + j;
+      delta_d = s->displacements[indexJ] - s->displacements_prev[indexJ];
+      WKE += s->mass[indexJ] * s->velocities[indexJ] * s->velocities[indexJ];
+      if (s->boundary[indexJ]) {
+        double reaction = s->fi_prev[indexJ] + s->fi[indexJ] +
+                          s->mass[indexJ] * (s->accelerations[indexJ] +
+                                             s->accelerations_prev[indexJ]);
+        sum_Wext_n += delta_d * reaction;
+      }
+      sum_Wint_n += delta_d * (s->fi_prev[indexJ] + s->fi[indexJ]);
+      sum_Wext_n += delta_d * (s->fe_prev[indexJ] + s->fe[indexJ]);
+    }
+  }
+  free(skip);
+  WKE *= 0.5;
+  sum_Wint_n *= 0.5;
+  sum_Wext_n *= 0.5;
+  out[0] = WKE;
+  out[1] = sum_Wint_n;
+  out[2] = sum_Wext_n;
+}
+
+/* examples/Benchmarking-Parallel/Benchmarking-Parallel.cpp:184-244 as a
+ * descriptor (see header) */
+static void applyBC(oracle_state *s, const int *bc_kind, const double *bc_rate) {
+  const int nDOF = NDIM * s->nNodes;
+  for (int i = 0; i < nDOF; ++i) {
+    int k = bc_kind[i];
+    if (k > 0) {
+      s->boundary[i] = 1;
+      s->displacements[i] = s->Time * bc_rate[k];
+      s->velocities[i] = bc_rate[k];
+      s->accelerations[i] = 0.0;
+    }
+  }
+}
+
+static double stable_dt_all(oracle_state **ranks, int nranks) {
+  double dtMin = huge_dt;
+  for (int r = 0; r < nranks; ++r) {
+    double d = oracle_StableTimeStep_local(ranks[r]);
+    if (d < dtMin) dtMin = d; /* MPI_Allreduce(MIN), StableTimeStep.cpp:33 */
+  }
+  return dtMin;
+}
+
+static int get_force_all(oracle_state **ranks, int nranks) {
+  int bad = 0;
+  for (int r = 0; r < nranks; ++r) bad |= oracle_GetForce_local(ranks[r]);
+  if (nranks > 1) oracle_halo_sum(ranks, nranks, 0);
+  for (int r = 0; r < nranks; ++r) oracle_GetForce_finish(ranks[r]);
+  return bad;
+}
+
+/* examples/Benchmarking-Parallel/Benchmarking-Parallel.cpp:83-171 */
+int oracle_run_explicit(oracle_state **ranks, int nranks, int *const *bc_kind,
+                        const double *bc_rate, double tMax, int maxSteps,
+                        double ExplicitTimeStepReduction,
+                        double FailureTimeStep, int first_call,
+                        double *dt_hist, double *energy_hist) {
+  double Time = ranks[0]->Time, dt = ranks[0]->dt;
+  if (first_call) {
+    for (int r = 0; r < nranks; ++r) applyBC(ranks[r], bc_kind[r], bc_rate);
+    double dtMin = stable_dt_all(ranks, nranks);
+    if (dtMin < FailureTimeStep) return -19;
+    dt = ExplicitTimeStepReduction * dtMin;
+    for (int r = 0; r < nranks; ++r) ranks[r]->dt = dt;
+    if (get_force_all(ranks, nranks)) return -1;
+    for (int r = 0; r < nranks; ++r) oracle_CalculateAccelerations(ranks[r]);
+  }
+  int steps = 0;
+  while (Time < tMax && steps < maxSteps) {
+    double t_n = Time;
+    double t_np1 = Time + dt;
+    Time = t_np1;
+    double dt_nphalf = dt;
+    double t_nphalf = 0.5 * (t_np1 + t_n);
+    if (dt_hist) dt_hist[steps] = dt;
+    for (int r = 0; r < nranks; ++r) {
+      oracle_state *s = ranks[r];
+      const int nDOF = NDIM * s->nNodes;
+      s->Time = Time;
+      for (int i = 0; i < nDOF; i++) {
+        if (s->boundary[i]) {
+          s->velocities_half[i] = s->velocities[i];
+        } else {
+          s->velocities_half[i] =
+              s->velocities[i] + (t_nphalf - t_n) * s->accelerations[i];
+        }
+      }
+      memcpy(s->displacements_prev, s->displacements, nDOF * sizeof(double));
+      memcpy(s->accelerations_prev, s->accelerations, nDOF * sizeof(double));
+      memcpy(s->fi_prev, s->fi, nDOF * sizeof(double));
+      memcpy(s->fe_prev, s->fe, nDOF * sizeof(double));
+      for (int i = 0; i < nDOF; i++)
+        if (!s->boundary[i])
+          s->displacements[i] = s->displacements[i] + dt_nphalf * s->velocities_half[i];
+      applyBC(s, bc_kind[r], bc_rate);
+    }
+    if (get_force_all(ranks, nranks)) return -1;
+    for (int r = 0; r < nranks; ++r) {
+      oracle_state *s = ranks[r];
+      const int nDOF = NDIM * s->nNodes;
+      oracle_CalculateAccelerations(s);
+      for (int i = 0; i < nDOF; i++)
+        if (!s->boundary[i])
+          s->velocities[i] =
+              s->velocities_half[i] + (t_np1 - t_nphalf) * s->accelerations[i];
+    }
+    /* CheckEnergy.cpp:54-64: three reductions to rank 0, running sums */
+    {
+      double WKE_Total = 0.0, Wint_n_total = 0.0, Wext_n_total = 0.0;
+      for (int r = 0; r < nranks; ++r) {
+        double part[3];
+        oracle_CheckEnergy_local(ranks[r], part);
+        WKE_Total += part[0];
+        Wint_n_total += part[1];
+        Wext_n_total += part[2];
+      }
+      ranks[0]->Wint_n += Wint_n_total;
+      ranks[0]->Wext_n += Wext_n_total;
+      if (energy_hist) {
+        energy_hist[4 * steps + 0] = ranks[0]->Wint_n;
+        energy_hist[4 * steps + 1] = ranks[0]->Wext_n;
+        energy_hist[4 * steps + 2] = WKE_Total;
+        energy_hist[4 * steps + 3] =
+            fabs(WKE_Total + ranks[0]->Wint_n - ranks[0]->Wext_n);
+      }
+    }
+    steps++;
+    double dtMin = stable_dt_all(ranks, nranks);
+    if (dtMin < FailureTimeStep) {
+      for (int r = 0; r < nranks; ++r) { ranks[r]->Time = Time; ranks[r]->dt = dt; }
+      return -19;
+    }
+    dt = ExplicitTimeStepReduction * dtMin;
+    for (int r = 0; r < nranks; ++r) ranks[r]->dt = dt;
+  }
+  for (int r = 0; r < nranks; ++r) { ranks[r]->Time = Time; ranks[r]->dt = dt; }
+  return steps;
+}
+
+/* src/elements/ElementCalculations/CalculateStrain.cpp:77-97: dgemm with
+ * alpha = 0.5/8, beta = 1 accumulating into E, then subtract 0.5 on the
+ * diagonal */
+void oracle_CalculateStrain(const oracle_state *s, double *Eavg) {
+  for (int elm = 0; elm < s->nElements; ++elm) {
+    double *E = &Eavg[9 * elm];
+    for (int i = 0; i < 9; ++i) E[i] = 0.0;
+    double preFactor = 0.5 / ((double)8);
+    for (int gp = 0; gp < 8; ++gp) {
+      const double *Fg = &s->F[72 * elm + 9 * gp];
+      for (int j = 0; j < 3; ++j)
+        for (int i = 0; i < 3; ++i) {
+          double sum = 0.0;
+          for (int l = 0; l < 3; ++l) sum += Fg[l + 3 * i] * Fg[l + 3 * j];
+          E[i + 3 * j] = 1.0 * E[i + 3 * j] + preFactor * sum;
+        }
+    }
+    E[0] -= 0.5;
+    E[4] -= 0.5;
+    E[8] -= 0.5;
+  }
+}

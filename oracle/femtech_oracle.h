@@ -1,0 +1,113 @@
+/*
+ * femtech_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (plain C99) of the FemTech explicit-dynamics hot path, used
+ * as the parity checker for the CUDA path.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this library.
+ * The product (femtech_b200/) never links, imports or calls it.
+ *
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks this restatement
+ * bit-for-bit against vectors dumped from the reference's own sources compiled
+ * in this container (oracle/ref/build_ref.sh -> oracle/_ref/ref_dump, recipe
+ * and generating script committed; vectors under tests/golden/), and against
+ * the reference's only known-answer test (examples/ex9 vs abaqus.rpt, 5 %).
+ * The BLAS under the reference is external and unversioned (CMakeLists.txt:140);
+ * "reference result" is defined with the naive left-to-right shim in
+ * oracle/ref/blas_shim.c, and this file uses the same summation order.
+ *
+ * All file:line citations are relative to /root/reference.
+ */
+#ifndef FEMTECH_ORACLE_H
+#define FEMTECH_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORACLE_MAXMATPARAMS 9 /* include/GlobalVariables.h:6 */
+
+/* One rank's view of the model: exactly the global arrays of
+ * include/GlobalVariables.h:18-127 that the hot path touches.  All arrays are
+ * caller-owned (numpy in the tests). */
+typedef struct oracle_state {
+  int nNodes, nElements, nPID;
+  /* mesh (GlobalVariables.h:32-33,47-49) */
+  const double *coordinates; /* [3*nNodes] AoS xyz */
+  const int *connectivity;   /* [8*nElements] local node ids, C3D8 order */
+  const int *pid;            /* [nElements] */
+  const int *materialID;     /* [nPID] */
+  const double *properties;  /* [9*nPID] rho mu lambda k1 k2 g1 t1 g2 t2 */
+  /* per-Gauss-point tables (ShapeFunctions.cpp:181-204) */
+  double *shp;          /* [64*nElements] */
+  double *dshp;         /* [192*nElements] dN/dX, reference config */
+  double *detJacobian;  /* [8*nElements] */
+  double *gaussWeights; /* [8*nElements] */
+  double *F;            /* [72*nElements] col-major 3x3 per GP */
+  double *detF;         /* [8*nElements] */
+  double *pk2;          /* [48*nElements] Voigt 11,22,33,23,13,12 */
+  double *Hn_1, *Hn_2, *S0n; /* [72*nElements] or NULL (material 5 only) */
+  /* nodal state (AllocateArrays.cpp:29-153) */
+  double *displacements, *velocities, *velocities_half, *accelerations;
+  double *mass, *fe, *fi, *f_net;
+  double *displacements_prev, *accelerations_prev, *fi_prev, *fe_prev;
+  int *boundary;
+  /* communication pattern (PartitionMesh.cpp:566-1128) */
+  int world_rank;
+  int sendProcessCount;
+  const int *sendProcessID;
+  const int *sendNeighbourCountCum;
+  const int *sendNodeIndex;
+  /* driver globals (Benchmarking-Parallel.cpp:9-17) */
+  double Time, dt;
+  /* CheckEnergy function-statics (CheckEnergy.cpp:4-5) */
+  double Wint_n, Wext_n;
+} oracle_state;
+
+/* ShapeFunctions.cpp:32-255 + ShapeFunction_C3D8.cpp:4-128 (hex8 only). Also
+ * resets F<-I, detF<-1, pk2<-0 and zeroes the history arrays. */
+void oracle_ShapeFunctions(oracle_state *s);
+/* Mass3D.cpp:127-157 without the halo (the caller sums shared nodes with
+ * oracle_halo_sum). mass must be zeroed by the caller. */
+void oracle_AssembleLumpedMass_local(oracle_state *s);
+/* GetForce_3D.cpp:11-46: f_net<-fe, fi<-0, element/GP loop, scatter. Returns
+ * 0, or 1 when an element carries an unknown material (StressUpdate.cpp:24). */
+int oracle_GetForce_local(oracle_state *s);
+/* GetForce_3D.cpp:49-51 */
+void oracle_GetForce_finish(oracle_state *s);
+/* CalculateAcclerations.cpp:4-13 */
+void oracle_CalculateAccelerations(oracle_state *s);
+/* StableTimeStep.cpp:11-30 (no Allreduce, no abort) */
+double oracle_StableTimeStep_local(const oracle_state *s);
+/* CheckEnergy.cpp:19-52: partial sums out[0..2] = WKE, Wint, Wext (already
+ * multiplied by 0.5) of the nodes this rank owns. */
+void oracle_CheckEnergy_local(const oracle_state *s, double out[3]);
+/* GetForce_3D.cpp:54-102 / Mass3D.cpp:77-125 for P ranks emulated in one
+ * process: field 0 = fi, 1 = mass. */
+void oracle_halo_sum(oracle_state **ranks, int nranks, int field);
+
+/* The explicit loop of Benchmarking-Parallel.cpp:83-171 (== ex9.cpp) for P
+ * emulated ranks.  Boundary conditions are a descriptor instead of the
+ * driver's coordinate scan (:184-244): bc_kind[r][dof] = 0 free, k>0 -> dof is
+ * prescribed with u = Time*bc_rate[k], v = bc_rate[k], a = 0, boundary = 1.
+ * Runs while Time < tMax and at most maxSteps iterations.  Step 0 (BC, dt,
+ * GetForce, accelerations) is done when s->Time == 0 and first_call != 0.
+ * Per-step records (optional, may be NULL): dt_hist[k] = dt used by step k,
+ * energy_hist[4k..] = Wint, Wext, WKE, total (rank-0 values).
+ * Returns the number of loop iterations executed, or -19 when dt drops below
+ * FailureTimeStep (StableTimeStep.cpp:35-38), -1 on an unknown material. */
+int oracle_run_explicit(oracle_state **ranks, int nranks, int *const *bc_kind,
+                        const double *bc_rate, double tMax, int maxSteps,
+                        double ExplicitTimeStepReduction,
+                        double FailureTimeStep, int first_call,
+                        double *dt_hist, double *energy_hist);
+
+/* Element-level helpers exported for unit tests */
+double oracle_volumeHexahedron(const double *c24);
+double oracle_areaHexahedronFace(const double *c24, const int *index4);
+double oracle_CalculateTimeStep(const oracle_state *s, int e);
+void oracle_CalculateStrain(const oracle_state *s, double *Eavg /*[9*nE]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the REFERENCE ITSELF.  TEST INFRASTRUCTURE.
+
+Runs oracle/_ref/ref_dump_exact (the unmodified reference sources compiled by
+oracle/ref/build_ref.sh, driven by oracle/ref/ref_dump.cpp) on the shipped
+meshes and on small synthetic ones, single- and multi-rank (through the ftmpi
+shim), and stores compact fixtures.  Must be run in the build container
+(needs /root/reference); the fixtures travel, the reference does not.
+
+    python oracle/make_golden.py            # regenerate everything
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from femtech_b200 import mesh  # noqa: E402
+from oracle import pyoracle  # noqa: E402
+
+REF = os.environ.get("FEMTECH_REFERENCE", "/root/reference")
+BIN = os.path.join(ROOT, "oracle", "_ref")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+BRAIN = [1000.0, 2673.23, 2.189982178466e8, 25459.0, 0.0, 0.6521, 0.0129, 0.0067, 0.0747]  # examples/ex5/materials.dat:2
+SOFT = [1040.0, 100.0, 100.0, 0, 0, 0, 0, 0, 0]  # examples/Benchmarking-Parallel/materials.dat:1
+
+
+def run_ref(meshfile, materialID, properties, nranks, maxSteps, tMax, dMax, cubeL=mesh.CUBE_L):
+    work = tempfile.mkdtemp(prefix="ftgold_")
+    try:
+        mesh.write_materials_dat(os.path.join(work, "materials.dat"), materialID, properties)
+        cmd = [os.path.join(BIN, "ref_dump_exact"), meshfile, os.path.join(work, "out"), str(maxSteps),
+               repr(tMax), repr(dMax), repr(cubeL)]
+        if nranks > 1:
+            cmd = [os.path.join(BIN, "ftmpirun"), "-np", str(nranks)] + cmd
+        out = subprocess.run(cmd, cwd=work, check=True, capture_output=True, text=True).stdout
+        dumps = [pyoracle.read_ref_dump(os.path.join(work, "out.rank%d.bin" % r)) for r in range(nranks)]
+        energy = None
+        for fn in os.listdir(work):
+            if fn.startswith("energy_"):
+                rows = [l.split() for l in open(os.path.join(work, fn)) if not l.startswith("#")]
+                energy = np.array(rows, dtype=np.float64) if rows else np.zeros((0, 5))
+        return dumps, energy, out
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+MESH_KEYS = ["coordinates", "connectivity", "pid", "materialID", "properties"]
+MAP_KEYS = ["global_eid", "globalNodeID", "sendProcessID", "sendNeighbourCountCum", "sendNodeIndex"]
+STATE_KEYS = ["mass", "boundary0", "dt0", "fi0", "accelerations0", "steps", "Time", "dt", "dt_hist", "displacements",
+              "velocities", "accelerations", "boundary", "fi", "f_net"]
+GP_KEYS = ["detJacobian", "F", "detF", "pk2", "pk2_0", "Eavg", "Hn_1", "Hn_2", "S0n"]
+
+
+def save(name, dumps, energy, params, keys):
+    out = {"nranks": np.int32(len(dumps))}
+    for k, v in params.items():
+        out["param_" + k] = np.asarray(v)
+    if energy is not None:
+        out["energy_file"] = energy
+    for r, d in enumerate(dumps):
+        for k in keys:
+            out["r%d_%s" % (r, k)] = d[k]
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s (%.1f kB)" % (path, os.path.getsize(path) / 1e3))
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="ftmesh_")
+    ex = os.path.join(REF, "examples")
+
+    # (A) ex9: the reference's only known-answer test (.travis.yml:113-115)
+    d, en, _ = run_ref(os.path.join(ex, "ex9", "1-elt-cube.k"), [1], SOFT, 1, 10 ** 9, 1.0, 0.007)
+    save("ex9_1elt", d, en[-1:], dict(tMax=1.0, dMax=0.007), MESH_KEYS + STATE_KEYS + GP_KEYS)
+
+    # (B) shipped benchmark mesh, full run, 1/2/4/8 ranks (BASELINE config 1)
+    m10 = os.path.join(ex, "Benchmarking-Parallel", "10elements.inp")
+    for P in (1, 2, 4, 8):
+        d, en, _ = run_ref(m10, [1], SOFT, P, 10 ** 9, 0.1, 0.007)
+        keys = MESH_KEYS + MAP_KEYS + STATE_KEYS + (["pk2", "Eavg"] if P == 1 else [])
+        save("bench10_p%d" % P, d, en[-1:], dict(tMax=0.1, dMax=0.007), keys)
+
+    # (C) small jittered cubes, every material, 200 steps
+    X, conn, pid = mesh.cube_mesh(4, jitter=0.1)
+    f4 = os.path.join(tmp, "cube4j.inp")
+    mesh.write_abaqus_inp(f4, X, conn, pid)
+    HGO = list(BRAIN[:4]) + [10.0, 0, 0, 0, 0]
+    cases = {
+        "cube4j_m1": (1, SOFT, 0.1), "cube4j_m2": (2, SOFT, 0.1), "cube4j_m3": (3, SOFT, 0.1),
+        "cube4j_m4": (4, HGO, 0.004), "cube4j_m5": (5, BRAIN, 0.004),
+    }
+    for name, (mid, props, tMax) in cases.items():
+        d, en, _ = run_ref(f4, [mid], props, 1, 200, tMax, 0.007)
+        save(name, d, en[-1:], dict(tMax=tMax, dMax=0.007), MESH_KEYS + STATE_KEYS + GP_KEYS)
+
+    # (D) mixed materials in three z-slabs (parts 0,1,2 = mats 1,4,5), 1 and 3 ranks
+    X, conn, pid = mesh.cube_mesh(6, jitter=0.05, nparts_z=3)
+    f6 = os.path.join(tmp, "cube6mix.inp")
+    mesh.write_abaqus_inp(f6, X, conn, pid)
+    STIFF1 = [1040.0, 2.0e5, 4.0e5, 0, 0, 0, 0, 0, 0]
+    mixprops = STIFF1 + HGO + BRAIN
+    for P in (1, 3):
+        d, en, _ = run_ref(f6, [1, 4, 5], mixprops, P, 150, 0.004, 0.007)
+        save("cube6mix_p%d" % P, d, en[-1:], dict(tMax=0.004, dMax=0.007),
+             MESH_KEYS + MAP_KEYS + STATE_KEYS + (GP_KEYS if P == 1 else []))
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,218 @@
+"""ctypes binding of the CPU oracle (oracle/femtech_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+(femtech_b200) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class OracleState(C.Structure):
+    """Mirror of `oracle_state` in femtech_oracle.h (same field order)."""
+    _fields_ = [
+        ("nNodes", C.c_int), ("nElements", C.c_int), ("nPID", C.c_int),
+        ("coordinates", _dp), ("connectivity", _ip), ("pid", _ip),
+        ("materialID", _ip), ("properties", _dp),
+        ("shp", _dp), ("dshp", _dp), ("detJacobian", _dp), ("gaussWeights", _dp),
+        ("F", _dp), ("detF", _dp), ("pk2", _dp),
+        ("Hn_1", _dp), ("Hn_2", _dp), ("S0n", _dp),
+        ("displacements", _dp), ("velocities", _dp), ("velocities_half", _dp),
+        ("accelerations", _dp), ("mass", _dp), ("fe", _dp), ("fi", _dp), ("f_net", _dp),
+        ("displacements_prev", _dp), ("accelerations_prev", _dp), ("fi_prev", _dp), ("fe_prev", _dp),
+        ("boundary", _ip),
+        ("world_rank", C.c_int), ("sendProcessCount", C.c_int),
+        ("sendProcessID", _ip), ("sendNeighbourCountCum", _ip), ("sendNodeIndex", _ip),
+        ("Time", C.c_double), ("dt", C.c_double), ("Wint_n", C.c_double), ("Wext_n", C.c_double),
+    ]
+
+
+def build(fast=False):
+    """Compile the oracle shared library if missing/stale; return its path."""
+    name = "libfemtech_oracle_fast.so" if fast else "libfemtech_oracle.so"
+    so = os.path.join(HERE, name)
+    src = os.path.join(HERE, "femtech_oracle.c")
+    hdr = os.path.join(HERE, "femtech_oracle.h")
+    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["make", "-C", HERE, name], stdout=subprocess.DEVNULL)
+    return so
+
+
+_libs = {}
+
+
+def lib(fast=False):
+    if fast not in _libs:
+        L = C.CDLL(build(fast))
+        sp = C.POINTER(OracleState)
+        L.oracle_ShapeFunctions.argtypes = [sp]
+        L.oracle_AssembleLumpedMass_local.argtypes = [sp]
+        L.oracle_GetForce_local.argtypes = [sp]
+        L.oracle_GetForce_local.restype = C.c_int
+        L.oracle_GetForce_finish.argtypes = [sp]
+        L.oracle_CalculateAccelerations.argtypes = [sp]
+        L.oracle_StableTimeStep_local.argtypes = [sp]
+        L.oracle_StableTimeStep_local.restype = C.c_double
+        L.oracle_CheckEnergy_local.argtypes = [sp, _dp]
+        L.oracle_halo_sum.argtypes = [C.POINTER(sp), C.c_int, C.c_int]
+        L.oracle_run_explicit.argtypes = [C.POINTER(sp), C.c_int, C.POINTER(_ip), _dp, C.c_double, C.c_int,
+                                          C.c_double, C.c_double, C.c_int, _dp, _dp]
+        L.oracle_run_explicit.restype = C.c_int
+        L.oracle_volumeHexahedron.argtypes = [_dp]
+        L.oracle_volumeHexahedron.restype = C.c_double
+        L.oracle_areaHexahedronFace.argtypes = [_dp, _ip]
+        L.oracle_areaHexahedronFace.restype = C.c_double
+        L.oracle_CalculateTimeStep.argtypes = [sp, C.c_int]
+        L.oracle_CalculateTimeStep.restype = C.c_double
+        L.oracle_CalculateStrain.argtypes = [sp, _dp]
+        _libs[fast] = L
+    return _libs[fast]
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+class OracleModel:
+    """One rank's model: owns the numpy arrays the C struct points at."""
+
+    NODAL = ["displacements", "velocities", "velocities_half", "accelerations", "mass", "fe", "fi", "f_net",
+             "displacements_prev", "accelerations_prev", "fi_prev", "fe_prev"]
+
+    def __init__(self, coordinates, connectivity, pid, materialID, properties, comm=None, world_rank=0, fast=False):
+        self.L = lib(fast)
+        self.coordinates = np.ascontiguousarray(coordinates, dtype=np.float64).reshape(-1)
+        self.connectivity = np.ascontiguousarray(connectivity, dtype=np.int32).reshape(-1)
+        self.pid = np.ascontiguousarray(pid, dtype=np.int32)
+        self.materialID = np.ascontiguousarray(materialID, dtype=np.int32)
+        self.properties = np.ascontiguousarray(properties, dtype=np.float64).reshape(-1)
+        nN = self.coordinates.size // 3
+        nE = self.connectivity.size // 8
+        self.nNodes, self.nElements = nN, nE
+        self.shp = np.zeros(64 * nE)
+        self.dshp = np.zeros(192 * nE)
+        self.detJacobian = np.zeros(8 * nE)
+        self.gaussWeights = np.zeros(8 * nE)
+        self.F = np.zeros(72 * nE)
+        self.detF = np.zeros(8 * nE)
+        self.pk2 = np.zeros(48 * nE)
+        visco = bool(np.any(self.materialID == 5))
+        self.Hn_1 = np.zeros(72 * nE) if visco else None
+        self.Hn_2 = np.zeros(72 * nE) if visco else None
+        self.S0n = np.zeros(72 * nE) if visco else None
+        for n in self.NODAL:
+            setattr(self, n, np.zeros(3 * nN))
+        self.boundary = np.zeros(3 * nN, dtype=np.int32)
+        if comm is None:
+            comm = dict(sendProcessID=np.zeros(0, np.int32), sendNeighbourCountCum=np.zeros(1, np.int32),
+                        sendNodeIndex=np.zeros(0, np.int32))
+        self.sendProcessID = np.ascontiguousarray(comm["sendProcessID"], dtype=np.int32)
+        self.sendNeighbourCountCum = np.ascontiguousarray(comm["sendNeighbourCountCum"], dtype=np.int32)
+        self.sendNodeIndex = np.ascontiguousarray(comm["sendNodeIndex"], dtype=np.int32)
+        s = OracleState()
+        s.nNodes, s.nElements, s.nPID = nN, nE, self.materialID.size
+        s.coordinates, s.connectivity, s.pid = _d(self.coordinates), _i(self.connectivity), _i(self.pid)
+        s.materialID, s.properties = _i(self.materialID), _d(self.properties)
+        for n in ["shp", "dshp", "detJacobian", "gaussWeights", "F", "detF", "pk2"] + self.NODAL:
+            setattr(s, n, _d(getattr(self, n)))
+        if visco:
+            s.Hn_1, s.Hn_2, s.S0n = _d(self.Hn_1), _d(self.Hn_2), _d(self.S0n)
+        s.boundary = _i(self.boundary)
+        s.world_rank = world_rank
+        s.sendProcessCount = self.sendProcessID.size
+        s.sendProcessID, s.sendNeighbourCountCum = _i(self.sendProcessID), _i(self.sendNeighbourCountCum)
+        s.sendNodeIndex = _i(self.sendNodeIndex)
+        s.Time = s.dt = s.Wint_n = s.Wext_n = 0.0
+        self.s = s
+
+    # --- reference-named entry points -------------------------------------
+    def ShapeFunctions(self):
+        self.L.oracle_ShapeFunctions(C.byref(self.s))
+
+    def AssembleLumpedMass(self):
+        self.mass[:] = 0.0
+        self.L.oracle_AssembleLumpedMass_local(C.byref(self.s))
+
+    def GetForce(self):
+        bad = self.L.oracle_GetForce_local(C.byref(self.s))
+        self.L.oracle_GetForce_finish(C.byref(self.s))
+        return bad
+
+    def CalculateAccelerations(self):
+        self.L.oracle_CalculateAccelerations(C.byref(self.s))
+
+    def StableTimeStep(self):
+        return self.L.oracle_StableTimeStep_local(C.byref(self.s))
+
+    def CheckEnergy(self):
+        out = np.zeros(3)
+        self.L.oracle_CheckEnergy_local(C.byref(self.s), _d(out))
+        return out
+
+    def CalculateStrain(self):
+        E = np.zeros(9 * self.nElements)
+        self.L.oracle_CalculateStrain(C.byref(self.s), _d(E))
+        return E
+
+    @property
+    def Time(self):
+        return self.s.Time
+
+    @property
+    def dt(self):
+        return self.s.dt
+
+
+def halo_sum(models, field):
+    """field: 'fi' or 'mass' (GetForce_3D.cpp:54-102 / Mass3D.cpp:77-125)."""
+    sp = C.POINTER(OracleState)
+    arr = (sp * len(models))(*[C.pointer(m.s) for m in models])
+    models[0].L.oracle_halo_sum(arr, len(models), 0 if field == "fi" else 1)
+
+
+def run_explicit(models, bc_kinds, bc_rate, tMax, maxSteps, reduction=0.8, failure_dt=1e-11, first_call=True,
+                 record=True):
+    """Benchmarking-Parallel.cpp:83-171 on P emulated ranks.  Returns
+    (steps_or_negative_code, dt_hist, energy_hist[steps,4])."""
+    P = len(models)
+    sp = C.POINTER(OracleState)
+    arr = (sp * P)(*[C.pointer(m.s) for m in models])
+    kinds = [np.ascontiguousarray(k, dtype=np.int32) for k in bc_kinds]
+    karr = (_ip * P)(*[_i(k) for k in kinds])
+    rate = np.ascontiguousarray(bc_rate, dtype=np.float64)
+    dth = np.zeros(max(maxSteps, 1)) if record else None
+    eh = np.zeros(4 * max(maxSteps, 1)) if record else None
+    n = models[0].L.oracle_run_explicit(arr, P, karr, _d(rate), tMax, maxSteps, reduction, failure_dt,
+                                        1 if first_call else 0, _d(dth) if record else None,
+                                        _d(eh) if record else None)
+    if record and n >= 0:
+        return n, dth[:n].copy(), eh[:4 * n].reshape(n, 4).copy()
+    return n, None, None
+
+
+def read_ref_dump(path):
+    """Parse a ref_dump record file (oracle/ref/ref_dump.cpp) into a dict."""
+    out = {}
+    with open(path, "rb") as f:
+        data = f.read()
+    off = 0
+    while off < len(data):
+        name = data[off:off + 32].split(b"\0")[0].decode()
+        dtype = data[off + 32:off + 40].split(b"\0")[0].decode()
+        count = int(np.frombuffer(data, dtype=np.int64, count=1, offset=off + 40)[0])
+        off += 48
+        dt = np.dtype("<" + dtype)
+        out[name] = np.frombuffer(data, dtype=dt, count=count, offset=off).copy()
+        off += count * dt.itemsize
+    return out

@@ -1,0 +1,233 @@
+/*
+ * ref_dump.cpp -- oracle harness driver.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Links against the UNMODIFIED reference sources (compiled where they lie under
+ * /root/reference by build_ref.sh) and drives them through the reference's own
+ * public API (include/FemTech.h) in the call order of the shipped explicit
+ * drivers (examples/Benchmarking-Parallel/Benchmarking-Parallel.cpp:19-182 and
+ * examples/ex9/ex9.cpp, whose time loop lives in main()).  It adds what those
+ * drivers lack: a step limit, full-precision binary dumps of every array on
+ * the hot path, and a per-step dt record.  The time loop and the boundary
+ * condition below restate the driver (:83-171, :184-244); all numerics are the
+ * reference library's.
+ *
+ * usage: ref_dump <mesh.inp|.k> <out-prefix> <maxSteps> <tMax> <dMax> [cubeL]
+ *        (materials.dat is read from the current directory, ReadMaterials.cpp:11)
+ * output: <out-prefix>.rank<r>.bin  -- records: name[32] dtype[8] count(int64) payload
+ */
+#include "FemTech.h"
+
+#include <stdint.h>
+#include <sys/time.h>
+#include <vector>
+
+double Time, dt;
+int nSteps;
+double ExplicitTimeStepReduction = 0.8;
+double FailureTimeStep = 1e-11;
+int nPlotSteps = 50;
+bool ImplicitStatic = false;
+bool ImplicitDynamic = false;
+bool ExplicitDynamic = true;
+
+static double g_cubeL = 0.005;
+static FILE *g_out = NULL;
+
+static void put(const char *name, const char *dtype, const void *p, int64_t count, size_t esz) {
+  char nb[32] = {0}, tb[8] = {0};
+  strncpy(nb, name, 31);
+  strncpy(tb, dtype, 7);
+  fwrite(nb, 1, 32, g_out);
+  fwrite(tb, 1, 8, g_out);
+  fwrite(&count, 8, 1, g_out);
+  if (count > 0) fwrite(p, esz, (size_t)count, g_out);
+}
+static void putd(const char *name, const double *p, int64_t n) { put(name, "f8", p, p ? n : 0, 8); }
+static void puti(const char *name, const int *p, int64_t n) { put(name, "i4", p, p ? n : 0, 4); }
+static void puts1(const char *name, double v) { putd(name, &v, 1); }
+static void puti1(const char *name, int v) { puti(name, &v, 1); }
+
+/* Benchmarking-Parallel.cpp:184-244, cube side parametrised */
+static void ApplyBoundaryConditions(double dMax, double tMax) {
+  double tol = 1e-5;
+  double AppliedDisp = Time * (dMax / tMax);
+  int index;
+  for (int i = 0; i < nNodes; i++) {
+    index = ndim * i + 0;
+    if (fabs(coordinates[index] - 0.0) < tol) {
+      boundary[index] = 1;
+      displacements[index] = 0.0;
+      velocities[index] = 0.0;
+      accelerations[index] = 0.0;
+    }
+    index = ndim * i + 1;
+    if (fabs(coordinates[index] - 0.0) < tol) {
+      boundary[index] = 1;
+      displacements[index] = 0.0;
+      velocities[index] = 0.0;
+      accelerations[index] = 0.0;
+    }
+    index = ndim * i + 2;
+    if (fabs(coordinates[index] - 0.0) < tol) {
+      boundary[index] = 1;
+      displacements[index] = 0.0;
+      velocities[index] = 0.0;
+      accelerations[index] = 0.0;
+    }
+    index = ndim * i + 1;
+    if (fabs(coordinates[index] - g_cubeL) < tol) {
+      boundary[index] = 1;
+      displacements[index] = AppliedDisp;
+      velocities[index] = dMax / tMax;
+      accelerations[index] = 0.0;
+    }
+  }
+}
+
+static double now() {
+  struct timeval tv;
+  gettimeofday(&tv, 0);
+  return tv.tv_sec + 1e-6 * tv.tv_usec;
+}
+
+int main(int argc, char **argv) {
+  if (argc < 6) {
+    fprintf(stderr, "usage: %s mesh out-prefix maxSteps tMax dMax [cubeL]\n", argv[0]);
+    return 2;
+  }
+  const char *outPrefix = argv[2];
+  const int maxSteps = atoi(argv[3]);
+  const double tMax = atof(argv[4]);
+  const double dMax = atof(argv[5]);
+  if (argc > 6) g_cubeL = atof(argv[6]);
+
+  double t0 = now();
+  InitFemTechWoInput(argc, argv);
+  ReadInputFile(argv[1]);
+  ReadMaterials();
+  PartitionMesh();
+  AllocateArrays();
+
+  char fname[1024];
+  snprintf(fname, sizeof fname, "%s.rank%d.bin", outPrefix, world_rank);
+  g_out = fopen(fname, "wb");
+  if (!g_out) { fprintf(stderr, "cannot open %s\n", fname); TerminateFemTech(3); }
+
+  puti1("world_size", world_size);
+  puti1("world_rank", world_rank);
+  puti1("nNodes", nNodes);
+  puti1("nelements", nelements);
+  puti1("nallelements", nallelements);
+  puti1("nPIDglobal", nPIDglobal);
+  putd("coordinates", coordinates, (int64_t)ndim * nNodes);
+  puti("connectivity", connectivity, eptr[nelements]);
+  puti("eptr", eptr, nelements + 1);
+  puti("pid", pid, nelements);
+  puti("global_eid", global_eid, nelements);
+  puti("globalNodeID", globalNodeID, nNodes);
+  puti("materialID", materialID, nPIDglobal);
+  putd("properties", properties, (int64_t)nPIDglobal * MAXMATPARAMS);
+  puti1("sendProcessCount", sendProcessCount);
+  puti("sendProcessID", sendProcessID, sendProcessCount);
+  puti("sendNeighbourCount", sendNeighbourCount, sendProcessCount);
+  puti("sendNeighbourCountCum", sendNeighbourCountCum, sendProcessCount + 1);
+  puti("sendNodeIndex", sendNodeIndex, sendProcessCount ? sendNeighbourCountCum[sendProcessCount] : 0);
+
+  Time = 0.0;
+  dt = 0.0;
+  ShapeFunctions();
+  putd("shp", shp, gptr[nelements]);
+  putd("dshp", dshp, dsptr[nelements]);
+  putd("detJacobian", detJacobian, gpPtr[nelements]);
+  putd("gaussWeights", gaussWeights, gpPtr[nelements]);
+  AssembleLumpedMass();
+  putd("mass", mass, nDOF);
+
+  ApplyBoundaryConditions(dMax, tMax);
+  puti("boundary0", boundary, nDOF);
+  dt = ExplicitTimeStepReduction * StableTimeStep();
+  GetForce();
+  CalculateAccelerations();
+  puts1("dt0", dt);
+  putd("fi0", fi, nDOF);
+  putd("accelerations0", accelerations, nDOF);
+  putd("pk2_0", pk2, pk2ptr[nelements]);
+
+  std::vector<double> dtHist;
+  int time_step_counter = 1;
+  double t_n = 0.0;
+  double tSetup = now() - t0;
+  double tLoop0 = now();
+  int steps = 0;
+  while (Time < tMax && steps < maxSteps) {
+    t_n = Time;
+    double t_np1 = Time + dt;
+    Time = t_np1;
+    double dt_nphalf = dt;
+    double t_nphalf = 0.5 * (t_np1 + t_n);
+    dtHist.push_back(dt);
+    for (int i = 0; i < nDOF; i++) {
+      if (boundary[i]) {
+        velocities_half[i] = velocities[i];
+      } else {
+        velocities_half[i] = velocities[i] + (t_nphalf - t_n) * accelerations[i];
+      }
+    }
+    memcpy(displacements_prev, displacements, nDOF * sizeof(double));
+    memcpy(accelerations_prev, accelerations, nDOF * sizeof(double));
+    memcpy(fi_prev, fi, nDOF * sizeof(double));
+    memcpy(fe_prev, fe, nDOF * sizeof(double));
+    for (int i = 0; i < nDOF; i++) {
+      if (!boundary[i]) {
+        displacements[i] = displacements[i] + dt_nphalf * velocities_half[i];
+      }
+    }
+    ApplyBoundaryConditions(dMax, tMax);
+    GetForce();
+    CalculateAccelerations();
+    for (int i = 0; i < nDOF; i++) {
+      if (!boundary[i]) {
+        velocities[i] = velocities_half[i] + (t_np1 - t_nphalf) * accelerations[i];
+      }
+    }
+    CheckEnergy(Time, 0); /* writeFlag 0: one energy_<uid>.dat line per step */
+    time_step_counter = time_step_counter + 1;
+    steps++;
+    dt = ExplicitTimeStepReduction * StableTimeStep();
+    MPI_Barrier(MPI_COMM_WORLD);
+  }
+  double tLoop = now() - tLoop0;
+  CalculateStrain();
+
+  puti1("steps", steps);
+  puts1("Time", Time);
+  puts1("dt", dt);
+  putd("dt_hist", dtHist.data(), (int64_t)dtHist.size());
+  putd("displacements", displacements, nDOF);
+  putd("velocities", velocities, nDOF);
+  putd("velocities_half", velocities_half, nDOF);
+  putd("accelerations", accelerations, nDOF);
+  puti("boundary", boundary, nDOF);
+  putd("fi", fi, nDOF);
+  putd("f_net", f_net, nDOF);
+  putd("F", F, fptr[nelements]);
+  putd("detF", detF, detFptr[nelements]);
+  putd("pk2", pk2, pk2ptr[nelements]);
+  putd("Eavg", Eavg, (int64_t)nelements * 9);
+  putd("Hn_1", Hn_1, Hn_1 ? fptr[nelements] : 0);
+  putd("Hn_2", Hn_2, Hn_2 ? fptr[nelements] : 0);
+  putd("S0n", S0n, S0n ? fptr[nelements] : 0);
+  puts1("wall_setup_s", tSetup);
+  puts1("wall_loop_s", tLoop);
+  fclose(g_out);
+  if (world_rank == 0) {
+    printf("REF_DUMP ranks=%d nallelements=%d steps=%d Time=%.17g dt=%.17g setup_s=%.3f loop_s=%.3f "
+           "element_steps_per_s=%.6e u0=(%.9e %.9e %.9e) uid=%s\n",
+           world_size, nallelements, steps, Time, dt, tSetup, tLoop,
+           tLoop > 0 ? (double)nallelements * steps / tLoop : 0.0, displacements[0], displacements[1],
+           displacements[2], uid.c_str());
+    fflush(stdout);
+  }
+  FinalizeFemTech();
+  return 0;
+}

@@ -1,0 +1,110 @@
+"""Pins the CPU oracle (oracle/femtech_oracle.c) against the reference itself.
+
+The fixtures in tests/golden/ were dumped from the UNMODIFIED reference sources
+(oracle/make_golden.py -> oracle/_ref/ref_dump_exact).  The oracle restates the
+reference operation by operation, so with -ffp-contract=off on both sides the
+comparison is BIT-EXACT, not a tolerance.  Also checks the reference's own
+known-answer test (examples/ex9/compareResults.py: 5 % vs Abaqus).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, rank_dict
+from femtech_b200 import mesh
+from oracle import pyoracle as po
+
+SINGLE = ["ex9_1elt", "bench10_p1", "cube4j_m1", "cube4j_m2", "cube4j_m3", "cube4j_m4", "cube4j_m5", "cube6mix_p1"]
+MULTI = ["bench10_p2", "bench10_p4", "bench10_p8", "cube6mix_p3"]
+
+
+def _models(g):
+    P = int(g["nranks"])
+    models, kinds, rate = [], [], None
+    for r in range(P):
+        d = rank_dict(g, r)
+        comm = None
+        if "sendProcessID" in d:
+            comm = {k: d[k] for k in ("sendProcessID", "sendNeighbourCountCum", "sendNodeIndex")}
+        m = po.OracleModel(d["coordinates"], d["connectivity"], d["pid"], d["materialID"], d["properties"], comm=comm,
+                           world_rank=r)
+        k, rate = mesh.benchmark_bc(d["coordinates"], dMax=float(g["param_dMax"]), tMax=float(g["param_tMax"]))
+        models.append(m)
+        kinds.append(k)
+    return models, kinds, rate
+
+
+def _run(g):
+    models, kinds, rate = _models(g)
+    for m in models:
+        m.ShapeFunctions()
+        m.AssembleLumpedMass()
+    if len(models) > 1:
+        po.halo_sum(models, "mass")
+    d0 = rank_dict(g, 0)
+    n, dth, eh = po.run_explicit(models, kinds, rate, float(g["param_tMax"]), int(d0["steps"][0]))
+    return models, n, dth, eh
+
+
+@pytest.mark.parametrize("name", SINGLE + MULTI)
+def test_oracle_bit_exact_vs_reference(name):
+    g = golden(name)
+    models, n, dth, eh = _run(g)
+    for r, m in enumerate(models):
+        d = rank_dict(g, r)
+        assert n == int(d["steps"][0])
+        assert m.Time == float(d["Time"][0]) and m.dt == float(d["dt"][0])
+        assert np.array_equal(dth, d["dt_hist"])
+        assert np.array_equal(m.mass, d["mass"])
+        for k in ["displacements", "velocities", "accelerations", "fi", "f_net", "boundary"]:
+            assert np.array_equal(getattr(m, k), d[k]), (name, r, k)
+        for k in ["detJacobian", "F", "detF", "pk2", "Hn_1", "Hn_2", "S0n"]:
+            if k in d and d[k].size:
+                assert np.array_equal(getattr(m, k), d[k]), (name, r, k)
+        if "Eavg" in d:
+            assert np.array_equal(m.CalculateStrain(), d["Eavg"])
+    # energy line written by the reference (%12.6e): time Wint Wext WKE total
+    ef = g["energy_file"][-1]
+    assert abs(models[0].Time - ef[0]) <= 1e-6 * abs(ef[0])
+    for got, want in zip(eh[-1], ef[1:]):
+        assert abs(got - want) <= 2e-6 * max(abs(want), 1e-300) + 1e-30
+
+
+def test_ex9_known_answer_vs_abaqus():
+    """examples/ex9/compareResults.py:14-29: last line of plot.dat vs last line
+    of abaqus/abaqus.rpt (columns 10-12 = U1..U3 of the node at (L,L,L)):
+    time within 1 %, displacements within 5 %."""
+    abaqus_t, abaqus_u = 1.0, np.array([-1.03349e-03, 7.0e-03, -1.03349e-03])
+    g = golden("ex9_1elt")
+    models, n, _, _ = _run(g)
+    m = models[0]
+    X = m.coordinates.reshape(-1, 3)
+    node = int(np.where(np.all(np.abs(X - mesh.CUBE_L) < 1e-5, axis=1))[0][0])
+    u = m.displacements.reshape(-1, 3)[node]
+    assert abs(m.Time - abaqus_t) * 100.0 / abaqus_t < 1.0
+    assert np.max(np.abs((u - abaqus_u) * 100.0 / abaqus_u)) < 5.0
+    # value observed when the reference itself was run in this container
+    assert np.allclose(u, [-1.07624e-03, 7.00001e-03, -1.07624e-03], rtol=2e-6)
+
+
+def test_golden_runs_are_nontrivial():
+    for name in SINGLE:
+        d = rank_dict(golden(name), 0)
+        assert np.all(np.isfinite(d["displacements"])) and np.abs(d["displacements"]).max() > 1e-6
+        assert int(d["steps"][0]) >= 50
+
+
+def test_geometry_quirk_signed_parallelogram_test():
+    """src/math/Geometry.cpp:46 compares centerD[i] < tol without fabs: a face
+    whose centre offset is large and NEGATIVE still takes the parallelogram
+    branch.  The oracle must reproduce that, not 'fix' it."""
+    L = po.lib()
+    c = np.array([[0, 0, 0], [1, 0, 0], [1.5, 1.5, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    idx = np.array([0, 1, 2, 3], dtype=np.int32)
+    a_pos = L.oracle_areaHexahedronFace(po._d(c.reshape(-1).copy()), po._i(idx))
+    c2 = c.copy()
+    c2[2] = [0.5, 0.5, 0]  # centerD negative -> parallelogram formula (quirk)
+    a_neg = L.oracle_areaHexahedronFace(po._d(c2.reshape(-1).copy()), po._i(idx))
+    p1, p2, p3, p4 = c2[0], c2[1], c2[2], c2[3]
+    c1v, c2v = 0.25 * (-p1 + p2 + p3 - p4), 0.25 * (-p1 - p2 + p3 + p4)
+    assert a_neg == pytest.approx(4.0 * np.linalg.norm(np.cross(c1v, c2v)), rel=1e-14)
+    assert a_pos == pytest.approx(1.5, rel=1e-12)  # planar quad: 2x2 Gauss is exact (shoelace area 1.5)
