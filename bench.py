@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- hex8 element-steps/s of the explicit step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, resident loop)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path on the host cores
+
+A "step" is one explicit time step (Benchmarking-Parallel.cpp:106-171: both kicks, drift, BC,
+GetForce, CalculateAccelerations, CheckEnergy, StableTimeStep) over the whole synthetic mesh.
+Prints ONE JSON line on rank 0.  See DESIGN.md section "Measurement" for every definition.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SOFT = [1040.0, 100.0, 100.0, 0, 0, 0, 0, 0, 0]  # examples/Benchmarking-Parallel/materials.dat:1
+BRAIN = [1000.0, 2673.23, 2.189982178466e8, 25459.0, 0.0, 0.6521, 0.0129, 0.0067, 0.0747]  # examples/ex5/materials.dat:2
+HGO = BRAIN[:4] + [10.0, 0, 0, 0, 0]
+MATERIALS = {1: SOFT, 4: HGO, 5: BRAIN}
+MAT_NAME = {1: "compressible neo-Hookean (mat 1)", 4: "HGO isotropic (mat 4)", 5: "HGO + 2-term Prony (mat 5)"}
+
+# Algorithmic work per element-step (DESIGN.md "Work model"): bytes = compulsory HBM traffic of the
+# design, flops = fp64 operations of the mode-basis formulation actually executed (FMA = 2).
+def algorithmic_bytes(n, mat, energy):
+    rho_n = ((n + 1.0) / n) ** 3
+    elem = 36 + 1 + 48 * rho_n + 192            # K_elem: conn+pid+eflag, X and u (unique nodes), f_e write
+    node = 192 + (4 + 32) * rho_n + (8 + 2 + 72 + 72) * rho_n  # K_node: f_e read, CSR, m, flags, u v a read + write
+    if energy:
+        node += 96 * rho_n                       # du and fi: write + read next step
+    hist = 2304 if mat == 5 else 0
+    return elem + hist, node
+
+
+ELEM_FLOPS = {1: 4690.0, 4: 5650.0, 5: 7300.0}  # per element-step, counted in DESIGN.md
+
+
+def clocks_sampler(stop, out, device_index):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", str(device_index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5)
+            out.append([x.strip() for x in r.stdout.strip().split(",")])
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def summarize_clocks(samples):
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for s in samples:
+        if len(s) < 6:
+            continue
+        try:
+            sm.append(float(s[0]))
+            mx.append(float(s[1]))
+        except ValueError:
+            continue
+        for nme, v in zip(names, s[2:6]):
+            if v.lower().startswith("active"):
+                reasons.add(nme)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU side
+def run_reference_cpu(n, mat, steps, warmup, ranks):
+    """Times the reference's own explicit loop (oracle/_ref/ref_dump_fast = unmodified reference sources,
+    built by oracle/ref/build_ref.sh) on a synthetic n^3 cube with `ranks` ranks through the ftmpi shim.
+    Falls back to the C port (oracle/) when the reference build is absent."""
+    from femtech_b200 import mesh
+    refbin = os.path.join(ROOT, "oracle", "_ref", "ref_dump_fast")
+    launcher = os.path.join(ROOT, "oracle", "_ref", "ftmpirun")
+    X, conn, pid = mesh.cube_mesh(n)
+    E = conn.shape[0]
+    if os.path.exists(refbin) and os.path.exists(launcher):
+        work = tempfile.mkdtemp(prefix="ftbench_")
+        mesh.write_abaqus_inp(os.path.join(work, "cube.inp"), X, conn, pid)
+        mesh.write_materials_dat(os.path.join(work, "materials.dat"), [mat], MATERIALS[mat])
+        tMax = 0.1 if mat == 1 else 0.004
+        cmd = [refbin, "cube.inp", "out", str(steps + warmup), repr(tMax), "0.007", "0.005", str(warmup), "nodump"]
+        if ranks > 1:
+            cmd = [launcher, "-np", str(ranks)] + cmd
+        r = subprocess.run(cmd, cwd=work, capture_output=True, text=True)
+        line = [l for l in r.stdout.splitlines() if l.startswith("REF_DUMP")]
+        if r.returncode == 0 and line:
+            kv = dict(t.split("=", 1) for t in line[0].split()[1:] if "=" in t)
+            timed = int(kv["timed_steps"])
+            loop_s = float(kv["loop_s"])
+            return {"value": E * timed / loop_s, "unit": "element-steps/s", "cores": ranks, "kind": "reference",
+                    "sample": "%d^3 hex8 cube (%d elements), %s, %d timed steps after %d warm-up, %d rank(s) via the "
+                              "in-repo MPI shim; loop only (setup excluded)" % (n, E, MAT_NAME[mat], timed, warmup, ranks),
+                    "loop_s": loop_s, "steps": timed}
+        sys.stderr.write("reference run failed (%d): %s\n" % (r.returncode, r.stderr[-500:]))
+    # port: the C restatement, one core
+    from oracle import pyoracle as po
+    kind, rate = mesh.benchmark_bc(X)
+    o = po.OracleModel(X, conn, pid, [mat], MATERIALS[mat], fast=True)
+    o.ShapeFunctions()
+    o.AssembleLumpedMass()
+    po.run_explicit([o], [kind], rate, 1e9, warmup, record=False)
+    t0 = time.time()
+    k, _, _ = po.run_explicit([o], [kind], rate, 1e9, steps, first_call=False, record=False)
+    loop_s = time.time() - t0
+    return {"value": E * k / loop_s, "unit": "element-steps/s", "cores": 1, "kind": "port",
+            "sample": "%d^3 hex8 cube (%d elements), %s, %d timed steps, C port of the reference (oracle/), 1 core"
+                      % (n, E, MAT_NAME[mat], k), "loop_s": loop_s, "steps": k}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = max(1, min(host_cores(), 32))
+    n = args.ref_n
+    res = run_reference_cpu(n, args.material, args.steps, args.warmup, cores)
+    E_work = args.n ** 3
+    out = {
+        "impl": "reference", "metric": "hex8 element-steps/sec fp64", "value": res["value"], "unit": "element-steps/s",
+        "n_gpus": args.gpus, "steps": res["steps"], "warmup": args.warmup,
+        "ms_per_step": 1e3 * res["loop_s"] / max(res["steps"], 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic %d^3 structured hex8 cube (%d elements), %s, benchmark BC, CheckEnergy every "
+                               "step; CPU arm timed on a bounded %d^3 sample of it" % (args.n, E_work, MAT_NAME[args.material], n)},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "element-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------ GPU side
+def ours_single(args):
+    import torch
+    from femtech_b200 import mesh, solver
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    n, mat = args.n, args.material
+    X, conn, pid = mesh.cube_mesh(n)
+    E, N = conn.shape[0], X.shape[0]
+    tMax = 1e30
+    dMax_over_tMax = 0.07 if mat == 1 else 1.75  # the drivers' ramp rate (0.007/0.1) / a faster one for stiff parts
+    kind, rate = mesh.benchmark_bc(X, dMax=dMax_over_tMax, tMax=1.0)
+    energy = 0 if args.no_energy else 1
+
+    m = solver.FemTech(X, conn, pid, [mat], MATERIALS[mat], device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    m.set_stream(stream.cuda_stream)
+    m.ShapeFunctions()
+    m.AssembleLumpedMass()
+    m.set_bc(kind, rate)
+    fp64_peak, copy_peak = solver.measure_peaks(m, reps=5)
+
+    # ---- device-resident timing (value) ---------------------------------------------------------
+    m.explicit_begin(energy_every=energy)
+    m.run_async(tMax, max(args.warmup, 3))
+    torch.cuda.synchronize()
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples, dev), daemon=True)
+    th.start()
+    l0 = m.gpu_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        m.run_async(tMax, args.steps)
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = m.gpu_launches - l0
+    # ---- same region again with per-kernel CUDA events (roofline) -------------------------------
+    m.profile(True)
+    with torch.cuda.stream(stream):
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev2.record(stream)
+        m.run_async(tMax, args.steps)
+        ev3.record(stream)
+    torch.cuda.synchronize()
+    prof = m.profile_get()
+    ms_total_prof = ev2.elapsed_time(ev3)
+    m.profile(False)
+    stop.set()
+    th.join(timeout=2)
+    m._poll()
+    assert np.isfinite(m.Time) and m.steps_done >= 2 * args.steps, "time loop did not advance"
+
+    value = E * args.steps / (ms_total * 1e-3)
+    b_elem, b_node = algorithmic_bytes(n, mat, energy)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    elem_s, node_s = prof["elem_ms"] * 1e-3, prof["node_ms"] * 1e-3
+    flops = ELEM_FLOPS[mat]
+    elem_tf = flops * E / elem_s / 1e12
+    elem_gbs = b_elem * E / elem_s / 1e9
+    node_gbs = b_node * E / node_s / 1e9
+    fp64_bound = elem_tf / fp64_peak >= elem_gbs / hbm_peak
+    roofline = {
+        "kernel": "k_elem (fused gather, F, material, B^T sigma, element dt)",
+        "bound": "fp64" if fp64_bound else "hbm",
+        "achieved": elem_tf if fp64_bound else elem_gbs,
+        "peak": fp64_peak if fp64_bound else hbm_peak,
+        "unit": "TFLOP/s" if fp64_bound else "GB/s",
+        "frac": (elem_tf / fp64_peak) if fp64_bound else (elem_gbs / hbm_peak),
+        "traffic": None,
+        "peak_source": "fp64: DFMA microbenchmark measured in this run; hbm: " + hbm_src,
+        "launch_ms": prof["elem_ms"], "launches_timed": prof["elem_launches"],
+        "algorithmic_flops_per_element": flops, "algorithmic_bytes_per_element": b_elem,
+        "hbm_view": {"achieved": elem_gbs, "peak": hbm_peak, "frac": elem_gbs / hbm_peak, "unit": "GB/s"},
+        "k_node": {"bound": "hbm", "achieved": node_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": node_gbs / hbm_peak,
+                   "launch_ms": prof["node_ms"], "algorithmic_bytes_per_element": b_node},
+        "step": {"element_steps_per_s": value,
+                 "roof_fp64": fp64_peak * 1e12 / flops, "roof_hbm": hbm_peak * 1e9 / (b_elem + b_node),
+                 "frac_of_min_roof": value / min(fp64_peak * 1e12 / flops, hbm_peak * 1e9 / (b_elem + b_node))},
+        "copy_gbs_measured_here": copy_peak,
+        "kernel_share_of_step": (prof["elem_ms"]) / (ms_total_prof / args.steps),
+    }
+
+    # ---- end to end through the public API with host buffers --------------------------------------
+    # (a) ExplicitDynamics(): state uploaded from pinned host arrays, K steps with the per-step scalars
+    #     (Time, dt, energies) read back every step, final state downloaded -- all inside the timed region
+    e2e_steps = min(args.steps, 50)
+    pin = {k: torch.zeros(3 * N, dtype=torch.float64).pin_memory() for k in ("u", "v", "a", "fi", "fn")}
+    pinb = torch.zeros(3 * N, dtype=torch.int32).pin_memory()
+    m.displacements, m.velocities, m.accelerations = pin["u"].numpy(), pin["v"].numpy(), pin["a"].numpy()
+    m.fi, m.f_net, m.boundary = pin["fi"].numpy(), pin["fn"].numpy(), pinb.numpy()
+    m.Time = 0.0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    m.explicit_begin(energy_every=energy)        # H2D of u, v, a, boundary + step 0
+    for _ in range(e2e_steps):
+        m.run_async(tMax, 1)
+        m._poll()                                # D2H of the step's scalars (Time, dt, status)
+        if energy:
+            m.energy()                           # D2H of Wint, Wext, WKE, total
+    m.sync_out()                                 # D2H of u, v, a, boundary, fi, f_net
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = (3 * 24 * N + 12 * N) / e2e_steps
+    d2h = (5 * 24 * N + 12 * N) / e2e_steps + 200 + (32 if energy else 0)
+    e2e = {"value": E * e2e_steps / e2e_s, "unit": "element-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "api": "ExplicitDynamics (resident): pinned host state in, %d single-step calls with per-step scalar read-back, "
+                  "host state out; copies inside the timed region" % e2e_steps, "steps": e2e_steps}
+    # (b) strict drop-in: the shipped drivers' four library calls per step, host arrays across PCIe every call
+    leg_steps = min(args.steps, 10)
+    bc = kind > 0
+    m.boundary[bc] = 1
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(leg_steps):
+        m.GetForce()
+        m.CalculateAccelerations()
+        m.CheckEnergy(m.Time, 1)
+        m.dt = 0.8 * m.StableTimeStep()
+    leg_s = time.perf_counter() - t0
+    e2e_legacy = {"value": E * leg_steps / leg_s, "unit": "element-steps/s",
+                  "h2d_bytes_per_step": (24 + 12 + 24 + 9 * 24 + 12 + 24 + 12) * N, "d2h_bytes_per_step": (24 + 24 + 24) * N,
+                  "api": "legacy drop-in: GetForce + CalculateAccelerations + CheckEnergy + StableTimeStep on host arrays "
+                         "(driver host loops not included)", "steps": leg_steps}
+
+    cpu = None
+    if not args.no_cpu:
+        cpu = run_reference_cpu(args.ref_n, mat, 40, 5, max(1, min(host_cores(), 32)))
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    out = {
+        "metric": "hex8 element-steps/sec fp64", "value": value, "unit": "element-steps/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic %d^3 structured hex8 cube (%d elements, %d nodes), %s, benchmark BC "
+                               "(Benchmarking-Parallel.cpp:184-244), %s, dt recomputed every step"
+                               % (n, E, N, MAT_NAME[mat], "CheckEnergy every step" if energy else "no energy check"),
+                   "mode": "resident ExplicitDynamics loop, CUDA graph of 25 steps",
+                   "l2": "per-step working set %.2f GB > 126 MB L2, no flush needed" % ((b_elem + b_node) * E / 1e9)},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_legacy": e2e_legacy,
+        "gpu_launches": launches, "clocks": summarize_clocks(samples),
+        "ms_per_step_with_kernel_events": ms_total_prof / args.steps,
+        "fp64_peak_tflops_measured": fp64_peak,
+    }
+    m.close()
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=100, help="cube edge in elements per GPU (BASELINE config 2: 100)")
+    ap.add_argument("--material", type=int, default=1, choices=[1, 4, 5])
+    ap.add_argument("--ref-n", type=int, default=40, help="edge of the bounded CPU sample")
+    ap.add_argument("--no-energy", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or args.gpus > 1:
+        from femtech_b200 import dist_bench
+        dist_bench.run(args)
+        return
+    ours_single(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,975 @@
+// ftb200_capi.cu -- the C-ABI (include/ftb200.h) over the CUDA kernels.
+// Host logic only: allocation, layout conversion at the boundary, CSR / halo map construction,
+// kernel sequencing (streams, CUDA graphs) and error mapping to the reference's abort codes.
+#include "../../include/ftb200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "ftb200_kernels.cuh"
+
+using namespace ftb;
+
+namespace {
+constexpr int GRAPH_STEPS = 25;
+
+struct ProfEvents {
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  std::vector<std::pair<size_t, size_t>> elem, node;  // (start,stop) indices
+};
+}  // namespace
+
+struct ftb200_ctx {
+  int rank = 0, nranks = 1, device = 0;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  bool own_stream = true;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  long long launches = 0;
+  char err[512] = {0};
+  int nN = 0, nE = 0, nPID = 0;
+  bool mesh_ok = false, mat_ok = false, shape_ok = false, begun = false, bc_ok = false;
+  // host copies of the inputs
+  std::vector<double> h_X;
+  std::vector<int> h_conn, h_pid, h_matid;
+  std::vector<double> h_props;
+  std::vector<int> h_sendProcessID, h_sendCum, h_sendNodeIndex;
+  // device arrays
+  double *X[3] = {0, 0, 0}, *u[3] = {0, 0, 0}, *v[3] = {0, 0, 0}, *a[3] = {0, 0, 0}, *fi[3] = {0, 0, 0};
+  double *du[3] = {0, 0, 0}, *fnet[3] = {0, 0, 0}, *fe[3] = {0, 0, 0};
+  bool has_fe = false;
+  double* m = nullptr;
+  uint16_t* flags = nullptr;
+  int *conn = nullptr, *pid = nullptr, *ref_of = nullptr;
+  uint8_t* eflag = nullptr;
+  double *felem = nullptr, *hist = nullptr, *mp = nullptr;
+  int *node_off = nullptr, *node_ent = nullptr;
+  DevScalars* sc = nullptr;
+  double *dthist = nullptr, *ehist = nullptr, *epart = nullptr, *out3 = nullptr;
+  long long hist_cap = 0;
+  int node_blocks = 0;
+  double* d_stage[3] = {0, 0, 0};  // 3N doubles each
+  int* d_istage = nullptr;         // 3N ints
+  double* d_big = nullptr;         // lazily sized scratch for legacy energy / gp outputs
+  size_t d_big_bytes = 0;
+  unsigned long long* d_detmin = nullptr;
+  int* d_nonpos = nullptr;
+  int uniform_mat = -1;
+  bool has_visco = false;
+  int energy = 0;
+  // halo
+  int halo_count = 0, nshared = 0, nE_boundary = 0;
+  int *d_sendNodeIndex = nullptr, *halo_nodes = nullptr, *halo_off = nullptr, *halo_slot = nullptr,
+      *halo_node_idx = nullptr;
+  const double* halo_recv_cur = nullptr;
+  // graph cache
+  cudaGraphExec_t graph = nullptr;
+  int graph_energy = -1;
+  // profiling
+  bool profile = false;
+  ProfEvents prof;
+  double prof_elem_ms = 0, prof_node_ms = 0;
+  long long prof_elem_n = 0, prof_node_n = 0;
+};
+
+namespace {
+
+int fail(ftb200_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c->err, sizeof(c->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CK(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? FTB200_ERR_ALLOC : FTB200_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                          \
+  } while (0)
+
+#define LAUNCH(kern, grid, block, strm, ...)            \
+  do {                                                  \
+    auto kfn_ = kern;                                   \
+    kfn_<<<(grid), (block), 0, (strm)>>>(__VA_ARGS__);  \
+    ctx->launches++;                                    \
+  } while (0)
+
+inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+template <class T>
+int dalloc(ftb200_ctx* ctx, T** p, size_t n) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  CK(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+  return 0;
+}
+template <class T>
+void dfree(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+int ensure_big(ftb200_ctx* ctx, size_t bytes) {
+  if (ctx->d_big_bytes >= bytes) return 0;
+  dfree(ctx->d_big);
+  CK(cudaMalloc((void**)&ctx->d_big, bytes));
+  ctx->d_big_bytes = bytes;
+  return 0;
+}
+
+ElemArgs elem_args(ftb200_ctx* c, int e0, int e1, int ignore) {
+  ElemArgs A;
+  for (int k = 0; k < 3; ++k) { A.X[k] = c->X[k]; A.u[k] = c->u[k]; }
+  A.conn = c->conn; A.pid = c->pid; A.eflag = c->eflag; A.mp = c->mp; A.felem = c->felem; A.hist = c->hist;
+  A.sc = c->sc; A.nE = c->nE; A.e0 = e0; A.e1 = e1; A.ignore_loop_flags = ignore;
+  return A;
+}
+NodeArgs node_args(ftb200_ctx* c, const double* recv) {
+  NodeArgs A;
+  for (int k = 0; k < 3; ++k) {
+    A.u[k] = c->u[k]; A.v[k] = c->v[k]; A.a[k] = c->a[k]; A.fi[k] = c->fi[k]; A.du[k] = c->du[k];
+    A.fe[k] = c->has_fe ? c->fe[k] : nullptr;
+  }
+  A.m = c->m; A.flags = c->flags; A.felem = c->felem; A.node_off = c->node_off; A.node_ent = c->node_ent;
+  A.halo_recv = recv;
+  A.halo_off = c->halo_off; A.halo_slot = c->halo_slot;
+  A.halo_node_idx = recv ? c->halo_node_idx : nullptr;
+  A.epart = c->epart; A.sc = c->sc; A.nN = c->nN; A.nE = c->nE;
+  A.store_fi = c->energy ? 1 : 0;
+  return A;
+}
+
+// element kernel dispatch on the (uniform) material of the launch
+template <bool WITH_FORCE, bool WITH_DT>
+void launch_elem(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore) {
+  if (e1 <= e0) return;
+  const ElemArgs A = elem_args(ctx, e0, e1, ignore);
+  const int grid = cdiv(e1 - e0, ELEM_BLOCK);
+  if (!WITH_FORCE) { LAUNCH((k_elem<-1, false, true>), grid, ELEM_BLOCK, s, A); return; }
+  switch (ctx->uniform_mat) {
+    case 1: LAUNCH((k_elem<1, WITH_FORCE, WITH_DT>), grid, ELEM_BLOCK, s, A); break;
+    case 4: LAUNCH((k_elem<4, WITH_FORCE, WITH_DT>), grid, ELEM_BLOCK, s, A); break;
+    case 5: LAUNCH((k_elem<5, WITH_FORCE, WITH_DT>), grid, ELEM_BLOCK, s, A); break;
+    default: LAUNCH((k_elem<-1, WITH_FORCE, WITH_DT>), grid, ELEM_BLOCK, s, A); break;
+  }
+}
+
+cudaEvent_t prof_event(ftb200_ctx* ctx, size_t* idx) {
+  ProfEvents& P = ctx->prof;
+  if (P.used == P.pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    P.pool.push_back(e);
+  }
+  *idx = P.used;
+  return P.pool[P.used++];
+}
+
+// one loop iteration: K_elem -> K_adv -> K_node (-> K_energy)
+void launch_step(ftb200_ctx* ctx, const double* recv) {
+  cudaStream_t s = ctx->stream;
+  size_t i0 = 0, i1 = 0;
+  if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
+  launch_elem<true, true>(ctx, s, 0, ctx->nE, 0);
+  if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.elem.push_back({i0, i1}); }
+  LAUNCH((k_adv<false>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, 0.0, ctx->dthist);
+  const NodeArgs N = node_args(ctx, recv);
+  if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
+  if (ctx->energy) LAUNCH((k_node<true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
+  else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+  if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.node.push_back({i0, i1}); }
+  if (ctx->energy) LAUNCH(k_energy, 1, 256, s, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
+}
+
+void prof_collect(ftb200_ctx* ctx) {
+  ProfEvents& P = ctx->prof;
+  for (auto& pr : P.elem) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, P.pool[pr.first], P.pool[pr.second]) == cudaSuccess) { ctx->prof_elem_ms += ms; ctx->prof_elem_n++; }
+  }
+  for (auto& pr : P.node) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, P.pool[pr.first], P.pool[pr.second]) == cudaSuccess) { ctx->prof_node_ms += ms; ctx->prof_node_n++; }
+  }
+  P.elem.clear(); P.node.clear(); P.used = 0;
+}
+
+int upload_aos(ftb200_ctx* ctx, const double* host, double* const dst[3]) {
+  const size_t n3 = 3 * (size_t)ctx->nN;
+  CK(cudaMemcpyAsync(ctx->d_stage[0], host, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(k_aos_to_soa, cdiv(ctx->nN, 256), 256, ctx->stream, ctx->d_stage[0], dst[0], dst[1], dst[2], ctx->nN);
+  return 0;
+}
+int download_aos(ftb200_ctx* ctx, double* const src[3], double* host, int stage) {
+  const size_t n3 = 3 * (size_t)ctx->nN;
+  LAUNCH(k_soa_to_aos, cdiv(ctx->nN, 256), 256, ctx->stream, src[0], src[1], src[2], ctx->d_stage[stage], ctx->nN);
+  CK(cudaMemcpyAsync(host, ctx->d_stage[stage], n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+int upload_boundary(ftb200_ctx* ctx, const int* boundary) {
+  const size_t n3 = 3 * (size_t)ctx->nN;
+  CK(cudaMemcpyAsync(ctx->d_istage, boundary, n3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(k_boundary_to_flags, cdiv(ctx->nN, 256), 256, ctx->stream, ctx->d_istage, ctx->flags, ctx->nN);
+  return 0;
+}
+
+void free_all(ftb200_ctx* c) {
+  for (int k = 0; k < 3; ++k) {
+    dfree(c->X[k]); dfree(c->u[k]); dfree(c->v[k]); dfree(c->a[k]); dfree(c->fi[k]); dfree(c->du[k]);
+    dfree(c->fnet[k]); dfree(c->fe[k]); dfree(c->d_stage[k]);
+  }
+  dfree(c->m); dfree(c->flags); dfree(c->conn); dfree(c->pid); dfree(c->ref_of); dfree(c->eflag);
+  dfree(c->felem); dfree(c->hist); dfree(c->mp); dfree(c->node_off); dfree(c->node_ent); dfree(c->sc);
+  dfree(c->dthist); dfree(c->ehist); dfree(c->epart); dfree(c->out3); dfree(c->d_istage); dfree(c->d_big);
+  c->d_big_bytes = 0;
+  dfree(c->d_detmin); dfree(c->d_nonpos);
+  dfree(c->d_sendNodeIndex); dfree(c->halo_nodes); dfree(c->halo_off); dfree(c->halo_slot); dfree(c->halo_node_idx);
+  if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ftb200_build_info(void) {
+  return "femtech_b200 C-ABI; CUDA kernels built for sm_100a (fp64, one thread per element / node)";
+}
+
+int ftb200_create(int rank, int nranks, int device, ftb200_ctx** out) {
+  if (!out) return FTB200_ERR_INPUT;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    fprintf(stderr, "ftb200_create: no usable CUDA device (%s); there is no CPU fallback\n", cudaGetErrorString(e));
+    return FTB200_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) return FTB200_ERR_INPUT;
+  ftb200_ctx* ctx = new ftb200_ctx();
+  ctx->rank = rank; ctx->nranks = nranks; ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    delete ctx;
+    return FTB200_ERR_CUDA;
+  }
+  *out = ctx;
+  return FTB200_OK;
+}
+
+int ftb200_destroy(ftb200_ctx* ctx) {
+  if (!ctx) return FTB200_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  free_all(ctx);
+  for (auto e : ctx->prof.pool) cudaEventDestroy(e);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  delete ctx;
+  return FTB200_OK;
+}
+
+const char* ftb200_last_error(const ftb200_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+long long ftb200_launch_count(const ftb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ftb200_set_stream(ftb200_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return FTB200_ERR_INPUT;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+  if (cuda_stream) {
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+  } else if (!ctx->own_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  return FTB200_OK;
+}
+
+int ftb200_upload_mesh(ftb200_ctx* ctx, const double* coordinates, const int* connectivity, const int* pid, int nNodes,
+                       int nElements) {
+  if (!ctx || !coordinates || !connectivity || !pid || nNodes <= 0 || nElements <= 0)
+    return fail(ctx, FTB200_ERR_INPUT, "upload_mesh: null pointer or empty mesh");
+  if ((long long)nElements * 8 >= (1LL << 31)) return fail(ctx, FTB200_ERR_INPUT, "upload_mesh: more than 2^28 elements per GPU");
+  for (long long i = 0; i < 8LL * nElements; ++i)
+    if (connectivity[i] < 0 || connectivity[i] >= nNodes)
+      return fail(ctx, FTB200_ERR_INPUT, "upload_mesh: connectivity[%lld] = %d out of range", i, connectivity[i]);
+  ctx->nN = nNodes; ctx->nE = nElements;
+  ctx->h_X.assign(coordinates, coordinates + 3 * (size_t)nNodes);
+  ctx->h_conn.assign(connectivity, connectivity + 8 * (size_t)nElements);
+  ctx->h_pid.assign(pid, pid + nElements);
+  ctx->mesh_ok = true; ctx->shape_ok = false; ctx->begun = false;
+  return FTB200_OK;
+}
+
+int ftb200_upload_materials(ftb200_ctx* ctx, const int* materialID, const double* properties, int nPID) {
+  if (!ctx || !materialID || !properties || nPID <= 0) return fail(ctx, FTB200_ERR_INPUT, "upload_materials: bad arguments");
+  for (int p = 0; p < nPID; ++p)
+    if (materialID[p] < 0 || materialID[p] > 5)  // StressUpdate.cpp:24-26
+      return fail(ctx, FTB200_ERR_MATERIAL, "Unknown material type %d for part %d", materialID[p], p);
+  ctx->nPID = nPID;
+  ctx->h_matid.assign(materialID, materialID + nPID);
+  ctx->h_props.assign(properties, properties + 9 * (size_t)nPID);
+  ctx->mat_ok = true; ctx->shape_ok = false;
+  return FTB200_OK;
+}
+
+int ftb200_upload_comm(ftb200_ctx* ctx, int sendProcessCount, const int* sendProcessID, const int* sendNeighbourCountCum,
+                       const int* sendNodeIndex) {
+  if (!ctx || sendProcessCount < 0) return fail(ctx, FTB200_ERR_INPUT, "upload_comm: bad arguments");
+  ctx->h_sendProcessID.clear(); ctx->h_sendCum.assign(1, 0); ctx->h_sendNodeIndex.clear();
+  if (sendProcessCount > 0) {
+    if (!sendProcessID || !sendNeighbourCountCum || !sendNodeIndex) return fail(ctx, FTB200_ERR_INPUT, "upload_comm: null pointer");
+    ctx->h_sendProcessID.assign(sendProcessID, sendProcessID + sendProcessCount);
+    ctx->h_sendCum.assign(sendNeighbourCountCum, sendNeighbourCountCum + sendProcessCount + 1);
+    ctx->h_sendNodeIndex.assign(sendNodeIndex, sendNodeIndex + sendNeighbourCountCum[sendProcessCount]);
+  }
+  ctx->shape_ok = false;
+  return FTB200_OK;
+}
+
+int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
+  if (!ctx || !ctx->mesh_ok || !ctx->mat_ok) return fail(ctx, FTB200_ERR_INPUT, "shape_functions: upload mesh and materials first");
+  CK(cudaSetDevice(ctx->device));
+  const int nN = ctx->nN, nE = ctx->nE, nPID = ctx->nPID;
+  for (int e = 0; e < nE; ++e)
+    if (ctx->h_pid[e] < 0 || ctx->h_pid[e] >= nPID) return fail(ctx, FTB200_ERR_INPUT, "pid[%d] = %d out of range", e, ctx->h_pid[e]);
+  free_all(ctx);
+  // ---- shared nodes and the boundary/interior element split -------------------------------
+  ctx->halo_count = (int)ctx->h_sendNodeIndex.size();
+  std::vector<int> node_h(nN, -1), halo_nodes;
+  for (int i = 0; i < ctx->halo_count; ++i) {
+    const int n = ctx->h_sendNodeIndex[i];
+    if (n < 0 || n >= nN) return fail(ctx, FTB200_ERR_INPUT, "sendNodeIndex[%d] = %d out of range", i, n);
+    if (node_h[n] < 0) { node_h[n] = 0; }
+  }
+  for (int n = 0; n < nN; ++n)
+    if (node_h[n] == 0) { node_h[n] = (int)halo_nodes.size(); halo_nodes.push_back(n); }
+  ctx->nshared = (int)halo_nodes.size();
+  // slots of every shared node in ascending neighbour order (slot index i is neighbour-major already)
+  std::vector<int> hoff(ctx->nshared + 1, 0), hslot(ctx->halo_count);
+  for (int i = 0; i < ctx->halo_count; ++i) hoff[node_h[ctx->h_sendNodeIndex[i]] + 1]++;
+  for (int h = 0; h < ctx->nshared; ++h) hoff[h + 1] += hoff[h];
+  {
+    std::vector<int> cur(hoff.begin(), hoff.end() - 1);
+    for (int i = 0; i < ctx->halo_count; ++i) hslot[cur[node_h[ctx->h_sendNodeIndex[i]]]++] = i;
+  }
+  // internal element order: elements touching a shared node first, reference order kept inside each group
+  std::vector<int> ref_of(nE), int_of(nE);
+  {
+    std::vector<char> isb(nE, 0);
+    int nb = 0;
+    if (ctx->nshared)
+      for (int e = 0; e < nE; ++e) {
+        for (int k = 0; k < 8; ++k)
+          if (node_h[ctx->h_conn[8 * (size_t)e + k]] >= 0) { isb[e] = 1; break; }
+        nb += isb[e];
+      }
+    ctx->nE_boundary = nb;
+    int ib = 0, ii = nb;
+    for (int e = 0; e < nE; ++e) {
+      const int t = isb[e] ? ib++ : ii++;
+      ref_of[t] = e; int_of[e] = t;
+    }
+  }
+  // ---- CSR node -> (element, slot), ascending reference element id -------------------------
+  std::vector<int> off(nN + 1, 0), ent(8 * (size_t)nE);
+  for (size_t i = 0; i < 8 * (size_t)nE; ++i) off[ctx->h_conn[i] + 1]++;
+  for (int n = 0; n < nN; ++n) off[n + 1] += off[n];
+  {
+    std::vector<int> cur(off.begin(), off.end() - 1);
+    for (int e = 0; e < nE; ++e)
+      for (int k = 0; k < 8; ++k) ent[cur[ctx->h_conn[8 * (size_t)e + k]]++] = int_of[e] * 8 + k;
+  }
+  // ---- SoA planes ----------------------------------------------------------------------------
+  std::vector<int> connT(8 * (size_t)nE), pidI(nE);
+  for (int t = 0; t < nE; ++t) {
+    const int e = ref_of[t];
+    for (int k = 0; k < 8; ++k) connT[(size_t)k * nE + t] = ctx->h_conn[8 * (size_t)e + k];
+    pidI[t] = ctx->h_pid[e];
+  }
+  std::vector<double> Xs(3 * (size_t)nN);
+  for (int n = 0; n < nN; ++n)
+    for (int c = 0; c < 3; ++c) Xs[(size_t)c * nN + n] = ctx->h_X[3 * (size_t)n + c];
+  // per-part parameter blocks
+  std::vector<double> mp((size_t)nPID * FTB_MP_STRIDE, 0.0);
+  std::vector<char> used(nPID, 0);
+  for (int e = 0; e < nE; ++e) used[ctx->h_pid[e]] = 1;
+  ctx->uniform_mat = -2; ctx->has_visco = false;
+  for (int p = 0; p < nPID; ++p) {
+    double* q = &mp[(size_t)p * FTB_MP_STRIDE];
+    for (int k = 0; k < 9; ++k) q[k] = ctx->h_props[9 * (size_t)p + k];
+    const double rho = q[MP_RHO], mu = q[MP_MU], lambda = q[MP_LAMBDA];
+    const double nu = 0.5 * lambda / (lambda + mu);          // CalculateTimeStep.cpp:15
+    q[MP_CE] = sqrt(lambda * (1.0 / nu - 1.0) / rho);       // :17
+    q[MP_KBULK] = lambda + 2.0 * mu / 3.0;                   // HGOIsotropic.cpp:44
+    q[MP_MATID] = (double)ctx->h_matid[p];
+    if (used[p]) {
+      if (ctx->h_matid[p] == 5) ctx->has_visco = true;
+      if (ctx->uniform_mat == -2) ctx->uniform_mat = ctx->h_matid[p];
+      else if (ctx->uniform_mat != ctx->h_matid[p]) ctx->uniform_mat = -1;
+    }
+  }
+  if (ctx->uniform_mat != 1 && ctx->uniform_mat != 4 && ctx->uniform_mat != 5) ctx->uniform_mat = -1;
+  // ---- device allocation ---------------------------------------------------------------------
+  int rc;
+  for (int k = 0; k < 3; ++k) {
+    if ((rc = dalloc(ctx, &ctx->X[k], nN)) || (rc = dalloc(ctx, &ctx->u[k], nN)) || (rc = dalloc(ctx, &ctx->v[k], nN)) ||
+        (rc = dalloc(ctx, &ctx->a[k], nN)) || (rc = dalloc(ctx, &ctx->fi[k], nN)) || (rc = dalloc(ctx, &ctx->du[k], nN)) ||
+        (rc = dalloc(ctx, &ctx->fnet[k], nN)) || (rc = dalloc(ctx, &ctx->d_stage[k], 3 * (size_t)nN)))
+      return rc;
+    CK(cudaMemcpy(ctx->X[k], &Xs[(size_t)k * nN], nN * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->u[k], 0, nN * sizeof(double)));
+    CK(cudaMemset(ctx->v[k], 0, nN * sizeof(double)));
+    CK(cudaMemset(ctx->a[k], 0, nN * sizeof(double)));
+    CK(cudaMemset(ctx->fi[k], 0, nN * sizeof(double)));
+    CK(cudaMemset(ctx->du[k], 0, nN * sizeof(double)));
+    CK(cudaMemset(ctx->fnet[k], 0, nN * sizeof(double)));
+  }
+  ctx->node_blocks = cdiv(nN, NODE_BLOCK);
+  if ((rc = dalloc(ctx, &ctx->m, nN)) || (rc = dalloc(ctx, &ctx->flags, nN)) || (rc = dalloc(ctx, &ctx->conn, 8 * (size_t)nE)) ||
+      (rc = dalloc(ctx, &ctx->pid, nE)) || (rc = dalloc(ctx, &ctx->ref_of, nE)) || (rc = dalloc(ctx, &ctx->eflag, nE)) ||
+      (rc = dalloc(ctx, &ctx->felem, 24 * (size_t)nE)) || (rc = dalloc(ctx, &ctx->mp, mp.size())) ||
+      (rc = dalloc(ctx, &ctx->node_off, nN + 1)) || (rc = dalloc(ctx, &ctx->node_ent, 8 * (size_t)nE)) ||
+      (rc = dalloc(ctx, &ctx->sc, 1)) || (rc = dalloc(ctx, &ctx->epart, 3 * (size_t)ctx->node_blocks)) ||
+      (rc = dalloc(ctx, &ctx->out3, 4)) || (rc = dalloc(ctx, &ctx->d_istage, 3 * (size_t)nN)) ||
+      (rc = dalloc(ctx, &ctx->d_detmin, 1)) || (rc = dalloc(ctx, &ctx->d_nonpos, 1)))
+    return rc;
+  CK(cudaMemset(ctx->m, 0, nN * sizeof(double)));
+  CK(cudaMemset(ctx->eflag, 0, nE));
+  CK(cudaMemset(ctx->felem, 0, 24 * (size_t)nE * sizeof(double)));
+  CK(cudaMemset(ctx->sc, 0, sizeof(DevScalars)));
+  CK(cudaMemcpy(ctx->conn, connT.data(), connT.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->pid, pidI.data(), nE * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->ref_of, ref_of.data(), nE * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->mp, mp.data(), mp.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->node_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->node_ent, ent.data(), ent.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (ctx->has_visco) {  // Hn_1, Hn_2, S0n zero at t = 0 (ShapeFunctions.cpp:245-252)
+    const size_t n = (size_t)3 * 6 * 8 * nE;
+    if ((rc = dalloc(ctx, &ctx->hist, n))) return rc;
+    CK(cudaMemset(ctx->hist, 0, n * sizeof(double)));
+  }
+  // flags: shared / not-owned bits (CheckEnergy.cpp:21-33: a shared node is counted by the lowest rank sharing it)
+  {
+    std::vector<uint16_t> fl(nN, 0);
+    for (int n : halo_nodes) fl[n] |= FTB_FLAG_SHARED;
+    for (size_t p = 0; p < ctx->h_sendProcessID.size(); ++p)
+      if (ctx->h_sendProcessID[p] < ctx->rank)
+        for (int i = ctx->h_sendCum[p]; i < ctx->h_sendCum[p + 1]; ++i) fl[ctx->h_sendNodeIndex[i]] |= FTB_FLAG_NOTOWNED;
+    CK(cudaMemcpy(ctx->flags, fl.data(), nN * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  }
+  if (ctx->halo_count) {
+    if ((rc = dalloc(ctx, &ctx->d_sendNodeIndex, ctx->halo_count)) || (rc = dalloc(ctx, &ctx->halo_nodes, ctx->nshared)) ||
+        (rc = dalloc(ctx, &ctx->halo_off, ctx->nshared + 1)) || (rc = dalloc(ctx, &ctx->halo_slot, ctx->halo_count)) ||
+        (rc = dalloc(ctx, &ctx->halo_node_idx, nN)))
+      return rc;
+    CK(cudaMemcpy(ctx->d_sendNodeIndex, ctx->h_sendNodeIndex.data(), ctx->halo_count * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->halo_nodes, halo_nodes.data(), ctx->nshared * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->halo_off, hoff.data(), hoff.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->halo_slot, hslot.data(), hslot.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->halo_node_idx, node_h.data(), nN * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  // ---- validate the reference configuration: detJ0 > 0 at every Gauss point --------------------
+  {
+    const unsigned long long inf = 0x7FF0000000000000ULL;
+    CK(cudaMemcpy(ctx->d_detmin, &inf, sizeof(inf), cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->d_nonpos, 0, sizeof(int)));
+    // the per-element masses land in the first 8 planes of felem (scratch until the first force call)
+    LAUNCH(k_mass_elem, cdiv(nE, 128), 128, ctx->stream, elem_args(ctx, 0, nE, 1), ctx->felem, ctx->d_detmin, ctx->d_nonpos);
+    LAUNCH(k_mass_gather, cdiv(nN, 256), 256, ctx->stream, ctx->felem, ctx->node_off, ctx->node_ent, ctx->m, nN, nE);
+    unsigned long long bits = 0;
+    int nonpos = 0;
+    CK(cudaMemcpyAsync(&bits, ctx->d_detmin, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&nonpos, ctx->d_nonpos, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double dmin;
+    memcpy(&dmin, &bits, 8);
+    if (min_detJ) *min_detJ = nonpos ? -1.0 : dmin;
+    if (nonpos) return fail(ctx, FTB200_ERR_INPUT, "%d elements have a non-positive reference Jacobian", nonpos);
+  }
+  ctx->shape_ok = true; ctx->begun = false; ctx->bc_ok = false; ctx->has_fe = false;
+  return FTB200_OK;
+}
+
+int ftb200_lumped_mass(ftb200_ctx* ctx, double* mass_out) {
+  if (!ctx || !ctx->shape_ok) return fail(ctx, FTB200_ERR_INPUT, "lumped_mass: call shape_functions first");
+  CK(cudaSetDevice(ctx->device));
+  const int nN = ctx->nN, nE = ctx->nE;
+  const unsigned long long inf = 0x7FF0000000000000ULL;
+  CK(cudaMemcpyAsync(ctx->d_detmin, &inf, sizeof(inf), cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(k_mass_elem, cdiv(nE, 128), 128, ctx->stream, elem_args(ctx, 0, nE, 1), ctx->felem, ctx->d_detmin, ctx->d_nonpos);
+  LAUNCH(k_mass_gather, cdiv(nN, 256), 256, ctx->stream, ctx->felem, ctx->node_off, ctx->node_ent, ctx->m, nN, nE);
+  if (mass_out) {
+    double* src[3] = {ctx->m, ctx->m, ctx->m};  // the same value on the three dofs of a node (Mass3D.cpp:146-151)
+    int rc = download_aos(ctx, src, mass_out, 0);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return FTB200_OK;
+}
+
+// ------------------------------------------------------------------------------------- legacy path
+static int legacy_force_local(ftb200_ctx* ctx, const double* displacements, const double* fe, double dt) {
+  int rc;
+  if ((rc = upload_aos(ctx, displacements, ctx->u))) return rc;
+  if (fe) {
+    for (int k = 0; k < 3; ++k)
+      if (!ctx->fe[k] && (rc = dalloc(ctx, &ctx->fe[k], ctx->nN))) return rc;
+    if ((rc = upload_aos(ctx, fe, ctx->fe))) return rc;
+    ctx->has_fe = true;
+  }
+  if (ctx->has_visco) LAUNCH(k_prony, 1, 128, ctx->stream, ctx->mp, ctx->nPID, dt);
+  launch_elem<true, false>(ctx, ctx->stream, 0, ctx->nE, 1);
+  return 0;
+}
+
+int ftb200_get_force(ftb200_ctx* ctx, const double* displacements, const double* fe, double dt, double* fi, double* f_net) {
+  if (!ctx || !ctx->shape_ok || !displacements) return fail(ctx, FTB200_ERR_INPUT, "get_force: bad arguments / setup incomplete");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = legacy_force_local(ctx, displacements, fe, dt))) return rc;
+  const NodeArgs N = node_args(ctx, nullptr);
+  LAUNCH(k_gather_force, ctx->node_blocks, NODE_BLOCK, ctx->stream, N, ctx->fnet[0], ctx->fnet[1], ctx->fnet[2]);
+  if (fi && (rc = download_aos(ctx, ctx->fi, fi, 0))) return rc;
+  if (f_net && (rc = download_aos(ctx, ctx->fnet, f_net, 1))) return rc;
+  int status = 0;
+  CK(cudaMemcpyAsync(&status, &ctx->sc->status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (status & 1) return fail(ctx, FTB200_ERR_MATERIAL, "Unknown material type");
+  return FTB200_OK;
+}
+
+int ftb200_calculate_accelerations(ftb200_ctx* ctx, const int* boundary, double* accelerations) {
+  if (!ctx || !ctx->shape_ok || !boundary || !accelerations) return fail(ctx, FTB200_ERR_INPUT, "calculate_accelerations: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = upload_boundary(ctx, boundary))) return rc;
+  // a = f_net/m on free dofs into scratch planes, then a masked merge into the caller's array
+  LAUNCH(k_accel, cdiv(ctx->nN, 256), 256, ctx->stream, ctx->fnet[0], ctx->fnet[1], ctx->fnet[2], ctx->m, ctx->flags,
+         ctx->a[0], ctx->a[1], ctx->a[2], ctx->nN);
+  const size_t n3 = 3 * (size_t)ctx->nN;
+  LAUNCH(k_soa_to_aos, cdiv(ctx->nN, 256), 256, ctx->stream, ctx->a[0], ctx->a[1], ctx->a[2], ctx->d_stage[0], ctx->nN);
+  CK(cudaMemcpyAsync(ctx->d_stage[1], accelerations, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(k_merge_free, cdiv((long long)n3, 256), 256, ctx->stream, ctx->d_stage[0], ctx->d_stage[1], ctx->d_istage, (int)n3);
+  CK(cudaMemcpyAsync(accelerations, ctx->d_stage[1], n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return FTB200_OK;
+}
+
+int ftb200_stable_time_step(ftb200_ctx* ctx, const double* displacements, const int* boundary, double* dtMin) {
+  if (!ctx || !ctx->shape_ok || !displacements || !boundary || !dtMin) return fail(ctx, FTB200_ERR_INPUT, "stable_time_step: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = upload_aos(ctx, displacements, ctx->u))) return rc;
+  if ((rc = upload_boundary(ctx, boundary))) return rc;
+  LAUNCH(k_eflag, cdiv(ctx->nE, 256), 256, ctx->stream, ctx->conn, ctx->flags, ctx->eflag, ctx->nE);
+  const unsigned long long inf = 0x7FF0000000000000ULL;
+  CK(cudaMemcpyAsync(&ctx->sc->dtmin_bits, &inf, sizeof(inf), cudaMemcpyHostToDevice, ctx->stream));
+  launch_elem<false, true>(ctx, ctx->stream, 0, ctx->nE, 1);
+  unsigned long long bits = 0;
+  CK(cudaMemcpyAsync(&bits, &ctx->sc->dtmin_bits, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  double d;
+  memcpy(&d, &bits, 8);
+  *dtMin = d > 1e20 ? 1e20 : d;  // dtMin starts at `huge`
+  return FTB200_OK;
+}
+
+int ftb200_check_energy(ftb200_ctx* ctx, const double* u, const double* up, const double* v, const double* a, const double* ap,
+                        const double* fi, const double* fip, const double* fe, const double* fep, const int* boundary,
+                        double out[3]) {
+  if (!ctx || !ctx->shape_ok || !u || !up || !v || !a || !ap || !fi || !fip || !boundary || !out)
+    return fail(ctx, FTB200_ERR_INPUT, "check_energy: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n3 = 3 * (size_t)ctx->nN, B = n3 * sizeof(double);
+  int rc;
+  if ((rc = ensure_big(ctx, 9 * B))) return rc;
+  const double* hp[9] = {u, up, v, a, ap, fi, fip, fe, fep};
+  double* dp[9];
+  for (int i = 0; i < 9; ++i) {
+    dp[i] = hp[i] ? ctx->d_big + i * n3 : nullptr;
+    if (hp[i]) CK(cudaMemcpyAsync(dp[i], hp[i], B, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaMemcpyAsync(ctx->d_istage, boundary, n3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(k_energy_legacy, ctx->node_blocks, NODE_BLOCK, ctx->stream, dp[0], dp[1], dp[2], dp[3], dp[4], dp[5], dp[6], dp[7],
+         dp[8], ctx->d_istage, ctx->m, ctx->flags, ctx->epart, ctx->nN);
+  LAUNCH(k_sum3, 1, 256, ctx->stream, ctx->epart, ctx->node_blocks, ctx->out3);
+  CK(cudaMemcpyAsync(out, ctx->out3, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return FTB200_OK;
+}
+
+int ftb200_get_gp_outputs(ftb200_ctx* ctx, double* F, double* detF, double* pk2, double* Eavg) {
+  if (!ctx || !ctx->shape_ok) return fail(ctx, FTB200_ERR_INPUT, "get_gp_outputs: setup incomplete");
+  CK(cudaSetDevice(ctx->device));
+  const size_t nE = ctx->nE;
+  const size_t nF = F ? 72 * nE : 0, nD = detF ? 8 * nE : 0, nP = pk2 ? 48 * nE : 0, nEa = Eavg ? 9 * nE : 0;
+  int rc;
+  if ((rc = ensure_big(ctx, (nF + nD + nP + nEa + 1) * sizeof(double)))) return rc;
+  double* dF = F ? ctx->d_big : nullptr;
+  double* dD = detF ? ctx->d_big + nF : nullptr;
+  double* dP = pk2 ? ctx->d_big + nF + nD : nullptr;
+  double* dE = Eavg ? ctx->d_big + nF + nD + nP : nullptr;
+  LAUNCH(k_gp_outputs, cdiv(ctx->nE, 64), 64, ctx->stream, elem_args(ctx, 0, ctx->nE, 1), ctx->ref_of, dF, dD, dP, dE);
+  if (F) CK(cudaMemcpyAsync(F, dF, nF * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (detF) CK(cudaMemcpyAsync(detF, dD, nD * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (pk2) CK(cudaMemcpyAsync(pk2, dP, nP * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (Eavg) CK(cudaMemcpyAsync(Eavg, dE, nEa * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return FTB200_OK;
+}
+
+// ----------------------------------------------------------------------------------- resident path
+int ftb200_set_state(ftb200_ctx* ctx, const double* displacements, const double* velocities, const double* accelerations,
+                     const int* boundary) {
+  if (!ctx || !ctx->shape_ok) return fail(ctx, FTB200_ERR_INPUT, "set_state: setup incomplete");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if (displacements && (rc = upload_aos(ctx, displacements, ctx->u))) return rc;
+  if (velocities) { CK(cudaStreamSynchronize(ctx->stream)); if ((rc = upload_aos(ctx, velocities, ctx->v))) return rc; }
+  if (accelerations) { CK(cudaStreamSynchronize(ctx->stream)); if ((rc = upload_aos(ctx, accelerations, ctx->a))) return rc; }
+  if (boundary && (rc = upload_boundary(ctx, boundary))) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return FTB200_OK;
+}
+
+int ftb200_get_state(ftb200_ctx* ctx, double* displacements, double* velocities, double* accelerations, int* boundary,
+                     double* fi, double* f_net) {
+  if (!ctx || !ctx->shape_ok) return fail(ctx, FTB200_ERR_INPUT, "get_state: setup incomplete");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if (fi || f_net) {  // lazily rebuilt from the element forces of the last evaluation
+    const NodeArgs N = node_args(ctx, ctx->halo_recv_cur);
+    LAUNCH(k_gather_force, ctx->node_blocks, NODE_BLOCK, ctx->stream, N, ctx->fnet[0], ctx->fnet[1], ctx->fnet[2]);
+  }
+  double* const* src[5] = {ctx->u, ctx->v, ctx->a, ctx->fi, ctx->fnet};
+  double* dst[5] = {displacements, velocities, accelerations, fi, f_net};
+  for (int i = 0; i < 5; ++i)
+    if (dst[i]) {
+      if ((rc = download_aos(ctx, const_cast<double**>(src[i]), dst[i], 0))) return rc;
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+  if (boundary) {
+    LAUNCH(k_flags_to_boundary, cdiv(ctx->nN, 256), 256, ctx->stream, ctx->flags, ctx->d_istage, ctx->nN);
+    CK(cudaMemcpyAsync(boundary, ctx->d_istage, 3 * (size_t)ctx->nN * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return FTB200_OK;
+}
+
+int ftb200_set_bc(ftb200_ctx* ctx, const int* bc_kind, const double bc_rate[4]) {
+  if (!ctx || !ctx->shape_ok || !bc_kind || !bc_rate) return fail(ctx, FTB200_ERR_INPUT, "set_bc: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n3 = 3 * (size_t)ctx->nN;
+  for (size_t i = 0; i < n3; ++i)
+    if (bc_kind[i] < 0 || bc_kind[i] > 3) return fail(ctx, FTB200_ERR_INPUT, "set_bc: bc_kind[%zu] = %d not in 0..3", i, bc_kind[i]);
+  CK(cudaMemcpyAsync(ctx->d_istage, bc_kind, n3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(k_set_bc_kinds, cdiv(ctx->nN, 256), 256, ctx->stream, ctx->d_istage, ctx->flags, ctx->nN);
+  CK(cudaMemcpyAsync(&ctx->sc->bc_rate[0], bc_rate, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->bc_ok = true;
+  return FTB200_OK;
+}
+
+int ftb200_record_history(ftb200_ctx* ctx, long long capacity) {
+  if (!ctx || !ctx->shape_ok || capacity < 0) return fail(ctx, FTB200_ERR_INPUT, "record_history: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  dfree(ctx->dthist); dfree(ctx->ehist);
+  ctx->hist_cap = capacity;
+  if (capacity > 0) {
+    int rc;
+    if ((rc = dalloc(ctx, &ctx->dthist, (size_t)capacity)) || (rc = dalloc(ctx, &ctx->ehist, 4 * (size_t)capacity))) return rc;
+    CK(cudaMemset(ctx->dthist, 0, capacity * sizeof(double)));
+    CK(cudaMemset(ctx->ehist, 0, 4 * capacity * sizeof(double)));
+  }
+  CK(cudaMemcpy(&ctx->sc->hist_cap, &capacity, sizeof(long long), cudaMemcpyHostToDevice));
+  if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+  return FTB200_OK;
+}
+
+int ftb200_get_history(ftb200_ctx* ctx, long long first, long long count, double* dt_hist, double* energy_hist4) {
+  if (!ctx || first < 0 || count < 0 || first + count > ctx->hist_cap) return fail(ctx, FTB200_ERR_INPUT, "get_history: range");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (dt_hist && count) CK(cudaMemcpy(dt_hist, ctx->dthist + first, count * sizeof(double), cudaMemcpyDeviceToHost));
+  if (energy_hist4 && count) CK(cudaMemcpy(energy_hist4, ctx->ehist + 4 * first, 4 * count * sizeof(double), cudaMemcpyDeviceToHost));
+  return FTB200_OK;
+}
+
+int ftb200_explicit_begin(ftb200_ctx* ctx, double Time0, double reduction, double failure_dt, int energy_every) {
+  if (!ctx || !ctx->shape_ok) return fail(ctx, FTB200_ERR_INPUT, "explicit_begin: setup incomplete");
+  if (energy_every != 0 && energy_every != 1)
+    return fail(ctx, FTB200_ERR_INPUT, "explicit_begin: energy_every must be 0 or 1 (the running sums need every step)");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  ctx->energy = energy_every;
+  if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+  // scalars: keep bc_rate / hist_cap, reset the rest
+  DevScalars h;
+  CK(cudaMemcpy(&h, ctx->sc, sizeof(h), cudaMemcpyDeviceToHost));
+  double rate[4];
+  memcpy(rate, h.bc_rate, sizeof(rate));
+  memset(&h, 0, sizeof(h));
+  memcpy(h.bc_rate, rate, sizeof(rate));
+  h.hist_cap = ctx->hist_cap;
+  h.Time = Time0; h.tMax = 1e300; h.reduction = reduction; h.failure_dt = failure_dt;
+  h.dtmin_bits = 0x7FF0000000000000ULL;
+  h.energy_every = energy_every;
+  CK(cudaMemcpyAsync(ctx->sc, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+  const int nb = cdiv(ctx->nN, 256);
+  // ApplyBoundaryConditions(Time0) (Benchmarking-Parallel.cpp:83)
+  LAUNCH(k_apply_bc, nb, 256, s, ctx->u[0], ctx->u[1], ctx->u[2], ctx->v[0], ctx->v[1], ctx->v[2], ctx->a[0], ctx->a[1],
+         ctx->a[2], ctx->flags, ctx->sc, Time0, ctx->nN);
+  LAUNCH(k_eflag, cdiv(ctx->nE, 256), 256, s, ctx->conn, ctx->flags, ctx->eflag, ctx->nE);
+  // dt = reduction * StableTimeStep() (:86) -- before GetForce because material 5 reads dt
+  launch_elem<false, true>(ctx, s, 0, ctx->nE, 1);
+  LAUNCH((k_adv<true>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, Time0, ctx->dthist);
+  // GetForce(); CalculateAccelerations() (:88-91)
+  launch_elem<true, false>(ctx, s, 0, ctx->nE, 1);
+  const NodeArgs N = node_args(ctx, nullptr);
+  LAUNCH((k_node<true, false, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+  int status = 0;
+  CK(cudaMemcpyAsync(&status, &ctx->sc->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  ctx->begun = true;
+  if (status & 1) return fail(ctx, FTB200_ERR_MATERIAL, "Unknown material type");
+  if (status & 16) return fail(ctx, FTB200_ERR_TIMESTEP, "Timestep too small");
+  return FTB200_OK;
+}
+
+static int build_graph(ftb200_ctx* ctx) {
+  if (ctx->graph && ctx->graph_energy == ctx->energy) return 0;
+  if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+  cudaGraph_t g = nullptr;
+  const long long before = ctx->launches;
+  CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  for (int i = 0; i < GRAPH_STEPS; ++i) launch_step(ctx, nullptr);
+  cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+  ctx->launches = before;  // captured, not launched
+  if (e != cudaSuccess) return fail(ctx, FTB200_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&ctx->graph, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) { ctx->graph = nullptr; return fail(ctx, FTB200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+  ctx->graph_energy = ctx->energy;
+  return 0;
+}
+
+int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
+  if (!ctx || !ctx->begun) return fail(ctx, FTB200_ERR_INPUT, "explicit_run: call explicit_begin first");
+  if (ctx->halo_count && ctx->nranks > 1)
+    return fail(ctx, FTB200_ERR_INPUT, "explicit_run: this rank has shared nodes; drive the loop with step_begin/step_end");
+  CK(cudaSetDevice(ctx->device));
+  if (steps <= 0) return FTB200_OK;
+  cudaStream_t s = ctx->stream;
+  LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
+  {
+    const NodeArgs N = node_args(ctx, nullptr);
+    if (ctx->energy) LAUNCH((k_node<false, true, false, true>), ctx->node_blocks, NODE_BLOCK, s, N);
+    else LAUNCH((k_node<false, true, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+  }
+  const int per_step = 3 + (ctx->energy ? 1 : 0);
+  long long left = steps;
+  const bool use_graph = !ctx->profile && steps >= GRAPH_STEPS;
+  if (use_graph) {
+    int rc = build_graph(ctx);
+    if (rc) return rc;
+  }
+  while (left > 0) {
+    if (use_graph && left >= GRAPH_STEPS) {
+      CK(cudaGraphLaunch(ctx->graph, s));
+      ctx->launches += (long long)per_step * GRAPH_STEPS;
+      left -= GRAPH_STEPS;
+    } else {
+      launch_step(ctx, nullptr);
+      left--;
+    }
+  }
+  CK(cudaGetLastError());
+  return FTB200_OK;
+}
+
+int ftb200_explicit_poll(ftb200_ctx* ctx, long long* steps_done, double* Time, double* dt, int* status_bits) {
+  if (!ctx || !ctx->begun) return fail(ctx, FTB200_ERR_INPUT, "explicit_poll: call explicit_begin first");
+  CK(cudaSetDevice(ctx->device));
+  DevScalars h;
+  CK(cudaMemcpyAsync(&h, ctx->sc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->profile) prof_collect(ctx);
+  if (steps_done) *steps_done = h.step;
+  if (Time) *Time = h.Time;
+  if (dt) *dt = h.ndt;
+  if (status_bits) *status_bits = h.status;
+  return FTB200_OK;
+}
+
+int ftb200_explicit_run(ftb200_ctx* ctx, double tMax, long long maxSteps, long long* steps_done, double* Time, double* dt) {
+  if (!ctx || !ctx->begun) return fail(ctx, FTB200_ERR_INPUT, "explicit_run: call explicit_begin first");
+  long long s0 = 0, s1 = 0;
+  double T = 0, d = 0;
+  int st = 0, rc;
+  if ((rc = ftb200_explicit_poll(ctx, &s0, &T, &d, &st))) return rc;
+  long long left = maxSteps;
+  s1 = s0;
+  while (left > 0 && T < tMax && !(st & 16)) {
+    const long long chunk = std::min<long long>(left, 200);
+    if ((rc = ftb200_explicit_run_async(ctx, tMax, chunk))) return rc;
+    long long s2;
+    if ((rc = ftb200_explicit_poll(ctx, &s2, &T, &d, &st))) return rc;
+    left -= chunk;
+    if (s2 == s1) break;
+    s1 = s2;
+  }
+  if (steps_done) *steps_done = s1 - s0;
+  if (Time) *Time = T;
+  if (dt) *dt = d;
+  if (st & 1) return fail(ctx, FTB200_ERR_MATERIAL, "Unknown material type");
+  if (st & 16) return fail(ctx, FTB200_ERR_TIMESTEP, "Timestep too small, dt below FailureTimeStep");
+  return FTB200_OK;
+}
+
+int ftb200_get_energy(ftb200_ctx* ctx, double out[4]) {
+  if (!ctx || !ctx->begun || !out) return fail(ctx, FTB200_ERR_INPUT, "get_energy: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  DevScalars h;
+  CK(cudaMemcpyAsync(&h, ctx->sc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  out[0] = h.Wint; out[1] = h.Wext; out[2] = h.WKE; out[3] = h.Etot;
+  return FTB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ halo
+int ftb200_halo_count(const ftb200_ctx* ctx) { return ctx ? ctx->halo_count : 0; }
+
+int ftb200_halo_pack(ftb200_ctx* ctx, int field, double* send_dev) {
+  if (!ctx || !ctx->shape_ok || !send_dev || (field != 0 && field != 1)) return fail(ctx, FTB200_ERR_INPUT, "halo_pack: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->halo_count) return FTB200_OK;
+  const double *x = field ? ctx->m : ctx->fi[0], *y = field ? ctx->m : ctx->fi[1], *z = field ? ctx->m : ctx->fi[2];
+  LAUNCH(k_halo_pack, cdiv(ctx->halo_count, 256), 256, ctx->stream, x, y, z, ctx->d_sendNodeIndex, send_dev, ctx->halo_count);
+  return FTB200_OK;
+}
+
+int ftb200_halo_add(ftb200_ctx* ctx, int field, const double* recv_dev) {
+  if (!ctx || !ctx->shape_ok || !recv_dev || (field != 0 && field != 1)) return fail(ctx, FTB200_ERR_INPUT, "halo_add: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->halo_count) return FTB200_OK;
+  if (field == 1) {
+    // mass: one value per node; the three received dofs are identical, add component 0
+    LAUNCH(k_halo_add, cdiv(ctx->nshared, 256), 256, ctx->stream, ctx->m, ctx->d_stage[2], ctx->d_stage[2] + ctx->nN,
+           ctx->halo_nodes, ctx->halo_off, ctx->halo_slot, recv_dev, ctx->nshared);
+  } else {
+    LAUNCH(k_halo_add, cdiv(ctx->nshared, 256), 256, ctx->stream, ctx->fi[0], ctx->fi[1], ctx->fi[2], ctx->halo_nodes,
+           ctx->halo_off, ctx->halo_slot, recv_dev, ctx->nshared);
+  }
+  return FTB200_OK;
+}
+
+int ftb200_step_begin(ftb200_ctx* ctx, double* send_dev, double** dtmin_dev) {
+  (void)send_dev; (void)dtmin_dev;
+  return fail(ctx, FTB200_ERR_INPUT, "step_begin: multi-GPU resident stepping not available in this build");
+}
+int ftb200_step_end(ftb200_ctx* ctx, const double* recv_dev) {
+  (void)recv_dev;
+  return fail(ctx, FTB200_ERR_INPUT, "step_end: multi-GPU resident stepping not available in this build");
+}
+int ftb200_p2p_export(ftb200_ctx* ctx, void* handle_out) {
+  (void)handle_out;
+  return fail(ctx, FTB200_ERR_INPUT, "p2p_export: not available in this build");
+}
+int ftb200_p2p_import(ftb200_ctx* ctx, const void* all_handles) {
+  (void)all_handles;
+  return fail(ctx, FTB200_ERR_INPUT, "p2p_import: not available in this build");
+}
+
+// ------------------------------------------------------------------------------------ measurement
+int ftb200_profile_enable(ftb200_ctx* ctx, int on) {
+  if (!ctx) return FTB200_ERR_INPUT;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->profile = on != 0;
+  ctx->prof_elem_ms = ctx->prof_node_ms = 0;
+  ctx->prof_elem_n = ctx->prof_node_n = 0;
+  ctx->prof.elem.clear(); ctx->prof.node.clear(); ctx->prof.used = 0;
+  return FTB200_OK;
+}
+int ftb200_profile_get(ftb200_ctx* ctx, double* elem_ms, double* node_ms, long long* elem_launches, long long* node_launches) {
+  if (!ctx) return FTB200_ERR_INPUT;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  prof_collect(ctx);
+  if (elem_ms) *elem_ms = ctx->prof_elem_n ? ctx->prof_elem_ms / ctx->prof_elem_n : 0.0;
+  if (node_ms) *node_ms = ctx->prof_node_n ? ctx->prof_node_ms / ctx->prof_node_n : 0.0;
+  if (elem_launches) *elem_launches = ctx->prof_elem_n;
+  if (node_launches) *node_launches = ctx->prof_node_n;
+  return FTB200_OK;
+}
+
+int ftb200_measure_peaks(ftb200_ctx* ctx, int reps, double* fp64_tflops, double* copy_gbs) {
+  if (!ctx) return FTB200_ERR_INPUT;
+  CK(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ctx->device));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  cudaStream_t s = ctx->stream;
+  if (reps < 1) reps = 1;
+  if (fp64_tflops) {
+    double* d = nullptr;
+    CK(cudaMalloc((void**)&d, 64));
+    const int iters = 1 << 14, blocks = prop.multiProcessorCount * 8;
+    double best = 0;
+    for (int r = 0; r < reps + 1; ++r) {
+      CK(cudaEventRecord(e0, s));
+      LAUNCH(k_dfma_peak, blocks, 256, s, d, iters, 1.0);
+      CK(cudaEventRecord(e1, s));
+      CK(cudaEventSynchronize(e1));
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double tf = 2.0 * 8.0 * iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+      if (r > 0 && tf > best) best = tf;
+    }
+    cudaFree(d);
+    *fp64_tflops = best;
+  }
+  if (copy_gbs) {
+    const size_t n2 = (size_t)1 << 26;  // 64 Mi double2 = 1 GiB per buffer, far larger than L2
+    double2 *a = nullptr, *b = nullptr;
+    CK(cudaMalloc((void**)&a, n2 * sizeof(double2)));
+    CK(cudaMalloc((void**)&b, n2 * sizeof(double2)));
+    CK(cudaMemsetAsync(a, 0, n2 * sizeof(double2), s));
+    double best = 0;
+    for (int r = 0; r < reps + 1; ++r) {
+      CK(cudaEventRecord(e0, s));
+      LAUNCH(k_copy_peak, prop.multiProcessorCount * 16, 256, s, a, b, n2);
+      CK(cudaEventRecord(e1, s));
+      CK(cudaEventSynchronize(e1));
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double gbs = 2.0 * n2 * sizeof(double2) / (ms * 1e-3) / 1e9;
+      if (r > 0 && gbs > best) best = gbs;
+    }
+    cudaFree(a);
+    cudaFree(b);
+    *copy_gbs = best;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return FTB200_OK;
+}
+
+}  // extern "C"

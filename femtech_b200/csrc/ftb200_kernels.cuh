@@ -1,0 +1,741 @@
+// ftb200_kernels.cuh -- CUDA kernels of the FemTech explicit step for sm_100a.
+//
+// Data layout in HBM (all fp64 / int32, SoA, 256-byte aligned planes):
+//   nodal   X,u,v,a,fi,du : 3 planes of nNodes doubles each;  m : nNodes;  flags : uint16 per node
+//   element conn          : 8 planes of nElements int32 (plane k = k-th C3D8 node of every element)
+//           pid           : nElements int32;  eflag : uint8 (1 = every node fully constrained)
+//           felem         : 24 planes of nElements doubles (plane 3k+c = force on node k, component c)
+//           hist          : 3 arrays x 6 components x 8 Gauss points planes of nElements doubles
+//   CSR     node_off[nNodes+1], node_ent[8 nElements] = element*8+slot, ascending REFERENCE element id
+// One thread per element (K_elem) / per node (K_node): every global access of a warp is a run of
+// consecutive 8-byte words, gathers excepted.
+//
+// Kernels (SURVEY.md section 2.1 naming):
+//   k_elem   K1  fused gather -> F -> material -> B^T sigma element forces (+ K6 per-element dt, block min)
+//   k_node   K2+K5  deterministic CSR gather of f_int + a = f/m + both velocity kicks + drift + BC (+K8 energy partials)
+//   k_adv        1-thread scalar update: Time, dt = reduction*min, Prony factors, loop control
+//   k_energy K8  fixed-order reduction of the energy partials
+//   k_mass_* K7  lumped mass
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hex8_element.cuh"
+
+namespace ftb {
+
+// flags word per node: bit c (0..2) = boundary[3n+c]; bits 4+2c..5+2c = BC kind of dof c (0 = none);
+// bit 12 = node is shared with another rank; bit 13 = energy of this node is owned by a lower rank
+#define FTB_FLAG_SHARED 0x1000
+#define FTB_FLAG_NOTOWNED 0x2000
+
+struct DevScalars {
+  double Time;                      // end time of the last finished step
+  double t_n, t_np1, t_half, dt;    // step being finished
+  double nt_n, nt_np1, nt_half, ndt;  // next step
+  double tMax, reduction, failure_dt;
+  unsigned long long dtmin_bits;    // atomicMin target: bit pattern of a non-negative double
+  long long step;                   // finished steps since explicit_begin
+  long long steps_left;             // budget of the current run call
+  int last;                         // the step being finished is the last of this run
+  int done;                         // nothing left to do in this run
+  int active;                       // this loop iteration is live (set by k_adv)
+  int status;                       // OR of element status bits | 16 = dt below FailureTimeStep
+  double Wint, Wext, WKE, Etot;     // CheckEnergy running sums (CheckEnergy.cpp:4-5,60-64)
+  double bc_rate[4];
+  long long hist_cap;               // capacity of dt/energy history (steps)
+  int energy_every;
+  int pad;
+};
+
+__device__ __forceinline__ unsigned long long dt_to_bits(double v) {
+  // NaN is never selected by the reference (`dtElem < dtMin` is false); a negative dt would be
+  // selected and trip FailureTimeStep -> map it to 0.
+  if (!(v == v)) return 0x7FF0000000000000ULL;
+  if (v < 0.0) return 0ULL;
+  return (unsigned long long)__double_as_longlong(v);
+}
+
+struct DevHist {
+  double* base;  // [3][6][8][E]
+  size_t E;
+  size_t e;
+  __device__ __forceinline__ void load(int gp, GpHistory& g) const {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      g.h1[i] = base[((size_t)(0 * 6 + i) * 8 + gp) * E + e];
+      g.h2[i] = base[((size_t)(1 * 6 + i) * 8 + gp) * E + e];
+      g.s0[i] = base[((size_t)(2 * 6 + i) * 8 + gp) * E + e];
+    }
+  }
+  __device__ __forceinline__ void store(int gp, const GpHistory& g) const {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      base[((size_t)(0 * 6 + i) * 8 + gp) * E + e] = g.h1[i];
+      base[((size_t)(1 * 6 + i) * 8 + gp) * E + e] = g.h2[i];
+      base[((size_t)(2 * 6 + i) * 8 + gp) * E + e] = g.s0[i];
+    }
+  }
+};
+
+struct ElemArgs {
+  const double* X[3];
+  const double* u[3];
+  const int* conn;  // 8 planes
+  const int* pid;
+  const uint8_t* eflag;
+  const double* mp;  // per-part parameter blocks
+  double* felem;     // 24 planes
+  double* hist;      // or nullptr
+  DevScalars* sc;
+  int nE;            // plane stride
+  int e0, e1;        // element range of this launch
+  int ignore_loop_flags;
+};
+
+constexpr int ELEM_BLOCK = 128;
+
+// K1 (+K6).  MATSEL >= 0: every element of the launch has that material (no switch).
+template <int MATSEL, bool WITH_FORCE, bool WITH_DT>
+__global__ void __launch_bounds__(ELEM_BLOCK) k_elem(const ElemArgs A) {
+  if (!A.ignore_loop_flags && (A.sc->last | A.sc->done)) return;
+  const int e = A.e0 + blockIdx.x * ELEM_BLOCK + threadIdx.x;
+  double dte = 1e300;
+  int status = 0;
+  if (e < A.e1) {
+    const size_t E = (size_t)A.nE;
+    int nd[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) nd[k] = __ldg(A.conn + (size_t)k * E + e);
+    double X[8][3], U[8][3];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        X[k][c] = __ldg(A.X[c] + nd[k]);
+        U[k][c] = __ldg(A.u[c] + nd[k]);
+      }
+    const int p = __ldg(A.pid + e);
+    const double* mp = A.mp + (size_t)p * FTB_MP_STRIDE;
+    const int mat = (MATSEL >= 0) ? MATSEL : (int)mp[MP_MATID];
+    if (WITH_FORCE) {
+      double fe[8][3];
+      DevHist h{A.hist, E, (size_t)e};
+      double d;
+      status = hex8_element<MATSEL, WITH_DT>(X, U, mat, mp, true, h, NoOutput(), fe, &d);
+      if (WITH_DT) dte = d;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) A.felem[(size_t)(3 * k + c) * E + e] = fe[k][c];
+    } else {
+      // dt only (legacy StableTimeStep, and the pre-pass of explicit_begin)
+      double xm[7][3];
+      double n[8], g[7];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) n[k] = X[k][c] + U[k][c];
+        hex_modes(n, g);
+#pragma unroll
+        for (int m = 0; m < 7; ++m) xm[m][c] = g[m];
+      }
+      dte = hex_char_length(xm) / mp[MP_CE];
+    }
+    if (WITH_DT && __ldg(A.eflag + e)) dte = 1e300;  // element skipped, StableTimeStep.cpp:13-19
+  }
+  if (WITH_DT) {
+    unsigned long long b = dt_to_bits(dte);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o);
+      b = t < b ? t : b;
+    }
+    __shared__ unsigned long long sb[ELEM_BLOCK / 32];
+    if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int w = 1; w < ELEM_BLOCK / 32; ++w) b = sb[w] < b ? sb[w] : b;
+      atomicMin(&A.sc->dtmin_bits, b);  // min is order independent: deterministic
+    }
+  }
+  if (status) atomicOr(&A.sc->status, status);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct NodeArgs {
+  double* u[3];
+  double* v[3];
+  double* a[3];
+  double* fi[3];        // written when store_fi
+  double* du[3];        // energy only
+  const double* fe[3];  // nullptr planes when the external force is identically zero
+  const double* m;
+  uint16_t* flags;
+  const double* felem;
+  const int* node_off;
+  const int* node_ent;
+  const double* halo_recv;   // device recv window or nullptr
+  const int* halo_off;       // per shared node CSR into halo_slot (ascending neighbour order)
+  const int* halo_slot;
+  const int* halo_node_idx;  // node -> index into halo_off (or -1), nullptr when no halo
+  double* epart;             // [3][gridDim.x] energy partials
+  DevScalars* sc;
+  int nN, nE;
+  int store_fi;
+};
+
+constexpr int NODE_BLOCK = 256;
+
+// K2 + K5 (+ K8 partials).  FINISH: gather fi, a = (fe-fi)/m, second kick.  START: first kick of the
+// next step, drift, boundary condition.  KICK2 = false for step 0 (accelerations only).
+template <bool FINISH, bool START, bool KICK2, bool ENERGY>
+__global__ void __launch_bounds__(NODE_BLOCK) k_node(const NodeArgs A) {
+  const DevScalars* sc = A.sc;
+  if (FINISH && !sc->active) return;
+  if (!FINISH && sc->done) return;
+  const bool do_start = START && !(FINISH && sc->last);
+  const int n = blockIdx.x * NODE_BLOCK + threadIdx.x;
+  double wke = 0.0, wint = 0.0, wext = 0.0;
+  if (n < A.nN) {
+    const unsigned fl = A.flags[n];
+    double uu[3], vv[3], aa[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      uu[c] = A.u[c][n];
+      vv[c] = A.v[c][n];
+      aa[c] = A.a[c][n];
+    }
+    if (FINISH) {
+      // deterministic assembly: ascending element id (GetForce_3D.cpp:15,39-44)
+      double f[3] = {0.0, 0.0, 0.0};
+      const int j0 = A.node_off[n], j1 = A.node_off[n + 1];
+      const size_t E = (size_t)A.nE;
+      for (int j = j0; j < j1; ++j) {
+        const int ent = __ldg(A.node_ent + j);
+        const size_t e = (size_t)(ent >> 3);
+        const int s = ent & 7;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) f[c] += __ldg(A.felem + (size_t)(3 * s + c) * E + e);
+      }
+      if (A.halo_node_idx) {  // shared node: add the neighbours' partial sums, ascending neighbour (:92-97)
+        const int h = A.halo_node_idx[n];
+        if (h >= 0)
+          for (int j = A.halo_off[h]; j < A.halo_off[h + 1]; ++j) {
+            const int slot = A.halo_slot[j];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) f[c] += A.halo_recv[3 * (size_t)slot + c];
+          }
+      }
+      const double m = A.m[n];
+      const double dt1 = sc->t_half - sc->t_n, dt2 = sc->t_np1 - sc->t_half;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const bool b = (fl >> c) & 1u;
+        const double fext = A.fe[c] ? A.fe[c][n] : 0.0;
+        const double fnet = fext - f[c];  // GetForce_3D.cpp:11,49-51
+        const double a_old = aa[c];
+        if (!b) aa[c] = fnet / m;  // CalculateAcclerations.cpp:7-11
+        if (KICK2) {
+          if (!b) {
+            const double vhalf = vv[c] + dt1 * a_old;  // Benchmarking-Parallel.cpp:115-122
+            vv[c] = vhalf + dt2 * aa[c];               // :146-151
+          }
+          if (ENERGY && !(fl & FTB_FLAG_NOTOWNED)) {   // CheckEnergy.cpp:19-52
+            const double dd = A.du[c][n];
+            const double fprev = A.fi[c][n];
+            wke += m * vv[c] * vv[c];
+            if (b) wext += dd * (fprev + f[c] + m * (aa[c] + a_old));
+            wint += dd * (fprev + f[c]);
+            wext += dd * (fext + fext);  // fe_prev == fe: the reference never updates fe
+          }
+        }
+        if (A.store_fi) A.fi[c][n] = f[c];
+      }
+    }
+    if (do_start) {
+      const double dt1 = sc->nt_half - sc->nt_n, dtn = sc->ndt, T = sc->nt_np1;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const bool b = (fl >> c) & 1u;
+        const unsigned kind = (fl >> (4 + 2 * c)) & 3u;
+        const double u_old = uu[c];
+        if (!b) {
+          const double vhalf = vv[c] + dt1 * aa[c];
+          uu[c] = u_old + dtn * vhalf;  // :131-135
+        }
+        if (kind) {  // ApplyBoundaryConditions, :184-244
+          const double r = sc->bc_rate[kind];
+          uu[c] = T * r;
+          vv[c] = r;
+          aa[c] = 0.0;
+        }
+        if (ENERGY) A.du[c][n] = uu[c] - u_old;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (do_start) A.u[c][n] = uu[c];
+      A.v[c][n] = vv[c];
+      A.a[c][n] = aa[c];
+    }
+  }
+  if (FINISH && KICK2 && ENERGY) {
+    // fixed-shape tree: warp shuffle, then shared memory, one partial per block
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      wke += __shfl_down_sync(0xffffffffu, wke, o);
+      wint += __shfl_down_sync(0xffffffffu, wint, o);
+      wext += __shfl_down_sync(0xffffffffu, wext, o);
+    }
+    __shared__ double sw[3][NODE_BLOCK / 32];
+    if ((threadIdx.x & 31) == 0) {
+      sw[0][threadIdx.x >> 5] = wke;
+      sw[1][threadIdx.x >> 5] = wint;
+      sw[2][threadIdx.x >> 5] = wext;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+      for (int w = 0; w < NODE_BLOCK / 32; ++w) {
+        s0 += sw[0][w];
+        s1 += sw[1][w];
+        s2 += sw[2][w];
+      }
+      A.epart[blockIdx.x] = s0;
+      A.epart[gridDim.x + blockIdx.x] = s1;
+      A.epart[2 * gridDim.x + blockIdx.x] = s2;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scalar bookkeeping of the time loop (Benchmarking-Parallel.cpp:106-112,168 and
+// StableTimeStep.cpp:33-38).  One thread block; thread p < nPID refreshes the Prony factors of part p
+// for the next dt (HGOIsotropicViscoelastic.cpp:126-131).
+template <bool INIT>
+__global__ void k_adv(DevScalars* sc, double* mp, int nPID, double Time0, double* dt_hist) {
+  __shared__ double s_ndt;
+  __shared__ int s_live;
+  if (threadIdx.x == 0) {
+    int live = 1;
+    if (!INIT) {
+      if (sc->done) live = 0;
+      else if (sc->last) { sc->done = 1; live = 0; }
+    }
+    sc->active = live;
+    if (live) {
+      double dtmin = __longlong_as_double((long long)sc->dtmin_bits);
+      if (dtmin > 1e20) dtmin = 1e20;  // `huge`, GlobalVariables.h:16
+      sc->dtmin_bits = 0x7FF0000000000000ULL;
+      if (INIT) {
+        sc->Time = Time0;
+        sc->t_n = sc->t_np1 = sc->t_half = Time0;
+        sc->dt = 0.0;
+      } else {
+        sc->t_n = sc->nt_n; sc->t_np1 = sc->nt_np1; sc->t_half = sc->nt_half; sc->dt = sc->ndt;
+        sc->Time = sc->t_np1;
+        if (dt_hist && sc->step < sc->hist_cap) dt_hist[sc->step] = sc->dt;
+        sc->step += 1;
+        sc->steps_left -= 1;
+      }
+      if (dtmin < sc->failure_dt) { sc->status |= 16; sc->last = 1; }  // TerminateFemTech(19)
+      const double ndt = sc->reduction * dtmin;
+      sc->ndt = ndt;
+      sc->nt_n = sc->Time;
+      sc->nt_np1 = sc->Time + ndt;                    // t_np1 = Time + dt
+      sc->nt_half = 0.5 * (sc->nt_np1 + sc->nt_n);    // t_nphalf = 0.5*(t_np1 + t_n)
+      if (!INIT && (!(sc->Time < sc->tMax) || sc->steps_left <= 0)) sc->last = 1;
+      s_ndt = ndt;
+    }
+    s_live = live;
+  }
+  __syncthreads();
+  if (!s_live) return;
+  for (int p = threadIdx.x; p < nPID; p += blockDim.x) {
+    double* q = mp + (size_t)p * FTB_MP_STRIDE;
+    if ((int)q[MP_MATID] == 5) {
+      const double rt1 = s_ndt / q[MP_T1], rt2 = s_ndt / q[MP_T2];
+      const double c11 = exp(-rt1), c12 = exp(-rt2);
+      q[MP_C11] = c11;
+      q[MP_C12] = c12;
+      q[MP_C21] = q[MP_G1] * (1 - c11) / rt1;
+      q[MP_C22] = q[MP_G2] * (1 - c12) / rt2;
+    }
+  }
+}
+
+// Prony factors for an explicit dt (legacy GetForce: the driver's global dt)
+__global__ void k_prony(double* mp, int nPID, double dt) {
+  for (int p = threadIdx.x; p < nPID; p += blockDim.x) {
+    double* q = mp + (size_t)p * FTB_MP_STRIDE;
+    if ((int)q[MP_MATID] == 5) {
+      const double rt1 = dt / q[MP_T1], rt2 = dt / q[MP_T2];
+      const double c11 = exp(-rt1), c12 = exp(-rt2);
+      q[MP_C11] = c11;
+      q[MP_C12] = c12;
+      q[MP_C21] = q[MP_G1] * (1 - c11) / rt1;
+      q[MP_C22] = q[MP_G2] * (1 - c12) / rt2;
+    }
+  }
+}
+
+__global__ void k_begin_run(DevScalars* sc, double tMax, long long steps) {
+  sc->tMax = tMax;
+  sc->steps_left = steps;
+  sc->last = 0;
+  sc->active = 0;
+  sc->done = (!(sc->Time < tMax) || steps <= 0 || (sc->status & 16)) ? 1 : 0;
+}
+
+// K8: fixed-order reduction of the per-block partials, running sums as in CheckEnergy.cpp:60-64
+__global__ void k_energy(DevScalars* sc, const double* epart, int nblocks, double* ehist) {
+  if (!sc->active) return;
+  __shared__ double sh[3][256];
+  double s[3] = {0, 0, 0};
+  for (int i = threadIdx.x; i < nblocks; i += 256) {
+    s[0] += epart[i];
+    s[1] += epart[nblocks + i];
+    s[2] += epart[2 * nblocks + i];
+  }
+  sh[0][threadIdx.x] = s[0]; sh[1][threadIdx.x] = s[1]; sh[2][threadIdx.x] = s[2];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+      sh[2][threadIdx.x] += sh[2][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double WKE = 0.5 * sh[0][0];
+    sc->Wint += 0.5 * sh[1][0];
+    sc->Wext += 0.5 * sh[2][0];
+    sc->WKE = WKE;
+    sc->Etot = fabs(WKE + sc->Wint - sc->Wext);
+    const long long k = sc->step - 1;
+    if (ehist && k >= 0 && k < sc->hist_cap) {
+      ehist[4 * k + 0] = sc->Wint; ehist[4 * k + 1] = sc->Wext; ehist[4 * k + 2] = WKE; ehist[4 * k + 3] = sc->Etot;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout conversion at the API boundary (host arrays are AoS xyz, GlobalVariables.h)
+__global__ void k_aos_to_soa(const double* __restrict__ aos, double* x, double* y, double* z, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { x[i] = aos[3 * (size_t)i]; y[i] = aos[3 * (size_t)i + 1]; z[i] = aos[3 * (size_t)i + 2]; }
+}
+__global__ void k_soa_to_aos(const double* __restrict__ x, const double* __restrict__ y,
+                             const double* __restrict__ z, double* aos, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { aos[3 * (size_t)i] = x[i]; aos[3 * (size_t)i + 1] = y[i]; aos[3 * (size_t)i + 2] = z[i]; }
+}
+__global__ void k_boundary_to_flags(const int* __restrict__ boundary, uint16_t* flags, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    unsigned f = flags[i] & ~7u;
+    f |= (boundary[3 * (size_t)i] ? 1u : 0u) | (boundary[3 * (size_t)i + 1] ? 2u : 0u) | (boundary[3 * (size_t)i + 2] ? 4u : 0u);
+    flags[i] = (uint16_t)f;
+  }
+}
+__global__ void k_flags_to_boundary(const uint16_t* __restrict__ flags, int* boundary, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const unsigned f = flags[i];
+    boundary[3 * (size_t)i] = f & 1u; boundary[3 * (size_t)i + 1] = (f >> 1) & 1u; boundary[3 * (size_t)i + 2] = (f >> 2) & 1u;
+  }
+}
+__global__ void k_set_bc_kinds(const int* __restrict__ kind, uint16_t* flags, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    unsigned f = flags[i] & ~0x3F0u;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const unsigned k = (unsigned)kind[3 * (size_t)i + c] & 3u;
+      f |= k << (4 + 2 * c);
+    }
+    flags[i] = (uint16_t)f;
+  }
+}
+// ApplyBoundaryConditions at a given Time (Benchmarking-Parallel.cpp:184-244)
+__global__ void k_apply_bc(double* ux, double* uy, double* uz, double* vx, double* vy, double* vz, double* ax,
+                           double* ay, double* az, uint16_t* flags, const DevScalars* sc, double Time, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned f = flags[i];
+  double* U[3] = {ux, uy, uz};
+  double* V[3] = {vx, vy, vz};
+  double* Ac[3] = {ax, ay, az};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const unsigned k = (f >> (4 + 2 * c)) & 3u;
+    if (k) {
+      const double r = sc->bc_rate[k];
+      f |= 1u << c;
+      U[c][i] = Time * r;
+      V[c][i] = r;
+      Ac[c][i] = 0.0;
+    }
+  }
+  flags[i] = (uint16_t)f;
+}
+// element is skipped by StableTimeStep when every node is constrained in x, y and z (:13-19)
+__global__ void k_eflag(const int* __restrict__ conn, const uint16_t* __restrict__ flags, uint8_t* eflag, int nE) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nE) return;
+  bool rigid = true;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) rigid = rigid && ((flags[conn[(size_t)k * nE + e]] & 7u) == 7u);
+  eflag[e] = rigid ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// legacy-path node kernels
+// fi = CSR gather (+ optional halo), f_net = fe - fi  (GetForce_3D.cpp:39-51)
+__global__ void k_gather_force(const NodeArgs A, double* fnx, double* fny, double* fnz) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= A.nN) return;
+  double f[3] = {0.0, 0.0, 0.0};
+  const size_t E = (size_t)A.nE;
+  for (int j = A.node_off[n]; j < A.node_off[n + 1]; ++j) {
+    const int ent = A.node_ent[j];
+    const size_t e = (size_t)(ent >> 3);
+    const int s = ent & 7;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) f[c] += A.felem[(size_t)(3 * s + c) * E + e];
+  }
+  if (A.halo_node_idx && A.halo_recv) {
+    const int h = A.halo_node_idx[n];
+    if (h >= 0)
+      for (int j = A.halo_off[h]; j < A.halo_off[h + 1]; ++j) {
+        const int slot = A.halo_slot[j];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) f[c] += A.halo_recv[3 * (size_t)slot + c];
+      }
+  }
+  double* fn[3] = {fnx, fny, fnz};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    A.fi[c][n] = f[c];
+    fn[c][n] = (A.fe[c] ? A.fe[c][n] : 0.0) - f[c];
+  }
+}
+__global__ void k_accel(const double* fnx, const double* fny, const double* fnz, const double* m,
+                        const uint16_t* flags, double* ax, double* ay, double* az, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned f = flags[i];
+  const double mm = m[i];
+  if (!(f & 1u)) ax[i] = fnx[i] / mm;
+  if (!(f & 2u)) ay[i] = fny[i] / mm;
+  if (!(f & 4u)) az[i] = fnz[i] / mm;
+}
+// masked merge on the way out: host accelerations keep their value on boundary dofs
+__global__ void k_merge_free(const double* __restrict__ src_aos, double* dst_aos, const int* __restrict__ boundary, int ndof) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ndof && !boundary[i]) dst_aos[i] = src_aos[i];
+}
+
+// K7: lumped mass.  Element part writes me[8 planes]; the gather sums in ascending element order
+// (Mass3D.cpp:127-157).  detmin: smallest reference Jacobian determinant (as ordered bits).
+__global__ void k_mass_elem(const ElemArgs A, double* me, unsigned long long* detmin_bits, int* nonpos) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= A.nE) return;
+  const size_t E = (size_t)A.nE;
+  double X[8][3];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int nd = A.conn[(size_t)k * E + e];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) X[k][c] = A.X[c][nd];
+  }
+  const double rho = A.mp[(size_t)A.pid[e] * FTB_MP_STRIDE + MP_RHO];
+  double m8[8];
+  const double dmin = hex8_lumped_mass(X, rho, m8);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) me[(size_t)k * E + e] = m8[k];
+  if (!(dmin > 0.0)) atomicAdd(nonpos, 1);
+  else atomicMin(detmin_bits, (unsigned long long)__double_as_longlong(dmin));
+}
+__global__ void k_mass_gather(const double* me, const int* node_off, const int* node_ent, double* m, int nN, int nE) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nN) return;
+  double s = 0.0;
+  for (int j = node_off[n]; j < node_off[n + 1]; ++j) {
+    const int ent = node_ent[j];
+    s += me[(size_t)(ent & 7) * nE + (ent >> 3)];
+  }
+  m[n] = s;
+}
+
+// halo pack / add (GetForce_3D.cpp:56-61,92-97; Mass3D.cpp:79-85,116-121)
+__global__ void k_halo_pack(const double* fx, const double* fy, const double* fz, const int* sendNodeIndex,
+                            double* send, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int n = sendNodeIndex[i];
+  send[3 * (size_t)i] = fx[n];
+  send[3 * (size_t)i + 1] = fy[n];
+  send[3 * (size_t)i + 2] = fz[n];
+}
+// one thread per shared node; its slots are visited in ascending neighbour order
+__global__ void k_halo_add(double* fx, double* fy, double* fz, const int* halo_nodes, const int* halo_off,
+                           const int* halo_slot, const double* recv, int nshared) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= nshared) return;
+  const int n = halo_nodes[h];
+  double f0 = fx[n], f1 = fy[n], f2 = fz[n];
+  for (int j = halo_off[h]; j < halo_off[h + 1]; ++j) {
+    const int s = halo_slot[j];
+    f0 += recv[3 * (size_t)s];
+    f1 += recv[3 * (size_t)s + 1];
+    f2 += recv[3 * (size_t)s + 2];
+  }
+  fx[n] = f0; fy[n] = f1; fz[n] = f2;
+}
+// partial internal force of the shared nodes only (boundary elements have been computed)
+__global__ void k_gather_shared(const double* felem, const int* node_off, const int* node_ent, const int* halo_nodes,
+                                double* fx, double* fy, double* fz, int nshared, int nE) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= nshared) return;
+  const int n = halo_nodes[h];
+  double f[3] = {0, 0, 0};
+  for (int j = node_off[n]; j < node_off[n + 1]; ++j) {
+    const int ent = node_ent[j];
+    const size_t e = (size_t)(ent >> 3);
+    const int s = ent & 7;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) f[c] += felem[(size_t)(3 * s + c) * nE + e];
+  }
+  fx[n] = f[0]; fy[n] = f[1]; fz[n] = f[2];
+}
+
+// Gauss-point outputs in the reference's layouts (lazy; never on the hot path)
+struct OutSink {
+  static constexpr bool enabled = true;
+  double *F, *detF, *pk2;
+  size_t e;
+  __device__ __forceinline__ void put(int gp, const double Fm[3][3], double J, const double Sv[6]) const {
+    if (F) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) F[72 * e + 9 * gp + 3 * j + i] = Fm[i][j];  // column-major, fptr[e]=72e
+    }
+    if (detF) detF[8 * e + gp] = J;
+    if (pk2) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) pk2[48 * e + 6 * gp + i] = Sv[i];
+    }
+  }
+};
+// ref_of[e]: reference (caller) element id of internal element e
+__global__ void k_gp_outputs(const ElemArgs A, const int* ref_of, double* F, double* detF, double* pk2, double* Eavg) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= A.nE) return;
+  const size_t E = (size_t)A.nE;
+  double X[8][3], U[8][3];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int nd = A.conn[(size_t)k * E + e];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { X[k][c] = A.X[c][nd]; U[k][c] = A.u[c][nd]; }
+  }
+  const double* mp = A.mp + (size_t)A.pid[e] * FTB_MP_STRIDE;
+  const int mat = (int)mp[MP_MATID];
+  const size_t re = (size_t)ref_of[e];
+  double Fl[72];
+  OutSink sink{Eavg ? Fl : F, detF, pk2, Eavg ? 0 : re};
+  if (Eavg) { sink.detF = nullptr; sink.pk2 = nullptr; }
+  DevHist h{A.hist, E, (size_t)e};
+  double fe[8][3], d;
+  hex8_element<-1, false>(X, U, mat, mp, false, h, sink, fe, &d);
+  if (Eavg) {
+    // CalculateStrain.cpp:77-97: E = sum_gp (0.5/8) F^T F - 0.5 I
+    double Em[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Em[i] = 0.0;
+    for (int gp = 0; gp < 8; ++gp)
+      for (int j = 0; j < 3; ++j)
+        for (int i = 0; i < 3; ++i) {
+          double s = 0.0;
+          for (int l = 0; l < 3; ++l) s += Fl[9 * gp + l + 3 * i] * Fl[9 * gp + l + 3 * j];
+          Em[i + 3 * j] += (0.5 / 8.0) * s;
+        }
+    Em[0] -= 0.5; Em[4] -= 0.5; Em[8] -= 0.5;
+    for (int i = 0; i < 9; ++i) Eavg[9 * re + i] = Em[i];
+    // second pass for the other outputs, if requested
+    if (F || detF || pk2) {
+      OutSink s2{F, detF, pk2, re};
+      hex8_element<-1, false>(X, U, mat, mp, false, h, s2, fe, &d);
+    }
+  }
+}
+
+// K8 for the legacy CheckEnergy call: all operands supplied by the host (AoS, staged on the device)
+__global__ void k_energy_legacy(const double* u, const double* up, const double* v, const double* a, const double* ap,
+                                const double* fi, const double* fip, const double* fe, const double* fep,
+                                const int* boundary, const double* m, const uint16_t* flags, double* epart, int nN) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  double wke = 0, wint = 0, wext = 0;
+  if (n < nN && !(flags[n] & FTB_FLAG_NOTOWNED)) {
+    const double mm = m[n];
+    for (int c = 0; c < 3; ++c) {
+      const size_t i = 3 * (size_t)n + c;
+      const double dd = u[i] - up[i];
+      wke += mm * v[i] * v[i];
+      if (boundary[i]) wext += dd * (fip[i] + fi[i] + mm * (a[i] + ap[i]));
+      wint += dd * (fip[i] + fi[i]);
+      wext += dd * ((fep ? fep[i] : 0.0) + (fe ? fe[i] : 0.0));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wke += __shfl_down_sync(0xffffffffu, wke, o);
+    wint += __shfl_down_sync(0xffffffffu, wint, o);
+    wext += __shfl_down_sync(0xffffffffu, wext, o);
+  }
+  __shared__ double sw[3][NODE_BLOCK / 32];
+  if ((threadIdx.x & 31) == 0) { sw[0][threadIdx.x >> 5] = wke; sw[1][threadIdx.x >> 5] = wint; sw[2][threadIdx.x >> 5] = wext; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int w = 0; w < NODE_BLOCK / 32; ++w) { s0 += sw[0][w]; s1 += sw[1][w]; s2 += sw[2][w]; }
+    epart[blockIdx.x] = s0; epart[gridDim.x + blockIdx.x] = s1; epart[2 * gridDim.x + blockIdx.x] = s2;
+  }
+}
+__global__ void k_sum3(const double* epart, int nblocks, double* out3) {
+  __shared__ double sh[3][256];
+  double s[3] = {0, 0, 0};
+  for (int i = threadIdx.x; i < nblocks; i += 256) { s[0] += epart[i]; s[1] += epart[nblocks + i]; s[2] += epart[2 * nblocks + i]; }
+  sh[0][threadIdx.x] = s[0]; sh[1][threadIdx.x] = s[1]; sh[2][threadIdx.x] = s[2];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; sh[2][threadIdx.x] += sh[2][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out3[0] = 0.5 * sh[0][0]; out3[1] = 0.5 * sh[1][0]; out3[2] = 0.5 * sh[2][0]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// roofline denominators
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 12345.678) out[0] = s;  // never true; keeps the chains alive
+}
+__global__ void __launch_bounds__(256) k_copy_peak(const double2* __restrict__ src, double2* __restrict__ dst, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
+}  // namespace ftb

@@ -1,0 +1,160 @@
+/*
+ * ftb200.h -- C-ABI of the B200-native FemTech explicit-dynamics hot path.
+ *
+ * This is the drop-in boundary: plain C, opaque handle, raw pointers and sizes,
+ * int status returns, no C++/torch types.  The C++ host layer that mirrors the
+ * reference's API (femtech_b200/csrc/femtech_host.cpp: ShapeFunctions(),
+ * AssembleLumpedMass(), GetForce(), CalculateAccelerations(), StableTimeStep(),
+ * CheckEnergy(), ExplicitDynamics() over the GlobalVariables.h arrays) and the
+ * Python mirror used by tests/bench (femtech_b200/solver.py) both sit on top of
+ * exactly these entry points.  Each one cites the reference interface it
+ * replaces (paths relative to the FemTech repository root).
+ *
+ * Conventions shared with the reference (include/GlobalVariables.h:18-127):
+ *   nodal arrays are AoS, xyz interleaved, double[3*nNodes]; boundary is
+ *   int[3*nNodes]; connectivity is int[8*nElements] of LOCAL node ids in C3D8
+ *   order; properties is double[9*nPID]; PK2 stress is Voigt [11,22,33,23,13,12]
+ *   per Gauss point, F is column-major 3x3 per Gauss point.
+ * Host pointers may be pageable or pinned.  All calls are synchronous with
+ * respect to the host unless stated otherwise, single-threaded per context.
+ *
+ * Return value: 0 on success, otherwise the reference's TerminateFemTech code
+ * for the same failure (src/io/InitFinalizeFemTech.cpp:82-86): 1 unknown
+ * material, 3 bad input, 12 allocation failure, 19 time step below
+ * FailureTimeStep; or FTB200_ERR_CUDA for a CUDA runtime error.  The message is
+ * available from ftb200_last_error().  There is no CPU fallback: without a
+ * usable CUDA device ftb200_create() fails.
+ */
+#ifndef FTB200_H
+#define FTB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FTB200_OK 0
+#define FTB200_ERR_MATERIAL 1
+#define FTB200_ERR_INPUT 3
+#define FTB200_ERR_ALLOC 12
+#define FTB200_ERR_TIMESTEP 19
+#define FTB200_ERR_CUDA 100
+
+typedef struct ftb200_ctx ftb200_ctx;
+
+/* ---- lifetime ----------------------------------------------------------- */
+/* One context per rank/GPU (reference: one MPI rank, InitFinalizeFemTech.cpp:49-73). */
+int ftb200_create(int rank, int nranks, int device, ftb200_ctx **out);
+int ftb200_destroy(ftb200_ctx *ctx);
+const char *ftb200_last_error(const ftb200_ctx *ctx);
+/* Run all kernels on the caller's CUDA stream (cudaStream_t as void*); NULL = own stream. */
+int ftb200_set_stream(ftb200_ctx *ctx, void *cuda_stream);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+long long ftb200_launch_count(const ftb200_ctx *ctx);
+/* Library build info: "sm_100a ..." */
+const char *ftb200_build_info(void);
+
+/* ---- setup (outputs of ReadInputFile / PartitionMesh / ReadMaterials) ---- */
+/* coordinates, connectivity, pid: GlobalVariables.h:32-33,47-49 after PartitionMesh.cpp:485-536 */
+int ftb200_upload_mesh(ftb200_ctx *ctx, const double *coordinates, const int *connectivity, const int *pid,
+                       int nNodes, int nElements);
+/* materialID, properties: src/io/input/ReadMaterials.cpp:8-138 */
+int ftb200_upload_materials(ftb200_ctx *ctx, const int *materialID, const double *properties, int nPID);
+/* sendProcessID / sendNeighbourCountCum / sendNodeIndex: PartitionMesh.cpp:566-1128 */
+int ftb200_upload_comm(ftb200_ctx *ctx, int sendProcessCount, const int *sendProcessID,
+                       const int *sendNeighbourCountCum, const int *sendNodeIndex);
+/* ShapeFunctions() (src/fem/ShapeFunctions/ShapeFunctions.cpp:32-255): validates the mesh (positive
+ * reference Jacobians), builds the node->element CSR map, zeroes the Prony history.  Nothing per
+ * Gauss point is stored.  min_detJ (optional) receives the smallest reference detJ. */
+int ftb200_shape_functions(ftb200_ctx *ctx, double *min_detJ);
+/* AssembleLumpedMass() without the neighbour sum (src/fem/Mass/Mass3D.cpp:127-157).  mass_out (optional)
+ * is double[3*nNodes].  Multi-GPU: sum shared nodes with the halo calls below (field 1). */
+int ftb200_lumped_mass(ftb200_ctx *ctx, double *mass_out);
+
+/* ---- legacy per-call path: host arrays in, host arrays out --------------- */
+/* GetForce()/GetForce_3D() (src/fem/SolidMechanics/GetForce_3D.cpp:5-53).  dt is the driver global `dt`
+ * (only material 5 reads it).  fe may be NULL (== 0).  With a comm pattern uploaded and nranks > 1 this
+ * call computes the LOCAL part only; see ftb200_force_begin/end for the split form. */
+int ftb200_get_force(ftb200_ctx *ctx, const double *displacements, const double *fe, double dt, double *fi,
+                     double *f_net);
+/* CalculateAccelerations() (src/fem/SolidMechanics/CalculateAcclerations.cpp:4-13): accelerations[i] =
+ * f_net[i]/mass[i] where !boundary[i]; other entries of the host array are left untouched. */
+int ftb200_calculate_accelerations(ftb200_ctx *ctx, const int *boundary, double *accelerations);
+/* StableTimeStep() local part (src/timestep/StableTimeStep.cpp:11-30): min over elements with a node that
+ * is not fully constrained.  The caller applies the cross-rank MIN and the FailureTimeStep test. */
+int ftb200_stable_time_step(ftb200_ctx *ctx, const double *displacements, const int *boundary, double *dtMin);
+/* CheckEnergy() local sums (src/fem/SolidMechanics/CheckEnergy.cpp:19-52): out[0..2] = WKE, Wint, Wext
+ * increments (already x0.5) over the nodes this rank owns. */
+int ftb200_check_energy(ftb200_ctx *ctx, const double *displacements, const double *displacements_prev,
+                        const double *velocities, const double *accelerations, const double *accelerations_prev,
+                        const double *fi, const double *fi_prev, const double *fe, const double *fe_prev,
+                        const int *boundary, double out[3]);
+/* Lazy outputs of the last force evaluation in the reference's layouts: F[72*nE], detF[8*nE], pk2[48*nE]
+ * (GetForce_3D.cpp side effects), Eavg[9*nE] (CalculateStrain.cpp:77-97).  Any pointer may be NULL. */
+int ftb200_get_gp_outputs(ftb200_ctx *ctx, double *F, double *detF, double *pk2, double *Eavg);
+
+/* ---- resident (fused) path ------------------------------------------------ */
+/* Upload / download nodal state; any pointer may be NULL (skipped). */
+int ftb200_set_state(ftb200_ctx *ctx, const double *displacements, const double *velocities,
+                     const double *accelerations, const int *boundary);
+int ftb200_get_state(ftb200_ctx *ctx, double *displacements, double *velocities, double *accelerations,
+                     int *boundary, double *fi, double *f_net);
+/* Boundary-condition descriptor replacing the drivers' ApplyBoundaryConditions callback
+ * (examples/Benchmarking-Parallel/Benchmarking-Parallel.cpp:184-244): bc_kind[3*nNodes] in 0..3;
+ * kind k > 0 prescribes u = Time*bc_rate[k], v = bc_rate[k], a = 0 and sets boundary = 1. */
+int ftb200_set_bc(ftb200_ctx *ctx, const int *bc_kind, const double bc_rate[4]);
+/* Step 0 of the explicit drivers (Benchmarking-Parallel.cpp:83-91): apply BC at Time0, dt =
+ * reduction*StableTimeStep(), GetForce(), CalculateAccelerations().  energy_every: 0 = never call the
+ * energy check, k = every k-th step (the shipped drivers use 1). */
+int ftb200_explicit_begin(ftb200_ctx *ctx, double Time0, double ExplicitTimeStepReduction, double FailureTimeStep,
+                          int energy_every);
+/* The time loop (Benchmarking-Parallel.cpp:106-171) on the device: runs while Time < tMax for at most
+ * maxSteps steps.  This is ExplicitDynamics(timeFinal, name) (include/FemTech.h:50, a stub in the
+ * reference).  Outputs (optional): steps executed, Time, next dt.  Asynchronous variant: _async enqueues
+ * `steps` steps on the stream without any host synchronisation (bench timing); _poll reads the scalars. */
+int ftb200_explicit_run(ftb200_ctx *ctx, double tMax, long long maxSteps, long long *steps_done, double *Time,
+                        double *dt);
+int ftb200_explicit_run_async(ftb200_ctx *ctx, double tMax, long long steps);
+int ftb200_explicit_poll(ftb200_ctx *ctx, long long *steps_done, double *Time, double *dt, int *status_bits);
+/* Running energies of the last checked step: out[0..3] = Wint, Wext, WKE, |WKE+Wint-Wext| */
+int ftb200_get_energy(ftb200_ctx *ctx, double out[4]);
+/* Optional per-step records kept on the device: capacity in steps (0 disables). */
+int ftb200_record_history(ftb200_ctx *ctx, long long capacity);
+int ftb200_get_history(ftb200_ctx *ctx, long long first, long long count, double *dt_hist, double *energy_hist4);
+
+/* ---- multi-GPU: shared-node exchange (GetForce_3D.cpp:54-102, Mass3D.cpp:77-125) ---- */
+/* Total number of shared-node slots (sendNeighbourCountCum[sendProcessCount]). */
+int ftb200_halo_count(const ftb200_ctx *ctx);
+/* Transport-agnostic split form.  Buffers are DEVICE pointers of 3*halo_count doubles laid out exactly
+ * like the reference's sendNodeDisplacement / recvNodeDisplacement (neighbour-major, xyz interleaved), so
+ * any transport (NCCL send/recv per neighbour, peer stores) can move slice i of send to the neighbour's
+ * slice of recv.  field: 0 = internal force, 1 = lumped mass. */
+int ftb200_halo_pack(ftb200_ctx *ctx, int field, double *send_dev);
+int ftb200_halo_add(ftb200_ctx *ctx, int field, const double *recv_dev);
+/* Resident path, split around the exchange: force_begin launches boundary elements, packs `send_dev`,
+ * then launches interior elements on a second stream; force_end adds `recv_dev` in ascending neighbour
+ * order and finishes the step.  dtmin_dev is a device double the caller MIN-reduces across ranks between
+ * the two calls (StableTimeStep.cpp:33). */
+int ftb200_step_begin(ftb200_ctx *ctx, double *send_dev, double **dtmin_dev);
+int ftb200_step_end(ftb200_ctx *ctx, const double *recv_dev);
+/* Peer-memory transport (NVLink/NVSwitch, no NCCL on the data path): every rank exports its receive
+ * window, imports the neighbours' and the whole step, exchange included, runs inside
+ * ftb200_explicit_run*.  handle is FTB200_IPC_HANDLE_BYTES bytes. */
+#define FTB200_IPC_HANDLE_BYTES 64
+int ftb200_p2p_export(ftb200_ctx *ctx, void *handle_out);
+int ftb200_p2p_import(ftb200_ctx *ctx, const void *all_handles /* nranks * 64 bytes, rank order */);
+
+/* ---- measurement helpers --------------------------------------------------- */
+/* Average device time per launch (ms) of the element and node kernels over the last explicit_run*,
+ * measured with CUDA events on the launching stream when profiling is enabled (adds two events per
+ * kernel; off by default). */
+int ftb200_profile_enable(ftb200_ctx *ctx, int on);
+int ftb200_profile_get(ftb200_ctx *ctx, double *elem_ms, double *node_ms, long long *elem_launches,
+                       long long *node_launches);
+/* Roofline denominators measured on this device: dependent-free DFMA chains on every SM (TFLOP/s, FMA = 2)
+ * and a STREAM-style fp64 copy (GB/s, read + write bytes).  Best of `reps` launches, CUDA-event timed. */
+int ftb200_measure_peaks(ftb200_ctx *ctx, int reps, double *fp64_tflops, double *copy_gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

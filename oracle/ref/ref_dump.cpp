@@ -11,8 +11,10 @@
  * condition below restate the driver (:83-171, :184-244); all numerics are the
  * reference library's.
  *
- * usage: ref_dump <mesh.inp|.k> <out-prefix> <maxSteps> <tMax> <dMax> [cubeL]
+ * usage: ref_dump <mesh.inp|.k> <out-prefix> <maxSteps> <tMax> <dMax> [cubeL] [warmupSteps] [nodump]
  *        (materials.dat is read from the current directory, ReadMaterials.cpp:11)
+ *        warmupSteps: loop iterations excluded from the reported loop time (bench.py);
+ *        nodump: write only scalars (timing runs on larger meshes)
  * output: <out-prefix>.rank<r>.bin  -- records: name[32] dtype[8] count(int64) payload
  */
 #include "FemTech.h"
@@ -33,7 +35,9 @@ bool ExplicitDynamic = true;
 static double g_cubeL = 0.005;
 static FILE *g_out = NULL;
 
+static bool g_nodump = false;
 static void put(const char *name, const char *dtype, const void *p, int64_t count, size_t esz) {
+  if (g_nodump && count > 4) return;
   char nb[32] = {0}, tb[8] = {0};
   strncpy(nb, name, 31);
   strncpy(tb, dtype, 7);
@@ -100,6 +104,8 @@ int main(int argc, char **argv) {
   const double tMax = atof(argv[4]);
   const double dMax = atof(argv[5]);
   if (argc > 6) g_cubeL = atof(argv[6]);
+  const int warmupSteps = argc > 7 ? atoi(argv[7]) : 0;
+  const bool nodump = argc > 8 && strcmp(argv[8], "nodump") == 0;
 
   double t0 = now();
   InitFemTechWoInput(argc, argv);
@@ -113,6 +119,7 @@ int main(int argc, char **argv) {
   g_out = fopen(fname, "wb");
   if (!g_out) { fprintf(stderr, "cannot open %s\n", fname); TerminateFemTech(3); }
 
+  g_nodump = nodump;
   puti1("world_size", world_size);
   puti1("world_rank", world_rank);
   puti1("nNodes", nNodes);
@@ -160,6 +167,7 @@ int main(int argc, char **argv) {
   double tLoop0 = now();
   int steps = 0;
   while (Time < tMax && steps < maxSteps) {
+    if (steps == warmupSteps) tLoop0 = now();
     t_n = Time;
     double t_np1 = Time + dt;
     Time = t_np1;
@@ -221,10 +229,11 @@ int main(int argc, char **argv) {
   puts1("wall_loop_s", tLoop);
   fclose(g_out);
   if (world_rank == 0) {
-    printf("REF_DUMP ranks=%d nallelements=%d steps=%d Time=%.17g dt=%.17g setup_s=%.3f loop_s=%.3f "
+    const int timed = steps > warmupSteps ? steps - warmupSteps : 0;
+    printf("REF_DUMP ranks=%d nallelements=%d steps=%d timed_steps=%d Time=%.17g dt=%.17g setup_s=%.3f loop_s=%.6f "
            "element_steps_per_s=%.6e u0=(%.9e %.9e %.9e) uid=%s\n",
-           world_size, nallelements, steps, Time, dt, tSetup, tLoop,
-           tLoop > 0 ? (double)nallelements * steps / tLoop : 0.0, displacements[0], displacements[1],
+           world_size, nallelements, steps, timed, Time, dt, tSetup, tLoop,
+           tLoop > 0 ? (double)nallelements * timed / tLoop : 0.0, displacements[0], displacements[1],
            displacements[2], uid.c_str());
     fflush(stdout);
   }

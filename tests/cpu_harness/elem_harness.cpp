@@ -1,0 +1,47 @@
+// elem_harness.cpp -- TEST ONLY.  Compiles femtech_b200/csrc/hex8_element.cuh
+// (the exact arithmetic the CUDA kernels run, one element per thread) with g++
+// so the `-m "not gpu"` suite can compare it with the oracle without a GPU.
+// Never loaded by the product.
+#include "../../femtech_b200/csrc/hex8_element.cuh"
+
+namespace {
+struct HostHist {
+  double* h;  // [8][18]: h1[6], h2[6], s0[6] per Gauss point
+  void load(int gp, ftb::GpHistory& g) const {
+    for (int i = 0; i < 6; ++i) { g.h1[i] = h[18 * gp + i]; g.h2[i] = h[18 * gp + 6 + i]; g.s0[i] = h[18 * gp + 12 + i]; }
+  }
+  void store(int gp, const ftb::GpHistory& g) const {
+    for (int i = 0; i < 6; ++i) { h[18 * gp + i] = g.h1[i]; h[18 * gp + 6 + i] = g.h2[i]; h[18 * gp + 12 + i] = g.s0[i]; }
+  }
+};
+struct HostOut {
+  static constexpr bool enabled = true;
+  double *F, *detF, *pk2;
+  void put(int gp, const double Fm[3][3], double J, const double Sv[6]) const {
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) F[9 * gp + 3 * j + i] = Fm[i][j];  // reference layout: column-major
+    detF[gp] = J;
+    for (int i = 0; i < 6; ++i) pk2[6 * gp + i] = Sv[i];
+  }
+};
+}  // namespace
+
+extern "C" int harness_element(const double* X24, const double* U24, int mat, const double* mp, double* hist144,
+                               int updHist, double* fe24, double* dtElem, double* F72, double* detF8, double* pk2_48) {
+  double X[8][3], U[8][3], fe[8][3];
+  for (int k = 0; k < 8; ++k)
+    for (int c = 0; c < 3; ++c) { X[k][c] = X24[3 * k + c]; U[k][c] = U24[3 * k + c]; }
+  HostHist hh{hist144};
+  HostOut ho{F72, detF8, pk2_48};
+  int st = ftb::hex8_element<-1, true>(X, U, mat, mp, updHist != 0, hh, ho, fe, dtElem);
+  for (int k = 0; k < 8; ++k)
+    for (int c = 0; c < 3; ++c) fe24[3 * k + c] = fe[k][c];
+  return st;
+}
+
+extern "C" double harness_mass(const double* X24, double rho, double* me8) {
+  double X[8][3];
+  for (int k = 0; k < 8; ++k)
+    for (int c = 0; c < 3; ++c) X[k][c] = X24[3 * k + c];
+  return ftb::hex8_lumped_mass(X, rho, me8);
+}
