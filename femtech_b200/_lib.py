@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libftb200.so")
+# FTB200_LIB selects an alternative build of the same library (kernel tuning experiments only)
+LIB_PATH = os.environ.get("FTB200_LIB") or os.path.join(HERE, "libftb200.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

@@ -93,13 +93,28 @@ struct ElemArgs {
   int ignore_loop_flags;
 };
 
-constexpr int ELEM_BLOCK = 128;
+#ifndef FTB_ELEM_BLOCK
+#define FTB_ELEM_BLOCK 64
+#endif
+#ifndef FTB_ELEM_MINBLOCKS
+#define FTB_ELEM_MINBLOCKS 6
+#endif
+constexpr int ELEM_BLOCK = FTB_ELEM_BLOCK;
+constexpr int ELEM_MINBLOCKS = FTB_ELEM_MINBLOCKS;
+
+// shared-memory scratch of hex8_element: [72][ELEM_BLOCK] doubles, thread t owns column t
+struct SmemScratch {
+  double* base;  // &sm[0][threadIdx.x]
+  __device__ __forceinline__ void st(int i, double x) { base[i * ELEM_BLOCK] = x; }
+  __device__ __forceinline__ double ld(int i) const { return base[i * ELEM_BLOCK]; }
+};
 
 // K1 (+K6).  MATSEL >= 0: every element of the launch has that material (no switch).
 template <int MATSEL, bool WITH_FORCE, bool WITH_DT>
-__global__ void __launch_bounds__(ELEM_BLOCK) k_elem(const ElemArgs A) {
+__global__ void __launch_bounds__(ELEM_BLOCK, ELEM_MINBLOCKS) k_elem(const ElemArgs A) {
   if (!A.ignore_loop_flags && (A.sc->last | A.sc->done)) return;
   const int e = A.e0 + blockIdx.x * ELEM_BLOCK + threadIdx.x;
+  __shared__ double sm_cols[WITH_FORCE ? 72 : 1][ELEM_BLOCK];
   double dte = 1e300;
   int status = 0;
   if (e < A.e1) {
@@ -122,7 +137,8 @@ __global__ void __launch_bounds__(ELEM_BLOCK) k_elem(const ElemArgs A) {
       double fe[8][3];
       DevHist h{A.hist, E, (size_t)e};
       double d;
-      status = hex8_element<MATSEL, WITH_DT>(X, U, mat, mp, true, h, NoOutput(), fe, &d);
+      SmemScratch S{&sm_cols[0][threadIdx.x]};
+      status = hex8_element<MATSEL, WITH_DT>(X, U, mat, mp, true, h, NoOutput(), S, fe, &d);
       if (WITH_DT) dte = d;
 #pragma unroll
       for (int k = 0; k < 8; ++k)
@@ -151,14 +167,8 @@ __global__ void __launch_bounds__(ELEM_BLOCK) k_elem(const ElemArgs A) {
       unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o);
       b = t < b ? t : b;
     }
-    __shared__ unsigned long long sb[ELEM_BLOCK / 32];
-    if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = b;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int w = 1; w < ELEM_BLOCK / 32; ++w) b = sb[w] < b ? sb[w] : b;
-      atomicMin(&A.sc->dtmin_bits, b);  // min is order independent: deterministic
-    }
+    // one atomic per warp, no block barrier; min is order independent: deterministic
+    if ((threadIdx.x & 31) == 0) atomicMin(&A.sc->dtmin_bits, b);
   }
   if (status) atomicOr(&A.sc->status, status);
 }
@@ -653,7 +663,8 @@ __global__ void k_gp_outputs(const ElemArgs A, const int* ref_of, double* F, dou
   if (Eavg) { sink.detF = nullptr; sink.pk2 = nullptr; }
   DevHist h{A.hist, E, (size_t)e};
   double fe[8][3], d;
-  hex8_element<-1, false>(X, U, mat, mp, false, h, sink, fe, &d);
+  LocalScratch S;
+  hex8_element<-1, false>(X, U, mat, mp, false, h, sink, S, fe, &d);
   if (Eavg) {
     // CalculateStrain.cpp:77-97: E = sum_gp (0.5/8) F^T F - 0.5 I
     double Em[9];
@@ -671,7 +682,7 @@ __global__ void k_gp_outputs(const ElemArgs A, const int* ref_of, double* F, dou
     // second pass for the other outputs, if requested
     if (F || detF || pk2) {
       OutSink s2{F, detF, pk2, re};
-      hex8_element<-1, false>(X, U, mat, mp, false, h, s2, fe, &d);
+      hex8_element<-1, false>(X, U, mat, mp, false, h, s2, S, fe, &d);
     }
   }
 }

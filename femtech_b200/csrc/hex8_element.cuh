@@ -381,20 +381,20 @@ FTB_HD double ncross(const double a[3], const double b[3]) {  // math.cpp:30-41
   const double y = -a[0] * b[2] + a[2] * b[0];
   return sqrt(x * x + y * y + z * z);
 }
-// face: centerD = (mD + sg*m123)/8, c1 = (mA + sg*mAn)/8, c2 = (mB + sg*mBn)/8
-FTB_HD double face_area(const double mD[3], const double m123[3], const double mA[3], const double mAn[3],
-                        const double mB[3], const double mBn[3], const double sg) {
+// Faces come in opposite pairs (zeta=-+1, xi=-+1, eta=-+1).  For a pair, with unscaled (x8) vectors
+//   centerD = mD -+ m123,  c1 = mA -+ mAn,  c2 = mB -+ mBn
+// the cross products share their terms: c1 x c2 = (mA x mB + mAn x mBn) -+ (mA x mBn + mAn x mB).
+// The parallelogram branch (Geometry.cpp:46-48, signed test kept) needs only |c1 x c2|^2, so the
+// square root is taken once per element; the 2x2 Gauss branch (:50-63) is the rare slow path.
+FTB_HD void cross3(const double a[3], const double b[3], double r[3]) {
+  r[0] = a[1] * b[2] - a[2] * b[1];
+  r[1] = a[2] * b[0] - a[0] * b[2];
+  r[2] = a[0] * b[1] - a[1] * b[0];
+}
+FTB_HD double face_area_gauss(const double cD8[3], const double c18[3], const double c28[3]) {
   double cD[3], c1[3], c2[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    cD[i] = 0.125 * (mD[i] + sg * m123[i]);
-    c1[i] = 0.125 * (mA[i] + sg * mAn[i]);
-    c2[i] = 0.125 * (mB[i] + sg * mBn[i]);
-  }
-  const double tol = 1e-6;
-  if ((cD[0] < tol) && (cD[1] < tol) && (cD[2] < tol)) {  // signed test, Geometry.cpp:46 (quirk kept)
-    return 4.0 * ncross(c1, c2);
-  }
+  for (int i = 0; i < 3; ++i) { cD[i] = 0.125 * cD8[i]; c1[i] = 0.125 * c18[i]; c2[i] = 0.125 * c28[i]; }
   const double t = sqrt(3.0) / 3.0;
   double area = 0.0;
 #pragma unroll
@@ -412,19 +412,48 @@ FTB_HD double face_area(const double mD[3], const double m123[3], const double m
     }
   return area;
 }
+// updates n2max (largest |c1 x c2|^2 of the parallelogram faces, x8 vectors) and aslow (largest
+// area among faces that took the Gauss branch)
+FTB_HD void face_pair(const double mD[3], const double m123[3], const double mA[3], const double mAn[3],
+                      const double mB[3], const double mBn[3], double& n2max, double& aslow) {
+  double p1[3], p2[3], q1[3], q2[3];
+  cross3(mA, mB, p1);
+  cross3(mAn, mBn, p2);
+  cross3(mA, mBn, q1);
+  cross3(mAn, mB, q2);
+  const double tol8 = 8.0e-6;  // centerD[i] < 1e-6  <=>  8 centerD[i] < 8e-6 (exact power-of-two scaling)
+#pragma unroll
+  for (int sgn = 0; sgn < 2; ++sgn) {
+    const double sg = sgn ? 1.0 : -1.0;
+    const double d0 = mD[0] + sg * m123[0], d1 = mD[1] + sg * m123[1], d2 = mD[2] + sg * m123[2];
+    if ((d0 < tol8) && (d1 < tol8) && (d2 < tol8)) {
+      const double x = (p1[0] + p2[0]) + sg * (q1[0] + q2[0]);
+      const double y = (p1[1] + p2[1]) + sg * (q1[1] + q2[1]);
+      const double z = (p1[2] + p2[2]) + sg * (q1[2] + q2[2]);
+      const double n2 = x * x + y * y + z * z;
+      if (n2 > n2max) n2max = n2;
+    } else {
+      double cD[3] = {d0, d1, d2}, c1[3], c2[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { c1[i] = mA[i] + sg * mAn[i]; c2[i] = mB[i] + sg * mBn[i]; }
+      const double ar = face_area_gauss(cD, c1, c2);
+      if (ar > aslow) aslow = ar;
+    }
+  }
+}
+// returns V / A_max (CalculateCharacteristicLength_C3D8.cpp:3-30)
 FTB_HD double hex_char_length(const double xm[7][3]) {
   const double* g1 = xm[0]; const double* g2 = xm[1]; const double* g3 = xm[2];
   const double* g12 = xm[3]; const double* g23 = xm[4]; const double* g13 = xm[5]; const double* g123 = xm[6];
   // volumeHexahedron: q0=g12 q1=g13 q2=g1 q3=g23 q4=g2 q5=g3
   const double vol = (tp3(g12, g2, g23) + tp3(g1, g12, g13) + tp3(g13, g23, g3)) / 192.0 + tp3(g1, g2, g3) / 64.0;
-  double amax = 0.0, ar;
-  // faces in the reference's order {0,1,2,3},{4,5,6,7},{0,3,7,4},{1,2,6,5},{0,1,5,4},{3,2,6,7}
-  ar = face_area(g12, g123, g1, g13, g2, g23, -1.0); if (ar > amax) amax = ar;  // zeta = -1
-  ar = face_area(g12, g123, g1, g13, g2, g23, +1.0); if (ar > amax) amax = ar;  // zeta = +1
-  ar = face_area(g23, g123, g2, g12, g3, g13, -1.0); if (ar > amax) amax = ar;  // xi = -1
-  ar = face_area(g23, g123, g2, g12, g3, g13, +1.0); if (ar > amax) amax = ar;  // xi = +1
-  ar = face_area(g13, g123, g1, g12, g3, g23, -1.0); if (ar > amax) amax = ar;  // eta = -1
-  ar = face_area(g13, g123, g1, g12, g3, g23, +1.0); if (ar > amax) amax = ar;  // eta = +1
+  double n2max = 0.0, aslow = 0.0;
+  face_pair(g12, g123, g1, g13, g2, g23, n2max, aslow);  // zeta = -+1: faces {0,1,2,3},{4,5,6,7}
+  face_pair(g23, g123, g2, g12, g3, g13, n2max, aslow);  // xi   = -+1: faces {0,3,7,4},{1,2,6,5}
+  face_pair(g13, g123, g1, g12, g3, g23, n2max, aslow);  // eta  = -+1: faces {0,1,5,4},{3,2,6,7}
+  // parallelogram area = 4 |c1 x c2| with c = (x8 vector)/8  ->  |x8 cross| / 16
+  const double afast = sqrt(n2max) * 0.0625;
+  const double amax = afast > aslow ? afast : aslow;
   return vol / amax;
 }
 
@@ -435,6 +464,28 @@ struct NoHistory {
   FTB_HD void load(int, GpHistory&) const {}
   FTB_HD void store(int, const GpHistory&) const {}
 };
+
+// Scratch for the 2 x 12 Jacobian column vectors of an element (72 doubles).  The CUDA kernel
+// keeps them in shared memory ([72][blockDim] doubles, conflict free) so that only the 21 force
+// modes stay in registers across the Gauss-point loop; the host harness uses a plain array.
+struct LocalScratch {
+  double v[72];
+  FTB_HD void st(int i, double x) { v[i] = x; }
+  FTB_HD double ld(int i) const { return v[i]; }
+};
+// index of component c of column type t (0 xi, 1 eta, 2 zeta), sign combination q, field f (0 X, 1 U)
+#define FTB_COL(f, t, q, c) ((((f) * 3 + (t)) * 4 + (q)) * 3 + (c))
+
+// r(sa,sb) = A + sa B + sb C + sa sb D for the four sign pairs: q = (sa>0) + 2 (sb>0)
+template <class Scratch>
+FTB_HD void col_butterfly(Scratch& S, const int f, const int t, const int c, const double A, const double B,
+                          const double C, const double D) {
+  const double ad = A + D, am = A - D, bc = B + C, bm = B - C;
+  S.st(FTB_COL(f, t, 3, c), ad + bc);  // (+,+)
+  S.st(FTB_COL(f, t, 0, c), ad - bc);  // (-,-)
+  S.st(FTB_COL(f, t, 1, c), am + bm);  // (+,-)
+  S.st(FTB_COL(f, t, 2, c), am - bm);  // (-,+)
+}
 
 // Output sink for K_out (F, detF, pk2 in the reference's layouts); the hot
 // kernel uses NoOutput.
@@ -447,55 +498,73 @@ struct NoOutput {
 // MATSEL: compile-time material id (1..5) when the whole launch is uniform,
 // or -1 for the generic per-element switch.  Returns status bits:
 // 1 = unknown material, 2 = non-positive det J0, 4 = non-finite / non-positive det F.
-template <int MATSEL, bool WITH_DT, class Hist, class Out>
+template <int MATSEL, bool WITH_DT, class Hist, class Out, class Scratch>
 FTB_HD int hex8_element(const double X[8][3], const double U[8][3], int mat, const double* __restrict__ mp,
-                        const bool updHist, const Hist& hist, const Out& out, double fe[8][3], double* dtElem) {
+                        const bool updHist, const Hist& hist, const Out& out, Scratch& S, double fe[8][3],
+                        double* dtElem) {
   if (MATSEL >= 0) mat = MATSEL;
-  double gX[7][3], gU[7][3];
+  const double a = FTB_GP_A, a2 = FTB_GP_A * FTB_GP_A;
   {
-    double n[8], g[7];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) n[k] = X[k][c];
-      hex_modes(n, g);
-#pragma unroll
-      for (int m = 0; m < 7; ++m) gX[m][c] = g[m];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) n[k] = U[k][c];
-      hex_modes(n, g);
-#pragma unroll
-      for (int m = 0; m < 7; ++m) gU[m][c] = g[m];
-    }
-  }
-  int status = 0;
-  if (WITH_DT) {
+    // One space component at a time keeps the live set small: 8+8 nodal values -> 7+7 modes ->
+    // 24 column entries written to the scratch; only the 21 current-configuration modes (for the
+    // time step) survive the loop.
     double xm[7][3];
 #pragma unroll
-    for (int m = 0; m < 7; ++m)
+    for (int c = 0; c < 3; ++c) {
+      double n[8], gX[7], gU[7];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) xm[m][c] = gX[m][c] + gU[m][c];
-    *dtElem = hex_char_length(xm) / mp[MP_CE];  // CalculateTimeStep.cpp:19
-  }
-  // pre-scale the bilinear modes by a and the trilinear mode by a^2
-  const double a = FTB_GP_A, a2 = FTB_GP_A * FTB_GP_A;
+      for (int k = 0; k < 8; ++k) n[k] = X[k][c];
+      hex_modes(n, gX);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    gX[3][c] *= a; gX[4][c] *= a; gX[5][c] *= a; gX[6][c] *= a2;
-    gU[3][c] *= a; gU[4][c] *= a; gU[5][c] *= a; gU[6][c] *= a2;
+      for (int k = 0; k < 8; ++k) n[k] = U[k][c];
+      hex_modes(n, gU);
+      if (WITH_DT) {
+#pragma unroll
+        for (int m = 0; m < 7; ++m) xm[m][c] = gX[m] + gU[m];
+      }
+      // Jacobian columns 8 dX/dxi_t and 8 dU/dxi_t at the Gauss points.  Column xi depends only on the
+      // signs (s2,s3) of the point, eta on (s1,s3), zeta on (s1,s2): 12 distinct vectors per field
+      // instead of 24, each built by a 4-point butterfly from the modes (bilinear modes x a, trilinear x a^2).
+      const double X12 = a * gX[3], X23 = a * gX[4], X13 = a * gX[5], X123 = a2 * gX[6];
+      col_butterfly(S, 0, 0, c, gX[0], X12, X13, X123);  // xi  : (s2, s3)
+      col_butterfly(S, 0, 1, c, gX[1], X12, X23, X123);  // eta : (s1, s3)
+      col_butterfly(S, 0, 2, c, gX[2], X13, X23, X123);  // zeta: (s1, s2)
+      const double U12 = a * gU[3], U23 = a * gU[4], U13 = a * gU[5], U123 = a2 * gU[6];
+      col_butterfly(S, 1, 0, c, gU[0], U12, U13, U123);
+      col_butterfly(S, 1, 1, c, gU[1], U12, U23, U123);
+      col_butterfly(S, 1, 2, c, gU[2], U13, U23, U123);
+    }
+    if (WITH_DT) *dtElem = hex_char_length(xm) / mp[MP_CE];  // CalculateTimeStep.cpp:19
   }
+  int status = 0;
   double phi[7][3];
 #pragma unroll
   for (int m = 0; m < 7; ++m)
 #pragma unroll
     for (int c = 0; c < 3; ++c) phi[m][c] = 0.0;
 
-#pragma unroll
+  // The Gauss-point loop is deliberately NOT unrolled: one iteration has 9-wide instruction-level
+  // parallelism (3x3 blocks), the rolled body fits the instruction cache, and the register count
+  // stays low enough for 12-16 resident warps per SM.  Signs are run-time +-1.0 folded into FMAs.
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
   for (int gp = 0; gp < 8; ++gp) {
-    const double s1 = FTB_GP_S1(gp), s2 = FTB_GP_S2(gp), s3 = FTB_GP_S3(gp);
+    // reference numbering (GaussQuadrature3D.cpp:19-49): xi + for gp 1,2,5,6; eta + for 2,3,6,7; zeta + for 0..3
+    const int b1 = ((gp + 1) >> 1) & 1, b2 = (gp >> 1) & 1, b3 = ((gp >> 2) & 1) ^ 1;
+    const double s1 = b1 ? 1.0 : -1.0, s2 = b2 ? 1.0 : -1.0, s3 = b3 ? 1.0 : -1.0;
+    const double s23 = s2 * s3, s13 = s1 * s3, s12 = s1 * s2;
+    const int qx = b2 + 2 * b3, qe = b1 + 2 * b3, qz = b1 + 2 * b2;
     double J0[3][3], Uh[3][3], cJ[3][3];
-    gp_jacobian(gX, s1, s2, s3, J0);
-    gp_jacobian(gU, s1, s2, s3, Uh);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      J0[i][0] = S.ld(FTB_COL(0, 0, qx, i));
+      J0[i][1] = S.ld(FTB_COL(0, 1, qe, i));
+      J0[i][2] = S.ld(FTB_COL(0, 2, qz, i));
+      Uh[i][0] = S.ld(FTB_COL(1, 0, qx, i));
+      Uh[i][1] = S.ld(FTB_COL(1, 1, qe, i));
+      Uh[i][2] = S.ld(FTB_COL(1, 2, qz, i));
+    }
     cofactor3(J0, cJ);
     const double det = J0[0][0] * cJ[0][0] + J0[0][1] * cJ[0][1] + J0[0][2] * cJ[0][2];  // 512 detJ0
     if (!(det > 0.0)) status |= 2;
@@ -517,21 +586,19 @@ FTB_HD int hex8_element(const double X[8][3], const double U[8][3], int mat, con
     status |= material_P<Out::enabled>(mat, F, cF, J, mp, &h, updHist, P, Sv);
     if (mat == 5 && updHist) hist.store(gp, h);
     if (Out::enabled) out.put(gp, F, J, Sv);
-    // Q = P * cof(J0)  (unscaled: 64 x the true one)
-    double Q[3][3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) Q[i][c] = P[i][0] * cJ[0][c] + P[i][1] * cJ[1][c] + P[i][2] * cJ[2][c];
+    // Q = P * cof(J0)  (unscaled: 64 x the true one), accumulated into the 7 force modes
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      phi[0][i] += Q[i][0];
-      phi[1][i] += Q[i][1];
-      phi[2][i] += Q[i][2];
-      phi[3][i] += s2 * Q[i][0] + s1 * Q[i][1];
-      phi[4][i] += s3 * Q[i][1] + s2 * Q[i][2];
-      phi[5][i] += s3 * Q[i][0] + s1 * Q[i][2];
-      phi[6][i] += (s2 * s3) * Q[i][0] + (s1 * s3) * Q[i][1] + (s1 * s2) * Q[i][2];
+      const double Q0 = P[i][0] * cJ[0][0] + P[i][1] * cJ[1][0] + P[i][2] * cJ[2][0];
+      const double Q1 = P[i][0] * cJ[0][1] + P[i][1] * cJ[1][1] + P[i][2] * cJ[2][1];
+      const double Q2 = P[i][0] * cJ[0][2] + P[i][1] * cJ[1][2] + P[i][2] * cJ[2][2];
+      phi[0][i] += Q0;
+      phi[1][i] += Q1;
+      phi[2][i] += Q2;
+      phi[3][i] = fma(s2, Q0, fma(s1, Q1, phi[3][i]));
+      phi[4][i] = fma(s3, Q1, fma(s2, Q2, phi[4][i]));
+      phi[5][i] = fma(s3, Q0, fma(s1, Q2, phi[5][i]));
+      phi[6][i] = fma(s23, Q0, fma(s13, Q1, fma(s12, Q2, phi[6][i])));
     }
   }
   // scale: 1/8 (dN/dxi) * 1/64 (cofactor of 8 J0); bilinear modes carry a, trilinear a^2

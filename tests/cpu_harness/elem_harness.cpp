@@ -33,7 +33,8 @@ extern "C" int harness_element(const double* X24, const double* U24, int mat, co
     for (int c = 0; c < 3; ++c) { X[k][c] = X24[3 * k + c]; U[k][c] = U24[3 * k + c]; }
   HostHist hh{hist144};
   HostOut ho{F72, detF8, pk2_48};
-  int st = ftb::hex8_element<-1, true>(X, U, mat, mp, updHist != 0, hh, ho, fe, dtElem);
+  ftb::LocalScratch sc;
+  int st = ftb::hex8_element<-1, true>(X, U, mat, mp, updHist != 0, hh, ho, sc, fe, dtElem);
   for (int k = 0; k < 8; ++k)
     for (int c = 0; c < 3; ++c) fe24[3 * k + c] = fe[k][c];
   return st;
