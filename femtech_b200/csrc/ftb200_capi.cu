@@ -32,6 +32,7 @@ struct ftb200_ctx {
   long long launches = 0;
   char err[512] = {0};
   int nN = 0, nE = 0, nPID = 0;
+  int nNp = 0;  // padded internal node count (node groups are aligned to NODE_TILE)
   bool mesh_ok = false, mat_ok = false, shape_ok = false, begun = false, bc_ok = false;
   // host copies of the inputs
   std::vector<double> h_X;
@@ -45,6 +46,19 @@ struct ftb200_ctx {
   double* m = nullptr;
   uint16_t* flags = nullptr;
   int *conn = nullptr, *pid = nullptr, *ref_of = nullptr;
+  int *d_nref = nullptr, *d_nint = nullptr;  // internal node -> caller's id (-1 = padding) and back
+  std::vector<int> h_nint;
+  // pipelined loop
+  PipeCtl* d_ctl = nullptr;
+  uint8_t *d_etile_chunk = nullptr, *d_ntile_group = nullptr;
+  int* d_ell = nullptr;
+  double* d_etile = nullptr;
+  int nTilesE = 0, nTilesN = 0, nChunks = 0;
+  int elem_grid = 0, node_grid = 0;
+  bool pipe = false;
+  cudaEvent_t ev_elem[2] = {nullptr, nullptr};
+  cudaGraphExec_t pgraph = nullptr;
+  int pgraph_energy = -1;
   uint8_t* eflag = nullptr;
   double *felem = nullptr, *hist = nullptr, *mp = nullptr;
   int *node_off = nullptr, *node_ent = nullptr;
@@ -142,7 +156,7 @@ NodeArgs node_args(ftb200_ctx* c, const double* recv) {
   A.halo_recv = recv;
   A.halo_off = c->halo_off; A.halo_slot = c->halo_slot;
   A.halo_node_idx = recv ? c->halo_node_idx : nullptr;
-  A.epart = c->epart; A.sc = c->sc; A.nN = c->nN; A.nE = c->nE;
+  A.epart = c->epart; A.sc = c->sc; A.nN = c->nNp; A.nE = c->nE;
   A.store_fi = c->energy ? 1 : 0;
   return A;
 }
@@ -189,6 +203,40 @@ void launch_step(ftb200_ctx* ctx, const double* recv) {
   if (ctx->energy) LAUNCH(k_energy, 1, 256, s, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
 }
 
+// ---- pipelined loop: k_elem_pipe on the main stream, k_node_pipe on the second (high priority) stream
+void launch_pipe_pair(ftb200_ctx* ctx, int i) {
+  cudaStream_t s1 = ctx->stream, s2 = ctx->stream2;
+  PipeElemArgs PE;
+  PE.E = elem_args(ctx, 0, ctx->nE, 0);
+  for (int k = 0; k < 3; ++k) { PE.v[k] = ctx->v[k]; PE.a[k] = ctx->a[k]; }
+  PE.flags = ctx->flags; PE.tile_chunk = ctx->d_etile_chunk; PE.ctl = ctx->d_ctl; PE.dt_hist = ctx->dthist; PE.nPID = ctx->nPID;
+  PipeNodeArgs PN;
+  PN.N = node_args(ctx, nullptr);
+  PN.ell = ctx->d_ell;
+  PN.tile_group = ctx->d_ntile_group; PN.ctl = ctx->d_ctl; PN.etile = ctx->d_etile; PN.ehist = ctx->ehist; PN.energy = ctx->energy;
+  size_t i0 = 0, i1 = 0;
+  if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s1);
+  switch (ctx->uniform_mat) {
+    case 1: LAUNCH((k_elem_pipe<1>), ctx->elem_grid, ELEM_BLOCK, s1, PE); break;
+    case 4: LAUNCH((k_elem_pipe<4>), ctx->elem_grid, ELEM_BLOCK, s1, PE); break;
+    case 5: LAUNCH((k_elem_pipe<5>), ctx->elem_grid, ELEM_BLOCK, s1, PE); break;
+    default: LAUNCH((k_elem_pipe<-1>), ctx->elem_grid, ELEM_BLOCK, s1, PE); break;
+  }
+  if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s1); ctx->prof.elem.push_back({i0, i1}); }
+  // k_node_pipe(i) may start once k_elem_pipe(i-1) has completely finished (counter recycling)
+  cudaStreamWaitEvent(s2, i == 0 ? ctx->ev_fork : ctx->ev_elem[(i - 1) & 1], 0);
+  if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s2);
+  LAUNCH(k_node_pipe, ctx->node_grid, NODE_TILE, s2, PN);
+  if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s2); ctx->prof.node.push_back({i0, i1}); }
+  cudaEventRecord(ctx->ev_elem[i & 1], s1);
+}
+void launch_pipe_steps(ftb200_ctx* ctx, int nsteps) {
+  cudaEventRecord(ctx->ev_fork, ctx->stream);
+  for (int i = 0; i < nsteps; ++i) launch_pipe_pair(ctx, i);
+  cudaEventRecord(ctx->ev_join, ctx->stream2);
+  cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+}
+
 void prof_collect(ftb200_ctx* ctx) {
   ProfEvents& P = ctx->prof;
   for (auto& pr : P.elem) {
@@ -205,19 +253,19 @@ void prof_collect(ftb200_ctx* ctx) {
 int upload_aos(ftb200_ctx* ctx, const double* host, double* const dst[3]) {
   const size_t n3 = 3 * (size_t)ctx->nN;
   CK(cudaMemcpyAsync(ctx->d_stage[0], host, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(k_aos_to_soa, cdiv(ctx->nN, 256), 256, ctx->stream, ctx->d_stage[0], dst[0], dst[1], dst[2], ctx->nN);
+  LAUNCH(k_aos_to_soa, cdiv(ctx->nNp, 256), 256, ctx->stream, ctx->d_stage[0], dst[0], dst[1], dst[2], ctx->d_nref, ctx->nNp);
   return 0;
 }
 int download_aos(ftb200_ctx* ctx, double* const src[3], double* host, int stage) {
   const size_t n3 = 3 * (size_t)ctx->nN;
-  LAUNCH(k_soa_to_aos, cdiv(ctx->nN, 256), 256, ctx->stream, src[0], src[1], src[2], ctx->d_stage[stage], ctx->nN);
+  LAUNCH(k_soa_to_aos, cdiv(ctx->nNp, 256), 256, ctx->stream, src[0], src[1], src[2], ctx->d_stage[stage], ctx->d_nref, ctx->nNp);
   CK(cudaMemcpyAsync(host, ctx->d_stage[stage], n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   return 0;
 }
 int upload_boundary(ftb200_ctx* ctx, const int* boundary) {
   const size_t n3 = 3 * (size_t)ctx->nN;
   CK(cudaMemcpyAsync(ctx->d_istage, boundary, n3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(k_boundary_to_flags, cdiv(ctx->nN, 256), 256, ctx->stream, ctx->d_istage, ctx->flags, ctx->nN);
+  LAUNCH(k_boundary_to_flags, cdiv(ctx->nNp, 256), 256, ctx->stream, ctx->d_istage, ctx->flags, ctx->d_nref, ctx->nNp);
   return 0;
 }
 
@@ -231,6 +279,8 @@ void free_all(ftb200_ctx* c) {
   dfree(c->dthist); dfree(c->ehist); dfree(c->epart); dfree(c->out3); dfree(c->d_istage); dfree(c->d_big);
   c->d_big_bytes = 0;
   dfree(c->d_detmin); dfree(c->d_nonpos);
+  dfree(c->d_nref); dfree(c->d_nint); dfree(c->d_ctl); dfree(c->d_etile_chunk); dfree(c->d_ntile_group); dfree(c->d_etile); dfree(c->d_ell);
+  if (c->pgraph) { cudaGraphExecDestroy(c->pgraph); c->pgraph = nullptr; }
   dfree(c->d_sendNodeIndex); dfree(c->halo_nodes); dfree(c->halo_off); dfree(c->halo_slot); dfree(c->halo_node_idx);
   if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
 }
@@ -255,10 +305,14 @@ int ftb200_create(int rank, int nranks, int device, ftb200_ctx** out) {
   if (device < 0 || device >= ndev) return FTB200_ERR_INPUT;
   ftb200_ctx* ctx = new ftb200_ctx();
   ctx->rank = rank; ctx->nranks = nranks; ctx->device = device;
-  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+  int prio_lo = 0, prio_hi = 0;
+  if (cudaSetDevice(device) != cudaSuccess || cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_elem[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_elem[1], cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return FTB200_ERR_CUDA;
   }
@@ -276,6 +330,8 @@ int ftb200_destroy(ftb200_ctx* ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->ev_elem[i]) cudaEventDestroy(ctx->ev_elem[i]);
   delete ctx;
   return FTB200_OK;
 }
@@ -288,6 +344,7 @@ int ftb200_set_stream(ftb200_ctx* ctx, void* cuda_stream) {
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+  if (ctx->pgraph) { cudaGraphExecDestroy(ctx->pgraph); ctx->pgraph = nullptr; }
   if (cuda_stream) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cuda_stream;
@@ -348,34 +405,23 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
   for (int e = 0; e < nE; ++e)
     if (ctx->h_pid[e] < 0 || ctx->h_pid[e] >= nPID) return fail(ctx, FTB200_ERR_INPUT, "pid[%d] = %d out of range", e, ctx->h_pid[e]);
   free_all(ctx);
-  // ---- shared nodes and the boundary/interior element split -------------------------------
+  // ---- internal element order: elements touching a shared node first (their forces feed the halo),
+  //      the caller's order kept inside each group --------------------------------------------------
   ctx->halo_count = (int)ctx->h_sendNodeIndex.size();
-  std::vector<int> node_h(nN, -1), halo_nodes;
+  std::vector<char> is_shared(nN, 0);
   for (int i = 0; i < ctx->halo_count; ++i) {
     const int n = ctx->h_sendNodeIndex[i];
     if (n < 0 || n >= nN) return fail(ctx, FTB200_ERR_INPUT, "sendNodeIndex[%d] = %d out of range", i, n);
-    if (node_h[n] < 0) { node_h[n] = 0; }
+    is_shared[n] = 1;
   }
-  for (int n = 0; n < nN; ++n)
-    if (node_h[n] == 0) { node_h[n] = (int)halo_nodes.size(); halo_nodes.push_back(n); }
-  ctx->nshared = (int)halo_nodes.size();
-  // slots of every shared node in ascending neighbour order (slot index i is neighbour-major already)
-  std::vector<int> hoff(ctx->nshared + 1, 0), hslot(ctx->halo_count);
-  for (int i = 0; i < ctx->halo_count; ++i) hoff[node_h[ctx->h_sendNodeIndex[i]] + 1]++;
-  for (int h = 0; h < ctx->nshared; ++h) hoff[h + 1] += hoff[h];
-  {
-    std::vector<int> cur(hoff.begin(), hoff.end() - 1);
-    for (int i = 0; i < ctx->halo_count; ++i) hslot[cur[node_h[ctx->h_sendNodeIndex[i]]]++] = i;
-  }
-  // internal element order: elements touching a shared node first, reference order kept inside each group
   std::vector<int> ref_of(nE), int_of(nE);
   {
     std::vector<char> isb(nE, 0);
     int nb = 0;
-    if (ctx->nshared)
+    if (ctx->halo_count)
       for (int e = 0; e < nE; ++e) {
         for (int k = 0; k < 8; ++k)
-          if (node_h[ctx->h_conn[8 * (size_t)e + k]] >= 0) { isb[e] = 1; break; }
+          if (is_shared[ctx->h_conn[8 * (size_t)e + k]]) { isb[e] = 1; break; }
         nb += isb[e];
       }
     ctx->nE_boundary = nb;
@@ -385,25 +431,79 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       ref_of[t] = e; int_of[e] = t;
     }
   }
-  // ---- CSR node -> (element, slot), ascending reference element id -------------------------
-  std::vector<int> off(nN + 1, 0), ent(8 * (size_t)nE);
-  for (size_t i = 0; i < 8 * (size_t)nE; ++i) off[ctx->h_conn[i] + 1]++;
-  for (int n = 0; n < nN; ++n) off[n + 1] += off[n];
+  // ---- element chunks (runs of 64-element tiles) and node groups for the pipelined loop ----------
+  const int nTilesE = cdiv(nE, ELEM_BLOCK);
+  int C = 32;
+  if (const char* ev = getenv("FTB200_CHUNKS")) C = atoi(ev);
+  C = std::max(1, std::min(std::min(C, PIPE_MAXC), nTilesE));
+  std::vector<uint8_t> etile_chunk(nTilesE);
+  std::vector<unsigned> elem_target(PIPE_MAXC, 0), node_target(PIPE_MAXC, 0), need(PIPE_MAXC, 0);
+  for (int t = 0; t < nTilesE; ++t) {
+    const int c = (int)(((long long)t * C) / nTilesE);
+    etile_chunk[t] = (uint8_t)c;
+    elem_target[c]++;
+  }
+  // node group = largest chunk among the elements of the node (0 for isolated nodes)
+  std::vector<int> ngroup(nN, 0);
+  for (int t = 0; t < nE; ++t) {
+    const int c = etile_chunk[t / ELEM_BLOCK], e = ref_of[t];
+    for (int k = 0; k < 8; ++k) { int& g = ngroup[ctx->h_conn[8 * (size_t)e + k]]; if (c > g) g = c; }
+  }
+  for (int t = 0; t < nE; ++t) {
+    const int c = etile_chunk[t / ELEM_BLOCK], e = ref_of[t];
+    for (int k = 0; k < 8; ++k) { const unsigned g = (unsigned)ngroup[ctx->h_conn[8 * (size_t)e + k]]; if (g > need[c]) need[c] = g; }
+  }
+  // internal node order: by group, caller's id inside a group; every group padded to whole node tiles
+  std::vector<int> gcount(C, 0), gstart(C + 1, 0);
+  for (int n = 0; n < nN; ++n) gcount[ngroup[n]]++;
+  for (int g = 0; g < C; ++g) gstart[g + 1] = gstart[g] + cdiv(gcount[g], NODE_TILE) * NODE_TILE;
+  const int nNp = std::max(gstart[C], NODE_TILE);
+  ctx->nNp = nNp;
+  const int nTilesN = nNp / NODE_TILE;
+  std::vector<int> nref(nNp, -1), nint(nN, -1);
+  {
+    std::vector<int> cur(gstart.begin(), gstart.end() - 1);
+    for (int n = 0; n < nN; ++n) { const int i = cur[ngroup[n]]++; nref[i] = n; nint[n] = i; }
+  }
+  std::vector<uint8_t> ntile_group(nTilesN, (uint8_t)(C - 1));
+  for (int g = 0; g < C; ++g)
+    for (int t = gstart[g] / NODE_TILE; t < gstart[g + 1] / NODE_TILE; ++t) { ntile_group[t] = (uint8_t)g; node_target[g]++; }
+  if (gstart[C] < nNp) node_target[C - 1] += (nNp - gstart[C]) / NODE_TILE;  // tiny meshes: one padding tile
+  ctx->h_nint = nint;
+  ctx->nTilesE = nTilesE; ctx->nTilesN = nTilesN; ctx->nChunks = C;
+  // ---- shared nodes (internal ids), slots in ascending neighbour order ---------------------------
+  std::vector<int> node_h(nNp, -1), halo_nodes, sendIdxInt(ctx->halo_count);
+  for (int i = 0; i < ctx->halo_count; ++i) sendIdxInt[i] = nint[ctx->h_sendNodeIndex[i]];
+  for (int i = 0; i < nNp; ++i)
+    if (nref[i] >= 0 && is_shared[nref[i]]) { node_h[i] = (int)halo_nodes.size(); halo_nodes.push_back(i); }
+  ctx->nshared = (int)halo_nodes.size();
+  std::vector<int> hoff(ctx->nshared + 1, 0), hslot(ctx->halo_count);
+  for (int i = 0; i < ctx->halo_count; ++i) hoff[node_h[sendIdxInt[i]] + 1]++;
+  for (int h = 0; h < ctx->nshared; ++h) hoff[h + 1] += hoff[h];
+  {
+    std::vector<int> cur(hoff.begin(), hoff.end() - 1);
+    for (int i = 0; i < ctx->halo_count; ++i) hslot[cur[node_h[sendIdxInt[i]]]++] = i;  // slot index is neighbour-major
+  }
+  // ---- CSR node -> (element, slot), ascending CALLER element id (GetForce_3D.cpp:15,39-44) ---------
+  std::vector<int> off(nNp + 1, 0), ent(8 * (size_t)nE);
+  for (size_t i = 0; i < 8 * (size_t)nE; ++i) off[nint[ctx->h_conn[i]] + 1]++;
+  for (int n = 0; n < nNp; ++n) off[n + 1] += off[n];
   {
     std::vector<int> cur(off.begin(), off.end() - 1);
     for (int e = 0; e < nE; ++e)
-      for (int k = 0; k < 8; ++k) ent[cur[ctx->h_conn[8 * (size_t)e + k]]++] = int_of[e] * 8 + k;
+      for (int k = 0; k < 8; ++k) ent[cur[nint[ctx->h_conn[8 * (size_t)e + k]]]++] = int_of[e] * 8 + k;
   }
   // ---- SoA planes ----------------------------------------------------------------------------
   std::vector<int> connT(8 * (size_t)nE), pidI(nE);
   for (int t = 0; t < nE; ++t) {
     const int e = ref_of[t];
-    for (int k = 0; k < 8; ++k) connT[(size_t)k * nE + t] = ctx->h_conn[8 * (size_t)e + k];
+    for (int k = 0; k < 8; ++k) connT[(size_t)k * nE + t] = nint[ctx->h_conn[8 * (size_t)e + k]];
     pidI[t] = ctx->h_pid[e];
   }
-  std::vector<double> Xs(3 * (size_t)nN);
-  for (int n = 0; n < nN; ++n)
-    for (int c = 0; c < 3; ++c) Xs[(size_t)c * nN + n] = ctx->h_X[3 * (size_t)n + c];
+  std::vector<double> Xs(3 * (size_t)nNp, 0.0);
+  for (int i = 0; i < nNp; ++i)
+    if (nref[i] >= 0)
+      for (int c = 0; c < 3; ++c) Xs[(size_t)c * nNp + i] = ctx->h_X[3 * (size_t)nref[i] + c];
   // per-part parameter blocks
   std::vector<double> mp((size_t)nPID * FTB_MP_STRIDE, 0.0);
   std::vector<char> used(nPID, 0);
@@ -427,61 +527,132 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
   // ---- device allocation ---------------------------------------------------------------------
   int rc;
   for (int k = 0; k < 3; ++k) {
-    if ((rc = dalloc(ctx, &ctx->X[k], nN)) || (rc = dalloc(ctx, &ctx->u[k], nN)) || (rc = dalloc(ctx, &ctx->v[k], nN)) ||
-        (rc = dalloc(ctx, &ctx->a[k], nN)) || (rc = dalloc(ctx, &ctx->fi[k], nN)) || (rc = dalloc(ctx, &ctx->du[k], nN)) ||
-        (rc = dalloc(ctx, &ctx->fnet[k], nN)) || (rc = dalloc(ctx, &ctx->d_stage[k], 3 * (size_t)nN)))
+    if ((rc = dalloc(ctx, &ctx->X[k], nNp)) || (rc = dalloc(ctx, &ctx->u[k], nNp)) || (rc = dalloc(ctx, &ctx->v[k], nNp)) ||
+        (rc = dalloc(ctx, &ctx->a[k], nNp)) || (rc = dalloc(ctx, &ctx->fi[k], nNp)) || (rc = dalloc(ctx, &ctx->du[k], nNp)) ||
+        (rc = dalloc(ctx, &ctx->fnet[k], nNp)) || (rc = dalloc(ctx, &ctx->d_stage[k], 3 * (size_t)std::max(nN, nNp))))
       return rc;
-    CK(cudaMemcpy(ctx->X[k], &Xs[(size_t)k * nN], nN * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemset(ctx->u[k], 0, nN * sizeof(double)));
-    CK(cudaMemset(ctx->v[k], 0, nN * sizeof(double)));
-    CK(cudaMemset(ctx->a[k], 0, nN * sizeof(double)));
-    CK(cudaMemset(ctx->fi[k], 0, nN * sizeof(double)));
-    CK(cudaMemset(ctx->du[k], 0, nN * sizeof(double)));
-    CK(cudaMemset(ctx->fnet[k], 0, nN * sizeof(double)));
+    CK(cudaMemcpy(ctx->X[k], &Xs[(size_t)k * nNp], nNp * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->u[k], 0, nNp * sizeof(double)));
+    CK(cudaMemset(ctx->v[k], 0, nNp * sizeof(double)));
+    CK(cudaMemset(ctx->a[k], 0, nNp * sizeof(double)));
+    CK(cudaMemset(ctx->fi[k], 0, nNp * sizeof(double)));
+    CK(cudaMemset(ctx->du[k], 0, nNp * sizeof(double)));
+    CK(cudaMemset(ctx->fnet[k], 0, nNp * sizeof(double)));
   }
-  ctx->node_blocks = cdiv(nN, NODE_BLOCK);
-  if ((rc = dalloc(ctx, &ctx->m, nN)) || (rc = dalloc(ctx, &ctx->flags, nN)) || (rc = dalloc(ctx, &ctx->conn, 8 * (size_t)nE)) ||
+  ctx->node_blocks = cdiv(nNp, NODE_BLOCK);
+  if ((rc = dalloc(ctx, &ctx->m, nNp)) || (rc = dalloc(ctx, &ctx->flags, nNp)) || (rc = dalloc(ctx, &ctx->conn, 8 * (size_t)nE)) ||
       (rc = dalloc(ctx, &ctx->pid, nE)) || (rc = dalloc(ctx, &ctx->ref_of, nE)) || (rc = dalloc(ctx, &ctx->eflag, nE)) ||
       (rc = dalloc(ctx, &ctx->felem, 24 * (size_t)nE)) || (rc = dalloc(ctx, &ctx->mp, mp.size())) ||
-      (rc = dalloc(ctx, &ctx->node_off, nN + 1)) || (rc = dalloc(ctx, &ctx->node_ent, 8 * (size_t)nE)) ||
-      (rc = dalloc(ctx, &ctx->sc, 1)) || (rc = dalloc(ctx, &ctx->epart, 3 * (size_t)ctx->node_blocks)) ||
+      (rc = dalloc(ctx, &ctx->node_off, nNp + 1)) || (rc = dalloc(ctx, &ctx->node_ent, 8 * (size_t)nE)) ||
+      (rc = dalloc(ctx, &ctx->sc, 1)) || (rc = dalloc(ctx, &ctx->epart, 3 * (size_t)std::max(ctx->node_blocks, cdiv(nN, NODE_BLOCK)))) ||
       (rc = dalloc(ctx, &ctx->out3, 4)) || (rc = dalloc(ctx, &ctx->d_istage, 3 * (size_t)nN)) ||
-      (rc = dalloc(ctx, &ctx->d_detmin, 1)) || (rc = dalloc(ctx, &ctx->d_nonpos, 1)))
+      (rc = dalloc(ctx, &ctx->d_detmin, 1)) || (rc = dalloc(ctx, &ctx->d_nonpos, 1)) ||
+      (rc = dalloc(ctx, &ctx->d_nref, nNp)) || (rc = dalloc(ctx, &ctx->d_nint, nN)) || (rc = dalloc(ctx, &ctx->d_ctl, 1)) ||
+      (rc = dalloc(ctx, &ctx->d_etile_chunk, nTilesE)) || (rc = dalloc(ctx, &ctx->d_ntile_group, nTilesN)) ||
+      (rc = dalloc(ctx, &ctx->d_etile, 3 * (size_t)nTilesN)) || (rc = dalloc(ctx, &ctx->d_ell, 8 * (size_t)nNp)))
     return rc;
-  CK(cudaMemset(ctx->m, 0, nN * sizeof(double)));
+  CK(cudaMemset(ctx->m, 0, nNp * sizeof(double)));
   CK(cudaMemset(ctx->eflag, 0, nE));
   CK(cudaMemset(ctx->felem, 0, 24 * (size_t)nE * sizeof(double)));
   CK(cudaMemset(ctx->sc, 0, sizeof(DevScalars)));
+  CK(cudaMemset(ctx->d_etile, 0, 3 * (size_t)nTilesN * sizeof(double)));
   CK(cudaMemcpy(ctx->conn, connT.data(), connT.size() * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->pid, pidI.data(), nE * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->ref_of, ref_of.data(), nE * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->mp, mp.data(), mp.size() * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->node_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->node_ent, ent.data(), ent.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_nref, nref.data(), nNp * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_nint, nint.data(), nN * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_etile_chunk, etile_chunk.data(), nTilesE, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_ntile_group, ntile_group.data(), nTilesN, cudaMemcpyHostToDevice));
+  std::vector<char> overflow(nNp, 0);
+  {
+    std::vector<int> ell(8 * (size_t)nNp, -1);
+    for (int i = 0; i < nNp; ++i) {
+      const int deg = off[i + 1] - off[i];
+      for (int q = 0; q < std::min(deg, 8); ++q) ell[(size_t)q * nNp + i] = ent[off[i] + q];
+      if (deg > 8) overflow[i] = 1;
+    }
+    CK(cudaMemcpy(ctx->d_ell, ell.data(), ell.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  {
+    PipeCtl h;
+    memset(&h, 0, sizeof(h));
+    for (int i = 0; i < PIPE_MAXC; ++i) { h.elem_target[i] = elem_target[i]; h.node_target[i] = node_target[i]; h.need[i] = need[i]; }
+    h.C = C; h.nTilesE = nTilesE; h.nTilesN = nTilesN;
+    h.stop_step = 0;
+    CK(cudaMemcpy(ctx->d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice));
+  }
   if (ctx->has_visco) {  // Hn_1, Hn_2, S0n zero at t = 0 (ShapeFunctions.cpp:245-252)
     const size_t n = (size_t)3 * 6 * 8 * nE;
     if ((rc = dalloc(ctx, &ctx->hist, n))) return rc;
     CK(cudaMemset(ctx->hist, 0, n * sizeof(double)));
   }
-  // flags: shared / not-owned bits (CheckEnergy.cpp:21-33: a shared node is counted by the lowest rank sharing it)
+  // flags: padding nodes are fully constrained and never counted; shared / not-owned bits
+  // (CheckEnergy.cpp:21-33: a shared node is counted by the lowest rank sharing it)
   {
-    std::vector<uint16_t> fl(nN, 0);
-    for (int n : halo_nodes) fl[n] |= FTB_FLAG_SHARED;
+    std::vector<uint16_t> fl(nNp, 0);
+    for (int i = 0; i < nNp; ++i) {
+      if (nref[i] < 0) fl[i] = 7u | FTB_FLAG_NOTOWNED;
+      if (overflow[i]) fl[i] |= FTB_FLAG_OVERFLOW;
+    }
+    for (int i : halo_nodes) fl[i] |= FTB_FLAG_SHARED;
     for (size_t p = 0; p < ctx->h_sendProcessID.size(); ++p)
       if (ctx->h_sendProcessID[p] < ctx->rank)
-        for (int i = ctx->h_sendCum[p]; i < ctx->h_sendCum[p + 1]; ++i) fl[ctx->h_sendNodeIndex[i]] |= FTB_FLAG_NOTOWNED;
-    CK(cudaMemcpy(ctx->flags, fl.data(), nN * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        for (int i = ctx->h_sendCum[p]; i < ctx->h_sendCum[p + 1]; ++i) fl[sendIdxInt[i]] |= FTB_FLAG_NOTOWNED;
+    CK(cudaMemcpy(ctx->flags, fl.data(), nNp * sizeof(uint16_t), cudaMemcpyHostToDevice));
   }
   if (ctx->halo_count) {
     if ((rc = dalloc(ctx, &ctx->d_sendNodeIndex, ctx->halo_count)) || (rc = dalloc(ctx, &ctx->halo_nodes, ctx->nshared)) ||
         (rc = dalloc(ctx, &ctx->halo_off, ctx->nshared + 1)) || (rc = dalloc(ctx, &ctx->halo_slot, ctx->halo_count)) ||
-        (rc = dalloc(ctx, &ctx->halo_node_idx, nN)))
+        (rc = dalloc(ctx, &ctx->halo_node_idx, nNp)))
       return rc;
-    CK(cudaMemcpy(ctx->d_sendNodeIndex, ctx->h_sendNodeIndex.data(), ctx->halo_count * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_sendNodeIndex, sendIdxInt.data(), ctx->halo_count * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->halo_nodes, halo_nodes.data(), ctx->nshared * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->halo_off, hoff.data(), hoff.size() * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->halo_slot, hslot.data(), hslot.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->halo_node_idx, node_h.data(), nN * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->halo_node_idx, node_h.data(), nNp * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  // ---- grids of the two persistent kernels: both must be resident on every SM at the same time ----
+  // Per SM sub-partition (4 per SM, 16384 registers each) the warps of both kernels must fit, and so
+  // must the shared memory (1 KB is reserved per resident block) and the thread slots.
+  {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    cudaFuncAttributes fe, fn;
+    switch (ctx->uniform_mat) {
+      case 1: CK(cudaFuncGetAttributes(&fe, k_elem_pipe<1>)); break;
+      case 4: CK(cudaFuncGetAttributes(&fe, k_elem_pipe<4>)); break;
+      case 5: CK(cudaFuncGetAttributes(&fe, k_elem_pipe<5>)); break;
+      default: CK(cudaFuncGetAttributes(&fe, k_elem_pipe<-1>)); break;
+    }
+    CK(cudaFuncGetAttributes(&fn, k_node_pipe));
+    CK(cudaFuncSetAttribute(k_elem_pipe<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_elem_pipe<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_elem_pipe<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_elem_pipe<-1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_node_pipe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    auto alloc = [](int r) { return ((r + 7) / 8) * 8 * 32; };  // registers per warp, allocation unit 8 per thread
+    const int regs_smsp = prop.regsPerMultiprocessor / 4;
+    const size_t smem_sm = prop.sharedMemPerMultiprocessor;
+    int nb = 1, eb = 0;
+    if (const char* ev = getenv("FTB200_NODE_BLOCKS_PER_SM")) nb = std::max(1, atoi(ev));
+    const int node_warps_smsp = (nb * (NODE_TILE / 32) + 3) / 4;
+    for (int t = 8; t >= 1; --t) {
+      const int elem_warps_smsp = (t * (ELEM_BLOCK / 32) + 3) / 4;
+      const bool regs_ok = elem_warps_smsp * alloc(fe.numRegs) + node_warps_smsp * alloc(fn.numRegs) <= regs_smsp;
+      const bool smem_ok = t * (fe.sharedSizeBytes + 1024) + nb * (fn.sharedSizeBytes + 1024) <= smem_sm;
+      const bool thr_ok = t * ELEM_BLOCK + nb * NODE_TILE <= prop.maxThreadsPerMultiProcessor;
+      if (regs_ok && smem_ok && thr_ok) { eb = t; break; }
+    }
+    if (const char* ev = getenv("FTB200_ELEM_BLOCKS_PER_SM")) eb = std::min(eb, std::max(0, atoi(ev)));
+    // The chunk-pipelined loop (k_elem_pipe || k_node_pipe) is functional and parity-tested but not yet
+    // faster than the serial sequence (per-tile synchronisation latency); opt in with FTB200_PIPE=1.
+    ctx->pipe = false;
+    if (const char* ev = getenv("FTB200_PIPE")) ctx->pipe = eb >= 1 && atoi(ev) != 0;
+    ctx->elem_grid = std::max(1, std::min(prop.multiProcessorCount * std::max(eb, 1), nTilesE));
+    ctx->node_grid = std::max(1, std::min(prop.multiProcessorCount * nb, nTilesN));
   }
   // ---- validate the reference configuration: detJ0 > 0 at every Gauss point --------------------
   {
@@ -490,7 +661,7 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
     CK(cudaMemset(ctx->d_nonpos, 0, sizeof(int)));
     // the per-element masses land in the first 8 planes of felem (scratch until the first force call)
     LAUNCH(k_mass_elem, cdiv(nE, 128), 128, ctx->stream, elem_args(ctx, 0, nE, 1), ctx->felem, ctx->d_detmin, ctx->d_nonpos);
-    LAUNCH(k_mass_gather, cdiv(nN, 256), 256, ctx->stream, ctx->felem, ctx->node_off, ctx->node_ent, ctx->m, nN, nE);
+    LAUNCH(k_mass_gather, cdiv(nNp, 256), 256, ctx->stream, ctx->felem, ctx->node_off, ctx->node_ent, ctx->m, nNp, nE);
     unsigned long long bits = 0;
     int nonpos = 0;
     CK(cudaMemcpyAsync(&bits, ctx->d_detmin, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
@@ -508,7 +679,7 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
 int ftb200_lumped_mass(ftb200_ctx* ctx, double* mass_out) {
   if (!ctx || !ctx->shape_ok) return fail(ctx, FTB200_ERR_INPUT, "lumped_mass: call shape_functions first");
   CK(cudaSetDevice(ctx->device));
-  const int nN = ctx->nN, nE = ctx->nE;
+  const int nN = ctx->nNp, nE = ctx->nE;
   const unsigned long long inf = 0x7FF0000000000000ULL;
   CK(cudaMemcpyAsync(ctx->d_detmin, &inf, sizeof(inf), cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(k_mass_elem, cdiv(nE, 128), 128, ctx->stream, elem_args(ctx, 0, nE, 1), ctx->felem, ctx->d_detmin, ctx->d_nonpos);
@@ -559,10 +730,10 @@ int ftb200_calculate_accelerations(ftb200_ctx* ctx, const int* boundary, double*
   int rc;
   if ((rc = upload_boundary(ctx, boundary))) return rc;
   // a = f_net/m on free dofs into scratch planes, then a masked merge into the caller's array
-  LAUNCH(k_accel, cdiv(ctx->nN, 256), 256, ctx->stream, ctx->fnet[0], ctx->fnet[1], ctx->fnet[2], ctx->m, ctx->flags,
-         ctx->a[0], ctx->a[1], ctx->a[2], ctx->nN);
+  LAUNCH(k_accel, cdiv(ctx->nNp, 256), 256, ctx->stream, ctx->fnet[0], ctx->fnet[1], ctx->fnet[2], ctx->m, ctx->flags,
+         ctx->a[0], ctx->a[1], ctx->a[2], ctx->nNp);
   const size_t n3 = 3 * (size_t)ctx->nN;
-  LAUNCH(k_soa_to_aos, cdiv(ctx->nN, 256), 256, ctx->stream, ctx->a[0], ctx->a[1], ctx->a[2], ctx->d_stage[0], ctx->nN);
+  LAUNCH(k_soa_to_aos, cdiv(ctx->nNp, 256), 256, ctx->stream, ctx->a[0], ctx->a[1], ctx->a[2], ctx->d_stage[0], ctx->d_nref, ctx->nNp);
   CK(cudaMemcpyAsync(ctx->d_stage[1], accelerations, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(k_merge_free, cdiv((long long)n3, 256), 256, ctx->stream, ctx->d_stage[0], ctx->d_stage[1], ctx->d_istage, (int)n3);
   CK(cudaMemcpyAsync(accelerations, ctx->d_stage[1], n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -605,9 +776,9 @@ int ftb200_check_energy(ftb200_ctx* ctx, const double* u, const double* up, cons
     if (hp[i]) CK(cudaMemcpyAsync(dp[i], hp[i], B, cudaMemcpyHostToDevice, ctx->stream));
   }
   CK(cudaMemcpyAsync(ctx->d_istage, boundary, n3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(k_energy_legacy, ctx->node_blocks, NODE_BLOCK, ctx->stream, dp[0], dp[1], dp[2], dp[3], dp[4], dp[5], dp[6], dp[7],
-         dp[8], ctx->d_istage, ctx->m, ctx->flags, ctx->epart, ctx->nN);
-  LAUNCH(k_sum3, 1, 256, ctx->stream, ctx->epart, ctx->node_blocks, ctx->out3);
+  LAUNCH(k_energy_legacy, cdiv(ctx->nN, NODE_BLOCK), NODE_BLOCK, ctx->stream, dp[0], dp[1], dp[2], dp[3], dp[4], dp[5], dp[6], dp[7],
+         dp[8], ctx->d_istage, ctx->m, ctx->flags, ctx->d_nint, ctx->epart, ctx->nN);
+  LAUNCH(k_sum3, 1, 256, ctx->stream, ctx->epart, cdiv(ctx->nN, NODE_BLOCK), ctx->out3);
   CK(cudaMemcpyAsync(out, ctx->out3, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return FTB200_OK;
@@ -664,7 +835,7 @@ int ftb200_get_state(ftb200_ctx* ctx, double* displacements, double* velocities,
       CK(cudaStreamSynchronize(ctx->stream));
     }
   if (boundary) {
-    LAUNCH(k_flags_to_boundary, cdiv(ctx->nN, 256), 256, ctx->stream, ctx->flags, ctx->d_istage, ctx->nN);
+    LAUNCH(k_flags_to_boundary, cdiv(ctx->nNp, 256), 256, ctx->stream, ctx->flags, ctx->d_istage, ctx->d_nref, ctx->nNp);
     CK(cudaMemcpyAsync(boundary, ctx->d_istage, 3 * (size_t)ctx->nN * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   }
@@ -678,7 +849,7 @@ int ftb200_set_bc(ftb200_ctx* ctx, const int* bc_kind, const double bc_rate[4]) 
   for (size_t i = 0; i < n3; ++i)
     if (bc_kind[i] < 0 || bc_kind[i] > 3) return fail(ctx, FTB200_ERR_INPUT, "set_bc: bc_kind[%zu] = %d not in 0..3", i, bc_kind[i]);
   CK(cudaMemcpyAsync(ctx->d_istage, bc_kind, n3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(k_set_bc_kinds, cdiv(ctx->nN, 256), 256, ctx->stream, ctx->d_istage, ctx->flags, ctx->nN);
+  LAUNCH(k_set_bc_kinds, cdiv(ctx->nNp, 256), 256, ctx->stream, ctx->d_istage, ctx->flags, ctx->d_nref, ctx->nNp);
   CK(cudaMemcpyAsync(&ctx->sc->bc_rate[0], bc_rate, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->bc_ok = true;
@@ -718,6 +889,7 @@ int ftb200_explicit_begin(ftb200_ctx* ctx, double Time0, double reduction, doubl
   cudaStream_t s = ctx->stream;
   ctx->energy = energy_every;
   if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+  if (ctx->pgraph) { cudaGraphExecDestroy(ctx->pgraph); ctx->pgraph = nullptr; }
   // scalars: keep bc_rate / hist_cap, reset the rest
   DevScalars h;
   CK(cudaMemcpy(&h, ctx->sc, sizeof(h), cudaMemcpyDeviceToHost));
@@ -730,10 +902,10 @@ int ftb200_explicit_begin(ftb200_ctx* ctx, double Time0, double reduction, doubl
   h.dtmin_bits = 0x7FF0000000000000ULL;
   h.energy_every = energy_every;
   CK(cudaMemcpyAsync(ctx->sc, &h, sizeof(h), cudaMemcpyHostToDevice, s));
-  const int nb = cdiv(ctx->nN, 256);
+  const int nb = cdiv(ctx->nNp, 256);
   // ApplyBoundaryConditions(Time0) (Benchmarking-Parallel.cpp:83)
   LAUNCH(k_apply_bc, nb, 256, s, ctx->u[0], ctx->u[1], ctx->u[2], ctx->v[0], ctx->v[1], ctx->v[2], ctx->a[0], ctx->a[1],
-         ctx->a[2], ctx->flags, ctx->sc, Time0, ctx->nN);
+         ctx->a[2], ctx->flags, ctx->sc, Time0, ctx->nNp);
   LAUNCH(k_eflag, cdiv(ctx->nE, 256), 256, s, ctx->conn, ctx->flags, ctx->eflag, ctx->nE);
   // dt = reduction * StableTimeStep() (:86) -- before GetForce because material 5 reads dt
   launch_elem<false, true>(ctx, s, 0, ctx->nE, 1);
@@ -742,6 +914,12 @@ int ftb200_explicit_begin(ftb200_ctx* ctx, double Time0, double reduction, doubl
   launch_elem<true, false>(ctx, s, 0, ctx->nE, 1);
   const NodeArgs N = node_args(ctx, nullptr);
   LAUNCH((k_node<true, false, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+  {
+    const long long zero = 0;
+    CK(cudaMemcpyAsync(&ctx->d_ctl->elem_step, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(&ctx->d_ctl->node_step, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(&ctx->d_ctl->stop_step, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
+  }
   int status = 0;
   CK(cudaMemcpyAsync(&status, &ctx->sc->status, sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -768,12 +946,54 @@ static int build_graph(ftb200_ctx* ctx) {
   return 0;
 }
 
+static int build_pipe_graph(ftb200_ctx* ctx) {
+  if (ctx->pgraph && ctx->pgraph_energy == ctx->energy) return 0;
+  if (ctx->pgraph) { cudaGraphExecDestroy(ctx->pgraph); ctx->pgraph = nullptr; }
+  cudaGraph_t g = nullptr;
+  const long long before = ctx->launches;
+  CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  launch_pipe_steps(ctx, GRAPH_STEPS);
+  cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+  ctx->launches = before;
+  if (e != cudaSuccess) return fail(ctx, FTB200_ERR_CUDA, "pipeline graph capture failed: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&ctx->pgraph, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) { ctx->pgraph = nullptr; return fail(ctx, FTB200_ERR_CUDA, "pipeline graph instantiate failed: %s", cudaGetErrorString(e)); }
+  ctx->pgraph_energy = ctx->energy;
+  return 0;
+}
+
+static int run_async_pipe(ftb200_ctx* ctx, double tMax, long long steps) {
+  cudaStream_t s = ctx->stream;
+  LAUNCH(k_pipe_begin, 1, 1, s, ctx->sc, ctx->d_ctl, tMax, steps);
+  long long left = steps;
+  const bool use_graph = !ctx->profile && steps >= GRAPH_STEPS;
+  if (use_graph) {
+    int rc = build_pipe_graph(ctx);
+    if (rc) return rc;
+  }
+  while (left > 0) {
+    if (use_graph && left >= GRAPH_STEPS) {
+      CK(cudaGraphLaunch(ctx->pgraph, s));
+      ctx->launches += 2LL * GRAPH_STEPS;
+      left -= GRAPH_STEPS;
+    } else {
+      const int n = (int)std::min<long long>(left, GRAPH_STEPS);
+      launch_pipe_steps(ctx, n);
+      left -= n;
+    }
+  }
+  CK(cudaGetLastError());
+  return FTB200_OK;
+}
+
 int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
   if (!ctx || !ctx->begun) return fail(ctx, FTB200_ERR_INPUT, "explicit_run: call explicit_begin first");
   if (ctx->halo_count && ctx->nranks > 1)
     return fail(ctx, FTB200_ERR_INPUT, "explicit_run: this rank has shared nodes; drive the loop with step_begin/step_end");
   CK(cudaSetDevice(ctx->device));
   if (steps <= 0) return FTB200_OK;
+  if (ctx->pipe) return run_async_pipe(ctx, tMax, steps);
   cudaStream_t s = ctx->stream;
   LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
   {
@@ -813,6 +1033,7 @@ int ftb200_explicit_poll(ftb200_ctx* ctx, long long* steps_done, double* Time, d
   if (Time) *Time = h.Time;
   if (dt) *dt = h.ndt;
   if (status_bits) *status_bits = h.status;
+  if (h.status & 32) return fail(ctx, FTB200_ERR_CUDA, "pipelined loop stalled: element and node kernels were not co-resident");
   return FTB200_OK;
 }
 
@@ -869,7 +1090,7 @@ int ftb200_halo_add(ftb200_ctx* ctx, int field, const double* recv_dev) {
   if (!ctx->halo_count) return FTB200_OK;
   if (field == 1) {
     // mass: one value per node; the three received dofs are identical, add component 0
-    LAUNCH(k_halo_add, cdiv(ctx->nshared, 256), 256, ctx->stream, ctx->m, ctx->d_stage[2], ctx->d_stage[2] + ctx->nN,
+    LAUNCH(k_halo_add, cdiv(ctx->nshared, 256), 256, ctx->stream, ctx->m, ctx->d_stage[2], ctx->d_stage[2] + ctx->nNp,
            ctx->halo_nodes, ctx->halo_off, ctx->halo_slot, recv_dev, ctx->nshared);
   } else {
     LAUNCH(k_halo_add, cdiv(ctx->nshared, 256), 256, ctx->stream, ctx->fi[0], ctx->fi[1], ctx->fi[2], ctx->halo_nodes,
@@ -915,6 +1136,75 @@ int ftb200_profile_get(ftb200_ctx* ctx, double* elem_ms, double* node_ms, long l
   if (node_ms) *node_ms = ctx->prof_node_n ? ctx->prof_node_ms / ctx->prof_node_n : 0.0;
   if (elem_launches) *elem_launches = ctx->prof_elem_n;
   if (node_launches) *node_launches = ctx->prof_node_n;
+  return FTB200_OK;
+}
+
+// Tuning experiment (not part of the public ABI): run the element kernel and the node kernel
+// concurrently on two streams, `reps` times, and report the elapsed time per pair.
+int ftb200_debug_overlap(ftb200_ctx* ctx, int reps, int concurrent, double* ms_per_pair) {
+  if (!ctx || !ctx->begun) return FTB200_ERR_INPUT;
+  CK(cudaSetDevice(ctx->device));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  cudaStream_t s = ctx->stream, s2 = ctx->stream2;
+  const NodeArgs N = node_args(ctx, nullptr);
+  CK(cudaStreamSynchronize(s));
+  CK(cudaEventRecord(e0, s));
+  for (int r = 0; r < reps; ++r) {
+    if (concurrent) {
+      CK(cudaEventRecord(ctx->ev_fork, s));
+      CK(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+      LAUNCH((k_node<true, false, false, false>), ctx->node_blocks, NODE_BLOCK, s2, N);
+      launch_elem<true, true>(ctx, s, 0, ctx->nE, 1);
+      CK(cudaEventRecord(ctx->ev_join, s2));
+      CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    } else {
+      launch_elem<true, true>(ctx, s, 0, ctx->nE, 1);
+      LAUNCH((k_node<true, false, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+    }
+  }
+  CK(cudaEventRecord(e1, s));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_per_pair = ms / reps;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return FTB200_OK;
+}
+
+// Tuning probe (not part of the public ABI): time one of the pipe kernels alone (which = 0 element,
+// 1 node), all dependencies pre-satisfied.  Leaves the state advanced by `reps` pseudo-steps.
+int ftb200_debug_pipe(ftb200_ctx* ctx, int which, int reps, double* ms_per_launch) {
+  if (!ctx || !ctx->begun) return FTB200_ERR_INPUT;
+  CK(cudaSetDevice(ctx->device));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  cudaStream_t s = ctx->stream;
+  PipeElemArgs PE;
+  PE.E = elem_args(ctx, 0, ctx->nE, 0);
+  for (int k = 0; k < 3; ++k) { PE.v[k] = ctx->v[k]; PE.a[k] = ctx->a[k]; }
+  PE.flags = ctx->flags; PE.tile_chunk = ctx->d_etile_chunk; PE.ctl = ctx->d_ctl; PE.dt_hist = nullptr; PE.nPID = ctx->nPID;
+  PipeNodeArgs PN;
+  PN.N = node_args(ctx, nullptr);
+  PN.ell = ctx->d_ell; PN.tile_group = ctx->d_ntile_group; PN.ctl = ctx->d_ctl; PN.etile = ctx->d_etile; PN.ehist = nullptr; PN.energy = ctx->energy;
+  float total = 0;
+  for (int r = 0; r < reps; ++r) {
+    LAUNCH(k_pipe_debug_arm, 1, 1, s, ctx->d_ctl, ctx->sc);
+    CK(cudaEventRecord(e0, s));
+    if (which == 0) LAUNCH((k_elem_pipe<1>), ctx->elem_grid, ELEM_BLOCK, s, PE);
+    else LAUNCH(k_node_pipe, ctx->node_grid, NODE_TILE, s, PN);
+    CK(cudaEventRecord(e1, s));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    total += ms;
+  }
+  *ms_per_launch = total / reps;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return FTB200_OK;
 }
 

@@ -28,6 +28,7 @@ namespace ftb {
 // bit 12 = node is shared with another rank; bit 13 = energy of this node is owned by a lower rank
 #define FTB_FLAG_SHARED 0x1000
 #define FTB_FLAG_NOTOWNED 0x2000
+#define FTB_FLAG_OVERFLOW 0x4000  // node has more than 8 elements: entries 9.. are read from the CSR arrays
 
 struct DevScalars {
   double Time;                      // end time of the last finished step
@@ -434,42 +435,50 @@ __global__ void k_energy(DevScalars* sc, const double* epart, int nblocks, doubl
 }
 
 // ---------------------------------------------------------------------------------------------
-// layout conversion at the API boundary (host arrays are AoS xyz, GlobalVariables.h)
-__global__ void k_aos_to_soa(const double* __restrict__ aos, double* x, double* y, double* z, int n) {
+// layout conversion at the API boundary (host arrays are AoS xyz in the caller's node numbering,
+// GlobalVariables.h; device planes use the internal node order, nref[i] = caller's id or -1 for padding)
+__global__ void k_aos_to_soa(const double* __restrict__ aos, double* x, double* y, double* z, const int* __restrict__ nref, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { x[i] = aos[3 * (size_t)i]; y[i] = aos[3 * (size_t)i + 1]; z[i] = aos[3 * (size_t)i + 2]; }
+  if (i >= n) return;
+  const int r = nref[i];
+  if (r >= 0) { x[i] = aos[3 * (size_t)r]; y[i] = aos[3 * (size_t)r + 1]; z[i] = aos[3 * (size_t)r + 2]; }
 }
 __global__ void k_soa_to_aos(const double* __restrict__ x, const double* __restrict__ y,
-                             const double* __restrict__ z, double* aos, int n) {
+                             const double* __restrict__ z, double* aos, const int* __restrict__ nref, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { aos[3 * (size_t)i] = x[i]; aos[3 * (size_t)i + 1] = y[i]; aos[3 * (size_t)i + 2] = z[i]; }
+  if (i >= n) return;
+  const int r = nref[i];
+  if (r >= 0) { aos[3 * (size_t)r] = x[i]; aos[3 * (size_t)r + 1] = y[i]; aos[3 * (size_t)r + 2] = z[i]; }
 }
-__global__ void k_boundary_to_flags(const int* __restrict__ boundary, uint16_t* flags, int n) {
+__global__ void k_boundary_to_flags(const int* __restrict__ boundary, uint16_t* flags, const int* __restrict__ nref, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    unsigned f = flags[i] & ~7u;
-    f |= (boundary[3 * (size_t)i] ? 1u : 0u) | (boundary[3 * (size_t)i + 1] ? 2u : 0u) | (boundary[3 * (size_t)i + 2] ? 4u : 0u);
-    flags[i] = (uint16_t)f;
-  }
+  if (i >= n) return;
+  const int r = nref[i];
+  if (r < 0) return;
+  unsigned f = flags[i] & ~7u;
+  f |= (boundary[3 * (size_t)r] ? 1u : 0u) | (boundary[3 * (size_t)r + 1] ? 2u : 0u) | (boundary[3 * (size_t)r + 2] ? 4u : 0u);
+  flags[i] = (uint16_t)f;
 }
-__global__ void k_flags_to_boundary(const uint16_t* __restrict__ flags, int* boundary, int n) {
+__global__ void k_flags_to_boundary(const uint16_t* __restrict__ flags, int* boundary, const int* __restrict__ nref, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const unsigned f = flags[i];
-    boundary[3 * (size_t)i] = f & 1u; boundary[3 * (size_t)i + 1] = (f >> 1) & 1u; boundary[3 * (size_t)i + 2] = (f >> 2) & 1u;
-  }
+  if (i >= n) return;
+  const int r = nref[i];
+  if (r < 0) return;
+  const unsigned f = flags[i];
+  boundary[3 * (size_t)r] = f & 1u; boundary[3 * (size_t)r + 1] = (f >> 1) & 1u; boundary[3 * (size_t)r + 2] = (f >> 2) & 1u;
 }
-__global__ void k_set_bc_kinds(const int* __restrict__ kind, uint16_t* flags, int n) {
+__global__ void k_set_bc_kinds(const int* __restrict__ kind, uint16_t* flags, const int* __restrict__ nref, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    unsigned f = flags[i] & ~0x3F0u;
+  if (i >= n) return;
+  const int r = nref[i];
+  if (r < 0) return;
+  unsigned f = flags[i] & ~0x3F0u;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const unsigned k = (unsigned)kind[3 * (size_t)i + c] & 3u;
-      f |= k << (4 + 2 * c);
-    }
-    flags[i] = (uint16_t)f;
+  for (int c = 0; c < 3; ++c) {
+    const unsigned k = (unsigned)kind[3 * (size_t)r + c] & 3u;
+    f |= k << (4 + 2 * c);
   }
+  flags[i] = (uint16_t)f;
 }
 // ApplyBoundaryConditions at a given Time (Benchmarking-Parallel.cpp:184-244)
 __global__ void k_apply_bc(double* ux, double* uy, double* uz, double* vx, double* vy, double* vz, double* ax,
@@ -690,11 +699,12 @@ __global__ void k_gp_outputs(const ElemArgs A, const int* ref_of, double* F, dou
 // K8 for the legacy CheckEnergy call: all operands supplied by the host (AoS, staged on the device)
 __global__ void k_energy_legacy(const double* u, const double* up, const double* v, const double* a, const double* ap,
                                 const double* fi, const double* fip, const double* fe, const double* fep,
-                                const int* boundary, const double* m, const uint16_t* flags, double* epart, int nN) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+                                const int* boundary, const double* m, const uint16_t* flags, const int* nint,
+                                double* epart, int nN) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;  // caller's node id
   double wke = 0, wint = 0, wext = 0;
-  if (n < nN && !(flags[n] & FTB_FLAG_NOTOWNED)) {
-    const double mm = m[n];
+  if (n < nN && !(flags[nint[n]] & FTB_FLAG_NOTOWNED)) {
+    const double mm = m[nint[n]];
     for (int c = 0; c < 3; ++c) {
       const size_t i = 3 * (size_t)n + c;
       const double dd = u[i] - up[i];
@@ -730,6 +740,438 @@ __global__ void k_sum3(const double* epart, int nblocks, double* out3) {
     __syncthreads();
   }
   if (threadIdx.x == 0) { out3[0] = 0.5 * sh[0][0]; out3[1] = 0.5 * sh[1][0]; out3[2] = 0.5 * sh[2][0]; }
+}
+
+// =============================================================================================
+// Pipelined resident loop: two PERSISTENT kernels per step running concurrently on two streams.
+//
+//   k_elem_pipe (fp64 bound)  tiles of 64 elements, in chunk order: gathers X,u,v,a,flags of the 8 nodes,
+//                             performs the first kick + drift + BC of the step on the fly (so the node
+//                             arrays are only read), element forces -> felem, element dt -> min.  Its last
+//                             block does the scalar bookkeeping of the time loop (old k_adv).
+//   k_node_pipe (HBM bound)   tiles of 128 nodes, in group order: node group g holds the nodes whose
+//                             elements all lie in chunks <= g, so it may run as soon as k_elem_pipe has
+//                             finished chunk g of the SAME step -- while later chunks are still being
+//                             computed.  Repeats the (bitwise identical) drift, gathers f_int through the CSR
+//                             map, a = f/m, second kick, energy partials; writes u, v, a.
+//
+// Dependencies are tracked with per-chunk completion counters in device memory (release: stores ->
+// __syncthreads -> __threadfence -> atomicAdd; acquire: volatile poll -> __threadfence -> __syncthreads ->
+// ld.cg loads).  k_elem_pipe of step m+1 waits, per tile, for the node groups of step m that its
+// elements touch (`need`), so the fp64 pipe never drains at a step boundary except for the dt reduction.
+// Both grids are sized to be co-resident on every SM and take tiles from an atomic ticket, so any
+// resident subset of blocks makes progress (no scheduling-order deadlock).
+constexpr int PIPE_MAXC = 64;
+constexpr int NODE_TILE = 128;
+
+struct StepScal {
+  double t_n, t_np1, t_half, dt;
+};
+struct PipeCtl {
+  unsigned elem_done[2][PIPE_MAXC];
+  unsigned node_done[2][PIPE_MAXC];
+  unsigned elem_prefix[2];
+  unsigned node_prefix[2];
+  unsigned elem_ticket[2];
+  unsigned node_ticket[2];
+  unsigned elem_blocks_done, node_blocks_done;
+  unsigned elem_target[PIPE_MAXC];  // tiles per element chunk
+  unsigned node_target[PIPE_MAXC];  // tiles per node group
+  unsigned need[PIPE_MAXC];         // element chunk c needs node groups <= need[c] of the previous step
+  int C;
+  int nTilesE, nTilesN;
+  long long elem_step, node_step, stop_step;  // index of the next step of either kernel / first step not to run
+  StepScal scal[2];                 // scal[m & 1]: times of step m
+};
+
+__device__ __forceinline__ void pipe_advance(unsigned* prefix, const unsigned* done, const unsigned* target, int C) {
+  for (;;) {
+    const unsigned p = *(volatile unsigned*)prefix;
+    if ((int)p >= C) break;
+    if (*(volatile const unsigned*)&done[p] != target[p]) break;
+    atomicCAS(prefix, p, p + 1);
+  }
+}
+__device__ __forceinline__ unsigned long long pipe_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// wait until *prefix > need_gt.  Bounded: if the two kernels are not co-resident (they must be, see the
+// grid sizing in ftb200_shape_functions) the wait gives up after 2 s, flags status bit 32 and stops the
+// loop instead of hanging the device.
+__device__ __forceinline__ bool pipe_wait(const unsigned* prefix, unsigned need_gt, DevScalars* sc, PipeCtl* ctl) {
+  if (*(volatile const unsigned*)prefix <= need_gt) {
+    const unsigned long long t0 = pipe_now_ns();
+    while (*(volatile const unsigned*)prefix <= need_gt) {
+      __nanosleep(40);
+      if (pipe_now_ns() - t0 > 2000000000ULL || (*(volatile int*)&sc->status & 32)) {
+        atomicOr(&sc->status, 32);
+        *(volatile long long*)&ctl->stop_step = 0;
+        return false;
+      }
+    }
+  }
+  __threadfence();
+  return true;
+}
+
+// first kick + drift + BC of one dof (Benchmarking-Parallel.cpp:115-122,131-135,184-244).  Explicit
+// intrinsics: k_elem_pipe and k_node_pipe must produce the SAME bits.
+__device__ __forceinline__ double pipe_drift(const double u, const double v, const double a, const bool b,
+                                             const unsigned kind, const double dt1, const double dt, const double T,
+                                             const double* __restrict__ bc_rate) {
+  double un = u;
+  if (!b) un = __fma_rn(dt, __fma_rn(dt1, a, v), u);
+  if (kind) un = __dmul_rn(T, bc_rate[kind]);
+  return un;
+}
+
+struct PipeElemArgs {
+  ElemArgs E;
+  const double* v[3];
+  const double* a[3];
+  const uint16_t* flags;
+  const uint8_t* tile_chunk;  // element tile -> chunk
+  PipeCtl* ctl;
+  double* dt_hist;
+  int nPID;
+};
+
+#ifndef FTB_PIPE_ELEM_REGS
+#define FTB_PIPE_ELEM_REGS 136
+#endif
+// 136 registers: three warps of this kernel use 13056 of the 16384 registers of an SM sub-partition and
+// leave room for one warp of k_node_pipe (<= 96 registers) -- the two kernels must be co-resident.
+template <int MATSEL>
+__global__ void __maxnreg__(FTB_PIPE_ELEM_REGS) k_elem_pipe(const PipeElemArgs P) {
+  const ElemArgs& A = P.E;
+  PipeCtl* ctl = P.ctl;
+  DevScalars* sc = A.sc;
+  const long long m = *(volatile long long*)&ctl->elem_step;
+  if (m >= *(volatile long long*)&ctl->stop_step) return;
+  const int p = (int)(m & 1);
+  const StepScal S = ctl->scal[p];
+  const double dt1 = S.t_half - S.t_n;
+  __shared__ double sm_cols[72][ELEM_BLOCK];
+  __shared__ unsigned s_tile;
+  __shared__ int s_last, s_ok;
+  const size_t E = (size_t)A.nE;
+  int status = 0;
+  unsigned long long bmin = 0x7FF0000000000000ULL;
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ctl->elem_ticket[p], 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    if (tile >= (unsigned)ctl->nTilesE) break;
+    const int c = P.tile_chunk[tile];
+    const int e = (int)(tile * ELEM_BLOCK + threadIdx.x);
+    int nd[8];
+    if (e < A.nE) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) nd[k] = __ldg(A.conn + (size_t)k * E + e);
+    }
+    // the node groups of the previous step that this chunk touches must be complete
+    if (threadIdx.x == 0) s_ok = pipe_wait(&ctl->node_prefix[p ^ 1], ctl->need[c], sc, ctl) ? 1 : 0;
+    __syncthreads();
+    if (!s_ok) return;
+    double dte = 1e300;
+    if (e < A.nE) {
+      double X[8][3], U[8][3];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const unsigned fl = P.flags[nd[k]];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          X[k][cc] = __ldg(A.X[cc] + nd[k]);
+          // plain (L1-allocating) loads are safe: a 128-byte line holds 16 consecutive nodes of ONE node
+          // tile, i.e. of one group, and this tile has waited for every group it touches
+          const double u = A.u[cc][nd[k]];
+          const double v = P.v[cc][nd[k]];
+          const double a = P.a[cc][nd[k]];
+          U[k][cc] = pipe_drift(u, v, a, (fl >> cc) & 1u, (fl >> (4 + 2 * cc)) & 3u, dt1, S.dt, S.t_np1, sc->bc_rate);
+        }
+      }
+      const int pp = __ldg(A.pid + e);
+      const double* mp = A.mp + (size_t)pp * FTB_MP_STRIDE;
+      const int mat = (MATSEL >= 0) ? MATSEL : (int)mp[MP_MATID];
+      double fe[8][3];
+      DevHist h{A.hist, E, (size_t)e};
+      SmemScratch Sc{&sm_cols[0][threadIdx.x]};
+      double d;
+      status |= hex8_element<MATSEL, true>(X, U, mat, mp, true, h, NoOutput(), Sc, fe, &d);
+      dte = d;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) __stcg(A.felem + (size_t)(3 * k + cc) * E + e, fe[k][cc]);
+      if (__ldg(A.eflag + e)) dte = 1e300;  // element skipped, StableTimeStep.cpp:13-19
+    }
+    unsigned long long b = dt_to_bits(dte);
+    bmin = b < bmin ? b : bmin;
+    __syncthreads();  // every store of the tile has been issued
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned old = atomicAdd(&ctl->elem_done[p][c], 1u);
+      if (old + 1 == ctl->elem_target[c]) pipe_advance(&ctl->elem_prefix[p], ctl->elem_done[p], ctl->elem_target, ctl->C);
+    }
+  }
+  // element dt: one atomic per warp for the whole kernel
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, bmin, o);
+    bmin = t < bmin ? t : bmin;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMin(&sc->dtmin_bits, bmin);
+  if (status) atomicOr(&sc->status, status);
+  // ---- last block: scalar bookkeeping of the time loop (Benchmarking-Parallel.cpp:106-112,168; StableTimeStep.cpp:33-38)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&ctl->elem_blocks_done, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __shared__ double s_ndt;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    double dtmin = __longlong_as_double((long long)*(volatile unsigned long long*)&sc->dtmin_bits);
+    if (dtmin > 1e20) dtmin = 1e20;
+    sc->dtmin_bits = 0x7FF0000000000000ULL;
+    // step m is complete as far as the elements are concerned
+    sc->t_n = S.t_n; sc->t_np1 = S.t_np1; sc->t_half = S.t_half; sc->dt = S.dt;
+    sc->Time = S.t_np1;
+    if (P.dt_hist && sc->step < sc->hist_cap) P.dt_hist[sc->step] = S.dt;
+    sc->step += 1;
+    sc->steps_left -= 1;
+    int stop = 0;
+    if (dtmin < sc->failure_dt) { sc->status |= 16; stop = 1; }  // TerminateFemTech(19)
+    const double ndt = sc->reduction * dtmin;
+    StepScal N;
+    N.t_n = S.t_np1; N.dt = ndt; N.t_np1 = S.t_np1 + ndt; N.t_half = 0.5 * (N.t_np1 + N.t_n);
+    ctl->scal[p ^ 1] = N;
+    sc->ndt = ndt; sc->nt_n = N.t_n; sc->nt_np1 = N.t_np1; sc->nt_half = N.t_half;
+    if (!(sc->Time < sc->tMax) || sc->steps_left <= 0) stop = 1;
+    if (stop) ctl->stop_step = m + 1;
+    // recycle the counters of the other parity (their readers are done: every tile above waited for them)
+    for (int i = 0; i < ctl->C; ++i) { ctl->elem_done[p ^ 1][i] = 0; ctl->node_done[p ^ 1][i] = 0; }
+    ctl->elem_prefix[p ^ 1] = 0; ctl->node_prefix[p ^ 1] = 0;
+    // tickets are recycled by the kernel that draws them (every block of THIS launch has left its loop);
+    // a straggler of k_node_pipe(m-1) may still draw from node_ticket[p ^ 1]
+    ctl->elem_ticket[p] = 0;
+    pipe_advance(&ctl->elem_prefix[p ^ 1], ctl->elem_done[p ^ 1], ctl->elem_target, ctl->C);
+    pipe_advance(&ctl->node_prefix[p ^ 1], ctl->node_done[p ^ 1], ctl->node_target, ctl->C);
+    ctl->elem_blocks_done = 0;
+    s_ndt = ndt;
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < P.nPID; q += ELEM_BLOCK) {  // Prony factors of the next dt
+    double* mq = const_cast<double*>(A.mp) + (size_t)q * FTB_MP_STRIDE;
+    if ((int)mq[MP_MATID] == 5) {
+      const double rt1 = s_ndt / mq[MP_T1], rt2 = s_ndt / mq[MP_T2];
+      const double c11 = exp(-rt1), c12 = exp(-rt2);
+      mq[MP_C11] = c11; mq[MP_C12] = c12;
+      mq[MP_C21] = mq[MP_G1] * (1 - c11) / rt1;
+      mq[MP_C22] = mq[MP_G2] * (1 - c12) / rt2;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    *(volatile long long*)&ctl->elem_step = m + 1;
+  }
+}
+
+struct PipeNodeArgs {
+  NodeArgs N;
+  const int* ell;             // [8][nN] first eight CSR entries of every node (-1 = none), plane q = q-th entry
+  const uint8_t* tile_group;  // node tile -> group
+  PipeCtl* ctl;
+  double* etile;              // [3][nTilesN] energy partials per node tile
+  double* ehist;
+  int energy;
+};
+
+__global__ void __maxnreg__(96) k_node_pipe(const PipeNodeArgs P) {
+  const NodeArgs& A = P.N;
+  PipeCtl* ctl = P.ctl;
+  DevScalars* sc = A.sc;
+  const long long m = *(volatile long long*)&ctl->node_step;
+  if (m >= *(volatile long long*)&ctl->stop_step) return;
+  const int p = (int)(m & 1);
+  const StepScal S = ctl->scal[p];
+  const double dt1 = S.t_half - S.t_n, dt2 = S.t_np1 - S.t_half;
+  __shared__ unsigned s_tile;
+  __shared__ int s_last, s_ok;
+  __shared__ double sw[3][NODE_TILE / 32];
+  const size_t E = (size_t)A.nE;
+  const int nT = ctl->nTilesN;
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ctl->node_ticket[p], 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    if (tile >= (unsigned)nT) break;
+    const int g = P.tile_group[tile];
+    const int n = (int)(tile * NODE_TILE + threadIdx.x);
+    // state of the previous step (written by an earlier kernel) can be loaded before the wait
+    const unsigned fl = A.flags[n];
+    double uu[3], vv[3], aa[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { uu[c] = __ldcg(A.u[c] + n); vv[c] = __ldcg(A.v[c] + n); aa[c] = __ldcg(A.a[c] + n); }
+    const double mass = A.m[n];
+    // static gather map in ELL form (eight entries per node, coalesced planes): no dependent offset load,
+    // so everything above and these entries are ONE round of independent loads issued before the wait
+    int ent[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ent[q] = __ldg(P.ell + (size_t)q * A.nN + n);
+    if (threadIdx.x == 0) s_ok = pipe_wait(&ctl->elem_prefix[p], (unsigned)g, sc, ctl) ? 1 : 0;
+    __syncthreads();
+    if (!s_ok) return;
+    // 24 independent loads in flight per thread, then the sum in ascending element order
+    // (GetForce_3D.cpp:15,39-44); adding an exact 0.0 for a missing entry does not change the result
+    double fv[8][3];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const size_t e = (size_t)((ent[q] < 0 ? 0 : ent[q]) >> 3);
+      const int sl = (ent[q] < 0 ? 0 : ent[q]) & 7;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) fv[q][c] = (ent[q] >= 0) ? A.felem[(size_t)(3 * sl + c) * E + e] : 0.0;
+    }
+    double f[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) f[c] += fv[q][c];
+    if (fl & FTB_FLAG_OVERFLOW)
+    for (int j = A.node_off[n] + 8, j1 = A.node_off[n + 1]; j < j1; ++j) {
+      const int en = __ldg(A.node_ent + j);
+      const size_t e = (size_t)(en >> 3);
+      const int sl = en & 7;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) f[c] += A.felem[(size_t)(3 * sl + c) * E + e];
+    }
+    double wke = 0.0, wint = 0.0, wext = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const bool b = (fl >> c) & 1u;
+      const unsigned kind = (fl >> (4 + 2 * c)) & 3u;
+      const double u_old = uu[c], a_old = kind ? 0.0 : aa[c];
+      const double un = pipe_drift(u_old, vv[c], aa[c], b, kind, dt1, S.dt, S.t_np1, sc->bc_rate);
+      double vn = vv[c], an = aa[c];
+      if (kind) { vn = sc->bc_rate[kind]; an = 0.0; }  // ApplyBoundaryConditions, :184-244
+      const double fext = A.fe[c] ? A.fe[c][n] : 0.0;
+      const double fnet = fext - f[c];                 // GetForce_3D.cpp:11,49-51
+      if (!b) {
+        const double vhalf = __fma_rn(dt1, aa[c], vv[c]);
+        an = fnet / mass;                              // CalculateAcclerations.cpp:7-11
+        vn = vhalf + dt2 * an;                         // :146-151
+      }
+      if (P.energy && !(fl & FTB_FLAG_NOTOWNED)) {     // CheckEnergy.cpp:19-52
+        const double dd = un - u_old;
+        const double fprev = A.fi[c][n];
+        wke += mass * vn * vn;
+        if (b) wext += dd * (fprev + f[c] + mass * (an + a_old));
+        wint += dd * (fprev + f[c]);
+        wext += dd * (fext + fext);
+      }
+      A.u[c][n] = un; A.v[c][n] = vn; A.a[c][n] = an;
+      if (A.store_fi) A.fi[c][n] = f[c];
+    }
+    if (P.energy) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        wke += __shfl_down_sync(0xffffffffu, wke, o);
+        wint += __shfl_down_sync(0xffffffffu, wint, o);
+        wext += __shfl_down_sync(0xffffffffu, wext, o);
+      }
+      if ((threadIdx.x & 31) == 0) { sw[0][threadIdx.x >> 5] = wke; sw[1][threadIdx.x >> 5] = wint; sw[2][threadIdx.x >> 5] = wext; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (P.energy) {
+        double s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int w = 0; w < NODE_TILE / 32; ++w) { s0 += sw[0][w]; s1 += sw[1][w]; s2 += sw[2][w]; }
+        P.etile[tile] = s0; P.etile[nT + tile] = s1; P.etile[2 * nT + tile] = s2;
+      }
+      __threadfence();
+      const unsigned old = atomicAdd(&ctl->node_done[p][g], 1u);
+      if (old + 1 == ctl->node_target[g]) pipe_advance(&ctl->node_prefix[p], ctl->node_done[p], ctl->node_target, ctl->C);
+    }
+  }
+  // ---- last block: fixed-order energy reduction (K8) and step counter
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&ctl->node_blocks_done, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (P.energy) {
+    __shared__ double sh[3][NODE_TILE];
+    __threadfence();
+    double s[3] = {0, 0, 0};
+    for (int i = threadIdx.x; i < nT; i += NODE_TILE) {
+      s[0] += __ldcg(P.etile + i); s[1] += __ldcg(P.etile + nT + i); s[2] += __ldcg(P.etile + 2 * nT + i);
+    }
+    sh[0][threadIdx.x] = s[0]; sh[1][threadIdx.x] = s[1]; sh[2][threadIdx.x] = s[2];
+    __syncthreads();
+    for (int o = NODE_TILE / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+        sh[2][threadIdx.x] += sh[2][threadIdx.x + o];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const double WKE = 0.5 * sh[0][0];
+      sc->Wint += 0.5 * sh[1][0];
+      sc->Wext += 0.5 * sh[2][0];
+      sc->WKE = WKE;
+      sc->Etot = fabs(WKE + sc->Wint - sc->Wext);
+      if (P.ehist && m >= 0 && m < sc->hist_cap) {
+        P.ehist[4 * m + 0] = sc->Wint; P.ehist[4 * m + 1] = sc->Wext; P.ehist[4 * m + 2] = WKE; P.ehist[4 * m + 3] = sc->Etot;
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    ctl->node_blocks_done = 0;
+    ctl->node_ticket[p] = 0;  // every block of this launch has left its loop
+    __threadfence();
+    *(volatile long long*)&ctl->node_step = m + 1;
+  }
+}
+
+// tuning probe: mark every chunk / group complete so that one of the pipe kernels can be timed alone
+__global__ void k_pipe_debug_arm(PipeCtl* ctl, DevScalars* sc) {
+  for (int q = 0; q < 2; ++q) {
+    for (int i = 0; i < ctl->C; ++i) { ctl->elem_done[q][i] = ctl->elem_target[i]; ctl->node_done[q][i] = ctl->node_target[i]; }
+    ctl->elem_prefix[q] = ctl->C; ctl->node_prefix[q] = ctl->C; ctl->elem_ticket[q] = 0; ctl->node_ticket[q] = 0;
+  }
+  ctl->elem_blocks_done = 0; ctl->node_blocks_done = 0;
+  ctl->stop_step = 0x7FFFFFFFFFFFFFFFLL;
+  sc->steps_left = 1 << 30;
+  sc->tMax = 1e300;
+}
+
+// (re)arm the pipeline counters at the start of a run call
+__global__ void k_pipe_begin(DevScalars* sc, PipeCtl* ctl, double tMax, long long steps) {
+  sc->tMax = tMax;
+  sc->steps_left = steps;
+  const bool none = (!(sc->Time < tMax) || steps <= 0 || (sc->status & 16));
+  ctl->stop_step = none ? ctl->elem_step : 0x7FFFFFFFFFFFFFFFLL;
+  ctl->node_step = ctl->elem_step;
+  const int p = (int)(ctl->elem_step & 1);
+  for (int q = 0; q < 2; ++q) {
+    for (int i = 0; i < ctl->C; ++i) { ctl->elem_done[q][i] = 0; ctl->node_done[q][i] = (q == (p ^ 1)) ? ctl->node_target[i] : 0; }
+    ctl->elem_prefix[q] = 0; ctl->node_prefix[q] = 0; ctl->elem_ticket[q] = 0; ctl->node_ticket[q] = 0;
+    pipe_advance(&ctl->elem_prefix[q], ctl->elem_done[q], ctl->elem_target, ctl->C);
+    pipe_advance(&ctl->node_prefix[q], ctl->node_done[q], ctl->node_target, ctl->C);
+  }
+  ctl->elem_blocks_done = 0; ctl->node_blocks_done = 0;
+  // times of the first step of this run: the scalars left by explicit_begin / the previous run
+  StepScal S; S.t_n = sc->nt_n; S.t_np1 = sc->nt_np1; S.t_half = sc->nt_half; S.dt = sc->ndt;
+  ctl->scal[p] = S;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -233,7 +233,9 @@ FTB_HD int material_P(const int mat, const double F[3][3], const double cofF[3][
     }
     case 1: {  // compressible neo-Hookean (CompressibleNeoHookean.cpp:43-55)
       // S = mu (I - C^-1) + lambda ln J C^-1  =>  P = mu F + (lambda ln J - mu) F^-T,  F^-T = cof F / J
-      const double c = (lambda * log(J) - mu) / J;
+      // the reciprocal runs concurrently with the logarithm (two independent serial chains)
+      const double rJ = 1.0 / J;
+      const double c = (lambda * log(J) - mu) * rJ;
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -546,8 +548,12 @@ FTB_HD int hex8_element(const double X[8][3], const double U[8][3], int mat, con
   // The Gauss-point loop is deliberately NOT unrolled: one iteration has 9-wide instruction-level
   // parallelism (3x3 blocks), the rolled body fits the instruction cache, and the register count
   // stays low enough for 12-16 resident warps per SM.  Signs are run-time +-1.0 folded into FMAs.
+#ifndef FTB_GP_UNROLL
+#define FTB_GP_UNROLL 1
+#endif
+  constexpr int kGpUnroll = FTB_GP_UNROLL;
 #if defined(__CUDA_ARCH__)
-#pragma unroll 1
+#pragma unroll kGpUnroll
 #endif
   for (int gp = 0; gp < 8; ++gp) {
     // reference numbering (GaussQuadrature3D.cpp:19-49): xi + for gp 1,2,5,6; eta + for 2,3,6,7; zeta + for 0..3

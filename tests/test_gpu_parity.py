@@ -97,7 +97,7 @@ def test_resident_explicit_dynamics_matches_reference(name):
     ef = g["energy_file"][-1]
     for got, want in zip(eh[-1], ef[1:]):
         assert abs(got - want) <= 5e-6 * max(abs(want), 1e-300) + 1e-25, (eh[-1], ef)
-    assert m.gpu_launches > 3 * steps
+    assert m.gpu_launches >= 2 * steps
     m.close()
 
 
