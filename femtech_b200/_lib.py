@@ -48,8 +48,13 @@ SIGNATURES = {
     "ftb200_halo_count": (C.c_int, [_vp]),
     "ftb200_halo_pack": (C.c_int, [_vp, C.c_int, _vp]),
     "ftb200_halo_add": (C.c_int, [_vp, C.c_int, _vp]),
+    "ftb200_run_begin": (C.c_int, [_vp, C.c_double, _ll]),
     "ftb200_step_begin": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "ftb200_step_join": (C.c_int, [_vp]),
     "ftb200_step_end": (C.c_int, [_vp, _vp]),
+    "ftb200_explicit_begin_dt": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(_vp)]),
+    "ftb200_explicit_begin_force": (C.c_int, [_vp, _vp]),
+    "ftb200_explicit_begin_finish": (C.c_int, [_vp, _vp]),
     "ftb200_p2p_export": (C.c_int, [_vp, _vp]),
     "ftb200_p2p_import": (C.c_int, [_vp, _vp]),
     "ftb200_profile_enable": (C.c_int, [_vp, C.c_int]),

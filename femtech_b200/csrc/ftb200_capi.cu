@@ -80,6 +80,7 @@ struct ftb200_ctx {
   int *d_sendNodeIndex = nullptr, *halo_nodes = nullptr, *halo_off = nullptr, *halo_slot = nullptr,
       *halo_node_idx = nullptr;
   const double* halo_recv_cur = nullptr;
+  double Time0 = 0.0;
   // graph cache
   cudaGraphExec_t graph = nullptr;
   int graph_energy = -1;
@@ -881,13 +882,18 @@ int ftb200_get_history(ftb200_ctx* ctx, long long first, long long count, double
   return FTB200_OK;
 }
 
-int ftb200_explicit_begin(ftb200_ctx* ctx, double Time0, double reduction, double failure_dt, int energy_every) {
+// explicit_begin in three phases so that a rank with shared nodes can put the cross-rank MIN of the time
+// step and the neighbour sum of the initial forces in between (single rank: the three run back to back)
+int ftb200_explicit_begin_dt(ftb200_ctx* ctx, double Time0, double reduction, double failure_dt, int energy_every,
+                             double** dtmin_dev) {
   if (!ctx || !ctx->shape_ok) return fail(ctx, FTB200_ERR_INPUT, "explicit_begin: setup incomplete");
   if (energy_every != 0 && energy_every != 1)
     return fail(ctx, FTB200_ERR_INPUT, "explicit_begin: energy_every must be 0 or 1 (the running sums need every step)");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   ctx->energy = energy_every;
+  ctx->Time0 = Time0;
+  ctx->halo_recv_cur = nullptr;
   if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
   if (ctx->pgraph) { cudaGraphExecDestroy(ctx->pgraph); ctx->pgraph = nullptr; }
   // scalars: keep bc_rate / hist_cap, reset the rest
@@ -909,11 +915,34 @@ int ftb200_explicit_begin(ftb200_ctx* ctx, double Time0, double reduction, doubl
   LAUNCH(k_eflag, cdiv(ctx->nE, 256), 256, s, ctx->conn, ctx->flags, ctx->eflag, ctx->nE);
   // dt = reduction * StableTimeStep() (:86) -- before GetForce because material 5 reads dt
   launch_elem<false, true>(ctx, s, 0, ctx->nE, 1);
-  LAUNCH((k_adv<true>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, Time0, ctx->dthist);
-  // GetForce(); CalculateAccelerations() (:88-91)
+  if (dtmin_dev) *dtmin_dev = reinterpret_cast<double*>(&ctx->sc->dtmin_bits);
+  return FTB200_OK;
+}
+
+int ftb200_explicit_begin_force(ftb200_ctx* ctx, double* send_dev) {
+  if (!ctx || !ctx->shape_ok || (ctx->halo_count && !send_dev)) return fail(ctx, FTB200_ERR_INPUT, "explicit_begin_force: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  LAUNCH((k_adv<true>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, ctx->Time0, ctx->dthist);
+  // GetForce() (:88)
   launch_elem<true, false>(ctx, s, 0, ctx->nE, 1);
-  const NodeArgs N = node_args(ctx, nullptr);
+  if (ctx->halo_count) {
+    LAUNCH(k_gather_shared, cdiv(ctx->nshared, 128), 128, s, ctx->felem, ctx->node_off, ctx->node_ent, ctx->halo_nodes,
+           ctx->fi[0], ctx->fi[1], ctx->fi[2], ctx->nshared, ctx->nE);
+    LAUNCH(k_halo_pack, cdiv(ctx->halo_count, 256), 256, s, ctx->fi[0], ctx->fi[1], ctx->fi[2], ctx->d_sendNodeIndex, send_dev,
+           ctx->halo_count);
+  }
+  return FTB200_OK;
+}
+
+int ftb200_explicit_begin_finish(ftb200_ctx* ctx, const double* recv_dev) {
+  if (!ctx || !ctx->shape_ok || (ctx->halo_count && !recv_dev)) return fail(ctx, FTB200_ERR_INPUT, "explicit_begin_finish: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  // CalculateAccelerations() (:91)
+  const NodeArgs N = node_args(ctx, ctx->halo_count ? recv_dev : nullptr);
   LAUNCH((k_node<true, false, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+  ctx->halo_recv_cur = ctx->halo_count ? recv_dev : nullptr;
   {
     const long long zero = 0;
     CK(cudaMemcpyAsync(&ctx->d_ctl->elem_step, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
@@ -927,6 +956,15 @@ int ftb200_explicit_begin(ftb200_ctx* ctx, double Time0, double reduction, doubl
   if (status & 1) return fail(ctx, FTB200_ERR_MATERIAL, "Unknown material type");
   if (status & 16) return fail(ctx, FTB200_ERR_TIMESTEP, "Timestep too small");
   return FTB200_OK;
+}
+
+int ftb200_explicit_begin(ftb200_ctx* ctx, double Time0, double reduction, double failure_dt, int energy_every) {
+  if (ctx && ctx->halo_count && ctx->nranks > 1)
+    return fail(ctx, FTB200_ERR_INPUT, "explicit_begin: this rank has shared nodes; use the explicit_begin_dt/_force/_finish sequence");
+  int rc;
+  if ((rc = ftb200_explicit_begin_dt(ctx, Time0, reduction, failure_dt, energy_every, nullptr))) return rc;
+  if ((rc = ftb200_explicit_begin_force(ctx, nullptr))) return rc;
+  return ftb200_explicit_begin_finish(ctx, nullptr);
 }
 
 static int build_graph(ftb200_ctx* ctx) {
@@ -1099,13 +1137,57 @@ int ftb200_halo_add(ftb200_ctx* ctx, int field, const double* recv_dev) {
   return FTB200_OK;
 }
 
-int ftb200_step_begin(ftb200_ctx* ctx, double* send_dev, double** dtmin_dev) {
-  (void)send_dev; (void)dtmin_dev;
-  return fail(ctx, FTB200_ERR_INPUT, "step_begin: multi-GPU resident stepping not available in this build");
+int ftb200_run_begin(ftb200_ctx* ctx, double tMax, long long steps) {
+  if (!ctx || !ctx->begun) return fail(ctx, FTB200_ERR_INPUT, "run_begin: call explicit_begin first");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
+  const NodeArgs N = node_args(ctx, nullptr);
+  if (ctx->energy) LAUNCH((k_node<false, true, false, true>), ctx->node_blocks, NODE_BLOCK, s, N);
+  else LAUNCH((k_node<false, true, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+  return FTB200_OK;
 }
+
+int ftb200_step_begin(ftb200_ctx* ctx, double* send_dev, double** dtmin_dev) {
+  if (!ctx || !ctx->begun || (ctx->halo_count && !send_dev)) return fail(ctx, FTB200_ERR_INPUT, "step_begin: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream, s2 = ctx->stream2;
+  const int nEb = ctx->nE_boundary;
+  // interior elements on the second stream: they only need the state left by the previous node kernel
+  CK(cudaEventRecord(ctx->ev_fork, s));
+  CK(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+  launch_elem<true, true>(ctx, s2, nEb, ctx->nE, 0);
+  CK(cudaEventRecord(ctx->ev_join, s2));
+  // elements touching a shared node, then the partial f_int of the shared nodes into the send window
+  launch_elem<true, true>(ctx, s, 0, nEb, 0);
+  if (ctx->halo_count) {
+    LAUNCH(k_gather_shared, cdiv(ctx->nshared, 128), 128, s, ctx->felem, ctx->node_off, ctx->node_ent, ctx->halo_nodes,
+           ctx->fi[0], ctx->fi[1], ctx->fi[2], ctx->nshared, ctx->nE);
+    LAUNCH(k_halo_pack, cdiv(ctx->halo_count, 256), 256, s, ctx->fi[0], ctx->fi[1], ctx->fi[2], ctx->d_sendNodeIndex, send_dev,
+           ctx->halo_count);
+  }
+  if (dtmin_dev) *dtmin_dev = reinterpret_cast<double*>(&ctx->sc->dtmin_bits);
+  return FTB200_OK;
+}
+
+int ftb200_step_join(ftb200_ctx* ctx) {
+  if (!ctx || !ctx->begun) return fail(ctx, FTB200_ERR_INPUT, "step_join: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  return FTB200_OK;
+}
+
 int ftb200_step_end(ftb200_ctx* ctx, const double* recv_dev) {
-  (void)recv_dev;
-  return fail(ctx, FTB200_ERR_INPUT, "step_end: multi-GPU resident stepping not available in this build");
+  if (!ctx || !ctx->begun || (ctx->halo_count && !recv_dev)) return fail(ctx, FTB200_ERR_INPUT, "step_end: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  LAUNCH((k_adv<false>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, 0.0, ctx->dthist);
+  const NodeArgs N = node_args(ctx, ctx->halo_count ? recv_dev : nullptr);
+  if (ctx->energy) LAUNCH((k_node<true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
+  else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+  if (ctx->energy) LAUNCH(k_energy, 1, 256, s, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
+  ctx->halo_recv_cur = ctx->halo_count ? recv_dev : nullptr;
+  return FTB200_OK;
 }
 int ftb200_p2p_export(ftb200_ctx* ctx, void* handle_out) {
   (void)handle_out;

@@ -1,0 +1,360 @@
+"""Multi-GPU side of the explicit step: one process per GPU (torchrun), one mesh
+partition per rank, shared nodes duplicated on every rank that touches them.
+
+What the reference does (and this module mirrors):
+  * partition maps -- local node numbering and the per-neighbour shared-node lists,
+    src/io/PartitionMesh.cpp:485-536 (renumbering: local id = rank among the sorted unique
+    global ids) and :566-1128 (sendProcessID ascending, per neighbour the shared nodes in
+    ascending GLOBAL id, identical on both sides);
+  * per step, the pairwise sum of partial internal forces at shared nodes,
+    src/fem/SolidMechanics/GetForce_3D.cpp:54-102, and the MIN of the stable time step,
+    src/timestep/StableTimeStep.cpp:33; once, the same sum for the lumped mass,
+    src/fem/Mass/Mass3D.cpp:77-125.
+
+Transport: `torch.distributed` point-to-point (NCCL over NVLink on GPUs, gloo on CPU for
+the host-logic tests).  The payload layout is the reference's sendNodeDisplacement /
+recvNodeDisplacement (neighbour-major, xyz interleaved), so slice i of the send window
+goes to neighbour i's slice of the receive window and no index exchange is needed.
+The element partition itself (ParMETIS in the reference) is an INPUT here: any
+`part[]` array works; `brick_partition` provides the structured split used for the
+synthetic scaling cubes.
+"""
+import numpy as np
+
+
+# ------------------------------------------------------------------------------- partition maps
+def maps_from_elements(global_conn, elem_ids_by_rank):
+    """Restates PartitionMesh.cpp:485-536 and :1071-1108 for a given element distribution.
+
+    global_conn: [E,8] global node ids (0-based); elem_ids_by_rank[r]: global element ids owned by rank r
+    in the rank's local element order.  Returns per rank a dict with
+      connectivity (local ids, [E_r*8]), globalNodeID (1-based, sorted), node_gids (0-based),
+      sendProcessID, sendNeighbourCount, sendNeighbourCountCum, sendNodeIndex (local ids).
+    O(N log N); the reference's O(N^2) scan (:492-513) gives the same result.
+    """
+    P = len(elem_ids_by_rank)
+    gconn = np.asarray(global_conn).reshape(-1, 8)
+    node_sets, out = [], []
+    for r in range(P):
+        c = gconn[np.asarray(elem_ids_by_rank[r], dtype=np.int64)]
+        gids = np.unique(c)  # sorted unique global ids -> local id = rank in this list
+        node_sets.append(gids)
+        local = np.searchsorted(gids, c).astype(np.int32)
+        out.append({"connectivity": local.reshape(-1), "node_gids": gids.astype(np.int64),
+                    "globalNodeID": (gids + 1).astype(np.int32)})
+    for r in range(P):
+        pids, counts, idx = [], [], []
+        for q in range(P):  # ascending neighbour rank
+            if q == r:
+                continue
+            shared = np.intersect1d(node_sets[r], node_sets[q], assume_unique=True)  # ascending global id
+            if shared.size:
+                pids.append(q)
+                counts.append(shared.size)
+                idx.append(np.searchsorted(node_sets[r], shared).astype(np.int32))
+        out[r]["sendProcessID"] = np.array(pids, dtype=np.int32)
+        out[r]["sendNeighbourCount"] = np.array(counts, dtype=np.int32)
+        out[r]["sendNeighbourCountCum"] = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        out[r]["sendNodeIndex"] = np.concatenate(idx).astype(np.int32) if idx else np.zeros(0, np.int32)
+    return out
+
+
+def proc_grid(P):
+    """Near-cubic px*py*pz = P, px >= py >= pz (1,2,4,8 -> 1x1x1, 2x1x1, 2x2x1, 2x2x2)."""
+    best = (P, 1, 1)
+    for a in range(1, P + 1):
+        if P % a:
+            continue
+        for b in range(1, P // a + 1):
+            if (P // a) % b:
+                continue
+            c = P // a // b
+            t = tuple(sorted((a, b, c), reverse=True))
+            if max(t) - min(t) < max(best) - min(best):
+                best = t
+    return best
+
+
+def brick_partition(n_local, pgrid, rank, L_local=0.005):
+    """Rank `rank`'s brick of a structured hex8 box made of pgrid = (px,py,pz) bricks of n_local^3
+    elements each (weak scaling: the global mesh grows with the rank count).  Node and element
+    numbering, C3D8 ordering and spacing follow femtech_b200.mesh.cube_mesh; the maps follow the
+    reference's rules (see maps_from_elements) but are built analytically, without the global mesh.
+
+    Returns dict(coordinates[N,3], connectivity[E,8] local ids, pid[E], node_gids[N], comm{...},
+                 box=(Lx,Ly,Lz), dims=(Nx,Ny,Nz)).
+    """
+    px, py, pz = pgrid
+    n = n_local
+    rx, ry, rz = rank % px, (rank // px) % py, rank // (px * py)
+    Nx, Ny, Nz = n * px, n * py, n * pz
+    h = L_local / n
+    ox, oy, oz = rx * n, ry * n, rz * n
+    n1 = n + 1
+    kk, jj, ii = np.meshgrid(np.arange(n1), np.arange(n1), np.arange(n1), indexing="ij")
+    gi, gj, gk = (ii + ox).reshape(-1), (jj + oy).reshape(-1), (kk + oz).reshape(-1)
+    X = np.stack([gi * h, gj * h, gk * h], axis=-1).astype(np.float64)
+    gids = gi.astype(np.int64) + (Nx + 1) * gj.astype(np.int64) + (Nx + 1) * (Ny + 1) * gk.astype(np.int64)
+    ek, ej, ei = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    ei, ej, ek = ei.reshape(-1), ej.reshape(-1), ek.reshape(-1)
+
+    def nid(i, j, k):
+        return (i + n1 * j + n1 * n1 * k).astype(np.int32)
+
+    conn = np.stack([nid(ei, ej, ek), nid(ei + 1, ej, ek), nid(ei + 1, ej + 1, ek), nid(ei, ej + 1, ek),
+                     nid(ei, ej, ek + 1), nid(ei + 1, ej, ek + 1), nid(ei + 1, ej + 1, ek + 1),
+                     nid(ei, ej + 1, ek + 1)], axis=1).astype(np.int32)
+    # neighbours: every brick that shares at least one node (faces, edges, corners), ascending rank;
+    # shared nodes of a pair = a face/edge/corner of the local node box, ascending global id == ascending local id
+    pids, counts, idx = [], [], []
+    local_ids = np.arange(n1 ** 3, dtype=np.int32).reshape(n1, n1, n1)  # [k, j, i]
+    for q in range(px * py * pz):
+        if q == rank:
+            continue
+        qx, qy, qz = q % px, (q // px) % py, q // (px * py)
+        dx, dy, dz = qx - rx, qy - ry, qz - rz
+        if max(abs(dx), abs(dy), abs(dz)) > 1:
+            continue
+        sel = []
+        for d in (dz, dy, dx):
+            sel.append(slice(None) if d == 0 else (slice(n, n + 1) if d > 0 else slice(0, 1)))
+        shared = local_ids[sel[0], sel[1], sel[2]].reshape(-1)
+        pids.append(q)
+        counts.append(shared.size)
+        idx.append(np.sort(shared))
+    comm = {
+        "sendProcessID": np.array(pids, dtype=np.int32),
+        "sendNeighbourCount": np.array(counts, dtype=np.int32),
+        "sendNeighbourCountCum": np.concatenate([[0], np.cumsum(counts)]).astype(np.int32),
+        "sendNodeIndex": np.concatenate(idx).astype(np.int32) if idx else np.zeros(0, np.int32),
+    }
+    return {"coordinates": X, "connectivity": conn, "pid": np.zeros(conn.shape[0], np.int32), "node_gids": gids,
+            "comm": comm, "box": (Nx * h, Ny * h, Nz * h), "dims": (Nx, Ny, Nz)}
+
+
+# ------------------------------------------------------------------------------------ transport
+class HaloExchange:
+    """Pairwise exchange of the shared-node windows (GetForce_3D.cpp:62-90) over torch.distributed."""
+
+    def __init__(self, comm, device, dist):
+        import torch
+        self.torch, self.dist = torch, dist
+        self.pids = [int(p) for p in comm["sendProcessID"]]
+        self.cum = [int(c) for c in comm["sendNeighbourCountCum"]]
+        total = self.cum[-1] if self.cum else 0
+        self.count = total
+        self.send = torch.zeros(3 * max(total, 1), dtype=torch.float64, device=device)
+        self.recv = torch.zeros(3 * max(total, 1), dtype=torch.float64, device=device)
+
+    def exchange(self):
+        """send window slice i -> neighbour i; neighbour i's slice -> recv window slice i."""
+        if not self.pids:
+            return
+        ops = []
+        for i, p in enumerate(self.pids):
+            lo, hi = 3 * self.cum[i], 3 * self.cum[i + 1]
+            ops.append(self.dist.P2POp(self.dist.isend, self.send[lo:hi], p))
+            ops.append(self.dist.P2POp(self.dist.irecv, self.recv[lo:hi], p))
+        for w in self.dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def halo_add_host(field_aos, comm, recv):
+    """CPU restatement of the add loop (GetForce_3D.cpp:92-97): slots in neighbour-major order."""
+    idx = np.asarray(comm["sendNodeIndex"])
+    f = field_aos.reshape(-1, 3)
+    r = np.asarray(recv).reshape(-1, 3)
+    for i in range(idx.size):  # sequential on purpose: a node shared with several neighbours is hit repeatedly
+        f[idx[i]] += r[i]
+
+
+class _DevDouble:
+    """Zero-copy view of one device double for torch (CUDA array interface)."""
+
+    def __init__(self, ptr):
+        self.__cuda_array_interface__ = {"shape": (1,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class DistFemTech:
+    """One rank of a multi-GPU run: a solver.FemTech plus the exchange, driving the split step API."""
+
+    def __init__(self, part, materialID, properties, rank, world, device, dist, **kw):
+        import ctypes as C
+        import torch
+        from . import solver
+        self.C, self.torch, self.dist = C, torch, dist
+        self.rank, self.world = rank, world
+        self.m = solver.FemTech(part["coordinates"], part["connectivity"], part["pid"], materialID, properties,
+                                comm=part["comm"], world_rank=rank, world_size=world, device=device, **kw)
+        self.halo = HaloExchange(part["comm"], torch.device("cuda", device), dist)
+        self._send = C.c_void_p(self.halo.send.data_ptr())
+        self._recv = C.c_void_p(self.halo.recv.data_ptr())
+        # kernels and NCCL ops must be ordered on ONE stream: torch's current stream inside these methods
+        self.stream = torch.cuda.Stream(device=device)
+        self.m.set_stream(self.stream.cuda_stream)
+
+    def setup(self):
+        with self.torch.cuda.stream(self.stream):
+            self._setup()
+
+    def explicit_begin(self, energy_every=1):
+        with self.torch.cuda.stream(self.stream):
+            self._explicit_begin(energy_every)
+
+    def run(self, tMax, steps):
+        """Enqueue `steps` time steps (no host synchronisation)."""
+        with self.torch.cuda.stream(self.stream):
+            self._run(tMax, steps)
+
+    def _setup(self):
+        m = self.m
+        m.ShapeFunctions()
+        m.AssembleLumpedMass()
+        if self.halo.count:  # updateMassMatrixNeighbour, Mass3D.cpp:77-125
+            m._check(m.L.ftb200_halo_pack(m._h, 1, self._send))
+            self.halo.exchange()
+            m._check(m.L.ftb200_halo_add(m._h, 1, self._recv))
+        else:
+            self.halo.exchange()
+
+    def _allreduce_dtmin(self, ptr):
+        if self.world > 1:
+            t = self.torch.as_tensor(_DevDouble(ptr.value), device=self.halo.send.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+
+    def _explicit_begin(self, energy_every=1):
+        m, C = self.m, self.C
+        m.sync_in()
+        ptr = C.c_void_p()
+        m._check(m.L.ftb200_explicit_begin_dt(m._h, float(m.Time), float(m.ExplicitTimeStepReduction),
+                                              float(m.FailureTimeStep), int(energy_every), C.byref(ptr)))
+        self._allreduce_dtmin(ptr)
+        m._check(m.L.ftb200_explicit_begin_force(m._h, self._send))
+        self.halo.exchange()
+        m._check(m.L.ftb200_explicit_begin_finish(m._h, self._recv))
+        m._poll()
+
+    def _run(self, tMax, steps):
+        m, C = self.m, self.C
+        m._check(m.L.ftb200_run_begin(m._h, float(tMax), int(steps)))
+        ptr = C.c_void_p()
+        for _ in range(steps):
+            m._check(m.L.ftb200_step_begin(m._h, self._send, C.byref(ptr)))
+            self.halo.exchange()
+            m._check(m.L.ftb200_step_join(m._h))
+            self._allreduce_dtmin(ptr)
+            m._check(m.L.ftb200_step_end(m._h, self._recv))
+
+    def energy(self):
+        """Wint, Wext, WKE summed over ranks (CheckEnergy.cpp:54-64)."""
+        e = self.torch.tensor(self.m.energy()[:3], dtype=self.torch.float64, device=self.halo.send.device)
+        if self.world > 1:
+            self.dist.all_reduce(e)
+        e = e.cpu().numpy()
+        return np.array([e[0], e[1], e[2], abs(e[2] + e[0] - e[1])])
+
+
+# ------------------------------------------------------------- in-process group (tests, 1 GPU)
+class LocalGroup:
+    """P partitions driven in lockstep inside ONE process on one GPU: the same C-ABI call sequence as
+    DistFemTech, with the exchange done by device-to-device copies between the ranks' windows.  Used by
+    the GPU parity tests to cover the multi-rank kernels (boundary/interior split, pack, neighbour sum,
+    cross-rank dt) on a single-GPU box."""
+
+    def __init__(self, parts, materialID, properties, device=0, **kw):
+        import ctypes as C
+        import torch
+        from . import solver
+        self.C, self.torch = C, torch
+        self.P = len(parts)
+        self.models = [solver.FemTech(p["coordinates"], p["connectivity"], p["pid"], materialID, properties,
+                                      comm=p["comm"], world_rank=r, world_size=self.P, device=device, **kw)
+                       for r, p in enumerate(parts)]
+        dev = torch.device("cuda", device)
+        self.comms = [p["comm"] for p in parts]
+        self.send = [torch.zeros(3 * max(int(c["sendNeighbourCountCum"][-1]), 1), dtype=torch.float64, device=dev)
+                     for c in self.comms]
+        self.recv = [torch.zeros_like(t) for t in self.send]
+
+    def _ptr(self, t):
+        return self.C.c_void_p(t.data_ptr())
+
+    def _sync(self):
+        self.torch.cuda.synchronize()
+
+    def _exchange(self):
+        self._sync()
+        for r, c in enumerate(self.comms):
+            cum = c["sendNeighbourCountCum"]
+            for i, q in enumerate(c["sendProcessID"]):
+                cq = self.comms[q]
+                j = int(np.where(cq["sendProcessID"] == r)[0][0])
+                lo, hi = 3 * int(cum[i]), 3 * int(cum[i + 1])
+                qlo, qhi = 3 * int(cq["sendNeighbourCountCum"][j]), 3 * int(cq["sendNeighbourCountCum"][j + 1])
+                assert hi - lo == qhi - qlo
+                self.recv[r][lo:hi].copy_(self.send[q][qlo:qhi])
+        self._sync()
+
+    def _min_dt(self, ptrs):
+        self._sync()
+        ts = [self.torch.as_tensor(_DevDouble(p.value), device=self.send[0].device) for p in ptrs]
+        mn = self.torch.stack([t[0] for t in ts]).min()
+        for t in ts:
+            t[0] = mn
+        self._sync()
+
+    def setup(self):
+        for m in self.models:
+            m.ShapeFunctions()
+            m.AssembleLumpedMass()
+        for r, m in enumerate(self.models):
+            m._check(m.L.ftb200_halo_pack(m._h, 1, self._ptr(self.send[r])))
+        self._exchange()
+        for r, m in enumerate(self.models):
+            m._check(m.L.ftb200_halo_add(m._h, 1, self._ptr(self.recv[r])))
+        self._sync()
+
+    def explicit_begin(self, energy_every=1):
+        C = self.C
+        ptrs = []
+        for m in self.models:
+            m.sync_in()
+            p = C.c_void_p()
+            m._check(m.L.ftb200_explicit_begin_dt(m._h, float(m.Time), float(m.ExplicitTimeStepReduction),
+                                                  float(m.FailureTimeStep), int(energy_every), C.byref(p)))
+            ptrs.append(p)
+        self._min_dt(ptrs)
+        for r, m in enumerate(self.models):
+            m._check(m.L.ftb200_explicit_begin_force(m._h, self._ptr(self.send[r])))
+        self._exchange()
+        for r, m in enumerate(self.models):
+            m._check(m.L.ftb200_explicit_begin_finish(m._h, self._ptr(self.recv[r])))
+            m._poll()
+
+    def run(self, tMax, steps):
+        C = self.C
+        for m in self.models:
+            m._check(m.L.ftb200_run_begin(m._h, float(tMax), int(steps)))
+        for _ in range(steps):
+            ptrs = []
+            for r, m in enumerate(self.models):
+                p = C.c_void_p()
+                m._check(m.L.ftb200_step_begin(m._h, self._ptr(self.send[r]), C.byref(p)))
+                ptrs.append(p)
+            self._exchange()
+            for m in self.models:
+                m._check(m.L.ftb200_step_join(m._h))
+            self._min_dt(ptrs)
+            for r, m in enumerate(self.models):
+                m._check(m.L.ftb200_step_end(m._h, self._ptr(self.recv[r])))
+        self._sync()
+        for m in self.models:
+            m._poll()
+
+    def energy(self):
+        e = np.sum([m.energy()[:3] for m in self.models], axis=0)
+        return np.array([e[0], e[1], e[2], abs(e[2] + e[0] - e[1])])
+
+    def close(self):
+        for m in self.models:
+            m.close()

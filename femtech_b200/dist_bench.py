@@ -1,10 +1,109 @@
-"""Multi-GPU bench leg (one process per GPU, torchrun).  Filled in by femtech_b200.dist."""
+"""Multi-GPU leg of bench.py: one process per GPU (torchrun), weak scaling -- every rank owns an
+n^3-element brick of a structured box (femtech_b200.dist.brick_partition), shared-node forces are
+summed every step over NCCL (send/recv per neighbour), the stable dt by an NCCL MIN all-reduce."""
 import json
 import os
+import threading
+import time
+
+import numpy as np
 
 
 def run(args):
+    import torch
+    import torch.distributed as dist
+    import bench
+    from femtech_b200 import dist as fdist
+    from femtech_b200 import mesh
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, mat = args.n, args.material
+    pg = fdist.proc_grid(world)
+    part = fdist.brick_partition(n, pg, rank)
+    E_local, N_local = part["connectivity"].shape[0], part["coordinates"].shape[0]
+    energy = 0 if args.no_energy else 1
+    rate_v = 0.07 if mat == 1 else 1.75
+    kind, rate = mesh.benchmark_bc(part["coordinates"], L=part["box"][1], dMax=rate_v, tMax=1.0)
+    d = fdist.DistFemTech(part, [mat], bench.MATERIALS[mat], rank, world, local, dist)
+    d.setup()
+    d.m.set_bc(kind, rate)
+    d.explicit_begin(energy_every=energy)
+    tMax = 1e30
+    warm = max(args.warmup, 3)
+    d.run(tMax, warm)
+    torch.cuda.synchronize()
+    dist.barrier()
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=bench.clocks_sampler, args=(stop, samples, local), daemon=True)
     if rank == 0:
-        print(json.dumps({"metric": "hex8 element-steps/sec fp64", "n_gpus": args.gpus,
-                          "unavailable": "multi-GPU stepping not wired into bench.py yet"}))
+        th.start()
+    l0 = d.m.gpu_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    with torch.cuda.stream(d.stream):
+        ev0.record(d.stream)
+    d.run(tMax, args.steps)
+    with torch.cuda.stream(d.stream):
+        ev1.record(d.stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms[0])
+    launches = d.m.gpu_launches - l0
+    d.m._poll()
+    ok = np.isfinite(d.m.Time) and d.m.steps_done == warm + args.steps
+    # end to end through the public API: host state in, per-step scalar read-back, host state out
+    e2e_steps = min(args.steps, 30)
+    pin = {k: torch.zeros(3 * N_local, dtype=torch.float64).pin_memory() for k in ("u", "v", "a", "fi", "fn")}
+    pinb = torch.zeros(3 * N_local, dtype=torch.int32).pin_memory()
+    m = d.m
+    m.displacements, m.velocities, m.accelerations = pin["u"].numpy(), pin["v"].numpy(), pin["a"].numpy()
+    m.fi, m.f_net, m.boundary = pin["fi"].numpy(), pin["fn"].numpy(), pinb.numpy()
+    m.Time = 0.0
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    d.explicit_begin(energy_every=energy)
+    for _ in range(e2e_steps):
+        d.run(tMax, 1)
+        m._poll()
+    m.sync_out()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        stop.set()
+        th.join(timeout=2)
+        E_total = E_local * world
+        out = {
+            "metric": "hex8 element-steps/sec fp64", "value": E_total * args.steps / (ms_total * 1e-3),
+            "unit": "element-steps/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic structured hex8 box of %dx%dx%d bricks, %d^3 elements per GPU (%d elements "
+                                   "total), %s, benchmark BC, %s, dt recomputed every step" %
+                                   (pg[0], pg[1], pg[2], n, E_total, bench.MAT_NAME[mat],
+                                    "CheckEnergy every step" if energy else "no energy check"),
+                       "partition": "structured brick split, one partition per GPU (ParMETIS part[] accepted as input; "
+                                    "node maps follow PartitionMesh.cpp, tests/test_partition_host.py)",
+                       "exchange": "NCCL send/recv per neighbour of the shared-node windows, overlapped with the interior "
+                                   "elements; NCCL MIN all-reduce of the stable dt",
+                       "l2": "per-step working set > 126 MB L2 per GPU, no flush needed"},
+            "roofline": None, "cpu_baseline": None,
+            "e2e": {"value": E_total * e2e_steps / float(e2e_s[0]), "unit": "element-steps/s",
+                    "h2d_bytes_per_step": (3 * 24 + 12) * N_local * world / e2e_steps,
+                    "d2h_bytes_per_step": (5 * 24 + 12) * N_local * world / e2e_steps + 200 * world,
+                    "api": "DistFemTech (resident): pinned host state in, %d single-step calls with per-step scalar "
+                           "read-back, host state out" % e2e_steps, "steps": e2e_steps},
+            "gpu_launches": launches, "clocks": bench.summarize_clocks(samples), "valid": bool(ok),
+        }
+        print(json.dumps(out))
+    d.m.close()
+    dist.barrier()
+    dist.destroy_process_group()

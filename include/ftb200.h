@@ -73,7 +73,7 @@ int ftb200_lumped_mass(ftb200_ctx *ctx, double *mass_out);
 /* ---- legacy per-call path: host arrays in, host arrays out --------------- */
 /* GetForce()/GetForce_3D() (src/fem/SolidMechanics/GetForce_3D.cpp:5-53).  dt is the driver global `dt`
  * (only material 5 reads it).  fe may be NULL (== 0).  With a comm pattern uploaded and nranks > 1 this
- * call computes the LOCAL part only; see ftb200_force_begin/end for the split form. */
+ * call computes the LOCAL part only; use ftb200_halo_pack / ftb200_halo_add (field 0) for the neighbour sum. */
 int ftb200_get_force(ftb200_ctx *ctx, const double *displacements, const double *fe, double dt, double *fi,
                      double *f_net);
 /* CalculateAccelerations() (src/fem/SolidMechanics/CalculateAcclerations.cpp:4-13): accelerations[i] =
@@ -130,11 +130,27 @@ int ftb200_halo_count(const ftb200_ctx *ctx);
  * slice of recv.  field: 0 = internal force, 1 = lumped mass. */
 int ftb200_halo_pack(ftb200_ctx *ctx, int field, double *send_dev);
 int ftb200_halo_add(ftb200_ctx *ctx, int field, const double *recv_dev);
-/* Resident path, split around the exchange: force_begin launches boundary elements, packs `send_dev`,
- * then launches interior elements on a second stream; force_end adds `recv_dev` in ascending neighbour
- * order and finishes the step.  dtmin_dev is a device double the caller MIN-reduces across ranks between
- * the two calls (StableTimeStep.cpp:33). */
+/* Resident path for a rank with shared nodes, split around the exchange (one call sequence per time step):
+ *   ftb200_run_begin(tMax, steps)   once per run: arms the loop and performs the first kick + drift + BC
+ *   ftb200_step_begin(send_dev, &dtmin_dev)
+ *        element kernel on the elements that touch a shared node, partial f_int of the shared nodes packed
+ *        into send_dev; the interior elements are launched on a second stream and overlap the exchange
+ *   ... caller moves send_dev -> neighbours' recv_dev (any transport; same stream) ...
+ *   ftb200_step_join()              the interior elements have been enqueued before what follows
+ *   ... caller MIN-reduces *dtmin_dev across ranks in place (StableTimeStep.cpp:33) ...
+ *   ftb200_step_end(recv_dev)       scalar update, then the node kernel adds recv_dev in ascending
+ *                                   neighbour order (GetForce_3D.cpp:92-97) and finishes the step
+ * dtmin_dev points at a device double.  Nothing here synchronises with the host. */
+int ftb200_run_begin(ftb200_ctx *ctx, double tMax, long long steps);
+/* explicit_begin for a rank with shared nodes, in three phases: _dt (BC + local element dt; caller then
+ * MIN-reduces *dtmin_dev), _force (dt := reduction*min, GetForce, shared-node partials packed into send_dev;
+ * caller exchanges), _finish (neighbour sum + CalculateAccelerations; synchronises and reports errors). */
+int ftb200_explicit_begin_dt(ftb200_ctx *ctx, double Time0, double ExplicitTimeStepReduction, double FailureTimeStep,
+                             int energy_every, double **dtmin_dev);
+int ftb200_explicit_begin_force(ftb200_ctx *ctx, double *send_dev);
+int ftb200_explicit_begin_finish(ftb200_ctx *ctx, const double *recv_dev);
 int ftb200_step_begin(ftb200_ctx *ctx, double *send_dev, double **dtmin_dev);
+int ftb200_step_join(ftb200_ctx *ctx);
 int ftb200_step_end(ftb200_ctx *ctx, const double *recv_dev);
 /* Peer-memory transport (NVLink/NVSwitch, no NCCL on the data path): every rank exports its receive
  * window, imports the neighbours' and the whole step, exchange included, runs inside
