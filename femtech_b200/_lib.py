@@ -30,6 +30,7 @@ SIGNATURES = {
     "ftb200_upload_comm": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip]),
     "ftb200_shape_functions": (C.c_int, [_vp, _dp]),
     "ftb200_lumped_mass": (C.c_int, [_vp, _dp]),
+    "ftb200_get_mass": (C.c_int, [_vp, _dp]),
     "ftb200_get_force": (C.c_int, [_vp, _dp, _dp, C.c_double, _dp, _dp]),
     "ftb200_calculate_accelerations": (C.c_int, [_vp, _ip, _dp]),
     "ftb200_stable_time_step": (C.c_int, [_vp, _dp, _ip, _dp]),

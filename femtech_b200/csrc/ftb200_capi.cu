@@ -694,6 +694,16 @@ int ftb200_lumped_mass(ftb200_ctx* ctx, double* mass_out) {
   return FTB200_OK;
 }
 
+int ftb200_get_mass(ftb200_ctx* ctx, double* mass_out) {
+  if (!ctx || !ctx->shape_ok || !mass_out) return fail(ctx, FTB200_ERR_INPUT, "get_mass: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  double* src[3] = {ctx->m, ctx->m, ctx->m};
+  int rc = download_aos(ctx, src, mass_out, 0);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return FTB200_OK;
+}
+
 // ------------------------------------------------------------------------------------- legacy path
 static int legacy_force_local(ftb200_ctx* ctx, const double* displacements, const double* fe, double dt) {
   int rc;
@@ -927,9 +937,11 @@ int ftb200_explicit_begin_force(ftb200_ctx* ctx, double* send_dev) {
   // GetForce() (:88)
   launch_elem<true, false>(ctx, s, 0, ctx->nE, 1);
   if (ctx->halo_count) {
+    // partial sums go to the f_net planes (scratch in the resident path): fi still holds the previous
+    // step's total, which the energy check needs as fi_prev
     LAUNCH(k_gather_shared, cdiv(ctx->nshared, 128), 128, s, ctx->felem, ctx->node_off, ctx->node_ent, ctx->halo_nodes,
-           ctx->fi[0], ctx->fi[1], ctx->fi[2], ctx->nshared, ctx->nE);
-    LAUNCH(k_halo_pack, cdiv(ctx->halo_count, 256), 256, s, ctx->fi[0], ctx->fi[1], ctx->fi[2], ctx->d_sendNodeIndex, send_dev,
+           ctx->fnet[0], ctx->fnet[1], ctx->fnet[2], ctx->nshared, ctx->nE);
+    LAUNCH(k_halo_pack, cdiv(ctx->halo_count, 256), 256, s, ctx->fnet[0], ctx->fnet[1], ctx->fnet[2], ctx->d_sendNodeIndex, send_dev,
            ctx->halo_count);
   }
   return FTB200_OK;
@@ -1161,9 +1173,11 @@ int ftb200_step_begin(ftb200_ctx* ctx, double* send_dev, double** dtmin_dev) {
   // elements touching a shared node, then the partial f_int of the shared nodes into the send window
   launch_elem<true, true>(ctx, s, 0, nEb, 0);
   if (ctx->halo_count) {
+    // partial sums go to the f_net planes (scratch in the resident path): fi still holds the previous
+    // step's total, which the energy check needs as fi_prev
     LAUNCH(k_gather_shared, cdiv(ctx->nshared, 128), 128, s, ctx->felem, ctx->node_off, ctx->node_ent, ctx->halo_nodes,
-           ctx->fi[0], ctx->fi[1], ctx->fi[2], ctx->nshared, ctx->nE);
-    LAUNCH(k_halo_pack, cdiv(ctx->halo_count, 256), 256, s, ctx->fi[0], ctx->fi[1], ctx->fi[2], ctx->d_sendNodeIndex, send_dev,
+           ctx->fnet[0], ctx->fnet[1], ctx->fnet[2], ctx->nshared, ctx->nE);
+    LAUNCH(k_halo_pack, cdiv(ctx->halo_count, 256), 256, s, ctx->fnet[0], ctx->fnet[1], ctx->fnet[2], ctx->d_sendNodeIndex, send_dev,
            ctx->halo_count);
   }
   if (dtmin_dev) *dtmin_dev = reinterpret_cast<double*>(&ctx->sc->dtmin_bits);

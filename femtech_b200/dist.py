@@ -214,6 +214,7 @@ class DistFemTech:
             m._check(m.L.ftb200_halo_pack(m._h, 1, self._send))
             self.halo.exchange()
             m._check(m.L.ftb200_halo_add(m._h, 1, self._recv))
+            m.refresh_mass()
         else:
             self.halo.exchange()
 
@@ -312,6 +313,7 @@ class LocalGroup:
         self._exchange()
         for r, m in enumerate(self.models):
             m._check(m.L.ftb200_halo_add(m._h, 1, self._ptr(self.recv[r])))
+            m.refresh_mass()
         self._sync()
 
     def explicit_begin(self, energy_every=1):

@@ -131,6 +131,10 @@ class FemTech:
         self.mass = np.zeros(self.nDOF)
         self._check(self.L.ftb200_lumped_mass(self._h, _d(self.mass)))
 
+    def refresh_mass(self):
+        """Re-read `mass` from the device (after the neighbour sum of a multi-GPU run)."""
+        self._check(self.L.ftb200_get_mass(self._h, _d(self.mass)))
+
     # --- legacy per-call path (host arrays in/out) ----------------------------------------------------
     def GetForce(self):
         fe = self.fe if np.any(self.fe) else None

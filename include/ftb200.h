@@ -69,6 +69,8 @@ int ftb200_shape_functions(ftb200_ctx *ctx, double *min_detJ);
 /* AssembleLumpedMass() without the neighbour sum (src/fem/Mass/Mass3D.cpp:127-157).  mass_out (optional)
  * is double[3*nNodes].  Multi-GPU: sum shared nodes with the halo calls below (field 1). */
 int ftb200_lumped_mass(ftb200_ctx *ctx, double *mass_out);
+/* Current nodal mass (after any neighbour sum), double[3*nNodes] like the reference's `mass` array. */
+int ftb200_get_mass(ftb200_ctx *ctx, double *mass_out);
 
 /* ---- legacy per-call path: host arrays in, host arrays out --------------- */
 /* GetForce()/GetForce_3D() (src/fem/SolidMechanics/GetForce_3D.cpp:5-53).  dt is the driver global `dt`
