@@ -1,0 +1,240 @@
+// femtech_host.cpp -- the reference-facing C++ host layer of femtech_b200.
+//
+// Exports the SAME C++ symbols the reference's libFemTech.a exports for the explicit-dynamics hot path
+// (include/FemTech.h:22-129) and defines the global arrays those translation units define
+// (src/fem/ShapeFunctions/ShapeFunctions.cpp:7-30, src/fem/AllocateArrays.cpp:5-27), so that the
+// reference's shipped drivers (examples/Benchmarking-Parallel/Benchmarking-Parallel.cpp, examples/ex9/ex9.cpp)
+// compile and link UNCHANGED: put this object before libFemTech.a on the link line and add -lftb200.
+// Every function is a thin marshalling shim over the C-ABI in include/ftb200.h -- no numerics here.
+//
+// Compiled against the reference's own headers (-I<FemTech>/include); see integration/build_dropin.sh
+// and INTEGRATION.md.  Replaced translation units of the reference:
+//   src/fem/ShapeFunctions/ShapeFunctions.cpp   ShapeFunctions()
+//   src/fem/Mass/Mass3D.cpp                     AssembleLumpedMass() (+ aborting stubs for the implicit-only entries)
+//   src/fem/AllocateArrays.cpp                  AllocateArrays()
+//   src/io/output/FreeArrays.cpp                FreeArrays()
+//   src/fem/SolidMechanics/GetForce.cpp, GetForce_3D.cpp, CalculateAcclerations.cpp, CheckEnergy.cpp
+//   src/timestep/StableTimeStep.cpp             StableTimeStep()
+//   src/fem/Solver/ExplicitDynamics.cpp         ExplicitDynamics() (a stub in the reference)
+//   src/elements/ElementCalculations/CalculateStrain.cpp  CalculateStrain() (lazy F/pk2/Eavg materialisation)
+// Modes: the per-call functions are the LEGACY mode -- host arrays cross PCIe on every call, the
+// drivers' own host loops stay as they are; ExplicitDynamics() is the RESIDENT mode.
+#include "FemTech.h"
+#include "utilities.h"
+
+#include "ftb200.h"
+#include "femtech_b200_ext.h"
+
+#include <string>
+
+/* ---- globals defined by the replaced translation units ---------------------------------------- */
+int *gptr, *dsptr, *GaussPoints, *fptr, *nShapeFunctions, *pk2ptr, *detFptr, *InternalsPtr, *gpPtr;
+double *shp, *dshp, *F, *detF, *invF, *pk2, *internals, *detJacobian, *gaussWeights, *fintGQ, *B;
+double *Hn_1, *Hn_2, *S0n;
+double *displacements, *velocities, *velocities_half, *accelerations, *Eavg, *fe, *fe_prev, *fi, *fi_prev, *f_net;
+double *fr_curr, *fr_prev, *fi_curr, *f_damp_prev, *f_damp_curr, *displacements_prev, *accelerations_prev, *stepTime;
+double *mat1, *mat2, *mat3, *mat4;
+int *boundary;
+FILE *energyFile;
+
+static ftb200_ctx *g_ctx = NULL;
+static int *g_bc_kind = NULL;
+static double g_bc_rate[4] = {0, 0, 0, 0};
+static int g_energy_every = 1;
+
+static void check(int rc) {
+  if (rc) {
+    FILE_LOG_SINGLE(ERROR, "femtech_b200: %s", ftb200_last_error(g_ctx));
+    TerminateFemTech(rc == FTB200_ERR_CUDA ? 3 : rc);  /* same abort codes as the reference */
+  }
+}
+
+static void ensure_ctx() {
+  if (g_ctx) return;
+  if (ndim != 3) { FILE_LOG_SINGLE(ERROR, "femtech_b200 supports ndim == 3 only"); TerminateFemTech(3); }
+  for (int e = 0; e < nelements; ++e)
+    if (strcmp(ElementType[e], "C3D8") != 0 || eptr[e + 1] - eptr[e] != 8) {
+      FILE_LOG_SINGLE(ERROR, "femtech_b200 hot path is hex8 (C3D8) only; element %d is %s", e, ElementType[e]);
+      TerminateFemTech(3);
+    }
+  int ndev_rank = world_rank;  /* one rank per GPU */
+  const char *ev = getenv("FTB200_DEVICE");
+  check(ftb200_create(world_rank, world_size, ev ? atoi(ev) : ndev_rank, &g_ctx));
+  check(ftb200_upload_mesh(g_ctx, coordinates, connectivity, pid, nNodes, nelements));
+  check(ftb200_upload_materials(g_ctx, materialID, properties, nPIDglobal));
+  check(ftb200_upload_comm(g_ctx, sendProcessCount, sendProcessID, sendNeighbourCountCum, sendNodeIndex));
+}
+
+/* ---- src/fem/AllocateArrays.cpp:29-153 ----------------------------------------------------------- */
+static double *zalloc(size_t n, const char *what) {
+  double *p = (double *)calloc(n ? n : 1, sizeof(double));
+  if (!p) { FILE_LOG_SINGLE(ERROR, "Error in allocating %s array", what); TerminateFemTech(12); }
+  return p;
+}
+void AllocateArrays() {
+  displacements = zalloc(nDOF, "displacements");
+  boundary = (int *)calloc(nDOF, sizeof(int));
+  if (!boundary) { FILE_LOG_SINGLE(ERROR, "Error in allocating boundary array"); TerminateFemTech(12); }
+  if (ImplicitDynamic || ExplicitDynamic) {
+    velocities = zalloc(nDOF, "velocities");
+    accelerations = zalloc(nDOF, "accelerations");
+    velocities_half = zalloc(nDOF, "velocities_half");
+    displacements_prev = zalloc(nDOF, "displacements_prev");
+    accelerations_prev = zalloc(nDOF, "accelerations_prev");
+    Eavg = zalloc((size_t)nelements * ndim * ndim, "Eavg");
+    fe = zalloc(nDOF, "fe"); fe_prev = zalloc(nDOF, "fe_prev");
+    fi = zalloc(nDOF, "fi"); fi_prev = zalloc(nDOF, "fi_prev");
+    f_net = zalloc(nDOF, "f_net");
+    fr_prev = zalloc(nDOF, "fr_prev"); fr_curr = zalloc(nDOF, "fr_curr"); fi_curr = zalloc(nDOF, "fi_curr");
+    f_damp_curr = zalloc(nDOF, "f_damp_curr"); f_damp_prev = zalloc(nDOF, "f_damp_prev");
+    std::string energyFileName = "energy_" + uid + ".dat";
+    energyFile = fopen(energyFileName.c_str(), "w");
+    fprintf(energyFile, "# Energy for FEM\n");
+    fprintf(energyFile, "# Time  Winternal   Wexternal   WKE   total\n");
+    stepTime = (double *)malloc((MAXPLOTSTEPS) * sizeof(double));
+    if (!stepTime) { FILE_LOG_SINGLE(ERROR, "Error in allocating stepTime array"); TerminateFemTech(12); }
+  }
+}
+
+/* ---- src/fem/ShapeFunctions/ShapeFunctions.cpp:32-255: only the offset tables are kept on the host; the
+ * per-Gauss-point tables (shp, dshp, detJacobian: 3.8 kB per element) are never built -- the device
+ * recomputes them.  F, detF and pk2 are materialised lazily by CalculateStrain(). ------------------------- */
+void ShapeFunctions() {
+  ensure_ctx();
+  GaussPoints = (int *)malloc(nelements * sizeof(int));
+  nShapeFunctions = (int *)malloc(nelements * sizeof(int));
+  gptr = (int *)malloc((nelements + 1) * sizeof(int)); dsptr = (int *)malloc((nelements + 1) * sizeof(int));
+  gpPtr = (int *)malloc((nelements + 1) * sizeof(int)); fptr = (int *)malloc((nelements + 1) * sizeof(int));
+  pk2ptr = (int *)malloc((nelements + 1) * sizeof(int)); detFptr = (int *)malloc((nelements + 1) * sizeof(int));
+  InternalsPtr = (int *)malloc((nelements + 1) * sizeof(int));
+  for (int i = 0; i <= nelements; ++i) {  /* hex8: ShapeFunctions.cpp:71-122,157-164 */
+    gptr[i] = 64 * i; dsptr[i] = 192 * i; gpPtr[i] = 8 * i; fptr[i] = 72 * i; pk2ptr[i] = 48 * i; detFptr[i] = 8 * i;
+    InternalsPtr[i] = MAXINTERNALVARS * 8 * i;
+    if (i < nelements) { GaussPoints[i] = 8; nShapeFunctions[i] = 8; }
+  }
+  double minDetJ = 0;
+  check(ftb200_shape_functions(g_ctx, &minDetJ));
+}
+
+/* ---- src/fem/Mass/Mass3D.cpp:127-157 ---------------------------------------------------------------- */
+void AssembleLumpedMass(void) {
+  ensure_ctx();
+  mass = (double *)calloc(nDOF, sizeof(double));
+  if (!mass) { FILE_LOG_SINGLE(ERROR, "Allocation of mass matrix failed"); TerminateFemTech(12); }
+  if (world_size > 1) {
+    FILE_LOG_SINGLE(ERROR, "femtech_b200 legacy mode is single rank; multi-GPU runs use the resident path (femtech_b200.dist)");
+    TerminateFemTech(3);
+  }
+  check(ftb200_lumped_mass(g_ctx, mass));
+}
+static void implicit_only(const char *what) {
+  FILE_LOG_SINGLE(ERROR, "%s belongs to the dense implicit solvers, which femtech_b200 does not replace", what);
+  TerminateFemTech(3);
+}
+void MassElementMatrix(double *, int) { implicit_only("MassElementMatrix"); }
+void LumpMassMatrix(void) { implicit_only("LumpMassMatrix"); }
+void updateMassMatrixNeighbour(void) { implicit_only("updateMassMatrixNeighbour"); }
+
+/* ---- src/fem/SolidMechanics/GetForce.cpp:12-25, GetForce_3D.cpp:5-53 ----------------------------------- */
+void GetForce_3D() {
+  bool anyFe = false;
+  for (int i = 0; i < nDOF && !anyFe; ++i) anyFe = fe[i] != 0.0;
+  check(ftb200_get_force(g_ctx, displacements, anyFe ? fe : NULL, dt, fi, f_net));
+}
+void GetForce() {
+  if (ndim != 3) { FILE_LOG_SINGLE(ERROR, "GetForce function not yet implemented for %dD", ndim); TerminateFemTech(3); }
+  GetForce_3D();
+}
+/* ---- src/fem/SolidMechanics/CalculateAcclerations.cpp:4-13 ------------------------------------------- */
+void CalculateAccelerations() { check(ftb200_calculate_accelerations(g_ctx, boundary, accelerations)); }
+
+/* ---- src/timestep/StableTimeStep.cpp:4-40 ------------------------------------------------------------- */
+double StableTimeStep() {
+  double dtMin = huge;
+  check(ftb200_stable_time_step(g_ctx, displacements, boundary, &dtMin));
+  MPI_Allreduce(MPI_IN_PLACE, &dtMin, 1, MPI_DOUBLE, MPI_MIN, MPI_COMM_WORLD);
+  if (dtMin < FailureTimeStep) {
+    FILE_LOG_MASTER(ERROR, "Timestep too small, dt = %15.9e", dtMin);
+    TerminateFemTech(19);
+  }
+  return dtMin;
+}
+
+/* ---- src/fem/SolidMechanics/CheckEnergy.cpp:3-85 ------------------------------------------------------- */
+void CheckEnergy(double time, int writeFlag) {
+  static double Wint_n = 0.0, Wext_n = 0.0;
+  double part[3];
+  check(ftb200_check_energy(g_ctx, displacements, displacements_prev, velocities, accelerations, accelerations_prev, fi,
+                            fi_prev, fe, fe_prev, boundary, part));
+  double WKE_Total = 0.0, Wint_n_total = 0.0, Wext_n_total = 0.0;
+  MPI_Reduce(&part[0], &WKE_Total, 1, MPI_DOUBLE, MPI_SUM, 0, MPI_COMM_WORLD);
+  MPI_Reduce(&part[1], &Wint_n_total, 1, MPI_DOUBLE, MPI_SUM, 0, MPI_COMM_WORLD);
+  MPI_Reduce(&part[2], &Wext_n_total, 1, MPI_DOUBLE, MPI_SUM, 0, MPI_COMM_WORLD);
+  if (world_rank == 0) {
+    Wint_n += Wint_n_total;
+    Wext_n += Wext_n_total;
+    double total = fabs(WKE_Total + Wint_n - Wext_n);
+    double max = fabs(Wint_n);
+    if (max < fabs(Wext_n)) max = fabs(Wext_n);
+    if (max < fabs(WKE_Total)) max = fabs(WKE_Total);
+    if (total > 0.01 * max)
+      FILE_LOG_MASTER(WARNING, "Energy Violation. Total = %15.9e, Max = %15.9e, Error%% : %10.2f", total, max, total * 100.0 / max);
+    if (writeFlag == 0) fprintf(energyFile, "%12.6e %12.6e  %12.6e  %12.6e %12.6e\n", time, Wint_n, Wext_n, WKE_Total, total);
+  }
+}
+
+/* ---- src/elements/ElementCalculations/CalculateStrain.cpp:77-97 + lazy Gauss-point outputs --------------- */
+void CalculateStrain() {
+  if (!F) F = (double *)calloc((size_t)72 * nelements, sizeof(double));
+  if (!detF) detF = (double *)calloc((size_t)8 * nelements, sizeof(double));
+  if (!pk2) pk2 = (double *)calloc((size_t)48 * nelements, sizeof(double));
+  check(ftb200_get_gp_outputs(g_ctx, F, detF, pk2, Eavg));
+}
+
+/* ---- include/FemTech.h:50 -- a stub in the reference (src/fem/Solver/ExplicitDynamics.cpp:7-9); here the whole
+ * loop of the drivers (Benchmarking-Parallel.cpp:83-171) resident on the GPU.  The driver's boundary-condition
+ * callback becomes the descriptor set with femtech_b200_set_bc() (femtech_b200_ext.h). ---------------------- */
+void femtech_b200_set_bc(const int *bc_kind, const double bc_rate[4], int energy_every) {
+  if (!g_bc_kind) g_bc_kind = (int *)malloc(sizeof(int) * nDOF);
+  memcpy(g_bc_kind, bc_kind, sizeof(int) * nDOF);
+  memcpy(g_bc_rate, bc_rate, sizeof(g_bc_rate));
+  g_energy_every = energy_every;
+}
+void ExplicitDynamics(double timeFinal, char *name) {
+  (void)name;
+  ensure_ctx();
+  if (!g_bc_kind) { FILE_LOG_SINGLE(ERROR, "ExplicitDynamics: call femtech_b200_set_bc() first"); TerminateFemTech(3); }
+  if (world_size > 1) { FILE_LOG_SINGLE(ERROR, "ExplicitDynamics: multi-GPU runs are driven by femtech_b200.dist"); TerminateFemTech(3); }
+  check(ftb200_set_state(g_ctx, displacements, velocities, accelerations, boundary));
+  check(ftb200_set_bc(g_ctx, g_bc_kind, g_bc_rate));
+  check(ftb200_explicit_begin(g_ctx, Time, ExplicitTimeStepReduction, FailureTimeStep, g_energy_every));
+  long long steps = 0;
+  check(ftb200_explicit_run(g_ctx, timeFinal, 0x7FFFFFFFFFFFLL, &steps, &Time, &dt));
+  check(ftb200_get_state(g_ctx, displacements, velocities, accelerations, boundary, fi, f_net));
+  if (g_energy_every && world_rank == 0) {
+    double e[4];
+    check(ftb200_get_energy(g_ctx, e));
+    fprintf(energyFile, "%12.6e %12.6e  %12.6e  %12.6e %12.6e\n", Time, e[0], e[1], e[2], e[3]);
+  }
+  FILE_LOG_MASTER(INFO, "ExplicitDynamics: %lld steps on the GPU, Time = %15.6e", steps, Time);
+}
+
+/* ---- src/io/output/FreeArrays.cpp:4-83 --------------------------------------------------------------------- */
+void FreeArrays() {
+  if (g_ctx) { ftb200_destroy(g_ctx); g_ctx = NULL; }
+  void *ptrs[] = {coordinates, connectivity, globalNodeID, pid, global_eid, eptr, shp, dshp, dsptr, gptr, nShapeFunctions, C,
+                  gaussWeights, gpPtr, detJacobian, mass, stiffness, rhs, displacements, velocities, accelerations,
+                  accelerations_prev, boundary, velocities_half, fe, fe_prev, fi, f_net, fr_prev, fr_curr, fi_prev, fi_curr,
+                  f_damp_prev, f_damp_curr, displacements_prev, F, pk2, pk2ptr, fptr, materialID, properties, detF, invF,
+                  Eavg, detFptr, InternalsPtr, internals, GaussPoints, recvNodeDisplacement, sendProcessID,
+                  sendNeighbourCount, sendNeighbourCountCum, sendNodeIndex, sendNodeDisplacement, stepTime, mat1, mat2,
+                  mat3, mat4, fintGQ, B, Hn_1, Hn_2, S0n, g_bc_kind};
+  for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); ++i) free1DArray(ptrs[i]);
+  g_bc_kind = NULL;
+  if (ElementType != NULL) {
+    for (int i = 0; i < nelements; i++) free(ElementType[i]);
+    free(ElementType);
+    ElementType = NULL;
+  }
+  if (world_rank == 0 && energyFile) fclose(energyFile);
+}

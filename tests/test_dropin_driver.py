@@ -1,0 +1,81 @@
+"""The reference's UNMODIFIED example drivers, linked against femtech_b200 (integration/femtech_host.cpp ->
+C-ABI -> CUDA), run on the GPU: examples/ex9/ex9.cpp is the reference's own known-answer test
+(.travis.yml:113-115, compareResults.py) and examples/Benchmarking-Parallel/Benchmarking-Parallel.cpp is
+BASELINE config 1.  The binaries are linked in the build container (integration/build_dropin.sh) and travel
+to the GPU box under oracle/_ref/."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from femtech_b200 import mesh
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _need(name):
+    p = os.path.join(BIN, name)
+    if not os.path.exists(p):
+        pytest.skip("%s not built (integration/build_dropin.sh needs the reference sources)" % name)
+    return p
+
+
+def test_ex9_unmodified_driver_on_gpu(tmp_path):
+    exe = _need("dropin_ex9")
+    X, conn, pid = mesh.cube_mesh(1)
+    mesh.write_abaqus_inp(str(tmp_path / "cube1.inp"), X, conn, pid)
+    mesh.write_materials_dat(str(tmp_path / "materials.dat"), [1], [1040.0, 100.0, 100.0, 0, 0, 0, 0, 0, 0])
+    os.makedirs(tmp_path / "results" / "vtu")  # WriteVTU.cpp:21-30 fopens ./results/vtu/... without creating it
+    r = subprocess.run([exe, "cube1.inp"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    last = open(tmp_path / "plot.dat").read().strip().splitlines()[-1].split()
+    t, u = float(last[0]), np.array([float(x) for x in last[1:4]])
+    # compareResults.py:14-29 against abaqus/abaqus.rpt (5 %), and the value the reference itself produces
+    abaqus = np.array([-1.03349e-03, 7.0e-03, -1.03349e-03])
+    assert abs(t - 1.0) < 0.01 and np.max(np.abs((u - abaqus) / abaqus)) < 0.05
+    assert np.allclose(u, [-1.07624e-03, 7.00001e-03, -1.07624e-03], rtol=2e-5)
+
+
+def test_benchmarking_parallel_unmodified_driver_on_gpu(tmp_path):
+    exe = _need("dropin_benchmarking_parallel")
+    from oracle import pyoracle as po
+    X, conn, pid = mesh.cube_mesh(10)
+    soft = [1040.0, 100.0, 100.0, 0, 0, 0, 0, 0, 0]
+    mesh.write_abaqus_inp(str(tmp_path / "cube10.inp"), X, conn, pid)
+    mesh.write_materials_dat(str(tmp_path / "materials.dat"), [1], soft)
+    r = subprocess.run([exe, "cube10.inp"], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    log = [f for f in os.listdir(tmp_path) if f.startswith("femtech_")][0]
+    txt = open(tmp_path / log).read()
+    m = re.findall(r"Total time steps : (\d+)", txt)
+    vals = re.findall(r"INFO\s*\[\s*0\]:\s+([-0-9.e+]+)\s+([-0-9.e+]+)\s+([-0-9.e+]+)\s+([-0-9.e+]+)\s*$", txt, flags=re.M)
+    assert m and vals
+    o = po.OracleModel(X, conn, pid, [1], soft)
+    o.ShapeFunctions()
+    o.AssembleLumpedMass()
+    kind, rate = mesh.benchmark_bc(X)
+    n, _, eh = po.run_explicit([o], [kind], rate, 0.1, 10 ** 6)
+    assert int(m[-1]) == n + 1  # the driver's counter starts at 1
+    got = np.array([float(x) for x in vals[-1]])
+    want = np.array([o.Time, o.displacements[0], o.displacements[1], o.displacements[2]])
+    assert np.allclose(got, want, rtol=2e-3, atol=1e-9)  # the driver logs %11.3e
+    en = [l.split() for l in open(tmp_path / [f for f in os.listdir(tmp_path) if f.startswith("energy_")][0])
+          if not l.startswith("#")]
+    # CheckEnergy writes a line whenever step % nsteps_plot == 0 (Benchmarking-Parallel.cpp:154-155)
+    nsteps_plot = int(int(0.1 / dth0(o, X, kind, rate)) / 50)
+    last = np.array(en[-1], dtype=float)
+    k = (n // nsteps_plot) * nsteps_plot  # 1-based step of the last written line
+    assert np.allclose(last[1:4], eh[k - 1][:3], rtol=5e-6, atol=1e-30)
+
+
+def dth0(o, X, kind, rate):
+    """initial dt of the same problem (fresh oracle model)"""
+    from oracle import pyoracle as po
+    m = po.OracleModel(o.coordinates, o.connectivity, o.pid, o.materialID, o.properties)
+    m.ShapeFunctions()
+    m.boundary[kind > 0] = 1
+    return 0.8 * m.StableTimeStep()
