@@ -40,7 +40,7 @@ def algorithmic_bytes(n, mat, energy):
     return elem + hist, node
 
 
-ELEM_FLOPS = {1: 4690.0, 4: 5650.0, 5: 7300.0}  # per element-step, counted in DESIGN.md
+ELEM_FLOPS = {1: 3490.0, 4: 4400.0, 5: 6550.0}  # executed fp64 flops per element in K_elem (ncu for mat 1, SASS count for 4/5)
 
 
 def clocks_sampler(stop, out, device_index):
