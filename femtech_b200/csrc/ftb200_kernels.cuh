@@ -113,16 +113,19 @@ struct SmemScratch {
 // K1 (+K6).  MATSEL >= 0: every element of the launch has that material (no switch).
 template <int MATSEL, bool WITH_FORCE, bool WITH_DT>
 __global__ void __launch_bounds__(ELEM_BLOCK, ELEM_MINBLOCKS) k_elem(const ElemArgs A) {
-  if (!A.ignore_loop_flags && (A.sc->last | A.sc->done)) return;
   const int e = A.e0 + blockIdx.x * ELEM_BLOCK + threadIdx.x;
+  const size_t E = (size_t)A.nE;
+  // the connectivity is requested before the loop-control flags are tested: one exposed latency, not two
+  int nd[8];
+  if (e < A.e1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) nd[k] = __ldg(A.conn + (size_t)k * E + e);
+  }
+  if (!A.ignore_loop_flags && (A.sc->last | A.sc->done)) return;
   __shared__ double sm_cols[WITH_FORCE ? 72 : 1][ELEM_BLOCK];
   double dte = 1e300;
   int status = 0;
   if (e < A.e1) {
-    const size_t E = (size_t)A.nE;
-    int nd[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) nd[k] = __ldg(A.conn + (size_t)k * E + e);
     double X[8][3], U[8][3];
 #pragma unroll
     for (int k = 0; k < 8; ++k)
