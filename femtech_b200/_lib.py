@@ -56,8 +56,8 @@ SIGNATURES = {
     "ftb200_explicit_begin_dt": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(_vp)]),
     "ftb200_explicit_begin_force": (C.c_int, [_vp, _vp]),
     "ftb200_explicit_begin_finish": (C.c_int, [_vp, _vp]),
-    "ftb200_p2p_export": (C.c_int, [_vp, _vp]),
-    "ftb200_p2p_import": (C.c_int, [_vp, _vp]),
+    "ftb200_p2p_export": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "ftb200_p2p_import": (C.c_int, [_vp, _vp, C.c_int, _ip, _ip, _ip]),
     "ftb200_profile_enable": (C.c_int, [_vp, C.c_int]),
     "ftb200_profile_get": (C.c_int, [_vp, _dp, _dp, C.POINTER(_ll), C.POINTER(_ll)]),
     "ftb200_measure_peaks": (C.c_int, [_vp, C.c_int, _dp, _dp]),

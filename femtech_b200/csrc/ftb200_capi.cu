@@ -80,6 +80,17 @@ struct ftb200_ctx {
   int *d_sendNodeIndex = nullptr, *halo_nodes = nullptr, *halo_off = nullptr, *halo_slot = nullptr,
       *halo_node_idx = nullptr;
   const double* halo_recv_cur = nullptr;
+  // peer-memory transport
+  char* p2p_window = nullptr;
+  size_t p2p_bytes = 0;
+  P2PArgs p2p;
+  bool p2p_ready = false;
+  unsigned long long* d_seq = nullptr;
+  unsigned* d_p2p_blocks = nullptr;
+  std::vector<void*> p2p_opened;
+  cudaGraphExec_t p2p_graph = nullptr;
+  int p2p_graph_energy = -1;
+  long long p2p_graph_launches = 0;
   double Time0 = 0.0;
   // graph cache
   cudaGraphExec_t graph = nullptr;
@@ -159,6 +170,8 @@ NodeArgs node_args(ftb200_ctx* c, const double* recv) {
   A.halo_node_idx = recv ? c->halo_node_idx : nullptr;
   A.epart = c->epart; A.sc = c->sc; A.nN = c->nNp; A.nE = c->nE;
   A.store_fi = c->energy ? 1 : 0;
+  A.halo_recv_alt = nullptr;
+  A.p2p_seq = nullptr;
   return A;
 }
 
@@ -280,6 +293,11 @@ void free_all(ftb200_ctx* c) {
   dfree(c->dthist); dfree(c->ehist); dfree(c->epart); dfree(c->out3); dfree(c->d_istage); dfree(c->d_big);
   c->d_big_bytes = 0;
   dfree(c->d_detmin); dfree(c->d_nonpos);
+  for (void* q : c->p2p_opened) cudaIpcCloseMemHandle(q);
+  c->p2p_opened.clear();
+  dfree(c->p2p_window); dfree(c->d_seq); dfree(c->d_p2p_blocks);
+  c->p2p_ready = false;
+  if (c->p2p_graph) { cudaGraphExecDestroy(c->p2p_graph); c->p2p_graph = nullptr; }
   dfree(c->d_nref); dfree(c->d_nint); dfree(c->d_ctl); dfree(c->d_etile_chunk); dfree(c->d_ntile_group); dfree(c->d_etile); dfree(c->d_ell);
   if (c->pgraph) { cudaGraphExecDestroy(c->pgraph); c->pgraph = nullptr; }
   dfree(c->d_sendNodeIndex); dfree(c->halo_nodes); dfree(c->halo_off); dfree(c->halo_slot); dfree(c->halo_node_idx);
@@ -835,6 +853,12 @@ int ftb200_get_state(ftb200_ctx* ctx, double* displacements, double* velocities,
   CK(cudaSetDevice(ctx->device));
   int rc;
   if (fi || f_net) {  // lazily rebuilt from the element forces of the last evaluation
+    if (ctx->p2p_ready && ctx->halo_count && !ctx->halo_recv_cur) {
+      unsigned long long seq = 0;
+      CK(cudaMemcpyAsync(&seq, ctx->d_seq, sizeof(seq), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      if (seq > 0) ctx->halo_recv_cur = p2p_recv(ctx->p2p_window, ctx->halo_count, (int)((seq - 1) & 1ULL));
+    }
     const NodeArgs N = node_args(ctx, ctx->halo_recv_cur);
     LAUNCH(k_gather_force, ctx->node_blocks, NODE_BLOCK, ctx->stream, N, ctx->fnet[0], ctx->fnet[1], ctx->fnet[2]);
   }
@@ -996,6 +1020,73 @@ static int build_graph(ftb200_ctx* ctx) {
   return 0;
 }
 
+// ---- peer-memory multi-GPU step: boundary elements -> pack into the neighbours' windows || interior elements ->
+//      dt exchange + arrival waits + scalar update -> node kernel (receive window selected by step parity)
+static void launch_step_p2p(ftb200_ctx* ctx) {
+  cudaStream_t s = ctx->stream, s2 = ctx->stream2;
+  const int nEb = ctx->nE_boundary;
+  cudaEventRecord(ctx->ev_fork, s);
+  cudaStreamWaitEvent(s2, ctx->ev_fork, 0);
+  launch_elem<true, true>(ctx, s2, nEb, ctx->nE, 0);
+  cudaEventRecord(ctx->ev_join, s2);
+  launch_elem<true, true>(ctx, s, 0, nEb, 0);
+  if (ctx->halo_count)
+    LAUNCH(k_p2p_pack, cdiv(ctx->halo_count, 128), 128, s, ctx->p2p, ctx->felem, ctx->node_off, ctx->node_ent,
+           ctx->d_sendNodeIndex, ctx->sc, ctx->nE);
+  cudaStreamWaitEvent(s, ctx->ev_join, 0);
+  LAUNCH(k_adv_p2p, 1, 128, s, ctx->p2p, ctx->sc, ctx->mp, ctx->nPID, ctx->dthist);
+  NodeArgs N = node_args(ctx, ctx->halo_count ? p2p_recv(ctx->p2p_window, ctx->halo_count, 0) : nullptr);
+  if (ctx->halo_count) {
+    N.halo_recv_alt = p2p_recv(ctx->p2p_window, ctx->halo_count, 1);
+    N.p2p_seq = ctx->d_seq;
+  }
+  if (ctx->energy) LAUNCH((k_node<true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
+  else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+  if (ctx->energy) LAUNCH(k_energy, 1, 256, s, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
+}
+
+static int run_async_p2p(ftb200_ctx* ctx, double tMax, long long steps) {
+  cudaStream_t s = ctx->stream;
+  LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
+  {
+    const NodeArgs N = node_args(ctx, nullptr);
+    if (ctx->energy) LAUNCH((k_node<false, true, false, true>), ctx->node_blocks, NODE_BLOCK, s, N);
+    else LAUNCH((k_node<false, true, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+  }
+  const bool use_graph = !ctx->profile && steps >= GRAPH_STEPS;
+  if (use_graph && !(ctx->p2p_graph && ctx->p2p_graph_energy == ctx->energy)) {
+    if (ctx->p2p_graph) { cudaGraphExecDestroy(ctx->p2p_graph); ctx->p2p_graph = nullptr; }
+    cudaGraph_t g = nullptr;
+    const long long before = ctx->launches;
+    CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < GRAPH_STEPS; ++i) launch_step_p2p(ctx);
+    cudaError_t e = cudaStreamEndCapture(s, &g);
+    const long long per_graph = ctx->launches - before;
+    ctx->launches = before;
+    if (e != cudaSuccess) return fail(ctx, FTB200_ERR_CUDA, "p2p graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&ctx->p2p_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { ctx->p2p_graph = nullptr; return fail(ctx, FTB200_ERR_CUDA, "p2p graph instantiate failed: %s", cudaGetErrorString(e)); }
+    ctx->p2p_graph_energy = ctx->energy;
+    ctx->p2p_graph_launches = per_graph;
+  }
+  long long left = steps;
+  while (left > 0) {
+    if (use_graph && left >= GRAPH_STEPS) {
+      CK(cudaGraphLaunch(ctx->p2p_graph, s));
+      ctx->launches += ctx->p2p_graph_launches;
+      left -= GRAPH_STEPS;
+    } else {
+      launch_step_p2p(ctx);
+      left--;
+    }
+  }
+  // the receive window of the last step, for a later get_state
+  ctx->halo_recv_cur = nullptr;
+  CK(cudaGetLastError());
+  return FTB200_OK;
+}
+
 static int build_pipe_graph(ftb200_ctx* ctx) {
   if (ctx->pgraph && ctx->pgraph_energy == ctx->energy) return 0;
   if (ctx->pgraph) { cudaGraphExecDestroy(ctx->pgraph); ctx->pgraph = nullptr; }
@@ -1039,9 +1130,14 @@ static int run_async_pipe(ftb200_ctx* ctx, double tMax, long long steps) {
 
 int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
   if (!ctx || !ctx->begun) return fail(ctx, FTB200_ERR_INPUT, "explicit_run: call explicit_begin first");
-  if (ctx->halo_count && ctx->nranks > 1)
-    return fail(ctx, FTB200_ERR_INPUT, "explicit_run: this rank has shared nodes; drive the loop with step_begin/step_end");
   CK(cudaSetDevice(ctx->device));
+  if (ctx->nranks > 1) {
+    if (!ctx->p2p_ready)
+      return fail(ctx, FTB200_ERR_INPUT, "explicit_run: multi-rank runs need the peer-memory windows (p2p_export/import) "
+                                         "or the step_begin/step_join/step_end sequence");
+    if (steps <= 0) return FTB200_OK;
+    return run_async_p2p(ctx, tMax, steps);
+  }
   if (steps <= 0) return FTB200_OK;
   if (ctx->pipe) return run_async_pipe(ctx, tMax, steps);
   cudaStream_t s = ctx->stream;
@@ -1084,6 +1180,7 @@ int ftb200_explicit_poll(ftb200_ctx* ctx, long long* steps_done, double* Time, d
   if (dt) *dt = h.ndt;
   if (status_bits) *status_bits = h.status;
   if (h.status & 32) return fail(ctx, FTB200_ERR_CUDA, "pipelined loop stalled: element and node kernels were not co-resident");
+  if (h.status & 64) return fail(ctx, FTB200_ERR_CUDA, "peer-memory exchange timed out: a neighbour rank never delivered its step");
   return FTB200_OK;
 }
 
@@ -1203,13 +1300,86 @@ int ftb200_step_end(ftb200_ctx* ctx, const double* recv_dev) {
   ctx->halo_recv_cur = ctx->halo_count ? recv_dev : nullptr;
   return FTB200_OK;
 }
-int ftb200_p2p_export(ftb200_ctx* ctx, void* handle_out) {
-  (void)handle_out;
-  return fail(ctx, FTB200_ERR_INPUT, "p2p_export: not available in this build");
+int ftb200_p2p_export(ftb200_ctx* ctx, void* handle_out, void** window_out) {
+  if (!ctx || !ctx->shape_ok) return fail(ctx, FTB200_ERR_INPUT, "p2p_export: call shape_functions first");
+  CK(cudaSetDevice(ctx->device));
+  if ((int)ctx->h_sendProcessID.size() > P2P_MAXNB || ctx->nranks > P2P_MAXP)
+    return fail(ctx, FTB200_ERR_INPUT, "p2p_export: more than %d neighbours or %d ranks", P2P_MAXNB, P2P_MAXP);
+  if (!ctx->p2p_window) {
+    ctx->p2p_bytes = sizeof(P2PHeader) + 2 * 3 * (size_t)std::max(ctx->halo_count, 1) * sizeof(double);
+    CK(cudaMalloc((void**)&ctx->p2p_window, ctx->p2p_bytes));
+    CK(cudaMemset(ctx->p2p_window, 0, ctx->p2p_bytes));
+    int rc;
+    if ((rc = dalloc(ctx, &ctx->d_seq, 1)) || (rc = dalloc(ctx, &ctx->d_p2p_blocks, 1))) return rc;
+    CK(cudaMemset(ctx->d_seq, 0, sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->d_p2p_blocks, 0, sizeof(unsigned)));
+    CK(cudaDeviceSynchronize());
+  }
+  if (handle_out) {
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->p2p_window));
+    static_assert(sizeof(cudaIpcMemHandle_t) == FTB200_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(handle_out, &h, sizeof(h));
+  }
+  if (window_out) *window_out = ctx->p2p_window;
+  return FTB200_OK;
 }
-int ftb200_p2p_import(ftb200_ctx* ctx, const void* all_handles) {
-  (void)all_handles;
-  return fail(ctx, FTB200_ERR_INPUT, "p2p_import: not available in this build");
+
+int ftb200_p2p_import(ftb200_ctx* ctx, const void* all_handles, int handles_are_pointers, const int* peer_slot_offset,
+                      const int* peer_my_index, const int* peer_halo_count) {
+  if (!ctx || !ctx->p2p_window || !all_handles) return fail(ctx, FTB200_ERR_INPUT, "p2p_import: call p2p_export first");
+  const int nnb = (int)ctx->h_sendProcessID.size();
+  if (nnb && (!peer_slot_offset || !peer_my_index || !peer_halo_count)) return fail(ctx, FTB200_ERR_INPUT, "p2p_import: null metadata");
+  CK(cudaSetDevice(ctx->device));
+  P2PArgs& P = ctx->p2p;
+  memset(&P, 0, sizeof(P));
+  P.self = ctx->p2p_window;
+  P.n_nb = nnb; P.n_ranks = ctx->nranks; P.rank = ctx->rank; P.H = ctx->halo_count;
+  P.seq = ctx->d_seq; P.blocks_done = ctx->d_p2p_blocks;
+  for (int r = 0; r < ctx->nranks; ++r) {
+    if (r == ctx->rank) { P.peer_rank[r] = ctx->p2p_window; continue; }
+    if (handles_are_pointers) {
+      P.peer_rank[r] = (char*)((void* const*)all_handles)[r];
+    } else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char*)all_handles + (size_t)r * FTB200_IPC_HANDLE_BYTES, sizeof(h));
+      void* q = nullptr;
+      CK(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+      ctx->p2p_opened.push_back(q);
+      P.peer_rank[r] = (char*)q;
+    }
+  }
+  for (int i = 0; i < nnb; ++i) {
+    const int q = ctx->h_sendProcessID[i];
+    if (q < 0 || q >= ctx->nranks) return fail(ctx, FTB200_ERR_INPUT, "p2p_import: neighbour rank %d out of range", q);
+    P.peer_nb[i] = P.peer_rank[q];
+    P.peer_slot_off[i] = peer_slot_offset[i];
+    P.peer_my_index[i] = peer_my_index[i];
+    P.peer_H[i] = peer_halo_count[i];
+    P.nb_cum[i] = ctx->h_sendCum[i];
+  }
+  P.nb_cum[nnb] = ctx->h_sendCum[nnb];
+  // Load every kernel of the loop NOW: with lazy module loading the first launch of a kernel may
+  // synchronise the context, which would deadlock against a peer's spinning wait kernel when several
+  // ranks live in one process.
+  {
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, k_p2p_pack));
+    CK(cudaFuncGetAttributes(&fa, k_adv_p2p));
+    CK(cudaFuncGetAttributes(&fa, k_begin_run));
+    CK(cudaFuncGetAttributes(&fa, k_energy));
+    CK(cudaFuncGetAttributes(&fa, k_gather_force));
+    CK(cudaFuncGetAttributes(&fa, k_node<true, true, true, true>));
+    CK(cudaFuncGetAttributes(&fa, k_node<true, true, true, false>));
+    CK(cudaFuncGetAttributes(&fa, k_node<false, true, false, true>));
+    CK(cudaFuncGetAttributes(&fa, k_node<false, true, false, false>));
+    CK(cudaFuncGetAttributes(&fa, k_elem<1, true, true>));
+    CK(cudaFuncGetAttributes(&fa, k_elem<4, true, true>));
+    CK(cudaFuncGetAttributes(&fa, k_elem<5, true, true>));
+    CK(cudaFuncGetAttributes(&fa, k_elem<-1, true, true>));
+  }
+  ctx->p2p_ready = true;
+  return FTB200_OK;
 }
 
 // ------------------------------------------------------------------------------------ measurement

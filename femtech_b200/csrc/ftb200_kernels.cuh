@@ -191,6 +191,8 @@ struct NodeArgs {
   const int* node_off;
   const int* node_ent;
   const double* halo_recv;   // device recv window or nullptr
+  const double* halo_recv_alt;  // peer-memory transport: second buffer; the step parity selects (nullptr = static)
+  const unsigned long long* p2p_seq;
   const int* halo_off;       // per shared node CSR into halo_slot (ascending neighbour order)
   const int* halo_slot;
   const int* halo_node_idx;  // node -> index into halo_off (or -1), nullptr when no halo
@@ -235,12 +237,16 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_node(const NodeArgs A) {
       }
       if (A.halo_node_idx) {  // shared node: add the neighbours' partial sums, ascending neighbour (:92-97)
         const int h = A.halo_node_idx[n];
-        if (h >= 0)
+        if (h >= 0) {
+          // peer-memory transport: the window that was filled during this step ((seq - 1) & 1, seq already advanced)
+          const double* rv = A.halo_recv;
+          if (A.halo_recv_alt && ((*A.p2p_seq - 1) & 1ULL)) rv = A.halo_recv_alt;
           for (int j = A.halo_off[h]; j < A.halo_off[h + 1]; ++j) {
             const int slot = A.halo_slot[j];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) f[c] += A.halo_recv[3 * (size_t)slot + c];
+            for (int c = 0; c < 3; ++c) f[c] += __ldcg(rv + 3 * (size_t)slot + c);
           }
+        }
       }
       const double m = A.m[n];
       const double dt1 = sc->t_half - sc->t_n, dt2 = sc->t_np1 - sc->t_half;
@@ -326,6 +332,44 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_node(const NodeArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pipe_now_ns_early() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// one loop iteration's scalar bookkeeping (thread 0 of one block); returns the next dt
+__device__ __forceinline__ double adv_step(DevScalars* sc, double* dt_hist) {
+  double dtmin = __longlong_as_double((long long)*(volatile unsigned long long*)&sc->dtmin_bits);
+  if (dtmin > 1e20) dtmin = 1e20;  // `huge`, GlobalVariables.h:16
+  sc->dtmin_bits = 0x7FF0000000000000ULL;
+  sc->t_n = sc->nt_n; sc->t_np1 = sc->nt_np1; sc->t_half = sc->nt_half; sc->dt = sc->ndt;
+  sc->Time = sc->t_np1;
+  if (dt_hist && sc->step < sc->hist_cap) dt_hist[sc->step] = sc->dt;
+  sc->step += 1;
+  sc->steps_left -= 1;
+  if (dtmin < sc->failure_dt) { sc->status |= 16; sc->last = 1; }  // TerminateFemTech(19)
+  const double ndt = sc->reduction * dtmin;
+  sc->ndt = ndt;
+  sc->nt_n = sc->Time;
+  sc->nt_np1 = sc->Time + ndt;                    // t_np1 = Time + dt
+  sc->nt_half = 0.5 * (sc->nt_np1 + sc->nt_n);    // t_nphalf = 0.5*(t_np1 + t_n)
+  if (!(sc->Time < sc->tMax) || sc->steps_left <= 0) sc->last = 1;
+  return ndt;
+}
+__device__ __forceinline__ void prony_update(double* mp, int nPID, double dt, int tid, int nthreads) {
+  for (int p = tid; p < nPID; p += nthreads) {  // HGOIsotropicViscoelastic.cpp:126-131
+    double* q = mp + (size_t)p * FTB_MP_STRIDE;
+    if ((int)q[MP_MATID] == 5) {
+      const double rt1 = dt / q[MP_T1], rt2 = dt / q[MP_T2];
+      const double c11 = exp(-rt1), c12 = exp(-rt2);
+      q[MP_C11] = c11;
+      q[MP_C12] = c12;
+      q[MP_C21] = q[MP_G1] * (1 - c11) / rt1;
+      q[MP_C22] = q[MP_G2] * (1 - c12) / rt2;
+    }
+  }
+}
+
 // Scalar bookkeeping of the time loop (Benchmarking-Parallel.cpp:106-112,168 and
 // StableTimeStep.cpp:33-38).  One thread block; thread p < nPID refreshes the Prony factors of part p
 // for the next dt (HGOIsotropicViscoelastic.cpp:126-131).
@@ -743,6 +787,131 @@ __global__ void k_sum3(const double* epart, int nblocks, double* out3) {
     __syncthreads();
   }
   if (threadIdx.x == 0) { out3[0] = 0.5 * sh[0][0]; out3[1] = 0.5 * sh[1][0]; out3[2] = 0.5 * sh[2][0]; }
+}
+
+// =============================================================================================
+// Peer-memory transport of the shared-node exchange (NVLink / NVSwitch, no NCCL on the data path).
+// Every rank owns one device "window" (cudaMalloc, exported with cudaIpcGetMemHandle):
+//     hflag[P2P_MAXNB]   per neighbour index: sequence number of the last step whose partials have arrived
+//     dflag[P2P_MAXP]    per source rank:    sequence number of the last step whose dt has arrived
+//     dtslot[2][P2P_MAXP] local stable dt of every rank, double buffered by step parity
+//     recv[2][3*H]       receive window in the reference's recvNodeDisplacement layout, double buffered
+// k_p2p_pack sums the element forces of each shared node and STORES the partial straight into the
+// neighbours' windows (the neighbour's slice offset is known from the symmetric send lists), then the last
+// block publishes the sequence number with a system-scope fence.  k_adv_p2p writes this rank's dt into
+// every rank's window, waits for all dt and all neighbours' partials of this step (bounded spin), takes the
+// MIN and does the scalar update of k_adv.  Two buffers suffice: a rank cannot run two steps ahead of a
+// neighbour because it needs that neighbour's dt to finish each step.  Everything is graph-capturable.
+constexpr int P2P_MAXNB = 64;
+constexpr int P2P_MAXP = 64;
+struct P2PHeader {
+  unsigned long long hflag[P2P_MAXNB];
+  unsigned long long dflag[P2P_MAXP];
+  double dtslot[2][P2P_MAXP];
+};
+struct P2PArgs {
+  char* self;                    // this rank's window
+  char* peer_nb[P2P_MAXNB];      // windows of the neighbours (by neighbour index)
+  int peer_slot_off[P2P_MAXNB];  // first slot of this rank's slice in the neighbour's receive window
+  int peer_my_index[P2P_MAXNB];  // this rank's neighbour index in the neighbour's list (its hflag entry)
+  int peer_H[P2P_MAXNB];         // slots of the neighbour's receive window (offset of its second buffer)
+  int nb_cum[P2P_MAXNB + 1];     // sendNeighbourCountCum
+  char* peer_rank[P2P_MAXP];     // windows of all ranks (dt exchange)
+  int n_nb, n_ranks, rank, H;
+  unsigned long long* seq;       // monotone step sequence (device), never reset
+  unsigned* blocks_done;
+};
+__host__ __device__ __forceinline__ double* p2p_recv(char* win, int H, int buf) {
+  return reinterpret_cast<double*>(win + sizeof(P2PHeader)) + (size_t)buf * 3 * (size_t)H;
+}
+
+__global__ void k_p2p_pack(const P2PArgs P, const double* felem, const int* node_off, const int* node_ent,
+                           const int* sendNodeIndex, const DevScalars* sc, int nE) {
+  if (sc->last | sc->done) return;
+  const unsigned long long seq = *P.seq;
+  const int buf = (int)(seq & 1ULL);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.H) {
+    int nb = 0;
+    while (i >= P.nb_cum[nb + 1]) ++nb;  // few neighbours: linear search in the cumulative counts
+    const int n = sendNodeIndex[i];
+    double f[3] = {0.0, 0.0, 0.0};
+    for (int j = node_off[n]; j < node_off[n + 1]; ++j) {  // every element of a shared node is a boundary element
+      const int ent = node_ent[j];
+      const size_t e = (size_t)(ent >> 3);
+      const int sl = ent & 7;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) f[c] += felem[(size_t)(3 * sl + c) * nE + e];
+    }
+    double* dst = p2p_recv(P.peer_nb[nb], P.peer_H[nb], buf) + 3 * (size_t)(P.peer_slot_off[nb] + (i - P.nb_cum[nb]));
+    dst[0] = f[0]; dst[1] = f[1]; dst[2] = f[2];  // peer store over NVLink
+  }
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = (atomicAdd(P.blocks_done, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence_system();
+    for (int nb = threadIdx.x; nb < P.n_nb; nb += blockDim.x) {
+      volatile unsigned long long* fl = &reinterpret_cast<P2PHeader*>(P.peer_nb[nb])->hflag[P.peer_my_index[nb]];
+      *fl = seq + 1;
+    }
+    if (threadIdx.x == 0) *P.blocks_done = 0;
+  }
+}
+
+// dt exchange + waits + the scalar update of k_adv<false>
+__global__ void k_adv_p2p(const P2PArgs P, DevScalars* sc, double* mp, int nPID, double* dt_hist) {
+  __shared__ double s_ndt;
+  __shared__ int s_live, s_ok;
+  if (threadIdx.x == 0) {
+    int live = 1;
+    if (sc->done) live = 0;
+    else if (sc->last) { sc->done = 1; live = 0; }
+    sc->active = live;
+    s_live = live;
+    s_ok = 1;
+  }
+  __syncthreads();
+  if (!s_live) return;
+  const unsigned long long seq = *P.seq;
+  const int buf = (int)(seq & 1ULL);
+  P2PHeader* self = reinterpret_cast<P2PHeader*>(P.self);
+  // publish this rank's dt to every rank (its own window included)
+  const double mydt = __longlong_as_double((long long)*(volatile unsigned long long*)&sc->dtmin_bits);
+  for (int r = threadIdx.x; r < P.n_ranks; r += blockDim.x) {
+    P2PHeader* w = reinterpret_cast<P2PHeader*>(P.peer_rank[r]);
+    *(volatile double*)&w->dtslot[buf][P.rank] = mydt;
+    __threadfence_system();
+    *(volatile unsigned long long*)&w->dflag[P.rank] = seq + 1;
+  }
+  // wait for every rank's dt and every neighbour's partials of this step
+  const unsigned long long t0 = pipe_now_ns_early();
+  for (int r = threadIdx.x; r < P.n_ranks + P.n_nb; r += blockDim.x) {
+    volatile unsigned long long* fl = r < P.n_ranks ? &self->dflag[r] : &self->hflag[r - P.n_ranks];
+    while (*fl < seq + 1) {
+      __nanosleep(100);
+      if (pipe_now_ns_early() - t0 > 5000000000ULL) { s_ok = 0; break; }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (!s_ok) { sc->status |= 64; sc->last = 1; }  // a peer never arrived: stop instead of hanging
+    double dtmin = 1e300;
+    for (int r = 0; r < P.n_ranks; ++r) {
+      const double d = *(volatile double*)&self->dtslot[buf][r];
+      if (d < dtmin) dtmin = d;
+    }
+    sc->dtmin_bits = (unsigned long long)__double_as_longlong(dtmin);
+    *P.seq = seq + 1;
+    s_ndt = adv_step(sc, dt_hist);
+  }
+  __syncthreads();
+  prony_update(mp, nPID, s_ndt, threadIdx.x, blockDim.x);
 }
 
 // =============================================================================================

@@ -168,6 +168,20 @@ def halo_add_host(field_aos, comm, recv):
         f[idx[i]] += r[i]
 
 
+def p2p_metadata(comms, rank):
+    """For rank `rank`: per neighbour i -> (first slot of our slice in its receive window, our index in its
+    neighbour list, its total slot count).  comms: every rank's comm pattern (the send lists are symmetric)."""
+    c = comms[rank]
+    off, idx, tot = [], [], []
+    for q in c["sendProcessID"]:
+        cq = comms[int(q)]
+        j = int(np.where(np.asarray(cq["sendProcessID"]) == rank)[0][0])
+        off.append(int(cq["sendNeighbourCountCum"][j]))
+        idx.append(j)
+        tot.append(int(cq["sendNeighbourCountCum"][-1]))
+    return (np.array(off, dtype=np.int32), np.array(idx, dtype=np.int32), np.array(tot, dtype=np.int32))
+
+
 class _DevDouble:
     """Zero-copy view of one device double for torch (CUDA array interface)."""
 
@@ -245,6 +259,28 @@ class DistFemTech:
             m._check(m.L.ftb200_step_join(m._h))
             self._allreduce_dtmin(ptr)
             m._check(m.L.ftb200_step_end(m._h, self._recv))
+
+    def enable_p2p(self, part_comm):
+        """Switch the loop to the peer-memory transport: exchange IPC handles and comm patterns once, then
+        `run_p2p` drives the whole multi-GPU step from CUDA graphs with no NCCL call per step."""
+        m, C, torch, dist = self.m, self.C, self.torch, self.dist
+        handle = (C.c_ubyte * 64)()
+        m._check(m.L.ftb200_p2p_export(m._h, handle, None))
+        mine = {"handle": bytes(handle), "comm": {k: np.asarray(v).tolist() for k, v in part_comm.items()}}
+        allr = [None] * self.world
+        dist.all_gather_object(allr, mine)
+        handles = b"".join(a["handle"] for a in allr)
+        comms = [{k: np.asarray(v, dtype=np.int32) for k, v in a["comm"].items()} for a in allr]
+        off, idx, tot = p2p_metadata(comms, self.rank)
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        ip = C.POINTER(C.c_int)
+        m._check(m.L.ftb200_p2p_import(m._h, buf, 0, off.ctypes.data_as(ip), idx.ctypes.data_as(ip), tot.ctypes.data_as(ip)))
+        self._p2p_keep = (off, idx, tot, buf)
+        dist.barrier()
+
+    def run_p2p(self, tMax, steps):
+        with self.torch.cuda.stream(self.stream):
+            self.m.run_async(tMax, steps)
 
     def energy(self):
         """Wint, Wext, WKE summed over ranks (CheckEnergy.cpp:54-64)."""
@@ -352,6 +388,34 @@ class LocalGroup:
         self._sync()
         for m in self.models:
             m._poll()
+
+    def enable_p2p(self):
+        """Peer-memory transport between the in-process ranks (device pointers instead of IPC handles)."""
+        C = self.C
+        wins = []
+        for m in self.models:
+            w = C.c_void_p()
+            m._check(m.L.ftb200_p2p_export(m._h, None, C.byref(w)))
+            wins.append(w.value)
+        arr = (C.c_void_p * self.P)(*wins)
+        ip = C.POINTER(C.c_int)
+        self._keep = []
+        for r, m in enumerate(self.models):
+            off, idx, tot = p2p_metadata(self.comms, r)
+            self._keep.append((off, idx, tot))
+            m._check(m.L.ftb200_p2p_import(m._h, arr, 1, off.ctypes.data_as(ip), idx.ctypes.data_as(ip), tot.ctypes.data_as(ip)))
+
+    def run_p2p(self, tMax, steps):
+        # direct launches (no graph capture/instantiate while a peer's wait kernel may be spinning: all the
+        # ranks share one CUDA context here; separate processes use the captured graph)
+        for m in self.models:
+            m.profile(True)
+        for m in self.models:
+            m.run_async(tMax, steps)
+        self._sync()
+        for m in self.models:
+            m._poll()
+            m.profile(False)
 
     def energy(self):
         e = np.sum([m.energy()[:3] for m in self.models], axis=0)

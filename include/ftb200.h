@@ -154,12 +154,22 @@ int ftb200_explicit_begin_finish(ftb200_ctx *ctx, const double *recv_dev);
 int ftb200_step_begin(ftb200_ctx *ctx, double *send_dev, double **dtmin_dev);
 int ftb200_step_join(ftb200_ctx *ctx);
 int ftb200_step_end(ftb200_ctx *ctx, const double *recv_dev);
-/* Peer-memory transport (NVLink/NVSwitch, no NCCL on the data path): every rank exports its receive
- * window, imports the neighbours' and the whole step, exchange included, runs inside
- * ftb200_explicit_run*.  handle is FTB200_IPC_HANDLE_BYTES bytes. */
+/* Peer-memory transport (NVLink/NVSwitch, no NCCL on the data path): every rank exports a device window,
+ * imports the other ranks', and from then on ftb200_explicit_run* runs the whole step on a rank with shared
+ * nodes -- pack kernel storing the shared-node partials straight into the neighbours' windows, flag-based
+ * arrival, dt MIN through the same windows -- with no host or NCCL involvement (CUDA-graph captured).
+ *   export: allocates the window; handle_out (64 bytes, may be NULL) receives the cudaIpcMemHandle_t,
+ *           *window_out (may be NULL) the device pointer (for ranks living in the same process).
+ *   import: all_handles = nranks entries in rank order, either 64-byte IPC handles (handles_are_pointers = 0)
+ *           or device pointers (void*, handles_are_pointers = 1).  For every neighbour i of this rank
+ *           (sendProcessID order): peer_slot_offset[i] = first slot of this rank's slice in that neighbour's
+ *           receive window (its sendNeighbourCountCum entry for us), peer_my_index[i] = our index in its
+ *           neighbour list, peer_halo_count[i] = its total slot count.  The send lists are symmetric
+ *           (PartitionMesh.cpp:1071-1108), so these come from an all-gather of the comm patterns. */
 #define FTB200_IPC_HANDLE_BYTES 64
-int ftb200_p2p_export(ftb200_ctx *ctx, void *handle_out);
-int ftb200_p2p_import(ftb200_ctx *ctx, const void *all_handles /* nranks * 64 bytes, rank order */);
+int ftb200_p2p_export(ftb200_ctx *ctx, void *handle_out, void **window_out);
+int ftb200_p2p_import(ftb200_ctx *ctx, const void *all_handles, int handles_are_pointers,
+                      const int *peer_slot_offset, const int *peer_my_index, const int *peer_halo_count);
 
 /* ---- measurement helpers --------------------------------------------------- */
 /* Average device time per launch (ms) of the element and node kernels over the last explicit_run*,

@@ -250,11 +250,9 @@ def test_full_size_properties(n):
     m.close()
 
 
-@pytest.mark.parametrize("P,mat", [(2, 1), (4, 1), (8, 1), (4, 5)])
-def test_multirank_split_step_matches_oracle(P, mat):
-    """P partitions driven through the multi-GPU C-ABI sequence (boundary/interior element split, shared-node
-    pack, neighbour sum in ascending neighbour order, cross-rank dt MIN) in one process on one GPU, against
-    the oracle emulating the same P ranks (GetForce_3D.cpp:54-102, StableTimeStep.cpp:33, Mass3D.cpp:77-125)."""
+def _multirank_case(P, mat, p2p):
+    """P partitions driven through the multi-GPU C-ABI sequence in one process on one GPU; returns the
+    relative errors against the oracle emulating the same P ranks."""
     from femtech_b200 import dist as fdist
     from oracle import pyoracle as po
     props = {1: [1040.0, 100.0, 100.0, 0, 0, 0, 0, 0, 0],
@@ -282,20 +280,63 @@ def test_multirank_split_step_matches_oracle(P, mat):
     for m, k in zip(grp.models, kinds):
         m.set_bc(k, rate)
     grp.explicit_begin(energy_every=1)
-    grp.run(tMax, nsteps)
+    if p2p:  # peer-memory transport: pack kernels store into the neighbours' windows, flags, dt through the windows
+        grp.enable_p2p()
+        grp.run_p2p(tMax, nsteps)
+    else:
+        grp.run(tMax, nsteps)
+    out = {"steps": [], "T": [], "dt": [], "mass": [], "u": [], "v": [], "fi": [], "pk2": []}
     for r, (m, o) in enumerate(zip(grp.models, om)):
         m.sync_out()
-        assert m.steps_done == nsteps
-        assert abs(m.Time - o.Time) <= 1e-12 * o.Time and abs(m.dt - o.dt) <= 1e-11 * o.dt
-        assert rel(m.mass, o.mass) < 1e-13
-        assert rel(m.displacements, o.displacements) < TOL, (r, "u")
-        assert rel(m.velocities, o.velocities) < TOL, (r, "v")
-        assert rel(m.fi, o.fi) < 1e-7, (r, "fi")
-        assert rel(m.gp_outputs()["pk2"], o.pk2) < TOL
+        out["steps"].append(int(m.steps_done))
+        out["T"].append(abs(m.Time - o.Time) / o.Time)
+        out["dt"].append(abs(m.dt - o.dt) / o.dt)
+        out["mass"].append(rel(m.mass, o.mass))
+        out["u"].append(rel(m.displacements, o.displacements))
+        out["v"].append(rel(m.velocities, o.velocities))
+        out["fi"].append(rel(m.fi, o.fi))
+        out["pk2"].append(rel(m.gp_outputs()["pk2"], o.pk2))
     e = grp.energy()
-    for got, want in zip(e[:3], [eh[-1][0], eh[-1][1], eh[-1][2]]):
-        assert abs(got - want) <= 1e-9 * max(abs(want), 1e-300) + 1e-22
+    out["energy"] = [abs(got - want) / max(abs(want), 1e-300) for got, want in zip(e[:3], eh[-1][:3])]
     grp.close()
+    return nsteps, out
+
+
+def _check_multirank(nsteps, out):
+    assert all(s == nsteps for s in out["steps"])
+    assert max(out["T"]) <= 1e-12 and max(out["dt"]) <= 1e-11
+    assert max(out["mass"]) < 1e-13
+    assert max(out["u"]) < TOL and max(out["v"]) < TOL and max(out["pk2"]) < TOL
+    assert max(out["fi"]) < 1e-7
+    assert max(out["energy"]) <= 1e-9
+
+
+@pytest.mark.parametrize("P,mat", [(2, 1), (4, 1), (8, 1), (4, 5)])
+def test_multirank_split_step_matches_oracle(P, mat):
+    """Boundary/interior element split, shared-node pack, neighbour sum in ascending neighbour order, cross-rank
+    dt MIN (GetForce_3D.cpp:54-102, StableTimeStep.cpp:33, Mass3D.cpp:77-125) with the transport-agnostic
+    step_begin/join/end sequence."""
+    _check_multirank(*_multirank_case(P, mat, False))
+
+
+@pytest.mark.parametrize("P,mat", [(2, 1), (8, 1), (4, 5)])
+def test_multirank_peer_memory_transport_matches_oracle(P, mat):
+    """Same, with the peer-memory transport (k_p2p_pack stores into the neighbours' windows, flag arrival, dt
+    through the windows; no NCCL, no host in the loop).  Run in a fresh process with enough hardware queues:
+    P ranks x 2 streams share ONE device here and a spinning wait kernel must not alias another rank's stream."""
+    import json
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
+    code = ("import json,sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_parity as t; "
+            "n,o = t._multirank_case(%d, %d, True); print('RESULT ' + json.dumps([n, o]))"
+            % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))), P, mat))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+    assert r.returncode == 0 and line, (r.stdout[-1500:], r.stderr[-1500:])
+    n, o = json.loads(line[-1][7:])
+    _check_multirank(n, o)
 
 
 def _nccl_worker(rank, world, port, q):
@@ -314,7 +355,9 @@ def _nccl_worker(rank, world, port, q):
     kind, rate = mesh.benchmark_bc(part["coordinates"], L=part["box"][1])
     d.m.set_bc(kind, rate)
     d.explicit_begin(energy_every=1)
-    d.run(0.1, 40)
+    d.run(0.1, 20)                 # NCCL send/recv + MIN all-reduce
+    d.enable_p2p(part["comm"])
+    d.run_p2p(0.1, 20)             # peer-memory windows over NVLink (CUDA IPC), no NCCL in the loop
     torch.cuda.synchronize()
     d.m.sync_out()
     d.m._poll()
