@@ -111,8 +111,10 @@ struct SmemScratch {
 };
 
 // K1 (+K6).  MATSEL >= 0: every element of the launch has that material (no switch).
+// material 5 (36 history doubles per Gauss point in flight) and the generic per-element switch need more
+// registers than 168: they run with 4 resident blocks per SM instead of 6
 template <int MATSEL, bool WITH_FORCE, bool WITH_DT>
-__global__ void __launch_bounds__(ELEM_BLOCK, ELEM_MINBLOCKS) k_elem(const ElemArgs A) {
+__global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : ELEM_MINBLOCKS) k_elem(const ElemArgs A) {
   const int e = A.e0 + blockIdx.x * ELEM_BLOCK + threadIdx.x;
   const size_t E = (size_t)A.nE;
   // the connectivity is requested before the loop-control flags are tested: one exposed latency, not two
