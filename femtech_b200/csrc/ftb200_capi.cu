@@ -52,6 +52,15 @@ struct ftb200_ctx {
   PipeCtl* d_ctl = nullptr;
   uint8_t *d_etile_chunk = nullptr, *d_ntile_group = nullptr;
   int* d_ell = nullptr;
+  // fused step kernel
+  StepCtl* d_sctl = nullptr;
+  uint8_t *d_etile32 = nullptr, *d_ntile32 = nullptr;
+  double *d_etile_e = nullptr, *d_eblock = nullptr;
+  int nTilesE32 = 0, nTilesN32 = 0, fused_grid = 0;
+  bool fused = false;  // opt-in (FTB200_FUSED=1): measured slower than the two-kernel step, DESIGN.md §3.6
+  cudaEvent_t ev_step = nullptr, ev_energy[2] = {nullptr, nullptr};
+  cudaGraphExec_t fgraph = nullptr;
+  int fgraph_energy = -1;
   double* d_etile = nullptr;
   int nTilesE = 0, nTilesN = 0, nChunks = 0;
   int elem_grid = 0, node_grid = 0;
@@ -298,7 +307,8 @@ void free_all(ftb200_ctx* c) {
   dfree(c->p2p_window); dfree(c->d_seq); dfree(c->d_p2p_blocks);
   c->p2p_ready = false;
   if (c->p2p_graph) { cudaGraphExecDestroy(c->p2p_graph); c->p2p_graph = nullptr; }
-  dfree(c->d_nref); dfree(c->d_nint); dfree(c->d_ctl); dfree(c->d_etile_chunk); dfree(c->d_ntile_group); dfree(c->d_etile); dfree(c->d_ell);
+  dfree(c->d_nref); dfree(c->d_nint); dfree(c->d_ctl); dfree(c->d_etile_chunk); dfree(c->d_ntile_group); dfree(c->d_etile); dfree(c->d_ell); dfree(c->d_sctl); dfree(c->d_etile32); dfree(c->d_ntile32); dfree(c->d_etile_e); dfree(c->d_eblock);
+  if (c->fgraph) { cudaGraphExecDestroy(c->fgraph); c->fgraph = nullptr; }
   if (c->pgraph) { cudaGraphExecDestroy(c->pgraph); c->pgraph = nullptr; }
   dfree(c->d_sendNodeIndex); dfree(c->halo_nodes); dfree(c->halo_off); dfree(c->halo_slot); dfree(c->halo_node_idx);
   if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
@@ -331,7 +341,10 @@ int ftb200_create(int rank, int nranks, int device, ftb200_ctx** out) {
       cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_elem[0], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_elem[1], cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&ctx->ev_elem[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_step, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_energy[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_energy[1], cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return FTB200_ERR_CUDA;
   }
@@ -349,8 +362,11 @@ int ftb200_destroy(ftb200_ctx* ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 2; ++i) {
     if (ctx->ev_elem[i]) cudaEventDestroy(ctx->ev_elem[i]);
+    if (ctx->ev_energy[i]) cudaEventDestroy(ctx->ev_energy[i]);
+  }
+  if (ctx->ev_step) cudaEventDestroy(ctx->ev_step);
   delete ctx;
   return FTB200_OK;
 }
@@ -603,6 +619,23 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
     h.stop_step = 0;
     CK(cudaMemcpy(ctx->d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice));
   }
+  {  // fused step kernel: warp-granular (32) tiles over the same chunks / groups
+    const int nTE = cdiv(nE, 32), nTN = nNp / 32;
+    ctx->nTilesE32 = nTE; ctx->nTilesN32 = nTN;
+    std::vector<uint8_t> e32(nTE), n32(nTN);
+    StepCtl h;
+    memset(&h, 0, sizeof(h));
+    for (int t = 0; t < nTE; ++t) { e32[t] = etile_chunk[(t * 32) / ELEM_BLOCK]; h.elem_target[e32[t]]++; }
+    for (int t = 0; t < nTN; ++t) n32[t] = ntile_group[(t * 32) / NODE_TILE];
+    h.C = C; h.nTilesE = nTE; h.nTilesN = nTN;
+    if ((rc = dalloc(ctx, &ctx->d_sctl, 1)) || (rc = dalloc(ctx, &ctx->d_etile32, nTE)) || (rc = dalloc(ctx, &ctx->d_ntile32, nTN)) ||
+        (rc = dalloc(ctx, &ctx->d_etile_e, 2 * 3 * (size_t)nTN)) || (rc = dalloc(ctx, &ctx->d_eblock, 3 * ENERGY_BLOCKS)))
+      return rc;
+    CK(cudaMemcpy(ctx->d_sctl, &h, sizeof(h), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_etile32, e32.data(), nTE, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_ntile32, n32.data(), nTN, cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->d_etile_e, 0, 2 * 3 * (size_t)nTN * sizeof(double)));
+  }
   if (ctx->has_visco) {  // Hn_1, Hn_2, S0n zero at t = 0 (ShapeFunctions.cpp:245-252)
     const size_t n = (size_t)3 * 6 * 8 * nE;
     if ((rc = dalloc(ctx, &ctx->hist, n))) return rc;
@@ -671,6 +704,13 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
     ctx->pipe = false;
     if (const char* ev = getenv("FTB200_PIPE")) ctx->pipe = eb >= 1 && atoi(ev) != 0;
     ctx->elem_grid = std::max(1, std::min(prop.multiProcessorCount * std::max(eb, 1), nTilesE));
+    {
+      int fb = (ctx->uniform_mat == 5 || ctx->uniform_mat < 0) ? 4 : 6;  // resident 64-thread blocks of k_step per SM
+      if (const char* ev = getenv("FTB200_FUSED_BLOCKS_PER_SM")) fb = std::max(1, atoi(ev));
+      ctx->fused_grid = std::max(1, std::min(prop.multiProcessorCount * fb, cdiv(nE, ELEM_BLOCK)));
+      ctx->fused = false;
+      if (const char* ev = getenv("FTB200_FUSED")) ctx->fused = atoi(ev) != 0;
+    }
     ctx->node_grid = std::max(1, std::min(prop.multiProcessorCount * nb, nTilesN));
   }
   // ---- validate the reference configuration: detJ0 > 0 at every Gauss point --------------------
@@ -930,6 +970,7 @@ int ftb200_explicit_begin_dt(ftb200_ctx* ctx, double Time0, double reduction, do
   ctx->halo_recv_cur = nullptr;
   if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
   if (ctx->pgraph) { cudaGraphExecDestroy(ctx->pgraph); ctx->pgraph = nullptr; }
+  if (ctx->fgraph) { cudaGraphExecDestroy(ctx->fgraph); ctx->fgraph = nullptr; }
   // scalars: keep bc_rate / hist_cap, reset the rest
   DevScalars h;
   CK(cudaMemcpy(&h, ctx->sc, sizeof(h), cudaMemcpyDeviceToHost));
@@ -984,6 +1025,7 @@ int ftb200_explicit_begin_finish(ftb200_ctx* ctx, const double* recv_dev) {
     CK(cudaMemcpyAsync(&ctx->d_ctl->elem_step, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(&ctx->d_ctl->node_step, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(&ctx->d_ctl->stop_step, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(&ctx->d_sctl->energy_step, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
   }
   int status = 0;
   CK(cudaMemcpyAsync(&status, &ctx->sc->status, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1087,6 +1129,74 @@ static int run_async_p2p(ftb200_ctx* ctx, double tMax, long long steps) {
   return FTB200_OK;
 }
 
+// ---- fused step: one k_step launch per time step on the main stream; the energy reduction of step n runs on
+//      the second stream concurrently with step n+1 (its partial buffer is reused by step n+2)
+static void launch_fused_steps(ftb200_ctx* ctx, int nsteps) {
+  cudaStream_t s1 = ctx->stream, s2 = ctx->stream2;
+  StepArgs P;
+  P.E = elem_args(ctx, 0, ctx->nE, 0);
+  P.N = node_args(ctx, nullptr);
+  P.ell = ctx->d_ell; P.etile_chunk = ctx->d_etile32; P.ntile_group = ctx->d_ntile32; P.ctl = ctx->d_sctl;
+  P.etile = ctx->d_etile_e; P.dt_hist = ctx->dthist; P.nPID = ctx->nPID; P.energy = ctx->energy;
+  for (int i = 0; i < nsteps; ++i) {
+    size_t i0 = 0, i1 = 0;
+    if (ctx->energy && i >= 2) cudaStreamWaitEvent(s1, ctx->ev_energy[i & 1], 0);  // buffer (i & 1) was read by step i-2's reduction
+    if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s1);
+    switch (ctx->uniform_mat) {
+      case 1: LAUNCH((k_step<1>), ctx->fused_grid, ELEM_BLOCK, s1, P); break;
+      case 4: LAUNCH((k_step<4>), ctx->fused_grid, ELEM_BLOCK, s1, P); break;
+      case 5: LAUNCH((k_step<5>), ctx->fused_grid, ELEM_BLOCK, s1, P); break;
+      default: LAUNCH((k_step<-1>), ctx->fused_grid, ELEM_BLOCK, s1, P); break;
+    }
+    if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s1); ctx->prof.elem.push_back({i0, i1}); }
+    if (ctx->energy) {
+      cudaEventRecord(ctx->ev_step, s1);
+      cudaStreamWaitEvent(s2, ctx->ev_step, 0);
+      LAUNCH(k_energy_tiles, ENERGY_BLOCKS, 256, s2, ctx->sc, ctx->d_sctl, ctx->d_etile_e, ctx->d_eblock, ctx->ehist);
+      cudaEventRecord(ctx->ev_energy[i & 1], s2);
+    }
+  }
+  if (ctx->energy) {  // join: everything of this batch is complete when the main stream continues
+    cudaStreamWaitEvent(s1, ctx->ev_energy[(nsteps - 1) & 1], 0);
+    if (nsteps >= 2) cudaStreamWaitEvent(s1, ctx->ev_energy[(nsteps - 2) & 1], 0);
+  }
+}
+
+static int run_async_fused(ftb200_ctx* ctx, double tMax, long long steps) {
+  cudaStream_t s = ctx->stream;
+  LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
+  const bool use_graph = !ctx->profile && steps >= GRAPH_STEPS;
+  if (use_graph && !(ctx->fgraph && ctx->fgraph_energy == ctx->energy)) {
+    if (ctx->fgraph) { cudaGraphExecDestroy(ctx->fgraph); ctx->fgraph = nullptr; }
+    cudaGraph_t g = nullptr;
+    const long long before = ctx->launches;
+    CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    launch_fused_steps(ctx, GRAPH_STEPS);
+    cudaError_t e = cudaStreamEndCapture(s, &g);
+    ctx->launches = before;
+    if (e != cudaSuccess) return fail(ctx, FTB200_ERR_CUDA, "fused graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&ctx->fgraph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { ctx->fgraph = nullptr; return fail(ctx, FTB200_ERR_CUDA, "fused graph instantiate failed: %s", cudaGetErrorString(e)); }
+    ctx->fgraph_energy = ctx->energy;
+  }
+  long long left = steps;
+  const int per_step = 1 + (ctx->energy ? 1 : 0);
+  while (left > 0) {
+    if (use_graph && left >= GRAPH_STEPS) {
+      CK(cudaGraphLaunch(ctx->fgraph, s));
+      ctx->launches += (long long)per_step * GRAPH_STEPS;
+      left -= GRAPH_STEPS;
+    } else {
+      const int n = (int)std::min<long long>(left, GRAPH_STEPS);
+      launch_fused_steps(ctx, n);
+      left -= n;
+    }
+  }
+  CK(cudaGetLastError());
+  return FTB200_OK;
+}
+
 static int build_pipe_graph(ftb200_ctx* ctx) {
   if (ctx->pgraph && ctx->pgraph_energy == ctx->energy) return 0;
   if (ctx->pgraph) { cudaGraphExecDestroy(ctx->pgraph); ctx->pgraph = nullptr; }
@@ -1140,6 +1250,7 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
   }
   if (steps <= 0) return FTB200_OK;
   if (ctx->pipe) return run_async_pipe(ctx, tMax, steps);
+  if (ctx->fused) return run_async_fused(ctx, tMax, steps);
   cudaStream_t s = ctx->stream;
   LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
   {

@@ -1348,6 +1348,295 @@ __global__ void k_pipe_begin(DevScalars* sc, PipeCtl* ctl, double tMax, long lon
   ctl->scal[p] = S;
 }
 
+// =============================================================================================
+// Fused step kernel (single GPU, resident loop): ONE launch per time step.  Every warp is an independent
+// worker that alternates between
+//   * an ELEMENT tile (32 elements, fp64 bound): gathers X,u,v,a,flags, does the first kick + drift + BC of
+//     the step on the fly, element forces -> felem, element dt, and
+//   * a NODE tile (32 nodes, HBM bound) whose dependency group is complete: drift (bitwise identical),
+//     CSR/ELL gather of f_int, a = f/m, second kick, energy partials, writes u, v, a.
+// While a warp waits on the memory of its node tile, the other warps of the SM keep the fp64 pipe busy, so the
+// HBM-bound node work is hidden under the fp64-bound element work without a second kernel.  Node group g
+// (nodes whose elements all lie in element chunks <= g) becomes ready when chunk g is complete; completion
+// is published per warp with __threadfence + atomicAdd, readiness is a prefix counter.  No warp ever waits
+// while element tiles remain, all tickets are dynamic, and the step's previous state is complete at launch,
+// so there is no cross-launch dependency and no co-residency requirement.  The warp that finishes last
+// performs the scalar update of the time loop; the energy partials (one per node tile, fixed order) are
+// reduced by k_energy_tiles on a second stream, off the critical path.
+constexpr int STEP_MAXC = 64;
+struct StepCtl {
+  unsigned elem_ticket, node_ticket;
+  unsigned elem_prefix;
+  unsigned warps_done;
+  unsigned elem_done[STEP_MAXC];
+  unsigned elem_target[STEP_MAXC];  // 32-element tiles per chunk
+  int C, nTilesE, nTilesN;
+  unsigned energy_blocks_done;
+  int pad;
+  long long energy_step;           // steps whose energy partials have been reduced (k_energy_tiles only)
+};
+struct StepArgs {
+  ElemArgs E;
+  NodeArgs N;
+  const int* ell;
+  const uint8_t* etile_chunk;  // 32-element tile -> chunk
+  const uint8_t* ntile_group;  // 32-node tile -> group
+  StepCtl* ctl;
+  double* etile;               // [2][3][nTilesN] energy partials, double buffered by step parity
+  double* dt_hist;
+  int nPID, energy;
+};
+
+template <int MATSEL>
+__global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : ELEM_MINBLOCKS) k_step(const StepArgs P) {
+  const ElemArgs& A = P.E;
+  const NodeArgs& Nd = P.N;
+  StepCtl* ctl = P.ctl;
+  DevScalars* sc = A.sc;
+  const int lane = threadIdx.x & 31;
+  if (sc->last | sc->done) {  // dead iteration of a graph replay
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      if (!sc->done && sc->last) sc->done = 1;
+      sc->active = 0;
+    }
+    return;
+  }
+  // times of THIS step (left by the previous launch / explicit_begin)
+  const double t_n = sc->nt_n, t_np1 = sc->nt_np1, t_half = sc->nt_half, dt = sc->ndt;
+  const double dt1 = t_half - t_n, dt2 = t_np1 - t_half;
+  const int parity = (int)(sc->step & 1);
+  __shared__ double sm_cols[72][ELEM_BLOCK];
+  const size_t E = (size_t)A.nE;
+  const int nTilesE = ctl->nTilesE, nTilesN = ctl->nTilesN;
+  int status = 0;
+  unsigned long long bmin = 0x7FF0000000000000ULL;
+  unsigned et = 0;
+  if (lane == 0) et = atomicAdd(&ctl->elem_ticket, 1u);
+  et = __shfl_sync(0xffffffffu, et, 0);
+  // every warp holds ONE claimed node tile (plain atomicAdd ticket: no compare-and-swap storm) and runs it as soon as
+  // its dependency group is complete; holders keep taking element tiles meanwhile, so the wait never blocks progress
+  unsigned nt = 0;
+  if (lane == 0) nt = atomicAdd(&ctl->node_ticket, 1u);
+  nt = __shfl_sync(0xffffffffu, nt, 0);
+  bool nodes_left = nt < (unsigned)nTilesN;
+  unsigned long long t_wait0 = 0;
+  for (;;) {
+    const bool have_elem = et < (unsigned)nTilesE;
+    if (have_elem) {
+      unsigned et_next = 0;
+      if (lane == 0) et_next = atomicAdd(&ctl->elem_ticket, 1u);  // next ticket: latency hidden by this tile
+      const int c = P.etile_chunk[et];
+      const int e = (int)(et * 32 + lane);
+      double dte = 1e300;
+      if (e < A.nE) {
+        int nd[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nd[k] = __ldg(A.conn + (size_t)k * E + e);
+        double X[8][3], U[8][3];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const unsigned fl = Nd.flags[nd[k]];
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) {
+            X[k][cc] = __ldg(A.X[cc] + nd[k]);
+            U[k][cc] = pipe_drift(Nd.u[cc][nd[k]], Nd.v[cc][nd[k]], Nd.a[cc][nd[k]], (fl >> cc) & 1u, (fl >> (4 + 2 * cc)) & 3u,
+                                  dt1, dt, t_np1, sc->bc_rate);
+          }
+        }
+        const int pp = __ldg(A.pid + e);
+        const double* mp = A.mp + (size_t)pp * FTB_MP_STRIDE;
+        const int mat = (MATSEL >= 0) ? MATSEL : (int)mp[MP_MATID];
+        double fe[8][3];
+        DevHist h{A.hist, E, (size_t)e};
+        SmemScratch Sc{&sm_cols[0][threadIdx.x]};
+        double d;
+        status |= hex8_element<MATSEL, true>(X, U, mat, mp, true, h, NoOutput(), Sc, fe, &d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) __stcg(A.felem + (size_t)(3 * k + cc) * E + e, fe[k][cc]);
+        dte = __ldg(A.eflag + e) ? 1e300 : d;  // element skipped, StableTimeStep.cpp:13-19
+      }
+      const unsigned long long b = dt_to_bits(dte);
+      bmin = b < bmin ? b : bmin;
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        const unsigned old = atomicAdd(&ctl->elem_done[c], 1u);
+        if (old + 1 == ctl->elem_target[c]) pipe_advance(&ctl->elem_prefix, ctl->elem_done, ctl->elem_target, ctl->C);
+      }
+      et = __shfl_sync(0xffffffffu, et_next, 0);
+    }
+    // ---- node tiles whose group is complete: one per element tile while elements remain, drain afterwards
+    bool did_node = false;
+    if (nodes_left) {
+      const unsigned cand = nt;
+      int state = 0;  // 0 not ready yet, 1 ready
+      if (lane == 0) state = ((unsigned)P.ntile_group[cand] < *(volatile unsigned*)&ctl->elem_prefix) ? 1 : 0;
+      state = __shfl_sync(0xffffffffu, state, 0);
+      if (state == 1) {
+        did_node = true;
+        __threadfence();  // acquire: the element forces of the group are visible
+        const int n = (int)(cand * 32 + lane);
+        const unsigned fl = Nd.flags[n];
+        double uu[3], vv[3], aa[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { uu[c] = Nd.u[c][n]; vv[c] = Nd.v[c][n]; aa[c] = Nd.a[c][n]; }
+        const double mass = Nd.m[n];
+        int ent[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ent[q] = __ldg(P.ell + (size_t)q * Nd.nN + n);
+        double fv[8][3];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const size_t e = (size_t)((ent[q] < 0 ? 0 : ent[q]) >> 3);
+          const int sl = (ent[q] < 0 ? 0 : ent[q]) & 7;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) fv[q][c] = (ent[q] >= 0) ? __ldcg(A.felem + (size_t)(3 * sl + c) * E + e) : 0.0;
+        }
+        double f[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < 8; ++q)  // ascending element id (GetForce_3D.cpp:15,39-44); + 0.0 for a missing entry is exact
+#pragma unroll
+          for (int c = 0; c < 3; ++c) f[c] += fv[q][c];
+        if (fl & FTB_FLAG_OVERFLOW)
+          for (int j = Nd.node_off[n] + 8, j1 = Nd.node_off[n + 1]; j < j1; ++j) {
+            const int en = __ldg(Nd.node_ent + j);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) f[c] += __ldcg(A.felem + (size_t)(3 * (en & 7) + c) * E + (size_t)(en >> 3));
+          }
+        double wke = 0.0, wint = 0.0, wext = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const bool bnd = (fl >> c) & 1u;
+          const unsigned kind = (fl >> (4 + 2 * c)) & 3u;
+          const double u_old = uu[c], a_old = kind ? 0.0 : aa[c];
+          const double un = pipe_drift(u_old, vv[c], aa[c], bnd, kind, dt1, dt, t_np1, sc->bc_rate);
+          double vn = vv[c], an = aa[c];
+          if (kind) { vn = sc->bc_rate[kind]; an = 0.0; }  // ApplyBoundaryConditions, :184-244
+          const double fext = Nd.fe[c] ? Nd.fe[c][n] : 0.0;
+          const double fnet = fext - f[c];                  // GetForce_3D.cpp:11,49-51
+          if (!bnd) {
+            const double vhalf = __fma_rn(dt1, aa[c], vv[c]);
+            an = fnet / mass;                               // CalculateAcclerations.cpp:7-11
+            vn = vhalf + dt2 * an;                          // :146-151
+          }
+          if (P.energy && !(fl & FTB_FLAG_NOTOWNED)) {      // CheckEnergy.cpp:19-52
+            const double dd = un - u_old;
+            const double fprev = Nd.fi[c][n];
+            wke += mass * vn * vn;
+            if (bnd) wext += dd * (fprev + f[c] + mass * (an + a_old));
+            wint += dd * (fprev + f[c]);
+            wext += dd * (fext + fext);
+          }
+          Nd.u[c][n] = un; Nd.v[c][n] = vn; Nd.a[c][n] = an;
+          if (Nd.store_fi) Nd.fi[c][n] = f[c];
+        }
+        if (P.energy) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            wke += __shfl_down_sync(0xffffffffu, wke, o);
+            wint += __shfl_down_sync(0xffffffffu, wint, o);
+            wext += __shfl_down_sync(0xffffffffu, wext, o);
+          }
+          if (lane == 0) {
+            double* et3 = P.etile + (size_t)parity * 3 * nTilesN;
+            et3[cand] = wke; et3[nTilesN + cand] = wint; et3[2 * nTilesN + cand] = wext;
+          }
+        }
+        if (lane == 0) nt = atomicAdd(&ctl->node_ticket, 1u);
+        nt = __shfl_sync(0xffffffffu, nt, 0);
+        nodes_left = nt < (unsigned)nTilesN;
+      }
+    }
+    if (!have_elem) {
+      if (!nodes_left) break;
+      if (!did_node) {  // drain phase: the remaining groups wait for the last element tiles (bounded)
+        if (t_wait0 == 0) t_wait0 = pipe_now_ns_early();
+        __nanosleep(200);
+        if (pipe_now_ns_early() - t_wait0 > 2000000000ULL) { atomicOr(&sc->status, 32); break; }
+      } else {
+        t_wait0 = 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, bmin, o);
+    bmin = t < bmin ? t : bmin;
+  }
+  int last = 0;
+  if (lane == 0) {
+    atomicMin(&sc->dtmin_bits, bmin);  // min is order independent: deterministic
+    if (status) atomicOr(&sc->status, status);
+    __threadfence();
+    const unsigned total = gridDim.x * (ELEM_BLOCK / 32);
+    last = (atomicAdd(&ctl->warps_done, 1u) == total - 1) ? 1 : 0;
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  // ---- the warp that finishes last: scalar update of the loop (Benchmarking-Parallel.cpp:106-112,168)
+  double ndt = 0.0;
+  if (lane == 0) {
+    __threadfence();
+    ctl->warps_done = 0; ctl->elem_ticket = 0; ctl->node_ticket = 0; ctl->elem_prefix = 0;
+    for (int i = 0; i < ctl->C; ++i) ctl->elem_done[i] = 0;
+    sc->active = 1;
+    ndt = adv_step(sc, P.dt_hist);
+  }
+  ndt = __shfl_sync(0xffffffffu, ndt, 0);
+  prony_update(const_cast<double*>(A.mp), P.nPID, ndt, lane, 32);
+}
+
+// K8 for the fused step: deterministic two-level reduction of the per-node-tile partials (fixed ranges, fixed
+// order), running on a second stream concurrently with the next step
+constexpr int ENERGY_BLOCKS = 32;
+__global__ void __launch_bounds__(256) k_energy_tiles(DevScalars* sc, StepCtl* ctl, const double* etile, double* eblock,
+                                                      double* ehist) {
+  const long long k = *(volatile long long*)&ctl->energy_step;  // launches are serialised on their stream: one step each
+  if (k >= *(volatile long long*)&sc->step) return;             // dead iteration: nothing new to reduce
+  const int nT = ctl->nTilesN;
+  const double* et3 = etile + (size_t)(k & 1) * 3 * nT;
+  __shared__ double sh[3][256];
+  __shared__ int s_last;
+  const int per = (nT + ENERGY_BLOCKS - 1) / ENERGY_BLOCKS;
+  const int lo = blockIdx.x * per, hi = min(nT, lo + per);
+  double s[3] = {0, 0, 0};
+  for (int i = lo + threadIdx.x; i < hi; i += 256) { s[0] += et3[i]; s[1] += et3[nT + i]; s[2] += et3[2 * nT + i]; }
+  sh[0][threadIdx.x] = s[0]; sh[1][threadIdx.x] = s[1]; sh[2][threadIdx.x] = s[2];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; sh[2][threadIdx.x] += sh[2][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    eblock[blockIdx.x] = sh[0][0]; eblock[ENERGY_BLOCKS + blockIdx.x] = sh[1][0]; eblock[2 * ENERGY_BLOCKS + blockIdx.x] = sh[2][0];
+    __threadfence();
+    s_last = (atomicAdd(&ctl->energy_blocks_done, 1u) == ENERGY_BLOCKS - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double t0 = 0, t1 = 0, t2 = 0;
+    for (int b = 0; b < ENERGY_BLOCKS; ++b) {
+      t0 += __ldcg(eblock + b); t1 += __ldcg(eblock + ENERGY_BLOCKS + b); t2 += __ldcg(eblock + 2 * ENERGY_BLOCKS + b);
+    }
+    const double WKE = 0.5 * t0;
+    sc->Wint += 0.5 * t1;
+    sc->Wext += 0.5 * t2;
+    sc->WKE = WKE;
+    sc->Etot = fabs(WKE + sc->Wint - sc->Wext);
+    if (ehist && k >= 0 && k < sc->hist_cap) {
+      ehist[4 * k + 0] = sc->Wint; ehist[4 * k + 1] = sc->Wext; ehist[4 * k + 2] = WKE; ehist[4 * k + 3] = sc->Etot;
+    }
+    ctl->energy_blocks_done = 0;
+    __threadfence();
+    *(volatile long long*)&ctl->energy_step = k + 1;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // roofline denominators
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed) {
