@@ -26,7 +26,7 @@ struct ProfEvents {
 
 struct ftb200_ctx {
   int rank = 0, nranks = 1, device = 0;
-  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr, stream_lo = nullptr;  // main (high priority), helper (high), interior elements (low)
   bool own_stream = true;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   long long launches = 0;
@@ -336,8 +336,9 @@ int ftb200_create(int rank, int nranks, int device, ftb200_ctx** out) {
   ctx->rank = rank; ctx->nranks = nranks; ctx->device = device;
   int prio_lo = 0, prio_hi = 0;
   if (cudaSetDevice(device) != cudaSuccess || cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
       cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&ctx->stream_lo, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_elem[0], cudaEventDisableTiming) != cudaSuccess ||
@@ -360,6 +361,7 @@ int ftb200_destroy(ftb200_ctx* ctx) {
   for (auto e : ctx->prof.pool) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->stream_lo) cudaStreamDestroy(ctx->stream_lo);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   for (int i = 0; i < 2; ++i) {
@@ -385,7 +387,9 @@ int ftb200_set_stream(ftb200_ctx* ctx, void* cuda_stream) {
     ctx->stream = (cudaStream_t)cuda_stream;
     ctx->own_stream = false;
   } else if (!ctx->own_stream) {
-    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    int plo = 0, phi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&plo, &phi));
+    CK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, phi));
     ctx->own_stream = true;
   }
   return FTB200_OK;
@@ -1065,13 +1069,14 @@ static int build_graph(ftb200_ctx* ctx) {
 // ---- peer-memory multi-GPU step: boundary elements -> pack into the neighbours' windows || interior elements ->
 //      dt exchange + arrival waits + scalar update -> node kernel (receive window selected by step parity)
 static void launch_step_p2p(ftb200_ctx* ctx) {
-  cudaStream_t s = ctx->stream, s2 = ctx->stream2;
+  cudaStream_t s = ctx->stream, s2 = ctx->stream_lo;
   const int nEb = ctx->nE_boundary;
+  // elements touching shared nodes first, on the high-priority main stream; the interior fills the machine behind them
   cudaEventRecord(ctx->ev_fork, s);
+  launch_elem<true, true>(ctx, s, 0, nEb, 0);
   cudaStreamWaitEvent(s2, ctx->ev_fork, 0);
   launch_elem<true, true>(ctx, s2, nEb, ctx->nE, 0);
   cudaEventRecord(ctx->ev_join, s2);
-  launch_elem<true, true>(ctx, s, 0, nEb, 0);
   if (ctx->halo_count)
     LAUNCH(k_p2p_pack, cdiv(ctx->halo_count, 128), 128, s, ctx->p2p, ctx->felem, ctx->node_off, ctx->node_ent,
            ctx->d_sendNodeIndex, ctx->sc, ctx->nE);
@@ -1095,7 +1100,7 @@ static int run_async_p2p(ftb200_ctx* ctx, double tMax, long long steps) {
     if (ctx->energy) LAUNCH((k_node<false, true, false, true>), ctx->node_blocks, NODE_BLOCK, s, N);
     else LAUNCH((k_node<false, true, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   }
-  const bool use_graph = !ctx->profile && steps >= GRAPH_STEPS;
+  const bool use_graph = !ctx->profile;  // built on the first run (warm-up), whatever its length
   if (use_graph && !(ctx->p2p_graph && ctx->p2p_graph_energy == ctx->energy)) {
     if (ctx->p2p_graph) { cudaGraphExecDestroy(ctx->p2p_graph); ctx->p2p_graph = nullptr; }
     cudaGraph_t g = nullptr;
@@ -1165,7 +1170,7 @@ static void launch_fused_steps(ftb200_ctx* ctx, int nsteps) {
 static int run_async_fused(ftb200_ctx* ctx, double tMax, long long steps) {
   cudaStream_t s = ctx->stream;
   LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
-  const bool use_graph = !ctx->profile && steps >= GRAPH_STEPS;
+  const bool use_graph = !ctx->profile;  // built on the first run (warm-up), whatever its length
   if (use_graph && !(ctx->fgraph && ctx->fgraph_energy == ctx->energy)) {
     if (ctx->fgraph) { cudaGraphExecDestroy(ctx->fgraph); ctx->fgraph = nullptr; }
     cudaGraph_t g = nullptr;
@@ -1218,7 +1223,7 @@ static int run_async_pipe(ftb200_ctx* ctx, double tMax, long long steps) {
   cudaStream_t s = ctx->stream;
   LAUNCH(k_pipe_begin, 1, 1, s, ctx->sc, ctx->d_ctl, tMax, steps);
   long long left = steps;
-  const bool use_graph = !ctx->profile && steps >= GRAPH_STEPS;
+  const bool use_graph = !ctx->profile;  // built on the first run (warm-up), whatever its length
   if (use_graph) {
     int rc = build_pipe_graph(ctx);
     if (rc) return rc;
@@ -1260,7 +1265,7 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
   }
   const int per_step = 3 + (ctx->energy ? 1 : 0);
   long long left = steps;
-  const bool use_graph = !ctx->profile && steps >= GRAPH_STEPS;
+  const bool use_graph = !ctx->profile;  // built on the first run (warm-up), whatever its length
   if (use_graph) {
     int rc = build_graph(ctx);
     if (rc) return rc;
@@ -1371,15 +1376,15 @@ int ftb200_run_begin(ftb200_ctx* ctx, double tMax, long long steps) {
 int ftb200_step_begin(ftb200_ctx* ctx, double* send_dev, double** dtmin_dev) {
   if (!ctx || !ctx->begun || (ctx->halo_count && !send_dev)) return fail(ctx, FTB200_ERR_INPUT, "step_begin: bad arguments");
   CK(cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream, s2 = ctx->stream2;
+  cudaStream_t s = ctx->stream, s2 = ctx->stream_lo;
   const int nEb = ctx->nE_boundary;
-  // interior elements on the second stream: they only need the state left by the previous node kernel
+  // elements touching a shared node first (main stream), then the partial f_int of the shared nodes into the send
+  // window; the interior elements run on the low-priority stream: they only need the state left by the previous node kernel
   CK(cudaEventRecord(ctx->ev_fork, s));
+  launch_elem<true, true>(ctx, s, 0, nEb, 0);
   CK(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
   launch_elem<true, true>(ctx, s2, nEb, ctx->nE, 0);
   CK(cudaEventRecord(ctx->ev_join, s2));
-  // elements touching a shared node, then the partial f_int of the shared nodes into the send window
-  launch_elem<true, true>(ctx, s, 0, nEb, 0);
   if (ctx->halo_count) {
     // partial sums go to the f_net planes (scratch in the resident path): fi still holds the previous
     // step's total, which the energy check needs as fi_prev

@@ -204,7 +204,7 @@ class DistFemTech:
         self._send = C.c_void_p(self.halo.send.data_ptr())
         self._recv = C.c_void_p(self.halo.recv.data_ptr())
         # kernels and NCCL ops must be ordered on ONE stream: torch's current stream inside these methods
-        self.stream = torch.cuda.Stream(device=device)
+        self.stream = torch.cuda.Stream(device=device, priority=-1)  # boundary elements + exchange ahead of the interior
         self.m.set_stream(self.stream.cuda_stream)
 
     def setup(self):
