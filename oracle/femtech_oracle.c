@@ -717,6 +717,13 @@ int oracle_run_explicit(oracle_state **ranks, int nranks, int *const *bc_kind,
                         double ExplicitTimeStepReduction,
                         double FailureTimeStep, int first_call,
                         double *dt_hist, double *energy_hist) {
+  return oracle_run_explicit_injury(ranks, nranks, bc_kind, bc_rate, tMax, maxSteps, ExplicitTimeStepReduction,
+                                    FailureTimeStep, first_call, dt_hist, energy_hist, NULL);
+}
+
+int oracle_run_explicit_injury(oracle_state **ranks, int nranks, int *const *bc_kind, const double *bc_rate,
+                               double tMax, int maxSteps, double ExplicitTimeStepReduction, double FailureTimeStep,
+                               int first_call, double *dt_hist, double *energy_hist, oracle_injury **inj) {
   double Time = ranks[0]->Time, dt = ranks[0]->dt;
   if (first_call) {
     for (int r = 0; r < nranks; ++r) applyBC(ranks[r], bc_kind[r], bc_rate);
@@ -786,6 +793,7 @@ int oracle_run_explicit(oracle_state **ranks, int nranks, int *const *bc_kind,
             fabs(WKE_Total + ranks[0]->Wint_n - ranks[0]->Wext_n);
       }
     }
+    if (inj) oracle_CalculateInjuryCriterions(ranks, inj, nranks, Time, dt); /* ex5.cpp:240 */
     steps++;
     double dtMin = stable_dt_all(ranks, nranks);
     if (dtMin < FailureTimeStep) {
@@ -819,5 +827,181 @@ void oracle_CalculateStrain(const oracle_state *s, double *Eavg) {
     E[0] -= 0.5;
     E[4] -= 0.5;
     E[8] -= 0.5;
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* injury criteria (examples/ex5/ex5.cpp, src/elements/ElementCalculations/CalculateStrain.cpp, src/math/math.cpp) */
+
+/* CalculateStrain.cpp:8-75 */
+void oracle_CalculateMaximumPrincipalStrain(const oracle_state *s, int elm, double *Eavg_e, double *currentStrainMax,
+                                            double *currentStrainMin, double *currentShearMax) {
+  const double kPi = 4.0 * atan(1.0); /* :6 */
+  double Eloc[9];
+  double *E = Eavg_e ? Eavg_e : Eloc;
+  for (int i = 0; i < 9; ++i) E[i] = 0.0;
+  const int countGP = 8;
+  double preFactor = 0.5 / ((double)countGP);
+  for (int gp = 0; gp < countGP; ++gp) {
+    const double *Fg = &s->F[72 * elm + 9 * gp];
+    for (int j = 0; j < 3; ++j) /* dgemm('T','N'), alpha = preFactor, beta = 1 */
+      for (int i = 0; i < 3; ++i) {
+        double sum = 0.0;
+        for (int l = 0; l < 3; ++l) sum += Fg[l + 3 * i] * Fg[l + 3 * j];
+        E[i + 3 * j] = 1.0 * E[i + 3 * j] + preFactor * sum;
+      }
+  }
+  E[0] -= 0.5;
+  E[4] -= 0.5;
+  E[8] -= 0.5;
+  double a = E[0], b = E[1], c = E[2], d = E[4], e = E[5], f = E[8];
+  double p1 = b * b + c * c + e * e;
+  double eps1, eps2, eps3;
+  if (p1 == 0) {
+    eps1 = a;
+    eps2 = d;
+    eps3 = f;
+  } else {
+    double I1 = a + d + f;
+    double I2 = a * (d + f) + d * f - b * b - c * c - e * e;
+    double I3 = a * d * f + 2.0 * b * c * e - b * b * f - c * c * d - e * e * a;
+    double Q = (3.0 * I2 - I1 * I1) / 9.0;
+    double R = (2.0 * I1 * I1 * I1 - 9.0 * I1 * I2 + 27.0 * I3) / 54.0;
+    double theta = acos(R / sqrt(-Q * Q * Q));
+    double sqrtQ = 2.0 * sqrt(-Q);
+    I1 = I1 / 3.0;
+    eps1 = sqrtQ * cos(theta / 3.0) + I1;
+    eps2 = sqrtQ * cos((theta + 2.0 * kPi) / 3.0) + I1;
+    eps3 = sqrtQ * cos((theta + 4.0 * kPi) / 3.0) + I1;
+  }
+  double min, max;
+  max = fmax(eps3, fmax(eps2, eps1));
+  min = fmin(eps3, fmin(eps2, eps1));
+  *currentShearMax = 0.5 * (max - min);
+  if (max > 0.0) *currentStrainMax = max; else *currentStrainMax = 0.0;
+  if (min < 0.0) *currentStrainMin = min; else *currentStrainMin = 0.0;
+}
+
+/* ex5.cpp:1251-1306 */
+void oracle_InitInjuryCriterion(const oracle_state *s, oracle_injury *inj, const int *injuryExcludePID,
+                                int injuryExcludePIDCount) {
+  int count = 0;
+  for (int i = 0; i < s->nElements; i++) {
+    int include = 1;
+    int elementPID = s->pid[i];
+    for (int j = 0; j < injuryExcludePIDCount; ++j)
+      if (elementPID == injuryExcludePID[j]) { include = 0; break; }
+    if (include) {
+      inj->elementIDInjury[count] = i;
+      count += 1;
+    }
+  }
+  inj->nElementsInjury = count;
+  for (int j = 0; j < count; ++j) {
+    inj->MPSgt15[j] = inj->MPSgt30[j] = inj->MPSRgt120[j] = inj->MPSxSRgt28[j] = 0;
+    inj->PS_Old[j] = 0.0;
+    inj->PSxSRArray[j] = 0.0;
+  }
+  inj->maxStrain = inj->minStrain = inj->maxShear = inj->maxPSxSR = 0.0; /* ex5.cpp:62,73 */
+  inj->maxElem = inj->minElem = inj->shearElem = inj->maxElemPSxSR = 0;  /* :63,74 */
+  inj->maxT = inj->minT = inj->maxShearT = inj->maxTimePSxSR = 0.0;
+  inj->maxMPS95 = inj->maxTimeMPS95 = inj->maxMPSxSR95 = inj->maxTimeMPSxSR95 = 0.0;
+  inj->maxElemCountMPS95 = inj->maxElemCountMPSxSR95 = 0;
+}
+
+static int cmp_double(const void *a, const void *b) {
+  double x = *(const double *)a, y = *(const double *)b;
+  return (x < y) ? -1 : (x > y) ? 1 : 0;
+}
+
+/* math.cpp:160-199: gather, nth_element at (int)(total*0.95)-1 */
+double oracle_compute95thPercentileValue(double *const *data, const int *sizes, int nranks) {
+  int totalSize = 0;
+  for (int r = 0; r < nranks; ++r) totalSize += sizes[r];
+  double *full = (double *)malloc((totalSize > 0 ? totalSize : 1) * sizeof(double));
+  int o = 0;
+  for (int r = 0; r < nranks; ++r) {
+    memcpy(full + o, data[r], sizes[r] * sizeof(double));
+    o += sizes[r];
+  }
+  int index95 = (int)(totalSize * 0.95) - 1; /* the reference faults when this is negative */
+  double v = 0.0;
+  if (index95 >= 0) {
+    qsort(full, totalSize, sizeof(double), cmp_double);
+    v = full[index95];
+  }
+  free(full);
+  return v;
+}
+
+/* ex5.cpp:1311-1430 */
+void oracle_CalculateInjuryCriterions(oracle_state **ranks, oracle_injury **injs, int nranks, double Time, double dt) {
+  for (int r = 0; r < nranks; ++r) {
+    const oracle_state *s = ranks[r];
+    oracle_injury *q = injs[r];
+    double currentStrainMaxElem, currentStrainMinElem, currentShearMaxElem;
+    double PSR = 0.0, PSxSR = 0.0;
+    for (int j = 0; j < q->nElementsInjury; j++) {
+      int i = q->elementIDInjury[j];
+      oracle_CalculateMaximumPrincipalStrain(s, i, NULL, &currentStrainMaxElem, &currentStrainMinElem,
+                                             &currentShearMaxElem);
+      if (q->maxStrain < currentStrainMaxElem) { q->maxStrain = currentStrainMaxElem; q->maxElem = i; q->maxT = Time; }
+      if (q->minStrain > currentStrainMinElem) { q->minStrain = currentStrainMinElem; q->minElem = i; q->minT = Time; }
+      if (q->maxShear < currentShearMaxElem) { q->maxShear = currentShearMaxElem; q->shearElem = i; q->maxShearT = Time; }
+      if (!q->MPSgt15[j]) if (currentStrainMaxElem > 0.15) q->MPSgt15[j] = 1;
+      if (!q->MPSgt30[j]) if (currentStrainMaxElem > 0.30) q->MPSgt30[j] = 1;
+      PSR = (currentStrainMaxElem - q->PS_Old[j]) / dt;
+      PSxSR = currentStrainMaxElem * PSR;
+      if (q->maxPSxSR < PSxSR) { q->maxPSxSR = PSxSR; q->maxElemPSxSR = i; q->maxTimePSxSR = Time; }
+      if (!q->MPSRgt120[j]) if (PSR > 120.0) q->MPSRgt120[j] = 1;
+      if (!q->MPSxSRgt28[j]) if (PSxSR > 28.0) q->MPSxSRgt28[j] = 1;
+      q->PS_Old[j] = currentStrainMaxElem;
+      q->PSxSRArray[j] = PSxSR;
+    }
+  }
+  double **arr = (double **)malloc(nranks * sizeof(double *));
+  int *sz = (int *)malloc(nranks * sizeof(int));
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int r = 0; r < nranks; ++r) {
+      arr[r] = pass ? injs[r]->PSxSRArray : injs[r]->PS_Old;
+      sz[r] = injs[r]->nElementsInjury;
+    }
+    double v95 = oracle_compute95thPercentileValue(arr, sz, nranks);
+    for (int r = 0; r < nranks; ++r) {
+      oracle_injury *q = injs[r];
+      double *mx = pass ? &q->maxMPSxSR95 : &q->maxMPS95;
+      double *mt = pass ? &q->maxTimeMPSxSR95 : &q->maxTimeMPS95;
+      int *list = pass ? q->maxElemListMPSxSR95 : q->maxElemListMPS95;
+      int *cnt = pass ? &q->maxElemCountMPSxSR95 : &q->maxElemCountMPS95;
+      if (v95 > *mx) {
+        *mx = v95;
+        *mt = Time;
+        int count = 0;
+        for (int j = 0; j < q->nElementsInjury; j++)
+          if (arr[r][j] >= *mx) { list[count] = q->elementIDInjury[j]; count = count + 1; }
+        *cnt = count;
+      }
+    }
+  }
+  free(arr);
+  free(sz);
+}
+
+/* ex5.cpp:1043-1066 with Elements.cpp:30-38 / CalculateCentroidAndVolume.cpp:26-37 */
+void oracle_injury_volumes(const oracle_state *s, const oracle_injury *inj, double out[5]) {
+  for (int k = 0; k < 5; ++k) out[k] = 0.0;
+  for (int j = 0; j < inj->nElementsInjury; ++j) {
+    int e = inj->elementIDInjury[j];
+    double coord[24];
+    for (int a = 0; a < 8; ++a)
+      for (int k = 0; k < 3; ++k) coord[3 * a + k] = s->coordinates[3 * s->connectivity[8 * e + a] + k];
+    double eV = oracle_volumeHexahedron(coord);
+    if (inj->MPSgt15[j]) {
+      out[0] += eV;
+      if (inj->MPSgt30[j]) out[1] += eV;
+    }
+    if (inj->MPSRgt120[j]) out[2] += eV;
+    if (inj->MPSxSRgt28[j]) out[3] += eV;
+    out[4] += eV;
   }
 }

@@ -107,6 +107,44 @@ double oracle_areaHexahedronFace(const double *c24, const int *index4);
 double oracle_CalculateTimeStep(const oracle_state *s, int e);
 void oracle_CalculateStrain(const oracle_state *s, double *Eavg /*[9*nE]*/);
 
+/* ---- injury criteria of the brain drivers ---------------------------------
+ * Per-rank state of examples/ex5/ex5.cpp:62-83,1251-1306.  All arrays are caller-owned with capacity
+ * nElements.  PS_Old is zero-initialised here (the reference mallocs it without initialising, ex5.cpp:1285; a
+ * fresh glibc mmap gives zeros). */
+typedef struct oracle_injury {
+  int nElementsInjury;
+  int *elementIDInjury;
+  int *MPSgt15, *MPSgt30, *MPSRgt120, *MPSxSRgt28;
+  double *PS_Old, *PSxSRArray;
+  int *maxElemListMPS95, *maxElemListMPSxSR95;
+  int maxElemCountMPS95, maxElemCountMPSxSR95;
+  double maxStrain, minStrain, maxShear, maxPSxSR;
+  int maxElem, minElem, shearElem, maxElemPSxSR;
+  double maxT, minT, maxShearT, maxTimePSxSR;
+  double maxMPS95, maxTimeMPS95, maxMPSxSR95, maxTimeMPSxSR95;
+} oracle_injury;
+
+/* CalculateStrain.cpp:8-75: E = mean over GP of 0.5 (F^T F - I) (written to Eavg_e[9] when not NULL), closed-form
+ * eigenvalues, max clipped at >= 0, min at <= 0, shear = (max - min)/2 of the unclipped values. */
+void oracle_CalculateMaximumPrincipalStrain(const oracle_state *s, int elm, double *Eavg_e, double *currentStrainMax,
+                                            double *currentStrainMin, double *currentShearMax);
+/* ex5.cpp:1251-1306 */
+void oracle_InitInjuryCriterion(const oracle_state *s, oracle_injury *inj, const int *injuryExcludePID,
+                                int injuryExcludePIDCount);
+/* math.cpp:160-199 (what math.cpp:235-332 always reduces to: its refinement loop never runs since N == totalSize):
+ * element (int)(0.95*total) - 1 of the ascending union of all ranks' arrays. */
+double oracle_compute95thPercentileValue(double *const *data, const int *sizes, int nranks);
+/* ex5.cpp:1311-1430 for P emulated ranks (Time, dt = the driver globals at the call, ex5.cpp:240) */
+void oracle_CalculateInjuryCriterions(oracle_state **ranks, oracle_injury **inj, int nranks, double Time, double dt);
+/* ex5.cpp:1049-1066 + Elements.cpp:30-38: reference-configuration volumes out[0..3] = MPS>15 %, MPS>30 % (within
+ * the >15 % set), MPSR>120, MPSxSR>28, out[4] = volume of all included elements (this rank's share). */
+void oracle_injury_volumes(const oracle_state *s, const oracle_injury *inj, double out[5]);
+/* oracle_run_explicit with CalculateInjuryCriterions after CheckEnergy of every step (ex5.cpp:237-240); inj may
+ * be NULL. */
+int oracle_run_explicit_injury(oracle_state **ranks, int nranks, int *const *bc_kind, const double *bc_rate,
+                               double tMax, int maxSteps, double ExplicitTimeStepReduction, double FailureTimeStep,
+                               int first_call, double *dt_hist, double *energy_hist, oracle_injury **inj);
+
 #ifdef __cplusplus
 }
 #endif

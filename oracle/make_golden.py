@@ -30,15 +30,18 @@ BRAIN = [1000.0, 2673.23, 2.189982178466e8, 25459.0, 0.0, 0.6521, 0.0129, 0.0067
 SOFT = [1040.0, 100.0, 100.0, 0, 0, 0, 0, 0, 0]  # examples/Benchmarking-Parallel/materials.dat:1
 
 
-def run_ref(meshfile, materialID, properties, nranks, maxSteps, tMax, dMax, cubeL=mesh.CUBE_L):
+def run_ref(meshfile, materialID, properties, nranks, maxSteps, tMax, dMax, cubeL=mesh.CUBE_L, injury_exclude=None):
     work = tempfile.mkdtemp(prefix="ftgold_")
+    env = dict(os.environ)
+    if injury_exclude is not None:
+        env["REF_INJURY_EXCLUDE"] = ",".join(str(p) for p in injury_exclude)
     try:
         mesh.write_materials_dat(os.path.join(work, "materials.dat"), materialID, properties)
         cmd = [os.path.join(BIN, "ref_dump_exact"), meshfile, os.path.join(work, "out"), str(maxSteps),
                repr(tMax), repr(dMax), repr(cubeL)]
         if nranks > 1:
             cmd = [os.path.join(BIN, "ftmpirun"), "-np", str(nranks)] + cmd
-        out = subprocess.run(cmd, cwd=work, check=True, capture_output=True, text=True).stdout
+        out = subprocess.run(cmd, cwd=work, check=True, capture_output=True, text=True, env=env).stdout
         dumps = [pyoracle.read_ref_dump(os.path.join(work, "out.rank%d.bin" % r)) for r in range(nranks)]
         energy = None
         for fn in os.listdir(work):
@@ -54,6 +57,9 @@ MESH_KEYS = ["coordinates", "connectivity", "pid", "materialID", "properties"]
 MAP_KEYS = ["global_eid", "globalNodeID", "sendProcessID", "sendNeighbourCountCum", "sendNodeIndex"]
 STATE_KEYS = ["mass", "boundary0", "dt0", "fi0", "accelerations0", "steps", "Time", "dt", "dt_hist", "displacements",
               "velocities", "accelerations", "boundary", "fi", "f_net"]
+INJ_KEYS = ["inj_elems", "inj_gt15", "inj_gt30", "inj_r120", "inj_xsr28", "inj_ps_old", "inj_psxsr", "inj_list95",
+            "inj_listx95", "inj_hist95", "inj_histx95", "inj_scalars", "inj_extreme_elems", "inj_volumes",
+            "inj_volume_part"]
 GP_KEYS = ["detJacobian", "F", "detF", "pk2", "pk2_0", "Eavg", "Hn_1", "Hn_2", "S0n"]
 
 
@@ -72,10 +78,22 @@ def save(name, dumps, energy, params, keys):
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
     os.makedirs(GOLD, exist_ok=True)
     tmp = tempfile.mkdtemp(prefix="ftmesh_")
     ex = os.path.join(REF, "examples")
 
+    if only == "injury":
+        X, conn, pid = mesh.cube_mesh(6, jitter=0.05, nparts_z=3)
+        f6 = os.path.join(tmp, "cube6mix.inp")
+        mesh.write_abaqus_inp(f6, X, conn, pid)
+    else:
+        f6 = group_a_to_d(tmp, ex)
+    group_e(tmp, f6)
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
+def group_a_to_d(tmp, ex):
     # (A) ex9: the reference's only known-answer test (.travis.yml:113-115)
     d, en, _ = run_ref(os.path.join(ex, "ex9", "1-elt-cube.k"), [1], SOFT, 1, 10 ** 9, 1.0, 0.007)
     save("ex9_1elt", d, en[-1:], dict(tMax=1.0, dMax=0.007), MESH_KEYS + STATE_KEYS + GP_KEYS)
@@ -110,7 +128,19 @@ def main():
         d, en, _ = run_ref(f6, [1, 4, 5], mixprops, P, 150, 0.004, 0.007)
         save("cube6mix_p%d" % P, d, en[-1:], dict(tMax=0.004, dMax=0.007),
              MESH_KEYS + MAP_KEYS + STATE_KEYS + (GP_KEYS if P == 1 else []))
-    shutil.rmtree(tmp, ignore_errors=True)
+    return f6
+
+
+def group_e(tmp, f6):
+    # (E) injury criteria of the brain drivers (ex5.cpp:1311-1430) on a large-strain, fast pull: three slabs
+    #     (neo-Hookean, HGO, neo-Hookean), the last part excluded from the criteria; 1 and 3 ranks
+    MED = [1040.0, 2.0e3, 2.0e4, 0, 0, 0, 0, 0, 0]
+    HGO_SOFT = [1000.0, 2.0e3, 2.0e4, 500.0, 10.0, 0, 0, 0, 0]
+    injprops = MED + HGO_SOFT + MED
+    INJ_SAVE = MESH_KEYS + MAP_KEYS + ["steps", "Time", "dt", "dt_hist", "displacements", "velocities"] + INJ_KEYS
+    for name, P, dMax, tMax in (("inj6_p1", 1, 0.0009, 0.005), ("inj6_p3", 3, 0.0009, 0.005), ("inj6b_p1", 1, 0.0012, 0.003)):
+        d, en, _ = run_ref(f6, [1, 4, 1], injprops, P, 400, tMax, dMax, injury_exclude=[2])
+        save(name, d, en[-1:], dict(tMax=tMax, dMax=dMax, exclude=[2]), INJ_SAVE + (["Eavg", "F"] if P == 1 else []))
 
 
 if __name__ == "__main__":

@@ -34,6 +34,22 @@ class OracleState(C.Structure):
     ]
 
 
+class OracleInjury(C.Structure):
+    """Mirror of `oracle_injury` in femtech_oracle.h (same field order)."""
+    _fields_ = [
+        ("nElementsInjury", C.c_int), ("elementIDInjury", _ip),
+        ("MPSgt15", _ip), ("MPSgt30", _ip), ("MPSRgt120", _ip), ("MPSxSRgt28", _ip),
+        ("PS_Old", _dp), ("PSxSRArray", _dp),
+        ("maxElemListMPS95", _ip), ("maxElemListMPSxSR95", _ip),
+        ("maxElemCountMPS95", C.c_int), ("maxElemCountMPSxSR95", C.c_int),
+        ("maxStrain", C.c_double), ("minStrain", C.c_double), ("maxShear", C.c_double), ("maxPSxSR", C.c_double),
+        ("maxElem", C.c_int), ("minElem", C.c_int), ("shearElem", C.c_int), ("maxElemPSxSR", C.c_int),
+        ("maxT", C.c_double), ("minT", C.c_double), ("maxShearT", C.c_double), ("maxTimePSxSR", C.c_double),
+        ("maxMPS95", C.c_double), ("maxTimeMPS95", C.c_double), ("maxMPSxSR95", C.c_double),
+        ("maxTimeMPSxSR95", C.c_double),
+    ]
+
+
 def build(fast=False):
     """Compile the oracle shared library if missing/stale; return its path."""
     name = "libfemtech_oracle_fast.so" if fast else "libfemtech_oracle.so"
@@ -72,6 +88,16 @@ def lib(fast=False):
         L.oracle_CalculateTimeStep.argtypes = [sp, C.c_int]
         L.oracle_CalculateTimeStep.restype = C.c_double
         L.oracle_CalculateStrain.argtypes = [sp, _dp]
+        qp = C.POINTER(OracleInjury)
+        L.oracle_CalculateMaximumPrincipalStrain.argtypes = [sp, C.c_int, _dp, _dp, _dp, _dp]
+        L.oracle_InitInjuryCriterion.argtypes = [sp, qp, _ip, C.c_int]
+        L.oracle_compute95thPercentileValue.argtypes = [C.POINTER(_dp), _ip, C.c_int]
+        L.oracle_compute95thPercentileValue.restype = C.c_double
+        L.oracle_CalculateInjuryCriterions.argtypes = [C.POINTER(sp), C.POINTER(qp), C.c_int, C.c_double, C.c_double]
+        L.oracle_injury_volumes.argtypes = [sp, qp, _dp]
+        L.oracle_run_explicit_injury.argtypes = [C.POINTER(sp), C.c_int, C.POINTER(_ip), _dp, C.c_double, C.c_int,
+                                                 C.c_double, C.c_double, C.c_int, _dp, _dp, C.POINTER(qp)]
+        L.oracle_run_explicit_injury.restype = C.c_int
         _libs[fast] = L
     return _libs[fast]
 
@@ -174,6 +200,73 @@ class OracleModel:
         return self.s.dt
 
 
+class InjuryCriteria:
+    """ex5.cpp:62-83,1251-1306 state of one rank, arrays owned here."""
+
+    def __init__(self, model, exclude_pids=()):
+        n = model.nElements
+        self.model = model
+        self.q = OracleInjury()
+        self.arrays = {}
+        for name in ("elementIDInjury", "MPSgt15", "MPSgt30", "MPSRgt120", "MPSxSRgt28", "maxElemListMPS95",
+                     "maxElemListMPSxSR95"):
+            self.arrays[name] = np.zeros(max(n, 1), dtype=np.int32)
+            setattr(self.q, name, _i(self.arrays[name]))
+        for name in ("PS_Old", "PSxSRArray"):
+            self.arrays[name] = np.zeros(max(n, 1))
+            setattr(self.q, name, _d(self.arrays[name]))
+        ex = np.ascontiguousarray(exclude_pids, dtype=np.int32)
+        model.L.oracle_InitInjuryCriterion(C.byref(model.s), C.byref(self.q), _i(ex), len(ex))
+
+    @property
+    def n(self):
+        return self.q.nElementsInjury
+
+    def get(self, name):
+        return self.arrays[name][:self.n]
+
+    def principal(self, e):
+        out = np.zeros(3)
+        E = np.zeros(9)
+        self.model.L.oracle_CalculateMaximumPrincipalStrain(C.byref(self.model.s), int(e), _d(E), _d(out[0:1]),
+                                                            _d(out[1:2]), _d(out[2:3]))
+        return out, E
+
+    def volumes(self):
+        out = np.zeros(5)
+        self.model.L.oracle_injury_volumes(C.byref(self.model.s), C.byref(self.q), _d(out))
+        return out
+
+    def lists(self):
+        return (self.arrays["maxElemListMPS95"][:self.q.maxElemCountMPS95].copy(),
+                self.arrays["maxElemListMPSxSR95"][:self.q.maxElemCountMPSxSR95].copy())
+
+    def scalars(self):
+        q = self.q
+        return np.array([q.maxStrain, q.maxT, q.minStrain, q.minT, q.maxShear, q.maxShearT, q.maxPSxSR, q.maxTimePSxSR,
+                         q.maxMPS95, q.maxTimeMPS95, q.maxMPSxSR95, q.maxTimeMPSxSR95])
+
+    def extreme_elems(self):
+        q = self.q
+        return np.array([q.maxElem, q.minElem, q.shearElem, q.maxElemPSxSR], dtype=np.int32)
+
+
+def percentile95(arrays):
+    """math.cpp:160-199 over the union of the per-rank arrays."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in arrays]
+    ptrs = (_dp * len(arrs))(*[_d(a) for a in arrs])
+    sizes = np.array([len(a) for a in arrs], dtype=np.int32)
+    return lib().oracle_compute95thPercentileValue(ptrs, _i(sizes), len(arrs))
+
+
+def injury_step(models, injuries, Time, dt):
+    P = len(models)
+    sp, qp = C.POINTER(OracleState), C.POINTER(OracleInjury)
+    arr = (sp * P)(*[C.pointer(m.s) for m in models])
+    qarr = (qp * P)(*[C.pointer(i.q) for i in injuries])
+    models[0].L.oracle_CalculateInjuryCriterions(arr, qarr, P, Time, dt)
+
+
 def halo_sum(models, field):
     """field: 'fi' or 'mass' (GetForce_3D.cpp:54-102 / Mass3D.cpp:77-125)."""
     sp = C.POINTER(OracleState)
@@ -182,7 +275,7 @@ def halo_sum(models, field):
 
 
 def run_explicit(models, bc_kinds, bc_rate, tMax, maxSteps, reduction=0.8, failure_dt=1e-11, first_call=True,
-                 record=True):
+                 record=True, injuries=None):
     """Benchmarking-Parallel.cpp:83-171 on P emulated ranks.  Returns
     (steps_or_negative_code, dt_hist, energy_hist[steps,4])."""
     P = len(models)
@@ -193,9 +286,13 @@ def run_explicit(models, bc_kinds, bc_rate, tMax, maxSteps, reduction=0.8, failu
     rate = np.ascontiguousarray(bc_rate, dtype=np.float64)
     dth = np.zeros(max(maxSteps, 1)) if record else None
     eh = np.zeros(4 * max(maxSteps, 1)) if record else None
-    n = models[0].L.oracle_run_explicit(arr, P, karr, _d(rate), tMax, maxSteps, reduction, failure_dt,
-                                        1 if first_call else 0, _d(dth) if record else None,
-                                        _d(eh) if record else None)
+    qarr = None
+    if injuries is not None:
+        qp = C.POINTER(OracleInjury)
+        qarr = (qp * P)(*[C.pointer(i.q) for i in injuries])
+    n = models[0].L.oracle_run_explicit_injury(arr, P, karr, _d(rate), tMax, maxSteps, reduction, failure_dt,
+                                               1 if first_call else 0, _d(dth) if record else None,
+                                               _d(eh) if record else None, qarr)
     if record and n >= 0:
         return n, dth[:n].copy(), eh[:4 * n].reshape(n, 4).copy()
     return n, None, None

@@ -11,6 +11,11 @@
  * condition below restate the driver (:83-171, :184-244); all numerics are the
  * reference library's.
  *
+ * With REF_INJURY_EXCLUDE set in the environment ("" or a comma-separated pid list) the loop also evaluates the
+ * brain drivers' injury criteria after CheckEnergy of every step, in the call order of examples/ex5/ex5.cpp:237-240:
+ * the driver-side bookkeeping (ex5.cpp:1251-1430, not part of the library) is restated below around the
+ * reference library's own CalculateMaximumPrincipalStrain, compute95thPercentileValue and computePartVolume.
+ *
  * usage: ref_dump <mesh.inp|.k> <out-prefix> <maxSteps> <tMax> <dMax> [cubeL] [warmupSteps] [nodump]
  *        (materials.dat is read from the current directory, ReadMaterials.cpp:11)
  *        warmupSteps: loop iterations excluded from the reported loop time (bench.py);
@@ -50,6 +55,101 @@ static void putd(const char *name, const double *p, int64_t n) { put(name, "f8",
 static void puti(const char *name, const int *p, int64_t n) { put(name, "i4", p, p ? n : 0, 4); }
 static void puts1(const char *name, double v) { putd(name, &v, 1); }
 static void puti1(const char *name, int v) { puti(name, &v, 1); }
+
+/* ---- injury criteria bookkeeping of ex5.cpp:62-83,1251-1430 (driver code in the reference, restated) ---- */
+struct Injury {
+  bool on = false;
+  std::vector<int> excl, elems, gt15, gt30, r120, xsr28, list95, listx95;
+  std::vector<double> psOld, psxsr, hist95, histx95;
+  double maxStrain = 0, minStrain = 0, maxShear = 0, maxPSxSR = 0, maxT = 0, minT = 0, maxShearT = 0, maxTimePSxSR = 0;
+  int maxElem = 0, minElem = 0, shearElem = 0, maxElemPSxSR = 0;
+  double max95 = 0, t95 = 0, maxx95 = 0, tx95 = 0;
+} g_inj;
+
+static void InjuryInit(const char *spec) {
+  g_inj.on = true;
+  for (const char *p = spec; *p;) {
+    char *end;
+    long v = strtol(p, &end, 10);
+    if (end == p) break;
+    g_inj.excl.push_back((int)v);
+    p = (*end == ',') ? end + 1 : end;
+  }
+  for (int i = 0; i < nelements; ++i) {
+    bool include = true;
+    for (size_t j = 0; j < g_inj.excl.size(); ++j)
+      if (pid[i] == g_inj.excl[j]) include = false;
+    if (include) g_inj.elems.push_back(i);
+  }
+  const size_t n = g_inj.elems.size();
+  g_inj.gt15.assign(n, 0); g_inj.gt30.assign(n, 0); g_inj.r120.assign(n, 0); g_inj.xsr28.assign(n, 0);
+  g_inj.psOld.assign(n, 0.0); g_inj.psxsr.assign(n, 0.0);
+}
+
+static void InjuryStep() {
+  const int n = (int)g_inj.elems.size();
+  for (int j = 0; j < n; ++j) {
+    const int i = g_inj.elems[j];
+    double smax, smin, shear;
+    CalculateMaximumPrincipalStrain(i, &smax, &smin, &shear); /* the reference's own */
+    if (g_inj.maxStrain < smax) { g_inj.maxStrain = smax; g_inj.maxElem = i; g_inj.maxT = Time; }
+    if (g_inj.minStrain > smin) { g_inj.minStrain = smin; g_inj.minElem = i; g_inj.minT = Time; }
+    if (g_inj.maxShear < shear) { g_inj.maxShear = shear; g_inj.shearElem = i; g_inj.maxShearT = Time; }
+    if (!g_inj.gt15[j] && smax > 0.15) g_inj.gt15[j] = 1;
+    if (!g_inj.gt30[j] && smax > 0.30) g_inj.gt30[j] = 1;
+    const double PSR = (smax - g_inj.psOld[j]) / dt;
+    const double PSxSR = smax * PSR;
+    if (g_inj.maxPSxSR < PSxSR) { g_inj.maxPSxSR = PSxSR; g_inj.maxElemPSxSR = i; g_inj.maxTimePSxSR = Time; }
+    if (!g_inj.r120[j] && PSR > 120.0) g_inj.r120[j] = 1;
+    if (!g_inj.xsr28[j] && PSxSR > 28.0) g_inj.xsr28[j] = 1;
+    g_inj.psOld[j] = smax;
+    g_inj.psxsr[j] = PSxSR;
+  }
+  const double v95 = compute95thPercentileValue(g_inj.psOld.data(), n); /* the reference's own (collective) */
+  g_inj.hist95.push_back(v95);
+  if (v95 > g_inj.max95) {
+    g_inj.max95 = v95; g_inj.t95 = Time;
+    g_inj.list95.clear();
+    for (int j = 0; j < n; ++j) if (g_inj.psOld[j] >= g_inj.max95) g_inj.list95.push_back(g_inj.elems[j]);
+  }
+  const double x95 = compute95thPercentileValue(g_inj.psxsr.data(), n);
+  g_inj.histx95.push_back(x95);
+  if (x95 > g_inj.maxx95) {
+    g_inj.maxx95 = x95; g_inj.tx95 = Time;
+    g_inj.listx95.clear();
+    for (int j = 0; j < n; ++j) if (g_inj.psxsr[j] >= g_inj.maxx95) g_inj.listx95.push_back(g_inj.elems[j]);
+  }
+}
+
+static void InjuryDump() {
+  const int n = (int)g_inj.elems.size();
+  puti("inj_elems", g_inj.elems.data(), n);
+  puti("inj_gt15", g_inj.gt15.data(), n); puti("inj_gt30", g_inj.gt30.data(), n);
+  puti("inj_r120", g_inj.r120.data(), n); puti("inj_xsr28", g_inj.xsr28.data(), n);
+  putd("inj_ps_old", g_inj.psOld.data(), n); putd("inj_psxsr", g_inj.psxsr.data(), n);
+  puti("inj_list95", g_inj.list95.data(), (int64_t)g_inj.list95.size());
+  puti("inj_listx95", g_inj.listx95.data(), (int64_t)g_inj.listx95.size());
+  putd("inj_hist95", g_inj.hist95.data(), (int64_t)g_inj.hist95.size());
+  putd("inj_histx95", g_inj.histx95.data(), (int64_t)g_inj.histx95.size());
+  const double sc[12] = {g_inj.maxStrain, g_inj.maxT, g_inj.minStrain, g_inj.minT, g_inj.maxShear, g_inj.maxShearT,
+                         g_inj.maxPSxSR, g_inj.maxTimePSxSR, g_inj.max95, g_inj.t95, g_inj.maxx95, g_inj.tx95};
+  putd("inj_scalars", sc, 12);
+  const int el[4] = {g_inj.maxElem, g_inj.minElem, g_inj.shearElem, g_inj.maxElemPSxSR};
+  puti("inj_extreme_elems", el, 4);
+  /* ex5.cpp:1043-1066: volumes by the reference's computePartVolume */
+  std::vector<double> volumePart(nPIDglobal, 0.0), elementVolume(nelements > 0 ? nelements : 1, 0.0);
+  computePartVolume(volumePart.data(), elementVolume.data());
+  double vol[5] = {0, 0, 0, 0, 0};
+  for (int j = 0; j < n; ++j) {
+    const double eV = elementVolume[g_inj.elems[j]];
+    if (g_inj.gt15[j]) { vol[0] += eV; if (g_inj.gt30[j]) vol[1] += eV; }
+    if (g_inj.r120[j]) vol[2] += eV;
+    if (g_inj.xsr28[j]) vol[3] += eV;
+    vol[4] += eV;
+  }
+  putd("inj_volumes", vol, 5);
+  putd("inj_volume_part", volumePart.data(), nPIDglobal);
+}
 
 /* Benchmarking-Parallel.cpp:184-244, cube side parametrised */
 static void ApplyBoundaryConditions(double dMax, double tMax) {
@@ -160,6 +260,7 @@ int main(int argc, char **argv) {
   putd("accelerations0", accelerations, nDOF);
   putd("pk2_0", pk2, pk2ptr[nelements]);
 
+  if (const char *spec = getenv("REF_INJURY_EXCLUDE")) InjuryInit(spec);
   std::vector<double> dtHist;
   int time_step_counter = 1;
   double t_n = 0.0;
@@ -199,6 +300,7 @@ int main(int argc, char **argv) {
       }
     }
     CheckEnergy(Time, 0); /* writeFlag 0: one energy_<uid>.dat line per step */
+    if (g_inj.on) InjuryStep();  /* ex5.cpp:240 */
     time_step_counter = time_step_counter + 1;
     steps++;
     dt = ExplicitTimeStepReduction * StableTimeStep();
@@ -225,6 +327,7 @@ int main(int argc, char **argv) {
   putd("Hn_1", Hn_1, Hn_1 ? fptr[nelements] : 0);
   putd("Hn_2", Hn_2, Hn_2 ? fptr[nelements] : 0);
   putd("S0n", S0n, S0n ? fptr[nelements] : 0);
+  if (g_inj.on) InjuryDump();
   puts1("wall_setup_s", tSetup);
   puts1("wall_loop_s", tLoop);
   fclose(g_out);

@@ -108,3 +108,72 @@ def test_geometry_quirk_signed_parallelogram_test():
     c1v, c2v = 0.25 * (-p1 + p2 + p3 - p4), 0.25 * (-p1 - p2 + p3 + p4)
     assert a_neg == pytest.approx(4.0 * np.linalg.norm(np.cross(c1v, c2v)), rel=1e-14)
     assert a_pos == pytest.approx(1.5, rel=1e-12)  # planar quad: 2x2 Gauss is exact (shoelace area 1.5)
+
+
+# ---- injury criteria: ex5.cpp:1311-1430 over the reference's own
+#      CalculateMaximumPrincipalStrain / compute95thPercentileValue / computePartVolume ---------------------
+INJURY = ["inj6_p1", "inj6_p3", "inj6b_p1"]
+
+
+def run_injury_oracle(g):
+    models, kinds, rate = _models(g)
+    for m in models:
+        m.ShapeFunctions()
+        m.AssembleLumpedMass()
+    if len(models) > 1:
+        po.halo_sum(models, "mass")
+    inj = [po.InjuryCriteria(m, exclude_pids=g["param_exclude"]) for m in models]
+    d0 = rank_dict(g, 0)
+    n, dth, eh = po.run_explicit(models, kinds, rate, float(g["param_tMax"]), int(d0["steps"][0]), injuries=inj)
+    return models, inj, n, dth
+
+
+@pytest.mark.parametrize("name", INJURY)
+def test_oracle_injury_bit_exact_vs_reference(name):
+    g = golden(name)
+    models, inj, n, dth = run_injury_oracle(g)
+    for r, (m, q) in enumerate(zip(models, inj)):
+        d = rank_dict(g, r)
+        assert n == int(d["steps"][0]) and np.array_equal(dth, d["dt_hist"])
+        assert np.array_equal(m.displacements, d["displacements"])
+        assert np.array_equal(q.get("elementIDInjury"), d["inj_elems"])
+        for ours, ref in (("MPSgt15", "inj_gt15"), ("MPSgt30", "inj_gt30"), ("MPSRgt120", "inj_r120"),
+                          ("MPSxSRgt28", "inj_xsr28"), ("PS_Old", "inj_ps_old"), ("PSxSRArray", "inj_psxsr")):
+            assert np.array_equal(q.get(ours), d[ref]), (name, r, ours)
+        assert np.array_equal(q.scalars(), d["inj_scalars"]), (name, r)
+        assert np.array_equal(q.extreme_elems(), d["inj_extreme_elems"])
+        l95, lx95 = q.lists()
+        assert np.array_equal(l95, d["inj_list95"]) and np.array_equal(lx95, d["inj_listx95"])
+        assert np.array_equal(q.volumes(), d["inj_volumes"])
+        if "Eavg" in d:
+            for e in (0, 7, m.nElements - 1):
+                _, E = q.principal(e)
+                assert np.array_equal(E, d["Eavg"][9 * e:9 * e + 9])
+    # the fixtures exercise every branch: some but not all flags set, both lists non-empty
+    d = rank_dict(g, 0)
+    assert 0 < d["inj_xsr28"].sum() < d["inj_xsr28"].size and len(d["inj_list95"]) and len(d["inj_listx95"])
+
+
+def test_percentile_is_the_order_statistic_the_reference_picks():
+    # math.cpp:160-199 (and :235-332, which always falls through to it): element (int)(0.95 n) - 1, ascending
+    rng = np.random.default_rng(5)
+    a, b = rng.random(1011), rng.random(1031) * 2.0
+    want = np.sort(np.concatenate([a, b]))[int((1011 + 1031) * 0.95) - 1]
+    assert po.percentile95([a, b]) == want
+    g = golden("inj6_p3")
+    h = rank_dict(g, 0)["inj_hist95"]
+    assert all(np.array_equal(rank_dict(g, r)["inj_hist95"], h) for r in range(3))  # collective: same on all ranks
+
+
+def test_principal_strain_degenerate_states():
+    # CalculateStrain.cpp:36-41: exactly diagonal E takes the shortcut; a double root that is not exactly diagonal can
+    # push acos's argument past 1 -> NaN -> the reference reports 0 (fmax/fmin drop NaN only if one operand is finite).
+    X, conn, pid = mesh.cube_mesh(1)
+    m = po.OracleModel(X, conn, pid, [1], [1040.0, 100.0, 100.0, 0, 0, 0, 0, 0, 0])
+    m.ShapeFunctions()
+    q = po.InjuryCriteria(m)
+    Fd = np.diag([1.2, 0.9, 0.9])
+    m.F[:] = np.tile(Fd.T.reshape(-1), 8)
+    (smax, smin, shear), E = q.principal(0)
+    assert smax == pytest.approx(0.5 * (1.44 - 1), rel=1e-14) and smin == pytest.approx(0.5 * (0.81 - 1), rel=1e-14)
+    assert shear == pytest.approx(0.5 * (smax - smin), rel=1e-14)
