@@ -37,6 +37,13 @@ struct ftb200_ctx {
   // host copies of the inputs
   std::vector<double> h_X;
   std::vector<int> h_conn, h_pid, h_matid;
+  // injury criteria (ftb200_injury_begin)
+  bool injury = false;
+  double *inj_ps = nullptr, *inj_psxsr = nullptr, *inj_smin = nullptr, *inj_shear = nullptr, *inj_part = nullptr, *inj_hist = nullptr;
+  uint8_t *inj_flags = nullptr, *inj_incl = nullptr;
+  int* inj_parti = nullptr;
+  InjState* inj_state = nullptr;
+  double inj_thr[4] = {0.15, 0.30, 120.0, 28.0};
   std::vector<double> h_props;
   std::vector<int> h_sendProcessID, h_sendCum, h_sendNodeIndex;
   // device arrays
@@ -165,6 +172,9 @@ ElemArgs elem_args(ftb200_ctx* c, int e0, int e1, int ignore) {
   for (int k = 0; k < 3; ++k) { A.X[k] = c->X[k]; A.u[k] = c->u[k]; }
   A.conn = c->conn; A.pid = c->pid; A.eflag = c->eflag; A.mp = c->mp; A.felem = c->felem; A.hist = c->hist;
   A.sc = c->sc; A.nE = c->nE; A.e0 = e0; A.e1 = e1; A.ignore_loop_flags = ignore;
+  A.inj_ps = c->inj_ps; A.inj_psxsr = c->inj_psxsr; A.inj_smin = c->inj_smin; A.inj_shear = c->inj_shear;
+  A.inj_flags = c->inj_flags; A.inj_incl = c->inj_incl;
+  for (int k = 0; k < 4; ++k) A.inj_thr[k] = c->inj_thr[k];
   return A;
 }
 NodeArgs node_args(ftb200_ctx* c, const double* recv) {
@@ -191,6 +201,15 @@ void launch_elem(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore) {
   const ElemArgs A = elem_args(ctx, e0, e1, ignore);
   const int grid = cdiv(e1 - e0, ELEM_BLOCK);
   if (!WITH_FORCE) { LAUNCH((k_elem<-1, false, true>), grid, ELEM_BLOCK, s, A); return; }
+  if (WITH_FORCE && WITH_DT && ctx->injury && !ignore) {  // a step of the loop with the injury criteria on
+    switch (ctx->uniform_mat) {
+      case 1: LAUNCH((k_elem<1, true, true, true>), grid, ELEM_BLOCK, s, A); break;
+      case 4: LAUNCH((k_elem<4, true, true, true>), grid, ELEM_BLOCK, s, A); break;
+      case 5: LAUNCH((k_elem<5, true, true, true>), grid, ELEM_BLOCK, s, A); break;
+      default: LAUNCH((k_elem<-1, true, true, true>), grid, ELEM_BLOCK, s, A); break;
+    }
+    return;
+  }
   switch (ctx->uniform_mat) {
     case 1: LAUNCH((k_elem<1, WITH_FORCE, WITH_DT>), grid, ELEM_BLOCK, s, A); break;
     case 4: LAUNCH((k_elem<4, WITH_FORCE, WITH_DT>), grid, ELEM_BLOCK, s, A); break;
@@ -210,7 +229,19 @@ cudaEvent_t prof_event(ftb200_ctx* ctx, size_t* idx) {
   return P.pool[P.used++];
 }
 
-// one loop iteration: K_elem -> K_adv -> K_node (-> K_energy)
+// CalculateInjuryCriterions (ex5.cpp:1311-1430) across elements, after k_adv has advanced Time: running extrema,
+// the two 95th-percentile selections (8 radix passes), the element lists.  INJ_LAUNCHES kernels.
+constexpr int INJ_LAUNCHES = 10;
+void launch_injury(ftb200_ctx* ctx, cudaStream_t s) {
+  const ElemArgs A = elem_args(ctx, 0, ctx->nE, 0);
+  LAUNCH(k_injury_reduce, INJ_BLOCKS, INJ_THREADS, s, A, ctx->ref_of, ctx->inj_state, ctx->inj_part, ctx->inj_parti);
+  double* h0 = ctx->inj_hist;
+  double* h1 = ctx->inj_hist ? ctx->inj_hist + ctx->hist_cap : nullptr;
+  for (int pass = 0; pass < 8; ++pass) LAUNCH(k_injury_select, dim3(INJ_BLOCKS, 2), INJ_THREADS, s, A, ctx->inj_state, pass, h0, h1);
+  LAUNCH(k_injury_lists, cdiv(ctx->nE, 256), 256, s, A, ctx->inj_state);
+}
+
+// one loop iteration: K_elem -> K_adv -> K_node (-> K_energy) (-> injury criteria)
 void launch_step(ftb200_ctx* ctx, const double* recv) {
   cudaStream_t s = ctx->stream;
   size_t i0 = 0, i1 = 0;
@@ -224,6 +255,7 @@ void launch_step(ftb200_ctx* ctx, const double* recv) {
   else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.node.push_back({i0, i1}); }
   if (ctx->energy) LAUNCH(k_energy, 1, 256, s, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
+  if (ctx->injury) launch_injury(ctx, s);
 }
 
 // ---- pipelined loop: k_elem_pipe on the main stream, k_node_pipe on the second (high priority) stream
@@ -299,6 +331,8 @@ void free_all(ftb200_ctx* c) {
   }
   dfree(c->m); dfree(c->flags); dfree(c->conn); dfree(c->pid); dfree(c->ref_of); dfree(c->eflag);
   dfree(c->felem); dfree(c->hist); dfree(c->mp); dfree(c->node_off); dfree(c->node_ent); dfree(c->sc);
+  dfree(c->inj_ps); dfree(c->inj_psxsr); dfree(c->inj_smin); dfree(c->inj_shear); dfree(c->inj_part); dfree(c->inj_hist);
+  dfree(c->inj_flags); dfree(c->inj_incl); dfree(c->inj_parti); dfree(c->inj_state);
   dfree(c->dthist); dfree(c->ehist); dfree(c->epart); dfree(c->out3); dfree(c->d_istage); dfree(c->d_big);
   c->d_big_bytes = 0;
   dfree(c->d_detmin); dfree(c->d_nonpos);
@@ -948,6 +982,12 @@ int ftb200_record_history(ftb200_ctx* ctx, long long capacity) {
   }
   CK(cudaMemcpy(&ctx->sc->hist_cap, &capacity, sizeof(long long), cudaMemcpyHostToDevice));
   if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+  dfree(ctx->inj_hist);
+  if (ctx->injury && capacity > 0) {
+    int rc;
+    if ((rc = dalloc(ctx, &ctx->inj_hist, 2 * (size_t)capacity))) return rc;
+    CK(cudaMemset(ctx->inj_hist, 0, 2 * capacity * sizeof(double)));
+  }
   return FTB200_OK;
 }
 
@@ -1263,7 +1303,7 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
     if (ctx->energy) LAUNCH((k_node<false, true, false, true>), ctx->node_blocks, NODE_BLOCK, s, N);
     else LAUNCH((k_node<false, true, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   }
-  const int per_step = 3 + (ctx->energy ? 1 : 0);
+  const int per_step = 3 + (ctx->energy ? 1 : 0) + (ctx->injury ? INJ_LAUNCHES : 0);
   long long left = steps;
   const bool use_graph = !ctx->profile;  // built on the first run (warm-up), whatever its length
   if (use_graph) {
@@ -1587,6 +1627,150 @@ int ftb200_debug_pipe(ftb200_ctx* ctx, int which, int reps, double* ms_per_launc
   *ms_per_launch = total / reps;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  return FTB200_OK;
+}
+
+// ----------------------------------------------------------------------------------- injury criteria
+static void drop_graphs(ftb200_ctx* ctx) {
+  if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+  if (ctx->p2p_graph) { cudaGraphExecDestroy(ctx->p2p_graph); ctx->p2p_graph = nullptr; }
+  if (ctx->fgraph) { cudaGraphExecDestroy(ctx->fgraph); ctx->fgraph = nullptr; }
+  if (ctx->pgraph) { cudaGraphExecDestroy(ctx->pgraph); ctx->pgraph = nullptr; }
+}
+
+int ftb200_injury_begin(ftb200_ctx* ctx, const int* exclude_pids, int n_exclude, const double* thresholds4) {
+  if (!ctx || !ctx->shape_ok || n_exclude < 0 || (n_exclude && !exclude_pids))
+    return fail(ctx, FTB200_ERR_INPUT, "injury_begin: setup incomplete or bad arguments");
+  if (ctx->nranks > 1) return fail(ctx, FTB200_ERR_INPUT, "injury_begin: single partition only in this version");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t nE = ctx->nE;
+  // InitInjuryCriterion (ex5.cpp:1251-1281): elements whose part is not excluded, internal element order
+  std::vector<int> ref_of(nE);
+  CK(cudaMemcpy(ref_of.data(), ctx->ref_of, nE * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<uint8_t> incl(nE, 1);
+  int n = 0;
+  for (size_t t = 0; t < nE; ++t) {
+    const int pide = ctx->h_pid[ref_of[t]];
+    for (int j = 0; j < n_exclude; ++j)
+      if (pide == exclude_pids[j]) { incl[t] = 0; break; }
+    n += incl[t];
+  }
+  const int index95 = (int)(n * 0.95) - 1;  // math.cpp:189; the reference faults on a negative index
+  if (index95 < 0) return fail(ctx, FTB200_ERR_INPUT, "injury_begin: %d participating elements, the 95th percentile needs >= 2", n);
+  int rc;
+  if (!ctx->inj_ps) {
+    if ((rc = dalloc(ctx, &ctx->inj_ps, nE)) || (rc = dalloc(ctx, &ctx->inj_psxsr, nE)) || (rc = dalloc(ctx, &ctx->inj_smin, nE)) ||
+        (rc = dalloc(ctx, &ctx->inj_shear, nE)) || (rc = dalloc(ctx, &ctx->inj_flags, nE)) || (rc = dalloc(ctx, &ctx->inj_incl, nE)) ||
+        (rc = dalloc(ctx, &ctx->inj_part, 4 * (size_t)INJ_BLOCKS)) || (rc = dalloc(ctx, &ctx->inj_parti, 4 * (size_t)INJ_BLOCKS)) ||
+        (rc = dalloc(ctx, &ctx->inj_state, 1)))
+      return rc;
+  }
+  // PS_Old starts at zero (the reference mallocs it uninitialised, ex5.cpp:1285; fresh pages read as zero)
+  CK(cudaMemset(ctx->inj_ps, 0, nE * sizeof(double)));
+  CK(cudaMemset(ctx->inj_psxsr, 0, nE * sizeof(double)));
+  CK(cudaMemset(ctx->inj_smin, 0, nE * sizeof(double)));
+  CK(cudaMemset(ctx->inj_shear, 0, nE * sizeof(double)));
+  CK(cudaMemset(ctx->inj_flags, 0, nE));
+  CK(cudaMemcpy(ctx->inj_incl, incl.data(), nE, cudaMemcpyHostToDevice));
+  InjState st;
+  memset(&st, 0, sizeof(st));
+  st.kth0 = (unsigned)index95;
+  st.nIncluded = n;
+  CK(cudaMemcpy(ctx->inj_state, &st, sizeof(st), cudaMemcpyHostToDevice));
+  if (thresholds4) for (int k = 0; k < 4; ++k) ctx->inj_thr[k] = thresholds4[k];
+  else { ctx->inj_thr[0] = 0.15; ctx->inj_thr[1] = 0.30; ctx->inj_thr[2] = 120.0; ctx->inj_thr[3] = 28.0; }
+  dfree(ctx->inj_hist);
+  if (ctx->hist_cap > 0) {
+    if ((rc = dalloc(ctx, &ctx->inj_hist, 2 * (size_t)ctx->hist_cap))) return rc;
+    CK(cudaMemset(ctx->inj_hist, 0, 2 * ctx->hist_cap * sizeof(double)));
+  }
+  ctx->injury = true;
+  ctx->fused = false; ctx->pipe = false;  // the criteria live in the two-kernel step
+  drop_graphs(ctx);
+  return FTB200_OK;
+}
+
+int ftb200_injury_end(ftb200_ctx* ctx) {
+  if (!ctx) return FTB200_ERR_INPUT;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->injury = false;
+  drop_graphs(ctx);
+  return FTB200_OK;
+}
+
+int ftb200_principal_strains(ftb200_ctx* ctx, double* smax, double* smin, double* shear, double* volume0) {
+  if (!ctx || !ctx->shape_ok) return fail(ctx, FTB200_ERR_INPUT, "principal_strains: setup incomplete");
+  if ((smax || smin || shear) && !(smax && smin && shear)) return fail(ctx, FTB200_ERR_INPUT, "principal_strains: smax, smin, shear go together");
+  CK(cudaSetDevice(ctx->device));
+  const size_t nE = ctx->nE;
+  int rc;
+  if ((rc = ensure_big(ctx, 4 * nE * sizeof(double)))) return rc;
+  double* d = ctx->d_big;
+  LAUNCH(k_principal, cdiv(ctx->nE, 64), 64, ctx->stream, elem_args(ctx, 0, ctx->nE, 1), ctx->ref_of, smax ? d : nullptr, d + nE,
+         d + 2 * nE, volume0 ? d + 3 * nE : nullptr);
+  if (smax) {
+    CK(cudaMemcpyAsync(smax, d, nE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(smin, d + nE, nE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(shear, d + 2 * nE, nE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (volume0) CK(cudaMemcpyAsync(volume0, d + 3 * nE, nE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return FTB200_OK;
+}
+
+int ftb200_injury_get(ftb200_ctx* ctx, double* scalars12, int* extreme_elems4, unsigned char* flags, double* ps, double* psxsr,
+                      double* volumes5) {
+  if (!ctx || !ctx->inj_state) return fail(ctx, FTB200_ERR_INPUT, "injury_get: call injury_begin first");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  InjState st;
+  CK(cudaMemcpy(&st, ctx->inj_state, sizeof(st), cudaMemcpyDeviceToHost));
+  if (scalars12) for (int k = 0; k < 12; ++k) scalars12[k] = st.scal[k];
+  if (extreme_elems4) for (int k = 0; k < 4; ++k) extreme_elems4[k] = st.elems[k];
+  if (!(flags || ps || psxsr || volumes5)) return FTB200_OK;
+  const size_t nE = ctx->nE;
+  std::vector<int> ref_of(nE);
+  std::vector<uint8_t> f(nE), incl(nE);
+  CK(cudaMemcpy(ref_of.data(), ctx->ref_of, nE * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(f.data(), ctx->inj_flags, nE, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(incl.data(), ctx->inj_incl, nE, cudaMemcpyDeviceToHost));
+  std::vector<uint8_t> fr(nE);
+  for (size_t t = 0; t < nE; ++t) fr[ref_of[t]] = (uint8_t)(f[t] | (incl[t] ? 0x80u : 0u));
+  if (flags) memcpy(flags, fr.data(), nE);
+  std::vector<double> tmp(nE);
+  if (ps) {
+    CK(cudaMemcpy(tmp.data(), ctx->inj_ps, nE * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t t = 0; t < nE; ++t) ps[ref_of[t]] = tmp[t];
+  }
+  if (psxsr) {
+    CK(cudaMemcpy(tmp.data(), ctx->inj_psxsr, nE * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t t = 0; t < nE; ++t) psxsr[ref_of[t]] = tmp[t];
+  }
+  if (volumes5) {  // ex5.cpp:1049-1066: summed in the reference's element order
+    int rc = ftb200_principal_strains(ctx, nullptr, nullptr, nullptr, tmp.data());
+    if (rc) return rc;
+    for (int k = 0; k < 5; ++k) volumes5[k] = 0.0;
+    for (size_t e = 0; e < nE; ++e) {
+      if (!(fr[e] & 0x80u)) continue;
+      const double eV = tmp[e];
+      if (fr[e] & FTB_INJ_MPS_LO) { volumes5[0] += eV; if (fr[e] & FTB_INJ_MPS_HI) volumes5[1] += eV; }
+      if (fr[e] & FTB_INJ_PSR) volumes5[2] += eV;
+      if (fr[e] & FTB_INJ_PSXSR) volumes5[3] += eV;
+      volumes5[4] += eV;
+    }
+  }
+  return FTB200_OK;
+}
+
+int ftb200_injury_history(ftb200_ctx* ctx, long long first, long long count, double* mps95, double* mpsxsr95) {
+  if (!ctx || !ctx->inj_hist || first < 0 || count < 0 || first + count > ctx->hist_cap)
+    return fail(ctx, FTB200_ERR_INPUT, "injury_history: no history recorded (record_history before injury_begin) or bad range");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (mps95 && count) CK(cudaMemcpy(mps95, ctx->inj_hist + first, count * sizeof(double), cudaMemcpyDeviceToHost));
+  if (mpsxsr95 && count) CK(cudaMemcpy(mpsxsr95, ctx->inj_hist + ctx->hist_cap + first, count * sizeof(double), cudaMemcpyDeviceToHost));
   return FTB200_OK;
 }
 

@@ -92,7 +92,21 @@ struct ElemArgs {
   int nE;            // plane stride
   int e0, e1;        // element range of this launch
   int ignore_loop_flags;
+  // injury criteria (k_elem<..., WITH_INJ>), internal element order; see InjState below
+  double* inj_ps;          // PS_Old: max principal strain of the previous step in, of this step out (ex5.cpp:1367)
+  double* inj_psxsr;       // PSxSRArray (:1368)
+  double* inj_smin;        // this step's minimum principal strain (clipped at <= 0)
+  double* inj_shear;       // this step's maximum shear strain
+  uint8_t* inj_flags;      // FTB_INJ_* bits
+  const uint8_t* inj_incl; // 1 = element takes part (its part is not excluded, ex5.cpp:1251-1281)
+  double inj_thr[4];       // MPS > thr0, MPS > thr1, PSR > thr2, PSxSR > thr3 (0.15, 0.30, 120, 28 in ex5.cpp:1335-1365)
 };
+#define FTB_INJ_MPS_LO 1u
+#define FTB_INJ_MPS_HI 2u
+#define FTB_INJ_PSR 4u
+#define FTB_INJ_PSXSR 8u
+#define FTB_INJ_LIST95 16u
+#define FTB_INJ_LISTX95 32u
 
 #ifndef FTB_ELEM_BLOCK
 #define FTB_ELEM_BLOCK 64
@@ -113,8 +127,8 @@ struct SmemScratch {
 // K1 (+K6).  MATSEL >= 0: every element of the launch has that material (no switch).
 // material 5 (36 history doubles per Gauss point in flight) and the generic per-element switch need more
 // registers than 168: they run with 4 resident blocks per SM instead of 6
-template <int MATSEL, bool WITH_FORCE, bool WITH_DT>
-__global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : ELEM_MINBLOCKS) k_elem(const ElemArgs A) {
+template <int MATSEL, bool WITH_FORCE, bool WITH_DT, bool WITH_INJ = false>
+__global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0 || WITH_INJ) ? 4 : ELEM_MINBLOCKS) k_elem(const ElemArgs A) {
   const int e = A.e0 + blockIdx.x * ELEM_BLOCK + threadIdx.x;
   const size_t E = (size_t)A.nE;
   // the connectivity is requested before the loop-control flags are tested: one exposed latency, not two
@@ -144,7 +158,26 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
       DevHist h{A.hist, E, (size_t)e};
       double d;
       SmemScratch S{&sm_cols[0][threadIdx.x]};
-      status = hex8_element<MATSEL, WITH_DT>(X, U, mat, mp, true, h, NoOutput(), S, fe, &d);
+      if (WITH_INJ) {
+        // strain/injury outputs fused into the force kernel: F never leaves the registers
+        double cs[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        status = hex8_element<MATSEL, WITH_DT>(X, U, mat, mp, true, h, StrainSink{cs}, S, fe, &d);
+        if (A.inj_incl[e]) {  // ex5.cpp:1313-1369, one element of the loop
+          double smax, smin, shear;
+          principal_strains(cs, &smax, &smin, &shear);
+          const double PSR = (smax - A.inj_ps[e]) / A.sc->ndt;  // first-order backward difference, :1347
+          const double PSxSR = smax * PSR;
+          unsigned f = A.inj_flags[e];
+          if (smax > A.inj_thr[0]) f |= FTB_INJ_MPS_LO;
+          if (smax > A.inj_thr[1]) f |= FTB_INJ_MPS_HI;
+          if (PSR > A.inj_thr[2]) f |= FTB_INJ_PSR;
+          if (PSxSR > A.inj_thr[3]) f |= FTB_INJ_PSXSR;
+          A.inj_flags[e] = (uint8_t)f;
+          A.inj_ps[e] = smax; A.inj_psxsr[e] = PSxSR; A.inj_smin[e] = smin; A.inj_shear[e] = shear;
+        }
+      } else {
+        status = hex8_element<MATSEL, WITH_DT>(X, U, mat, mp, true, h, NoOutput(), S, fe, &d);
+      }
       if (WITH_DT) dte = d;
 #pragma unroll
       for (int k = 0; k < 8; ++k)
@@ -685,6 +718,7 @@ __global__ void k_gather_shared(const double* felem, const int* node_off, const 
 // Gauss-point outputs in the reference's layouts (lazy; never on the hot path)
 struct OutSink {
   static constexpr bool enabled = true;
+  static constexpr bool want_S = true;
   double *F, *detF, *pk2;
   size_t e;
   __device__ __forceinline__ void put(int gp, const double Fm[3][3], double J, const double Sv[6]) const {
@@ -1635,6 +1669,205 @@ __global__ void __launch_bounds__(256) k_energy_tiles(DevScalars* sc, StepCtl* c
     __threadfence();
     *(volatile long long*)&ctl->energy_step = k + 1;
   }
+}
+
+// =============================================================================================
+// Injury criteria of the brain drivers (examples/ex5/ex5.cpp:1311-1430), device side.  k_elem<..., WITH_INJ> leaves
+// the per-element quantities of the step; the kernels below do what the reference's loop does across elements:
+// running extrema with their element and time, the 95th-percentile values (math.cpp:160-199: the order statistic
+// (int)(0.95 n) - 1, found here by an 8-pass radix select on order-preserving keys -- a selection, so bit-exact),
+// and the element lists of the percentile maxima.
+struct InjState {
+  double scal[12];  // maxStrain, maxT, minStrain, minT, maxShear, maxShearT, maxPSxSR, maxTimePSxSR, MPS95, t, MPSxSR95, t
+  int elems[4];     // reference element ids of the four extrema (ex5.cpp:63,74)
+  int upd[2];       // this step raised MPS-95 / MPSxSR-95
+  unsigned red_done, sel_done[2];
+  unsigned kth0, kth[2];
+  unsigned long long prefix[2];
+  unsigned hist[2][256];
+  int nIncluded, pad;
+};
+constexpr int INJ_BLOCKS = 296;  // 2 per SM
+constexpr int INJ_THREADS = 256;
+
+struct InjCand { double v; int id; };
+// a beats b: strictly larger value, or the same value at a lower reference element id (the reference's loop keeps
+// the first element that attains the maximum, ex5.cpp:1318-1332)
+__device__ __forceinline__ InjCand inj_best(InjCand a, InjCand b) {
+  return (b.v > a.v || (b.v == a.v && b.id < a.id)) ? b : a;
+}
+__device__ __forceinline__ InjCand inj_shfl(InjCand a, int o) {
+  InjCand b;
+  b.v = __shfl_xor_sync(0xffffffffu, a.v, o);
+  b.id = __shfl_xor_sync(0xffffffffu, a.id, o);
+  return b;
+}
+
+// part: [4][INJ_BLOCKS] values, parti: [4][INJ_BLOCKS] ids.  Metric 1 (minimum strain) is reduced as the maximum of -smin.
+__global__ void __launch_bounds__(INJ_THREADS) k_injury_reduce(const ElemArgs A, const int* ref_of, InjState* st, double* part,
+                                                                int* parti) {
+  const DevScalars* sc = A.sc;
+  if (!sc->active) return;
+  InjCand c[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) { c[m].v = -1.0; c[m].id = 0x7fffffff; }
+  for (int e = blockIdx.x * INJ_THREADS + threadIdx.x; e < A.nE; e += gridDim.x * INJ_THREADS) {
+    if (!A.inj_incl[e]) continue;
+    const int id = ref_of[e];
+    const InjCand n0{A.inj_ps[e], id}, n1{-A.inj_smin[e], id}, n2{A.inj_shear[e], id}, n3{A.inj_psxsr[e], id};
+    c[0] = inj_best(c[0], n0); c[1] = inj_best(c[1], n1); c[2] = inj_best(c[2], n2); c[3] = inj_best(c[3], n3);
+  }
+  __shared__ double sv[4][INJ_THREADS / 32];
+  __shared__ int si[4][INJ_THREADS / 32];
+  __shared__ int s_last;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c[m] = inj_best(c[m], inj_shfl(c[m], o));
+    if ((threadIdx.x & 31) == 0) { sv[m][threadIdx.x >> 5] = c[m].v; si[m][threadIdx.x >> 5] = c[m].id; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    const int m = threadIdx.x;
+    InjCand b{sv[m][0], si[m][0]};
+    for (int w = 1; w < INJ_THREADS / 32; ++w) b = inj_best(b, InjCand{sv[m][w], si[m][w]});
+    part[m * INJ_BLOCKS + blockIdx.x] = b.v;
+    parti[m * INJ_BLOCKS + blockIdx.x] = b.id;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&st->red_done, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < 4) {
+    const int m = threadIdx.x;
+    InjCand b{-1.0, 0x7fffffff};
+    for (int k = 0; k < (int)gridDim.x; ++k) b = inj_best(b, InjCand{__ldcg(part + m * INJ_BLOCKS + k), __ldcg(parti + m * INJ_BLOCKS + k)});
+    // running extremum with its element and time: `if (maxStrain < current)`, ex5.cpp:1318-1332,1350-1354
+    const double cur = (m == 1) ? -st->scal[2] : st->scal[2 * m];
+    if (b.id != 0x7fffffff && cur < b.v) {
+      st->scal[2 * m] = (m == 1) ? -b.v : b.v;
+      st->scal[2 * m + 1] = sc->Time;
+      st->elems[m] = b.id;
+    }
+    if (m == 0) st->red_done = 0;
+  }
+}
+
+__device__ __forceinline__ unsigned long long inj_key(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);  // ascending keys == ascending doubles
+}
+__device__ __forceinline__ double inj_unkey(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+// one digit (8 bits, most significant first) of the two selections: blockIdx.y = 0 MPS, 1 MPSxSR
+__global__ void __launch_bounds__(INJ_THREADS) k_injury_select(const ElemArgs A, InjState* st, const int pass, double* hist95,
+                                                                double* histx95) {
+  const DevScalars* sc = A.sc;
+  if (!sc->active) return;
+  const int arr = blockIdx.y;
+  const double* data = arr ? A.inj_psxsr : A.inj_ps;
+  __shared__ unsigned h[256];
+  __shared__ int s_last;
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int shift = 56 - 8 * pass;
+  const unsigned long long prefix = st->prefix[arr];
+  for (int e = blockIdx.x * INJ_THREADS + threadIdx.x; e < A.nE; e += gridDim.x * INJ_THREADS) {
+    if (!A.inj_incl[e]) continue;
+    const unsigned long long k = inj_key(data[e]);
+    if (pass == 0 || ((k ^ prefix) >> (shift + 8)) == 0) atomicAdd(&h[(unsigned)(k >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  if (h[threadIdx.x]) atomicAdd(&st->hist[arr][threadIdx.x], h[threadIdx.x]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&st->sel_done[arr], 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  h[threadIdx.x] = __ldcg(&st->hist[arr][threadIdx.x]);
+  st->hist[arr][threadIdx.x] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned k = pass == 0 ? st->kth0 : st->kth[arr];
+    unsigned digit = 255;
+    for (unsigned i = 0; i < 256; ++i) {
+      if (k < h[i]) { digit = i; break; }
+      k -= h[i];
+    }
+    const unsigned long long np = (pass == 0 ? 0ULL : prefix) | ((unsigned long long)digit << shift);
+    st->prefix[arr] = np;
+    st->kth[arr] = k;
+    st->sel_done[arr] = 0;
+    if (pass == 7) {  // ex5.cpp:1372-1377 / :1402-1406
+      const double v = inj_unkey(np);
+      const long long i = sc->step - 1;
+      double* hh = arr ? histx95 : hist95;
+      if (hh && i >= 0 && i < sc->hist_cap) hh[i] = v;
+      if (v > st->scal[8 + 2 * arr]) {
+        st->scal[8 + 2 * arr] = v;
+        st->scal[9 + 2 * arr] = sc->Time;
+        st->upd[arr] = 1;
+      } else {
+        st->upd[arr] = 0;
+      }
+    }
+  }
+}
+
+// element lists of the percentile maxima, rebuilt in the step that raised them (ex5.cpp:1376-1398, :1406-1428)
+__global__ void __launch_bounds__(256) k_injury_lists(const ElemArgs A, const InjState* st) {
+  if (!A.sc->active) return;
+  const int u0 = st->upd[0], u1 = st->upd[1];
+  if (!(u0 | u1)) return;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= A.nE || !A.inj_incl[e]) return;
+  unsigned f = A.inj_flags[e];
+  if (u0) f = (f & ~FTB_INJ_LIST95) | (A.inj_ps[e] >= st->scal[8] ? FTB_INJ_LIST95 : 0u);
+  if (u1) f = (f & ~FTB_INJ_LISTX95) | (A.inj_psxsr[e] >= st->scal[10] ? FTB_INJ_LISTX95 : 0u);
+  A.inj_flags[e] = (uint8_t)f;
+}
+
+// CalculateMaximumPrincipalStrain for every element from the current displacements (legacy / on-demand path) and
+// the reference-configuration volumes of computePartVolume (Elements.cpp:30-38); outputs in reference element order
+__global__ void k_principal(const ElemArgs A, const int* ref_of, double* smax, double* smin, double* shear, double* vol0) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= A.nE) return;
+  const size_t E = (size_t)A.nE;
+  double X[8][3], U[8][3];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int nd = A.conn[(size_t)k * E + e];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { X[k][c] = A.X[c][nd]; U[k][c] = A.u[c][nd]; }
+  }
+  const size_t re = (size_t)ref_of[e];
+  if (vol0) {
+    double xm[7][3], n[8], g[7];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) n[k] = X[k][c];
+      hex_modes(n, g);
+#pragma unroll
+      for (int m = 0; m < 7; ++m) xm[m][c] = g[m];
+    }
+    vol0[re] = hex_volume_modes(xm);
+  }
+  if (!smax) return;
+  const double* mp = A.mp + (size_t)A.pid[e] * FTB_MP_STRIDE;
+  double cs[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double fe[8][3], d;
+  LocalScratch S;
+  hex8_element<0, false>(X, U, 0, mp, false, NoHistory(), StrainSink{cs}, S, fe, &d);  // material 0: kinematics only
+  double a, b, c;
+  principal_strains(cs, &a, &b, &c);
+  smax[re] = a; smin[re] = b; shear[re] = c;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -493,8 +493,67 @@ FTB_HD void col_butterfly(Scratch& S, const int f, const int t, const int c, con
 // kernel uses NoOutput.
 struct NoOutput {
   static constexpr bool enabled = false;
+  static constexpr bool want_S = false;
   FTB_HD void put(int, const double[3][3], double, const double[6]) const {}
 };
+
+// Sink of the injury criteria: sum over the Gauss points of F^T F (6 unique entries 00 11 22 12 02 01), the raw
+// material of CalculateMaximumPrincipalStrain (CalculateStrain.cpp:16-24).  Lives in registers of the hot kernel.
+struct StrainSink {
+  static constexpr bool enabled = true;
+  static constexpr bool want_S = false;
+  double* c;
+  FTB_HD void put(int, const double F[3][3], double, const double[6]) const {
+    c[0] += F[0][0] * F[0][0] + F[1][0] * F[1][0] + F[2][0] * F[2][0];
+    c[1] += F[0][1] * F[0][1] + F[1][1] * F[1][1] + F[2][1] * F[2][1];
+    c[2] += F[0][2] * F[0][2] + F[1][2] * F[1][2] + F[2][2] * F[2][2];
+    c[3] += F[0][1] * F[0][2] + F[1][1] * F[1][2] + F[2][1] * F[2][2];
+    c[4] += F[0][0] * F[0][2] + F[1][0] * F[1][2] + F[2][0] * F[2][2];
+    c[5] += F[0][0] * F[0][1] + F[1][0] * F[1][1] + F[2][0] * F[2][1];
+  }
+};
+
+// CalculateStrain.cpp:8-75: E = (0.5/8) sum_gp F^T F - 0.5 I, closed-form eigenvalues of the symmetric 3x3,
+// max clipped at >= 0, min at <= 0, shear = (max - min)/2 of the unclipped values.
+// One deliberate difference: the argument of acos is clamped to [-1, 1].  For a double root that is not exactly
+// diagonal the reference's ratio R/sqrt(-Q^3) can round past 1, acos gives NaN and the element silently reports
+// 0 strain (:50-58,61-74); here it reports the eigenvalues.  Where the reference is finite the two agree.
+FTB_HD void principal_strains(const double csum[6], double* smax, double* smin, double* shear) {
+  const double pre = 0.5 / 8.0;
+  const double a = pre * csum[0] - 0.5, d = pre * csum[1] - 0.5, f = pre * csum[2] - 0.5;
+  const double e = pre * csum[3], c = pre * csum[4], b = pre * csum[5];
+  const double p1 = b * b + c * c + e * e;
+  double eps1, eps2, eps3;
+  if (p1 == 0) {
+    eps1 = a; eps2 = d; eps3 = f;
+  } else {
+    double I1 = a + d + f;
+    const double I2 = a * (d + f) + d * f - b * b - c * c - e * e;
+    const double I3 = a * d * f + 2.0 * b * c * e - b * b * f - c * c * d - e * e * a;
+    const double Q = (3.0 * I2 - I1 * I1) / 9.0;
+    const double R = (2.0 * I1 * I1 * I1 - 9.0 * I1 * I2 + 27.0 * I3) / 54.0;
+    double ratio = R / sqrt(-Q * Q * Q);
+    ratio = ratio > 1.0 ? 1.0 : (ratio < -1.0 ? -1.0 : ratio);
+    const double theta = acos(ratio);
+    const double sqrtQ = 2.0 * sqrt(-Q);
+    const double kPi = 3.14159265358979323846;  // 4 atan(1)
+    I1 = I1 / 3.0;
+    eps1 = sqrtQ * cos(theta / 3.0) + I1;
+    eps2 = sqrtQ * cos((theta + 2.0 * kPi) / 3.0) + I1;
+    eps3 = sqrtQ * cos((theta + 4.0 * kPi) / 3.0) + I1;
+  }
+  const double mx = fmax(eps3, fmax(eps2, eps1)), mn = fmin(eps3, fmin(eps2, eps1));
+  *shear = 0.5 * (mx - mn);
+  *smax = mx > 0.0 ? mx : 0.0;
+  *smin = mn < 0.0 ? mn : 0.0;
+}
+
+// volumeHexahedron (Geometry.cpp:3-27) from the mode vectors of the nodal coordinates
+FTB_HD double hex_volume_modes(const double xm[7][3]) {
+  const double* g1 = xm[0]; const double* g2 = xm[1]; const double* g3 = xm[2];
+  const double* g12 = xm[3]; const double* g23 = xm[4]; const double* g13 = xm[5];
+  return (tp3(g12, g2, g23) + tp3(g1, g12, g13) + tp3(g13, g23, g3)) / 192.0 + tp3(g1, g2, g3) / 64.0;
+}
 
 // The whole element: nodal X[8][3], U[8][3] (C3D8 node order) -> fe[8][3].
 // MATSEL: compile-time material id (1..5) when the whole launch is uniform,
@@ -589,7 +648,7 @@ FTB_HD int hex8_element(const double X[8][3], const double U[8][3], int mat, con
     double P[3][3], Sv[6];
     GpHistory h;
     if (mat == 5) hist.load(gp, h);
-    status |= material_P<Out::enabled>(mat, F, cF, J, mp, &h, updHist, P, Sv);
+    status |= material_P<Out::want_S>(mat, F, cF, J, mp, &h, updHist, P, Sv);
     if (mat == 5 && updHist) hist.store(gp, h);
     if (Out::enabled) out.put(gp, F, J, Sv);
     // Q = P * cof(J0)  (unscaled: 64 x the true one), accumulated into the 7 force modes

@@ -184,6 +184,46 @@ class FemTech:
     def CalculateStrain(self):
         return self.gp_outputs(F=False, detF=False, pk2=False, Eavg=True)["Eavg"]
 
+    def CalculateMaximumPrincipalStrain(self, volume=False):
+        """CalculateStrain.cpp:8-75 for every element at the displacements now on the device: (max, min, shear)
+        arrays [nE] (+ calculateVolume(e) of the reference configuration when volume=True)."""
+        nE = self.nelements
+        a, b, c = np.zeros(nE), np.zeros(nE), np.zeros(nE)
+        v = np.zeros(nE) if volume else None
+        self._check(self.L.ftb200_principal_strains(self._h, _d(a), _d(b), _d(c), _d(v)))
+        return (a, b, c, v) if volume else (a, b, c)
+
+    # --- injury criteria of the brain drivers (ex5.cpp:1251-1430), evaluated inside the resident loop ---------
+    def InitInjuryCriterion(self, exclude_pids=(), thresholds=None):
+        ex = np.ascontiguousarray(exclude_pids, dtype=np.int32)
+        th = None if thresholds is None else np.ascontiguousarray(thresholds, dtype=np.float64)
+        self._check(self.L.ftb200_injury_begin(self._h, _i(ex) if len(ex) else None, len(ex), _d(th)))
+
+    def injury_end(self):
+        self._check(self.L.ftb200_injury_end(self._h))
+
+    def injury_results(self):
+        """dict with the reference's names: scalars (maxStrain, maxT, minStrain, minT, maxShear, maxShearT,
+        maxPSxSR, maxTimePSxSR, maxMPS95, maxTimeMPS95, maxMPSxSR95, maxTimeMPSxSR95), the four extreme elements,
+        per-element flags / PS_Old / PSxSRArray, the MPS-95 element lists and the flagged volumes."""
+        nE = self.nelements
+        sc, el = np.zeros(12), np.zeros(4, dtype=np.int32)
+        fl = np.zeros(nE, dtype=np.uint8)
+        ps, px, vol = np.zeros(nE), np.zeros(nE), np.zeros(5)
+        self._check(self.L.ftb200_injury_get(self._h, _d(sc), _i(el), fl.ctypes.data_as(C.POINTER(C.c_ubyte)), _d(ps),
+                                             _d(px), _d(vol)))
+        incl = (fl & 0x80) != 0
+        ids = np.nonzero(incl)[0].astype(np.int32)
+        return dict(scalars=sc, extreme_elems=el, flags=fl, elementIDInjury=ids, PS_Old=ps[incl], PSxSRArray=px[incl],
+                    MPSgt15=(fl[incl] & 1) != 0, MPSgt30=(fl[incl] & 2) != 0, MPSRgt120=(fl[incl] & 4) != 0,
+                    MPSxSRgt28=(fl[incl] & 8) != 0, maxElemListMPS95=np.nonzero(fl & 16)[0].astype(np.int32),
+                    maxElemListMPSxSR95=np.nonzero(fl & 32)[0].astype(np.int32), volumes=vol)
+
+    def injury_history(self, first, count):
+        a, b = np.zeros(count), np.zeros(count)
+        self._check(self.L.ftb200_injury_history(self._h, int(first), int(count), _d(a), _d(b)))
+        return a, b
+
     # --- resident path ---------------------------------------------------------------------------------
     def sync_in(self):
         self._check(self.L.ftb200_set_state(self._h, _d(self.displacements), _d(self.velocities),

@@ -182,6 +182,31 @@ int ftb200_profile_get(ftb200_ctx *ctx, double *elem_ms, double *node_ms, long l
  * and a STREAM-style fp64 copy (GB/s, read + write bytes).  Best of `reps` launches, CUDA-event timed. */
 int ftb200_measure_peaks(ftb200_ctx *ctx, int reps, double *fp64_tflops, double *copy_gbs);
 
+/* ---- injury criteria of the brain drivers (next row after the hot path: SURVEY.md 8(f).1) ---------------
+ * Device-resident restatement of examples/ex5/ex5.cpp:1251-1430 (InitInjuryCriterion, CalculateInjuryCriterions)
+ * over src/elements/ElementCalculations/CalculateStrain.cpp:8-75 (CalculateMaximumPrincipalStrain) and
+ * src/math/math.cpp:160-332 (compute95thPercentileValue).  Once begun, every step of the resident loop evaluates
+ * the criteria inside the element force kernel (F never leaves the chip) right after the step's energy check,
+ * as ex5.cpp:237-240 does.
+ * exclude_pids: parts left out (ex5's injuryExcludePID).  thresholds: NULL = the reference's 0.15, 0.30 (MPS),
+ * 120 1/s (MPSR), 28 1/s (MPSxSR), ex5.cpp:1335-1365.  Single partition only in this version (nranks == 1). */
+int ftb200_injury_begin(ftb200_ctx *ctx, const int *exclude_pids, int n_exclude, const double *thresholds4);
+int ftb200_injury_end(ftb200_ctx *ctx);
+/* Results so far.  scalars[12] = maxStrain, time, minStrain, time, maxShear, time, maxPSxSR, time, MPS-95, time,
+ * MPSxSR-95, time (ex5.cpp:62-83); extreme_elems[4] = the elements of the first four (caller's element ids);
+ * flags[nE]: bit0 MPS>thr0 (CSDM-15), bit1 MPS>thr1 (CSDM-30), bit2 MPSR>thr2, bit3 MPSxSR>thr3, bit4 in the
+ * MPS-95 element list, bit5 in the MPSxSR-95 list, bit7 element takes part; ps[nE], psxsr[nE] = PS_Old and
+ * PSxSRArray (0 for excluded elements); volumes[5] = reference-configuration volume with bit0, bit0&bit1, bit2,
+ * bit3 set and of all participating elements (ex5.cpp:1043-1066, Elements.cpp:30-38).  Pointers may be NULL. */
+int ftb200_injury_get(ftb200_ctx *ctx, double *scalars12, int *extreme_elems4, unsigned char *flags, double *ps,
+                      double *psxsr, double *volumes5);
+/* Per-step 95th-percentile values (needs ftb200_record_history before ftb200_injury_begin) */
+int ftb200_injury_history(ftb200_ctx *ctx, long long first, long long count, double *mps95, double *mpsxsr95);
+/* CalculateMaximumPrincipalStrain (CalculateStrain.cpp:8-75) of every element for the displacements now on the
+ * device: smax, smin, shear [nE] each (caller's element order), volume0[nE] = calculateVolume(e)
+ * (CalculateCentroidAndVolume.cpp:26-37).  Pointers may be NULL. */
+int ftb200_principal_strains(ftb200_ctx *ctx, double *smax, double *smin, double *shear, double *volume0);
+
 #ifdef __cplusplus
 }
 #endif

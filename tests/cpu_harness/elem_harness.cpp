@@ -16,6 +16,7 @@ struct HostHist {
 };
 struct HostOut {
   static constexpr bool enabled = true;
+  static constexpr bool want_S = true;
   double *F, *detF, *pk2;
   void put(int gp, const double Fm[3][3], double J, const double Sv[6]) const {
     for (int i = 0; i < 3; ++i)
@@ -45,4 +46,17 @@ extern "C" double harness_mass(const double* X24, double rho, double* me8) {
   for (int k = 0; k < 8; ++k)
     for (int c = 0; c < 3; ++c) X[k][c] = X24[3 * k + c];
   return ftb::hex8_lumped_mass(X, rho, me8);
+}
+
+// CalculateMaximumPrincipalStrain of one element: out = max, min, shear, then the 6 sums of F^T F
+extern "C" void harness_principal(const double* X24, const double* U24, double* out9) {
+  double X[8][3], U[8][3], fe[8][3], d;
+  for (int k = 0; k < 8; ++k)
+    for (int c = 0; c < 3; ++c) { X[k][c] = X24[3 * k + c]; U[k][c] = U24[3 * k + c]; }
+  double mp[ftb::FTB_MP_STRIDE] = {0};
+  double cs[6] = {0, 0, 0, 0, 0, 0};
+  ftb::LocalScratch sc;
+  ftb::hex8_element<0, false>(X, U, 0, mp, false, ftb::NoHistory(), ftb::StrainSink{cs}, sc, fe, &d);
+  ftb::principal_strains(cs, &out9[0], &out9[1], &out9[2]);
+  for (int i = 0; i < 6; ++i) out9[3 + i] = cs[i];
 }

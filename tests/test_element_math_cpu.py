@@ -30,6 +30,7 @@ def harness():
     L.harness_element.restype = C.c_int
     L.harness_mass.argtypes = [_dp, C.c_double, _dp]
     L.harness_mass.restype = C.c_double
+    L.harness_principal.argtypes = [_dp, _dp, _dp]
     return L
 
 
@@ -137,3 +138,52 @@ def test_lumped_mass_matches_oracle(harness):
         assert det > 0
         np.add.at(mass, conn[e], me)
     assert np.allclose(np.repeat(mass, 3), d["mass"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["inj6_p1", "inj6b_p1"])
+def test_principal_strains_match_reference(harness, name):
+    """principal_strains + StrainSink (what k_elem<..., WITH_INJ> runs) vs the reference's own
+    CalculateMaximumPrincipalStrain on the final state of the injury fixtures (PS_Old = max principal strain)."""
+    g = golden(name)
+    d = rank_dict(g, 0)
+    X = d["coordinates"].reshape(-1, 3)
+    U = d["displacements"].reshape(-1, 3)
+    conn = d["connectivity"].reshape(-1, 8)
+    Eavg = d["Eavg"].reshape(-1, 9)
+    ps = dict(zip(d["inj_elems"].tolist(), d["inj_ps_old"].tolist()))
+    worst = 0.0
+    for e in range(conn.shape[0]):
+        Xe = np.ascontiguousarray(X[conn[e]])
+        Ue = np.ascontiguousarray(U[conn[e]])
+        out = np.zeros(9)
+        harness.harness_principal(Xe.ctypes.data_as(_dp), Ue.ctypes.data_as(_dp), out.ctypes.data_as(_dp))
+        # E = (0.5/8) sum F^T F - 0.5 I against the reference's Eavg (column-major 3x3)
+        Em = Eavg[e].reshape(3, 3)
+        mine = 0.0625 * np.array([out[3], out[4], out[5], out[6], out[7], out[8]]) - np.array([0.5, 0.5, 0.5, 0, 0, 0])
+        want = np.array([Em[0, 0], Em[1, 1], Em[2, 2], Em[1, 2], Em[0, 2], Em[0, 1]])
+        assert np.max(np.abs(mine - want)) <= 1e-12 * max(1.0, np.max(np.abs(want)))
+        ev = np.linalg.eigvalsh(Em)
+        assert out[0] == pytest.approx(max(ev[-1], 0.0), rel=1e-9, abs=1e-12)
+        assert out[1] == pytest.approx(min(ev[0], 0.0), rel=1e-9, abs=1e-12)
+        assert out[2] == pytest.approx(0.5 * (ev[-1] - ev[0]), rel=1e-9, abs=1e-12)
+        if e in ps:
+            worst = max(worst, abs(out[0] - ps[e]) / max(abs(ps[e]), 1e-12))
+    assert worst <= 1e-9  # tolerance of the north star for strains
+
+
+def test_principal_strains_double_root_is_finite(harness):
+    """Uniaxial stretch along a skew axis: a double eigenvalue with non-zero off-diagonals.  The reference's acos
+    argument may round past 1 there (NaN -> it reports 0); the device formula clamps and returns the eigenvalues."""
+    n = np.array([1.0, 2.0, 2.0]) / 3.0
+    lam = 1.3
+    Fm = np.eye(3) + (lam - 1.0) * np.outer(n, n)
+    g = golden("inj6_p1")
+    conn = rank_dict(g, 0)["connectivity"].reshape(-1, 8)[0]
+    X = rank_dict(g, 0)["coordinates"].reshape(-1, 3)[conn]
+    X = np.ascontiguousarray(X)
+    U = np.ascontiguousarray(X @ Fm.T - X)
+    out = np.zeros(9)
+    harness.harness_principal(X.ctypes.data_as(_dp), U.ctypes.data_as(_dp), out.ctypes.data_as(_dp))
+    assert np.all(np.isfinite(out))
+    assert out[0] == pytest.approx(0.5 * (lam * lam - 1.0), rel=1e-7)
+    assert out[1] == 0.0 or abs(out[1]) < 1e-9
