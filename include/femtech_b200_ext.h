@@ -1,5 +1,5 @@
 /*
- * femtech_b200_ext.h -- the ONE addition to the reference's API that the resident mode needs.
+ * femtech_b200_ext.h -- the additions to the reference's API that the resident mode needs.
  *
  * The reference's ExplicitDynamics(double timeFinal, char *name) (include/FemTech.h:50) carries no boundary
  * condition: the shipped drivers apply it from a callback inside their own time loop
@@ -11,4 +11,15 @@
 #ifndef FEMTECH_B200_EXT_H
 #define FEMTECH_B200_EXT_H
 void femtech_b200_set_bc(const int *bc_kind, const double bc_rate[4], int energy_every);
+
+/* The brain drivers evaluate their injury criteria from a second callback in the same loop
+ * (examples/ex5/ex5.cpp:240 CalculateInjuryCriterions, :1251 InitInjuryCriterion; driver code, not library code).
+ * Resident mode: call femtech_b200_injury_begin() once after ShapeFunctions(); every step of ExplicitDynamics() then
+ * updates the criteria on the device; read them back with femtech_b200_injury_results() (arguments as
+ * ftb200_injury_get in ftb200.h: the driver's maxStrain/maxT/..., MPSgt15/.. as flag bits, PS_Old, PSxSRArray,
+ * flagged volumes).  Strict legacy drivers need nothing new: CalculateMaximumPrincipalStrain(e, ...) keeps its
+ * signature (include/FemTech.h:60) and is served from one device evaluation per force call. */
+void femtech_b200_injury_begin(const int *injuryExcludePID, int injuryExcludePIDCount);
+void femtech_b200_injury_results(double scalars12[12], int extreme_elems4[4], unsigned char *flags, double *PS_Old,
+                                 double *PSxSRArray, double volumes5[5]);
 #endif

@@ -4,7 +4,8 @@
 #   hot path       : integration/femtech_host.o  ->  libftb200.so (CUDA)
 #   everything else: the reference's own objects (readers, PartitionMesh, log, VTU, ParMETIS) from oracle/_ref
 # femtech_host.o comes first, so the archive members of the replaced translation units are never pulled.
-# Output: oracle/_ref/dropin_benchmarking_parallel, oracle/_ref/dropin_ex9 (git-ignored, travel with gpurun).
+# Output: oracle/_ref/dropin_benchmarking_parallel, dropin_ex9, dropin_ref_dump (the oracle harness driver, which
+# also exercises CalculateMaximumPrincipalStrain / the injury loop in legacy mode); git-ignored, travel with gpurun.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 ROOT="$HERE/.."
@@ -14,8 +15,9 @@ if [ ! -d "$REF/src" ] || [ ! -f "$OUT/libftref_fast.a" ]; then echo "build_drop
 PM="$REF/third-party/parmetis-4.0.3"
 INC="-I$ROOT/oracle/ref -I$OUT/gen -I$REF/include -I$OUT/jsoncpp-1.8.4/include -I$PM/include -I$PM/metis/include -I$ROOT/include"
 g++ -std=c++11 -O2 -w -fPIC $INC -c "$HERE/femtech_host.cpp" -o "$OUT/obj/femtech_host.o"
-for drv in benchmarking_parallel ex9; do
-  g++ -o "$OUT/dropin_$drv" "$OUT/obj/fast/driver_$drv.o" "$OUT/obj/femtech_host.o" "$OUT/libftref_fast.a" "$OUT/libftref_tp.a" \
+for drv in benchmarking_parallel ex9 ref_dump; do
+  obj="$OUT/obj/fast/driver_$drv.o"; [ "$drv" = ref_dump ] && obj="$OUT/obj/fast/ref_dump.o"
+  g++ -o "$OUT/dropin_$drv" "$obj" "$OUT/obj/femtech_host.o" "$OUT/libftref_fast.a" "$OUT/libftref_tp.a" \
       -L"$ROOT/femtech_b200" -lftb200 -Wl,-rpath,'$ORIGIN/../../femtech_b200' -lm
 done
 echo "build_dropin: done"

@@ -136,7 +136,9 @@ void LumpMassMatrix(void) { implicit_only("LumpMassMatrix"); }
 void updateMassMatrixNeighbour(void) { implicit_only("updateMassMatrixNeighbour"); }
 
 /* ---- src/fem/SolidMechanics/GetForce.cpp:12-25, GetForce_3D.cpp:5-53 ----------------------------------- */
+static unsigned long long g_state_gen = 1;   /* bumped whenever the device displacements change */
 void GetForce_3D() {
+  g_state_gen++;
   bool anyFe = false;
   for (int i = 0; i < nDOF && !anyFe; ++i) anyFe = fe[i] != 0.0;
   check(ftb200_get_force(g_ctx, displacements, anyFe ? fe : NULL, dt, fi, f_net));
@@ -191,6 +193,37 @@ void CalculateStrain() {
   check(ftb200_get_gp_outputs(g_ctx, F, detF, pk2, Eavg));
 }
 
+/* ---- CalculateStrain.cpp:8-75.  The brain drivers call this per element right after GetForce (ex5.cpp:1313-1317,
+ * :556); the device evaluates all elements in one launch and the per-element calls read the cached arrays until
+ * the next force evaluation.  Like the reference it leaves E of the element in Eavg. -------------------------- */
+static double *g_ps_max = NULL, *g_ps_min = NULL, *g_ps_shear = NULL;
+static unsigned long long g_ps_gen = 0;
+void CalculateMaximumPrincipalStrain(int elm, double *currentStrainMax, double *currentStrainMin, double *currentShearMax) {
+  if (g_ps_gen != g_state_gen) {
+    if (!g_ps_max) {
+      g_ps_max = (double *)malloc(sizeof(double) * nelements);
+      g_ps_min = (double *)malloc(sizeof(double) * nelements);
+      g_ps_shear = (double *)malloc(sizeof(double) * nelements);
+    }
+    check(ftb200_principal_strains(g_ctx, g_ps_max, g_ps_min, g_ps_shear, NULL));
+    check(ftb200_get_gp_outputs(g_ctx, NULL, NULL, NULL, Eavg));
+    g_ps_gen = g_state_gen;
+  }
+  *currentStrainMax = g_ps_max[elm];
+  *currentStrainMin = g_ps_min[elm];
+  *currentShearMax = g_ps_shear[elm];
+}
+
+/* Resident counterpart of InitInjuryCriterion / CalculateInjuryCriterions (ex5.cpp:1251-1430), femtech_b200_ext.h */
+void femtech_b200_injury_begin(const int *injuryExcludePID, int injuryExcludePIDCount) {
+  ensure_ctx();
+  check(ftb200_injury_begin(g_ctx, injuryExcludePID, injuryExcludePIDCount, NULL));
+}
+void femtech_b200_injury_results(double scalars12[12], int extreme_elems4[4], unsigned char *flags, double *PS_Old,
+                                 double *PSxSRArray, double volumes5[5]) {
+  check(ftb200_injury_get(g_ctx, scalars12, extreme_elems4, flags, PS_Old, PSxSRArray, volumes5));
+}
+
 /* ---- include/FemTech.h:50 -- a stub in the reference (src/fem/Solver/ExplicitDynamics.cpp:7-9); here the whole
  * loop of the drivers (Benchmarking-Parallel.cpp:83-171) resident on the GPU.  The driver's boundary-condition
  * callback becomes the descriptor set with femtech_b200_set_bc() (femtech_b200_ext.h). ---------------------- */
@@ -203,6 +236,7 @@ void femtech_b200_set_bc(const int *bc_kind, const double bc_rate[4], int energy
 void ExplicitDynamics(double timeFinal, char *name) {
   (void)name;
   ensure_ctx();
+  g_state_gen++;
   if (!g_bc_kind) { FILE_LOG_SINGLE(ERROR, "ExplicitDynamics: call femtech_b200_set_bc() first"); TerminateFemTech(3); }
   if (world_size > 1) { FILE_LOG_SINGLE(ERROR, "ExplicitDynamics: multi-GPU runs are driven by femtech_b200.dist"); TerminateFemTech(3); }
   check(ftb200_set_state(g_ctx, displacements, velocities, accelerations, boundary));
@@ -228,9 +262,11 @@ void FreeArrays() {
                   f_damp_prev, f_damp_curr, displacements_prev, F, pk2, pk2ptr, fptr, materialID, properties, detF, invF,
                   Eavg, detFptr, InternalsPtr, internals, GaussPoints, recvNodeDisplacement, sendProcessID,
                   sendNeighbourCount, sendNeighbourCountCum, sendNodeIndex, sendNodeDisplacement, stepTime, mat1, mat2,
-                  mat3, mat4, fintGQ, B, Hn_1, Hn_2, S0n, g_bc_kind};
+                  mat3, mat4, fintGQ, B, Hn_1, Hn_2, S0n, g_bc_kind, g_ps_max, g_ps_min, g_ps_shear};
   for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); ++i) free1DArray(ptrs[i]);
   g_bc_kind = NULL;
+  g_ps_max = g_ps_min = g_ps_shear = NULL;
+  g_ps_gen = 0;
   if (ElementType != NULL) {
     for (int i = 0; i < nelements; i++) free(ElementType[i]);
     free(ElementType);

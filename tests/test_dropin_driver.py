@@ -79,3 +79,29 @@ def dth0(o, X, kind, rate):
     m.ShapeFunctions()
     m.boundary[kind > 0] = 1
     return 0.8 * m.StableTimeStep()
+
+
+def test_legacy_injury_loop_through_reference_symbols(tmp_path):
+    """The oracle harness driver (oracle/ref/ref_dump.cpp: the drivers' time loop + ex5's injury loop, calling
+    CalculateMaximumPrincipalStrain / compute95thPercentileValue / computePartVolume by their reference names),
+    linked against femtech_b200 instead of the reference's hot path, vs the fixture the all-reference build wrote."""
+    exe = _need("dropin_ref_dump")
+    from conftest import golden, rank_dict
+    from oracle import pyoracle as po
+    g = golden("inj6_p1")
+    d = rank_dict(g, 0)
+    mesh.write_abaqus_inp(str(tmp_path / "cube6.inp"), d["coordinates"].reshape(-1, 3), d["connectivity"].reshape(-1, 8), d["pid"])
+    mesh.write_materials_dat(str(tmp_path / "materials.dat"), d["materialID"], d["properties"])
+    env = dict(os.environ, REF_INJURY_EXCLUDE=",".join(str(int(p)) for p in g["param_exclude"]))
+    r = subprocess.run([exe, "cube6.inp", "out", "400", repr(float(g["param_tMax"])), repr(float(g["param_dMax"]))],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    o = po.read_ref_dump(str(tmp_path / "out.rank0.bin"))
+    assert int(o["steps"][0]) == int(d["steps"][0])
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    assert rel(o["displacements"], d["displacements"]) < 1e-9
+    assert rel(o["inj_ps_old"], d["inj_ps_old"]) < 1e-9 and rel(o["inj_psxsr"], d["inj_psxsr"]) < 1e-6
+    for k in ("inj_elems", "inj_gt15", "inj_gt30", "inj_r120", "inj_xsr28", "inj_list95", "inj_listx95", "inj_extreme_elems"):
+        assert np.array_equal(o[k], d[k]), k
+    assert rel(o["inj_hist95"], d["inj_hist95"]) < 1e-9 and rel(o["inj_volumes"], d["inj_volumes"]) < 1e-12
+    assert rel(o["Eavg"], d["Eavg"]) < 1e-9
