@@ -171,6 +171,8 @@ def ours_single(args):
 
     # ---- device-resident timing (value) ---------------------------------------------------------
     m.explicit_begin(energy_every=energy)
+    if args.injury:  # not the headline: the brain drivers' per-step injury criteria on top of the same loop
+        m.InitInjuryCriterion()
     m.run_async(tMax, max(args.warmup, 3))
     torch.cuda.synchronize()
     stop, samples = threading.Event(), []
@@ -317,6 +319,7 @@ def ours_single(args):
         "config": {"workload": "synthetic %d^3 structured hex8 cube (%d elements, %d nodes), %s, benchmark BC "
                                "(Benchmarking-Parallel.cpp:184-244), %s, dt recomputed every step"
                                % (n, E, N, MAT_NAME[mat], "CheckEnergy every step" if energy else "no energy check"),
+                   "injury_criteria": bool(args.injury),
                    "mode": "resident ExplicitDynamics loop, CUDA graph of 25 steps, " +
                            ("one fused kernel per step" if prof["node_launches"] == 0 else "element + node kernels per step"),
                    "l2": "per-step working set %.2f GB > 126 MB L2, no flush needed" % ((b_elem + b_node) * E / 1e9)},
@@ -340,6 +343,7 @@ def main():
     ap.add_argument("--ref-n", type=int, default=40, help="edge of the bounded CPU sample")
     ap.add_argument("--no-energy", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--injury", action="store_true", help="also evaluate the injury criteria every step (ex5.cpp:240)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -230,14 +230,14 @@ cudaEvent_t prof_event(ftb200_ctx* ctx, size_t* idx) {
 }
 
 // CalculateInjuryCriterions (ex5.cpp:1311-1430) across elements, after k_adv has advanced Time: running extrema,
-// the two 95th-percentile selections (8 radix passes), the element lists.  INJ_LAUNCHES kernels.
-constexpr int INJ_LAUNCHES = 10;
+// the two 95th-percentile selections (INJ_PASSES radix passes), the element lists.  INJ_LAUNCHES kernels.
+constexpr int INJ_LAUNCHES = 2 + INJ_PASSES;
 void launch_injury(ftb200_ctx* ctx, cudaStream_t s) {
   const ElemArgs A = elem_args(ctx, 0, ctx->nE, 0);
-  LAUNCH(k_injury_reduce, INJ_BLOCKS, INJ_THREADS, s, A, ctx->ref_of, ctx->inj_state, ctx->inj_part, ctx->inj_parti);
+  LAUNCH(k_injury_reduce, std::min(INJ_BLOCKS, cdiv(ctx->nE, INJ_THREADS * 4)), INJ_THREADS, s, A, ctx->ref_of, ctx->inj_state, ctx->inj_part, ctx->inj_parti);
   double* h0 = ctx->inj_hist;
   double* h1 = ctx->inj_hist ? ctx->inj_hist + ctx->hist_cap : nullptr;
-  for (int pass = 0; pass < 8; ++pass) LAUNCH(k_injury_select, dim3(INJ_BLOCKS, 2), INJ_THREADS, s, A, ctx->inj_state, pass, h0, h1);
+  for (int pass = 0; pass < INJ_PASSES; ++pass) LAUNCH(k_injury_select, dim3(std::min(INJ_BLOCKS, cdiv(ctx->nE, INJ_THREADS * INJ_ITEMS)), 2), INJ_THREADS, s, A, ctx->inj_state, pass, h0, h1);
   LAUNCH(k_injury_lists, cdiv(ctx->nE, 256), 256, s, A, ctx->inj_state);
 }
 

@@ -116,6 +116,9 @@ struct ElemArgs {
 #endif
 constexpr int ELEM_BLOCK = FTB_ELEM_BLOCK;
 constexpr int ELEM_MINBLOCKS = FTB_ELEM_MINBLOCKS;
+#ifndef FTB_INJ_MINBLOCKS
+#define FTB_INJ_MINBLOCKS 5
+#endif
 
 // shared-memory scratch of hex8_element: [72][ELEM_BLOCK] doubles, thread t owns column t
 struct SmemScratch {
@@ -128,7 +131,7 @@ struct SmemScratch {
 // material 5 (36 history doubles per Gauss point in flight) and the generic per-element switch need more
 // registers than 168: they run with 4 resident blocks per SM instead of 6
 template <int MATSEL, bool WITH_FORCE, bool WITH_DT, bool WITH_INJ = false>
-__global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0 || WITH_INJ) ? 4 : ELEM_MINBLOCKS) k_elem(const ElemArgs A) {
+__global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : (WITH_INJ ? FTB_INJ_MINBLOCKS : ELEM_MINBLOCKS)) k_elem(const ElemArgs A) {
   const int e = A.e0 + blockIdx.x * ELEM_BLOCK + threadIdx.x;
   const size_t E = (size_t)A.nE;
   // the connectivity is requested before the loop-control flags are tested: one exposed latency, not two
@@ -1675,8 +1678,10 @@ __global__ void __launch_bounds__(256) k_energy_tiles(DevScalars* sc, StepCtl* c
 // Injury criteria of the brain drivers (examples/ex5/ex5.cpp:1311-1430), device side.  k_elem<..., WITH_INJ> leaves
 // the per-element quantities of the step; the kernels below do what the reference's loop does across elements:
 // running extrema with their element and time, the 95th-percentile values (math.cpp:160-199: the order statistic
-// (int)(0.95 n) - 1, found here by an 8-pass radix select on order-preserving keys -- a selection, so bit-exact),
+// (int)(0.95 n) - 1, found here by a 6-pass (11-bit digits) radix select on order-preserving keys -- a selection, so bit-exact),
 // and the element lists of the percentile maxima.
+constexpr int INJ_BINS = 2048;    // 11-bit digits: 6 passes over the 64-bit keys (the top pass has 9 bits)
+constexpr int INJ_PASSES = 6;
 struct InjState {
   double scal[12];  // maxStrain, maxT, minStrain, minT, maxShear, maxShearT, maxPSxSR, maxTimePSxSR, MPS95, t, MPSxSR95, t
   int elems[4];     // reference element ids of the four extrema (ex5.cpp:63,74)
@@ -1684,11 +1689,12 @@ struct InjState {
   unsigned red_done, sel_done[2];
   unsigned kth0, kth[2];
   unsigned long long prefix[2];
-  unsigned hist[2][256];
+  unsigned hist[2][INJ_BINS];
   int nIncluded, pad;
 };
-constexpr int INJ_BLOCKS = 296;  // 2 per SM
+constexpr int INJ_BLOCKS = 592;  // 4 per SM
 constexpr int INJ_THREADS = 256;
+constexpr int INJ_ITEMS = 8;      // elements per thread and loop trip, loaded before they are used
 
 struct InjCand { double v; int id; };
 // a beats b: strictly larger value, or the same value at a lower reference element id (the reference's loop keeps
@@ -1711,11 +1717,23 @@ __global__ void __launch_bounds__(INJ_THREADS) k_injury_reduce(const ElemArgs A,
   InjCand c[4];
 #pragma unroll
   for (int m = 0; m < 4; ++m) { c[m].v = -1.0; c[m].id = 0x7fffffff; }
-  for (int e = blockIdx.x * INJ_THREADS + threadIdx.x; e < A.nE; e += gridDim.x * INJ_THREADS) {
-    if (!A.inj_incl[e]) continue;
-    const int id = ref_of[e];
-    const InjCand n0{A.inj_ps[e], id}, n1{-A.inj_smin[e], id}, n2{A.inj_shear[e], id}, n3{A.inj_psxsr[e], id};
-    c[0] = inj_best(c[0], n0); c[1] = inj_best(c[1], n1); c[2] = inj_best(c[2], n2); c[3] = inj_best(c[3], n3);
+  for (int base = blockIdx.x * INJ_THREADS * 4 + threadIdx.x; base < A.nE; base += gridDim.x * INJ_THREADS * 4) {
+    double q[4][4];
+    int id[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // loads first
+      const int e = base + j * INJ_THREADS;
+      const bool on = e < A.nE && A.inj_incl[e];
+      id[j] = on ? ref_of[e] : -1;
+      q[j][0] = on ? A.inj_ps[e] : 0.0; q[j][1] = on ? -A.inj_smin[e] : 0.0;
+      q[j][2] = on ? A.inj_shear[e] : 0.0; q[j][3] = on ? A.inj_psxsr[e] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (id[j] < 0) continue;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) c[m] = inj_best(c[m], InjCand{q[j][m], id[j]});
+    }
   }
   __shared__ double sv[4][INJ_THREADS / 32];
   __shared__ int si[4][INJ_THREADS / 32];
@@ -1740,10 +1758,21 @@ __global__ void __launch_bounds__(INJ_THREADS) k_injury_reduce(const ElemArgs A,
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // final stage: the block partials, again by the order-independent "best" rule -> deterministic
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    InjCand b{-1.0, 0x7fffffff};
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += INJ_THREADS)
+      b = inj_best(b, InjCand{__ldcg(part + m * INJ_BLOCKS + k), __ldcg(parti + m * INJ_BLOCKS + k)});
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b = inj_best(b, inj_shfl(b, o));
+    if ((threadIdx.x & 31) == 0) { sv[m][threadIdx.x >> 5] = b.v; si[m][threadIdx.x >> 5] = b.id; }
+  }
+  __syncthreads();
   if (threadIdx.x < 4) {
     const int m = threadIdx.x;
-    InjCand b{-1.0, 0x7fffffff};
-    for (int k = 0; k < (int)gridDim.x; ++k) b = inj_best(b, InjCand{__ldcg(part + m * INJ_BLOCKS + k), __ldcg(parti + m * INJ_BLOCKS + k)});
+    InjCand b{sv[m][0], si[m][0]};
+    for (int w = 1; w < INJ_THREADS / 32; ++w) b = inj_best(b, InjCand{sv[m][w], si[m][w]});
     // running extremum with its element and time: `if (maxStrain < current)`, ex5.cpp:1318-1332,1350-1354
     const double cur = (m == 1) ? -st->scal[2] : st->scal[2 * m];
     if (b.id != 0x7fffffff && cur < b.v) {
@@ -1764,47 +1793,88 @@ __device__ __forceinline__ double inj_unkey(unsigned long long k) {
   return __longlong_as_double((long long)b);
 }
 
-// one digit (8 bits, most significant first) of the two selections: blockIdx.y = 0 MPS, 1 MPSxSR
+// one digit (most significant first) of the two selections: blockIdx.y = 0 MPS, 1 MPSxSR.  Pass p looks at bits
+// [shift, shift + width) with shift = 55, 44, 33, 22, 11, 0.  The strains of a step share their exponent, so the
+// leading digits are nearly constant: the histogram votes are aggregated per warp (__match_any_sync) before they
+// reach shared memory -- one atomic per distinct digit per warp instead of 32 colliding ones.
 __global__ void __launch_bounds__(INJ_THREADS) k_injury_select(const ElemArgs A, InjState* st, const int pass, double* hist95,
                                                                 double* histx95) {
   const DevScalars* sc = A.sc;
   if (!sc->active) return;
   const int arr = blockIdx.y;
   const double* data = arr ? A.inj_psxsr : A.inj_ps;
-  __shared__ unsigned h[256];
+  __shared__ unsigned h[INJ_BINS];
   __shared__ int s_last;
-  h[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < INJ_BINS; i += INJ_THREADS) h[i] = 0;
   __syncthreads();
-  const int shift = 56 - 8 * pass;
+  const int shift = 55 - 11 * pass;
   const unsigned long long prefix = st->prefix[arr];
-  for (int e = blockIdx.x * INJ_THREADS + threadIdx.x; e < A.nE; e += gridDim.x * INJ_THREADS) {
-    if (!A.inj_incl[e]) continue;
-    const unsigned long long k = inj_key(data[e]);
-    if (pass == 0 || ((k ^ prefix) >> (shift + 8)) == 0) atomicAdd(&h[(unsigned)(k >> shift) & 255u], 1u);
+  const int lane = threadIdx.x & 31;
+  const int nLoop = (A.nE + gridDim.x * INJ_THREADS * INJ_ITEMS - 1) / (gridDim.x * INJ_THREADS * INJ_ITEMS);
+  for (int it = 0; it < nLoop; ++it) {  // whole warps stay in the loop: __match_any_sync needs a full mask
+    const int base = (it * gridDim.x + blockIdx.x) * INJ_THREADS * INJ_ITEMS + threadIdx.x;
+    double v[INJ_ITEMS];
+    uint8_t in[INJ_ITEMS];
+#pragma unroll
+    for (int j = 0; j < INJ_ITEMS; ++j) {  // all loads in flight before the first vote
+      const int e = base + j * INJ_THREADS;
+      in[j] = e < A.nE ? A.inj_incl[e] : (uint8_t)0;
+      v[j] = e < A.nE ? data[e] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < INJ_ITEMS; ++j) {
+      unsigned d = 0xFFFFFFFFu;  // not a candidate
+      if (in[j]) {
+        const unsigned long long k = inj_key(v[j]);
+        if (pass == 0 || ((k ^ prefix) >> (shift + 11)) == 0) d = (unsigned)(k >> shift) & (INJ_BINS - 1);
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      if (d != 0xFFFFFFFFu && lane == __ffs(peers) - 1) atomicAdd(&h[d], (unsigned)__popc(peers));
+    }
   }
   __syncthreads();
-  if (h[threadIdx.x]) atomicAdd(&st->hist[arr][threadIdx.x], h[threadIdx.x]);
+  for (int i = threadIdx.x; i < INJ_BINS; i += INJ_THREADS)
+    if (h[i]) atomicAdd(&st->hist[arr][i], h[i]);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(&st->sel_done[arr], 1u) == gridDim.x - 1) ? 1 : 0;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  h[threadIdx.x] = __ldcg(&st->hist[arr][threadIdx.x]);
-  st->hist[arr][threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < INJ_BINS; i += INJ_THREADS) {
+    h[i] = __ldcg(&st->hist[arr][i]);
+    st->hist[arr][i] = 0;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned k = pass == 0 ? st->kth0 : st->kth[arr];
-    unsigned digit = 255;
-    for (unsigned i = 0; i < 256; ++i) {
-      if (k < h[i]) { digit = i; break; }
-      k -= h[i];
-    }
+  // the digit whose bucket holds rank k: 8 bins per thread, exclusive scan of the per-thread sums, then a local walk
+  constexpr int PER = INJ_BINS / INJ_THREADS;
+  __shared__ unsigned tsum[INJ_THREADS];
+  unsigned mine = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) mine += h[threadIdx.x * PER + j];
+  tsum[threadIdx.x] = mine;
+  __shared__ unsigned s_k0;
+  if (threadIdx.x == 0) s_k0 = pass == 0 ? st->kth0 : st->kth[arr];  // read once, before the owner rewrites it
+  __syncthreads();
+  for (int o = 1; o < INJ_THREADS; o <<= 1) {  // inclusive scan of the per-thread sums
+    const unsigned add = threadIdx.x >= o ? tsum[threadIdx.x - o] : 0u;
+    __syncthreads();
+    tsum[threadIdx.x] += add;
+    __syncthreads();
+  }
+  const unsigned k0 = s_k0;
+  const unsigned excl = tsum[threadIdx.x] - mine;
+  // exactly one thread owns rank k0 (the last one also catches an inconsistent count)
+  const bool owner = (k0 >= excl && k0 < excl + mine) || (threadIdx.x == INJ_THREADS - 1 && k0 >= tsum[INJ_THREADS - 1]);
+  if (owner) {
+    unsigned k = k0 - excl;
+    unsigned digit = threadIdx.x * PER;
+    for (int j = 0; j < PER - 1 && k >= h[digit]; ++j) { k -= h[digit]; ++digit; }
     const unsigned long long np = (pass == 0 ? 0ULL : prefix) | ((unsigned long long)digit << shift);
     st->prefix[arr] = np;
     st->kth[arr] = k;
     st->sel_done[arr] = 0;
-    if (pass == 7) {  // ex5.cpp:1372-1377 / :1402-1406
+    if (pass == INJ_PASSES - 1) {  // ex5.cpp:1372-1377 / :1402-1406
       const double v = inj_unkey(np);
       const long long i = sc->step - 1;
       double* hh = arr ? histx95 : hist95;
