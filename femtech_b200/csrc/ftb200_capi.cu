@@ -72,6 +72,9 @@ struct ftb200_ctx {
   int nTilesE = 0, nTilesN = 0, nChunks = 0;
   int elem_grid = 0, node_grid = 0;
   bool pipe = false;
+  bool fuse_adv = false;  // opt-in FTB200_FUSE_ADV=1: k_adv + k_energy folded into k_node's last block.  Measured slower
+                          // (k_node 98 -> 115 us at 100^3: every block pays a fence + atomic round trip) than the two
+                          // tiny kernels it saves (14 us), so the four-launch step stays the default.
   cudaEvent_t ev_elem[2] = {nullptr, nullptr};
   cudaGraphExec_t pgraph = nullptr;
   int pgraph_energy = -1;
@@ -189,6 +192,7 @@ NodeArgs node_args(ftb200_ctx* c, const double* recv) {
   A.halo_node_idx = recv ? c->halo_node_idx : nullptr;
   A.epart = c->epart; A.sc = c->sc; A.nN = c->nNp; A.nE = c->nE;
   A.store_fi = c->energy ? 1 : 0;
+  A.dt_hist = c->dthist; A.ehist = c->ehist; A.mp_rw = c->mp; A.nPID = c->nPID;
   A.halo_recv_alt = nullptr;
   A.p2p_seq = nullptr;
   return A;
@@ -248,13 +252,19 @@ void launch_step(ftb200_ctx* ctx, const double* recv) {
   if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
   launch_elem<true, true>(ctx, s, 0, ctx->nE, 0);
   if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.elem.push_back({i0, i1}); }
-  LAUNCH((k_adv<false>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, 0.0, ctx->dthist);
   const NodeArgs N = node_args(ctx, recv);
+  const bool adv_fused = ctx->nranks == 1 && !recv && ctx->fuse_adv;
+  if (!adv_fused) LAUNCH((k_adv<false>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, 0.0, ctx->dthist);
   if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
-  if (ctx->energy) LAUNCH((k_node<true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
-  else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+  if (adv_fused) {
+    if (ctx->energy) LAUNCH((k_node<true, true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
+    else LAUNCH((k_node<true, true, true, false, true>), ctx->node_blocks, NODE_BLOCK, s, N);
+  } else {
+    if (ctx->energy) LAUNCH((k_node<true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
+    else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+  }
   if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.node.push_back({i0, i1}); }
-  if (ctx->energy) LAUNCH(k_energy, 1, 256, s, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
+  if (ctx->energy && !adv_fused) LAUNCH(k_energy, 1, 256, s, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
   if (ctx->injury) launch_injury(ctx, s);
 }
 
@@ -748,6 +758,7 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       ctx->fused_grid = std::max(1, std::min(prop.multiProcessorCount * fb, cdiv(nE, ELEM_BLOCK)));
       ctx->fused = false;
       if (const char* ev = getenv("FTB200_FUSED")) ctx->fused = atoi(ev) != 0;
+      if (const char* ev = getenv("FTB200_FUSE_ADV")) ctx->fuse_adv = atoi(ev) != 0;
     }
     ctx->node_grid = std::max(1, std::min(prop.multiProcessorCount * nb, nTilesN));
   }
@@ -1303,7 +1314,8 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
     if (ctx->energy) LAUNCH((k_node<false, true, false, true>), ctx->node_blocks, NODE_BLOCK, s, N);
     else LAUNCH((k_node<false, true, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   }
-  const int per_step = 3 + (ctx->energy ? 1 : 0) + (ctx->injury ? INJ_LAUNCHES : 0);
+  const bool adv_fused = ctx->nranks == 1 && ctx->fuse_adv;
+  const int per_step = (adv_fused ? 2 : 3 + (ctx->energy ? 1 : 0)) + (ctx->injury ? INJ_LAUNCHES : 0);
   long long left = steps;
   const bool use_graph = !ctx->profile;  // built on the first run (warm-up), whatever its length
   if (use_graph) {

@@ -46,7 +46,7 @@ struct DevScalars {
   double bc_rate[4];
   long long hist_cap;               // capacity of dt/energy history (steps)
   int energy_every;
-  int pad;
+  unsigned node_done;               // k_node<..., ADV>: blocks finished (reset by the last one)
 };
 
 __device__ __forceinline__ unsigned long long dt_to_bits(double v) {
@@ -127,6 +127,33 @@ struct SmemScratch {
   __device__ __forceinline__ double ld(int i) const { return base[i * ELEM_BLOCK]; }
 };
 
+// Staged gather of k_elem: component 0 of X and u is loaded into registers, components 1 and 2 are copied
+// global -> shared with cp.async (no registers) into the column slots they will later overwrite, so all 48 gathers
+// of an element are in flight at once although only 16 values occupy registers.  (Left to itself ptxas sinks the
+// last third of the loads behind the first butterflies to save registers: a second exposed memory latency.)
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+struct StagedIn {
+  const double* x0;  // [8] component 0, registers
+  const double* u0;
+  double* base;      // &sm[0][threadIdx.x]
+  __device__ __forceinline__ void get(const int c, double nx[8], double nu[8]) const {
+    if (c == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { nx[k] = x0[k]; nu[k] = u0[k]; }
+    } else {
+      if (c == 1) asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        nx[k] = base[FTB_STAGE_SLOT(0, k, c) * ELEM_BLOCK];
+        nu[k] = base[FTB_STAGE_SLOT(1, k, c) * ELEM_BLOCK];
+      }
+    }
+  }
+};
+
 // K1 (+K6).  MATSEL >= 0: every element of the launch has that material (no switch).
 // material 5 (36 history doubles per Gauss point in flight) and the generic per-element switch need more
 // registers than 168: they run with 4 resident blocks per SM instead of 6
@@ -136,24 +163,44 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
   const size_t E = (size_t)A.nE;
   // the connectivity is requested before the loop-control flags are tested: one exposed latency, not two
   int nd[8];
+  int p = 0;
+  unsigned skip = 0;
   if (e < A.e1) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) nd[k] = __ldg(A.conn + (size_t)k * E + e);
+    p = __ldg(A.pid + e);                       // with the connectivity: the parameter block is a dependent load too
+    if (WITH_DT) skip = __ldg(A.eflag + e);     // element skipped by StableTimeStep (:13-19); not a late, exposed load
   }
   if (!A.ignore_loop_flags && (A.sc->last | A.sc->done)) return;
   __shared__ double sm_cols[WITH_FORCE ? 72 : 1][ELEM_BLOCK];
   double dte = 1e300;
   int status = 0;
   if (e < A.e1) {
-    double X[8][3], U[8][3];
+    double X0[8], U0[8];
+    double X[8][3], U[8][3];  // dt-only variant
+    if (WITH_FORCE) {
+      double* colbase = &sm_cols[0][threadIdx.x];
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        X[k][c] = __ldg(A.X[c] + nd[k]);
-        U[k][c] = __ldg(A.u[c] + nd[k]);
+      for (int k = 0; k < 8; ++k) {
+        X0[k] = __ldg(A.X[0] + nd[k]);
+        U0[k] = __ldg(A.u[0] + nd[k]);
       }
-    const int p = __ldg(A.pid + e);
+#pragma unroll
+      for (int c = 1; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          cp_async8(colbase + FTB_STAGE_SLOT(0, k, c) * ELEM_BLOCK, A.X[c] + nd[k]);
+          cp_async8(colbase + FTB_STAGE_SLOT(1, k, c) * ELEM_BLOCK, A.u[c] + nd[k]);
+        }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          X[k][c] = __ldg(A.X[c] + nd[k]);
+          U[k][c] = __ldg(A.u[c] + nd[k]);
+        }
+    }
     const double* mp = A.mp + (size_t)p * FTB_MP_STRIDE;
     const int mat = (MATSEL >= 0) ? MATSEL : (int)mp[MP_MATID];
     if (WITH_FORCE) {
@@ -164,7 +211,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
       if (WITH_INJ) {
         // strain/injury outputs fused into the force kernel: F never leaves the registers
         double cs[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        status = hex8_element<MATSEL, WITH_DT>(X, U, mat, mp, true, h, StrainSink{cs}, S, fe, &d);
+        status = hex8_element_in<MATSEL, WITH_DT>(StagedIn{X0, U0, S.base}, mat, mp, true, h, StrainSink{cs}, S, fe, &d);
         if (A.inj_incl[e]) {  // ex5.cpp:1313-1369, one element of the loop
           double smax, smin, shear;
           principal_strains(cs, &smax, &smin, &shear);
@@ -179,7 +226,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
           A.inj_ps[e] = smax; A.inj_psxsr[e] = PSxSR; A.inj_smin[e] = smin; A.inj_shear[e] = shear;
         }
       } else {
-        status = hex8_element<MATSEL, WITH_DT>(X, U, mat, mp, true, h, NoOutput(), S, fe, &d);
+        status = hex8_element_in<MATSEL, WITH_DT>(StagedIn{X0, U0, S.base}, mat, mp, true, h, NoOutput(), S, fe, &d);
       }
       if (WITH_DT) dte = d;
 #pragma unroll
@@ -200,7 +247,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
       }
       dte = hex_char_length(xm) / mp[MP_CE];
     }
-    if (WITH_DT && __ldg(A.eflag + e)) dte = 1e300;  // element skipped, StableTimeStep.cpp:13-19
+    if (WITH_DT && skip) dte = 1e300;
   }
   if (WITH_DT) {
     unsigned long long b = dt_to_bits(dte);
@@ -217,6 +264,10 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
 
 // ---------------------------------------------------------------------------------------------
 struct NodeArgs {
+  double* dt_hist;      // ADV only
+  double* ehist;        // ADV only
+  double* mp_rw;        // ADV only: parameter blocks (Prony factors)
+  int nPID;
   double* u[3];
   double* v[3];
   double* a[3];
@@ -244,12 +295,42 @@ constexpr int NODE_BLOCK = 256;
 
 // K2 + K5 (+ K8 partials).  FINISH: gather fi, a = (fe-fi)/m, second kick.  START: first kick of the
 // next step, drift, boundary condition.  KICK2 = false for step 0 (accelerations only).
-template <bool FINISH, bool START, bool KICK2, bool ENERGY>
+struct DevScalars;
+__device__ __forceinline__ double adv_step(DevScalars* sc, double* dt_hist);
+__device__ __forceinline__ void prony_update(double* mp, int nPID, double dt, int tid, int nthreads);
+// ADV (single-partition loop only): the scalar update of the time loop (k_adv) and the energy reduction (k_energy)
+// are folded into this kernel.  Every thread derives the times of the finished and of the next step from the same
+// read-only scalars k_adv would use; the block that finishes last writes them back, reduces the energy partials in
+// the fixed order of k_energy and refreshes the Prony factors.  Two launches per step instead of four.
+template <bool FINISH, bool START, bool KICK2, bool ENERGY, bool ADV = false>
 __global__ void __launch_bounds__(NODE_BLOCK) k_node(const NodeArgs A) {
-  const DevScalars* sc = A.sc;
-  if (FINISH && !sc->active) return;
-  if (!FINISH && sc->done) return;
-  const bool do_start = START && !(FINISH && sc->last);
+  DevScalars* sc = A.sc;
+  double c_tn, c_tnp1, c_thalf;            // step being finished
+  double n_tn, n_tnp1, n_thalf, n_dt;      // next step
+  bool last_new;
+  if (ADV) {
+    if (sc->done | sc->last) {  // dead iteration of a graph replay (k_adv: done <- last, active <- 0)
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (!sc->done) sc->done = 1;
+        sc->active = 0;
+      }
+      return;
+    }
+    double dtmin = __longlong_as_double((long long)sc->dtmin_bits);
+    if (dtmin > 1e20) dtmin = 1e20;
+    c_tn = sc->nt_n; c_tnp1 = sc->nt_np1; c_thalf = sc->nt_half;
+    n_dt = sc->reduction * dtmin;
+    n_tn = c_tnp1;
+    n_tnp1 = c_tnp1 + n_dt;
+    n_thalf = 0.5 * (n_tnp1 + n_tn);
+    last_new = (dtmin < sc->failure_dt) || !(c_tnp1 < sc->tMax) || (sc->steps_left - 1 <= 0);
+  } else {
+    if (FINISH && !sc->active) return;
+    if (!FINISH && sc->done) return;
+    c_tn = c_tnp1 = c_thalf = n_tn = n_tnp1 = n_thalf = n_dt = 0.0;  // read from sc where they are used
+    last_new = sc->last != 0;
+  }
+  const bool do_start = START && !(FINISH && last_new);
   const int n = blockIdx.x * NODE_BLOCK + threadIdx.x;
   double wke = 0.0, wint = 0.0, wext = 0.0;
   if (n < A.nN) {
@@ -287,7 +368,7 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_node(const NodeArgs A) {
         }
       }
       const double m = A.m[n];
-      const double dt1 = sc->t_half - sc->t_n, dt2 = sc->t_np1 - sc->t_half;
+      const double dt1 = ADV ? c_thalf - c_tn : sc->t_half - sc->t_n, dt2 = ADV ? c_tnp1 - c_thalf : sc->t_np1 - sc->t_half;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const bool b = (fl >> c) & 1u;
@@ -313,7 +394,7 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_node(const NodeArgs A) {
       }
     }
     if (do_start) {
-      const double dt1 = sc->nt_half - sc->nt_n, dtn = sc->ndt, T = sc->nt_np1;
+      const double dt1 = ADV ? n_thalf - n_tn : sc->nt_half - sc->nt_n, dtn = ADV ? n_dt : sc->ndt, T = ADV ? n_tnp1 : sc->nt_np1;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const bool b = (fl >> c) & 1u;
@@ -366,6 +447,69 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_node(const NodeArgs A) {
       A.epart[gridDim.x + blockIdx.x] = s1;
       A.epart[2 * gridDim.x + blockIdx.x] = s2;
     }
+  }
+  if (ADV) {
+    __shared__ int s_tail;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_tail = (atomicAdd(&sc->node_done, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_tail) return;
+    __threadfence();
+    __shared__ double s_ndt;
+    __shared__ double sh[3][NODE_BLOCK];
+    double s[3] = {0, 0, 0};
+    if (ENERGY) {  // k_energy's sums; four independent loads per operand in flight, fixed order
+      const int nblocks = gridDim.x;
+      int i = threadIdx.x;
+      for (; i + 3 * NODE_BLOCK < nblocks; i += 4 * NODE_BLOCK) {
+        double q[3][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          q[0][j] = __ldcg(A.epart + i + j * NODE_BLOCK);
+          q[1][j] = __ldcg(A.epart + nblocks + i + j * NODE_BLOCK);
+          q[2][j] = __ldcg(A.epart + 2 * nblocks + i + j * NODE_BLOCK);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s[0] += q[0][j]; s[1] += q[1][j]; s[2] += q[2][j]; }
+      }
+      for (; i < nblocks; i += NODE_BLOCK) {
+        s[0] += __ldcg(A.epart + i);
+        s[1] += __ldcg(A.epart + nblocks + i);
+        s[2] += __ldcg(A.epart + 2 * nblocks + i);
+      }
+    }
+    if (threadIdx.x == 0) {  // meanwhile: the scalar update of the loop
+      sc->node_done = 0;
+      sc->active = 1;
+      s_ndt = adv_step(sc, A.dt_hist);
+    }
+    if (ENERGY) {
+      sh[0][threadIdx.x] = s[0]; sh[1][threadIdx.x] = s[1]; sh[2][threadIdx.x] = s[2];
+      __syncthreads();
+      for (int o = NODE_BLOCK / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+          sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+          sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+          sh[2][threadIdx.x] += sh[2][threadIdx.x + o];
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) {
+        const double WKE = 0.5 * sh[0][0];
+        sc->Wint += 0.5 * sh[1][0];
+        sc->Wext += 0.5 * sh[2][0];
+        sc->WKE = WKE;
+        sc->Etot = fabs(WKE + sc->Wint - sc->Wext);
+        const long long k = sc->step - 1;
+        if (A.ehist && k >= 0 && k < sc->hist_cap) {
+          A.ehist[4 * k + 0] = sc->Wint; A.ehist[4 * k + 1] = sc->Wext; A.ehist[4 * k + 2] = WKE; A.ehist[4 * k + 3] = sc->Etot;
+        }
+      }
+    } else {
+      __syncthreads();
+    }
+    prony_update(A.mp_rw, A.nPID, s_ndt, threadIdx.x, NODE_BLOCK);
   }
 }
 

@@ -559,10 +559,35 @@ FTB_HD double hex_volume_modes(const double xm[7][3]) {
 // MATSEL: compile-time material id (1..5) when the whole launch is uniform,
 // or -1 for the generic per-element switch.  Returns status bits:
 // 1 = unknown material, 2 = non-positive det J0, 4 = non-finite / non-positive det F.
+// Nodal input of an element: get(c, nx, nu) delivers component c of the 8 reference coordinates and displacements.
+// ArrayIn reads plain arrays; the force kernel passes a staged source (k_elem) whose later components arrive
+// through shared memory.
+struct ArrayIn {
+  const double (*X)[3];
+  const double (*U)[3];
+  FTB_HD void get(const int c, double nx[8], double nu[8]) const {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { nx[k] = X[k][c]; nu[k] = U[k][c]; }
+  }
+};
+// scratch slot in which node k of component c is parked before that component's columns are built (the 24 column
+// slots of component c are free until then)
+#define FTB_STAGE_SLOT(f, k, c) FTB_COL(f, (k) >> 2, (k) & 3, c)
+
+template <int MATSEL, bool WITH_DT, class In, class Hist, class Out, class Scratch>
+FTB_HD int hex8_element_in(const In& in, int mat, const double* __restrict__ mp, const bool updHist, const Hist& hist,
+                           const Out& out, Scratch& S, double fe[8][3], double* dtElem);
+
 template <int MATSEL, bool WITH_DT, class Hist, class Out, class Scratch>
 FTB_HD int hex8_element(const double X[8][3], const double U[8][3], int mat, const double* __restrict__ mp,
                         const bool updHist, const Hist& hist, const Out& out, Scratch& S, double fe[8][3],
                         double* dtElem) {
+  return hex8_element_in<MATSEL, WITH_DT>(ArrayIn{X, U}, mat, mp, updHist, hist, out, S, fe, dtElem);
+}
+
+template <int MATSEL, bool WITH_DT, class In, class Hist, class Out, class Scratch>
+FTB_HD int hex8_element_in(const In& in, int mat, const double* __restrict__ mp, const bool updHist, const Hist& hist,
+                           const Out& out, Scratch& S, double fe[8][3], double* dtElem) {
   if (MATSEL >= 0) mat = MATSEL;
   const double a = FTB_GP_A, a2 = FTB_GP_A * FTB_GP_A;
   {
@@ -572,13 +597,10 @@ FTB_HD int hex8_element(const double X[8][3], const double U[8][3], int mat, con
     double xm[7][3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      double n[8], gX[7], gU[7];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) n[k] = X[k][c];
-      hex_modes(n, gX);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) n[k] = U[k][c];
-      hex_modes(n, gU);
+      double nx[8], nu[8], gX[7], gU[7];
+      in.get(c, nx, nu);
+      hex_modes(nx, gX);
+      hex_modes(nu, gU);
       if (WITH_DT) {
 #pragma unroll
         for (int m = 0; m < 7; ++m) xm[m][c] = gX[m] + gU[m];

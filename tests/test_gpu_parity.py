@@ -442,7 +442,7 @@ def test_injury_criteria_match_reference(name):
     # on-demand CalculateMaximumPrincipalStrain of the end state == PS_Old of the last step
     smax, smin, shear, vol = m.CalculateMaximumPrincipalStrain(volume=True)
     assert rel(smax[d["inj_elems"]], d["inj_ps_old"]) < TOL
-    assert m.gpu_launches >= 12 * steps
+    assert m.gpu_launches >= 10 * steps  # 2-4 step kernels + 8 for the criteria
     # switching the criteria off restores the plain loop
     m.injury_end()
     m.ExplicitDynamics(float(g["param_tMax"]) * 1.05, maxSteps=3)
