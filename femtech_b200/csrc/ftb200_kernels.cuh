@@ -635,7 +635,19 @@ __global__ void k_energy(DevScalars* sc, const double* epart, int nblocks, doubl
   if (!sc->active) return;
   __shared__ double sh[3][256];
   double s[3] = {0, 0, 0};
-  for (int i = threadIdx.x; i < nblocks; i += 256) {
+  int i = threadIdx.x;
+  for (; i + 3 * 256 < nblocks; i += 4 * 256) {  // four independent loads per operand in flight; same summation order
+    double q[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      q[0][j] = epart[i + j * 256];
+      q[1][j] = epart[nblocks + i + j * 256];
+      q[2][j] = epart[2 * nblocks + i + j * 256];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s[0] += q[0][j]; s[1] += q[1][j]; s[2] += q[2][j]; }
+  }
+  for (; i < nblocks; i += 256) {
     s[0] += epart[i];
     s[1] += epart[nblocks + i];
     s[2] += epart[2 * nblocks + i];
