@@ -1005,3 +1005,251 @@ void oracle_injury_volumes(const oracle_state *s, const oracle_injury *inj, doub
     out[4] += eV;
   }
 }
+
+/* ------------------------------------------------------------------------ */
+/* rigid-body prescribed motion (examples/ex5/ex5.cpp, src/math/math.cpp) */
+
+/* math.cpp:99-119 (the out-of-range error message is not reproduced) */
+double oracle_interpolateLinear(int n, const double *x, const double *y, double value) {
+  if (value < x[0]) return 0.0;
+  if (value > x[n - 1]) return y[n - 1];
+  if (value == x[0]) return y[0];
+  int index = 0;
+  for (int i = 1; i < n; ++i) {
+    if (value <= x[i]) { index = i - 1; break; }
+  }
+  const double yValue = y[index] + (y[index + 1] - y[index]) * (value - x[index]) / (x[index + 1] - x[index]);
+  return yValue;
+}
+/* math.cpp:50-54 */
+static void crossProduct(const double *a, const double *b, double *result) {
+  result[0] = a[1] * b[2] - a[2] * b[1];
+  result[1] = -a[0] * b[2] + a[2] * b[0];
+  result[2] = a[0] * b[1] - a[1] * b[0];
+}
+/* math.cpp:122-132 */
+void oracle_quaternionExp(const double *q1, double *q2) {
+  double vMag = q1[1] * q1[1] + q1[2] * q1[2] + q1[3] * q1[3];
+  if (vMag == 0) {
+    q2[0] = 1.0; q2[1] = 0.0; q2[2] = 0.0; q2[3] = 0.0;
+  } else {
+    vMag = sqrt(vMag);
+    const double d1 = exp(q1[0]);
+    const double d2 = d1 * sin(vMag) / vMag;
+    q2[0] = d1 * cos(vMag); q2[1] = d2 * q1[1]; q2[2] = d2 * q1[2]; q2[3] = d2 * q1[3];
+  }
+}
+/* math.cpp:134-139 */
+static void quaternionMultiply(const double *q1, const double *q2, double *qr) {
+  qr[0] = q1[0] * q2[0] - q1[1] * q2[1] - q1[2] * q2[2] - q1[3] * q2[3];
+  qr[1] = q1[0] * q2[1] + q1[1] * q2[0] + q1[2] * q2[3] - q1[3] * q2[2];
+  qr[2] = q1[0] * q2[2] - q1[1] * q2[3] + q1[2] * q2[0] + q1[3] * q2[1];
+  qr[3] = q1[0] * q2[3] + q1[1] * q2[2] - q1[2] * q2[1] + q1[3] * q2[0];
+}
+/* math.cpp:141-145 */
+static void quaternionInverse(const double *q, double *qinv) {
+  double norm = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  qinv[0] = q[0] / norm; qinv[1] = -q[1] / norm;
+  qinv[2] = -q[2] / norm; qinv[3] = -q[3] / norm;
+}
+/* math.cpp:154-158 */
+void oracle_quaternionRotate(const double *v, const double *R, const double *Rinv, double *vp) {
+  double Rv[4];
+  quaternionMultiply(R, v, Rv);
+  quaternionMultiply(Rv, Rinv, vp);
+}
+
+/* ex5.cpp:976-1020 */
+void oracle_computeDerivatives(const oracle_rigid *rb, const double *y, double *ydot, double t) {
+  ydot[0] = oracle_interpolateLinear(rb->size[0], rb->t[0], rb->v[0], t);
+  ydot[1] = oracle_interpolateLinear(rb->size[1], rb->t[1], rb->v[1], t);
+  ydot[2] = oracle_interpolateLinear(rb->size[2], rb->t[2], rb->v[2], t);
+  ydot[6] = oracle_interpolateLinear(rb->size[3], rb->t[3], rb->v[3], t);
+  ydot[7] = oracle_interpolateLinear(rb->size[4], rb->t[4], rb->v[4], t);
+  ydot[8] = oracle_interpolateLinear(rb->size[5], rb->t[5], rb->v[5], t);
+  ydot[9] = y[6];
+  ydot[10] = y[7];
+  ydot[11] = y[8];
+  double r[3];
+  r[0] = y[3]; r[1] = y[4]; r[2] = y[5];
+  double *rdot = &(ydot[3]);
+  double rMagnitude = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  if (rMagnitude < 1e-10) {
+    rdot[0] = 0.5 * y[0];
+    rdot[1] = 0.5 * y[1];
+    rdot[2] = 0.5 * y[2];
+  } else {
+    double rCotR = rMagnitude / tan(rMagnitude);
+    double omega[3]; omega[0] = y[0]; omega[1] = y[1]; omega[2] = y[2];
+    crossProduct(omega, r, rdot);
+    for (int i = 0; i < 3; ++i) r[i] = r[i] / rMagnitude;
+    double rDotOmega = r[0] * omega[0] + r[1] * omega[1] + r[2] * omega[2];
+    for (int i = 0; i < 3; ++i) rdot[i] = 0.5 * (rdot[i] + rCotR * y[i] + (1.0 - rCotR) * rDotOmega * r[i]);
+  }
+}
+
+/* boost/numeric/odeint/stepper/runge_kutta_dopri5.hpp, do_step_impl(system, in, dxdt_in, t, out, dxdt_out, dt) with
+ * in == out, dxdt_in == dxdt_out (what do_step(sys, x, dxdt, t, dt) does for an FSAL stepper).  Published
+ * Dormand-Prince coefficients; sums evaluated left to right as odeint's scale_sumN functors do.  UNPINNED (no Boost
+ * in this image). */
+void oracle_dopri5_step(const oracle_rigid *rb, double *x, double *dxdt, double t, double dt) {
+  const double a2 = 1.0 / 5.0, a3 = 3.0 / 10.0, a4 = 4.0 / 5.0, a5 = 8.0 / 9.0;
+  const double b21 = 1.0 / 5.0;
+  const double b31 = 3.0 / 40.0, b32 = 9.0 / 40.0;
+  const double b41 = 44.0 / 45.0, b42 = -56.0 / 15.0, b43 = 32.0 / 9.0;
+  const double b51 = 19372.0 / 6561.0, b52 = -25360.0 / 2187.0, b53 = 64448.0 / 6561.0, b54 = -212.0 / 729.0;
+  const double b61 = 9017.0 / 3168.0, b62 = -355.0 / 33.0, b63 = 46732.0 / 5247.0, b64 = 49.0 / 176.0,
+               b65 = -5103.0 / 18656.0;
+  const double c1 = 35.0 / 384.0, c3 = 500.0 / 1113.0, c4 = 125.0 / 192.0, c5 = -2187.0 / 6784.0, c6 = 11.0 / 84.0;
+  double xt[12], k2[12], k3[12], k4[12], k5[12], k6[12];
+  const double *k1 = dxdt;
+  for (int i = 0; i < 12; ++i) xt[i] = 1.0 * x[i] + dt * b21 * k1[i];
+  oracle_computeDerivatives(rb, xt, k2, t + dt * a2);
+  for (int i = 0; i < 12; ++i) xt[i] = 1.0 * x[i] + dt * b31 * k1[i] + dt * b32 * k2[i];
+  oracle_computeDerivatives(rb, xt, k3, t + dt * a3);
+  for (int i = 0; i < 12; ++i) xt[i] = 1.0 * x[i] + dt * b41 * k1[i] + dt * b42 * k2[i] + dt * b43 * k3[i];
+  oracle_computeDerivatives(rb, xt, k4, t + dt * a4);
+  for (int i = 0; i < 12; ++i)
+    xt[i] = 1.0 * x[i] + dt * b51 * k1[i] + dt * b52 * k2[i] + dt * b53 * k3[i] + dt * b54 * k4[i];
+  oracle_computeDerivatives(rb, xt, k5, t + dt * a5);
+  for (int i = 0; i < 12; ++i)
+    xt[i] = 1.0 * x[i] + dt * b61 * k1[i] + dt * b62 * k2[i] + dt * b63 * k3[i] + dt * b64 * k4[i] + dt * b65 * k5[i];
+  oracle_computeDerivatives(rb, xt, k6, t + dt);
+  for (int i = 0; i < 12; ++i)
+    xt[i] = 1.0 * x[i] + dt * c1 * k1[i] + dt * c3 * k3[i] + dt * c4 * k4[i] + dt * c5 * k5[i] + dt * c6 * k6[i];
+  for (int i = 0; i < 12; ++i) x[i] = xt[i];
+  oracle_computeDerivatives(rb, x, dxdt, t + dt);
+}
+
+static int cmp_int(const void *a, const void *b) { return (*(const int *)a - *(const int *)b); }
+
+/* ex5.cpp:819-911 */
+void oracle_InitRigidBoundary(oracle_state *s, oracle_rigid *rb) {
+  int rigidNodeCount = 0;
+  for (int i = 0; i < s->nElements; ++i)
+    if (s->materialID[s->pid[i]] == 0) rigidNodeCount += 8;
+  int *rigidNodeID = (int *)malloc((rigidNodeCount > 0 ? rigidNodeCount : 1) * sizeof(int));
+  int nodePtr = 0;
+  for (int i = 0; i < s->nElements; ++i)
+    if (s->materialID[s->pid[i]] == 0)
+      for (int j = 8 * i; j < 8 * i + 8; ++j) rigidNodeID[nodePtr++] = s->connectivity[j];
+  qsort(rigidNodeID, rigidNodeCount, sizeof(int), cmp_int);
+  for (int i = 0; i < rigidNodeCount; ++i) {
+    int index = rigidNodeID[i] * NDIM;
+    s->boundary[index] = 1;
+    s->boundary[index + 1] = 1;
+    s->boundary[index + 2] = 1;
+  }
+  free(rigidNodeID);
+  int idIndex = 0;
+  for (int i = 0; i < s->nNodes; ++i)
+    if (s->boundary[i * NDIM]) rb->boundaryID[idIndex++] = i;
+  rb->boundarySize = idIndex;
+  for (int j = 0; j < 12; ++j) { rb->y[j] = 0.0; rb->ydot[j] = 0.0; }
+  for (int i = 0; i < rb->boundarySize; i++) {
+    int index = rb->boundaryID[i] * NDIM;
+    for (int j = 0; j < NDIM; ++j) {
+      s->displacements[index + j] = 0.0;
+      s->velocities[index + j] = 0.0;
+      s->accelerations[index + j] = 0.0;
+    }
+  }
+}
+
+/* ex5.cpp:339-371 */
+void oracle_ApplyAccBoundaryConditions(oracle_state *s, oracle_rigid *rb, double Time, double dt) {
+  double r[4], R[4], Rinv[4], V[4], Vp[4];
+  double omegaR[3], omega[3], omegaOmegaR[3], omegaVel[3], vel[3];
+  double alpha[3], alphaR[3], locV[3];
+  double *yInt = rb->y, *ydotInt = rb->ydot;
+  oracle_dopri5_step(rb, yInt, ydotInt, Time - dt, dt);
+  r[0] = 0.0; r[1] = yInt[3]; r[2] = yInt[4]; r[3] = yInt[5];
+  oracle_quaternionExp(r, R);
+  quaternionInverse(R, Rinv);
+  omega[0] = yInt[0]; omega[1] = yInt[1]; omega[2] = yInt[2];
+  alpha[0] = ydotInt[0]; alpha[1] = ydotInt[1]; alpha[2] = ydotInt[2];
+  vel[0] = yInt[6]; vel[1] = yInt[7]; vel[2] = yInt[8];
+  for (int i = 0; i < rb->boundarySize; i++) {
+    int index = rb->boundaryID[i] * NDIM;
+    for (int j = 0; j < NDIM; ++j) locV[j] = s->coordinates[index + j];
+    V[0] = 0.0; V[1] = locV[0]; V[2] = locV[1]; V[3] = locV[2];
+    oracle_quaternionRotate(V, R, Rinv, Vp);
+    crossProduct(omega, &(Vp[1]), omegaR);
+    crossProduct(omega, omegaR, omegaOmegaR);
+    crossProduct(omega, vel, omegaVel);
+    crossProduct(alpha, &(Vp[1]), alphaR);
+    for (int j = 0; j < NDIM; ++j) {
+      s->displacements[index + j] = Vp[j + 1] - locV[j] + yInt[9 + j];
+      s->velocities[index + j] = omegaR[j] + yInt[6 + j];
+      s->accelerations[index + j] = 2.0 * omegaVel[j] + omegaOmegaR[j] + ydotInt[6 + j] + alphaR[j];
+    }
+  }
+}
+
+/* ex5.cpp:159-295 */
+int oracle_run_explicit_rigid(oracle_state *s, oracle_rigid *rb, double tMax, int maxSteps,
+                              double ExplicitTimeStepReduction, double FailureTimeStep, int first_call, double *dt_hist,
+                              double *energy_hist, oracle_injury *inj) {
+  double Time = s->Time, dt = s->dt;
+  const int nDOF = NDIM * s->nNodes;
+  if (first_call) {
+    double dtMin = oracle_StableTimeStep_local(s);
+    if (dtMin < FailureTimeStep) return -19;
+    dt = ExplicitTimeStepReduction * dtMin;
+    s->dt = dt;
+    if (oracle_GetForce_local(s)) return -1;
+    oracle_GetForce_finish(s);
+    oracle_CalculateAccelerations(s);
+  }
+  int steps = 0;
+  while (Time < tMax && steps < maxSteps) {
+    double t_n = Time;
+    double t_np1 = Time + dt;
+    Time = t_np1;
+    double dt_nphalf = dt;
+    double t_nphalf = 0.5 * (t_np1 + t_n);
+    if (dt_hist) dt_hist[steps] = dt;
+    s->Time = Time;
+    for (int i = 0; i < nDOF; i++) {
+      if (s->boundary[i]) s->velocities_half[i] = s->velocities[i];
+      else s->velocities_half[i] = s->velocities[i] + (t_nphalf - t_n) * s->accelerations[i];
+    }
+    memcpy(s->displacements_prev, s->displacements, nDOF * sizeof(double));
+    memcpy(s->accelerations_prev, s->accelerations, nDOF * sizeof(double));
+    memcpy(s->fi_prev, s->fi, nDOF * sizeof(double));
+    memcpy(s->fe_prev, s->fe, nDOF * sizeof(double));
+    for (int i = 0; i < nDOF; i++)
+      if (!s->boundary[i]) s->displacements[i] = s->displacements[i] + dt_nphalf * s->velocities_half[i];
+    oracle_ApplyAccBoundaryConditions(s, rb, Time, dt);
+    if (oracle_GetForce_local(s)) return -1;
+    oracle_GetForce_finish(s);
+    oracle_CalculateAccelerations(s);
+    for (int i = 0; i < nDOF; i++)
+      if (!s->boundary[i]) s->velocities[i] = s->velocities_half[i] + (t_np1 - t_nphalf) * s->accelerations[i];
+    {
+      double part[3];
+      oracle_CheckEnergy_local(s, part);
+      s->Wint_n += part[1];
+      s->Wext_n += part[2];
+      if (energy_hist) {
+        energy_hist[4 * steps + 0] = s->Wint_n;
+        energy_hist[4 * steps + 1] = s->Wext_n;
+        energy_hist[4 * steps + 2] = part[0];
+        energy_hist[4 * steps + 3] = fabs(part[0] + s->Wint_n - s->Wext_n);
+      }
+    }
+    if (inj) {
+      oracle_state *rs[1] = {s};
+      oracle_injury *ri[1] = {inj};
+      oracle_CalculateInjuryCriterions(rs, ri, 1, Time, dt);
+    }
+    steps++;
+    double dtMin = oracle_StableTimeStep_local(s);
+    if (dtMin < FailureTimeStep) { s->Time = Time; s->dt = dt; return -19; }
+    dt = ExplicitTimeStepReduction * dtMin;
+    s->dt = dt;
+  }
+  s->Time = Time;
+  s->dt = dt;
+  return steps;
+}

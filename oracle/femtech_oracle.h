@@ -145,6 +145,40 @@ int oracle_run_explicit_injury(oracle_state **ranks, int nranks, int *const *bc_
                                double tMax, int maxSteps, double ExplicitTimeStepReduction, double FailureTimeStep,
                                int first_call, double *dt_hist, double *energy_hist, oracle_injury **inj);
 
+/* ---- rigid-body prescribed-motion boundary condition of the brain drivers ----
+ * examples/ex5/ex5.cpp:339-371 (ApplyAccBoundaryConditions), :574-912 (InitBoundaryCondition), :976-1020
+ * (computeDerivatives), src/math/math.cpp:99-158 (interpolateLinear, quaternions).  The driver integrates 12 states
+ * y = [omega(3), r(3) = generator of the rotation quaternion, v(3), d(3)] with boost::numeric::odeint
+ * runge_kutta_dopri5::do_step(sys, y, ydot, Time - dt, dt) (FSAL form: ydot in = derivative at t, out = at t + dt).
+ * Boost is NOT in this image and not vendored by the reference (third-party/boost_1_71_0.zip is a missing blob):
+ * oracle_dopri5_step restates the published Dormand-Prince 5(4) tableau in Boost's evaluation order; parity of that
+ * one function is UNPINNED, everything around it is pinned against the reference library (quaternionExp,
+ * quaternionInverse, quaternionRotate, crossProduct, interpolateLinear via oracle/ref/ref_dump.cpp). */
+typedef struct oracle_rigid {
+  /* acceleration time traces, seconds / (rad/s^2 | m/s^2): index 0..2 angular x,y,z, 3..5 linear x,y,z */
+  int size[6];
+  const double *t[6];
+  const double *v[6];
+  double y[12], ydot[12];   /* yInt, ydotInt (ex5.cpp:105) */
+  int boundarySize;
+  int *boundaryID;          /* caller-owned, capacity nNodes */
+} oracle_rigid;
+double oracle_interpolateLinear(int n, const double *x, const double *y, double value);
+void oracle_quaternionExp(const double *q1, double *q2);
+void oracle_quaternionRotate(const double *v, const double *R, const double *Rinv, double *vp);
+void oracle_computeDerivatives(const oracle_rigid *rb, const double *y, double *ydot, double t);
+void oracle_dopri5_step(const oracle_rigid *rb, double *y, double *ydot, double t, double dt);
+/* ex5.cpp:819-911: boundary nodes = nodes of the elements whose part has material 0 (single rank: no neighbour
+ * exchange), all three dofs constrained, u = v = a = 0, y = ydot = 0 */
+void oracle_InitRigidBoundary(oracle_state *s, oracle_rigid *rb);
+/* ex5.cpp:339-371 with Time, dt of the driver */
+void oracle_ApplyAccBoundaryConditions(oracle_state *s, oracle_rigid *rb, double Time, double dt);
+/* The ex5 time loop (ex5.cpp:186-295): as oracle_run_explicit_injury with ApplyAccBoundaryConditions in place of
+ * the benchmark BC; single rank. */
+int oracle_run_explicit_rigid(oracle_state *s, oracle_rigid *rb, double tMax, int maxSteps,
+                              double ExplicitTimeStepReduction, double FailureTimeStep, int first_call, double *dt_hist,
+                              double *energy_hist, oracle_injury *inj);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,11 +30,22 @@ BRAIN = [1000.0, 2673.23, 2.189982178466e8, 25459.0, 0.0, 0.6521, 0.0129, 0.0067
 SOFT = [1040.0, 100.0, 100.0, 0, 0, 0, 0, 0, 0]  # examples/Benchmarking-Parallel/materials.dat:1
 
 
-def run_ref(meshfile, materialID, properties, nranks, maxSteps, tMax, dMax, cubeL=mesh.CUBE_L, injury_exclude=None):
+def write_rigid_tables(path, tables):
+    """6 lines `n t0 v0 t1 v1 ...`: angular x,y,z then linear x,y,z acceleration traces (s, SI), ref_dump REF_RIGID."""
+    with open(path, "w") as f:
+        for t, v in tables:
+            f.write("%d %s\n" % (len(t), " ".join("%.17g %.17g" % (a, b) for a, b in zip(t, v))))
+
+
+def run_ref(meshfile, materialID, properties, nranks, maxSteps, tMax, dMax, cubeL=mesh.CUBE_L, injury_exclude=None,
+            rigid_tables=None):
     work = tempfile.mkdtemp(prefix="ftgold_")
     env = dict(os.environ)
     if injury_exclude is not None:
         env["REF_INJURY_EXCLUDE"] = ",".join(str(p) for p in injury_exclude)
+    if rigid_tables is not None:
+        write_rigid_tables(os.path.join(work, "rigid.txt"), rigid_tables)
+        env["REF_RIGID"] = "rigid.txt"
     try:
         mesh.write_materials_dat(os.path.join(work, "materials.dat"), materialID, properties)
         cmd = [os.path.join(BIN, "ref_dump_exact"), meshfile, os.path.join(work, "out"), str(maxSteps),
@@ -83,13 +94,16 @@ def main():
     tmp = tempfile.mkdtemp(prefix="ftmesh_")
     ex = os.path.join(REF, "examples")
 
-    if only == "injury":
+    if only in ("injury", "rigid"):
         X, conn, pid = mesh.cube_mesh(6, jitter=0.05, nparts_z=3)
         f6 = os.path.join(tmp, "cube6mix.inp")
         mesh.write_abaqus_inp(f6, X, conn, pid)
     else:
         f6 = group_a_to_d(tmp, ex)
-    group_e(tmp, f6)
+    if only != "rigid":
+        group_e(tmp, f6)
+    if only != "injury":
+        group_f(tmp, f6)
     shutil.rmtree(tmp, ignore_errors=True)
 
 
@@ -129,6 +143,29 @@ def group_a_to_d(tmp, ex):
         save("cube6mix_p%d" % P, d, en[-1:], dict(tMax=0.004, dMax=0.007),
              MESH_KEYS + MAP_KEYS + STATE_KEYS + (GP_KEYS if P == 1 else []))
     return f6
+
+
+RIGID_TABLES = [  # (t[s], value): angular acceleration x,y,z [rad/s^2], linear acceleration x,y,z [m/s^2]
+    ([0.0, 0.002, 0.006], [0.0, 1.5e4, 0.0]), ([0.0, 0.002, 0.006], [0.0, -0.8e4, 0.0]),
+    ([0.0, 0.001, 0.003, 0.006], [0.0, 4.0e4, -1.0e4, 0.0]),
+    ([0.0, 0.002, 0.006], [0.0, 300.0, 0.0]), ([0.0, 0.002, 0.006], [0.0, 0.0, 0.0]), ([0.0, 0.003, 0.006], [0.0, -200.0, 0.0]),
+]
+
+
+def group_f(tmp, f6):
+    # (F) rigid-body prescribed motion of ex5 (ApplyAccBoundaryConditions): the first slab is a rigid part (material 0)
+    #     driven by acceleration traces, the others follow; injury criteria on, rigid part excluded
+    MED = [1040.0, 2.0e3, 2.0e4, 0, 0, 0, 0, 0, 0]
+    HGO_SOFT = [1000.0, 2.0e3, 2.0e4, 500.0, 10.0, 0, 0, 0, 0]
+    props = [1500.0, 0, 0, 0, 0, 0, 0, 0, 0] + MED + HGO_SOFT
+    d, en, _ = run_ref(f6, [0, 1, 4], props, 1, 400, 0.005, 0.0, injury_exclude=[0], rigid_tables=RIGID_TABLES)
+    params = dict(tMax=0.005, dMax=0.0, exclude=[0])
+    for k, (t, v) in enumerate(RIGID_TABLES):
+        params["rigid_t%d" % k] = t
+        params["rigid_v%d" % k] = v
+    save("rigid6_p1", d, en[-1:], params,
+         MESH_KEYS + ["steps", "Time", "dt", "dt_hist", "displacements", "velocities", "accelerations", "boundary", "fi", "pk2",
+                      "rb_y", "rb_ydot", "rb_boundaryID"] + INJ_KEYS)
 
 
 def group_e(tmp, f6):

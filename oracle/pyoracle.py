@@ -50,6 +50,12 @@ class OracleInjury(C.Structure):
     ]
 
 
+class OracleRigid(C.Structure):
+    """Mirror of `oracle_rigid` in femtech_oracle.h."""
+    _fields_ = [("size", C.c_int * 6), ("t", _dp * 6), ("v", _dp * 6), ("y", C.c_double * 12), ("ydot", C.c_double * 12),
+                ("boundarySize", C.c_int), ("boundaryID", _ip)]
+
+
 def build(fast=False):
     """Compile the oracle shared library if missing/stale; return its path."""
     name = "libfemtech_oracle_fast.so" if fast else "libfemtech_oracle.so"
@@ -98,6 +104,15 @@ def lib(fast=False):
         L.oracle_run_explicit_injury.argtypes = [C.POINTER(sp), C.c_int, C.POINTER(_ip), _dp, C.c_double, C.c_int,
                                                  C.c_double, C.c_double, C.c_int, _dp, _dp, C.POINTER(qp)]
         L.oracle_run_explicit_injury.restype = C.c_int
+        rp = C.POINTER(OracleRigid)
+        L.oracle_interpolateLinear.argtypes = [C.c_int, _dp, _dp, C.c_double]
+        L.oracle_interpolateLinear.restype = C.c_double
+        L.oracle_computeDerivatives.argtypes = [rp, _dp, _dp, C.c_double]
+        L.oracle_dopri5_step.argtypes = [rp, _dp, _dp, C.c_double, C.c_double]
+        L.oracle_InitRigidBoundary.argtypes = [sp, rp]
+        L.oracle_ApplyAccBoundaryConditions.argtypes = [sp, rp, C.c_double, C.c_double]
+        L.oracle_run_explicit_rigid.argtypes = [sp, rp, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, _dp, _dp, qp]
+        L.oracle_run_explicit_rigid.restype = C.c_int
         _libs[fast] = L
     return _libs[fast]
 
@@ -265,6 +280,55 @@ def injury_step(models, injuries, Time, dt):
     arr = (sp * P)(*[C.pointer(m.s) for m in models])
     qarr = (qp * P)(*[C.pointer(i.q) for i in injuries])
     models[0].L.oracle_CalculateInjuryCriterions(arr, qarr, P, Time, dt)
+
+
+class RigidBody:
+    """ex5.cpp:92-106: acceleration traces (6 x (t, v), angular x,y,z then linear x,y,z) + the integrator state."""
+
+    def __init__(self, model, tables):
+        self.model = model
+        self.rb = OracleRigid()
+        self.keep = []
+        for k, (t, v) in enumerate(tables):
+            t = np.ascontiguousarray(t, dtype=np.float64)
+            v = np.ascontiguousarray(v, dtype=np.float64)
+            self.keep += [t, v]
+            self.rb.size[k] = len(t)
+            self.rb.t[k] = _d(t)
+            self.rb.v[k] = _d(v)
+        self.bid = np.zeros(max(model.nNodes, 1), dtype=np.int32)
+        self.rb.boundaryID = _i(self.bid)
+        model.L.oracle_InitRigidBoundary(C.byref(model.s), C.byref(self.rb))
+
+    @property
+    def boundaryID(self):
+        return self.bid[:self.rb.boundarySize]
+
+    @property
+    def y(self):
+        return np.array(self.rb.y[:])
+
+    @property
+    def ydot(self):
+        return np.array(self.rb.ydot[:])
+
+    def step(self, t, dt):
+        """one dopri5 step of the 12 states from t to t + dt (ex5.cpp:344)"""
+        y, yd = np.array(self.rb.y[:]), np.array(self.rb.ydot[:])
+        self.model.L.oracle_dopri5_step(C.byref(self.rb), _d(y), _d(yd), t, dt)
+        for i in range(12):
+            self.rb.y[i], self.rb.ydot[i] = y[i], yd[i]
+
+
+def run_explicit_rigid(model, rigid, tMax, maxSteps, reduction=0.8, failure_dt=1e-11, first_call=True, injury=None):
+    """The ex5 loop (ex5.cpp:159-295), single rank.  Returns (steps, dt_hist, energy_hist)."""
+    dth, eh = np.zeros(max(maxSteps, 1)), np.zeros(4 * max(maxSteps, 1))
+    n = model.L.oracle_run_explicit_rigid(C.byref(model.s), C.byref(rigid.rb), tMax, maxSteps, reduction, failure_dt,
+                                          1 if first_call else 0, _d(dth), _d(eh),
+                                          C.byref(injury.q) if injury is not None else None)
+    if n >= 0:
+        return n, dth[:n].copy(), eh[:4 * n].reshape(n, 4).copy()
+    return n, None, None
 
 
 def halo_sum(models, field):

@@ -151,6 +151,114 @@ static void InjuryDump() {
   putd("inj_volume_part", volumePart.data(), nPIDglobal);
 }
 
+/* ---- rigid-body prescribed motion of the brain drivers (ex5.cpp:339-371,574-912,976-1020): driver code in the
+ * reference, restated here around the reference library's own quaternionExp / quaternionInverse / quaternionRotate /
+ * crossProduct / dotProduct3D / interpolateLinear.  The driver's integrator is boost::numeric::odeint's
+ * runge_kutta_dopri5 (Boost is neither in this image nor vendored): its do_step(sys, y, ydot, t, dt) is restated from
+ * the published Dormand-Prince tableau -- the one piece of this path that is NOT the reference's own code. */
+struct Rigid {
+  bool on = false;
+  std::vector<double> t[6], v[6];  // 0..2 angular x,y,z; 3..5 linear x,y,z (seconds, SI)
+  double y[12], ydot[12];
+  std::vector<int> boundaryID;
+} g_rb;
+
+static void rbDerivatives(const double *y, double *ydot, const double t) {  /* ex5.cpp:976-1020 */
+  for (int k = 0; k < 3; ++k) {
+    ydot[k] = interpolateLinear((int)g_rb.t[k].size(), g_rb.t[k].data(), g_rb.v[k].data(), t);
+    ydot[6 + k] = interpolateLinear((int)g_rb.t[3 + k].size(), g_rb.t[3 + k].data(), g_rb.v[3 + k].data(), t);
+    ydot[9 + k] = y[6 + k];
+  }
+  double r[3] = {y[3], y[4], y[5]};
+  double *rdot = &ydot[3];
+  double rMagnitude = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  if (rMagnitude < 1e-10) {
+    rdot[0] = 0.5 * y[0]; rdot[1] = 0.5 * y[1]; rdot[2] = 0.5 * y[2];
+  } else {
+    double rCotR = rMagnitude / tan(rMagnitude);
+    double omega[3] = {y[0], y[1], y[2]};
+    crossProduct(omega, r, rdot);
+    for (int i = 0; i < 3; ++i) r[i] = r[i] / rMagnitude;
+    double rDotOmega = dotProduct3D(r, omega);
+    for (int i = 0; i < 3; ++i) rdot[i] = 0.5 * (rdot[i] + rCotR * y[i] + (1.0 - rCotR) * rDotOmega * r[i]);
+  }
+}
+static void rbDopri5(double *x, double *dxdt, double t, double dt) {
+  static const double a2 = 1.0 / 5, a3 = 3.0 / 10, a4 = 4.0 / 5, a5 = 8.0 / 9, b21 = 1.0 / 5, b31 = 3.0 / 40, b32 = 9.0 / 40,
+                      b41 = 44.0 / 45, b42 = -56.0 / 15, b43 = 32.0 / 9, b51 = 19372.0 / 6561, b52 = -25360.0 / 2187,
+                      b53 = 64448.0 / 6561, b54 = -212.0 / 729, b61 = 9017.0 / 3168, b62 = -355.0 / 33, b63 = 46732.0 / 5247,
+                      b64 = 49.0 / 176, b65 = -5103.0 / 18656, c1 = 35.0 / 384, c3 = 500.0 / 1113, c4 = 125.0 / 192,
+                      c5 = -2187.0 / 6784, c6 = 11.0 / 84;
+  double xt[12], k2[12], k3[12], k4[12], k5[12], k6[12];
+  const double *k1 = dxdt;
+  for (int i = 0; i < 12; ++i) xt[i] = 1.0 * x[i] + dt * b21 * k1[i];
+  rbDerivatives(xt, k2, t + dt * a2);
+  for (int i = 0; i < 12; ++i) xt[i] = 1.0 * x[i] + dt * b31 * k1[i] + dt * b32 * k2[i];
+  rbDerivatives(xt, k3, t + dt * a3);
+  for (int i = 0; i < 12; ++i) xt[i] = 1.0 * x[i] + dt * b41 * k1[i] + dt * b42 * k2[i] + dt * b43 * k3[i];
+  rbDerivatives(xt, k4, t + dt * a4);
+  for (int i = 0; i < 12; ++i) xt[i] = 1.0 * x[i] + dt * b51 * k1[i] + dt * b52 * k2[i] + dt * b53 * k3[i] + dt * b54 * k4[i];
+  rbDerivatives(xt, k5, t + dt * a5);
+  for (int i = 0; i < 12; ++i)
+    xt[i] = 1.0 * x[i] + dt * b61 * k1[i] + dt * b62 * k2[i] + dt * b63 * k3[i] + dt * b64 * k4[i] + dt * b65 * k5[i];
+  rbDerivatives(xt, k6, t + dt);
+  for (int i = 0; i < 12; ++i) xt[i] = 1.0 * x[i] + dt * c1 * k1[i] + dt * c3 * k3[i] + dt * c4 * k4[i] + dt * c5 * k5[i] + dt * c6 * k6[i];
+  for (int i = 0; i < 12; ++i) x[i] = xt[i];
+  rbDerivatives(x, dxdt, t + dt);
+}
+static void RigidInit(const char *file) {  /* tables: 6 lines "n t0 v0 t1 v1 ..."; ex5.cpp:819-911 for the node set */
+  FILE *f = fopen(file, "r");
+  if (!f) { fprintf(stderr, "cannot open %s\n", file); TerminateFemTech(3); }
+  for (int k = 0; k < 6; ++k) {
+    int n = 0;
+    if (fscanf(f, "%d", &n) != 1) TerminateFemTech(3);
+    g_rb.t[k].resize(n); g_rb.v[k].resize(n);
+    for (int i = 0; i < n; ++i)
+      if (fscanf(f, "%lf %lf", &g_rb.t[k][i], &g_rb.v[k][i]) != 2) TerminateFemTech(3);
+  }
+  fclose(f);
+  g_rb.on = true;
+  for (int i = 0; i < nelements; ++i)
+    if (materialID[pid[i]] == 0)
+      for (int j = eptr[i]; j < eptr[i + 1]; ++j)
+        for (int c = 0; c < 3; ++c) boundary[connectivity[j] * ndim + c] = 1;
+  for (int i = 0; i < nNodes; ++i)
+    if (boundary[i * ndim]) g_rb.boundaryID.push_back(i);
+  for (int j = 0; j < 12; ++j) { g_rb.y[j] = 0.0; g_rb.ydot[j] = 0.0; }
+  for (size_t i = 0; i < g_rb.boundaryID.size(); ++i)
+    for (int j = 0; j < ndim; ++j) {
+      const int index = g_rb.boundaryID[i] * ndim + j;
+      displacements[index] = 0.0; velocities[index] = 0.0; accelerations[index] = 0.0;
+    }
+}
+static void ApplyAccBoundaryConditions() {  /* ex5.cpp:339-371 */
+  double r[4], R[4], Rinv[4], V[4], Vp[4];
+  double omegaR[3], omega[3], omegaOmegaR[3], omegaVel[3], vel[3], alpha[3], alphaR[3], locV[3];
+  double *yInt = g_rb.y, *ydotInt = g_rb.ydot;
+  rbDopri5(yInt, ydotInt, Time - dt, dt);
+  r[0] = 0.0; r[1] = yInt[3]; r[2] = yInt[4]; r[3] = yInt[5];
+  quaternionExp(r, R);
+  quaternionInverse(R, Rinv);
+  omega[0] = yInt[0]; omega[1] = yInt[1]; omega[2] = yInt[2];
+  alpha[0] = ydotInt[0]; alpha[1] = ydotInt[1]; alpha[2] = ydotInt[2];
+  vel[0] = yInt[6]; vel[1] = yInt[7]; vel[2] = yInt[8];
+  for (size_t i = 0; i < g_rb.boundaryID.size(); i++) {
+    int index = g_rb.boundaryID[i] * ndim;
+    for (int j = 0; j < ndim; ++j) locV[j] = coordinates[index + j];
+    V[0] = 0.0; V[1] = locV[0]; V[2] = locV[1]; V[3] = locV[2];
+    quaternionRotate(V, R, Rinv, Vp);
+    crossProduct(omega, &(Vp[1]), omegaR);
+    crossProduct(omega, omegaR, omegaOmegaR);
+    crossProduct(omega, vel, omegaVel);
+    crossProduct(alpha, &(Vp[1]), alphaR);
+    for (int j = 0; j < ndim; ++j) {
+      displacements[index + j] = Vp[j + 1] - locV[j] + yInt[9 + j];
+      velocities[index + j] = omegaR[j] + yInt[6 + j];
+      accelerations[index + j] = 2.0 * omegaVel[j] + omegaOmegaR[j] + ydotInt[6 + j] + alphaR[j];
+    }
+  }
+}
+
 /* Benchmarking-Parallel.cpp:184-244, cube side parametrised */
 static void ApplyBoundaryConditions(double dMax, double tMax) {
   double tol = 1e-5;
@@ -250,7 +358,8 @@ int main(int argc, char **argv) {
   AssembleLumpedMass();
   putd("mass", mass, nDOF);
 
-  ApplyBoundaryConditions(dMax, tMax);
+  if (const char *rf = getenv("REF_RIGID")) RigidInit(rf);  /* ex5.cpp:136 InitBoundaryCondition */
+  else ApplyBoundaryConditions(dMax, tMax);
   puti("boundary0", boundary, nDOF);
   dt = ExplicitTimeStepReduction * StableTimeStep();
   GetForce();
@@ -291,7 +400,8 @@ int main(int argc, char **argv) {
         displacements[i] = displacements[i] + dt_nphalf * velocities_half[i];
       }
     }
-    ApplyBoundaryConditions(dMax, tMax);
+    if (g_rb.on) ApplyAccBoundaryConditions();  /* ex5.cpp:222 */
+    else ApplyBoundaryConditions(dMax, tMax);
     GetForce();
     CalculateAccelerations();
     for (int i = 0; i < nDOF; i++) {
@@ -328,6 +438,10 @@ int main(int argc, char **argv) {
   putd("Hn_2", Hn_2, Hn_2 ? fptr[nelements] : 0);
   putd("S0n", S0n, S0n ? fptr[nelements] : 0);
   if (g_inj.on) InjuryDump();
+  if (g_rb.on) {
+    putd("rb_y", g_rb.y, 12); putd("rb_ydot", g_rb.ydot, 12);
+    puti("rb_boundaryID", g_rb.boundaryID.data(), (int64_t)g_rb.boundaryID.size());
+  }
   puts1("wall_setup_s", tSetup);
   puts1("wall_loop_s", tLoop);
   fclose(g_out);
