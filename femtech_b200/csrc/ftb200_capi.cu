@@ -37,6 +37,10 @@ struct ftb200_ctx {
   // host copies of the inputs
   std::vector<double> h_X;
   std::vector<int> h_conn, h_pid, h_matid;
+  // rigid-body prescribed motion (ftb200_set_rigid_bc)
+  DevRigid* rigid = nullptr;
+  double *rigid_tab = nullptr, *aprev[3] = {nullptr, nullptr, nullptr};
+  int rigid_count = 0;
   // injury criteria (ftb200_injury_begin)
   bool injury = false;
   double *inj_ps = nullptr, *inj_psxsr = nullptr, *inj_smin = nullptr, *inj_shear = nullptr, *inj_part = nullptr, *inj_hist = nullptr;
@@ -193,6 +197,8 @@ NodeArgs node_args(ftb200_ctx* c, const double* recv) {
   A.epart = c->epart; A.sc = c->sc; A.nN = c->nNp; A.nE = c->nE;
   A.store_fi = c->energy ? 1 : 0;
   A.dt_hist = c->dthist; A.ehist = c->ehist; A.mp_rw = c->mp; A.nPID = c->nPID;
+  for (int k = 0; k < 3; ++k) { A.X[k] = c->X[k]; A.aprev[k] = c->aprev[k]; }
+  A.rigid = c->rigid;
   A.halo_recv_alt = nullptr;
   A.p2p_seq = nullptr;
   return A;
@@ -253,8 +259,9 @@ void launch_step(ftb200_ctx* ctx, const double* recv) {
   launch_elem<true, true>(ctx, s, 0, ctx->nE, 0);
   if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.elem.push_back({i0, i1}); }
   const NodeArgs N = node_args(ctx, recv);
-  const bool adv_fused = ctx->nranks == 1 && !recv && ctx->fuse_adv;
+  const bool adv_fused = ctx->nranks == 1 && !recv && ctx->fuse_adv && !ctx->rigid;
   if (!adv_fused) LAUNCH((k_adv<false>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, 0.0, ctx->dthist);
+  if (ctx->rigid) LAUNCH(k_rigid_step, 1, 32, s, ctx->sc, ctx->rigid, 0);
   if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
   if (adv_fused) {
     if (ctx->energy) LAUNCH((k_node<true, true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
@@ -341,6 +348,7 @@ void free_all(ftb200_ctx* c) {
   }
   dfree(c->m); dfree(c->flags); dfree(c->conn); dfree(c->pid); dfree(c->ref_of); dfree(c->eflag);
   dfree(c->felem); dfree(c->hist); dfree(c->mp); dfree(c->node_off); dfree(c->node_ent); dfree(c->sc);
+  dfree(c->rigid); dfree(c->rigid_tab); dfree(c->aprev[0]); dfree(c->aprev[1]); dfree(c->aprev[2]);
   dfree(c->inj_ps); dfree(c->inj_psxsr); dfree(c->inj_smin); dfree(c->inj_shear); dfree(c->inj_part); dfree(c->inj_hist);
   dfree(c->inj_flags); dfree(c->inj_incl); dfree(c->inj_parti); dfree(c->inj_state);
   dfree(c->dthist); dfree(c->ehist); dfree(c->epart); dfree(c->out3); dfree(c->d_istage); dfree(c->d_big);
@@ -1133,6 +1141,7 @@ static void launch_step_p2p(ftb200_ctx* ctx) {
            ctx->d_sendNodeIndex, ctx->sc, ctx->nE);
   cudaStreamWaitEvent(s, ctx->ev_join, 0);
   LAUNCH(k_adv_p2p, 1, 128, s, ctx->p2p, ctx->sc, ctx->mp, ctx->nPID, ctx->dthist);
+  if (ctx->rigid) LAUNCH(k_rigid_step, 1, 32, s, ctx->sc, ctx->rigid, 0);
   NodeArgs N = node_args(ctx, ctx->halo_count ? p2p_recv(ctx->p2p_window, ctx->halo_count, 0) : nullptr);
   if (ctx->halo_count) {
     N.halo_recv_alt = p2p_recv(ctx->p2p_window, ctx->halo_count, 1);
@@ -1148,6 +1157,7 @@ static int run_async_p2p(ftb200_ctx* ctx, double tMax, long long steps) {
   LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
   {
     const NodeArgs N = node_args(ctx, nullptr);
+    if (ctx->rigid) LAUNCH(k_rigid_step, 1, 32, s, ctx->sc, ctx->rigid, 1);
     if (ctx->energy) LAUNCH((k_node<false, true, false, true>), ctx->node_blocks, NODE_BLOCK, s, N);
     else LAUNCH((k_node<false, true, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   }
@@ -1311,11 +1321,12 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
   LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
   {
     const NodeArgs N = node_args(ctx, nullptr);
+    if (ctx->rigid) LAUNCH(k_rigid_step, 1, 32, s, ctx->sc, ctx->rigid, 1);
     if (ctx->energy) LAUNCH((k_node<false, true, false, true>), ctx->node_blocks, NODE_BLOCK, s, N);
     else LAUNCH((k_node<false, true, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   }
-  const bool adv_fused = ctx->nranks == 1 && ctx->fuse_adv;
-  const int per_step = (adv_fused ? 2 : 3 + (ctx->energy ? 1 : 0)) + (ctx->injury ? INJ_LAUNCHES : 0);
+  const bool adv_fused = ctx->nranks == 1 && ctx->fuse_adv && !ctx->rigid;
+  const int per_step = (adv_fused ? 2 : 3 + (ctx->energy ? 1 : 0)) + (ctx->injury ? INJ_LAUNCHES : 0) + (ctx->rigid ? 1 : 0);
   long long left = steps;
   const bool use_graph = !ctx->profile;  // built on the first run (warm-up), whatever its length
   if (use_graph) {
@@ -1420,6 +1431,7 @@ int ftb200_run_begin(ftb200_ctx* ctx, double tMax, long long steps) {
   cudaStream_t s = ctx->stream;
   LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
   const NodeArgs N = node_args(ctx, nullptr);
+  if (ctx->rigid) LAUNCH(k_rigid_step, 1, 32, s, ctx->sc, ctx->rigid, 1);
   if (ctx->energy) LAUNCH((k_node<false, true, false, true>), ctx->node_blocks, NODE_BLOCK, s, N);
   else LAUNCH((k_node<false, true, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   return FTB200_OK;
@@ -1461,6 +1473,7 @@ int ftb200_step_end(ftb200_ctx* ctx, const double* recv_dev) {
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   LAUNCH((k_adv<false>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, 0.0, ctx->dthist);
+  if (ctx->rigid) LAUNCH(k_rigid_step, 1, 32, s, ctx->sc, ctx->rigid, 0);
   const NodeArgs N = node_args(ctx, ctx->halo_count ? recv_dev : nullptr);
   if (ctx->energy) LAUNCH((k_node<true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
   else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
@@ -1649,6 +1662,86 @@ static void drop_graphs(ftb200_ctx* ctx) {
   if (ctx->fgraph) { cudaGraphExecDestroy(ctx->fgraph); ctx->fgraph = nullptr; }
   if (ctx->pgraph) { cudaGraphExecDestroy(ctx->pgraph); ctx->pgraph = nullptr; }
 }
+
+// ----------------------------------------------------------------------------------- rigid-body BC
+__global__ void k_rigid_mark(const int* __restrict__ ids, int n, const int* __restrict__ nint, uint16_t* flags, double* ux,
+                             double* uy, double* uz, double* vx, double* vy, double* vz, double* ax, double* ay, double* az) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = nint[ids[i]];
+  flags[k] = (uint16_t)(flags[k] | 7u | FTB_FLAG_RIGID);  // boundary on x, y, z (ex5.cpp:849-854)
+  ux[k] = uy[k] = uz[k] = 0.0; vx[k] = vy[k] = vz[k] = 0.0; ax[k] = ay[k] = az[k] = 0.0;  // :901-908
+}
+
+int ftb200_set_rigid_bc(ftb200_ctx* ctx, const int sizes[6], const double* const t[6], const double* const v[6],
+                        const int* boundaryID, int boundarySize) {
+  if (!ctx || !ctx->shape_ok || !sizes || !t || !v) return fail(ctx, FTB200_ERR_INPUT, "set_rigid_bc: setup incomplete or bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  DevRigid h;
+  memset(&h, 0, sizeof(h));
+  int total = 0;
+  for (int k = 0; k < 6; ++k) {
+    if (sizes[k] < 2 || !t[k] || !v[k]) return fail(ctx, FTB200_ERR_INPUT, "set_rigid_bc: trace %d needs at least two points", k);
+    h.size[k] = sizes[k]; h.off[k] = total; total += sizes[k];
+  }
+  std::vector<double> tab(2 * (size_t)total);
+  for (int k = 0; k < 6; ++k)
+    for (int i = 0; i < sizes[k]; ++i) { tab[h.off[k] + i] = t[k][i]; tab[total + h.off[k] + i] = v[k][i]; }
+  // node set: given, or the nodes of the elements of rigid parts (material 0), ex5.cpp:819-846
+  std::vector<int> ids;
+  if (boundaryID) {
+    ids.assign(boundaryID, boundaryID + boundarySize);
+    for (int id : ids) if (id < 0 || id >= ctx->nN) return fail(ctx, FTB200_ERR_INPUT, "set_rigid_bc: node %d out of range", id);
+  } else {
+    std::vector<uint8_t> mark(ctx->nN, 0);
+    for (int e = 0; e < ctx->nE; ++e)
+      if (ctx->h_matid[ctx->h_pid[e]] == 0)
+        for (int k = 0; k < 8; ++k) mark[ctx->h_conn[8 * (size_t)e + k]] = 1;
+    for (int n = 0; n < ctx->nN; ++n) if (mark[n]) ids.push_back(n);
+  }
+  int rc;
+  dfree(ctx->rigid_tab);
+  if ((rc = dalloc(ctx, &ctx->rigid_tab, 2 * (size_t)total))) return rc;
+  CK(cudaMemcpy(ctx->rigid_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  h.tab_t = ctx->rigid_tab; h.tab_v = ctx->rigid_tab + total;
+  h.R[0] = h.Rinv[0] = 1.0;
+  if (!ctx->rigid && (rc = dalloc(ctx, &ctx->rigid, 1))) return rc;
+  CK(cudaMemcpy(ctx->rigid, &h, sizeof(h), cudaMemcpyHostToDevice));
+  for (int k = 0; k < 3; ++k) {
+    if (!ctx->aprev[k] && (rc = dalloc(ctx, &ctx->aprev[k], (size_t)ctx->nNp))) return rc;
+    CK(cudaMemset(ctx->aprev[k], 0, (size_t)ctx->nNp * sizeof(double)));
+  }
+  ctx->rigid_count = (int)ids.size();
+  if (!ids.empty()) {
+    if ((rc = ensure_big(ctx, (ids.size() + (size_t)ctx->nN) * sizeof(int) + 16))) return rc;
+    int* d_ids = reinterpret_cast<int*>(ctx->d_big);
+    int* d_nint = d_ids + ids.size();
+    CK(cudaMemcpy(d_ids, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_nint, ctx->h_nint.data(), (size_t)ctx->nN * sizeof(int), cudaMemcpyHostToDevice));
+    LAUNCH(k_rigid_mark, cdiv((int)ids.size(), 256), 256, ctx->stream, d_ids, (int)ids.size(), d_nint, ctx->flags, ctx->u[0], ctx->u[1],
+           ctx->u[2], ctx->v[0], ctx->v[1], ctx->v[2], ctx->a[0], ctx->a[1], ctx->a[2]);
+    LAUNCH(k_eflag, cdiv(ctx->nE, 256), 256, ctx->stream, ctx->conn, ctx->flags, ctx->eflag, ctx->nE);
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->fused = false; ctx->pipe = false;
+  drop_graphs(ctx);
+  ctx->bc_ok = true;
+  return FTB200_OK;
+}
+
+int ftb200_get_rigid_state(ftb200_ctx* ctx, double* y12, double* ydot12, int* boundary_count) {
+  if (!ctx || !ctx->rigid) return fail(ctx, FTB200_ERR_INPUT, "get_rigid_state: call set_rigid_bc first");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  DevRigid h;
+  CK(cudaMemcpy(&h, ctx->rigid, sizeof(h), cudaMemcpyDeviceToHost));
+  if (y12) for (int i = 0; i < 12; ++i) y12[i] = h.y[i];
+  if (ydot12) for (int i = 0; i < 12; ++i) ydot12[i] = h.ydot[i];
+  if (boundary_count) *boundary_count = ctx->rigid_count;
+  return FTB200_OK;
+}
+
 
 int ftb200_injury_begin(ftb200_ctx* ctx, const int* exclude_pids, int n_exclude, const double* thresholds4) {
   if (!ctx || !ctx->shape_ok || n_exclude < 0 || (n_exclude && !exclude_pids))

@@ -29,6 +29,7 @@ namespace ftb {
 #define FTB_FLAG_SHARED 0x1000
 #define FTB_FLAG_NOTOWNED 0x2000
 #define FTB_FLAG_OVERFLOW 0x4000  // node has more than 8 elements: entries 9.. are read from the CSR arrays
+#define FTB_FLAG_RIGID 0x0400     // bit 10: node follows the prescribed rigid-body motion (k_rigid_step, DevRigid)
 
 struct DevScalars {
   double Time;                      // end time of the last finished step
@@ -263,7 +264,114 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Rigid-body prescribed motion of the brain drivers (examples/ex5/ex5.cpp:339-371, :976-1020).
+// 12 states y = [omega, r (generator of the rotation quaternion), v, d] driven by six acceleration traces, advanced
+// once per time step by one thread with the Dormand-Prince 5(4) step that boost::odeint's runge_kutta_dopri5 takes in
+// do_step(sys, y, ydot, Time - dt, dt) (FSAL: ydot in = derivative at t, out = at t + dt); the kinematics of the
+// step then sit in this struct and k_node applies them to the flagged nodes.
+struct DevRigid {
+  double y[12], ydot[12];
+  double R[4], Rinv[4];
+  double omega[3], alpha[3], vel[3], acc[3], disp[3];
+  int size[6], off[6];   // trace k occupies tab_t/tab_v[off[k] .. off[k] + size[k])
+  const double* tab_t;
+  const double* tab_v;
+};
+__device__ inline double rb_interp(const DevRigid* rb, int k, double value) {  // math.cpp:99-119
+  const int n = rb->size[k];
+  const double* x = rb->tab_t + rb->off[k];
+  const double* y = rb->tab_v + rb->off[k];
+  if (value < x[0]) return 0.0;
+  if (value > x[n - 1]) return y[n - 1];
+  if (value == x[0]) return y[0];
+  int index = 0;
+  for (int i = 1; i < n; ++i)
+    if (value <= x[i]) { index = i - 1; break; }
+  return y[index] + (y[index + 1] - y[index]) * (value - x[index]) / (x[index + 1] - x[index]);
+}
+__device__ inline void rb_cross(const double* a, const double* b, double* r) {  // math.cpp:50-54
+  r[0] = a[1] * b[2] - a[2] * b[1];
+  r[1] = -a[0] * b[2] + a[2] * b[0];
+  r[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ inline void rb_qmul(const double* q1, const double* q2, double* qr) {  // math.cpp:134-139
+  qr[0] = q1[0] * q2[0] - q1[1] * q2[1] - q1[2] * q2[2] - q1[3] * q2[3];
+  qr[1] = q1[0] * q2[1] + q1[1] * q2[0] + q1[2] * q2[3] - q1[3] * q2[2];
+  qr[2] = q1[0] * q2[2] - q1[1] * q2[3] + q1[2] * q2[0] + q1[3] * q2[1];
+  qr[3] = q1[0] * q2[3] + q1[1] * q2[2] - q1[2] * q2[1] + q1[3] * q2[0];
+}
+__device__ inline void rb_derivatives(const DevRigid* rb, const double* y, double* ydot, double t) {  // ex5.cpp:976-1020
+  for (int k = 0; k < 3; ++k) {
+    ydot[k] = rb_interp(rb, k, t);
+    ydot[6 + k] = rb_interp(rb, 3 + k, t);
+    ydot[9 + k] = y[6 + k];
+  }
+  double r[3] = {y[3], y[4], y[5]};
+  double* rdot = &ydot[3];
+  const double rMagnitude = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  if (rMagnitude < 1e-10) {
+    rdot[0] = 0.5 * y[0]; rdot[1] = 0.5 * y[1]; rdot[2] = 0.5 * y[2];
+  } else {
+    const double rCotR = rMagnitude / tan(rMagnitude);
+    const double omega[3] = {y[0], y[1], y[2]};
+    rb_cross(omega, r, rdot);
+    for (int i = 0; i < 3; ++i) r[i] = r[i] / rMagnitude;
+    const double rDotOmega = r[0] * omega[0] + r[1] * omega[1] + r[2] * omega[2];
+    for (int i = 0; i < 3; ++i) rdot[i] = 0.5 * (rdot[i] + rCotR * y[i] + (1.0 - rCotR) * rDotOmega * r[i]);
+  }
+}
+// begin = 1: before the START of a run's first step (skipped when the run is already done);
+// begin = 0: after k_adv, before k_node's START of the next step (skipped on a dead or last iteration)
+__global__ void k_rigid_step(const DevScalars* sc, DevRigid* rb, const int begin) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (begin ? (sc->done != 0) : (!sc->active || sc->last)) return;
+  const double t = sc->nt_n, dt = sc->ndt;  // ex5.cpp:344: from Time - dt over dt
+  const double a2 = 1.0 / 5.0, a3 = 3.0 / 10.0, a4 = 4.0 / 5.0, a5 = 8.0 / 9.0;
+  const double b21 = 1.0 / 5.0, b31 = 3.0 / 40.0, b32 = 9.0 / 40.0, b41 = 44.0 / 45.0, b42 = -56.0 / 15.0, b43 = 32.0 / 9.0;
+  const double b51 = 19372.0 / 6561.0, b52 = -25360.0 / 2187.0, b53 = 64448.0 / 6561.0, b54 = -212.0 / 729.0;
+  const double b61 = 9017.0 / 3168.0, b62 = -355.0 / 33.0, b63 = 46732.0 / 5247.0, b64 = 49.0 / 176.0, b65 = -5103.0 / 18656.0;
+  const double c1 = 35.0 / 384.0, c3 = 500.0 / 1113.0, c4 = 125.0 / 192.0, c5 = -2187.0 / 6784.0, c6 = 11.0 / 84.0;
+  double x[12], k1[12], xt[12], k2[12], k3[12], k4[12], k5[12], k6[12];
+  for (int i = 0; i < 12; ++i) { x[i] = rb->y[i]; k1[i] = rb->ydot[i]; }
+  for (int i = 0; i < 12; ++i) xt[i] = x[i] + dt * b21 * k1[i];
+  rb_derivatives(rb, xt, k2, t + dt * a2);
+  for (int i = 0; i < 12; ++i) xt[i] = x[i] + dt * b31 * k1[i] + dt * b32 * k2[i];
+  rb_derivatives(rb, xt, k3, t + dt * a3);
+  for (int i = 0; i < 12; ++i) xt[i] = x[i] + dt * b41 * k1[i] + dt * b42 * k2[i] + dt * b43 * k3[i];
+  rb_derivatives(rb, xt, k4, t + dt * a4);
+  for (int i = 0; i < 12; ++i) xt[i] = x[i] + dt * b51 * k1[i] + dt * b52 * k2[i] + dt * b53 * k3[i] + dt * b54 * k4[i];
+  rb_derivatives(rb, xt, k5, t + dt * a5);
+  for (int i = 0; i < 12; ++i)
+    xt[i] = x[i] + dt * b61 * k1[i] + dt * b62 * k2[i] + dt * b63 * k3[i] + dt * b64 * k4[i] + dt * b65 * k5[i];
+  rb_derivatives(rb, xt, k6, t + dt);
+  for (int i = 0; i < 12; ++i) x[i] = x[i] + dt * c1 * k1[i] + dt * c3 * k3[i] + dt * c4 * k4[i] + dt * c5 * k5[i] + dt * c6 * k6[i];
+  rb_derivatives(rb, x, k1, t + dt);
+  for (int i = 0; i < 12; ++i) { rb->y[i] = x[i]; rb->ydot[i] = k1[i]; }
+  // ex5.cpp:345-350: R = exp(r) (math.cpp:122-132), its inverse (:141-145), the vectors of the kinematics
+  const double q1[4] = {0.0, x[3], x[4], x[5]};
+  double R[4];
+  double vMag = q1[1] * q1[1] + q1[2] * q1[2] + q1[3] * q1[3];
+  if (vMag == 0) {
+    R[0] = 1.0; R[1] = 0.0; R[2] = 0.0; R[3] = 0.0;
+  } else {
+    vMag = sqrt(vMag);
+    const double d1 = exp(q1[0]);
+    const double d2 = d1 * sin(vMag) / vMag;
+    R[0] = d1 * cos(vMag); R[1] = d2 * q1[1]; R[2] = d2 * q1[2]; R[3] = d2 * q1[3];
+  }
+  const double norm = R[0] * R[0] + R[1] * R[1] + R[2] * R[2] + R[3] * R[3];
+  rb->R[0] = R[0]; rb->R[1] = R[1]; rb->R[2] = R[2]; rb->R[3] = R[3];
+  rb->Rinv[0] = R[0] / norm; rb->Rinv[1] = -R[1] / norm; rb->Rinv[2] = -R[2] / norm; rb->Rinv[3] = -R[3] / norm;
+  for (int j = 0; j < 3; ++j) {
+    rb->omega[j] = x[j]; rb->alpha[j] = k1[j]; rb->vel[j] = x[6 + j]; rb->acc[j] = k1[6 + j]; rb->disp[j] = x[9 + j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 struct NodeArgs {
+  const double* X[3];   // reference coordinates (rigid-body nodes only)
+  const DevRigid* rigid;  // or nullptr
+  double* aprev[3];     // previous acceleration of the rigid-body nodes (energy check), or nullptr planes
   double* dt_hist;      // ADV only
   double* ehist;        // ADV only
   double* mp_rw;        // ADV only: parameter blocks (Prony factors)
@@ -374,7 +482,9 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_node(const NodeArgs A) {
         const bool b = (fl >> c) & 1u;
         const double fext = A.fe[c] ? A.fe[c][n] : 0.0;
         const double fnet = fext - f[c];  // GetForce_3D.cpp:11,49-51
-        const double a_old = aa[c];
+        // accelerations_prev of the energy check: for a rigid-body node the START of this step replaced a, the value
+        // before it was parked in aprev (ex5.cpp:209 memcpy before :222 ApplyAccBoundaryConditions)
+        const double a_old = (A.rigid && (fl & FTB_FLAG_RIGID)) ? A.aprev[c][n] : aa[c];
         if (!b) aa[c] = fnet / m;  // CalculateAcclerations.cpp:7-11
         if (KICK2) {
           if (!b) {
@@ -410,7 +520,28 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_node(const NodeArgs A) {
           vv[c] = r;
           aa[c] = 0.0;
         }
-        if (ENERGY) A.du[c][n] = uu[c] - u_old;
+        if (ENERGY && !(A.rigid && (fl & FTB_FLAG_RIGID))) A.du[c][n] = uu[c] - u_old;
+      }
+      if (A.rigid && (fl & FTB_FLAG_RIGID)) {  // ApplyAccBoundaryConditions, ex5.cpp:352-371
+        const DevRigid* rb = A.rigid;
+        const double locV[3] = {A.X[0][n], A.X[1][n], A.X[2][n]};
+        const double V[4] = {0.0, locV[0], locV[1], locV[2]};
+        double Rv[4], Vp[4], omegaR[3], omegaOmegaR[3], omegaVel[3], alphaR[3];
+        rb_qmul(rb->R, V, Rv);
+        rb_qmul(Rv, rb->Rinv, Vp);  // Vp = R V R^-1
+        rb_cross(rb->omega, &Vp[1], omegaR);
+        rb_cross(rb->omega, omegaR, omegaOmegaR);
+        rb_cross(rb->omega, rb->vel, omegaVel);
+        rb_cross(rb->alpha, &Vp[1], alphaR);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double u_old = uu[j];
+          A.aprev[j][n] = aa[j];
+          uu[j] = Vp[j + 1] - locV[j] + rb->disp[j];
+          vv[j] = omegaR[j] + rb->vel[j];
+          aa[j] = 2.0 * omegaVel[j] + omegaOmegaR[j] + rb->acc[j] + alphaR[j];
+          if (ENERGY) A.du[j][n] = uu[j] - u_old;
+        }
       }
     }
 #pragma unroll
@@ -698,6 +829,7 @@ __global__ void k_boundary_to_flags(const int* __restrict__ boundary, uint16_t* 
   if (r < 0) return;
   unsigned f = flags[i] & ~7u;
   f |= (boundary[3 * (size_t)r] ? 1u : 0u) | (boundary[3 * (size_t)r + 1] ? 2u : 0u) | (boundary[3 * (size_t)r + 2] ? 4u : 0u);
+  if (f & FTB_FLAG_RIGID) f |= 7u;  // rigid-body nodes stay fully constrained whatever the caller's array says
   flags[i] = (uint16_t)f;
 }
 __global__ void k_flags_to_boundary(const uint16_t* __restrict__ flags, int* boundary, const int* __restrict__ nref, int n) {

@@ -193,6 +193,26 @@ class FemTech:
         self._check(self.L.ftb200_principal_strains(self._h, _d(a), _d(b), _d(c), _d(v)))
         return (a, b, c, v) if volume else (a, b, c)
 
+    # --- rigid-body prescribed motion of the brain drivers (ex5.cpp:339-371, :574-912) ----------------------------
+    def set_rigid_bc(self, tables, boundaryID=None):
+        """tables: six (t, v) traces -- angular acceleration x, y, z [rad/s^2] then linear x, y, z [m/s^2] over t [s].
+        boundaryID None: every node of an element whose part has material 0 (InitBoundaryCondition)."""
+        keep, sizes = [], np.zeros(6, dtype=np.int32)
+        tp, vp = (_dp * 6)(), (_dp * 6)()
+        for k, (t, v) in enumerate(tables):
+            t = np.ascontiguousarray(t, dtype=np.float64)
+            v = np.ascontiguousarray(v, dtype=np.float64)
+            keep += [t, v]
+            sizes[k] = len(t)
+            tp[k], vp[k] = _d(t), _d(v)
+        ids = None if boundaryID is None else np.ascontiguousarray(boundaryID, dtype=np.int32)
+        self._check(self.L.ftb200_set_rigid_bc(self._h, _i(sizes), tp, vp, _i(ids), 0 if ids is None else len(ids)))
+
+    def rigid_state(self):
+        y, yd, n = np.zeros(12), np.zeros(12), C.c_int()
+        self._check(self.L.ftb200_get_rigid_state(self._h, _d(y), _d(yd), C.byref(n)))
+        return y, yd, n.value
+
     # --- injury criteria of the brain drivers (ex5.cpp:1251-1430), evaluated inside the resident loop ---------
     def InitInjuryCriterion(self, exclude_pids=(), thresholds=None):
         ex = np.ascontiguousarray(exclude_pids, dtype=np.int32)

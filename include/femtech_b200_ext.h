@@ -20,6 +20,13 @@ void femtech_b200_set_bc(const int *bc_kind, const double bc_rate[4], int energy
  * flagged volumes).  Strict legacy drivers need nothing new: CalculateMaximumPrincipalStrain(e, ...) keeps its
  * signature (include/FemTech.h:60) and is served from one device evaluation per force call. */
 void femtech_b200_injury_begin(const int *injuryExcludePID, int injuryExcludePIDCount);
+
+/* The brain drivers' boundary condition is a third callback, ApplyAccBoundaryConditions (ex5.cpp:222,339-371): the
+ * nodes of the rigid part follow a prescribed rigid-body motion integrated from acceleration traces.  Resident mode:
+ * hand the traces over once (arguments as ftb200_set_rigid_bc in ftb200.h: angular x,y,z then linear x,y,z traces in
+ * s and SI units as InitBoundaryCondition leaves them, ex5.cpp:577-645; boundaryID NULL = nodes of material-0 parts). */
+void femtech_b200_set_rigid_bc(const int sizes[6], const double *const t[6], const double *const v[6], const int *boundaryID,
+                               int boundarySize, int energy_every);
 void femtech_b200_injury_results(double scalars12[12], int extreme_elems4[4], unsigned char *flags, double *PS_Old,
                                  double *PSxSRArray, double volumes5[5]);
 #endif

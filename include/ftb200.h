@@ -207,6 +207,20 @@ int ftb200_injury_history(ftb200_ctx *ctx, long long first, long long count, dou
  * (CalculateCentroidAndVolume.cpp:26-37).  Pointers may be NULL. */
 int ftb200_principal_strains(ftb200_ctx *ctx, double *smax, double *smin, double *shear, double *volume0);
 
+/* ---- rigid-body prescribed-motion boundary condition of the brain drivers -------------
+ * Replaces the drivers' ApplyAccBoundaryConditions callback (examples/ex5/ex5.cpp:339-371) and the node selection
+ * of InitBoundaryCondition (:819-911) in the resident loop.  sizes[k], t[k], v[k], k = 0..5: the acceleration traces
+ * angular x,y,z [rad/s^2] then linear x,y,z [m/s^2] over time [s] (ex5.cpp:92-98, already converted).  boundaryID
+ * [boundarySize]: nodes that follow the rigid motion; NULL = every node of an element whose part has material 0
+ * (ex5.cpp:819-846).  Those nodes get boundary = 1 on all dofs and u = v = a = 0; the 12 integrator states start at 0
+ * (:897-900).  Each step the device advances the states with the Dormand-Prince step of odeint's runge_kutta_dopri5
+ * (from Time - dt over dt) and sets u, v, a of the nodes from the rotation quaternion (math.cpp:122-158).
+ * Call after ftb200_shape_functions and before ftb200_explicit_begin; combines with ftb200_set_bc for other nodes. */
+int ftb200_set_rigid_bc(ftb200_ctx *ctx, const int sizes[6], const double *const t[6], const double *const v[6],
+                        const int *boundaryID, int boundarySize);
+/* yInt[12] = omega, r, v, d and ydotInt[12] (ex5.cpp:105); boundary_count = number of rigid-motion nodes */
+int ftb200_get_rigid_state(ftb200_ctx *ctx, double *y12, double *ydot12, int *boundary_count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -233,11 +233,23 @@ void femtech_b200_set_bc(const int *bc_kind, const double bc_rate[4], int energy
   memcpy(g_bc_rate, bc_rate, sizeof(g_bc_rate));
   g_energy_every = energy_every;
 }
+/* Resident counterpart of InitBoundaryCondition / ApplyAccBoundaryConditions (ex5.cpp:574-912, :339-371) */
+static bool g_rigid = false;
+void femtech_b200_set_rigid_bc(const int sizes[6], const double *const t[6], const double *const v[6], const int *boundaryID,
+                               int boundarySize, int energy_every) {
+  ensure_ctx();
+  check(ftb200_set_rigid_bc(g_ctx, sizes, t, v, boundaryID, boundarySize));
+  g_rigid = true;
+  g_energy_every = energy_every;
+}
 void ExplicitDynamics(double timeFinal, char *name) {
   (void)name;
   ensure_ctx();
   g_state_gen++;
-  if (!g_bc_kind) { FILE_LOG_SINGLE(ERROR, "ExplicitDynamics: call femtech_b200_set_bc() first"); TerminateFemTech(3); }
+  if (!g_bc_kind && g_rigid) {  /* only the rigid-body condition: no other dof is prescribed */
+    g_bc_kind = (int *)calloc(nDOF, sizeof(int));
+  }
+  if (!g_bc_kind) { FILE_LOG_SINGLE(ERROR, "ExplicitDynamics: call femtech_b200_set_bc() or femtech_b200_set_rigid_bc() first"); TerminateFemTech(3); }
   if (world_size > 1) { FILE_LOG_SINGLE(ERROR, "ExplicitDynamics: multi-GPU runs are driven by femtech_b200.dist"); TerminateFemTech(3); }
   check(ftb200_set_state(g_ctx, displacements, velocities, accelerations, boundary));
   check(ftb200_set_bc(g_ctx, g_bc_kind, g_bc_rate));

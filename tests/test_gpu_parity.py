@@ -488,3 +488,46 @@ def test_injury_selection_is_exact_order_statistic():
     # element lists: everything at or above the percentile maximum at the step that set it
     t95 = r["scalars"][9]
     assert (r["flags"] & 16).sum() >= nin - k95 - 1 or t95 < r["scalars"][1]
+
+
+# ---- rigid-body prescribed motion of the brain drivers --------------------------------------------
+def test_rigid_body_bc_matches_reference_fixture():
+    """ex5's loop (ApplyAccBoundaryConditions: dopri5 on 12 states, quaternion kinematics on the nodes of the rigid part)
+    resident on the device, with the injury criteria on, vs the fixture written by the reference library under the harness
+    driver.  1e-9 on u, v, stresses; the energy line at its printed precision."""
+    g = golden("rigid6_p1")
+    d = rank_dict(g, 0)
+    m = make_model(d)
+    tables = [(g["param_rigid_t%d" % k], g["param_rigid_v%d" % k]) for k in range(6)]
+    nsteps = int(d["steps"][0])
+    m.set_rigid_bc(tables)
+    m.explicit_begin(energy_every=1, record_steps=nsteps + 8)
+    m.InitInjuryCriterion(exclude_pids=g["param_exclude"])
+    steps = m.ExplicitDynamics(float(g["param_tMax"]), maxSteps=nsteps)
+    assert steps == nsteps
+    dth, eh = m.history(0, steps)
+    assert rel(dth, d["dt_hist"]) < 1e-11
+    y, yd, nb = m.rigid_state()
+    assert nb == d["rb_boundaryID"].size
+    assert rel(y, d["rb_y"]) < 1e-12 and rel(yd, d["rb_ydot"]) < 1e-12
+    assert np.array_equal(m.boundary, d["boundary"])
+    assert rel(m.displacements, d["displacements"]) < TOL and rel(m.velocities, d["velocities"]) < TOL
+    assert rel(m.accelerations, d["accelerations"]) < 1e-6
+    assert rel(m.gp_outputs(F=False, detF=False)["pk2"], d["pk2"]) < TOL
+    ef = g["energy_file"][-1]
+    for got, want in zip(eh[-1], ef[1:]):
+        assert abs(got - want) <= 5e-6 * max(abs(want), 1e-300) + 1e-25, (eh[-1], ef)
+    r = m.injury_results()
+    assert rel(r["PS_Old"], d["inj_ps_old"]) < TOL
+    assert np.array_equal(r["MPSgt15"].astype(np.int32), d["inj_gt15"])
+    assert np.array_equal(r["extreme_elems"], d["inj_extreme_elems"])
+    # chunked run == one run, bit for bit (the integrator state lives on the device across calls)
+    m2 = make_model(d)
+    m2.set_rigid_bc(tables)
+    m2.explicit_begin(energy_every=1)
+    done = 0
+    while done < nsteps:
+        done += m2.ExplicitDynamics(float(g["param_tMax"]), maxSteps=min(7, nsteps - done))
+    assert np.array_equal(m2.displacements, m.displacements)
+    m.close()
+    m2.close()
