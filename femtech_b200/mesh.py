@@ -44,6 +44,53 @@ def cube_mesh(n, L=CUBE_L, jitter=0.0, seed=1234, nparts_z=1):
     return np.ascontiguousarray(X), np.ascontiguousarray(conn), pid
 
 
+KUHN_TETS = ((0, 1, 2, 6), (0, 2, 3, 6), (0, 3, 7, 6), (0, 7, 4, 6), (0, 4, 5, 6), (0, 5, 1, 6))
+
+
+def split_hex_to_tets(conn, pid, which):
+    """Mixed C3D8 / C3D4 mesh: hexahedra with which[e] true are replaced by six tetrahedra around the 0-6 diagonal
+    (conforming between neighbours of a structured mesh).  Returns (connectivity packed 8 or 4 per element [flat],
+    eptr[E'+1], pid[E'], etype list) in element order: every hexahedron stays in place, its tets take its slot."""
+    flat, eptr, pids, etype = [], [0], [], []
+    for e in range(conn.shape[0]):
+        if which[e]:
+            for t in KUHN_TETS:
+                flat.extend(int(conn[e, k]) for k in t)
+                eptr.append(eptr[-1] + 4)
+                pids.append(int(pid[e]))
+                etype.append("C3D4")
+        else:
+            flat.extend(int(v) for v in conn[e])
+            eptr.append(eptr[-1] + 8)
+            pids.append(int(pid[e]))
+            etype.append("C3D8")
+    return np.array(flat, dtype=np.int32), np.array(eptr, dtype=np.int32), np.array(pids, dtype=np.int32), etype
+
+
+def write_abaqus_inp_mixed(path, coordinates, connectivity, eptr, pid, etype):
+    """write_abaqus_inp for mixed element types: one *ELEMENT block per run of equal (part, type), so the file order is
+    the element order and part ids follow the first appearance of the ELSET names (ReadAbaqus.cpp:171-178)."""
+    X = np.asarray(coordinates, dtype=np.float64).reshape(-1, 3)
+    order = []
+    for p in pid:
+        if p not in order:
+            order.append(int(p))
+    if order != sorted(order):
+        raise ValueError("part ids must first appear in ascending order (ReadAbaqus.cpp:173-179)")
+    with open(path, "w") as f:
+        f.write("*Heading\n** femtech_b200 synthetic mixed mesh\n*Node\n")
+        for i, (x, y, z) in enumerate(X):
+            f.write("%d, %.17g, %.17g, %.17g\n" % (i + 1, x, y, z))
+        prev = None
+        for e in range(len(pid)):
+            key = (int(pid[e]), etype[e])
+            if key != prev:
+                f.write("*ELEMENT,TYPE=%s,ELSET=PART_%d\n" % (etype[e], key[0] + 1))
+                prev = key
+            nodes = connectivity[eptr[e]:eptr[e + 1]]
+            f.write("%d, %s\n" % (e + 1, ", ".join(str(int(v) + 1) for v in nodes)))
+
+
 def benchmark_bc(coordinates, L=CUBE_L, dMax=0.007, tMax=0.1, tol=1e-5):
     """The benchmark driver's boundary condition as a descriptor.
 

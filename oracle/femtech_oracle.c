@@ -18,6 +18,15 @@
 #define NDIM 3
 static const double huge_dt = 1e20; /* include/GlobalVariables.h:16 */
 
+/* Mixed C3D8 / C3D4 meshes (ShapeFunctions.cpp:71-164): gpoff[e] = Gauss points before element e (8 per hexahedron,
+ * 1 per tetrahedron); NULL = all hexahedra.  With h hexahedra and t tetrahedra before e: gpoff = 8h + t, e = h + t. */
+static inline int el_hex_before(const oracle_state *s, int e) { return s->gpoff ? (s->gpoff[e] - e) / 7 : e; }
+static inline int NGP(const oracle_state *s, int e) { return s->gpoff ? s->gpoff[e + 1] - s->gpoff[e] : 8; }
+static inline int NEN(const oracle_state *s, int e) { return NGP(s, e) == 8 ? 8 : 4; }
+static inline int GP0(const oracle_state *s, int e) { return s->gpoff ? s->gpoff[e] : 8 * e; }          /* gpPtr, detFptr */
+static inline int C0(const oracle_state *s, int e) { return 4 * e + 4 * el_hex_before(s, e); }           /* eptr */
+static inline int SHP0(const oracle_state *s, int e) { return 4 * e + 60 * el_hex_before(s, e); }        /* gptr; dsptr = 3x */
+
 /* ------------------------------------------------------------------------ */
 /* tiny BLAS restatements: naive left-to-right sums, identical to            */
 /* oracle/ref/blas_shim.c (the definition of "reference result")  */
@@ -95,6 +104,17 @@ double oracle_volumeHexahedron(const double *L) {
          tripleProduct(q2, q4, q5) / 64.0;
 }
 
+/* src/math/Geometry.cpp:66-76 */
+static double volumeTetrahedron(const double *L) {
+  double a[3], b[3], c[3];
+  for (int i = 0; i < 3; ++i) {
+    a[i] = L[i] - L[9 + i];
+    b[i] = L[3 + i] - L[9 + i];
+    c[i] = L[6 + i] - L[9 + i];
+  }
+  return fabs(tripleProduct(a, b, c)) / 6.0;
+}
+
 /* src/math/Geometry.cpp:29-64, including the signed (no fabs) parallelogram
  * test of :46 */
 double oracle_areaHexahedronFace(const double *L, const int *index) {
@@ -132,7 +152,7 @@ double oracle_areaHexahedronFace(const double *L, const int *index) {
 static double characteristicLength_C3D8(const oracle_state *s, int e) {
   double ec[24];
   for (int j = 0; j < 8; ++j) {
-    int n = s->connectivity[8 * e + j];
+    int n = s->connectivity[C0(s, e) + j];
     for (int k = 0; k < 3; ++k) {
       int index = NDIM * n + k;
       ec[j * NDIM + k] = s->coordinates[index] + s->displacements[index];
@@ -149,9 +169,41 @@ static double characteristicLength_C3D8(const oracle_state *s, int e) {
   return cl / areaMax;
 }
 
+/* src/elements/CharacteristicLength/CalculateCharacteristicLength_C3D4.cpp:5-47: smallest altitude */
+static double distancePointPlane(const double *x0, const double *x1, const double *x2, const double *x3) {
+  double v1[3], v2[3], normal[3];
+  for (int i = 0; i < 3; ++i) {
+    v1[i] = x2[i] - x1[i];
+    v2[i] = x3[i] - x1[i];
+  }
+  normal[0] = v1[1] * v2[2] - v1[2] * v2[1];
+  normal[1] = -v1[0] * v2[2] + v1[2] * v2[0];
+  normal[2] = v1[0] * v2[1] - v1[1] * v2[0];
+  double crossNorm = sqrt(normal[0] * normal[0] + normal[1] * normal[1] + normal[2] * normal[2]);
+  for (int i = 0; i < 3; ++i) normal[i] /= crossNorm;
+  double v3[3];
+  for (int i = 0; i < 3; ++i) v3[i] = x0[i] - x1[i];
+  return fabs(normal[0] * v3[0] + normal[1] * v3[1] + normal[2] * v3[2]);
+}
+static double characteristicLength_C3D4(const oracle_state *s, int e) {
+  static const int index[16] = {0, 1, 2, 3, 1, 2, 3, 0, 2, 3, 0, 1, 3, 0, 1, 2};
+  double ec[12];
+  for (int j = 0; j < 4; ++j) {
+    int n = s->connectivity[C0(s, e) + j];
+    for (int k = 0; k < 3; ++k) ec[j * NDIM + k] = s->coordinates[NDIM * n + k] + s->displacements[NDIM * n + k];
+  }
+  double altitudeMin = 1e6, minAlt;
+  for (int i = 0; i < 4; ++i) {
+    minAlt = distancePointPlane(&ec[index[4 * i] * NDIM], &ec[index[4 * i + 1] * NDIM], &ec[index[4 * i + 2] * NDIM],
+                                &ec[index[4 * i + 3] * NDIM]);
+    if (minAlt < altitudeMin) altitudeMin = minAlt;
+  }
+  return altitudeMin;
+}
+
 /* src/timestep/CalculateTimeStep.cpp:7-21 */
 double oracle_CalculateTimeStep(const oracle_state *s, int e) {
-  double le = characteristicLength_C3D8(s, e);
+  double le = NEN(s, e) == 8 ? characteristicLength_C3D8(s, e) : characteristicLength_C3D4(s, e);
   int pide = s->pid[e];
   double mu = s->properties[ORACLE_MAXMATPARAMS * pide + 1];
   double lambda = s->properties[ORACLE_MAXMATPARAMS * pide + 2];
@@ -166,7 +218,7 @@ double oracle_StableTimeStep_local(const oracle_state *s) {
   double dtMin = huge_dt;
   for (int i = 0; i < s->nElements; i++) {
     int isNotRigid = 0;
-    for (int j = 8 * i; j < 8 * i + 8; ++j) {
+    for (int j = C0(s, i); j < C0(s, i) + NEN(s, i); ++j) {
       int index = s->connectivity[j] * NDIM;
       if (!(s->boundary[index] & s->boundary[index + 1] &
             s->boundary[index + 2])) {
@@ -196,10 +248,10 @@ static void shapeFunction_C3D8(oracle_state *s, int e, int gp) {
   const double chi = gp_sign[gp][0] * GP_A;
   const double eta = gp_sign[gp][1] * GP_A;
   const double iota = gp_sign[gp][2] * GP_A;
-  double *shp = &s->shp[64 * e + 8 * gp];
-  double *d = &s->dshp[192 * e + 24 * gp];
+  double *shp = &s->shp[SHP0(s, e) + 8 * gp];
+  double *d = &s->dshp[3 * SHP0(s, e) + 24 * gp];
   const double *X = s->coordinates;
-  const int *c = &s->connectivity[8 * e];
+  const int *c = &s->connectivity[C0(s, e)];
 
   shp[0] = ((1 - chi) * (1 - eta) * (1 - iota)) / 8;
   shp[1] = ((1 + chi) * (1 - eta) * (1 - iota)) / 8;
@@ -257,7 +309,7 @@ static void shapeFunction_C3D8(oracle_state *s, int e, int gp) {
 #undef XC
   double det, J_Inv[9];
   inverse3x3Matrix(xs, J_Inv, &det);
-  s->detJacobian[8 * e + gp] = det;
+  s->detJacobian[GP0(s, e) + gp] = det;
   /* dN/dX (:108-119) */
   for (int i = 0; i < 8; ++i) {
     double *b = &d[3 * i];
@@ -271,24 +323,67 @@ static void shapeFunction_C3D8(oracle_state *s, int e, int gp) {
 }
 
 /* src/fem/ShapeFunctions/ShapeFunctions.cpp:181-252 */
+/* src/fem/ShapeFunctions/ShapeFunction_C3D4.cpp:6-85: one Gauss point at (1/4,1/4,1/4), weight 1/6
+ * (GaussQuadrature3D.cpp:62-69), detJ = |det| (:70) */
+static void shapeFunction_C3D4(oracle_state *s, int e) {
+  const double chi = 0.25, eta = 0.25, iota = 0.25;
+  double *shp = &s->shp[SHP0(s, e)];
+  double *d = &s->dshp[3 * SHP0(s, e)];
+  const double *X = s->coordinates;
+  const int *c = &s->connectivity[C0(s, e)];
+  shp[0] = chi;
+  shp[1] = eta;
+  shp[2] = iota;
+  shp[3] = 1.0 - eta - iota - chi;
+  d[3 * 0 + 0] = 1.0; d[3 * 1 + 0] = 0.0; d[3 * 2 + 0] = 0.0; d[3 * 3 + 0] = -1.0;
+  d[3 * 0 + 1] = 0.0; d[3 * 1 + 1] = 1.0; d[3 * 2 + 1] = 0.0; d[3 * 3 + 1] = -1.0;
+  d[3 * 0 + 2] = 0.0; d[3 * 1 + 2] = 0.0; d[3 * 2 + 2] = 1.0; d[3 * 3 + 2] = -1.0;
+  double xs[9];
+  for (int j = 0; j < 3; ++j) {
+    xs[0 + 3 * j] = X[NDIM * c[0] + j] - X[NDIM * c[3] + j];
+    xs[1 + 3 * j] = X[NDIM * c[1] + j] - X[NDIM * c[3] + j];
+    xs[2 + 3 * j] = X[NDIM * c[2] + j] - X[NDIM * c[3] + j];
+  }
+  double det, J_Inv[9];
+  inverse3x3Matrix(xs, J_Inv, &det);
+  s->detJacobian[GP0(s, e)] = fabs(det);
+  s->gaussWeights[GP0(s, e)] = 1.0 / 6.0;
+  for (int i = 0; i < 4; ++i) {
+    double *b = &d[3 * i];
+    double c1 = b[0] * J_Inv[0] + b[1] * J_Inv[3] + b[2] * J_Inv[6];
+    double c2 = b[0] * J_Inv[1] + b[1] * J_Inv[4] + b[2] * J_Inv[7];
+    double c3 = b[0] * J_Inv[2] + b[1] * J_Inv[5] + b[2] * J_Inv[8];
+    b[0] = c1;
+    b[1] = c2;
+    b[2] = c3;
+  }
+}
+
+/* src/fem/ShapeFunctions/ShapeFunctions.cpp:181-252 */
 void oracle_ShapeFunctions(oracle_state *s) {
   const int nE = s->nElements;
-  memset(s->shp, 0, sizeof(double) * 64 * (size_t)nE);
-  memset(s->dshp, 0, sizeof(double) * 192 * (size_t)nE);
-  memset(s->F, 0, sizeof(double) * 72 * (size_t)nE);
-  memset(s->pk2, 0, sizeof(double) * 48 * (size_t)nE);
-  for (size_t i = 0; i < 8 * (size_t)nE; ++i) {
+  const size_t nGP = (size_t)GP0(s, nE), nShp = (size_t)SHP0(s, nE);
+  memset(s->shp, 0, sizeof(double) * nShp);
+  memset(s->dshp, 0, sizeof(double) * 3 * nShp);
+  memset(s->F, 0, sizeof(double) * 9 * nGP);
+  memset(s->pk2, 0, sizeof(double) * 6 * nGP);
+  for (size_t i = 0; i < nGP; ++i) {
     s->F[i * 9] = 1.0;
     s->F[i * 9 + 4] = 1.0;
     s->F[i * 9 + 8] = 1.0;
     s->detF[i] = 1.0;
     s->gaussWeights[i] = 1.0;
   }
-  for (int e = 0; e < nE; ++e)
-    for (int k = 0; k < 8; ++k) shapeFunction_C3D8(s, e, k);
-  if (s->Hn_1) memset(s->Hn_1, 0, sizeof(double) * 72 * (size_t)nE);
-  if (s->Hn_2) memset(s->Hn_2, 0, sizeof(double) * 72 * (size_t)nE);
-  if (s->S0n) memset(s->S0n, 0, sizeof(double) * 72 * (size_t)nE);
+  for (int e = 0; e < nE; ++e) {
+    if (NEN(s, e) == 8) {
+      for (int k = 0; k < 8; ++k) shapeFunction_C3D8(s, e, k);
+    } else {
+      shapeFunction_C3D4(s, e);
+    }
+  }
+  if (s->Hn_1) memset(s->Hn_1, 0, sizeof(double) * 9 * nGP);
+  if (s->Hn_2) memset(s->Hn_2, 0, sizeof(double) * 9 * nGP);
+  if (s->S0n) memset(s->S0n, 0, sizeof(double) * 9 * nGP);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -304,30 +399,31 @@ void oracle_AssembleLumpedMass_local(oracle_state *s) {
   for (int e = 0; e < s->nElements; ++e) {
     double Me[8][8]; /* Me[n][m] = sum_gp (N_n N_m) * pre */
     memset(Me, 0, sizeof(Me));
-    for (int k = 0; k < 8; ++k) {
-      const double *shp = &s->shp[64 * e + 8 * k];
-      int wIndex = 8 * e + k;
+    const int nen = NEN(s, e), ngp = NGP(s, e);
+    for (int k = 0; k < ngp; ++k) {
+      const double *shp = &s->shp[SHP0(s, e) + nen * k];
+      int wIndex = GP0(s, e) + k;
       const double preFactor = s->gaussWeights[wIndex] * s->detJacobian[wIndex];
-      for (int n = 0; n < 8; ++n)
-        for (int m = 0; m < 8; ++m) {
+      for (int n = 0; n < nen; ++n)
+        for (int m = 0; m < nen; ++m) {
           /* dgemm inner sum: 0 + Nn*Nm + (exact zeros) ; alpha = 1 */
           double MeGQ = shp[n] * shp[m];
           Me[n][m] += MeGQ * preFactor;
         }
     }
     double rho = s->properties[ORACLE_MAXMATPARAMS * s->pid[e]];
-    for (int n = 0; n < 8; ++n)
-      for (int m = 0; m < 8; ++m) Me[n][m] *= rho;
+    for (int n = 0; n < nen; ++n)
+      for (int m = 0; m < nen; ++m) Me[n][m] *= rho;
     /* row-sum lumping: Me[j] += Me[j + i*24], i = 1..23 (:140-144).  For row
      * j = 3n+a only columns i = 3m+a are non-zero; adding exact zeros is a
      * no-op, so the sum runs over m = 0..7 in ascending order starting from
      * the m = 0 column (i = a is the first non-zero column for row 3n+a:
      * for a > 0 the row starts from the zero in column 0). */
-    for (int l = 0; l < 8; ++l) {
-      const int gIndex = s->connectivity[8 * e + l];
+    for (int l = 0; l < nen; ++l) {
+      const int gIndex = s->connectivity[C0(s, e) + l];
       for (int a = 0; a < 3; ++a) {
         double lumped = (a == 0) ? Me[l][0] : 0.0;
-        for (int m = (a == 0) ? 1 : 0; m < 8; ++m) lumped += Me[l][m];
+        for (int m = (a == 0) ? 1 : 0; m < nen; ++m) lumped += Me[l][m];
         s->mass[gIndex * NDIM + a] += lumped;
       }
     }
@@ -523,17 +619,18 @@ int oracle_GetForce_local(oracle_state *s) {
   for (int e = 0; e < s->nElements; e++) {
     double fintLocal[24];
     memset(fintLocal, 0, sizeof(fintLocal));
-    const int *conn = &s->connectivity[8 * e];
+    const int *conn = &s->connectivity[C0(s, e)];
     const int pide = s->pid[e];
     const double *props = &s->properties[ORACLE_MAXMATPARAMS * pide];
-    for (int gp = 0; gp < 8; gp++) {
-      double *Fg = &s->F[72 * e + 9 * gp];
-      const double *dshp = &s->dshp[192 * e + 24 * gp];
+    const int nen = NEN(s, e), ngp = NGP(s, e), gp0 = GP0(s, e);
+    for (int gp = 0; gp < ngp; gp++) {
+      double *Fg = &s->F[9 * (gp0 + gp)];
+      const double *dshp = &s->dshp[3 * SHP0(s, e) + 3 * nen * gp];
       /* CalculateDeformationGradient.cpp:11-25 */
       for (int i = 0; i < NDIM; i++)
         for (int j = 0; j < NDIM; j++) {
           double theSum = 0.0;
-          for (int k = 0; k < 8; k++) {
+          for (int k = 0; k < nen; k++) {
             int node_a = conn[k];
             theSum = theSum + (s->coordinates[NDIM * node_a + i] +
                                s->displacements[NDIM * node_a + i]) *
@@ -546,12 +643,12 @@ int oracle_GetForce_local(oracle_state *s) {
         double da = Fg[0], db = Fg[3], dc = Fg[6];
         double dd = Fg[1], de = Fg[4], df = Fg[7];
         double dg = Fg[2], dh = Fg[5], di = Fg[8];
-        s->detF[8 * e + gp] = da * (de * di - df * dh) -
+        s->detF[gp0 + gp] = da * (de * di - df * dh) -
                               db * (dd * di - df * dg) +
                               dc * (dd * dh - de * dg);
       }
-      const double J = s->detF[8 * e + gp];
-      double *pk2 = &s->pk2[48 * e + 6 * gp];
+      const double J = s->detF[gp0 + gp];
+      double *pk2 = &s->pk2[6 * (gp0 + gp)];
       /* StressUpdate.cpp:7-27 */
       switch (s->materialID[pide]) {
         case 0: break;
@@ -561,20 +658,20 @@ int oracle_GetForce_local(oracle_state *s) {
         case 4: HGOIsotropic(Fg, J, props, pk2); break;
         case 5:
           HGOIsotropicViscoelastic(Fg, J, props, s->dt,
-                                   &s->Hn_1[72 * e + 9 * gp],
-                                   &s->Hn_2[72 * e + 9 * gp],
-                                   &s->S0n[72 * e + 9 * gp], pk2);
+                                   &s->Hn_1[9 * (gp0 + gp)],
+                                   &s->Hn_2[9 * (gp0 + gp)],
+                                   &s->S0n[9 * (gp0 + gp)], pk2);
           break;
         default: bad = 1; break;
       }
       /* InternalForceUpdate.cpp:4-28: B (6x24), fintGQ = B^T sigma via the
        * naive dgemv ('T', m=6, n=24, alpha=1, beta=0), then the weighted add */
       double B[144];
-      for (int k = 0; k < 8; ++k)
+      for (int k = 0; k < nen; ++k)
         StrainDisplacementMatrix(&dshp[3 * k], Fg, &B[18 * k]);
-      const int wIndex = 8 * e + gp;
+      const int wIndex = gp0 + gp;
       const double preFactor = s->gaussWeights[wIndex] * s->detJacobian[wIndex];
-      for (int k = 0; k < 24; ++k) {
+      for (int k = 0; k < 3 * nen; ++k) {
         double sum = 0.0;
         for (int j = 0; j < 6; ++j) sum += B[j + 6 * k] * pk2[j];
         double fintGQ = 1.0 * sum;
@@ -582,7 +679,7 @@ int oracle_GetForce_local(oracle_state *s) {
       }
     }
     /* scatter (:39-44) */
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < nen; ++k) {
       int dIndex = conn[k];
       for (int l = 0; l < NDIM; ++l)
         s->fi[dIndex * NDIM + l] += fintLocal[k * NDIM + l];
@@ -814,9 +911,10 @@ void oracle_CalculateStrain(const oracle_state *s, double *Eavg) {
   for (int elm = 0; elm < s->nElements; ++elm) {
     double *E = &Eavg[9 * elm];
     for (int i = 0; i < 9; ++i) E[i] = 0.0;
-    double preFactor = 0.5 / ((double)8);
-    for (int gp = 0; gp < 8; ++gp) {
-      const double *Fg = &s->F[72 * elm + 9 * gp];
+    const int countGP = NGP(s, elm);
+    double preFactor = 0.5 / ((double)countGP);
+    for (int gp = 0; gp < countGP; ++gp) {
+      const double *Fg = &s->F[9 * (GP0(s, elm) + gp)];
       for (int j = 0; j < 3; ++j)
         for (int i = 0; i < 3; ++i) {
           double sum = 0.0;
@@ -840,10 +938,10 @@ void oracle_CalculateMaximumPrincipalStrain(const oracle_state *s, int elm, doub
   double Eloc[9];
   double *E = Eavg_e ? Eavg_e : Eloc;
   for (int i = 0; i < 9; ++i) E[i] = 0.0;
-  const int countGP = 8;
+  const int countGP = NGP(s, elm);
   double preFactor = 0.5 / ((double)countGP);
   for (int gp = 0; gp < countGP; ++gp) {
-    const double *Fg = &s->F[72 * elm + 9 * gp];
+    const double *Fg = &s->F[9 * (GP0(s, elm) + gp)];
     for (int j = 0; j < 3; ++j) /* dgemm('T','N'), alpha = preFactor, beta = 1 */
       for (int i = 0; i < 3; ++i) {
         double sum = 0.0;
@@ -993,9 +1091,9 @@ void oracle_injury_volumes(const oracle_state *s, const oracle_injury *inj, doub
   for (int j = 0; j < inj->nElementsInjury; ++j) {
     int e = inj->elementIDInjury[j];
     double coord[24];
-    for (int a = 0; a < 8; ++a)
-      for (int k = 0; k < 3; ++k) coord[3 * a + k] = s->coordinates[3 * s->connectivity[8 * e + a] + k];
-    double eV = oracle_volumeHexahedron(coord);
+    for (int a = 0; a < NEN(s, e); ++a)
+      for (int k = 0; k < 3; ++k) coord[3 * a + k] = s->coordinates[3 * s->connectivity[C0(s, e) + a] + k];
+    double eV = NEN(s, e) == 8 ? oracle_volumeHexahedron(coord) : volumeTetrahedron(coord);
     if (inj->MPSgt15[j]) {
       out[0] += eV;
       if (inj->MPSgt30[j]) out[1] += eV;
@@ -1127,12 +1225,12 @@ static int cmp_int(const void *a, const void *b) { return (*(const int *)a - *(c
 void oracle_InitRigidBoundary(oracle_state *s, oracle_rigid *rb) {
   int rigidNodeCount = 0;
   for (int i = 0; i < s->nElements; ++i)
-    if (s->materialID[s->pid[i]] == 0) rigidNodeCount += 8;
+    if (s->materialID[s->pid[i]] == 0) rigidNodeCount += NEN(s, i);
   int *rigidNodeID = (int *)malloc((rigidNodeCount > 0 ? rigidNodeCount : 1) * sizeof(int));
   int nodePtr = 0;
   for (int i = 0; i < s->nElements; ++i)
     if (s->materialID[s->pid[i]] == 0)
-      for (int j = 8 * i; j < 8 * i + 8; ++j) rigidNodeID[nodePtr++] = s->connectivity[j];
+      for (int j = C0(s, i); j < C0(s, i) + NEN(s, i); ++j) rigidNodeID[nodePtr++] = s->connectivity[j];
   qsort(rigidNodeID, rigidNodeCount, sizeof(int), cmp_int);
   for (int i = 0; i < rigidNodeCount; ++i) {
     int index = rigidNodeID[i] * NDIM;

@@ -61,6 +61,10 @@ typedef struct oracle_state {
   double Time, dt;
   /* CheckEnergy function-statics (CheckEnergy.cpp:4-5) */
   double Wint_n, Wext_n;
+  /* mixed C3D8/C3D4 meshes: gpoff[nElements+1] = Gauss points before each element (8 per hexahedron, 1 per
+   * tetrahedron, ShapeFunctions.cpp:71-164); connectivity is then packed 8 or 4 per element (eptr) and the per-GP
+   * arrays hold gpoff[nElements] points.  NULL = all hexahedra (the layouts documented above). */
+  const int *gpoff;
 } oracle_state;
 
 /* ShapeFunctions.cpp:32-255 + ShapeFunction_C3D8.cpp:4-128 (hex8 only). Also

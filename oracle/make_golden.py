@@ -94,6 +94,10 @@ def main():
     tmp = tempfile.mkdtemp(prefix="ftmesh_")
     ex = os.path.join(REF, "examples")
 
+    if only == "mixed":
+        group_g(tmp)
+        shutil.rmtree(tmp, ignore_errors=True)
+        return
     if only in ("injury", "rigid"):
         X, conn, pid = mesh.cube_mesh(6, jitter=0.05, nparts_z=3)
         f6 = os.path.join(tmp, "cube6mix.inp")
@@ -104,6 +108,8 @@ def main():
         group_e(tmp, f6)
     if only != "injury":
         group_f(tmp, f6)
+    if only == "":
+        group_g(tmp)
     shutil.rmtree(tmp, ignore_errors=True)
 
 
@@ -166,6 +172,23 @@ def group_f(tmp, f6):
     save("rigid6_p1", d, en[-1:], params,
          MESH_KEYS + ["steps", "Time", "dt", "dt_hist", "displacements", "velocities", "accelerations", "boundary", "fi", "pk2",
                       "rb_y", "rb_ydot", "rb_boundaryID"] + INJ_KEYS)
+
+
+def group_g(tmp):
+    # (G) mixed C3D8 / C3D4 meshes: every third hexahedron of part 0 and all of part 1 split into
+    #     six tetrahedra; neo-Hookean + HGO, and neo-Hookean + viscoelastic HGO (history on one-point elements)
+    X, conn, pid = mesh.cube_mesh(4, jitter=0.1, nparts_z=2)
+    which = (np.arange(conn.shape[0]) % 3 == 1) | (pid == 1)
+    flat, eptr, pids, etype = mesh.split_hex_to_tets(conn, pid, which)
+    f = os.path.join(tmp, "mix4.inp")
+    mesh.write_abaqus_inp_mixed(f, X, flat, eptr, pids, etype)
+    MED = [1040.0, 2.0e3, 2.0e4, 0, 0, 0, 0, 0, 0]
+    HGO_SOFT = [1000.0, 2.0e3, 2.0e4, 500.0, 10.0, 0, 0, 0, 0]
+    VISCO_SOFT = [1000.0, 2.0e3, 2.0e4, 500.0, 10.0, 0.6521, 0.0129, 0.0067, 0.0747]
+    for name, mats, props in (("mix4_p1", [1, 4], MED + HGO_SOFT), ("mix4v_p1", [1, 5], MED + VISCO_SOFT)):
+        d, en, _ = run_ref(f, mats, props, 1, 150, 0.005, 0.0009, injury_exclude=[])
+        save(name, d, en[-1:], dict(tMax=0.005, dMax=0.0009, exclude=[]),
+             MESH_KEYS + ["eptr"] + STATE_KEYS + GP_KEYS + INJ_KEYS)
 
 
 def group_e(tmp, f6):

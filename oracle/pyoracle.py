@@ -31,6 +31,7 @@ class OracleState(C.Structure):
         ("world_rank", C.c_int), ("sendProcessCount", C.c_int),
         ("sendProcessID", _ip), ("sendNeighbourCountCum", _ip), ("sendNodeIndex", _ip),
         ("Time", C.c_double), ("dt", C.c_double), ("Wint_n", C.c_double), ("Wext_n", C.c_double),
+        ("gpoff", _ip),
     ]
 
 
@@ -131,7 +132,9 @@ class OracleModel:
     NODAL = ["displacements", "velocities", "velocities_half", "accelerations", "mass", "fe", "fi", "f_net",
              "displacements_prev", "accelerations_prev", "fi_prev", "fe_prev"]
 
-    def __init__(self, coordinates, connectivity, pid, materialID, properties, comm=None, world_rank=0, fast=False):
+    def __init__(self, coordinates, connectivity, pid, materialID, properties, comm=None, world_rank=0, fast=False,
+                 eptr=None):
+        """eptr given: mixed C3D8 / C3D4 mesh, connectivity packed 8 or 4 node ids per element."""
         self.L = lib(fast)
         self.coordinates = np.ascontiguousarray(coordinates, dtype=np.float64).reshape(-1)
         self.connectivity = np.ascontiguousarray(connectivity, dtype=np.int32).reshape(-1)
@@ -139,19 +142,30 @@ class OracleModel:
         self.materialID = np.ascontiguousarray(materialID, dtype=np.int32)
         self.properties = np.ascontiguousarray(properties, dtype=np.float64).reshape(-1)
         nN = self.coordinates.size // 3
-        nE = self.connectivity.size // 8
+        self.gpoff = None
+        if eptr is None:
+            nE = self.connectivity.size // 8
+            nGP, nShp = 8 * nE, 64 * nE
+        else:
+            eptr = np.asarray(eptr, dtype=np.int64)
+            nE = eptr.size - 1
+            nen = np.diff(eptr)
+            assert np.all((nen == 8) | (nen == 4)) and eptr[-1] == self.connectivity.size
+            ngp = np.where(nen == 8, 8, 1)
+            self.gpoff = np.concatenate([[0], np.cumsum(ngp)]).astype(np.int32)
+            nGP, nShp = int(self.gpoff[-1]), int(np.sum(nen * ngp))
         self.nNodes, self.nElements = nN, nE
-        self.shp = np.zeros(64 * nE)
-        self.dshp = np.zeros(192 * nE)
-        self.detJacobian = np.zeros(8 * nE)
-        self.gaussWeights = np.zeros(8 * nE)
-        self.F = np.zeros(72 * nE)
-        self.detF = np.zeros(8 * nE)
-        self.pk2 = np.zeros(48 * nE)
+        self.shp = np.zeros(nShp)
+        self.dshp = np.zeros(3 * nShp)
+        self.detJacobian = np.zeros(nGP)
+        self.gaussWeights = np.zeros(nGP)
+        self.F = np.zeros(9 * nGP)
+        self.detF = np.zeros(nGP)
+        self.pk2 = np.zeros(6 * nGP)
         visco = bool(np.any(self.materialID == 5))
-        self.Hn_1 = np.zeros(72 * nE) if visco else None
-        self.Hn_2 = np.zeros(72 * nE) if visco else None
-        self.S0n = np.zeros(72 * nE) if visco else None
+        self.Hn_1 = np.zeros(9 * nGP) if visco else None
+        self.Hn_2 = np.zeros(9 * nGP) if visco else None
+        self.S0n = np.zeros(9 * nGP) if visco else None
         for n in self.NODAL:
             setattr(self, n, np.zeros(3 * nN))
         self.boundary = np.zeros(3 * nN, dtype=np.int32)
@@ -175,6 +189,7 @@ class OracleModel:
         s.sendProcessID, s.sendNeighbourCountCum = _i(self.sendProcessID), _i(self.sendNeighbourCountCum)
         s.sendNodeIndex = _i(self.sendNodeIndex)
         s.Time = s.dt = s.Wint_n = s.Wext_n = 0.0
+        s.gpoff = _i(self.gpoff) if self.gpoff is not None else None
         self.s = s
 
     # --- reference-named entry points -------------------------------------

@@ -235,3 +235,35 @@ def test_dopri5_restatement_is_fifth_order_and_fsal():
     assert y[6] == pytest.approx(y1[6] + acc * T, rel=1e-13)
     assert y[9] == pytest.approx(y1[9] + y1[6] * T + 0.5 * acc * T * T, rel=1e-12)
     assert rb.ydot[2] == al and rb.ydot[9] == y[6]
+
+
+# ---- mixed C3D8 / C3D4 meshes -------------------------------------------------------------------
+MIXED = ["mix4_p1", "mix4v_p1"]
+
+
+def mixed_model(d):
+    return po.OracleModel(d["coordinates"], d["connectivity"], d["pid"], d["materialID"], d["properties"], eptr=d["eptr"])
+
+
+@pytest.mark.parametrize("name", MIXED)
+def test_oracle_mixed_hex_tet_bit_exact_vs_reference(name):
+    """One-point tetrahedra (ShapeFunction_C3D4.cpp, CalculateCharacteristicLength_C3D4.cpp, GaussQuadrature3D.cpp:62-69)
+    next to hexahedra: mass, dt history, end state, per-Gauss-point arrays in the reference's packed layouts, Prony
+    history, and the injury criteria with one Gauss point per element."""
+    g = golden(name)
+    d = rank_dict(g, 0)
+    m = mixed_model(d)
+    m.ShapeFunctions()
+    m.AssembleLumpedMass()
+    assert np.array_equal(m.mass, d["mass"]) and np.array_equal(m.detJacobian, d["detJacobian"])
+    kind, rate = mesh.benchmark_bc(d["coordinates"], dMax=float(g["param_dMax"]), tMax=float(g["param_tMax"]))
+    inj = po.InjuryCriteria(m, exclude_pids=[])
+    n, dth, eh = po.run_explicit([m], [kind], rate, float(g["param_tMax"]), int(d["steps"][0]), injuries=[inj])
+    assert n == int(d["steps"][0]) and np.array_equal(dth, d["dt_hist"])
+    for k in ["displacements", "velocities", "accelerations", "fi", "f_net", "F", "detF", "pk2", "Hn_1", "Hn_2", "S0n"]:
+        if k in d and d[k].size:
+            assert np.array_equal(getattr(m, k), d[k]), (name, k)
+    assert np.array_equal(m.CalculateStrain(), d["Eavg"])
+    assert np.array_equal(inj.get("PS_Old"), d["inj_ps_old"]) and np.array_equal(inj.scalars(), d["inj_scalars"])
+    assert np.array_equal(inj.volumes(), d["inj_volumes"])
+    assert (np.diff(d["eptr"]) == 4).sum() > 0 and (np.diff(d["eptr"]) == 8).sum() > 0
