@@ -37,6 +37,13 @@ struct ftb200_ctx {
   // host copies of the inputs
   std::vector<double> h_X;
   std::vector<int> h_conn, h_pid, h_matid;
+  // mixed C3D8 / C3D4 meshes (ftb200_upload_mesh_mixed)
+  std::vector<uint8_t> h_etype;   // 1 = tetrahedron, reference element order; empty = all hexahedra
+  uint8_t* etype = nullptr;       // internal order
+  int* gpoff = nullptr;           // [nE+1] Gauss points before each element, reference order
+  bool has_tet = false;
+  long long nGP = 0;              // Gauss points of the mesh (8 nE without tetrahedra)
+  int nEb_hex = 0, nEi_hex = 0;   // hexahedra among the boundary / interior elements (they come first in each class)
   // rigid-body prescribed motion (ftb200_set_rigid_bc)
   DevRigid* rigid = nullptr;
   double *rigid_tab = nullptr, *aprev[3] = {nullptr, nullptr, nullptr};
@@ -179,6 +186,7 @@ ElemArgs elem_args(ftb200_ctx* c, int e0, int e1, int ignore) {
   for (int k = 0; k < 3; ++k) { A.X[k] = c->X[k]; A.u[k] = c->u[k]; }
   A.conn = c->conn; A.pid = c->pid; A.eflag = c->eflag; A.mp = c->mp; A.felem = c->felem; A.hist = c->hist;
   A.sc = c->sc; A.nE = c->nE; A.e0 = e0; A.e1 = e1; A.ignore_loop_flags = ignore;
+  A.etype = c->etype;
   A.inj_ps = c->inj_ps; A.inj_psxsr = c->inj_psxsr; A.inj_smin = c->inj_smin; A.inj_shear = c->inj_shear;
   A.inj_flags = c->inj_flags; A.inj_incl = c->inj_incl;
   for (int k = 0; k < 4; ++k) A.inj_thr[k] = c->inj_thr[k];
@@ -206,7 +214,34 @@ NodeArgs node_args(ftb200_ctx* c, const double* recv) {
 
 // element kernel dispatch on the (uniform) material of the launch
 template <bool WITH_FORCE, bool WITH_DT>
+void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore);
+
+template <bool WITH_FORCE, bool WITH_DT>
+void launch_elem_tet(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore) {
+  if (e1 <= e0) return;
+  const ElemArgs A = elem_args(ctx, e0, e1, ignore);
+  const int grid = cdiv(e1 - e0, TET_BLOCK);
+  if (WITH_FORCE && WITH_DT && ctx->injury && !ignore) LAUNCH((k_elem_tet<true, true, true>), grid, TET_BLOCK, s, A);
+  else LAUNCH((k_elem_tet<WITH_FORCE, WITH_DT, false>), grid, TET_BLOCK, s, A);
+}
+
+// [e0, e1) of the internal order = [boundary hex | boundary tet | interior hex | interior tet] (no tets: one launch)
+template <bool WITH_FORCE, bool WITH_DT>
 void launch_elem(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore) {
+  if (e1 <= e0) return;
+  if (!ctx->has_tet) { launch_elem_hex<WITH_FORCE, WITH_DT>(ctx, s, e0, e1, ignore); return; }
+  const int nb = ctx->nE_boundary;
+  const int cut[5] = {0, ctx->nEb_hex, nb, nb + ctx->nEi_hex, ctx->nE};
+  for (int c = 0; c < 4; ++c) {
+    const int a = std::max(e0, cut[c]), b = std::min(e1, cut[c + 1]);
+    if (b <= a) continue;
+    if (c & 1) launch_elem_tet<WITH_FORCE, WITH_DT>(ctx, s, a, b, ignore);
+    else launch_elem_hex<WITH_FORCE, WITH_DT>(ctx, s, a, b, ignore);
+  }
+}
+
+template <bool WITH_FORCE, bool WITH_DT>
+void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore) {
   if (e1 <= e0) return;
   const ElemArgs A = elem_args(ctx, e0, e1, ignore);
   const int grid = cdiv(e1 - e0, ELEM_BLOCK);
@@ -348,6 +383,7 @@ void free_all(ftb200_ctx* c) {
   }
   dfree(c->m); dfree(c->flags); dfree(c->conn); dfree(c->pid); dfree(c->ref_of); dfree(c->eflag);
   dfree(c->felem); dfree(c->hist); dfree(c->mp); dfree(c->node_off); dfree(c->node_ent); dfree(c->sc);
+  dfree(c->etype); dfree(c->gpoff);
   dfree(c->rigid); dfree(c->rigid_tab); dfree(c->aprev[0]); dfree(c->aprev[1]); dfree(c->aprev[2]);
   dfree(c->inj_ps); dfree(c->inj_psxsr); dfree(c->inj_smin); dfree(c->inj_shear); dfree(c->inj_part); dfree(c->inj_hist);
   dfree(c->inj_flags); dfree(c->inj_incl); dfree(c->inj_parti); dfree(c->inj_state);
@@ -459,7 +495,36 @@ int ftb200_upload_mesh(ftb200_ctx* ctx, const double* coordinates, const int* co
   ctx->h_X.assign(coordinates, coordinates + 3 * (size_t)nNodes);
   ctx->h_conn.assign(connectivity, connectivity + 8 * (size_t)nElements);
   ctx->h_pid.assign(pid, pid + nElements);
+  ctx->h_etype.clear(); ctx->has_tet = false;
   ctx->mesh_ok = true; ctx->shape_ok = false; ctx->begun = false;
+  return FTB200_OK;
+}
+
+long long ftb200_gauss_point_count(ftb200_ctx* ctx) { return ctx ? (ctx->shape_ok ? ctx->nGP : (ctx->has_tet ? -1 : 8LL * ctx->nE)) : -1; }
+
+int ftb200_upload_mesh_mixed(ftb200_ctx* ctx, const double* coordinates, const int* connectivity, const int* eptr, const int* pid,
+                             int nNodes, int nElements) {
+  if (!ctx || !coordinates || !connectivity || !eptr || !pid || nNodes <= 0 || nElements <= 0)
+    return fail(ctx, FTB200_ERR_INPUT, "upload_mesh_mixed: null pointer or empty mesh");
+  if ((long long)nElements * 8 >= (1LL << 31)) return fail(ctx, FTB200_ERR_INPUT, "upload_mesh_mixed: more than 2^28 elements per GPU");
+  std::vector<int> conn8(8 * (size_t)nElements);
+  std::vector<uint8_t> et(nElements);
+  bool any = false;
+  for (int e = 0; e < nElements; ++e) {
+    const int n = eptr[e + 1] - eptr[e];
+    if (n != 8 && n != 4)  // the reference terminates on other element types in 3-D (ShapeFunctions.cpp, code 3)
+      return fail(ctx, FTB200_ERR_INPUT, "upload_mesh_mixed: element %d has %d nodes; C3D8 and C3D4 are supported", e, n);
+    for (int k = 0; k < 8; ++k) {
+      const int v = connectivity[eptr[e] + (k < n ? k : 0)];  // unused slots of a tetrahedron repeat its first node
+      if (v < 0 || v >= nNodes) return fail(ctx, FTB200_ERR_INPUT, "upload_mesh_mixed: node %d of element %d out of range", v, e);
+      conn8[8 * (size_t)e + k] = v;
+    }
+    et[e] = n == 4;
+    any = any || n == 4;
+  }
+  int rc = ftb200_upload_mesh(ctx, coordinates, conn8.data(), pid, nNodes, nElements);
+  if (rc) return rc;
+  if (any) { ctx->h_etype = et; ctx->has_tet = true; }
   return FTB200_OK;
 }
 
@@ -516,9 +581,16 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
         nb += isb[e];
       }
     ctx->nE_boundary = nb;
-    int ib = 0, ii = nb;
+    // inside each class the hexahedra come first, the tetrahedra after them (their own kernel), caller's order kept
+    const bool mixed = ctx->has_tet;
+    int nbh = 0, nih = 0;
+    for (int e = 0; e < nE; ++e)
+      if (!(mixed && ctx->h_etype[e])) (isb[e] ? nbh : nih)++;
+    ctx->nEb_hex = nbh; ctx->nEi_hex = nih;
+    int cur[4] = {0, nbh, nb, nb + nih};  // boundary hex, boundary tet, interior hex, interior tet
     for (int e = 0; e < nE; ++e) {
-      const int t = isb[e] ? ib++ : ii++;
+      const int cls = (isb[e] ? 0 : 2) + ((mixed && ctx->h_etype[e]) ? 1 : 0);
+      const int t = cur[cls]++;
       ref_of[t] = e; int_of[e] = t;
     }
   }
@@ -577,12 +649,14 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
   }
   // ---- CSR node -> (element, slot), ascending CALLER element id (GetForce_3D.cpp:15,39-44) ---------
   std::vector<int> off(nNp + 1, 0), ent(8 * (size_t)nE);
-  for (size_t i = 0; i < 8 * (size_t)nE; ++i) off[nint[ctx->h_conn[i]] + 1]++;
+  auto nen = [&](int e) { return (ctx->has_tet && ctx->h_etype[e]) ? 4 : 8; };
+  for (int e = 0; e < nE; ++e)
+    for (int k = 0; k < nen(e); ++k) off[nint[ctx->h_conn[8 * (size_t)e + k]] + 1]++;
   for (int n = 0; n < nNp; ++n) off[n + 1] += off[n];
   {
     std::vector<int> cur(off.begin(), off.end() - 1);
     for (int e = 0; e < nE; ++e)
-      for (int k = 0; k < 8; ++k) ent[cur[nint[ctx->h_conn[8 * (size_t)e + k]]]++] = int_of[e] * 8 + k;
+      for (int k = 0; k < nen(e); ++k) ent[cur[nint[ctx->h_conn[8 * (size_t)e + k]]]++] = int_of[e] * 8 + k;
   }
   // ---- SoA planes ----------------------------------------------------------------------------
   std::vector<int> connT(8 * (size_t)nE), pidI(nE);
@@ -650,6 +724,17 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
   CK(cudaMemcpy(ctx->conn, connT.data(), connT.size() * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->pid, pidI.data(), nE * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->ref_of, ref_of.data(), nE * sizeof(int), cudaMemcpyHostToDevice));
+  ctx->nGP = 8LL * nE;
+  if (ctx->has_tet) {  // element types (internal order) and the packed Gauss-point offsets (reference order)
+    std::vector<uint8_t> etI(nE);
+    std::vector<int> gpoff(nE + 1, 0);
+    for (int t = 0; t < nE; ++t) etI[t] = ctx->h_etype[ref_of[t]];
+    for (int e = 0; e < nE; ++e) gpoff[e + 1] = gpoff[e] + (ctx->h_etype[e] ? 1 : 8);
+    ctx->nGP = gpoff[nE];
+    if ((rc = dalloc(ctx, &ctx->etype, nE)) || (rc = dalloc(ctx, &ctx->gpoff, nE + 1))) return rc;
+    CK(cudaMemcpy(ctx->etype, etI.data(), nE, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->gpoff, gpoff.data(), (nE + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  }
   CK(cudaMemcpy(ctx->mp, mp.data(), mp.size() * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->node_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->node_ent, ent.data(), ent.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -767,6 +852,7 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       ctx->fused = false;
       if (const char* ev = getenv("FTB200_FUSED")) ctx->fused = atoi(ev) != 0;
       if (const char* ev = getenv("FTB200_FUSE_ADV")) ctx->fuse_adv = atoi(ev) != 0;
+      if (ctx->has_tet) { ctx->fused = false; ctx->pipe = false; }  // the one-kernel variants are hexahedra only
     }
     ctx->node_grid = std::max(1, std::min(prop.multiProcessorCount * nb, nTilesN));
   }
@@ -914,14 +1000,15 @@ int ftb200_get_gp_outputs(ftb200_ctx* ctx, double* F, double* detF, double* pk2,
   if (!ctx || !ctx->shape_ok) return fail(ctx, FTB200_ERR_INPUT, "get_gp_outputs: setup incomplete");
   CK(cudaSetDevice(ctx->device));
   const size_t nE = ctx->nE;
-  const size_t nF = F ? 72 * nE : 0, nD = detF ? 8 * nE : 0, nP = pk2 ? 48 * nE : 0, nEa = Eavg ? 9 * nE : 0;
+  const size_t nG = (size_t)ctx->nGP;  // 8 per hexahedron, 1 per tetrahedron (ShapeFunctions.cpp:71-164)
+  const size_t nF = F ? 9 * nG : 0, nD = detF ? nG : 0, nP = pk2 ? 6 * nG : 0, nEa = Eavg ? 9 * nE : 0;
   int rc;
   if ((rc = ensure_big(ctx, (nF + nD + nP + nEa + 1) * sizeof(double)))) return rc;
   double* dF = F ? ctx->d_big : nullptr;
   double* dD = detF ? ctx->d_big + nF : nullptr;
   double* dP = pk2 ? ctx->d_big + nF + nD : nullptr;
   double* dE = Eavg ? ctx->d_big + nF + nD + nP : nullptr;
-  LAUNCH(k_gp_outputs, cdiv(ctx->nE, 64), 64, ctx->stream, elem_args(ctx, 0, ctx->nE, 1), ctx->ref_of, dF, dD, dP, dE);
+  LAUNCH(k_gp_outputs, cdiv(ctx->nE, 64), 64, ctx->stream, elem_args(ctx, 0, ctx->nE, 1), ctx->ref_of, ctx->gpoff, dF, dD, dP, dE);
   if (F) CK(cudaMemcpyAsync(F, dF, nF * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (detF) CK(cudaMemcpyAsync(detF, dD, nD * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (pk2) CK(cudaMemcpyAsync(pk2, dP, nP * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

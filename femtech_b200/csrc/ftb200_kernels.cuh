@@ -93,6 +93,7 @@ struct ElemArgs {
   int nE;            // plane stride
   int e0, e1;        // element range of this launch
   int ignore_loop_flags;
+  const uint8_t* etype;    // 1 = C3D4 (nodes in conn planes 0..3), nullptr = all C3D8; internal order
   // injury criteria (k_elem<..., WITH_INJ>), internal element order; see InjState below
   double* inj_ps;          // PS_Old: max principal strain of the previous step in, of this step out (ex5.cpp:1367)
   double* inj_psxsr;       // PSxSRArray (:1368)
@@ -261,6 +262,67 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
     if ((threadIdx.x & 31) == 0) atomicMin(&A.sc->dtmin_bits, b);
   }
   if (status) atomicOr(&A.sc->status, status);
+}
+
+// The C3D4 elements of a mixed mesh: they sit in their own index ranges of the internal element
+// order, so this kernel sees only tetrahedra and k_elem only hexahedra.  One thread per element, generic material.
+constexpr int TET_BLOCK = 128;
+template <bool WITH_FORCE, bool WITH_DT, bool WITH_INJ>
+__global__ void __launch_bounds__(TET_BLOCK) k_elem_tet(const ElemArgs A) {
+  const int e = A.e0 + blockIdx.x * TET_BLOCK + threadIdx.x;
+  if (!A.ignore_loop_flags && (A.sc->last | A.sc->done)) return;
+  const size_t E = (size_t)A.nE;
+  double dte = 1e300;
+  int status = 0;
+  if (e < A.e1) {
+    double X[4][3], U[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int nd = __ldg(A.conn + (size_t)k * E + e);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { X[k][c] = __ldg(A.X[c] + nd); U[k][c] = __ldg(A.u[c] + nd); }
+    }
+    const double* mp = A.mp + (size_t)__ldg(A.pid + e) * FTB_MP_STRIDE;
+    const int mat = (int)mp[MP_MATID];
+    double fe[4][3], d = 1e300;
+    DevHist h{A.hist, E, (size_t)e};
+    if (WITH_INJ) {
+      double cs[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      status = tet4_element<-1, WITH_DT>(X, U, mat, mp, WITH_FORCE, h, StrainSink{cs}, fe, &d);
+      if (A.inj_incl[e]) {  // ex5.cpp:1313-1369 with GaussPoints[e] = 1
+        double smax, smin, shear;
+        principal_strains(cs, &smax, &smin, &shear, 1);
+        const double PSR = (smax - A.inj_ps[e]) / A.sc->ndt;
+        const double PSxSR = smax * PSR;
+        unsigned f = A.inj_flags[e];
+        if (smax > A.inj_thr[0]) f |= FTB_INJ_MPS_LO;
+        if (smax > A.inj_thr[1]) f |= FTB_INJ_MPS_HI;
+        if (PSR > A.inj_thr[2]) f |= FTB_INJ_PSR;
+        if (PSxSR > A.inj_thr[3]) f |= FTB_INJ_PSXSR;
+        A.inj_flags[e] = (uint8_t)f;
+        A.inj_ps[e] = smax; A.inj_psxsr[e] = PSxSR; A.inj_smin[e] = smin; A.inj_shear[e] = shear;
+      }
+    } else {
+      status = tet4_element<-1, WITH_DT>(X, U, WITH_FORCE ? mat : 0, mp, WITH_FORCE, h, NoOutput(), fe, &d);
+    }
+    if (WITH_DT) dte = __ldg(A.eflag + e) ? 1e300 : d;
+    if (WITH_FORCE) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) A.felem[(size_t)(3 * k + c) * E + e] = fe[k][c];
+    }
+  }
+  if (WITH_DT) {
+    unsigned long long b = dt_to_bits(dte);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o);
+      b = t < b ? t : b;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMin(&A.sc->dtmin_bits, b);
+  }
+  if (WITH_FORCE && status) atomicOr(&A.sc->status, status);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -947,7 +1009,19 @@ __global__ void k_mass_elem(const ElemArgs A, double* me, unsigned long long* de
   }
   const double rho = A.mp[(size_t)A.pid[e] * FTB_MP_STRIDE + MP_RHO];
   double m8[8];
-  const double dmin = hex8_lumped_mass(X, rho, m8);
+  double dmin;
+  if (A.etype && A.etype[e]) {
+    double Xt[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Xt[k][c] = X[k][c];
+    dmin = tet4_lumped_mass(Xt, rho, m8);
+#pragma unroll
+    for (int k = 4; k < 8; ++k) m8[k] = 0.0;
+  } else {
+    dmin = hex8_lumped_mass(X, rho, m8);
+  }
 #pragma unroll
   for (int k = 0; k < 8; ++k) me[(size_t)k * E + e] = m8[k];
   if (!(dmin > 0.0)) atomicAdd(nonpos, 1);
@@ -1027,7 +1101,7 @@ struct OutSink {
   }
 };
 // ref_of[e]: reference (caller) element id of internal element e
-__global__ void k_gp_outputs(const ElemArgs A, const int* ref_of, double* F, double* detF, double* pk2, double* Eavg) {
+__global__ void k_gp_outputs(const ElemArgs A, const int* ref_of, const int* gpoff, double* F, double* detF, double* pk2, double* Eavg) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= A.nE) return;
   const size_t E = (size_t)A.nE;
@@ -1041,8 +1115,37 @@ __global__ void k_gp_outputs(const ElemArgs A, const int* ref_of, double* F, dou
   const double* mp = A.mp + (size_t)A.pid[e] * FTB_MP_STRIDE;
   const int mat = (int)mp[MP_MATID];
   const size_t re = (size_t)ref_of[e];
+  if (A.etype && A.etype[e]) {  // C3D4: one Gauss point, packed layouts (fptr = 9 gpoff, pk2ptr = 6 gpoff)
+    double Xt[4][3], Ut[4][3], Fl1[9], ft[4][3], dd;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { Xt[k][c] = X[k][c]; Ut[k][c] = U[k][c]; }
+    const size_t g0 = (size_t)gpoff[re];
+    OutSink st{Eavg ? Fl1 : (F ? F + 9 * g0 : nullptr), detF ? detF + g0 : nullptr, pk2 ? pk2 + 6 * g0 : nullptr, 0};
+    if (Eavg && !F) { st.detF = nullptr; st.pk2 = nullptr; }
+    DevHist ht{A.hist, E, (size_t)e};
+    tet4_element<-1, false>(Xt, Ut, mat, mp, false, ht, st, ft, &dd);
+    if (Eavg) {
+      double Em[9];
+      for (int j = 0; j < 3; ++j)
+        for (int i = 0; i < 3; ++i) {
+          double sum = 0.0;
+          for (int l = 0; l < 3; ++l) sum += Fl1[l + 3 * i] * Fl1[l + 3 * j];
+          Em[i + 3 * j] = 0.5 * sum;
+        }
+      Em[0] -= 0.5; Em[4] -= 0.5; Em[8] -= 0.5;
+      for (int i = 0; i < 9; ++i) Eavg[9 * re + i] = Em[i];
+      if (F || detF || pk2) {
+        OutSink s2{F ? F + 9 * g0 : nullptr, detF ? detF + g0 : nullptr, pk2 ? pk2 + 6 * g0 : nullptr, 0};
+        tet4_element<-1, false>(Xt, Ut, mat, mp, false, ht, s2, ft, &dd);
+      }
+    }
+    return;
+  }
+  const size_t ge = gpoff ? (size_t)gpoff[re] : 8 * re;  // first Gauss point of the element in the packed arrays
   double Fl[72];
-  OutSink sink{Eavg ? Fl : F, detF, pk2, Eavg ? 0 : re};
+  OutSink sink{Eavg ? Fl : (F ? F + 9 * ge : nullptr), detF ? detF + ge : nullptr, pk2 ? pk2 + 6 * ge : nullptr, 0};
   if (Eavg) { sink.detF = nullptr; sink.pk2 = nullptr; }
   DevHist h{A.hist, E, (size_t)e};
   double fe[8][3], d;
@@ -1064,7 +1167,7 @@ __global__ void k_gp_outputs(const ElemArgs A, const int* ref_of, double* F, dou
     for (int i = 0; i < 9; ++i) Eavg[9 * re + i] = Em[i];
     // second pass for the other outputs, if requested
     if (F || detF || pk2) {
-      OutSink s2{F, detF, pk2, re};
+      OutSink s2{F ? F + 9 * ge : nullptr, detF ? detF + ge : nullptr, pk2 ? pk2 + 6 * ge : nullptr, 0};
       hex8_element<-1, false>(X, U, mat, mp, false, h, s2, S, fe, &d);
     }
   }
@@ -2205,6 +2308,21 @@ __global__ void k_principal(const ElemArgs A, const int* ref_of, double* smax, d
     for (int c = 0; c < 3; ++c) { X[k][c] = A.X[c][nd]; U[k][c] = A.u[c][nd]; }
   }
   const size_t re = (size_t)ref_of[e];
+  if (A.etype && A.etype[e]) {
+    double Xt[4][3], Ut[4][3], ft[4][3], dd;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { Xt[k][c] = X[k][c]; Ut[k][c] = U[k][c]; }
+    if (vol0) vol0[re] = tet4_volume(Xt);
+    if (!smax) return;
+    double cs1[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    tet4_element<0, false>(Xt, Ut, 0, A.mp, false, NoHistory(), StrainSink{cs1}, ft, &dd);
+    double a1, b1, c1;
+    principal_strains(cs1, &a1, &b1, &c1, 1);
+    smax[re] = a1; smin[re] = b1; shear[re] = c1;
+    return;
+  }
   if (vol0) {
     double xm[7][3], n[8], g[7];
 #pragma unroll

@@ -518,8 +518,8 @@ struct StrainSink {
 // One deliberate difference: the argument of acos is clamped to [-1, 1].  For a double root that is not exactly
 // diagonal the reference's ratio R/sqrt(-Q^3) can round past 1, acos gives NaN and the element silently reports
 // 0 strain (:50-58,61-74); here it reports the eigenvalues.  Where the reference is finite the two agree.
-FTB_HD void principal_strains(const double csum[6], double* smax, double* smin, double* shear) {
-  const double pre = 0.5 / 8.0;
+FTB_HD void principal_strains(const double csum[6], double* smax, double* smin, double* shear, const int countGP = 8) {
+  const double pre = 0.5 / (double)countGP;
   const double a = pre * csum[0] - 0.5, d = pre * csum[1] - 0.5, f = pre * csum[2] - 0.5;
   const double e = pre * csum[3], c = pre * csum[4], b = pre * csum[5];
   const double p1 = b * b + c * c + e * e;
@@ -701,6 +701,99 @@ FTB_HD int hex8_element_in(const In& in, int mat, const double* __restrict__ mp,
     for (int k = 0; k < 8; ++k) fe[k][c] = f[k];
   }
   return status;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C3D4: the reference's other solid element.  One Gauss point at the centroid with weight 1/6
+// (GaussQuadrature3D.cpp:62-69), N = (xi, eta, zeta, 1 - xi - eta - zeta), detJ = |det| (ShapeFunction_C3D4.cpp:70).
+// Same algebra as one Gauss point of the hexahedron with the edge vectors x_k - x_3 as Jacobian columns:
+//   F = I + [u_k - u_3] [X_k - X_3]^-1,   f_k = (|det|/6) P grad N_k = sign(det)/6 (P cof J0)[:, k],  f_3 = -sum.
+// Characteristic length = smallest altitude of the current configuration (CalculateCharacteristicLength_C3D4.cpp:5-47).
+template <int MATSEL, bool WITH_DT, class Hist, class Out>
+FTB_HD int tet4_element(const double X[4][3], const double U[4][3], int mat, const double* __restrict__ mp, const bool updHist,
+                        const Hist& hist, const Out& out, double fe[4][3], double* dtElem) {
+  if (MATSEL >= 0) mat = MATSEL;
+  int status = 0;
+  double J0[3][3], Uh[3][3], cJ[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      J0[i][k] = X[k][i] - X[3][i];
+      Uh[i][k] = U[k][i] - U[3][i];
+    }
+  cofactor3(J0, cJ);
+  const double det = J0[0][0] * cJ[0][0] + J0[0][1] * cJ[0][1] + J0[0][2] * cJ[0][2];
+  if (det == 0.0 || !(det == det)) status |= 2;
+  const double rdet = 1.0 / det;
+  double F[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      F[i][j] = (Uh[i][0] * cJ[j][0] + Uh[i][1] * cJ[j][1] + Uh[i][2] * cJ[j][2]) * rdet + (i == j ? 1.0 : 0.0);
+  double cF[3][3];
+  cofactor3(F, cF);
+  const double J = F[0][0] * cF[0][0] + F[0][1] * cF[0][1] + F[0][2] * cF[0][2];
+  if (!(J > 0.0) && mat != 0) status |= 4;
+  double P[3][3], Sv[6];
+  GpHistory h;
+  if (mat == 5) hist.load(0, h);
+  status |= material_P<Out::want_S>(mat, F, cF, J, mp, &h, updHist, P, Sv);
+  if (mat == 5 && updHist) hist.store(0, h);
+  if (Out::enabled) out.put(0, F, J, Sv);
+  const double w = (det > 0.0 ? 1.0 : -1.0) / 6.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double Q0 = (P[i][0] * cJ[0][0] + P[i][1] * cJ[1][0] + P[i][2] * cJ[2][0]) * w;
+    const double Q1 = (P[i][0] * cJ[0][1] + P[i][1] * cJ[1][1] + P[i][2] * cJ[2][1]) * w;
+    const double Q2 = (P[i][0] * cJ[0][2] + P[i][1] * cJ[1][2] + P[i][2] * cJ[2][2]) * w;
+    fe[0][i] = Q0; fe[1][i] = Q1; fe[2][i] = Q2;
+    fe[3][i] = -(Q0 + Q1 + Q2);
+  }
+  if (WITH_DT) {
+    double x[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) x[k][c] = X[k][c] + U[k][c];
+    double altMin = 1e6;  // the reference's start value (:15)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // vertex i against the plane of the other three, index table of :6
+      const double* x0 = x[i]; const double* x1 = x[(i + 1) & 3]; const double* x2 = x[(i + 2) & 3]; const double* x3 = x[(i + 3) & 3];
+      const double v1[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]};
+      const double v2[3] = {x3[0] - x1[0], x3[1] - x1[1], x3[2] - x1[2]};
+      const double n[3] = {v1[1] * v2[2] - v1[2] * v2[1], -v1[0] * v2[2] + v1[2] * v2[0], v1[0] * v2[1] - v1[1] * v2[0]};
+      const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      const double alt = fabs(n[0] * (x0[0] - x1[0]) + n[1] * (x0[1] - x1[1]) + n[2] * (x0[2] - x1[2])) / nn;
+      if (alt < altMin) altMin = alt;
+    }
+    *dtElem = altMin / mp[MP_CE];
+  }
+  return status;
+}
+// lumped nodal mass of a tetrahedron: rho (1/6) |det| N_k sum_m N_m with N = 1/4 at the Gauss point (Mass3D.cpp:5-67);
+// returns |det| (the reference's detJacobian)
+FTB_HD double tet4_lumped_mass(const double X[4][3], const double rho, double me[4]) {
+  double J0[3][3], cJ[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) J0[i][k] = X[k][i] - X[3][i];
+  cofactor3(J0, cJ);
+  const double det = fabs(J0[0][0] * cJ[0][0] + J0[0][1] * cJ[0][1] + J0[0][2] * cJ[0][2]);
+  // Me[n][m] = (N_n N_m) (w detJ) rho, row sum over m in ascending order (the reference's lumping order)
+  const double entry = (0.25 * 0.25) * ((1.0 / 6.0) * det) * rho;
+  const double row = ((entry + entry) + entry) + entry;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) me[k] = row;
+  return det;
+}
+FTB_HD double tet4_volume(const double X[4][3]) {  // Geometry.cpp:66-76
+  double a[3], b[3], c[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { a[i] = X[0][i] - X[3][i]; b[i] = X[1][i] - X[3][i]; c[i] = X[2][i] - X[3][i]; }
+  return fabs(tp3(a, b, c)) / 6.0;
 }
 
 // Lumped nodal masses of one element (src/fem/Mass/Mass3D.cpp:5-67,127-151):

@@ -46,7 +46,8 @@ class FemTech:
     """One rank's model (the reference: one MPI rank's globals)."""
 
     def __init__(self, coordinates, connectivity, pid, materialID, properties, comm=None, world_rank=0,
-                 world_size=1, device=0, ExplicitTimeStepReduction=0.8, FailureTimeStep=1e-11):
+                 world_size=1, device=0, ExplicitTimeStepReduction=0.8, FailureTimeStep=1e-11, eptr=None):
+        """eptr given: mixed C3D8 / C3D4 mesh, connectivity packed 8 or 4 node ids per element (GlobalVariables.h:32-33)."""
         self.L = _lib.load()
         self._h = C.c_void_p()
         self.world_rank, self.world_size = world_rank, world_size
@@ -63,13 +64,22 @@ class FemTech:
         self.materialID = np.ascontiguousarray(materialID, dtype=np.int32)
         self.properties = np.ascontiguousarray(properties, dtype=np.float64).reshape(-1)
         self.nNodes = self.coordinates.size // 3
-        self.nelements = self.connectivity.size // 8
         self.nDOF = 3 * self.nNodes
         self.ndim = 3
-        if self.connectivity.size != 8 * self.nelements or self.pid.size != self.nelements:
-            raise FemTechB200Error(3, "connectivity/pid size mismatch (hex8 only)")
-        self._check(self.L.ftb200_upload_mesh(self._h, _d(self.coordinates), _i(self.connectivity), _i(self.pid),
-                                              self.nNodes, self.nelements))
+        if eptr is None:
+            self.nelements = self.connectivity.size // 8
+            self.eptr = 8 * np.arange(self.nelements + 1, dtype=np.int32)
+            if self.connectivity.size != 8 * self.nelements or self.pid.size != self.nelements:
+                raise FemTechB200Error(3, "connectivity/pid size mismatch (pass eptr for meshes that are not all C3D8)")
+            self._check(self.L.ftb200_upload_mesh(self._h, _d(self.coordinates), _i(self.connectivity), _i(self.pid),
+                                                  self.nNodes, self.nelements))
+        else:
+            self.eptr = np.ascontiguousarray(eptr, dtype=np.int32)
+            self.nelements = self.eptr.size - 1
+            if self.pid.size != self.nelements or self.eptr[-1] != self.connectivity.size:
+                raise FemTechB200Error(3, "connectivity/eptr/pid size mismatch")
+            self._check(self.L.ftb200_upload_mesh_mixed(self._h, _d(self.coordinates), _i(self.connectivity), _i(self.eptr),
+                                                        _i(self.pid), self.nNodes, self.nelements))
         self._check(self.L.ftb200_upload_materials(self._h, _i(self.materialID), _d(self.properties),
                                                    self.materialID.size))
         if comm is not None:
@@ -166,15 +176,17 @@ class FemTech:
         return self._Wint_n, self._Wext_n, out[0], abs(out[0] + self._Wint_n - self._Wext_n)
 
     def gp_outputs(self, F=True, detF=True, pk2=True, Eavg=False):
-        """F[72E], detF[8E], pk2[48E], Eavg[9E] of the last force evaluation, reference layouts."""
+        """F[9 nGP], detF[nGP], pk2[6 nGP], Eavg[9E] of the last force evaluation, reference layouts (nGP = 8 per
+        hexahedron + 1 per tetrahedron)."""
         nE = self.nelements
+        nG = int(self.L.ftb200_gauss_point_count(self._h))
         res = {}
         if F:
-            res["F"] = np.zeros(72 * nE)
+            res["F"] = np.zeros(9 * nG)
         if detF:
-            res["detF"] = np.zeros(8 * nE)
+            res["detF"] = np.zeros(nG)
         if pk2:
-            res["pk2"] = np.zeros(48 * nE)
+            res["pk2"] = np.zeros(6 * nG)
         if Eavg:
             res["Eavg"] = np.zeros(9 * nE)
         self._check(self.L.ftb200_get_gp_outputs(self._h, _d(res.get("F")), _d(res.get("detF")), _d(res.get("pk2")),

@@ -57,6 +57,13 @@ const char *ftb200_build_info(void);
 /* coordinates, connectivity, pid: GlobalVariables.h:32-33,47-49 after PartitionMesh.cpp:485-536 */
 int ftb200_upload_mesh(ftb200_ctx *ctx, const double *coordinates, const int *connectivity, const int *pid,
                        int nNodes, int nElements);
+/* Mixed meshes of the reference's two solid elements: connectivity packed 8 (C3D8) or 4 (C3D4)
+ * node ids per element as in include/GlobalVariables.h:32-33 with eptr[nElements+1] (ReadAbaqus.cpp:113-146).  C3D4:
+ * one Gauss point, src/fem/ShapeFunctions/ShapeFunction_C3D4.cpp, CalculateCharacteristicLength_C3D4.cpp.  The lazy
+ * outputs then use the reference's packed layouts: F[9*nGP], detF[nGP], pk2[6*nGP], nGP = ftb200_gauss_point_count. */
+int ftb200_upload_mesh_mixed(ftb200_ctx *ctx, const double *coordinates, const int *connectivity, const int *eptr,
+                             const int *pid, int nNodes, int nElements);
+long long ftb200_gauss_point_count(ftb200_ctx *ctx);
 /* materialID, properties: src/io/input/ReadMaterials.cpp:8-138 */
 int ftb200_upload_materials(ftb200_ctx *ctx, const int *materialID, const double *properties, int nPID);
 /* sendProcessID / sendNeighbourCountCum / sendNodeIndex: PartitionMesh.cpp:566-1128 */

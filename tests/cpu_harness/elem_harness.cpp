@@ -60,3 +60,18 @@ extern "C" void harness_principal(const double* X24, const double* U24, double* 
   ftb::principal_strains(cs, &out9[0], &out9[1], &out9[2]);
   for (int i = 0; i < 6; ++i) out9[3 + i] = cs[i];
 }
+
+// one C3D4 element: the arithmetic of the mixed-mesh branch of k_elem
+extern "C" int harness_tet(const double* X12, const double* U12, int mat, const double* mp, double* hist18, int updHist,
+                           double* fe12, double* dtElem, double* F9, double* detF1, double* pk2_6, double* me4) {
+  double X[4][3], U[4][3], fe[4][3];
+  for (int k = 0; k < 4; ++k)
+    for (int c = 0; c < 3; ++c) { X[k][c] = X12[3 * k + c]; U[k][c] = U12[3 * k + c]; }
+  HostHist hh{hist18};
+  HostOut ho{F9, detF1, pk2_6};
+  int st = ftb::tet4_element<-1, true>(X, U, mat, mp, updHist != 0, hh, ho, fe, dtElem);
+  for (int k = 0; k < 4; ++k)
+    for (int c = 0; c < 3; ++c) fe12[3 * k + c] = fe[k][c];
+  if (me4) ftb::tet4_lumped_mass(X, mp[ftb::MP_RHO], me4);
+  return st;
+}

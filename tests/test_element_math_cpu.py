@@ -31,6 +31,8 @@ def harness():
     L.harness_mass.argtypes = [_dp, C.c_double, _dp]
     L.harness_mass.restype = C.c_double
     L.harness_principal.argtypes = [_dp, _dp, _dp]
+    L.harness_tet.argtypes = [_dp, _dp, C.c_int, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
+    L.harness_tet.restype = C.c_int
     return L
 
 
@@ -187,3 +189,92 @@ def test_principal_strains_double_root_is_finite(harness):
     assert np.all(np.isfinite(out))
     assert out[0] == pytest.approx(0.5 * (lam * lam - 1.0), rel=1e-7)
     assert out[1] == 0.0 or abs(out[1]) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["mix4_p1", "mix4v_p1"])
+def test_tet4_element_matches_oracle(harness, name):
+    """tet4_element / tet4_lumped_mass (the C3D4 branch of the device kernels) vs the oracle on the tetrahedra of the mixed
+    fixtures: one force evaluation from the state before the last step, incl. the Prony history of one-point elements."""
+    from femtech_b200 import mesh
+    g = golden(name)
+    d = rank_dict(g, 0)
+    m = po.OracleModel(d["coordinates"], d["connectivity"], d["pid"], d["materialID"], d["properties"], eptr=d["eptr"])
+    m.ShapeFunctions()
+    m.AssembleLumpedMass()
+    kind, rate = mesh.benchmark_bc(d["coordinates"], dMax=float(g["param_dMax"]), tMax=float(g["param_tMax"]))
+    nsteps = int(d["steps"][0])
+    n, _, _ = po.run_explicit([m], [kind], rate, float(g["param_tMax"]), nsteps - 1)
+    assert n == nsteps - 1
+    Time, dt = m.Time, m.dt
+    t_np1 = Time + dt
+    free = m.boundary == 0
+    vh = np.where(free, m.velocities + (0.5 * (t_np1 + Time) - Time) * m.accelerations, m.velocities)
+    m.displacements[free] += dt * vh[free]
+    bc = kind > 0
+    m.displacements[bc] = t_np1 * rate[kind[bc]]
+    hist0 = [a.copy() for a in (m.Hn_1, m.Hn_2, m.S0n)] if m.Hn_1 is not None else None
+    m.GetForce()
+    mp = part_params(d["materialID"], d["properties"], dt)
+    X, U = m.coordinates.reshape(-1, 3), m.displacements.reshape(-1, 3)
+    eptr, gpoff = d["eptr"], m.gpoff
+    ntet = 0
+    masses = np.zeros(X.shape[0])
+    for e in range(m.nElements):
+        if eptr[e + 1] - eptr[e] != 4:
+            continue
+        ntet += 1
+        nodes = m.connectivity[eptr[e]:eptr[e + 1]]
+        Xe, Ue = np.ascontiguousarray(X[nodes]).reshape(-1), np.ascontiguousarray(U[nodes]).reshape(-1)
+        p = int(d["pid"][e])
+        g0 = int(gpoff[e])
+        hist = np.zeros(18)
+        if hist0 is not None:
+            for a, arr in enumerate(hist0):
+                hist[6 * a:6 * a + 6] = arr[9 * g0 + np.array(VOIGT)]
+        fe, dte, F9, dF, pk, me = np.zeros(12), np.zeros(1), np.zeros(9), np.zeros(1), np.zeros(6), np.zeros(4)
+        mpp = np.ascontiguousarray(mp[p])
+        st = harness.harness_tet(Xe.ctypes.data_as(_dp), Ue.ctypes.data_as(_dp), int(d["materialID"][p]), mpp.ctypes.data_as(_dp),
+                                 hist.ctypes.data_as(_dp), 1, fe.ctypes.data_as(_dp), dte.ctypes.data_as(_dp),
+                                 F9.ctypes.data_as(_dp), dF.ctypes.data_as(_dp), pk.ctypes.data_as(_dp), me.ctypes.data_as(_dp))
+        assert st == 0
+        assert np.allclose(F9, m.F[9 * g0:9 * g0 + 9], rtol=0, atol=1e-13)
+        assert abs(dF[0] - m.detF[g0]) <= 1e-13 * abs(m.detF[g0])
+        scale = max(np.abs(m.pk2).max(), 1e-300)
+        assert np.allclose(pk, m.pk2[6 * g0:6 * g0 + 6], rtol=0, atol=1e-10 * scale)
+        assert dte[0] == pytest.approx(po.lib().oracle_CalculateTimeStep(C.byref(m.s), e), rel=1e-12)
+        if hist0 is not None:
+            for a, arr in enumerate([m.Hn_1, m.Hn_2, m.S0n]):
+                assert np.allclose(hist[6 * a:6 * a + 6], arr[9 * g0 + np.array(VOIGT)], rtol=0, atol=1e-10 * max(np.abs(m.S0n).max(), 1e-300))
+        np.add.at(masses, nodes, me)
+    assert ntet > 50
+    # forces: assemble tets through the harness and hexahedra through the hex harness == the oracle's fi
+    fi = np.zeros_like(U)
+    for e in range(m.nElements):
+        nodes = m.connectivity[eptr[e]:eptr[e + 1]]
+        Xe, Ue = np.ascontiguousarray(X[nodes]).reshape(-1), np.ascontiguousarray(U[nodes]).reshape(-1)
+        p = int(d["pid"][e])
+        g0 = int(gpoff[e])
+        mpp = np.ascontiguousarray(mp[p])
+        dte = np.zeros(1)
+        if len(nodes) == 4:
+            hist = np.zeros(18)
+            if hist0 is not None:
+                for a, arr in enumerate(hist0):
+                    hist[6 * a:6 * a + 6] = arr[9 * g0 + np.array(VOIGT)]
+            fe = np.zeros(12)
+            harness.harness_tet(Xe.ctypes.data_as(_dp), Ue.ctypes.data_as(_dp), int(d["materialID"][p]), mpp.ctypes.data_as(_dp),
+                                hist.ctypes.data_as(_dp), 1, fe.ctypes.data_as(_dp), dte.ctypes.data_as(_dp), np.zeros(9).ctypes.data_as(_dp),
+                                np.zeros(1).ctypes.data_as(_dp), np.zeros(6).ctypes.data_as(_dp), None)
+            np.add.at(fi, nodes, fe.reshape(4, 3))
+        else:
+            hist = np.zeros(144)
+            if hist0 is not None:
+                for gp in range(8):
+                    for a, arr in enumerate(hist0):
+                        hist[18 * gp + 6 * a:18 * gp + 6 * a + 6] = arr[9 * (g0 + gp) + np.array(VOIGT)]
+            fe = np.zeros(24)
+            harness.harness_element(Xe.ctypes.data_as(_dp), Ue.ctypes.data_as(_dp), int(d["materialID"][p]), mpp.ctypes.data_as(_dp),
+                                    hist.ctypes.data_as(_dp), 1, fe.ctypes.data_as(_dp), dte.ctypes.data_as(_dp), np.zeros(72).ctypes.data_as(_dp),
+                                    np.zeros(8).ctypes.data_as(_dp), np.zeros(48).ctypes.data_as(_dp))
+            np.add.at(fi, nodes, fe.reshape(8, 3))
+    assert np.abs(fi.reshape(-1) - m.fi).max() < 1e-11 * np.abs(m.fi).max()
