@@ -40,6 +40,8 @@ def algorithmic_bytes(n, mat, energy):
     return elem + hist, node
 
 
+# (n, material, energy, injury) -> measured DRAM bytes per k_elem launch (ncu, see profiles/)
+NCU_TRAFFIC_BYTES = {(100, 1, True, False): 86518016 + 140992768}
 ELEM_FLOPS = {1: 3490.0, 4: 4400.0, 5: 6550.0}  # executed fp64 flops per element in K_elem (ncu for mat 1, SASS count for 4/5)
 
 
@@ -251,7 +253,10 @@ def ours_single(args):
             "peak": fp64_peak if fp64_bound else hbm_peak,
             "unit": "TFLOP/s" if fp64_bound else "GB/s",
             "frac": (elem_tf / fp64_peak) if fp64_bound else (elem_gbs / hbm_peak),
-            "traffic": None,
+            # DRAM bytes of one k_elem launch from the ncu --set full capture of this configuration
+            # (profiles/r01_k_elem_final_ncu_full.csv: dram__bytes_read.sum + dram__bytes_write.sum); other configs: null
+            "traffic": NCU_TRAFFIC_BYTES.get((n, mat, bool(energy), bool(args.injury))),
+            "traffic_unit": "bytes per launch (algorithmic: %d)" % int(b_elem * E),
             "peak_source": "fp64: DFMA microbenchmark measured in this run; hbm: " + hbm_src,
             "launch_ms": prof["elem_ms"], "launches_timed": prof["elem_launches"],
             "algorithmic_flops_per_element": flops, "algorithmic_bytes_per_element": b_elem,

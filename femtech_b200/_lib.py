@@ -67,6 +67,11 @@ SIGNATURES = {
     "ftb200_get_rigid_state": (C.c_int, [_vp, _dp, _dp, _ip]),
     "ftb200_injury_begin": (C.c_int, [_vp, _ip, C.c_int, _dp]),
     "ftb200_injury_end": (C.c_int, [_vp]),
+    "ftb200_injury_local_count": (C.c_int, [_vp, C.POINTER(_ll)]),
+    "ftb200_injury_global_count": (C.c_int, [_vp, _ll]),
+    "ftb200_injury_passes": (C.c_int, []),
+    "ftb200_injury_select_hist": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), _ip]),
+    "ftb200_injury_select_pick": (C.c_int, [_vp, C.c_int]),
     "ftb200_injury_get": (C.c_int, [_vp, _dp, _ip, C.POINTER(C.c_ubyte), _dp, _dp, _dp]),
     "ftb200_injury_history": (C.c_int, [_vp, _ll, _ll, _dp, _dp]),
     "ftb200_principal_strains": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),

@@ -282,7 +282,8 @@ void launch_injury(ftb200_ctx* ctx, cudaStream_t s) {
   LAUNCH(k_injury_reduce, std::min(INJ_BLOCKS, cdiv(ctx->nE, INJ_THREADS * 4)), INJ_THREADS, s, A, ctx->ref_of, ctx->inj_state, ctx->inj_part, ctx->inj_parti);
   double* h0 = ctx->inj_hist;
   double* h1 = ctx->inj_hist ? ctx->inj_hist + ctx->hist_cap : nullptr;
-  for (int pass = 0; pass < INJ_PASSES; ++pass) LAUNCH(k_injury_select, dim3(std::min(INJ_BLOCKS, cdiv(ctx->nE, INJ_THREADS * INJ_ITEMS)), 2), INJ_THREADS, s, A, ctx->inj_state, pass, h0, h1);
+  if (ctx->nranks > 1) return;  // several partitions: the caller drives the passes (ftb200_injury_select_hist/_pick/_lists)
+  for (int pass = 0; pass < INJ_PASSES; ++pass) LAUNCH(k_injury_select, dim3(std::min(INJ_BLOCKS, cdiv(ctx->nE, INJ_THREADS * INJ_ITEMS)), 2), INJ_THREADS, s, A, ctx->inj_state, pass, h0, h1, 0);
   LAUNCH(k_injury_lists, cdiv(ctx->nE, 256), 256, s, A, ctx->inj_state);
 }
 
@@ -1565,6 +1566,7 @@ int ftb200_step_end(ftb200_ctx* ctx, const double* recv_dev) {
   if (ctx->energy) LAUNCH((k_node<true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
   else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   if (ctx->energy) LAUNCH(k_energy, 1, 256, s, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
+  if (ctx->injury) launch_injury(ctx, s);  // several partitions: running extrema only, the selection passes follow
   ctx->halo_recv_cur = ctx->halo_count ? recv_dev : nullptr;
   return FTB200_OK;
 }
@@ -1833,7 +1835,6 @@ int ftb200_get_rigid_state(ftb200_ctx* ctx, double* y12, double* ydot12, int* bo
 int ftb200_injury_begin(ftb200_ctx* ctx, const int* exclude_pids, int n_exclude, const double* thresholds4) {
   if (!ctx || !ctx->shape_ok || n_exclude < 0 || (n_exclude && !exclude_pids))
     return fail(ctx, FTB200_ERR_INPUT, "injury_begin: setup incomplete or bad arguments");
-  if (ctx->nranks > 1) return fail(ctx, FTB200_ERR_INPUT, "injury_begin: single partition only in this version");
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   const size_t nE = ctx->nE;
@@ -1849,7 +1850,8 @@ int ftb200_injury_begin(ftb200_ctx* ctx, const int* exclude_pids, int n_exclude,
     n += incl[t];
   }
   const int index95 = (int)(n * 0.95) - 1;  // math.cpp:189; the reference faults on a negative index
-  if (index95 < 0) return fail(ctx, FTB200_ERR_INPUT, "injury_begin: %d participating elements, the 95th percentile needs >= 2", n);
+  if (index95 < 0 && ctx->nranks == 1)
+    return fail(ctx, FTB200_ERR_INPUT, "injury_begin: %d participating elements, the 95th percentile needs >= 2", n);
   int rc;
   if (!ctx->inj_ps) {
     if ((rc = dalloc(ctx, &ctx->inj_ps, nE)) || (rc = dalloc(ctx, &ctx->inj_psxsr, nE)) || (rc = dalloc(ctx, &ctx->inj_smin, nE)) ||
@@ -1867,7 +1869,7 @@ int ftb200_injury_begin(ftb200_ctx* ctx, const int* exclude_pids, int n_exclude,
   CK(cudaMemcpy(ctx->inj_incl, incl.data(), nE, cudaMemcpyHostToDevice));
   InjState st;
   memset(&st, 0, sizeof(st));
-  st.kth0 = (unsigned)index95;
+  st.kth0 = (unsigned)std::max(index95, 0);  // several partitions: ftb200_injury_global_count sets the global rank
   st.nIncluded = n;
   CK(cudaMemcpy(ctx->inj_state, &st, sizeof(st), cudaMemcpyHostToDevice));
   if (thresholds4) for (int k = 0; k < 4; ++k) ctx->inj_thr[k] = thresholds4[k];
@@ -1965,6 +1967,45 @@ int ftb200_injury_history(ftb200_ctx* ctx, long long first, long long count, dou
   if (mpsxsr95 && count) CK(cudaMemcpy(mpsxsr95, ctx->inj_hist + ctx->hist_cap + first, count * sizeof(double), cudaMemcpyDeviceToHost));
   return FTB200_OK;
 }
+
+// ---- several partitions: the percentile is a global order statistic (math.cpp:160-199 gathers all ranks) -----
+int ftb200_injury_local_count(ftb200_ctx* ctx, long long* n_included) {
+  if (!ctx || !ctx->inj_state || !n_included) return fail(ctx, FTB200_ERR_INPUT, "injury_local_count: call injury_begin first");
+  CK(cudaSetDevice(ctx->device));
+  InjState st;
+  CK(cudaMemcpy(&st, ctx->inj_state, sizeof(st), cudaMemcpyDeviceToHost));
+  *n_included = st.nIncluded;
+  return FTB200_OK;
+}
+int ftb200_injury_global_count(ftb200_ctx* ctx, long long n_total) {
+  if (!ctx || !ctx->inj_state) return fail(ctx, FTB200_ERR_INPUT, "injury_global_count: call injury_begin first");
+  const long long index95 = (long long)(n_total * 0.95) - 1;
+  if (index95 < 0) return fail(ctx, FTB200_ERR_INPUT, "injury_global_count: %lld participating elements, the 95th percentile needs >= 2", n_total);
+  CK(cudaSetDevice(ctx->device));
+  const unsigned k = (unsigned)index95;
+  CK(cudaMemcpy(&ctx->inj_state->kth0, &k, sizeof(k), cudaMemcpyHostToDevice));
+  return FTB200_OK;
+}
+int ftb200_injury_select_hist(ftb200_ctx* ctx, int pass, unsigned** hist_dev, int* hist_len) {
+  if (!ctx || !ctx->injury || pass < 0 || pass >= INJ_PASSES) return fail(ctx, FTB200_ERR_INPUT, "injury_select_hist: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  const ElemArgs A = elem_args(ctx, 0, ctx->nE, 0);
+  LAUNCH(k_injury_select, dim3(std::min(INJ_BLOCKS, cdiv(ctx->nE, INJ_THREADS * INJ_ITEMS)), 2), INJ_THREADS, ctx->stream, A, ctx->inj_state,
+         pass, nullptr, nullptr, 1);
+  if (hist_dev) *hist_dev = &ctx->inj_state->hist[0][0];
+  if (hist_len) *hist_len = 2 * INJ_BINS;
+  return FTB200_OK;
+}
+int ftb200_injury_select_pick(ftb200_ctx* ctx, int pass) {
+  if (!ctx || !ctx->injury || pass < 0 || pass >= INJ_PASSES) return fail(ctx, FTB200_ERR_INPUT, "injury_select_pick: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  double* h0 = ctx->inj_hist;
+  double* h1 = ctx->inj_hist ? ctx->inj_hist + ctx->hist_cap : nullptr;
+  LAUNCH(k_injury_pick, dim3(1, 2), INJ_THREADS, ctx->stream, ctx->sc, ctx->inj_state, pass, h0, h1);
+  if (pass == INJ_PASSES - 1) LAUNCH(k_injury_lists, cdiv(ctx->nE, 256), 256, ctx->stream, elem_args(ctx, 0, ctx->nE, 0), ctx->inj_state);
+  return FTB200_OK;
+}
+int ftb200_injury_passes(void) { return INJ_PASSES; }
 
 int ftb200_measure_peaks(ftb200_ctx* ctx, int reps, double* fp64_tflops, double* copy_gbs) {
   if (!ctx) return FTB200_ERR_INPUT;

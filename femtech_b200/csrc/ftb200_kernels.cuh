@@ -2189,7 +2189,7 @@ __device__ __forceinline__ double inj_unkey(unsigned long long k) {
 // leading digits are nearly constant: the histogram votes are aggregated per warp (__match_any_sync) before they
 // reach shared memory -- one atomic per distinct digit per warp instead of 32 colliding ones.
 __global__ void __launch_bounds__(INJ_THREADS) k_injury_select(const ElemArgs A, InjState* st, const int pass, double* hist95,
-                                                                double* histx95) {
+                                                                double* histx95, const int hist_only) {
   const DevScalars* sc = A.sc;
   if (!sc->active) return;
   const int arr = blockIdx.y;
@@ -2226,6 +2226,7 @@ __global__ void __launch_bounds__(INJ_THREADS) k_injury_select(const ElemArgs A,
   __syncthreads();
   for (int i = threadIdx.x; i < INJ_BINS; i += INJ_THREADS)
     if (h[i]) atomicAdd(&st->hist[arr][i], h[i]);
+  if (hist_only) return;  // several partitions: the histograms are summed across ranks first, then k_injury_pick
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(&st->sel_done[arr], 1u) == gridDim.x - 1) ? 1 : 0;
@@ -2277,6 +2278,59 @@ __global__ void __launch_bounds__(INJ_THREADS) k_injury_select(const ElemArgs A,
       } else {
         st->upd[arr] = 0;
       }
+    }
+  }
+}
+
+// Bucket search of one radix pass on histograms that were summed across the partitions (k_injury_select with
+// hist_only, then an all-reduce of st->hist): grid (1, 2), one block per array.  Every rank computes the same digit.
+__global__ void __launch_bounds__(INJ_THREADS) k_injury_pick(const DevScalars* sc, InjState* st, const int pass, double* hist95,
+                                                              double* histx95) {
+  if (!sc->active) return;
+  const int arr = blockIdx.y;
+  __shared__ unsigned h[INJ_BINS];
+  __shared__ unsigned tsum[INJ_THREADS];
+  __shared__ unsigned s_k0;
+  for (int i = threadIdx.x; i < INJ_BINS; i += INJ_THREADS) {
+    h[i] = st->hist[arr][i];
+    st->hist[arr][i] = 0;
+  }
+  __syncthreads();
+  constexpr int PER = INJ_BINS / INJ_THREADS;
+  unsigned mine = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) mine += h[threadIdx.x * PER + j];
+  tsum[threadIdx.x] = mine;
+  if (threadIdx.x == 0) s_k0 = pass == 0 ? st->kth0 : st->kth[arr];
+  __syncthreads();
+  for (int o = 1; o < INJ_THREADS; o <<= 1) {
+    const unsigned add = threadIdx.x >= o ? tsum[threadIdx.x - o] : 0u;
+    __syncthreads();
+    tsum[threadIdx.x] += add;
+    __syncthreads();
+  }
+  const unsigned k0 = s_k0;
+  const unsigned excl = tsum[threadIdx.x] - mine;
+  const bool owner = (k0 >= excl && k0 < excl + mine) || (threadIdx.x == INJ_THREADS - 1 && k0 >= tsum[INJ_THREADS - 1]);
+  if (!owner) return;
+  const int shift = 55 - 11 * pass;
+  unsigned k = k0 - excl;
+  unsigned digit = threadIdx.x * PER;
+  for (int j = 0; j < PER - 1 && k >= h[digit]; ++j) { k -= h[digit]; ++digit; }
+  const unsigned long long np = (pass == 0 ? 0ULL : st->prefix[arr]) | ((unsigned long long)digit << shift);
+  st->prefix[arr] = np;
+  st->kth[arr] = k;
+  if (pass == INJ_PASSES - 1) {
+    const double v = inj_unkey(np);
+    const long long i = sc->step - 1;
+    double* hh = arr ? histx95 : hist95;
+    if (hh && i >= 0 && i < sc->hist_cap) hh[i] = v;
+    if (v > st->scal[8 + 2 * arr]) {
+      st->scal[8 + 2 * arr] = v;
+      st->scal[9 + 2 * arr] = sc->Time;
+      st->upd[arr] = 1;
+    } else {
+      st->upd[arr] = 0;
     }
   }
 }

@@ -189,6 +189,13 @@ class _DevDouble:
         self.__cuda_array_interface__ = {"shape": (1,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
 
+class _DevInt32:
+    """__cuda_array_interface__ view of n int32 in device memory owned by the C-ABI context."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+
+
 class DistFemTech:
     """One rank of a multi-GPU run: a solver.FemTech plus the exchange, driving the split step API."""
 
@@ -198,6 +205,7 @@ class DistFemTech:
         from . import solver
         self.C, self.torch, self.dist = C, torch, dist
         self.rank, self.world = rank, world
+        self.device = torch.device("cuda", device)
         self.m = solver.FemTech(part["coordinates"], part["connectivity"], part["pid"], materialID, properties,
                                 comm=part["comm"], world_rank=rank, world_size=world, device=device, **kw)
         self.halo = HaloExchange(part["comm"], torch.device("cuda", device), dist)
@@ -259,6 +267,34 @@ class DistFemTech:
             m._check(m.L.ftb200_step_join(m._h))
             self._allreduce_dtmin(ptr)
             m._check(m.L.ftb200_step_end(m._h, self._recv))
+            if self.injury:
+                self._injury_select()
+
+    # --- injury criteria across partitions: the 95th percentile is a global order statistic (math.cpp:160-199) -------
+    injury = False
+
+    def InitInjuryCriterion(self, exclude_pids=(), thresholds=None):
+        import torch
+        m, C = self.m, self.C
+        m.InitInjuryCriterion(exclude_pids, thresholds)
+        n = C.c_longlong()
+        m._check(m.L.ftb200_injury_local_count(m._h, C.byref(n)))
+        with torch.cuda.stream(self.stream):
+            t = torch.tensor([n.value], dtype=torch.int64, device=self.device)
+            self.dist.all_reduce(t)
+        m._check(m.L.ftb200_injury_global_count(m._h, int(t.item())))
+        self.injury = True
+
+    def _injury_select(self):
+        import torch
+        m, C = self.m, self.C
+        hp, hn = C.c_void_p(), C.c_int()
+        for p in range(m.L.ftb200_injury_passes()):
+            m._check(m.L.ftb200_injury_select_hist(m._h, p, C.byref(hp), C.byref(hn)))
+            with torch.cuda.stream(self.stream):
+                h = torch.as_tensor(_DevInt32(hp.value, hn.value), device=self.device)
+                self.dist.all_reduce(h)  # counts < 2^31: int32 sums of the per-rank histograms
+            m._check(m.L.ftb200_injury_select_pick(m._h, p))
 
     def enable_p2p(self, part_comm):
         """Switch the loop to the peer-memory transport: exchange IPC handles and comm patterns once, then
@@ -385,9 +421,42 @@ class LocalGroup:
             self._min_dt(ptrs)
             for r, m in enumerate(self.models):
                 m._check(m.L.ftb200_step_end(m._h, self._ptr(self.recv[r])))
+            if self.injury:
+                self._injury_select()
         self._sync()
         for m in self.models:
             m._poll()
+
+    injury = False
+
+    def InitInjuryCriterion(self, exclude_pids=(), thresholds=None):
+        C = self.C
+        total = 0
+        for m in self.models:
+            m.InitInjuryCriterion(exclude_pids, thresholds)
+            n = C.c_longlong()
+            m._check(m.L.ftb200_injury_local_count(m._h, C.byref(n)))
+            total += n.value
+        for m in self.models:
+            m._check(m.L.ftb200_injury_global_count(m._h, total))
+        self.injury = True
+
+    def _injury_select(self):
+        C, torch = self.C, self.torch
+        dev = self.send[0].device
+        for p in range(self.models[0].L.ftb200_injury_passes()):
+            hs = []
+            for m in self.models:
+                hp, hn = C.c_void_p(), C.c_int()
+                m._check(m.L.ftb200_injury_select_hist(m._h, p, C.byref(hp), C.byref(hn)))
+                hs.append(torch.as_tensor(_DevInt32(hp.value, hn.value), device=dev))
+            self._sync()
+            tot = torch.stack(hs).sum(dim=0).to(torch.int32)  # what the all-reduce does
+            for h in hs:
+                h.copy_(tot)
+            self._sync()
+            for m in self.models:
+                m._check(m.L.ftb200_injury_select_pick(m._h, p))
 
     def enable_p2p(self):
         """Peer-memory transport between the in-process ranks (device pointers instead of IPC handles)."""

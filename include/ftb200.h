@@ -196,9 +196,19 @@ int ftb200_measure_peaks(ftb200_ctx *ctx, int reps, double *fp64_tflops, double 
  * the criteria inside the element force kernel (F never leaves the chip) right after the step's energy check,
  * as ex5.cpp:237-240 does.
  * exclude_pids: parts left out (ex5's injuryExcludePID).  thresholds: NULL = the reference's 0.15, 0.30 (MPS),
- * 120 1/s (MPSR), 28 1/s (MPSxSR), ex5.cpp:1335-1365.  Single partition only in this version (nranks == 1). */
+ * 120 1/s (MPSR), 28 1/s (MPSxSR), ex5.cpp:1335-1365.
+ * Several partitions (nranks > 1): the flags, extrema and lists are per rank as in the reference, but the percentile is
+ * a global order statistic (math.cpp:160-199 gathers every rank's array).  After injury_begin tell every rank the
+ * global number of participating elements (sum of ftb200_injury_local_count), and after each ftb200_step_end run the
+ * ftb200_injury_passes() radix passes: ftb200_injury_select_hist (local histogram into device memory, 2 x 2048
+ * unsigned) -> sum over the ranks (e.g. NCCL all-reduce on *hist_dev) -> ftb200_injury_select_pick. */
 int ftb200_injury_begin(ftb200_ctx *ctx, const int *exclude_pids, int n_exclude, const double *thresholds4);
 int ftb200_injury_end(ftb200_ctx *ctx);
+int ftb200_injury_local_count(ftb200_ctx *ctx, long long *n_included);
+int ftb200_injury_global_count(ftb200_ctx *ctx, long long n_total);
+int ftb200_injury_passes(void);
+int ftb200_injury_select_hist(ftb200_ctx *ctx, int pass, unsigned **hist_dev, int *hist_len);
+int ftb200_injury_select_pick(ftb200_ctx *ctx, int pass);
 /* Results so far.  scalars[12] = maxStrain, time, minStrain, time, maxShear, time, maxPSxSR, time, MPS-95, time,
  * MPSxSR-95, time (ex5.cpp:62-83); extreme_elems[4] = the elements of the first four (caller's element ids);
  * flags[nE]: bit0 MPS>thr0 (CSDM-15), bit1 MPS>thr1 (CSDM-30), bit2 MPSR>thr2, bit3 MPSxSR>thr3, bit4 in the

@@ -576,3 +576,48 @@ def test_mixed_hex_tet_mesh_matches_reference(name):
     dt_legacy = m.ExplicitTimeStepReduction * m.StableTimeStep()
     assert abs(dt_legacy - d["dt"][0]) <= 1e-11 * d["dt"][0]
     m.close()
+
+
+def test_injury_criteria_three_partitions_match_reference():
+    """ex5's injury loop on the reference's own 3-rank ParMETIS partition (fixture inj6_p3): per-rank flags, strains,
+    extrema and lists, and the GLOBAL 95th percentile (math.cpp:160-199 gathers all ranks) through per-pass histogram sums."""
+    from femtech_b200 import dist as fdist
+    g = golden("inj6_p3")
+    P = int(g["nranks"])
+    parts = []
+    for r in range(P):
+        d = rank_dict(g, r)
+        parts.append(dict(coordinates=d["coordinates"], connectivity=d["connectivity"], pid=d["pid"],
+                          comm={k: d[k] for k in ("sendProcessID", "sendNeighbourCountCum", "sendNodeIndex")}))
+    d0 = rank_dict(g, 0)
+    grp = fdist.LocalGroup(parts, d0["materialID"], d0["properties"])
+    grp.setup()
+    for m, p in zip(grp.models, parts):
+        k, rate = mesh.benchmark_bc(p["coordinates"], dMax=float(g["param_dMax"]), tMax=float(g["param_tMax"]))
+        m.set_bc(k, rate)
+    nsteps = int(d0["steps"][0])
+    for m in grp.models:
+        m._check(m.L.ftb200_record_history(m._h, nsteps + 8))
+    grp.explicit_begin(energy_every=1)
+    grp.InitInjuryCriterion(exclude_pids=g["param_exclude"])
+    grp.run(float(g["param_tMax"]), nsteps)
+    for r, m in enumerate(grp.models):
+        d = rank_dict(g, r)
+        m.sync_out()
+        assert int(m.steps_done) == nsteps
+        assert rel(m.displacements, d["displacements"]) < TOL
+        res = m.injury_results()
+        assert np.array_equal(res["elementIDInjury"], d["inj_elems"])
+        assert rel(res["PS_Old"], d["inj_ps_old"]) < TOL and rel(res["PSxSRArray"], d["inj_psxsr"]) < 1e-6
+        for ours, ref in (("MPSgt15", "inj_gt15"), ("MPSgt30", "inj_gt30"), ("MPSRgt120", "inj_r120"), ("MPSxSRgt28", "inj_xsr28")):
+            assert np.array_equal(res[ours].astype(np.int32), d[ref]), (r, ours)
+        sc, want = res["scalars"], d["inj_scalars"]
+        for k in range(12):
+            tol = 1e-6 if k in (6, 10) else TOL
+            assert abs(sc[k] - want[k]) <= tol * abs(want[k]), (r, k, sc[k], want[k])
+        assert np.array_equal(res["extreme_elems"], d["inj_extreme_elems"])
+        assert np.array_equal(res["maxElemListMPS95"], d["inj_list95"]) and np.array_equal(res["maxElemListMPSxSR95"], d["inj_listx95"])
+        h95, hx95 = m.injury_history(0, nsteps)
+        assert rel(h95, d["inj_hist95"]) < TOL and rel(hx95, d["inj_histx95"]) < 1e-6
+        assert rel(res["volumes"], d["inj_volumes"]) < 1e-12
+    grp.close()
