@@ -362,6 +362,17 @@ def _nccl_worker(rank, world, port, q):
     d.m.sync_out()
     d.m._poll()
     q.put((rank, d.m.displacements.copy(), d.m.velocities.copy(), d.m.Time, d.energy()))
+    # injury criteria over NCCL: the percentile is global (histogram all-reduce per radix pass)
+    d.InitInjuryCriterion()
+    d.run(0.1, 5)
+    torch.cuda.synchronize()
+    res = d.m.injury_results()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (res["PS_Old"], float(res["scalars"][8])))
+    allps = np.sort(np.concatenate([g[0] for g in gathered]))
+    k95 = int(allps.size * 0.95) - 1
+    assert all(g[1] == gathered[0][1] for g in gathered), "MPS-95 must be the same on every rank"
+    assert gathered[0][1] >= allps[k95] and (gathered[0][1] == allps[k95] or allps[k95] < gathered[0][1])
     dist.destroy_process_group()
 
 
