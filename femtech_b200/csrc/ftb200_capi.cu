@@ -83,6 +83,7 @@ struct ftb200_ctx {
   int nTilesE = 0, nTilesN = 0, nChunks = 0;
   int elem_grid = 0, node_grid = 0;
   bool pipe = false;
+  bool node_ell = true;   // k_node gathers through the fixed-width map (FTB200_NODE_ELL=0: CSR loop)
   bool fuse_adv = false;  // opt-in FTB200_FUSE_ADV=1: k_adv + k_energy folded into k_node's last block.  Measured slower
                           // (k_node 98 -> 115 us at 100^3: every block pays a fence + atomic round trip) than the two
                           // tiny kernels it saves (14 us), so the four-launch step stays the default.
@@ -207,6 +208,7 @@ NodeArgs node_args(ftb200_ctx* c, const double* recv) {
   A.dt_hist = c->dthist; A.ehist = c->ehist; A.mp_rw = c->mp; A.nPID = c->nPID;
   for (int k = 0; k < 3; ++k) { A.X[k] = c->X[k]; A.aprev[k] = c->aprev[k]; }
   A.rigid = c->rigid;
+  A.ell = c->node_ell ? c->d_ell : nullptr;
   A.halo_recv_alt = nullptr;
   A.p2p_seq = nullptr;
   return A;
@@ -853,6 +855,7 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       ctx->fused = false;
       if (const char* ev = getenv("FTB200_FUSED")) ctx->fused = atoi(ev) != 0;
       if (const char* ev = getenv("FTB200_FUSE_ADV")) ctx->fuse_adv = atoi(ev) != 0;
+      if (const char* ev = getenv("FTB200_NODE_ELL")) ctx->node_ell = atoi(ev) != 0;
       if (ctx->has_tet) { ctx->fused = false; ctx->pipe = false; }  // the one-kernel variants are hexahedra only
     }
     ctx->node_grid = std::max(1, std::min(prop.multiProcessorCount * nb, nTilesN));

@@ -431,6 +431,7 @@ __global__ void k_rigid_step(const DevScalars* sc, DevRigid* rb, const int begin
 
 // ---------------------------------------------------------------------------------------------
 struct NodeArgs {
+  const int* ell;       // fixed-width node -> (element, slot) map [8][nN], or nullptr (CSR loop)
   const double* X[3];   // reference coordinates (rigid-body nodes only)
   const DevRigid* rigid;  // or nullptr
   double* aprev[3];     // previous acceleration of the rigid-body nodes (energy check), or nullptr planes
@@ -515,14 +516,39 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_node(const NodeArgs A) {
     if (FINISH) {
       // deterministic assembly: ascending element id (GetForce_3D.cpp:15,39-44)
       double f[3] = {0.0, 0.0, 0.0};
-      const int j0 = A.node_off[n], j1 = A.node_off[n + 1];
       const size_t E = (size_t)A.nE;
-      for (int j = j0; j < j1; ++j) {
-        const int ent = __ldg(A.node_ent + j);
-        const size_t e = (size_t)(ent >> 3);
-        const int s = ent & 7;
+      if (A.ell) {
+        // fixed-width map [8][nN] (-1 = no entry): the 8 entries and then all 24 force loads are issued before the
+        // first add, instead of a dependent load per trip of a variable-length loop; same ascending order
+        int ent[8];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) f[c] += __ldg(A.felem + (size_t)(3 * s + c) * E + e);
+        for (int q = 0; q < 8; ++q) ent[q] = __ldg(A.ell + (size_t)q * A.nN + n);
+        double fv[8][3];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int en = ent[q] < 0 ? 0 : ent[q];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) fv[q][c] = (ent[q] >= 0) ? __ldg(A.felem + (size_t)(3 * (en & 7) + c) * E + (size_t)(en >> 3)) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)  // + 0.0 for a missing entry is exact
+#pragma unroll
+          for (int c = 0; c < 3; ++c) f[c] += fv[q][c];
+        if (fl & FTB_FLAG_OVERFLOW)
+          for (int j = A.node_off[n] + 8, j1 = A.node_off[n + 1]; j < j1; ++j) {
+            const int en = __ldg(A.node_ent + j);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) f[c] += __ldg(A.felem + (size_t)(3 * (en & 7) + c) * E + (size_t)(en >> 3));
+          }
+      } else {
+        const int j0 = A.node_off[n], j1 = A.node_off[n + 1];
+        for (int j = j0; j < j1; ++j) {
+          const int ent = __ldg(A.node_ent + j);
+          const size_t e = (size_t)(ent >> 3);
+          const int s = ent & 7;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) f[c] += __ldg(A.felem + (size_t)(3 * s + c) * E + e);
+        }
       }
       if (A.halo_node_idx) {  // shared node: add the neighbours' partial sums, ascending neighbour (:92-97)
         const int h = A.halo_node_idx[n];
