@@ -52,15 +52,19 @@ static void check(int rc) {
 static void ensure_ctx() {
   if (g_ctx) return;
   if (ndim != 3) { FILE_LOG_SINGLE(ERROR, "femtech_b200 supports ndim == 3 only"); TerminateFemTech(3); }
-  for (int e = 0; e < nelements; ++e)
-    if (strcmp(ElementType[e], "C3D8") != 0 || eptr[e + 1] - eptr[e] != 8) {
-      FILE_LOG_SINGLE(ERROR, "femtech_b200 hot path is hex8 (C3D8) only; element %d is %s", e, ElementType[e]);
+  for (int e = 0; e < nelements; ++e) {  /* the solid elements of the reference: C3D8 and C3D4 (ShapeFunctions.cpp:71-164) */
+    const bool hex = strcmp(ElementType[e], "C3D8") == 0 && eptr[e + 1] - eptr[e] == 8;
+    const bool tet = strcmp(ElementType[e], "C3D4") == 0 && eptr[e + 1] - eptr[e] == 4;
+    if (!hex && !tet) {
+      FILE_LOG_SINGLE(ERROR, "femtech_b200 replaces the C3D8 / C3D4 path; element %d is %s with %d nodes", e, ElementType[e],
+                      eptr[e + 1] - eptr[e]);
       TerminateFemTech(3);
     }
+  }
   int ndev_rank = world_rank;  /* one rank per GPU */
   const char *ev = getenv("FTB200_DEVICE");
   check(ftb200_create(world_rank, world_size, ev ? atoi(ev) : ndev_rank, &g_ctx));
-  check(ftb200_upload_mesh(g_ctx, coordinates, connectivity, pid, nNodes, nelements));
+  check(ftb200_upload_mesh_mixed(g_ctx, coordinates, connectivity, eptr, pid, nNodes, nelements));
   check(ftb200_upload_materials(g_ctx, materialID, properties, nPIDglobal));
   check(ftb200_upload_comm(g_ctx, sendProcessCount, sendProcessID, sendNeighbourCountCum, sendNodeIndex));
 }
@@ -107,10 +111,15 @@ void ShapeFunctions() {
   gpPtr = (int *)malloc((nelements + 1) * sizeof(int)); fptr = (int *)malloc((nelements + 1) * sizeof(int));
   pk2ptr = (int *)malloc((nelements + 1) * sizeof(int)); detFptr = (int *)malloc((nelements + 1) * sizeof(int));
   InternalsPtr = (int *)malloc((nelements + 1) * sizeof(int));
-  for (int i = 0; i <= nelements; ++i) {  /* hex8: ShapeFunctions.cpp:71-122,157-164 */
-    gptr[i] = 64 * i; dsptr[i] = 192 * i; gpPtr[i] = 8 * i; fptr[i] = 72 * i; pk2ptr[i] = 48 * i; detFptr[i] = 8 * i;
-    InternalsPtr[i] = MAXINTERNALVARS * 8 * i;
-    if (i < nelements) { GaussPoints[i] = 8; nShapeFunctions[i] = 8; }
+  int ngp = 0, nshp = 0;  /* offset tables of ShapeFunctions.cpp:71-164: 8 points x 8 functions (C3D8), 1 x 4 (C3D4) */
+  for (int i = 0; i <= nelements; ++i) {
+    gptr[i] = nshp; dsptr[i] = 3 * nshp; gpPtr[i] = ngp; fptr[i] = 9 * ngp; pk2ptr[i] = 6 * ngp; detFptr[i] = ngp;
+    InternalsPtr[i] = MAXINTERNALVARS * ngp;
+    if (i < nelements) {
+      const bool tet = eptr[i + 1] - eptr[i] == 4;
+      GaussPoints[i] = tet ? 1 : 8; nShapeFunctions[i] = tet ? 4 : 8;
+      ngp += GaussPoints[i]; nshp += GaussPoints[i] * nShapeFunctions[i];
+    }
   }
   double minDetJ = 0;
   check(ftb200_shape_functions(g_ctx, &minDetJ));
@@ -187,9 +196,9 @@ void CheckEnergy(double time, int writeFlag) {
 
 /* ---- src/elements/ElementCalculations/CalculateStrain.cpp:77-97 + lazy Gauss-point outputs --------------- */
 void CalculateStrain() {
-  if (!F) F = (double *)calloc((size_t)72 * nelements, sizeof(double));
-  if (!detF) detF = (double *)calloc((size_t)8 * nelements, sizeof(double));
-  if (!pk2) pk2 = (double *)calloc((size_t)48 * nelements, sizeof(double));
+  if (!F) F = (double *)calloc((size_t)fptr[nelements] + 1, sizeof(double));
+  if (!detF) detF = (double *)calloc((size_t)detFptr[nelements] + 1, sizeof(double));
+  if (!pk2) pk2 = (double *)calloc((size_t)pk2ptr[nelements] + 1, sizeof(double));
   check(ftb200_get_gp_outputs(g_ctx, F, detF, pk2, Eavg));
 }
 

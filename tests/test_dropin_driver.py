@@ -105,3 +105,25 @@ def test_legacy_injury_loop_through_reference_symbols(tmp_path):
         assert np.array_equal(o[k], d[k]), k
     assert rel(o["inj_hist95"], d["inj_hist95"]) < 1e-9 and rel(o["inj_volumes"], d["inj_volumes"]) < 1e-12
     assert rel(o["Eavg"], d["Eavg"]) < 1e-9
+
+
+def test_mixed_mesh_through_reference_reader_and_symbols(tmp_path):
+    """A C3D8 + C3D4 .inp file read by the reference's own reader/partitioner, integrated by femtech_b200 under the
+    reference's symbol names (harness driver), vs the all-reference fixture mix4_p1."""
+    exe = _need("dropin_ref_dump")
+    from conftest import golden, rank_dict
+    from oracle import pyoracle as po
+    g = golden("mix4_p1")
+    d = rank_dict(g, 0)
+    etype = ["C3D8" if n == 8 else "C3D4" for n in np.diff(d["eptr"])]
+    mesh.write_abaqus_inp_mixed(str(tmp_path / "mix.inp"), d["coordinates"].reshape(-1, 3), d["connectivity"], d["eptr"], d["pid"], etype)
+    mesh.write_materials_dat(str(tmp_path / "materials.dat"), d["materialID"], d["properties"])
+    r = subprocess.run([exe, "mix.inp", "out", "150", repr(float(g["param_tMax"])), repr(float(g["param_dMax"]))],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    o = po.read_ref_dump(str(tmp_path / "out.rank0.bin"))
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    assert int(o["steps"][0]) == int(d["steps"][0]) and np.array_equal(o["eptr"], d["eptr"])
+    assert rel(o["displacements"], d["displacements"]) < 1e-9 and rel(o["mass"], d["mass"]) < 1e-13
+    assert o["F"].size == d["F"].size and rel(o["F"], d["F"]) < 1e-9 and rel(o["pk2"], d["pk2"]) < 1e-9
+    assert rel(o["Eavg"], d["Eavg"]) < 1e-9
