@@ -160,6 +160,19 @@ int fail(ftb200_ctx* c, int code, const char* fmt, ...) {
     ctx->launches++;                                    \
   } while (0)
 
+// material-5 element kernels: the two-stage history buffer is dynamic shared memory beyond the 48 KB static limit
+#define LAUNCH_HIST(kern, grid, block, strm, ...)                                                        \
+  do {                                                                                                   \
+    auto kfn_ = kern;                                                                                    \
+    static bool attr_set_ = false;                                                                       \
+    if (!attr_set_) {                                                                                    \
+      cudaFuncSetAttribute(kfn_, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_STAGE_BYTES);         \
+      attr_set_ = true;                                                                                  \
+    }                                                                                                    \
+    kfn_<<<(grid), (block), HIST_STAGE_BYTES, (strm)>>>(__VA_ARGS__);                                    \
+    ctx->launches++;                                                                                     \
+  } while (0)
+
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 template <class T>
@@ -252,7 +265,7 @@ void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore
     switch (ctx->uniform_mat) {
       case 1: LAUNCH((k_elem<1, true, true, true>), grid, ELEM_BLOCK, s, A); break;
       case 4: LAUNCH((k_elem<4, true, true, true>), grid, ELEM_BLOCK, s, A); break;
-      case 5: LAUNCH((k_elem<5, true, true, true>), grid, ELEM_BLOCK, s, A); break;
+      case 5: LAUNCH_HIST((k_elem<5, true, true, true>), grid, ELEM_BLOCK, s, A); break;
       default: LAUNCH((k_elem<-1, true, true, true>), grid, ELEM_BLOCK, s, A); break;
     }
     return;
@@ -260,7 +273,7 @@ void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore
   switch (ctx->uniform_mat) {
     case 1: LAUNCH((k_elem<1, WITH_FORCE, WITH_DT>), grid, ELEM_BLOCK, s, A); break;
     case 4: LAUNCH((k_elem<4, WITH_FORCE, WITH_DT>), grid, ELEM_BLOCK, s, A); break;
-    case 5: LAUNCH((k_elem<5, WITH_FORCE, WITH_DT>), grid, ELEM_BLOCK, s, A); break;
+    case 5: LAUNCH_HIST((k_elem<5, WITH_FORCE, WITH_DT>), grid, ELEM_BLOCK, s, A); break;
     default: LAUNCH((k_elem<-1, WITH_FORCE, WITH_DT>), grid, ELEM_BLOCK, s, A); break;
   }
 }

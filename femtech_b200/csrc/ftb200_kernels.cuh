@@ -80,6 +80,59 @@ struct DevHist {
   }
 };
 
+#ifndef FTB_ELEM_BLOCK
+#define FTB_ELEM_BLOCK 64
+#endif
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+// Prony history of the viscoelastic material with the loads of Gauss point gp + 1 in flight while gp is integrated:
+// 18 doubles per point are copied global -> shared (cp.async, no registers) into a two-stage buffer; load(gp) waits
+// for its stage and immediately issues the next one.  With 36 history doubles per Gauss point and only 8 warps per
+// SM the plain loads left the kernel latency-bound at ~60 % of the HBM roof.
+struct DevHistStaged {
+  double* base;   // [3][6][8][E]
+  size_t E;
+  size_t e;
+  double* stage;  // &stage_smem[0][threadIdx.x], layout [2][18][FTB_ELEM_BLOCK]
+  __device__ __forceinline__ void prefetch(int gp) const {
+    double* st = stage + (size_t)(gp & 1) * 18 * FTB_ELEM_BLOCK;
+#pragma unroll
+    for (int j = 0; j < 18; ++j) cp_async8(st + j * FTB_ELEM_BLOCK, base + ((size_t)j * 8 + gp) * E + e);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  __device__ __forceinline__ void load(int gp, GpHistory& g) const {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const double* st = stage + (size_t)(gp & 1) * 18 * FTB_ELEM_BLOCK;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      g.h1[i] = st[(0 * 6 + i) * FTB_ELEM_BLOCK];
+      g.h2[i] = st[(1 * 6 + i) * FTB_ELEM_BLOCK];
+      g.s0[i] = st[(2 * 6 + i) * FTB_ELEM_BLOCK];
+    }
+    if (gp < 7) prefetch(gp + 1);
+  }
+  __device__ __forceinline__ void store(int gp, const GpHistory& g) const {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      base[((size_t)(0 * 6 + i) * 8 + gp) * E + e] = g.h1[i];
+      base[((size_t)(1 * 6 + i) * 8 + gp) * E + e] = g.h2[i];
+      base[((size_t)(2 * 6 + i) * 8 + gp) * E + e] = g.s0[i];
+    }
+  }
+};
+
+template <bool STAGED>
+struct HistSel {
+  static __device__ __forceinline__ DevHist make(double* b, size_t E, size_t e, double*) { return DevHist{b, E, e}; }
+};
+template <>
+struct HistSel<true> {
+  static __device__ __forceinline__ DevHistStaged make(double* b, size_t E, size_t e, double* st) { return DevHistStaged{b, E, e, st}; }
+};
+constexpr int HIST_STAGE_BYTES = 2 * 18 * FTB_ELEM_BLOCK * (int)sizeof(double);
+
 struct ElemArgs {
   const double* X[3];
   const double* u[3];
@@ -133,10 +186,6 @@ struct SmemScratch {
 // global -> shared with cp.async (no registers) into the column slots they will later overwrite, so all 48 gathers
 // of an element are in flight at once although only 16 values occupy registers.  (Left to itself ptxas sinks the
 // last third of the loads behind the first butterflies to save registers: a second exposed memory latency.)
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
 struct StagedIn {
   const double* x0;  // [8] component 0, registers
   const double* u0;
@@ -175,6 +224,12 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
   }
   if (!A.ignore_loop_flags && (A.sc->last | A.sc->done)) return;
   __shared__ double sm_cols[WITH_FORCE ? 72 : 1][ELEM_BLOCK];
+  extern __shared__ double sm_hstage[];  // material 5 only: [2][18][ELEM_BLOCK] (dynamic: beyond the 48 KB static limit)
+  constexpr bool STAGED_HIST = WITH_FORCE && MATSEL == 5;
+  if (STAGED_HIST && e < A.e1) {  // the history address does not depend on the connectivity: first thing in flight
+    const DevHistStaged hs{A.hist, E, (size_t)e, sm_hstage + threadIdx.x};
+    hs.prefetch(0);
+  }
   double dte = 1e300;
   int status = 0;
   if (e < A.e1) {
@@ -207,7 +262,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
     const int mat = (MATSEL >= 0) ? MATSEL : (int)mp[MP_MATID];
     if (WITH_FORCE) {
       double fe[8][3];
-      DevHist h{A.hist, E, (size_t)e};
+      const auto h = HistSel<STAGED_HIST>::make(A.hist, E, (size_t)e, sm_hstage + threadIdx.x);
       double d;
       SmemScratch S{&sm_cols[0][threadIdx.x]};
       if (WITH_INJ) {
