@@ -794,7 +794,7 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
     CK(cudaMemset(ctx->d_etile_e, 0, 2 * 3 * (size_t)nTN * sizeof(double)));
   }
   if (ctx->has_visco) {  // Hn_1, Hn_2, S0n zero at t = 0 (ShapeFunctions.cpp:245-252)
-    const size_t n = (size_t)3 * 6 * 8 * nE;
+    const size_t n = (size_t)144 * 32 * cdiv(nE, 32);  // tiles of 32 elements (FTB_HIDX)
     if ((rc = dalloc(ctx, &ctx->hist, n))) return rc;
     CK(cudaMemset(ctx->hist, 0, n * sizeof(double)));
   }
