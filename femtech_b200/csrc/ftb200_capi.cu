@@ -723,7 +723,7 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
   ctx->node_blocks = cdiv(nNp, NODE_BLOCK);
   if ((rc = dalloc(ctx, &ctx->m, nNp)) || (rc = dalloc(ctx, &ctx->flags, nNp)) || (rc = dalloc(ctx, &ctx->conn, 8 * (size_t)nE)) ||
       (rc = dalloc(ctx, &ctx->pid, nE)) || (rc = dalloc(ctx, &ctx->ref_of, nE)) || (rc = dalloc(ctx, &ctx->eflag, nE)) ||
-      (rc = dalloc(ctx, &ctx->felem, 24 * (size_t)nE)) || (rc = dalloc(ctx, &ctx->mp, mp.size())) ||
+      (rc = dalloc(ctx, &ctx->felem, 24 * 32 * (size_t)cdiv(nE, 32))) || (rc = dalloc(ctx, &ctx->mp, mp.size())) ||
       (rc = dalloc(ctx, &ctx->node_off, nNp + 1)) || (rc = dalloc(ctx, &ctx->node_ent, 8 * (size_t)nE)) ||
       (rc = dalloc(ctx, &ctx->sc, 1)) || (rc = dalloc(ctx, &ctx->epart, 3 * (size_t)std::max(ctx->node_blocks, cdiv(nN, NODE_BLOCK)))) ||
       (rc = dalloc(ctx, &ctx->out3, 4)) || (rc = dalloc(ctx, &ctx->d_istage, 3 * (size_t)nN)) ||
@@ -734,7 +734,7 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
     return rc;
   CK(cudaMemset(ctx->m, 0, nNp * sizeof(double)));
   CK(cudaMemset(ctx->eflag, 0, nE));
-  CK(cudaMemset(ctx->felem, 0, 24 * (size_t)nE * sizeof(double)));
+  CK(cudaMemset(ctx->felem, 0, 24 * 32 * (size_t)cdiv(nE, 32) * sizeof(double)));  // tiles of 32 elements (FTB_FIDX)
   CK(cudaMemset(ctx->sc, 0, sizeof(DevScalars)));
   CK(cudaMemset(ctx->d_etile, 0, 3 * (size_t)nTilesN * sizeof(double)));
   CK(cudaMemcpy(ctx->conn, connT.data(), connT.size() * sizeof(int), cudaMemcpyHostToDevice));

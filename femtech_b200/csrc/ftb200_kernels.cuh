@@ -63,6 +63,10 @@ __device__ __forceinline__ unsigned long long dt_to_bits(double v) {
 // value, but all 144 values of an element now sit in one tile (plane-major [144][E] put them 8 MB apart: one TLB entry
 // and one DRAM page per value; measured +2.4 % on the material-5 kernel).
 #define FTB_HIDX(j, gp, e) ((((size_t)(e) >> 5) * 144 + (size_t)(j) * 8 + (size_t)(gp)) * 32 + ((size_t)(e) & 31))
+// Element force planes, same tiling: 32 consecutive elements x 24 values (8 nodes x 3 components) per 6 KB tile.  K_elem
+// writes one contiguous tile per warp, K_node finds the three components of an (element, node) entry 256 B apart
+// instead of in three planes 8 MB apart.
+#define FTB_FIDX(s3, e) ((((size_t)(e) >> 5) * 24 + (size_t)(s3)) * 32 + ((size_t)(e) & 31))
 struct DevHist {
   double* base;  // [3][6][8][E]
   size_t E;
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
 #pragma unroll
       for (int k = 0; k < 8; ++k)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) A.felem[(size_t)(3 * k + c) * E + e] = fe[k][c];
+        for (int c = 0; c < 3; ++c) A.felem[FTB_FIDX(3 * k + c, e)] = fe[k][c];
     } else {
       // dt only (legacy StableTimeStep, and the pre-pass of explicit_begin)
       double xm[7][3];
@@ -370,7 +374,7 @@ __global__ void __launch_bounds__(TET_BLOCK) k_elem_tet(const ElemArgs A) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) A.felem[(size_t)(3 * k + c) * E + e] = fe[k][c];
+        for (int c = 0; c < 3; ++c) A.felem[FTB_FIDX(3 * k + c, e)] = fe[k][c];
     }
   }
   if (WITH_DT) {
@@ -588,7 +592,7 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_node(const NodeArgs A) {
         for (int q = 0; q < 8; ++q) {
           const int en = ent[q] < 0 ? 0 : ent[q];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) fv[q][c] = (ent[q] >= 0) ? __ldg(A.felem + (size_t)(3 * (en & 7) + c) * E + (size_t)(en >> 3)) : 0.0;
+          for (int c = 0; c < 3; ++c) fv[q][c] = (ent[q] >= 0) ? __ldg(A.felem + FTB_FIDX(3 * (en & 7) + c, en >> 3)) : 0.0;
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q)  // + 0.0 for a missing entry is exact
@@ -598,7 +602,7 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_node(const NodeArgs A) {
           for (int j = A.node_off[n] + 8, j1 = A.node_off[n + 1]; j < j1; ++j) {
             const int en = __ldg(A.node_ent + j);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) f[c] += __ldg(A.felem + (size_t)(3 * (en & 7) + c) * E + (size_t)(en >> 3));
+            for (int c = 0; c < 3; ++c) f[c] += __ldg(A.felem + FTB_FIDX(3 * (en & 7) + c, en >> 3));
           }
       } else {
         const int j0 = A.node_off[n], j1 = A.node_off[n + 1];
@@ -607,7 +611,7 @@ __global__ void __launch_bounds__(NODE_BLOCK) k_node(const NodeArgs A) {
           const size_t e = (size_t)(ent >> 3);
           const int s = ent & 7;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) f[c] += __ldg(A.felem + (size_t)(3 * s + c) * E + e);
+          for (int c = 0; c < 3; ++c) f[c] += __ldg(A.felem + FTB_FIDX(3 * s + c, e));
         }
       }
       if (A.halo_node_idx) {  // shared node: add the neighbours' partial sums, ascending neighbour (:92-97)
@@ -1046,7 +1050,7 @@ __global__ void k_gather_force(const NodeArgs A, double* fnx, double* fny, doubl
     const size_t e = (size_t)(ent >> 3);
     const int s = ent & 7;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) f[c] += A.felem[(size_t)(3 * s + c) * E + e];
+    for (int c = 0; c < 3; ++c) f[c] += A.felem[FTB_FIDX(3 * s + c, e)];
   }
   if (A.halo_node_idx && A.halo_recv) {
     const int h = A.halo_node_idx[n];
@@ -1161,7 +1165,7 @@ __global__ void k_gather_shared(const double* felem, const int* node_off, const 
     const size_t e = (size_t)(ent >> 3);
     const int s = ent & 7;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) f[c] += felem[(size_t)(3 * s + c) * nE + e];
+    for (int c = 0; c < 3; ++c) f[c] += felem[FTB_FIDX(3 * s + c, e)];
   }
   fx[n] = f[0]; fy[n] = f[1]; fz[n] = f[2];
 }
@@ -1357,7 +1361,7 @@ __global__ void k_p2p_pack(const P2PArgs P, const double* felem, const int* node
       const size_t e = (size_t)(ent >> 3);
       const int sl = ent & 7;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) f[c] += felem[(size_t)(3 * sl + c) * nE + e];
+      for (int c = 0; c < 3; ++c) f[c] += felem[FTB_FIDX(3 * sl + c, e)];
     }
     double* dst = p2p_recv(P.peer_nb[nb], P.peer_H[nb], buf) + 3 * (size_t)(P.peer_slot_off[nb] + (i - P.nb_cum[nb]));
     dst[0] = f[0]; dst[1] = f[1]; dst[2] = f[2];  // peer store over NVLink
@@ -1592,7 +1596,7 @@ __global__ void __maxnreg__(FTB_PIPE_ELEM_REGS) k_elem_pipe(const PipeElemArgs P
 #pragma unroll
       for (int k = 0; k < 8; ++k)
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) __stcg(A.felem + (size_t)(3 * k + cc) * E + e, fe[k][cc]);
+        for (int cc = 0; cc < 3; ++cc) __stcg(A.felem + FTB_FIDX(3 * k + cc, e), fe[k][cc]);
       if (__ldg(A.eflag + e)) dte = 1e300;  // element skipped, StableTimeStep.cpp:13-19
     }
     unsigned long long b = dt_to_bits(dte);
@@ -1723,7 +1727,7 @@ __global__ void __maxnreg__(96) k_node_pipe(const PipeNodeArgs P) {
       const size_t e = (size_t)((ent[q] < 0 ? 0 : ent[q]) >> 3);
       const int sl = (ent[q] < 0 ? 0 : ent[q]) & 7;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) fv[q][c] = (ent[q] >= 0) ? A.felem[(size_t)(3 * sl + c) * E + e] : 0.0;
+      for (int c = 0; c < 3; ++c) fv[q][c] = (ent[q] >= 0) ? A.felem[FTB_FIDX(3 * sl + c, e)] : 0.0;
     }
     double f[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -1736,7 +1740,7 @@ __global__ void __maxnreg__(96) k_node_pipe(const PipeNodeArgs P) {
       const size_t e = (size_t)(en >> 3);
       const int sl = en & 7;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) f[c] += A.felem[(size_t)(3 * sl + c) * E + e];
+      for (int c = 0; c < 3; ++c) f[c] += A.felem[FTB_FIDX(3 * sl + c, e)];
     }
     double wke = 0.0, wint = 0.0, wext = 0.0;
 #pragma unroll
@@ -1968,7 +1972,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
 #pragma unroll
         for (int k = 0; k < 8; ++k)
 #pragma unroll
-          for (int cc = 0; cc < 3; ++cc) __stcg(A.felem + (size_t)(3 * k + cc) * E + e, fe[k][cc]);
+          for (int cc = 0; cc < 3; ++cc) __stcg(A.felem + FTB_FIDX(3 * k + cc, e), fe[k][cc]);
         dte = __ldg(A.eflag + e) ? 1e300 : d;  // element skipped, StableTimeStep.cpp:13-19
       }
       const unsigned long long b = dt_to_bits(dte);
@@ -2006,7 +2010,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
           const size_t e = (size_t)((ent[q] < 0 ? 0 : ent[q]) >> 3);
           const int sl = (ent[q] < 0 ? 0 : ent[q]) & 7;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) fv[q][c] = (ent[q] >= 0) ? __ldcg(A.felem + (size_t)(3 * sl + c) * E + e) : 0.0;
+          for (int c = 0; c < 3; ++c) fv[q][c] = (ent[q] >= 0) ? __ldcg(A.felem + FTB_FIDX(3 * sl + c, e)) : 0.0;
         }
         double f[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -2017,7 +2021,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
           for (int j = Nd.node_off[n] + 8, j1 = Nd.node_off[n + 1]; j < j1; ++j) {
             const int en = __ldg(Nd.node_ent + j);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) f[c] += __ldcg(A.felem + (size_t)(3 * (en & 7) + c) * E + (size_t)(en >> 3));
+            for (int c = 0; c < 3; ++c) f[c] += __ldcg(A.felem + FTB_FIDX(3 * (en & 7) + c, en >> 3));
           }
         double wke = 0.0, wint = 0.0, wext = 0.0;
 #pragma unroll
