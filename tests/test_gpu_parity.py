@@ -632,3 +632,27 @@ def test_injury_criteria_three_partitions_match_reference():
         assert rel(h95, d["inj_hist95"]) < TOL and rel(hx95, d["inj_histx95"]) < 1e-6
         assert rel(res["volumes"], d["inj_volumes"]) < 1e-12
     grp.close()
+
+
+def test_brain_like_example_runs_all_next_rows_together(tmp_path):
+    """examples/brain_like.py at a small size: rigid shell + soft layer + viscoelastic core, rigid-body motion, injury criteria,
+    VTU output -- the rows of SURVEY.md 8(f) in one resident run; energy balance within the reference's 1 % criterion."""
+    import importlib.util
+    import sys
+    from conftest import ROOT
+    import os
+    spec = importlib.util.spec_from_file_location("brain_like", os.path.join(ROOT, "examples", "brain_like.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    argv = sys.argv
+    sys.argv = ["brain_like.py", "--n", "12", "--t-end", "0.0004", "--vtu", str(tmp_path / "b.vtu")]
+    try:
+        steps, r, e = mod.main()
+    finally:
+        sys.argv = argv
+    assert steps > 10 and np.all(np.isfinite(r["scalars"])) and r["scalars"][0] > 0
+    wint, wext, wke, bal = e
+    assert bal <= 0.01 * max(wint, wext, wke)  # CheckEnergy.cpp:66-72
+    from femtech_b200 import io as fio
+    a = fio.read_vtu_arrays(str(tmp_path / "b.vtu"))
+    assert a["PartID"].size == 12 ** 3 and set(np.unique(a["PartID"])) == {0, 1, 2} and "CSDM-15" in a
