@@ -44,6 +44,8 @@ struct ftb200_ctx {
   bool has_tet = false;
   long long nGP = 0;              // Gauss points of the mesh (8 nE without tetrahedra)
   int nEb_hex = 0, nEi_hex = 0;   // hexahedra among the boundary / interior elements (they come first in each class)
+  struct ElemRange { int e0, e1, tet, mat; };
+  std::vector<ElemRange> ranges;  // internal element order = runs of equal (class, element type, material)
   // rigid-body prescribed motion (ftb200_set_rigid_bc)
   DevRigid* rigid = nullptr;
   double *rigid_tab = nullptr, *aprev[3] = {nullptr, nullptr, nullptr};
@@ -229,7 +231,7 @@ NodeArgs node_args(ftb200_ctx* c, const double* recv) {
 
 // element kernel dispatch on the (uniform) material of the launch
 template <bool WITH_FORCE, bool WITH_DT>
-void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore);
+void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore, int mat);
 
 template <bool WITH_FORCE, bool WITH_DT>
 void launch_elem_tet(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore) {
@@ -240,29 +242,27 @@ void launch_elem_tet(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore
   else LAUNCH((k_elem_tet<WITH_FORCE, WITH_DT, false>), grid, TET_BLOCK, s, A);
 }
 
-// [e0, e1) of the internal order = [boundary hex | boundary tet | interior hex | interior tet] (no tets: one launch)
+// [e0, e1) of the internal order is cut into runs of equal (element type, material): every run gets the kernel
+// specialised for its material (a uniform mesh is one run = one launch, as before)
 template <bool WITH_FORCE, bool WITH_DT>
 void launch_elem(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore) {
   if (e1 <= e0) return;
-  if (!ctx->has_tet) { launch_elem_hex<WITH_FORCE, WITH_DT>(ctx, s, e0, e1, ignore); return; }
-  const int nb = ctx->nE_boundary;
-  const int cut[5] = {0, ctx->nEb_hex, nb, nb + ctx->nEi_hex, ctx->nE};
-  for (int c = 0; c < 4; ++c) {
-    const int a = std::max(e0, cut[c]), b = std::min(e1, cut[c + 1]);
+  for (const auto& r : ctx->ranges) {
+    const int a = std::max(e0, r.e0), b = std::min(e1, r.e1);
     if (b <= a) continue;
-    if (c & 1) launch_elem_tet<WITH_FORCE, WITH_DT>(ctx, s, a, b, ignore);
-    else launch_elem_hex<WITH_FORCE, WITH_DT>(ctx, s, a, b, ignore);
+    if (r.tet) launch_elem_tet<WITH_FORCE, WITH_DT>(ctx, s, a, b, ignore);
+    else launch_elem_hex<WITH_FORCE, WITH_DT>(ctx, s, a, b, ignore, r.mat);
   }
 }
 
 template <bool WITH_FORCE, bool WITH_DT>
-void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore) {
+void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore, int mat) {
   if (e1 <= e0) return;
   const ElemArgs A = elem_args(ctx, e0, e1, ignore);
   const int grid = cdiv(e1 - e0, ELEM_BLOCK);
   if (!WITH_FORCE) { LAUNCH((k_elem<-1, false, true>), grid, ELEM_BLOCK, s, A); return; }
   if (WITH_FORCE && WITH_DT && ctx->injury && !ignore) {  // a step of the loop with the injury criteria on
-    switch (ctx->uniform_mat) {
+    switch (mat) {
       case 1: LAUNCH((k_elem<1, true, true, true>), grid, ELEM_BLOCK, s, A); break;
       case 4: LAUNCH((k_elem<4, true, true, true>), grid, ELEM_BLOCK, s, A); break;
       case 5: LAUNCH_HIST((k_elem<5, true, true, true>), grid, ELEM_BLOCK, s, A); break;
@@ -270,7 +270,7 @@ void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore
     }
     return;
   }
-  switch (ctx->uniform_mat) {
+  switch (mat) {
     case 1: LAUNCH((k_elem<1, WITH_FORCE, WITH_DT>), grid, ELEM_BLOCK, s, A); break;
     case 4: LAUNCH((k_elem<4, WITH_FORCE, WITH_DT>), grid, ELEM_BLOCK, s, A); break;
     case 5: LAUNCH_HIST((k_elem<5, WITH_FORCE, WITH_DT>), grid, ELEM_BLOCK, s, A); break;
@@ -597,16 +597,34 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
         nb += isb[e];
       }
     ctx->nE_boundary = nb;
-    // inside each class the hexahedra come first, the tetrahedra after them (their own kernel), caller's order kept
+    // inside each class: hexahedra first, tetrahedra after them (their own kernel); inside each type by material id, so
+    // that every run of the internal order is uniform and gets the kernel specialised for it; caller's order kept
     const bool mixed = ctx->has_tet;
-    int nbh = 0, nih = 0;
-    for (int e = 0; e < nE; ++e)
-      if (!(mixed && ctx->h_etype[e])) (isb[e] ? nbh : nih)++;
-    ctx->nEb_hex = nbh; ctx->nEi_hex = nih;
-    int cur[4] = {0, nbh, nb, nb + nih};  // boundary hex, boundary tet, interior hex, interior tet
+    constexpr int NM = 6;  // material ids 0..5 (StressUpdate.cpp:7-27)
+    auto bucket = [&](int e) {
+      const int mid = ctx->h_matid[ctx->h_pid[e]];
+      const int mslot = (mid >= 0 && mid < NM) ? mid : 0;  // unknown ids go with the generic kernel, which reports them
+      return ((isb[e] ? 0 : 1) * 2 + ((mixed && ctx->h_etype[e]) ? 1 : 0)) * NM + mslot;
+    };
+    std::vector<int> count(4 * NM, 0), start(4 * NM + 1, 0);
+    for (int e = 0; e < nE; ++e) count[bucket(e)]++;
+    for (int b = 0; b < 4 * NM; ++b) start[b + 1] = start[b] + count[b];
+    ctx->nEb_hex = start[NM]; ctx->nEi_hex = start[3 * NM] - start[2 * NM];
+    ctx->ranges.clear();
+    for (int b = 0; b < 4 * NM; ++b)
+      if (count[b]) {
+        const int tet = (b / NM) & 1, mid = b % NM;
+        // neighbouring buckets of the same type that would run the same kernel are merged (materials 0, 2, 3 -> generic)
+        const int kmat = (mid == 1 || mid == 4 || mid == 5) ? mid : -1;
+        if (!ctx->ranges.empty() && ctx->ranges.back().e1 == start[b] && ctx->ranges.back().tet == tet &&
+            (tet || ctx->ranges.back().mat == kmat) && (start[b] != nb))
+          ctx->ranges.back().e1 = start[b + 1];
+        else
+          ctx->ranges.push_back({start[b], start[b + 1], tet, kmat});
+      }
+    std::vector<int> cur(start.begin(), start.end() - 1);
     for (int e = 0; e < nE; ++e) {
-      const int cls = (isb[e] ? 0 : 2) + ((mixed && ctx->h_etype[e]) ? 1 : 0);
-      const int t = cur[cls]++;
+      const int t = cur[bucket(e)]++;
       ref_of[t] = e; int_of[e] = t;
     }
   }

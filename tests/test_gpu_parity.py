@@ -536,6 +536,7 @@ def test_rigid_body_bc_matches_reference_fixture():
     m2 = make_model(d)
     m2.set_rigid_bc(tables)
     m2.explicit_begin(energy_every=1)
+    m2.InitInjuryCriterion(exclude_pids=g["param_exclude"])  # same kernel instantiations as the run above
     done = 0
     while done < nsteps:
         done += m2.ExplicitDynamics(float(g["param_tMax"]), maxSteps=min(7, nsteps - done))
