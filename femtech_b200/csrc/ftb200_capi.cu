@@ -79,6 +79,9 @@ struct ftb200_ctx {
   int nTilesE32 = 0, nTilesN32 = 0, fused_grid = 0;
   bool fused = false;  // opt-in (FTB200_FUSED=1): measured slower than the two-kernel step, DESIGN.md §3.6
   cudaEvent_t ev_step = nullptr, ev_energy[2] = {nullptr, nullptr};
+  // single-partition step: the energy reduction of step n runs on the helper stream under the element kernel of n + 1
+  cudaEvent_t ev_nodes_done = nullptr, ev_energy_done = nullptr;
+  bool energy_async = true, energy_pending = false, energy_async_now = true;  // _now: off for single-step calls (nothing to overlap)
   cudaGraphExec_t fgraph = nullptr;
   int fgraph_energy = -1;
   double* d_etile = nullptr;
@@ -311,6 +314,9 @@ void launch_step(ftb200_ctx* ctx, const double* recv) {
   if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.elem.push_back({i0, i1}); }
   const NodeArgs N = node_args(ctx, recv);
   const bool adv_fused = ctx->nranks == 1 && !recv && ctx->fuse_adv && !ctx->rigid;
+  const bool en_async = ctx->energy && ctx->energy_async && ctx->energy_async_now && ctx->nranks == 1 && !recv && !adv_fused && !ctx->profile;
+  // k_adv moves sc->step / sc->active, which the energy reduction of the previous step (helper stream) still reads
+  if (ctx->energy_pending) { cudaStreamWaitEvent(s, ctx->ev_energy_done, 0); ctx->energy_pending = false; }
   if (!adv_fused) LAUNCH((k_adv<false>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, 0.0, ctx->dthist);
   if (ctx->rigid) LAUNCH(k_rigid_step, 1, 32, s, ctx->sc, ctx->rigid, 0);
   if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
@@ -322,7 +328,17 @@ void launch_step(ftb200_ctx* ctx, const double* recv) {
     else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   }
   if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.node.push_back({i0, i1}); }
-  if (ctx->energy && !adv_fused) LAUNCH(k_energy, 1, 256, s, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
+  if (ctx->energy && !adv_fused) {
+    if (en_async) {  // K8 of this step overlaps K1 of the next one; joined before the next k_adv / at the end of the run
+      cudaEventRecord(ctx->ev_nodes_done, s);
+      cudaStreamWaitEvent(ctx->stream2, ctx->ev_nodes_done, 0);
+      LAUNCH(k_energy, 1, 256, ctx->stream2, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
+      cudaEventRecord(ctx->ev_energy_done, ctx->stream2);
+      ctx->energy_pending = true;
+    } else {
+      LAUNCH(k_energy, 1, 256, s, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
+    }
+  }
   if (ctx->injury) launch_injury(ctx, s);
 }
 
@@ -448,6 +464,8 @@ int ftb200_create(int rank, int nranks, int device, ftb200_ctx** out) {
       cudaEventCreateWithFlags(&ctx->ev_elem[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_elem[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_step, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_nodes_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_energy_done, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_energy[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_energy[1], cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
@@ -473,6 +491,8 @@ int ftb200_destroy(ftb200_ctx* ctx) {
     if (ctx->ev_energy[i]) cudaEventDestroy(ctx->ev_energy[i]);
   }
   if (ctx->ev_step) cudaEventDestroy(ctx->ev_step);
+  if (ctx->ev_nodes_done) cudaEventDestroy(ctx->ev_nodes_done);
+  if (ctx->ev_energy_done) cudaEventDestroy(ctx->ev_energy_done);
   delete ctx;
   return FTB200_OK;
 }
@@ -887,6 +907,7 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       if (const char* ev = getenv("FTB200_FUSED")) ctx->fused = atoi(ev) != 0;
       if (const char* ev = getenv("FTB200_FUSE_ADV")) ctx->fuse_adv = atoi(ev) != 0;
       if (const char* ev = getenv("FTB200_NODE_ELL")) ctx->node_ell = atoi(ev) != 0;
+      if (const char* ev = getenv("FTB200_ENERGY_ASYNC")) ctx->energy_async = atoi(ev) != 0;
       if (ctx->has_tet) { ctx->fused = false; ctx->pipe = false; }  // the one-kernel variants are hexahedra only
     }
     ctx->node_grid = std::max(1, std::min(prop.multiProcessorCount * nb, nTilesN));
@@ -1230,6 +1251,10 @@ int ftb200_explicit_begin(ftb200_ctx* ctx, double Time0, double reduction, doubl
   return ftb200_explicit_begin_finish(ctx, nullptr);
 }
 
+static void join_energy(ftb200_ctx* ctx) {
+  if (ctx->energy_pending) { cudaStreamWaitEvent(ctx->stream, ctx->ev_energy_done, 0); ctx->energy_pending = false; }
+}
+
 static int build_graph(ftb200_ctx* ctx) {
   if (ctx->graph && ctx->graph_energy == ctx->energy) return 0;
   if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
@@ -1237,6 +1262,7 @@ static int build_graph(ftb200_ctx* ctx) {
   const long long before = ctx->launches;
   CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
   for (int i = 0; i < GRAPH_STEPS; ++i) launch_step(ctx, nullptr);
+  join_energy(ctx);  // the helper stream rejoins before the capture ends
   cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
   ctx->launches = before;  // captured, not launched
   if (e != cudaSuccess) return fail(ctx, FTB200_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
@@ -1452,9 +1478,11 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
   long long left = steps;
   const bool use_graph = !ctx->profile;  // built on the first run (warm-up), whatever its length
   if (use_graph) {
+    ctx->energy_async_now = true;
     int rc = build_graph(ctx);
     if (rc) return rc;
   }
+  ctx->energy_async_now = steps >= 2;
   while (left > 0) {
     if (use_graph && left >= GRAPH_STEPS) {
       CK(cudaGraphLaunch(ctx->graph, s));
@@ -1465,6 +1493,7 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
       left--;
     }
   }
+  join_energy(ctx);
   CK(cudaGetLastError());
   return FTB200_OK;
 }
