@@ -657,3 +657,20 @@ def test_brain_like_example_runs_all_next_rows_together(tmp_path):
     from femtech_b200 import io as fio
     a = fio.read_vtu_arrays(str(tmp_path / "b.vtu"))
     assert a["PartID"].size == 12 ** 3 and set(np.unique(a["PartID"])) == {0, 1, 2} and "CSDM-15" in a
+
+
+@pytest.mark.parametrize("var", ["FTB200_FUSED", "FTB200_PIPE", "FTB200_FUSE_ADV", "FTB200_ENERGY_ASYNC=0", "FTB200_NODE_ELL=0"])
+def test_opt_in_loop_variants_still_match_the_oracle(var):
+    """The experimental step organisations kept behind environment switches (fused per-step kernel,
+    chunk-pipelined kernels, k_adv/k_energy folded into k_node) and the off-switches of two defaults must stay correct:
+    the smoke run (mixed materials 1 + 5, 25 steps, checked against the oracle) under each of them."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    env = dict(os.environ)
+    k, _, v = var.partition("=")
+    env[k] = v or "1"
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=env, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
