@@ -65,6 +65,7 @@ SIGNATURES = {
     "ftb200_gauss_point_count": (_ll, [_vp]),
     "ftb200_set_rigid_bc": (C.c_int, [_vp, _ip, C.POINTER(_dp), C.POINTER(_dp), _ip, C.c_int]),
     "ftb200_get_rigid_state": (C.c_int, [_vp, _dp, _dp, _ip]),
+    "ftb200_explicit_poll_async": (C.c_int, [_vp, _dp]),
     "ftb200_injury_begin": (C.c_int, [_vp, _ip, C.c_int, _dp]),
     "ftb200_injury_end": (C.c_int, [_vp]),
     "ftb200_injury_local_count": (C.c_int, [_vp, C.POINTER(_ll)]),

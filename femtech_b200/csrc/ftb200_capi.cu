@@ -764,7 +764,7 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       (rc = dalloc(ctx, &ctx->felem, 24 * 32 * (size_t)cdiv(nE, 32))) || (rc = dalloc(ctx, &ctx->mp, mp.size())) ||
       (rc = dalloc(ctx, &ctx->node_off, nNp + 1)) || (rc = dalloc(ctx, &ctx->node_ent, 8 * (size_t)nE)) ||
       (rc = dalloc(ctx, &ctx->sc, 1)) || (rc = dalloc(ctx, &ctx->epart, 3 * (size_t)std::max(ctx->node_blocks, cdiv(nN, NODE_BLOCK)))) ||
-      (rc = dalloc(ctx, &ctx->out3, 4)) || (rc = dalloc(ctx, &ctx->d_istage, 3 * (size_t)nN)) ||
+      (rc = dalloc(ctx, &ctx->out3, 16)) || (rc = dalloc(ctx, &ctx->d_istage, 3 * (size_t)nN)) ||
       (rc = dalloc(ctx, &ctx->d_detmin, 1)) || (rc = dalloc(ctx, &ctx->d_nonpos, 1)) ||
       (rc = dalloc(ctx, &ctx->d_nref, nNp)) || (rc = dalloc(ctx, &ctx->d_nint, nN)) || (rc = dalloc(ctx, &ctx->d_ctl, 1)) ||
       (rc = dalloc(ctx, &ctx->d_etile_chunk, nTilesE)) || (rc = dalloc(ctx, &ctx->d_ntile_group, nTilesN)) ||
@@ -1495,6 +1495,14 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
   }
   join_energy(ctx);
   CK(cudaGetLastError());
+  return FTB200_OK;
+}
+
+int ftb200_explicit_poll_async(ftb200_ctx* ctx, double* out8_pinned) {
+  if (!ctx || !ctx->begun || !out8_pinned) return fail(ctx, FTB200_ERR_INPUT, "explicit_poll_async: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  LAUNCH(k_scalars_out, 1, 1, ctx->stream, ctx->sc, ctx->out3 + 8);  // staged through device memory
+  CK(cudaMemcpyAsync(out8_pinned, ctx->out3 + 8, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   return FTB200_OK;
 }
 

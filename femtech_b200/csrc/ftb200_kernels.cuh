@@ -905,6 +905,12 @@ __global__ void k_prony(double* mp, int nPID, double dt) {
   }
 }
 
+// scalars of the last finished step as 8 doubles (ftb200_explicit_poll_async)
+__global__ void k_scalars_out(const DevScalars* sc, double* out8) {
+  out8[0] = sc->Time; out8[1] = sc->ndt; out8[2] = (double)sc->step; out8[3] = (double)sc->status;
+  out8[4] = sc->Wint; out8[5] = sc->Wext; out8[6] = sc->WKE; out8[7] = sc->Etot;
+}
+
 __global__ void k_begin_run(DevScalars* sc, double tMax, long long steps) {
   sc->tMax = tMax;
   sc->steps_left = steps;

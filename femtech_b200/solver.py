@@ -298,6 +298,10 @@ class FemTech:
             self.sync_out()
         return steps.value
 
+    def poll_async(self, out8_pinned):
+        """Enqueue a D2H copy of (Time, dt, steps, status, Wint, Wext, WKE, balance) into pinned host memory; no sync."""
+        self._check(self.L.ftb200_explicit_poll_async(self._h, _d(out8_pinned)))
+
     def run_async(self, timeFinal, steps):
         self._check(self.L.ftb200_explicit_run_async(self._h, float(timeFinal), int(steps)))
 

@@ -124,6 +124,10 @@ int ftb200_explicit_run(ftb200_ctx *ctx, double tMax, long long maxSteps, long l
                         double *dt);
 int ftb200_explicit_run_async(ftb200_ctx *ctx, double tMax, long long steps);
 int ftb200_explicit_poll(ftb200_ctx *ctx, long long *steps_done, double *Time, double *dt, int *status_bits);
+/* Non-blocking variant: enqueues a device->host copy of the step scalars behind the work already queued; out8 (pinned
+ * host memory, 8 doubles) receives Time, dt, steps done, status bits, Wint, Wext, WKE, |balance| once the stream gets
+ * there.  No host synchronisation. */
+int ftb200_explicit_poll_async(ftb200_ctx *ctx, double *out8_pinned);
 /* Running energies of the last checked step: out[0..3] = Wint, Wext, WKE, |WKE+Wint-Wext| */
 int ftb200_get_energy(ftb200_ctx *ctx, double out[4]);
 /* Optional per-step records kept on the device: capacity in steps (0 disables). */
