@@ -41,7 +41,7 @@ def algorithmic_bytes(n, mat, energy):
 
 
 # (n, material, energy, injury) -> measured DRAM bytes per k_elem launch (ncu, see profiles/)
-NCU_TRAFFIC_BYTES = {(100, 1, True, False): 86518016 + 140992768}
+NCU_TRAFFIC_BYTES = {(100, 1, True, False): 86516992 + 138026496}
 ELEM_FLOPS = {1: 3490.0, 4: 4400.0, 5: 6550.0}  # executed fp64 flops per element in K_elem (ncu for mat 1, SASS count for 4/5)
 
 
