@@ -41,8 +41,13 @@ def algorithmic_bytes(n, mat, energy):
 
 
 # (n, material, energy, injury) -> measured DRAM bytes per k_elem launch (ncu, see profiles/)
-NCU_TRAFFIC_BYTES = {(100, 1, True, False): 86516992 + 138026496}
+# key: (n, material, energy, injury, affine kernel)
+NCU_TRAFFIC_BYTES = {(100, 1, True, False, False): 86516992 + 138026496}
 ELEM_FLOPS = {1: 3490.0, 4: 4400.0, 5: 6550.0}  # executed fp64 flops per element in K_elem (ncu for mat 1, SASS count for 4/5)
+# k_elem_affine (parallelepiped reference geometry): per Gauss point 16 DFMA + 19 DMUL fewer (no cofactor / determinant /
+# reciprocal of J0, F in 27 FMAs), no coordinate modes and columns in the prologue, + one cofactor/inverse per element:
+# 510 flops less than the general kernel (SASS count)
+ELEM_FLOPS_AFFINE = {k: v - 510.0 for k, v in ELEM_FLOPS.items()}
 
 
 def clocks_sampler(stop, out, device_index):
@@ -156,7 +161,7 @@ def ours_single(args):
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
     n, mat = args.n, args.material
-    X, conn, pid = mesh.cube_mesh(n)
+    X, conn, pid = mesh.cube_mesh(n, jitter=args.jitter) if args.jitter else mesh.cube_mesh(n)
     E, N = conn.shape[0], X.shape[0]
     tMax = 1e30
     dMax_over_tMax = 0.07 if mat == 1 else 1.75  # the drivers' ramp rate (0.007/0.1) / a faster one for stiff parts
@@ -167,6 +172,7 @@ def ours_single(args):
     stream = torch.cuda.Stream(device=dev)
     m.set_stream(stream.cuda_stream)
     m.ShapeFunctions()
+    n_affine = m.affine_elements
     m.AssembleLumpedMass()
     m.set_bc(kind, rate)
     fp64_peak, copy_peak = solver.measure_peaks(m, reps=5)
@@ -215,7 +221,7 @@ def ours_single(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    flops = ELEM_FLOPS[mat]
+    flops = (n_affine * ELEM_FLOPS_AFFINE[mat] + (E - n_affine) * ELEM_FLOPS[mat]) / E
     fused = prof["node_launches"] == 0  # one fused kernel per step (k_step): element and node work in the same launch
     elem_s = prof["elem_ms"] * 1e-3
     if fused:
@@ -247,7 +253,7 @@ def ours_single(args):
         node_gbs = b_node * E / node_s / 1e9
         fp64_bound = elem_tf / fp64_peak >= elem_gbs / hbm_peak
         roofline = {
-            "kernel": "k_elem (fused gather, F, material, B^T sigma, element dt)",
+            "kernel": ("k_elem_affine" if n_affine == E else "k_elem") + " (fused gather, F, material, B^T sigma, element dt)",
             "bound": "fp64" if fp64_bound else "hbm",
             "achieved": elem_tf if fp64_bound else elem_gbs,
             "peak": fp64_peak if fp64_bound else hbm_peak,
@@ -255,7 +261,7 @@ def ours_single(args):
             "frac": (elem_tf / fp64_peak) if fp64_bound else (elem_gbs / hbm_peak),
             # DRAM bytes of one k_elem launch from the ncu --set full capture of this configuration
             # (profiles/r01_k_elem_final_ncu_full.csv: dram__bytes_read.sum + dram__bytes_write.sum); other configs: null
-            "traffic": NCU_TRAFFIC_BYTES.get((n, mat, bool(energy), bool(args.injury))),
+            "traffic": NCU_TRAFFIC_BYTES.get((n, mat, bool(energy), bool(args.injury), n_affine == E)),
             "traffic_unit": "bytes per launch (algorithmic: %d)" % int(b_elem * E),
             "peak_source": "fp64: DFMA microbenchmark measured in this run; hbm: " + hbm_src,
             "launch_ms": prof["elem_ms"], "launches_timed": prof["elem_launches"],
@@ -341,9 +347,12 @@ def ours_single(args):
         "metric": "hex8 element-steps/sec fp64", "value": value, "unit": "element-steps/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic %d^3 structured hex8 cube (%d elements, %d nodes), %s, benchmark BC "
+        "config": {"workload": "synthetic %d^3 %s hex8 cube (%d elements, %d nodes), %s, benchmark BC "
                                "(Benchmarking-Parallel.cpp:184-244), %s, dt recomputed every step"
-                               % (n, E, N, MAT_NAME[mat], "CheckEnergy every step" if energy else "no energy check"),
+                               % (n, ("structured, nodes jittered by %g of the spacing" % args.jitter) if args.jitter else "structured",
+                                  E, N, MAT_NAME[mat], "CheckEnergy every step" if energy else "no energy check"),
+                   "element_kernel": "%d of %d hexahedra have a parallelepiped reference geometry and run k_elem_affine "
+                                     "(dN/dX once per element); the rest run the general k_elem" % (n_affine, E),
                    "injury_criteria": bool(args.injury),
                    "mode": "resident ExplicitDynamics loop, CUDA graph of 25 steps, " +
                            ("one fused kernel per step" if prof["node_launches"] == 0 else "element + node kernels per step"),
@@ -369,6 +378,8 @@ def main():
     ap.add_argument("--no-energy", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--injury", action="store_true", help="also evaluate the injury criteria every step (ex5.cpp:240)")
+    ap.add_argument("--jitter", type=float, default=0.0, help="move the interior nodes by this fraction of the spacing: "
+                    "no element is a parallelepiped any more, so the general element kernel is measured")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -44,8 +44,10 @@ struct ftb200_ctx {
   bool has_tet = false;
   long long nGP = 0;              // Gauss points of the mesh (8 nE without tetrahedra)
   int nEb_hex = 0, nEi_hex = 0;   // hexahedra among the boundary / interior elements (they come first in each class)
-  struct ElemRange { int e0, e1, tet, mat; };
-  std::vector<ElemRange> ranges;  // internal element order = runs of equal (class, element type, material)
+  struct ElemRange { int e0, e1, tet, mat, affine; };
+  std::vector<ElemRange> ranges;  // internal element order = runs of equal (class, element type, material, affine geometry)
+  bool use_affine = true;  // FTB200_AFFINE=0: parallelepiped hexahedra go through the general kernel too
+  long long nE_affine = 0;
   // rigid-body prescribed motion (ftb200_set_rigid_bc)
   DevRigid* rigid = nullptr;
   double *rigid_tab = nullptr, *aprev[3] = {nullptr, nullptr, nullptr};
@@ -234,7 +236,7 @@ NodeArgs node_args(ftb200_ctx* c, const double* recv) {
 
 // element kernel dispatch on the (uniform) material of the launch
 template <bool WITH_FORCE, bool WITH_DT>
-void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore, int mat);
+void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore, int mat, int affine);
 
 template <bool WITH_FORCE, bool WITH_DT>
 void launch_elem_tet(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore) {
@@ -254,16 +256,34 @@ void launch_elem(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore) {
     const int a = std::max(e0, r.e0), b = std::min(e1, r.e1);
     if (b <= a) continue;
     if (r.tet) launch_elem_tet<WITH_FORCE, WITH_DT>(ctx, s, a, b, ignore);
-    else launch_elem_hex<WITH_FORCE, WITH_DT>(ctx, s, a, b, ignore, r.mat);
+    else launch_elem_hex<WITH_FORCE, WITH_DT>(ctx, s, a, b, ignore, r.mat, r.affine);
   }
 }
 
 template <bool WITH_FORCE, bool WITH_DT>
-void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore, int mat) {
+void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore, int mat, int affine) {
   if (e1 <= e0) return;
   const ElemArgs A = elem_args(ctx, e0, e1, ignore);
   const int grid = cdiv(e1 - e0, ELEM_BLOCK);
   if (!WITH_FORCE) { LAUNCH((k_elem<-1, false, true>), grid, ELEM_BLOCK, s, A); return; }
+  if (WITH_FORCE && WITH_DT && affine && mat > 0) {  // a run of parallelepipeds of material 1, 4 or 5: k_elem_affine
+    const bool inj = ctx->injury && !ignore;
+    switch (mat) {
+      case 1:
+        if (inj) LAUNCH((k_elem_affine<1, true>), grid, ELEM_BLOCK, s, A);
+        else LAUNCH((k_elem_affine<1, false>), grid, ELEM_BLOCK, s, A);
+        return;
+      case 4:
+        if (inj) LAUNCH((k_elem_affine<4, true>), grid, ELEM_BLOCK, s, A);
+        else LAUNCH((k_elem_affine<4, false>), grid, ELEM_BLOCK, s, A);
+        return;
+      case 5:
+        if (inj) LAUNCH_HIST((k_elem_affine<5, true>), grid, ELEM_BLOCK, s, A);
+        else LAUNCH_HIST((k_elem_affine<5, false>), grid, ELEM_BLOCK, s, A);
+        return;
+      default: break;
+    }
+  }
   if (WITH_FORCE && WITH_DT && ctx->injury && !ignore) {  // a step of the loop with the injury criteria on
     switch (mat) {
       case 1: LAUNCH((k_elem<1, true, true, true>), grid, ELEM_BLOCK, s, A); break;
@@ -536,6 +556,7 @@ int ftb200_upload_mesh(ftb200_ctx* ctx, const double* coordinates, const int* co
   return FTB200_OK;
 }
 
+long long ftb200_affine_element_count(ftb200_ctx* ctx) { return (ctx && ctx->shape_ok) ? ctx->nE_affine : -1; }
 long long ftb200_gauss_point_count(ftb200_ctx* ctx) { return ctx ? (ctx->shape_ok ? ctx->nGP : (ctx->has_tet ? -1 : 8LL * ctx->nE)) : -1; }
 
 int ftb200_upload_mesh_mixed(ftb200_ctx* ctx, const double* coordinates, const int* connectivity, const int* eptr, const int* pid,
@@ -620,10 +641,26 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
     // inside each class: hexahedra first, tetrahedra after them (their own kernel); inside each type by material id, so
     // that every run of the internal order is uniform and gets the kernel specialised for it; caller's order kept
     const bool mixed = ctx->has_tet;
-    constexpr int NM = 6;  // material ids 0..5 (StressUpdate.cpp:7-27)
+    // hexahedra of materials 1, 4, 5 whose reference geometry is a parallelepiped (hex8_is_affine, exact test) form their
+    // own runs behind the other elements of the same material: they are integrated by k_elem_affine
+    std::vector<char> aff(nE, 0);
+    ctx->nE_affine = 0;
+    if (const char* ev = getenv("FTB200_AFFINE")) ctx->use_affine = atoi(ev) != 0;
+    if (ctx->use_affine)
+      for (int e = 0; e < nE; ++e) {
+        if (mixed && ctx->h_etype[e]) continue;
+        const int mid = ctx->h_matid[ctx->h_pid[e]];
+        if (mid != 1 && mid != 4 && mid != 5) continue;
+        double Xe[8][3];
+        for (int k = 0; k < 8; ++k)
+          for (int c = 0; c < 3; ++c) Xe[k][c] = ctx->h_X[3 * (size_t)ctx->h_conn[8 * (size_t)e + k] + c];
+        aff[e] = hex8_is_affine(Xe) ? 1 : 0;
+        ctx->nE_affine += aff[e];
+      }
+    constexpr int NM = 12;  // (material id 0..5, StressUpdate.cpp:7-27) x (general, affine)
     auto bucket = [&](int e) {
       const int mid = ctx->h_matid[ctx->h_pid[e]];
-      const int mslot = (mid >= 0 && mid < NM) ? mid : 0;  // unknown ids go with the generic kernel, which reports them
+      const int mslot = ((mid >= 0 && mid < 6) ? mid : 0) * 2 + aff[e];  // unknown ids go with the generic kernel, which reports them
       return ((isb[e] ? 0 : 1) * 2 + ((mixed && ctx->h_etype[e]) ? 1 : 0)) * NM + mslot;
     };
     std::vector<int> count(4 * NM, 0), start(4 * NM + 1, 0);
@@ -633,14 +670,14 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
     ctx->ranges.clear();
     for (int b = 0; b < 4 * NM; ++b)
       if (count[b]) {
-        const int tet = (b / NM) & 1, mid = b % NM;
+        const int tet = (b / NM) & 1, mid = (b % NM) >> 1, af = (b % NM) & 1;
         // neighbouring buckets of the same type that would run the same kernel are merged (materials 0, 2, 3 -> generic)
         const int kmat = (mid == 1 || mid == 4 || mid == 5) ? mid : -1;
         if (!ctx->ranges.empty() && ctx->ranges.back().e1 == start[b] && ctx->ranges.back().tet == tet &&
-            (tet || ctx->ranges.back().mat == kmat) && (start[b] != nb))
+            (tet || (ctx->ranges.back().mat == kmat && ctx->ranges.back().affine == af)) && (start[b] != nb))
           ctx->ranges.back().e1 = start[b + 1];
         else
-          ctx->ranges.push_back({start[b], start[b + 1], tet, kmat});
+          ctx->ranges.push_back({start[b], start[b + 1], tet, kmat, af});
       }
     std::vector<int> cur(start.begin(), start.end() - 1);
     for (int e = 0; e < nE; ++e) {

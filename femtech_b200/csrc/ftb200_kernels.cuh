@@ -328,6 +328,136 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
   if (status) atomicOr(&A.sc->status, status);
 }
 
+// K_elem for runs of hexahedra whose reference geometry is affine (hex8_element_affine_in: parallelepipeds, e.g. every
+// element of a structured or voxel mesh; the host sorts them into their own runs with hex8_is_affine).  Same step semantics as
+// k_elem<MATSEL, true, true, WITH_INJ>; what changes is the cost: cof(J0), det J0, J0^-1 once per element, 54 instead of
+// 72 scratch doubles per thread, 36 instead of 48 gathers -- which also lets more blocks share an SM.
+#ifndef FTB_AFF_MINBLOCKS
+#define FTB_AFF_MINBLOCKS 8
+#endif
+// Scratch of k_elem_affine: cof(J0) and J0^-1 are loop invariants; left to itself the compiler hoists their 18 loads out
+// of the Gauss loop and pays 36 registers for it.  ld_inloop() is a volatile shared-memory load, so they are re-read in
+// every iteration (18 LDS against ~170 fp64 instructions) and the kernel fits FTB_AFF_MINBLOCKS blocks per SM.
+#ifndef FTB_AFF_REREAD
+#define FTB_AFF_REREAD 1
+#endif
+struct SmemScratchAffine {
+  double* base;  // &sm[0][threadIdx.x]
+  __device__ __forceinline__ void st(int i, double x) { base[i * ELEM_BLOCK] = x; }
+  __device__ __forceinline__ double ld(int i) const { return base[i * ELEM_BLOCK]; }
+  __device__ __forceinline__ double ld_inloop(int i) const {
+#if FTB_AFF_REREAD
+    double v;
+    // "memory": the slot was written with ordinary stores before the loop; the compiler must not move them past this
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(base + i * ELEM_BLOCK)) : "memory");
+    return v;
+#else
+    return base[i * ELEM_BLOCK];
+#endif
+  }
+};
+struct StagedInAffine {
+  const double* x0;  // [4] component 0 of nodes 0, 1, 3, 4 (registers)
+  const double* u0;  // [8] component 0
+  double* base;      // &sm[0][threadIdx.x]
+  __device__ __forceinline__ void getX(const int c, double x[4]) const {
+    if (c == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k] = x0[k];
+    } else {
+      if (c == 1) asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k] = base[FTB_ASTAGE_X(k, c) * ELEM_BLOCK];
+    }
+  }
+  __device__ __forceinline__ void getU(const int c, double nu[8]) const {
+    if (c == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) nu[k] = u0[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) nu[k] = base[FTB_ASTAGE_U(k, c) * ELEM_BLOCK];
+    }
+  }
+};
+template <int MATSEL, bool WITH_INJ>
+__global__ void __launch_bounds__(ELEM_BLOCK, MATSEL == 5 ? 4 : (WITH_INJ ? FTB_INJ_MINBLOCKS : FTB_AFF_MINBLOCKS)) k_elem_affine(const ElemArgs A) {
+  const int e = A.e0 + blockIdx.x * ELEM_BLOCK + threadIdx.x;
+  const size_t E = (size_t)A.nE;
+  int nd[8];
+  int p = 0;
+  unsigned skip = 0;
+  if (e < A.e1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) nd[k] = __ldg(A.conn + (size_t)k * E + e);
+    p = __ldg(A.pid + e);
+    skip = __ldg(A.eflag + e);
+  }
+  if (!A.ignore_loop_flags && (A.sc->last | A.sc->done)) return;
+  __shared__ double sm_cols[FTB_AFFINE_SLOTS][ELEM_BLOCK];
+  extern __shared__ double sm_hstage[];
+  constexpr bool STAGED_HIST = MATSEL == 5;
+  if (STAGED_HIST && e < A.e1) {
+    const DevHistStaged hs{A.hist, E, (size_t)e, sm_hstage + threadIdx.x};
+    hs.prefetch(0);
+  }
+  double dte = 1e300;
+  int status = 0;
+  if (e < A.e1) {
+    double X0[4], U0[8];
+    double* colbase = &sm_cols[0][threadIdx.x];
+    const int nx[4] = {nd[0], nd[1], nd[3], nd[4]};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) U0[k] = __ldg(A.u[0] + nd[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) X0[k] = __ldg(A.X[0] + nx[k]);
+#pragma unroll
+    for (int c = 1; c < 3; ++c) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cp_async8(colbase + FTB_ASTAGE_U(k, c) * ELEM_BLOCK, A.u[c] + nd[k]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cp_async8(colbase + FTB_ASTAGE_X(k, c) * ELEM_BLOCK, A.X[c] + nx[k]);
+    }
+    const double* mp = A.mp + (size_t)p * FTB_MP_STRIDE;
+    double fe[8][3];
+    const auto h = HistSel<STAGED_HIST>::make(A.hist, E, (size_t)e, sm_hstage + threadIdx.x);
+    double d;
+    SmemScratchAffine S{colbase};
+    if (WITH_INJ) {
+      double cs[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      status = hex8_element_affine_in<MATSEL, true>(StagedInAffine{X0, U0, colbase}, MATSEL, mp, true, h, StrainSink{cs}, S, fe, &d);
+      if (A.inj_incl[e]) {  // ex5.cpp:1313-1369, one element of the loop (same as k_elem)
+        double smax, smin, shear;
+        principal_strains(cs, &smax, &smin, &shear);
+        const double PSR = (smax - A.inj_ps[e]) / A.sc->ndt;
+        const double PSxSR = smax * PSR;
+        unsigned f = A.inj_flags[e];
+        if (smax > A.inj_thr[0]) f |= FTB_INJ_MPS_LO;
+        if (smax > A.inj_thr[1]) f |= FTB_INJ_MPS_HI;
+        if (PSR > A.inj_thr[2]) f |= FTB_INJ_PSR;
+        if (PSxSR > A.inj_thr[3]) f |= FTB_INJ_PSXSR;
+        A.inj_flags[e] = (uint8_t)f;
+        A.inj_ps[e] = smax; A.inj_psxsr[e] = PSxSR; A.inj_smin[e] = smin; A.inj_shear[e] = shear;
+      }
+    } else {
+      status = hex8_element_affine_in<MATSEL, true>(StagedInAffine{X0, U0, colbase}, MATSEL, mp, true, h, NoOutput(), S, fe, &d);
+    }
+    dte = skip ? 1e300 : d;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) A.felem[FTB_FIDX(3 * k + c, e)] = fe[k][c];
+  }
+  unsigned long long b = dt_to_bits(dte);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o);
+    b = t < b ? t : b;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMin(&A.sc->dtmin_bits, b);
+  if (status) atomicOr(&A.sc->status, status);
+}
+
 // The C3D4 elements of a mixed mesh: they sit in their own index ranges of the internal element
 // order, so this kernel sees only tetrahedra and k_elem only hexahedra.  One thread per element, generic material.
 constexpr int TET_BLOCK = 128;

@@ -129,6 +129,11 @@ class FemTech:
     def gpu_launches(self):
         return int(self.L.ftb200_launch_count(self._h))
 
+    @property
+    def affine_elements(self):
+        """Hexahedra integrated by the parallelepiped kernel (after ShapeFunctions)."""
+        return int(self.L.ftb200_affine_element_count(self._h))
+
     # --- one-time setup ----------------------------------------------------------------------------
     def ShapeFunctions(self):
         md = C.c_double()

@@ -64,6 +64,11 @@ int ftb200_upload_mesh(ftb200_ctx *ctx, const double *coordinates, const int *co
 int ftb200_upload_mesh_mixed(ftb200_ctx *ctx, const double *coordinates, const int *connectivity, const int *eptr,
                              const int *pid, int nNodes, int nElements);
 long long ftb200_gauss_point_count(ftb200_ctx *ctx);
+/* Hexahedra of the mesh whose reference geometry is a parallelepiped (valid after ftb200_shape_functions; -1 before).
+ * They are integrated by the kernel that forms dN/dX once per element instead of once per Gauss point
+ * (ShapeFunction_C3D8.cpp:60-115 stores it per point); FTB200_AFFINE=0 in the environment sends them through the
+ * general kernel.  Reported by bench.py next to the throughput. */
+long long ftb200_affine_element_count(ftb200_ctx *ctx);
 /* materialID, properties: src/io/input/ReadMaterials.cpp:8-138 */
 int ftb200_upload_materials(ftb200_ctx *ctx, const int *materialID, const double *properties, int nPID);
 /* sendProcessID / sendNeighbourCountCum / sendNodeIndex: PartitionMesh.cpp:566-1128 */

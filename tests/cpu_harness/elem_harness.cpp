@@ -48,6 +48,62 @@ extern "C" double harness_mass(const double* X24, double rho, double* me8) {
   return ftb::hex8_lumped_mass(X, rho, me8);
 }
 
+// the affine-reference-geometry variant of the hexahedron (parallelepipeds); returns -1 if the element does not qualify
+extern "C" int harness_element_affine(const double* X24, const double* U24, int mat, const double* mp, double* hist144,
+                                      int updHist, double* fe24, double* dtElem, double* F72, double* detF8, double* pk2_48) {
+  double X[8][3], U[8][3], fe[8][3];
+  for (int k = 0; k < 8; ++k)
+    for (int c = 0; c < 3; ++c) { X[k][c] = X24[3 * k + c]; U[k][c] = U24[3 * k + c]; }
+  if (!ftb::hex8_is_affine(X)) return -1;
+  HostHist hh{hist144};
+  HostOut ho{F72, detF8, pk2_48};
+  ftb::LocalScratchAffine sc;
+  int st = ftb::hex8_element_affine_in<-1, true>(ftb::ArrayInAffine{X, U}, mat, mp, updHist != 0, hh, ho, sc, fe, dtElem);
+  for (int k = 0; k < 8; ++k)
+    for (int c = 0; c < 3; ++c) fe24[3 * k + c] = fe[k][c];
+  return st;
+}
+
+// The slot plan of k_elem_affine's asynchronous gather, replayed on the host: components 1 and 2 of the nodal input wait
+// in the scratch slots FTB_ASTAGE_U / FTB_ASTAGE_X that the element function later overwrites with columns and cofactors.
+// Any aliasing between a staged value and an earlier store would change the result.
+namespace {
+struct HostStagedAffine {
+  const double* x0;  // component 0 of nodes 0, 1, 3, 4
+  const double* u0;  // component 0 of the 8 nodes
+  const double* v;   // the scratch itself
+  void getX(const int c, double x[4]) const {
+    for (int k = 0; k < 4; ++k) x[k] = (c == 0) ? x0[k] : v[FTB_ASTAGE_X(k, c)];
+  }
+  void getU(const int c, double nu[8]) const {
+    for (int k = 0; k < 8; ++k) nu[k] = (c == 0) ? u0[k] : v[FTB_ASTAGE_U(k, c)];
+  }
+};
+}  // namespace
+extern "C" int harness_element_affine_staged(const double* X24, const double* U24, int mat, const double* mp, double* hist144,
+                                             int updHist, double* fe24, double* dtElem, double* F72, double* detF8, double* pk2_48) {
+  double X[8][3], fe[8][3];
+  for (int k = 0; k < 8; ++k)
+    for (int c = 0; c < 3; ++c) X[k][c] = X24[3 * k + c];
+  if (!ftb::hex8_is_affine(X)) return -1;
+  const int nx[4] = {0, 1, 3, 4};
+  ftb::LocalScratchAffine sc;
+  for (int i = 0; i < FTB_AFFINE_SLOTS; ++i) sc.v[i] = 1e300;  // poison
+  double x0[4], u0[8];
+  for (int k = 0; k < 8; ++k) u0[k] = U24[3 * k];
+  for (int k = 0; k < 4; ++k) x0[k] = X24[3 * nx[k]];
+  for (int c = 1; c < 3; ++c) {
+    for (int k = 0; k < 8; ++k) sc.v[FTB_ASTAGE_U(k, c)] = U24[3 * k + c];
+    for (int k = 0; k < 4; ++k) sc.v[FTB_ASTAGE_X(k, c)] = X24[3 * nx[k] + c];
+  }
+  HostHist hh{hist144};
+  HostOut ho{F72, detF8, pk2_48};
+  int st = ftb::hex8_element_affine_in<-1, true>(HostStagedAffine{x0, u0, sc.v}, mat, mp, updHist != 0, hh, ho, sc, fe, dtElem);
+  for (int k = 0; k < 8; ++k)
+    for (int c = 0; c < 3; ++c) fe24[3 * k + c] = fe[k][c];
+  return st;
+}
+
 // CalculateMaximumPrincipalStrain of one element: out = max, min, shear, then the 6 sums of F^T F
 extern "C" void harness_principal(const double* X24, const double* U24, double* out9) {
   double X[8][3], U[8][3], fe[8][3], d;

@@ -28,6 +28,10 @@ def harness():
     L = C.CDLL(so)
     L.harness_element.argtypes = [_dp, _dp, C.c_int, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp]
     L.harness_element.restype = C.c_int
+    L.harness_element_affine.argtypes = L.harness_element.argtypes
+    L.harness_element_affine.restype = C.c_int
+    L.harness_element_affine_staged.argtypes = L.harness_element.argtypes
+    L.harness_element_affine_staged.restype = C.c_int
     L.harness_mass.argtypes = [_dp, C.c_double, _dp]
     L.harness_mass.restype = C.c_double
     L.harness_principal.argtypes = [_dp, _dp, _dp]
@@ -278,3 +282,49 @@ def test_tet4_element_matches_oracle(harness, name):
                                     np.zeros(8).ctypes.data_as(_dp), np.zeros(48).ctypes.data_as(_dp))
             np.add.at(fi, nodes, fe.reshape(8, 3))
     assert np.abs(fi.reshape(-1) - m.fi).max() < 1e-11 * np.abs(m.fi).max()
+
+
+def _call_elem(fn, X, U, mat, mp, hist):
+    fe, dte, F, dF, pk = np.zeros(24), np.zeros(1), np.zeros(72), np.zeros(8), np.zeros(48)
+    st = fn(np.ascontiguousarray(X).reshape(-1).ctypes.data_as(_dp), np.ascontiguousarray(U).reshape(-1).ctypes.data_as(_dp), mat,
+            mp.ctypes.data_as(_dp), hist.ctypes.data_as(_dp), 1, fe.ctypes.data_as(_dp), dte.ctypes.data_as(_dp),
+            F.ctypes.data_as(_dp), dF.ctypes.data_as(_dp), pk.ctypes.data_as(_dp))
+    return st, fe, dte[0], F, dF, pk
+
+
+@pytest.mark.parametrize("mat", [1, 2, 3, 4, 5])
+def test_affine_hexahedron_path_equals_general_path(harness, mat):
+    """hex8_element_affine_in (parallelepiped elements: cof(J0), J0^-1 once per element) against the general mode-basis
+    path on sheared parallelepipeds with dyadic coordinates (edge vectors bit-equal) and random displacements: forces,
+    F, det F, PK2, dt and the updated Prony history agree to rounding.  A jittered element must be refused."""
+    rng = np.random.default_rng(7 + mat)
+    props = np.array([1000.0, 2673.23, 2.189982178466e8, 25459.0, 0.0, 0.6521, 0.0129, 0.0067, 0.0747])
+    if mat in (1, 2, 3):
+        props = np.array([1040.0, 2.0e5, 4.0e5, 0, 0, 0, 0, 0, 0.0])
+    mp = np.ascontiguousarray(part_params([mat], props, 1e-6)[0])
+    signs = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]])
+    for trial in range(20):
+        # edge vectors and origin on a 2^-10 grid: every node coordinate and every edge difference is exact
+        D = (np.eye(3) * 64 + rng.integers(-16, 17, size=(3, 3))) / 1024.0
+        x0 = rng.integers(-2048, 2048, size=3) / 1024.0
+        X = x0 + ((signs + 1) // 2) @ D
+        U = 0.004 * rng.standard_normal((8, 3))
+        h0 = 50.0 * rng.standard_normal(144)
+        ha, hg = h0.copy(), h0.copy()
+        sa, fa, dta, Fa, dFa, pka = _call_elem(harness.harness_element_affine, X, U, mat, mp, ha)
+        sg, fg, dtg, Fg, dFg, pkg = _call_elem(harness.harness_element, X, U, mat, mp, hg)
+        assert sa == sg == 0
+        # the kernel's staging-slot plan replayed on the host gives the very same bits
+        hs = h0.copy()
+        ss, fs, dts_, Fs, dFs, pks = _call_elem(harness.harness_element_affine_staged, X, U, mat, mp, hs)
+        assert ss == 0 and np.array_equal(fs, fa) and dts_ == dta and np.array_equal(Fs, Fa) and np.array_equal(hs, ha)
+        assert np.abs(Fa - Fg).max() < 1e-14
+        assert np.abs(dFa - dFg).max() < 1e-14
+        assert np.abs(fa - fg).max() <= 1e-13 * np.abs(fg).max()
+        assert np.abs(pka - pkg).max() <= 1e-12 * max(np.abs(pkg).max(), 1.0)
+        assert dta == pytest.approx(dtg, rel=1e-14)
+        if mat == 5:
+            assert np.abs(ha - hg).max() <= 1e-12 * max(np.abs(hg).max(), np.abs(pkg).max())  # history carries stress differences
+            assert np.abs(ha - h0).max() > 0
+    Xj = X + 1e-9 * rng.standard_normal((8, 3))
+    assert _call_elem(harness.harness_element_affine, Xj, U, mat, mp, h0.copy())[0] == -1

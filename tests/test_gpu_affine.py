@@ -1,0 +1,135 @@
+"""GPU parity of the parallelepiped element kernel (k_elem_affine: cof(J0), J0^-1 once per element).
+
+The host sorts the hexahedra whose parallel edges are bit-equal vectors into their own runs; these tests
+check, through the C-ABI, (1) that the structured meshes really take that path, (2) the results against
+the CPU oracle on the same inputs (1e-9, the north-star tolerance) for the three specialised materials and
+with the injury criteria on, (3) a mesh that is half structured, half jittered (both kernels in one step,
+the internal element order permuted by the sort), and (4) agreement with the general kernel on the same
+mesh (FTB200_AFFINE=0) far below the parity tolerance.  The shipped 10^3 mesh and ex9's single element in
+tests/test_gpu_parity.py are structured too, so the reference's own golden vectors cover this kernel as well."""
+import os
+
+import numpy as np
+import pytest
+
+from femtech_b200 import mesh
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+SOFT = [1040.0, 2.0e5, 4.0e5, 0, 0, 0, 0, 0, 0]
+BRAIN = [1000.0, 2673.23, 2.189982178466e8, 25459.0, 0.0, 0.6521, 0.0129, 0.0067, 0.0747]
+HGO = BRAIN[:4] + [10.0, 0, 0, 0, 0]
+PROPS = {1: SOFT, 4: HGO, 5: BRAIN}
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def half_jittered_cube(n):
+    """n^3 cube, two z-slabs = two parts; the nodes strictly inside the upper slab are jittered, so the lower
+    slab's elements stay parallelepipeds and the upper slab's do not."""
+    X, conn, pid = mesh.cube_mesh(n, nparts_z=2)
+    Xj, _, _ = mesh.cube_mesh(n, jitter=0.05, nparts_z=2)
+    h = X[:, 2].max() / n
+    upper = X[:, 2] > (n // 2 + 0.5) * h
+    X[upper] = Xj[upper]
+    return X, conn, pid
+
+
+def run_gpu(X, conn, pid, matid, props, kind, rate, nsteps, injury=False):
+    from femtech_b200 import solver
+    m = solver.FemTech(X, conn, pid, matid, props)
+    m.ShapeFunctions()
+    m.AssembleLumpedMass()
+    m.set_bc(kind, rate)
+    m.explicit_begin(energy_every=1, record_steps=nsteps)
+    if injury:
+        m.InitInjuryCriterion()
+    assert m.ExplicitDynamics(1.0, maxSteps=nsteps) == nsteps
+    return m
+
+
+def run_oracle(X, conn, pid, matid, props, kind, rate, nsteps):
+    from oracle import pyoracle as po
+    o = po.OracleModel(X, conn, pid, matid, props)
+    o.ShapeFunctions()
+    o.AssembleLumpedMass()
+    n, dth, _ = po.run_explicit([o], [kind], rate, 1.0, nsteps)
+    assert n == nsteps
+    return o, dth
+
+
+@pytest.mark.parametrize("mat", [1, 4, 5])
+def test_structured_cube_runs_the_affine_kernel_and_matches_oracle(mat):
+    X, conn, pid = mesh.cube_mesh(6)
+    kind, rate = mesh.benchmark_bc(X, dMax=0.007, tMax=0.1 if mat == 1 else 0.004)
+    nsteps = 150
+    o, dth_o = run_oracle(X, conn, pid, [mat], PROPS[mat], kind, rate, nsteps)
+    m = run_gpu(X, conn, pid, [mat], PROPS[mat], kind, rate, nsteps)
+    assert m.affine_elements == conn.shape[0]
+    dth, _ = m.history(0, nsteps)
+    assert np.allclose(dth, dth_o, rtol=1e-11, atol=0)
+    assert rel(m.displacements, o.displacements) < TOL
+    assert rel(m.velocities, o.velocities) < TOL
+    out = m.gp_outputs()
+    assert rel(out["pk2"], o.pk2) < TOL
+    assert rel(out["F"], o.F) < TOL
+    m.close()
+
+
+@pytest.mark.parametrize("mats", [(1, 5), (4, 1)])
+def test_half_structured_half_jittered_mesh_matches_oracle(mats):
+    """Both element kernels in every step; the affine elements are moved behind the others in the internal order."""
+    X, conn, pid = half_jittered_cube(6)
+    props = PROPS[mats[0]] + PROPS[mats[1]]
+    kind, rate = mesh.benchmark_bc(X, dMax=0.007, tMax=0.004)
+    nsteps = 120
+    o, dth_o = run_oracle(X, conn, pid, list(mats), props, kind, rate, nsteps)
+    m = run_gpu(X, conn, pid, list(mats), props, kind, rate, nsteps)
+    E = conn.shape[0]
+    assert 0 < m.affine_elements < E
+    assert m.affine_elements == int((pid == 0).sum())  # exactly the lower slab (none of its nodes is jittered)
+    dth, _ = m.history(0, nsteps)
+    assert np.allclose(dth, dth_o, rtol=1e-11, atol=0)
+    assert rel(m.displacements, o.displacements) < TOL
+    assert rel(m.velocities, o.velocities) < TOL
+    out = m.gp_outputs()
+    assert rel(out["pk2"], o.pk2) < TOL
+    m.close()
+
+
+@pytest.mark.parametrize("mat,injury", [(1, False), (5, False), (1, True)])
+def test_affine_kernel_agrees_with_general_kernel(mat, injury):
+    """Same structured mesh through k_elem_affine and (FTB200_AFFINE=0) through the general k_elem: rounding-level
+    agreement of the state after 100 steps, identical injury flags."""
+    X, conn, pid = mesh.cube_mesh(8)
+    kind, rate = mesh.benchmark_bc(X, dMax=0.02, tMax=0.004)
+    nsteps = 100
+    res = []
+    for flag in ("1", "0"):
+        os.environ["FTB200_AFFINE"] = flag
+        try:
+            m = run_gpu(X, conn, pid, [mat], PROPS[mat], kind, rate, nsteps, injury=injury)
+        finally:
+            del os.environ["FTB200_AFFINE"]
+        assert m.affine_elements == (conn.shape[0] if flag == "1" else 0)
+        r = {"u": m.displacements.copy(), "v": m.velocities.copy(), "pk2": m.gp_outputs()["pk2"].copy(), "t": m.Time}
+        if injury:
+            r["inj"] = m.injury_results()
+        res.append(r)
+        m.close()
+    a, g = res
+    assert abs(a["t"] - g["t"]) <= 1e-13 * abs(g["t"])
+    for k in ("u", "v", "pk2"):
+        assert rel(a[k], g[k]) < 1e-11, k
+    if injury:
+        ia, ig = a["inj"], g["inj"]
+        for k in ig:
+            va, vg = np.asarray(ia[k]), np.asarray(ig[k])
+            if vg.dtype.kind in "iub":
+                assert np.array_equal(va, vg), k
+            else:
+                assert np.allclose(va, vg, rtol=1e-6, atol=1e-12), k
