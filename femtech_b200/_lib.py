@@ -43,6 +43,7 @@ SIGNATURES = {
     "ftb200_explicit_run": (C.c_int, [_vp, C.c_double, _ll, C.POINTER(_ll), _dp, _dp]),
     "ftb200_explicit_run_async": (C.c_int, [_vp, C.c_double, _ll]),
     "ftb200_explicit_poll": (C.c_int, [_vp, C.POINTER(_ll), _dp, _dp, _ip]),
+    "ftb200_step_ring": (C.c_int, [_vp, _ll, C.POINTER(_dp)]),
     "ftb200_get_energy": (C.c_int, [_vp, _dp]),
     "ftb200_record_history": (C.c_int, [_vp, _ll]),
     "ftb200_get_history": (C.c_int, [_vp, _ll, _ll, _dp, _dp]),

@@ -46,6 +46,10 @@ struct ftb200_ctx {
   int nEb_hex = 0, nEi_hex = 0;   // hexahedra among the boundary / interior elements (they come first in each class)
   struct ElemRange { int e0, e1, tet, mat, affine; };
   std::vector<ElemRange> ranges;  // internal element order = runs of equal (class, element type, material, affine geometry)
+  double* ring_host = nullptr;   // step ring (ftb200_step_ring): mapped pinned host memory, its device alias, records
+  double* ring_dev = nullptr;
+  long long ring_cap = 0;
+  int pf_dist = 0;         // L2 prefetch distance of the element kernels in elements (elem_prefetch_begin); FTB200_PREFETCH_WAVES
   bool use_affine = true;  // FTB200_AFFINE=0: parallelepiped hexahedra go through the general kernel too
   long long nE_affine = 0;
   // rigid-body prescribed motion (ftb200_set_rigid_bc)
@@ -207,6 +211,7 @@ ElemArgs elem_args(ftb200_ctx* c, int e0, int e1, int ignore) {
   for (int k = 0; k < 3; ++k) { A.X[k] = c->X[k]; A.u[k] = c->u[k]; }
   A.conn = c->conn; A.pid = c->pid; A.eflag = c->eflag; A.mp = c->mp; A.felem = c->felem; A.hist = c->hist;
   A.sc = c->sc; A.nE = c->nE; A.e0 = e0; A.e1 = e1; A.ignore_loop_flags = ignore;
+  A.pf_dist = c->pf_dist;
   A.etype = c->etype;
   A.inj_ps = c->inj_ps; A.inj_psxsr = c->inj_psxsr; A.inj_smin = c->inj_smin; A.inj_shear = c->inj_shear;
   A.inj_flags = c->inj_flags; A.inj_incl = c->inj_incl;
@@ -513,6 +518,7 @@ int ftb200_destroy(ftb200_ctx* ctx) {
   if (ctx->ev_step) cudaEventDestroy(ctx->ev_step);
   if (ctx->ev_nodes_done) cudaEventDestroy(ctx->ev_nodes_done);
   if (ctx->ev_energy_done) cudaEventDestroy(ctx->ev_energy_done);
+  if (ctx->ring_host) cudaFreeHost(ctx->ring_host);
   delete ctx;
   return FTB200_OK;
 }
@@ -948,6 +954,14 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       if (ctx->has_tet) { ctx->fused = false; ctx->pipe = false; }  // the one-kernel variants are hexahedra only
     }
     ctx->node_grid = std::max(1, std::min(prop.multiProcessorCount * nb, nTilesN));
+    {
+      // element kernels: optional L2 prefetch for the blocks `waves` waves ahead (a wave = SMs x 8 resident 64-element
+      // blocks).  Measured at 100^3 for 1-4 waves: no gain (k_elem_affine 170 -> 172 us, general kernel unchanged), so
+      // the exposed part of the prologue is not DRAM latency of first-touch lines; off unless asked for.
+      double waves = 0.0;
+      if (const char* ev = getenv("FTB200_PREFETCH_WAVES")) waves = atof(ev);
+      ctx->pf_dist = waves > 0.0 ? (int)(waves * prop.multiProcessorCount * 8) * ELEM_BLOCK : 0;
+    }
   }
   // ---- validate the reference configuration: detJ0 > 0 at every Gauss point --------------------
   {
@@ -1222,6 +1236,7 @@ int ftb200_explicit_begin_dt(ftb200_ctx* ctx, double Time0, double reduction, do
   memset(&h, 0, sizeof(h));
   memcpy(h.bc_rate, rate, sizeof(rate));
   h.hist_cap = ctx->hist_cap;
+  h.ring = ctx->ring_dev; h.ring_cap = ctx->ring_cap;
   h.Time = Time0; h.tMax = 1e300; h.reduction = reduction; h.failure_dt = failure_dt;
   h.dtmin_bits = 0x7FF0000000000000ULL;
   h.energy_every = energy_every;
@@ -1581,6 +1596,28 @@ int ftb200_explicit_run(ftb200_ctx* ctx, double tMax, long long maxSteps, long l
   if (dt) *dt = d;
   if (st & 1) return fail(ctx, FTB200_ERR_MATERIAL, "Unknown material type");
   if (st & 16) return fail(ctx, FTB200_ERR_TIMESTEP, "Timestep too small, dt below FailureTimeStep");
+  return FTB200_OK;
+}
+
+int ftb200_step_ring(ftb200_ctx* ctx, long long capacity, double** host_ring) {
+  if (!ctx || !ctx->shape_ok || capacity < 0) return fail(ctx, FTB200_ERR_INPUT, "step_ring: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->ring_host) { cudaFreeHost(ctx->ring_host); ctx->ring_host = nullptr; ctx->ring_dev = nullptr; }
+  ctx->ring_cap = 0;
+  if (capacity > 0) {
+    void* hp = nullptr;
+    void* dp = nullptr;
+    CK(cudaHostAlloc(&hp, 8 * sizeof(double) * (size_t)capacity, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(&dp, hp, 0));
+    ctx->ring_host = static_cast<double*>(hp);
+    ctx->ring_dev = static_cast<double*>(dp);
+    ctx->ring_cap = capacity;
+    for (long long i = 0; i < 8 * capacity; ++i) ctx->ring_host[i] = (i % 8 == 2) ? -1.0 : 0.0;
+  }
+  CK(cudaMemcpy(&ctx->sc->ring, &ctx->ring_dev, sizeof(double*), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(&ctx->sc->ring_cap, &ctx->ring_cap, sizeof(long long), cudaMemcpyHostToDevice));
+  if (host_ring) *host_ring = ctx->ring_host;
   return FTB200_OK;
 }
 

@@ -48,7 +48,24 @@ struct DevScalars {
   long long hist_cap;               // capacity of dt/energy history (steps)
   int energy_every;
   unsigned node_done;               // k_node<..., ADV>: blocks finished (reset by the last one)
+  double* ring;                     // step ring in mapped pinned host memory (ftb200_step_ring), or nullptr
+  long long ring_cap;               // records (8 doubles each)
 };
+
+// One record per finished step, written by the device straight into pinned host memory (64 bytes over PCIe, no host
+// synchronisation): Time, next dt, finished steps, status bits, Wint, Wext, WKE, |total|.  The step counter is stored
+// last, behind a system-scope fence: a host that sees record[2] == k may read the rest of the record of step k.
+__device__ __forceinline__ void step_ring_write(DevScalars* sc) {
+  double* r = sc->ring;
+  if (!r || sc->ring_cap <= 0 || sc->step <= 0) return;
+  volatile double* q = r + 8 * ((sc->step - 1) % sc->ring_cap);
+  q[2] = -1.0;
+  __threadfence_system();
+  q[0] = sc->Time; q[1] = sc->ndt; q[3] = (double)sc->status;
+  q[4] = sc->Wint; q[5] = sc->Wext; q[6] = sc->WKE; q[7] = sc->Etot;
+  __threadfence_system();
+  q[2] = (double)sc->step;
+}
 
 __device__ __forceinline__ unsigned long long dt_to_bits(double v) {
   // NaN is never selected by the reference (`dtElem < dtMin` is false); a negative dt would be
@@ -155,6 +172,7 @@ struct ElemArgs {
   int nE;            // plane stride
   int e0, e1;        // element range of this launch
   int ignore_loop_flags;
+  int pf_dist;             // L2 prefetch distance in elements (0 = off), see elem_prefetch_begin
   const uint8_t* etype;    // 1 = C3D4 (nodes in conn planes 0..3), nullptr = all C3D8; internal order
   // injury criteria (k_elem<..., WITH_INJ>), internal element order; see InjState below
   double* inj_ps;          // PS_Old: max principal strain of the previous step in, of this step out (ex5.cpp:1367)
@@ -214,6 +232,37 @@ struct StagedIn {
   }
 };
 
+// L2 prefetch for the blocks that will take this block's place two waves from now.  The first touch of an element's
+// connectivity and of its "new" nodes comes from DRAM (K_node streams 0.45 GB through L2 between two element kernels), and
+// with 12-16 warps per SM the two dependent DRAM latencies (connectivity -> nodal gather) are the exposed part of the
+// prologue (ncu: 47 % of the warp time for 23 % of the fp64 work).  Every thread asks for the connectivity/pid lines of
+// element e + pf_dist and reads ONE node id of that element -- not used until the kernel's last instruction, where the
+// node's displacement (and coordinate) lines are requested: off the critical path, 1 register, 5-8 instructions.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ int elem_prefetch_begin(const ElemArgs& A, const int e) {
+  int pfn = -1;
+  if (A.pf_dist > 0) {
+    const int epf = e + A.pf_dist;
+    if (epf < A.e1) {
+      const size_t E = (size_t)A.nE;
+      prefetch_l2(A.conn + (size_t)(threadIdx.x & 7) * E + epf);  // 8 planes x 4 sectors per warp = the 8 lines
+      prefetch_l2(A.pid + epf);
+      pfn = __ldg(A.conn + 6 * E + epf);  // local node 6 (+,+,+): the node a sweep through the mesh meets first here
+    }
+  }
+  return pfn;
+}
+template <bool WITH_X>
+__device__ __forceinline__ void elem_prefetch_end(const ElemArgs& A, const int pfn) {
+  if (pfn >= 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      prefetch_l2(A.u[c] + pfn);
+      if (WITH_X) prefetch_l2(A.X[c] + pfn);
+    }
+  }
+}
+
 // K1 (+K6).  MATSEL >= 0: every element of the launch has that material (no switch).
 // material 5 (36 history doubles per Gauss point in flight) and the generic per-element switch need more
 // registers than 168: they run with 4 resident blocks per SM instead of 6
@@ -232,6 +281,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
     if (WITH_DT) skip = __ldg(A.eflag + e);     // element skipped by StableTimeStep (:13-19); not a late, exposed load
   }
   if (!A.ignore_loop_flags && (A.sc->last | A.sc->done)) return;
+  const int pfn = (WITH_FORCE && WITH_DT) ? elem_prefetch_begin(A, e) : -1;
   __shared__ double sm_cols[WITH_FORCE ? 72 : 1][ELEM_BLOCK];
   extern __shared__ double sm_hstage[];  // material 5 only: [2][18][ELEM_BLOCK] (dynamic: beyond the 48 KB static limit)
   constexpr bool STAGED_HIST = WITH_FORCE && MATSEL == 5;
@@ -326,6 +376,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
     if ((threadIdx.x & 31) == 0) atomicMin(&A.sc->dtmin_bits, b);
   }
   if (status) atomicOr(&A.sc->status, status);
+  if (WITH_FORCE && WITH_DT) elem_prefetch_end<true>(A, pfn);
 }
 
 // K_elem for runs of hexahedra whose reference geometry is affine (hex8_element_affine_in: parallelepipeds, e.g. every
@@ -394,6 +445,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, MATSEL == 5 ? 4 : (WITH_INJ ? FTB_
     skip = __ldg(A.eflag + e);
   }
   if (!A.ignore_loop_flags && (A.sc->last | A.sc->done)) return;
+  const int pfn = elem_prefetch_begin(A, e);
   __shared__ double sm_cols[FTB_AFFINE_SLOTS][ELEM_BLOCK];
   extern __shared__ double sm_hstage[];
   constexpr bool STAGED_HIST = MATSEL == 5;
@@ -456,6 +508,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, MATSEL == 5 ? 4 : (WITH_INJ ? FTB_
   }
   if ((threadIdx.x & 31) == 0) atomicMin(&A.sc->dtmin_bits, b);
   if (status) atomicOr(&A.sc->status, status);
+  elem_prefetch_end<false>(A, pfn);  // its coordinates are only read if it is node 0, 1, 3 or 4 of an element: rarely first here
 }
 
 // The C3D4 elements of a mixed mesh: they sit in their own index ranges of the internal element
@@ -656,7 +709,15 @@ struct NodeArgs {
   int store_fi;
 };
 
-constexpr int NODE_BLOCK = 256;
+// k_node launch shape: 128-thread blocks, 8 per SM (64 registers, 32 warps/SM).  Measured at 100^3 (k_node with the energy
+// check): 256 threads x 3 blocks (80 registers) 99.8 us, 256 x 4 (64) 98.2 us, 128 x 8 (64) 96.5 us.
+#ifndef FTB_NODE_BLOCK
+#define FTB_NODE_BLOCK 128
+#endif
+#ifndef FTB_NODE_MINBLOCKS
+#define FTB_NODE_MINBLOCKS 8
+#endif
+constexpr int NODE_BLOCK = FTB_NODE_BLOCK;
 
 // K2 + K5 (+ K8 partials).  FINISH: gather fi, a = (fe-fi)/m, second kick.  START: first kick of the
 // next step, drift, boundary condition.  KICK2 = false for step 0 (accelerations only).
@@ -668,7 +729,7 @@ __device__ __forceinline__ void prony_update(double* mp, int nPID, double dt, in
 // read-only scalars k_adv would use; the block that finishes last writes them back, reduces the energy partials in
 // the fixed order of k_energy and refreshes the Prony factors.  Two launches per step instead of four.
 template <bool FINISH, bool START, bool KICK2, bool ENERGY, bool ADV = false>
-__global__ void __launch_bounds__(NODE_BLOCK) k_node(const NodeArgs A) {
+__global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node(const NodeArgs A) {
   DevScalars* sc = A.sc;
   double c_tn, c_tnp1, c_thalf;            // step being finished
   double n_tn, n_tnp1, n_thalf, n_dt;      // next step
@@ -949,6 +1010,7 @@ __device__ __forceinline__ double adv_step(DevScalars* sc, double* dt_hist) {
   sc->nt_np1 = sc->Time + ndt;                    // t_np1 = Time + dt
   sc->nt_half = 0.5 * (sc->nt_np1 + sc->nt_n);    // t_nphalf = 0.5*(t_np1 + t_n)
   if (!(sc->Time < sc->tMax) || sc->steps_left <= 0) sc->last = 1;
+  if (!sc->energy_every) step_ring_write(sc);
   return ndt;
 }
 __device__ __forceinline__ void prony_update(double* mp, int nPID, double dt, int tid, int nthreads) {
@@ -1001,6 +1063,7 @@ __global__ void k_adv(DevScalars* sc, double* mp, int nPID, double Time0, double
       sc->nt_np1 = sc->Time + ndt;                    // t_np1 = Time + dt
       sc->nt_half = 0.5 * (sc->nt_np1 + sc->nt_n);    // t_nphalf = 0.5*(t_np1 + t_n)
       if (!INIT && (!(sc->Time < sc->tMax) || sc->steps_left <= 0)) sc->last = 1;
+      if (!INIT && !sc->energy_every) step_ring_write(sc);  // with the energy check on, k_energy writes the record
       s_ndt = ndt;
     }
     s_live = live;
@@ -1091,6 +1154,7 @@ __global__ void k_energy(DevScalars* sc, const double* epart, int nblocks, doubl
     if (ehist && k >= 0 && k < sc->hist_cap) {
       ehist[4 * k + 0] = sc->Wint; ehist[4 * k + 1] = sc->Wext; ehist[4 * k + 2] = WKE; ehist[4 * k + 3] = sc->Etot;
     }
+    step_ring_write(sc);  // the step's record is complete once its energies are
   }
 }
 

@@ -307,6 +307,27 @@ class FemTech:
         """Enqueue a D2H copy of (Time, dt, steps, status, Wint, Wext, WKE, balance) into pinned host memory; no sync."""
         self._check(self.L.ftb200_explicit_poll_async(self._h, _d(out8_pinned)))
 
+    def step_ring(self, capacity):
+        """Per-step records written by the device into pinned host memory (ftb200_step_ring): returns a live
+        (capacity, 8) view -- Time, next dt, finished steps, status, Wint, Wext, WKE, |balance|; row (k - 1) % capacity
+        belongs to step k once its column 2 reads k."""
+        p = _dp()
+        self._check(self.L.ftb200_step_ring(self._h, int(capacity), C.byref(p)))
+        self._ring = np.ctypeslib.as_array(p, shape=(int(capacity), 8)) if capacity else None
+        return self._ring
+
+    def wait_step(self, k, timeout_s=120.0):
+        """Spin on the step ring until the record of step k (counted from explicit_begin) has arrived; returns a copy."""
+        import time as _t
+        row = self._ring[(k - 1) % self._ring.shape[0]]
+        t0 = _t.perf_counter()
+        while row[2] != k:
+            if row[2] > k:
+                raise FemTechB200Error(3, "step ring overrun: record of step %d was overwritten" % k)
+            if _t.perf_counter() - t0 > timeout_s:
+                raise FemTechB200Error(100, "step %d did not arrive in the step ring" % k)
+        return row.copy()
+
     def run_async(self, timeFinal, steps):
         self._check(self.L.ftb200_explicit_run_async(self._h, float(timeFinal), int(steps)))
 

@@ -133,6 +133,13 @@ int ftb200_explicit_poll(ftb200_ctx *ctx, long long *steps_done, double *Time, d
  * host memory, 8 doubles) receives Time, dt, steps done, status bits, Wint, Wext, WKE, |balance| once the stream gets
  * there.  No host synchronisation. */
 int ftb200_explicit_poll_async(ftb200_ctx *ctx, double *out8_pinned);
+/* Step ring: the device itself writes one 8-double record per finished step -- Time, next dt, finished steps, status
+ * bits, Wint, Wext, WKE, |balance| (the drivers' per-step log line, Benchmarking-Parallel.cpp:160-166 / CheckEnergy.cpp:66-83)
+ * -- into pinned host memory owned by the library (*host_ring, capacity records, slot = (step - 1) % capacity), 64 bytes
+ * over PCIe per step and no host synchronisation.  record[2] (the step counter) is stored last: a host that reads
+ * record[2] == k may use the rest of step k's record.  capacity 0 releases the ring.  Standard loop (element + node
+ * kernels per step, one or several partitions); the opt-in one-kernel variants do not write it. */
+int ftb200_step_ring(ftb200_ctx *ctx, long long capacity, double **host_ring);
 /* Running energies of the last checked step: out[0..3] = Wint, Wext, WKE, |WKE+Wint-Wext| */
 int ftb200_get_energy(ftb200_ctx *ctx, double out[4]);
 /* Optional per-step records kept on the device: capacity in steps (0 disables). */
