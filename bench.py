@@ -42,12 +42,13 @@ def algorithmic_bytes(n, mat, energy):
 
 # (n, material, energy, injury) -> measured DRAM bytes per k_elem launch (ncu, see profiles/)
 # key: (n, material, energy, injury, affine kernel)
-NCU_TRAFFIC_BYTES = {(100, 1, True, False, False): 86516992 + 138026496}
+NCU_TRAFFIC_BYTES = {(100, 1, True, False, False): 86516992 + 138026496,   # profiles/r01_k_elem_final_ncu_full.csv
+                     (100, 1, True, False, True): 86512128 + 143659520}    # profiles/r01_k_elem_affine_ncu_full.csv
 ELEM_FLOPS = {1: 3490.0, 4: 4400.0, 5: 6550.0}  # executed fp64 flops per element in K_elem (ncu for mat 1, SASS count for 4/5)
 # k_elem_affine (parallelepiped reference geometry): per Gauss point 16 DFMA + 19 DMUL fewer (no cofactor / determinant /
 # reciprocal of J0, F in 27 FMAs), no coordinate modes and columns in the prologue, + one cofactor/inverse per element:
-# 510 flops less than the general kernel (SASS count)
-ELEM_FLOPS_AFFINE = {k: v - 510.0 for k, v in ELEM_FLOPS.items()}
+# 552 flops less than the general kernel (ncu, profiles/r01_k_elem_affine_ncu_full.csv)
+ELEM_FLOPS_AFFINE = {k: v - 552.0 for k, v in ELEM_FLOPS.items()}  # mat 1: 2938 (ncu: 1099 DFMA + 357 DADD + 383 DMUL per element)
 
 
 def clocks_sampler(stop, out, device_index):
