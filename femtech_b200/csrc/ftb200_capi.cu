@@ -46,6 +46,12 @@ struct ftb200_ctx {
   int nEb_hex = 0, nEi_hex = 0;   // hexahedra among the boundary / interior elements (they come first in each class)
   struct ElemRange { int e0, e1, tet, mat, affine; };
   std::vector<ElemRange> ranges;  // internal element order = runs of equal (class, element type, material, affine geometry)
+  // overlapped step (k_node_ovl beside the element kernel), see launch_step_overlap
+  bool overlap = false;            // chosen in shape_functions: FTB200_OVERLAP and a mesh that qualifies
+  unsigned *d_ovl_ctr = nullptr, *d_ovl_target = nullptr;
+  unsigned short *d_ovl_lo = nullptr, *d_ovl_hi = nullptr;
+  int ovl_chunks = 0, ovl_grid = 0, ovl_elem_dyn = 0;
+  cudaEvent_t ev_ovl_reset = nullptr, ev_ovl_n1 = nullptr;
   double* ring_host = nullptr;   // step ring (ftb200_step_ring): mapped pinned host memory, its device alias, records
   double* ring_dev = nullptr;
   long long ring_cap = 0;
@@ -212,6 +218,7 @@ ElemArgs elem_args(ftb200_ctx* c, int e0, int e1, int ignore) {
   A.conn = c->conn; A.pid = c->pid; A.eflag = c->eflag; A.mp = c->mp; A.felem = c->felem; A.hist = c->hist;
   A.sc = c->sc; A.nE = c->nE; A.e0 = e0; A.e1 = e1; A.ignore_loop_flags = ignore;
   A.pf_dist = c->pf_dist;
+  A.ovl_ctr = nullptr;
   A.etype = c->etype;
   A.inj_ps = c->inj_ps; A.inj_psxsr = c->inj_psxsr; A.inj_smin = c->inj_smin; A.inj_shear = c->inj_shear;
   A.inj_flags = c->inj_flags; A.inj_incl = c->inj_incl;
@@ -330,8 +337,74 @@ void launch_injury(ftb200_ctx* ctx, cudaStream_t s) {
   LAUNCH(k_injury_lists, cdiv(ctx->nE, 256), 256, s, A, ctx->inj_state);
 }
 
+// ---- overlapped step: element kernel (fp64 pipe) on the main stream with one block per SM less than it
+//      could hold; k_node_ovl (HBM) on the helper stream takes the freed slot and follows it chunk by chunk; then the scalar
+//      update and the START half of the node kernel.  Single partition, one uniform run of hexahedra of material 1 or 4.
+bool overlap_now(const ftb200_ctx* ctx, const double* recv) {
+  return ctx->overlap && !recv && ctx->nranks == 1 && !ctx->rigid && !ctx->injury && !ctx->fuse_adv && ctx->node_ell;
+}
+void launch_elem_overlap(ftb200_ctx* ctx, cudaStream_t s) {
+  const auto& r = ctx->ranges[0];
+  ElemArgs A = elem_args(ctx, 0, ctx->nE, 0);
+  A.ovl_ctr = ctx->d_ovl_ctr;
+  const int grid = cdiv(ctx->nE, ELEM_BLOCK);
+  const size_t dyn = (size_t)ctx->ovl_elem_dyn;  // unused bytes: they only cap the resident blocks per SM
+#define LAUNCH_OVL(kern)                          \
+  do {                                            \
+    auto kfn_ = kern;                             \
+    kfn_<<<grid, ELEM_BLOCK, dyn, s>>>(A);        \
+    ctx->launches++;                              \
+  } while (0)
+  if (r.affine) {
+    if (r.mat == 1) LAUNCH_OVL((k_elem_affine<1, false>));
+    else LAUNCH_OVL((k_elem_affine<4, false>));
+  } else {
+    if (r.mat == 1) LAUNCH_OVL((k_elem<1, true, true>));
+    else LAUNCH_OVL((k_elem<4, true, true>));
+  }
+#undef LAUNCH_OVL
+}
+void launch_step_overlap(ftb200_ctx* ctx) {
+  cudaStream_t s = ctx->stream, s2 = ctx->stream2;
+  size_t i0 = 0, i1 = 0;
+  cudaMemsetAsync(ctx->d_ovl_ctr, 0, ctx->ovl_chunks * sizeof(unsigned), s);
+  cudaEventRecord(ctx->ev_ovl_reset, s);
+  if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
+  launch_elem_overlap(ctx, s);
+  if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.elem.push_back({i0, i1}); }
+  cudaStreamWaitEvent(s2, ctx->ev_ovl_reset, 0);
+  OvlArgs P;
+  P.N = node_args(ctx, nullptr);
+  P.ctr = ctx->d_ovl_ctr; P.target = ctx->d_ovl_target; P.lo = ctx->d_ovl_lo; P.hi = ctx->d_ovl_hi; P.nTiles = ctx->node_blocks;
+  if (ctx->energy) LAUNCH((k_node_ovl<true>), ctx->ovl_grid, NODE_BLOCK, s2, P);
+  else LAUNCH((k_node_ovl<false>), ctx->ovl_grid, NODE_BLOCK, s2, P);
+  cudaEventRecord(ctx->ev_ovl_n1, s2);
+  // k_adv moves the step times k_node_ovl reads and the scalars the previous step's energy reduction reads: after both
+  if (ctx->energy_pending) { cudaStreamWaitEvent(s, ctx->ev_energy_done, 0); ctx->energy_pending = false; }
+  cudaStreamWaitEvent(s, ctx->ev_ovl_n1, 0);
+  LAUNCH((k_adv<false>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, 0.0, ctx->dthist);
+  if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
+  const NodeArgs N = node_args(ctx, nullptr);
+  if (ctx->energy) LAUNCH((k_node<false, true, false, true>), ctx->node_blocks, NODE_BLOCK, s, N);
+  else LAUNCH((k_node<false, true, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+  if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.node.push_back({i0, i1}); }
+  if (ctx->energy) {
+    const bool en_async = ctx->energy_async && ctx->energy_async_now && !ctx->profile;
+    if (en_async) {
+      cudaEventRecord(ctx->ev_nodes_done, s);
+      cudaStreamWaitEvent(s2, ctx->ev_nodes_done, 0);
+      LAUNCH(k_energy, 1, 256, s2, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
+      cudaEventRecord(ctx->ev_energy_done, s2);
+      ctx->energy_pending = true;
+    } else {
+      LAUNCH(k_energy, 1, 256, s, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
+    }
+  }
+}
+
 // one loop iteration: K_elem -> K_adv -> K_node (-> K_energy) (-> injury criteria)
 void launch_step(ftb200_ctx* ctx, const double* recv) {
+  if (overlap_now(ctx, recv)) { launch_step_overlap(ctx); return; }
   cudaStream_t s = ctx->stream;
   size_t i0 = 0, i1 = 0;
   if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
@@ -452,7 +525,8 @@ void free_all(ftb200_ctx* c) {
   dfree(c->p2p_window); dfree(c->d_seq); dfree(c->d_p2p_blocks);
   c->p2p_ready = false;
   if (c->p2p_graph) { cudaGraphExecDestroy(c->p2p_graph); c->p2p_graph = nullptr; }
-  dfree(c->d_nref); dfree(c->d_nint); dfree(c->d_ctl); dfree(c->d_etile_chunk); dfree(c->d_ntile_group); dfree(c->d_etile); dfree(c->d_ell); dfree(c->d_sctl); dfree(c->d_etile32); dfree(c->d_ntile32); dfree(c->d_etile_e); dfree(c->d_eblock);
+  dfree(c->d_nref); dfree(c->d_nint); dfree(c->d_ctl); dfree(c->d_etile_chunk); dfree(c->d_ntile_group); dfree(c->d_etile); dfree(c->d_ell); dfree(c->d_ovl_ctr); dfree(c->d_ovl_target); dfree(c->d_ovl_lo); dfree(c->d_ovl_hi); dfree(c->d_sctl); dfree(c->d_etile32); dfree(c->d_ntile32); dfree(c->d_etile_e); dfree(c->d_eblock);
+  if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
   if (c->fgraph) { cudaGraphExecDestroy(c->fgraph); c->fgraph = nullptr; }
   if (c->pgraph) { cudaGraphExecDestroy(c->pgraph); c->pgraph = nullptr; }
   dfree(c->d_sendNodeIndex); dfree(c->halo_nodes); dfree(c->halo_off); dfree(c->halo_slot); dfree(c->halo_node_idx);
@@ -491,6 +565,8 @@ int ftb200_create(int rank, int nranks, int device, ftb200_ctx** out) {
       cudaEventCreateWithFlags(&ctx->ev_step, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_nodes_done, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_energy_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_ovl_reset, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_ovl_n1, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_energy[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_energy[1], cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
@@ -518,6 +594,8 @@ int ftb200_destroy(ftb200_ctx* ctx) {
   if (ctx->ev_step) cudaEventDestroy(ctx->ev_step);
   if (ctx->ev_nodes_done) cudaEventDestroy(ctx->ev_nodes_done);
   if (ctx->ev_energy_done) cudaEventDestroy(ctx->ev_energy_done);
+  if (ctx->ev_ovl_reset) cudaEventDestroy(ctx->ev_ovl_reset);
+  if (ctx->ev_ovl_n1) cudaEventDestroy(ctx->ev_ovl_n1);
   if (ctx->ring_host) cudaFreeHost(ctx->ring_host);
   delete ctx;
   return FTB200_OK;
@@ -849,6 +927,29 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
     }
     CK(cudaMemcpy(ctx->d_ell, ell.data(), ell.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
+  {  // overlapped step: warps per element chunk, and the range of element chunks every 128-node tile gathers from
+    const int nC = cdiv(nE, OVL_CHUNK), nT = cdiv(nNp, NODE_BLOCK);
+    ctx->ovl_chunks = nC;
+    std::vector<unsigned> target(nC);
+    for (int c = 0; c < nC; ++c) target[c] = (unsigned)cdiv(std::min<long long>(nE, (long long)(c + 1) * OVL_CHUNK) - (long long)c * OVL_CHUNK, 32);
+    std::vector<unsigned short> lo(nT, 0xFFFF), hi(nT, 0);
+    for (int i = 0; i < nNp; ++i) {
+      const int t = i / NODE_BLOCK;
+      for (int j = off[i]; j < off[i + 1]; ++j) {
+        const unsigned short c = (unsigned short)((ent[j] >> 3) >> OVL_CHUNK_SHIFT);
+        lo[t] = std::min(lo[t], c); hi[t] = std::max(hi[t], c);
+      }
+    }
+    for (int t = 0; t < nT; ++t)
+      if (lo[t] == 0xFFFF) { lo[t] = 1; hi[t] = 0; }  // a tile of padding nodes waits for nothing
+    if ((rc = dalloc(ctx, &ctx->d_ovl_ctr, nC)) || (rc = dalloc(ctx, &ctx->d_ovl_target, nC)) || (rc = dalloc(ctx, &ctx->d_ovl_lo, nT)) ||
+        (rc = dalloc(ctx, &ctx->d_ovl_hi, nT)))
+      return rc;
+    CK(cudaMemset(ctx->d_ovl_ctr, 0, nC * sizeof(unsigned)));
+    CK(cudaMemcpy(ctx->d_ovl_target, target.data(), nC * sizeof(unsigned), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_ovl_lo, lo.data(), nT * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_ovl_hi, hi.data(), nT * sizeof(unsigned short), cudaMemcpyHostToDevice));
+  }
   {
     PipeCtl h;
     memset(&h, 0, sizeof(h));
@@ -954,6 +1055,39 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       if (ctx->has_tet) { ctx->fused = false; ctx->pipe = false; }  // the one-kernel variants are hexahedra only
     }
     ctx->node_grid = std::max(1, std::min(prop.multiProcessorCount * nb, nTilesN));
+    {
+      // overlapped step: opt-in while it is being measured (FTB200_OVERLAP=1).  The element kernel gives up one resident
+      // block per SM (a few unused bytes of dynamic shared memory), k_node_ovl runs FTB200_OVL_NODE_BLOCKS (1) per SM.
+      bool want = false;
+      if (const char* ev = getenv("FTB200_OVERLAP")) want = atoi(ev) != 0;
+      const bool ok = ctx->nranks == 1 && ctx->halo_count == 0 && !ctx->has_tet && ctx->ranges.size() == 1 && ctx->ranges[0].e0 == 0 &&
+                      (ctx->ranges[0].mat == 1 || ctx->ranges[0].mat == 4) && ctx->ovl_chunks < 65535;
+      ctx->overlap = want && ok;
+      if (ctx->overlap) {
+        const bool aff = ctx->ranges[0].affine != 0;
+        const int stat = (aff ? FTB_AFFINE_SLOTS : 72) * ELEM_BLOCK * (int)sizeof(double) + 1024;  // static + reserved bytes per block
+        int natural = aff ? FTB_AFF_MINBLOCKS : ELEM_MINBLOCKS;
+        natural = std::min(natural, (int)(prop.sharedMemPerMultiprocessor / stat));
+        int eb2 = natural - 1;
+        if (const char* ev = getenv("FTB200_OVL_ELEM_BLOCKS")) eb2 = std::max(1, std::min(natural, atoi(ev)));
+        // smallest request that no longer lets eb2 + 1 blocks share an SM
+        int dyn = (int)(prop.sharedMemPerMultiprocessor / (eb2 + 1)) - stat + 16;
+        dyn = eb2 >= natural ? 0 : std::max(16, (dyn + 15) / 16 * 16);
+        ctx->ovl_elem_dyn = dyn;
+        int per_sm = 1;
+        if (const char* ev = getenv("FTB200_OVL_NODE_BLOCKS")) per_sm = std::max(1, atoi(ev));
+        ctx->ovl_grid = std::max(1, std::min(prop.multiProcessorCount * per_sm, ctx->node_blocks));
+        // co-residency: an SM's shared-memory carve-out is fixed while blocks live on it; every kernel of the pair asks for
+        // the same (largest) one, otherwise whichever kernel reaches an SM first locks the other out of it
+        const int co = cudaSharedmemCarveoutMaxShared;
+        CK(cudaFuncSetAttribute(k_node_ovl<true>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+        CK(cudaFuncSetAttribute(k_node_ovl<false>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+        CK(cudaFuncSetAttribute(k_elem_affine<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+        CK(cudaFuncSetAttribute(k_elem_affine<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+        CK(cudaFuncSetAttribute(k_elem<1, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+        CK(cudaFuncSetAttribute(k_elem<4, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+      }
+    }
     {
       // element kernels: optional L2 prefetch for the blocks `waves` waves ahead (a wave = SMs x 8 resident 64-element
       // blocks).  Measured at 100^3 for 1-4 waves: no gain (k_elem_affine 170 -> 172 us, general kernel unchanged), so
@@ -1225,7 +1359,9 @@ int ftb200_explicit_begin_dt(ftb200_ctx* ctx, double Time0, double reduction, do
   ctx->energy = energy_every;
   ctx->Time0 = Time0;
   ctx->halo_recv_cur = nullptr;
-  if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+  // the 25-step graph of the standard loop survives a restart: its kernel arguments are device pointers and flags that
+  // explicit_begin does not change (build_graph compares the ones that can; injury / rigid-body / history / stream
+  // changes drop it themselves).  Rebuilding it cost 1-2 ms of every ExplicitDynamics call that starts from host state.
   if (ctx->pgraph) { cudaGraphExecDestroy(ctx->pgraph); ctx->pgraph = nullptr; }
   if (ctx->fgraph) { cudaGraphExecDestroy(ctx->fgraph); ctx->fgraph = nullptr; }
   // scalars: keep bc_rate / hist_cap, reset the rest
@@ -1308,7 +1444,9 @@ static void join_energy(ftb200_ctx* ctx) {
 }
 
 static int build_graph(ftb200_ctx* ctx) {
-  if (ctx->graph && ctx->graph_energy == ctx->energy) return 0;
+  const int sig = ctx->energy | (ctx->has_fe ? 2 : 0) | (overlap_now(ctx, nullptr) ? 4 : 0) | (ctx->energy_async ? 8 : 0) |
+                  (ctx->fuse_adv ? 16 : 0) | (ctx->node_ell ? 32 : 0) | (ctx->injury ? 64 : 0) | (ctx->rigid ? 128 : 0);
+  if (ctx->graph && ctx->graph_energy == sig) return 0;
   if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
   cudaGraph_t g = nullptr;
   const long long before = ctx->launches;
@@ -1321,7 +1459,7 @@ static int build_graph(ftb200_ctx* ctx) {
   e = cudaGraphInstantiate(&ctx->graph, g, 0);
   cudaGraphDestroy(g);
   if (e != cudaSuccess) { ctx->graph = nullptr; return fail(ctx, FTB200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
-  ctx->graph_energy = ctx->energy;
+  ctx->graph_energy = sig;
   return 0;
 }
 
@@ -1526,7 +1664,8 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
     else LAUNCH((k_node<false, true, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   }
   const bool adv_fused = ctx->nranks == 1 && ctx->fuse_adv && !ctx->rigid;
-  const int per_step = (adv_fused ? 2 : 3 + (ctx->energy ? 1 : 0)) + (ctx->injury ? INJ_LAUNCHES : 0) + (ctx->rigid ? 1 : 0);
+  const int per_step = overlap_now(ctx, nullptr) ? 4 + (ctx->energy ? 1 : 0)
+                                                 : (adv_fused ? 2 : 3 + (ctx->energy ? 1 : 0)) + (ctx->injury ? INJ_LAUNCHES : 0) + (ctx->rigid ? 1 : 0);
   long long left = steps;
   const bool use_graph = !ctx->profile;  // built on the first run (warm-up), whatever its length
   if (use_graph) {

@@ -173,6 +173,7 @@ struct ElemArgs {
   int e0, e1;        // element range of this launch
   int ignore_loop_flags;
   int pf_dist;             // L2 prefetch distance in elements (0 = off), see elem_prefetch_begin
+  unsigned* ovl_ctr;       // overlapped step (k_node_ovl): finished warps per chunk of OVL_CHUNK elements, or nullptr
   const uint8_t* etype;    // 1 = C3D4 (nodes in conn planes 0..3), nullptr = all C3D8; internal order
   // injury criteria (k_elem<..., WITH_INJ>), internal element order; see InjState below
   double* inj_ps;          // PS_Old: max principal strain of the previous step in, of this step out (ex5.cpp:1367)
@@ -260,6 +261,20 @@ __device__ __forceinline__ void elem_prefetch_end(const ElemArgs& A, const int p
       prefetch_l2(A.u[c] + pfn);
       if (WITH_X) prefetch_l2(A.X[c] + pfn);
     }
+  }
+}
+
+// Overlapped step: the element kernel announces every finished warp (32 consecutive elements, forces stored) in the
+// counter of its chunk; k_node_ovl, running beside it, starts a node tile as soon as the chunks holding its elements are
+// complete.  Release side: stores -> device-scope fence (every lane) -> warp barrier -> one atomic per warp.
+#define OVL_CHUNK_SHIFT 14
+#define OVL_CHUNK (1 << OVL_CHUNK_SHIFT)
+__device__ __forceinline__ void elem_announce(const ElemArgs& A, const int e) {
+  if (A.ovl_ctr) {
+    __threadfence();
+    __syncwarp();
+    const int e_warp = e - (int)(threadIdx.x & 31);
+    if ((threadIdx.x & 31) == 0 && e_warp < A.e1) atomicAdd(A.ovl_ctr + (e_warp >> OVL_CHUNK_SHIFT), 1u);
   }
 }
 
@@ -376,7 +391,10 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
     if ((threadIdx.x & 31) == 0) atomicMin(&A.sc->dtmin_bits, b);
   }
   if (status) atomicOr(&A.sc->status, status);
-  if (WITH_FORCE && WITH_DT) elem_prefetch_end<true>(A, pfn);
+  if (WITH_FORCE && WITH_DT) {
+    elem_announce(A, e);
+    elem_prefetch_end<true>(A, pfn);
+  }
 }
 
 // K_elem for runs of hexahedra whose reference geometry is affine (hex8_element_affine_in: parallelepipeds, e.g. every
@@ -508,6 +526,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, MATSEL == 5 ? 4 : (WITH_INJ ? FTB_
   }
   if ((threadIdx.x & 31) == 0) atomicMin(&A.sc->dtmin_bits, b);
   if (status) atomicOr(&A.sc->status, status);
+  elem_announce(A, e);
   elem_prefetch_end<false>(A, pfn);  // its coordinates are only read if it is node 0, 1, 3 or 4 of an element: rarely first here
 }
 
@@ -752,7 +771,7 @@ __global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node(const N
     last_new = (dtmin < sc->failure_dt) || !(c_tnp1 < sc->tMax) || (sc->steps_left - 1 <= 0);
   } else {
     if (FINISH && !sc->active) return;
-    if (!FINISH && sc->done) return;
+    if (!FINISH && (sc->done | sc->last)) return;  // START alone: at the beginning of a run, or behind k_adv in the overlapped step
     c_tn = c_tnp1 = c_thalf = n_tn = n_tnp1 = n_thalf = n_dt = 0.0;  // read from sc where they are used
     last_new = sc->last != 0;
   }
@@ -994,6 +1013,158 @@ __device__ __forceinline__ unsigned long long pipe_now_ns_early() {
   return t;
 }
 // one loop iteration's scalar bookkeeping (thread 0 of one block); returns the next dt
+// ---------------------------------------------------------------------------------------------
+// Overlapped step (single partition, one uniform run of hexahedra): the memory-bound half of the node work runs BESIDE
+// the fp64-bound element kernel instead of after it.
+//   k_node_ovl  (helper stream, persistent, at most one or two blocks per SM): the FINISH phase of k_node -- deterministic
+//               gather of f_int in ascending element id, a = (f_e - f_i)/m, second kick, energy partials -- tile by tile,
+//               each tile as soon as the element chunks it depends on are announced (elem_announce).  It needs only the
+//               times of the step being integrated (sc->nt_*: k_adv has not yet moved them to sc->t_*), never the new dt.
+//   k_node<false, true, ...> (main stream, after k_adv): the START phase -- first kick and drift with the new dt,
+//               boundary conditions -- the only node work left on the critical path.
+// The element kernel never waits for anything, and k_node_ovl holds a bounded number of blocks (grid <= 2 x SMs), so the
+// pair cannot deadlock whatever order the hardware schedules them in.  Same arithmetic, same summation order and the same
+// 128-node energy partials as the serial step: the results are bit-identical (tests/test_gpu_overlap.py).
+__device__ __forceinline__ unsigned long long ovl_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct OvlArgs {
+  NodeArgs N;
+  const unsigned* ctr;       // finished warps per element chunk (this step)
+  const unsigned* target;    // warps per element chunk
+  const unsigned short* lo;  // per node tile: first and last element chunk it reads
+  const unsigned short* hi;
+  int nTiles;
+};
+template <bool ENERGY>
+__global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node_ovl(const OvlArgs P) {
+  const NodeArgs& A = P.N;
+  DevScalars* sc = A.sc;
+  if (sc->done | sc->last) return;  // the step does not run (the element kernel and k_adv apply the same test)
+  const double dt1 = sc->nt_half - sc->nt_n, dt2 = sc->nt_np1 - sc->nt_half;
+  __shared__ int s_ok;
+  __shared__ double sw[2][3][NODE_BLOCK / 32];
+  int upto = 0;  // thread 0: element chunks [0, upto) are known to be complete (tiles come in ascending order)
+  int par = 0;
+  for (int tile = blockIdx.x; tile < P.nTiles; tile += gridDim.x, par ^= 1) {
+    const int n = tile * NODE_BLOCK + threadIdx.x;
+    // everything that does not depend on the element kernel is requested before the wait
+    unsigned fl = 0;
+    double vv[3], aa[3], dd[3], fprev[3], fext[3], m = 1.0;
+    int ent[8];
+    if (n < A.nN) {
+      fl = A.flags[n];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) ent[q] = __ldg(A.ell + (size_t)q * A.nN + n);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        vv[c] = A.v[c][n];
+        aa[c] = A.a[c][n];
+        fext[c] = A.fe[c] ? A.fe[c][n] : 0.0;
+        if (ENERGY) { dd[c] = A.du[c][n]; fprev[c] = A.fi[c][n]; }
+      }
+      m = A.m[n];
+    }
+    if (threadIdx.x == 0) {
+      int ok = 1;
+      const int c1 = P.hi[tile];
+      if (c1 >= upto) {
+        for (int c = upto; c <= c1 && ok; ++c) {
+          const unsigned want = P.target[c];
+          const volatile unsigned* q = P.ctr + c;
+          if (*q < want) {
+            const unsigned long long t0 = ovl_now_ns();
+            while (*q < want) {
+              __nanosleep(100);
+              if (ovl_now_ns() - t0 > 2000000000ULL) { ok = 0; break; }  // 2 s: the element kernel is gone
+            }
+          }
+        }
+        upto = c1 + 1;
+        __threadfence();  // acquire: the forces announced by the counters are visible to the loads below
+      }
+      s_ok = ok;
+    }
+    __syncthreads();
+    if (!s_ok) {
+      if (threadIdx.x == 0) atomicOr(&sc->status, 32);
+      return;
+    }
+    double wke = 0.0, wint = 0.0, wext = 0.0;
+    if (n < A.nN) {
+      double f[3] = {0.0, 0.0, 0.0};
+      double fv[8][3];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int en = ent[q] < 0 ? 0 : ent[q];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)  // written by the concurrently running element kernel: L2 loads, never the read-only path
+          fv[q][c] = (ent[q] >= 0) ? __ldcg(A.felem + FTB_FIDX(3 * (en & 7) + c, en >> 3)) : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) f[c] += fv[q][c];
+      if (fl & FTB_FLAG_OVERFLOW)
+        for (int j = A.node_off[n] + 8, j1 = A.node_off[n + 1]; j < j1; ++j) {
+          const int en = __ldg(A.node_ent + j);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) f[c] += __ldcg(A.felem + FTB_FIDX(3 * (en & 7) + c, en >> 3));
+        }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const bool b = (fl >> c) & 1u;
+        const double fnet = fext[c] - f[c];
+        const double a_old = aa[c];
+        if (!b) aa[c] = fnet / m;
+        if (!b) {
+          const double vhalf = vv[c] + dt1 * a_old;
+          vv[c] = vhalf + dt2 * aa[c];
+        }
+        if (ENERGY && !(fl & FTB_FLAG_NOTOWNED)) {
+          wke += m * vv[c] * vv[c];
+          if (b) wext += dd[c] * (fprev[c] + f[c] + m * (aa[c] + a_old));
+          wint += dd[c] * (fprev[c] + f[c]);
+          wext += dd[c] * (fext[c] + fext[c]);
+        }
+        if (A.store_fi) A.fi[c][n] = f[c];
+        A.v[c][n] = vv[c];
+        A.a[c][n] = aa[c];
+      }
+    }
+    if (ENERGY) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        wke += __shfl_down_sync(0xffffffffu, wke, o);
+        wint += __shfl_down_sync(0xffffffffu, wint, o);
+        wext += __shfl_down_sync(0xffffffffu, wext, o);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        sw[par][0][threadIdx.x >> 5] = wke;
+        sw[par][1][threadIdx.x >> 5] = wint;
+        sw[par][2][threadIdx.x >> 5] = wext;
+      }
+      __syncthreads();  // the other parity's buffer is free again by the time any warp gets here next
+      if (threadIdx.x == 0) {
+        double s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int w = 0; w < NODE_BLOCK / 32; ++w) {
+          s0 += sw[par][0][w];
+          s1 += sw[par][1][w];
+          s2 += sw[par][2][w];
+        }
+        A.epart[tile] = s0;  // the serial kernel's layout: partial of node block `tile`
+        A.epart[P.nTiles + tile] = s1;
+        A.epart[2 * P.nTiles + tile] = s2;
+      }
+    } else {
+      __syncthreads();  // s_ok is rewritten by thread 0 at the top of the next tile
+    }
+  }
+}
+
 __device__ __forceinline__ double adv_step(DevScalars* sc, double* dt_hist) {
   double dtmin = __longlong_as_double((long long)*(volatile unsigned long long*)&sc->dtmin_bits);
   if (dtmin > 1e20) dtmin = 1e20;  // `huge`, GlobalVariables.h:16

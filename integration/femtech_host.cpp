@@ -263,14 +263,32 @@ void ExplicitDynamics(double timeFinal, char *name) {
   check(ftb200_set_state(g_ctx, displacements, velocities, accelerations, boundary));
   check(ftb200_set_bc(g_ctx, g_bc_kind, g_bc_rate));
   check(ftb200_explicit_begin(g_ctx, Time, ExplicitTimeStepReduction, FailureTimeStep, g_energy_every));
-  long long steps = 0;
-  check(ftb200_explicit_run(g_ctx, timeFinal, 0x7FFFFFFFFFFFLL, &steps, &Time, &dt));
-  check(ftb200_get_state(g_ctx, displacements, velocities, accelerations, boundary, fi, f_net));
-  if (g_energy_every && world_rank == 0) {
-    double e[4];
-    check(ftb200_get_energy(g_ctx, e));
-    fprintf(energyFile, "%12.6e %12.6e  %12.6e  %12.6e %12.6e\n", Time, e[0], e[1], e[2], e[3]);
+  /* The loop runs in slices of RING/2 steps; every finished step's record (Time, dt, step, status, energies) is written by
+   * the device into the pinned host ring of ftb200_step_ring, and the energy file gets the line CheckEnergy would have
+   * written for that step (CheckEnergy.cpp:66-83: "%12.6e %12.6e  %12.6e  %12.6e %12.6e") -- one line per step, as in the
+   * reference's drivers, without a host round trip per step. */
+  const long long RING = 512;
+  double *ring = NULL;
+  check(ftb200_step_ring(g_ctx, RING, &ring));
+  long long steps = 0, done = 0;
+  int st = 0;
+  for (;;) {
+    check(ftb200_explicit_run_async(g_ctx, timeFinal, RING / 2));
+    long long now = 0;
+    check(ftb200_explicit_poll(g_ctx, &now, &Time, &dt, &st));
+    for (long long k = done + 1; k <= now; ++k) {
+      const volatile double *r = ring + 8 * ((k - 1) % RING);
+      if (r[2] != (double)k) { FILE_LOG_SINGLE(ERROR, "ExplicitDynamics: step ring out of sequence at step %lld", k); TerminateFemTech(3); }
+      if (g_energy_every && world_rank == 0) fprintf(energyFile, "%12.6e %12.6e  %12.6e  %12.6e %12.6e\n", r[0], r[4], r[5], r[6], r[7]);
+    }
+    steps += now - done;
+    if (now == done || !(Time < timeFinal) || (st & 16)) break;
+    done = now;
   }
+  check(ftb200_step_ring(g_ctx, 0, NULL));
+  if (st & 1) { FILE_LOG_SINGLE(ERROR, "Unknown material type"); TerminateFemTech(1); }
+  if (st & 16) { FILE_LOG_SINGLE(ERROR, "Timestep too small, dt below FailureTimeStep"); TerminateFemTech(19); }
+  check(ftb200_get_state(g_ctx, displacements, velocities, accelerations, boundary, fi, f_net));
   FILE_LOG_MASTER(INFO, "ExplicitDynamics: %lld steps on the GPU, Time = %15.6e", steps, Time);
 }
 

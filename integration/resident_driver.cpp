@@ -1,0 +1,68 @@
+// resident_driver.cpp -- a FemTech driver in the style of examples/Benchmarking-Parallel that uses the RESIDENT mode of
+// femtech_b200: the reference's own setup calls (InitFemTechWoInput, ReadInputFile, ReadMaterials, PartitionMesh,
+// AllocateArrays, ShapeFunctions, AssembleLumpedMass: include/FemTech.h), the boundary condition of the benchmark
+// (Benchmarking-Parallel.cpp:184-244) handed over as a descriptor, then ONE ExplicitDynamics(tMax) -- the whole time
+// loop of Benchmarking-Parallel.cpp:106-171 runs on the GPU and the energy file receives one line per step, written from
+// the records the device streams into pinned host memory.  Linked by integration/build_dropin.sh against
+// femtech_host.o + libftb200.so + the reference's readers/partitioner.
+//
+//   resident_driver <mesh.inp|.k> [tMax=0.1] [dMax=0.007] [cubeL=0.005] [energy_every=1]
+//
+// Writes <mesh>.resident.txt: nNodes, steps (from the energy file), Time, then u of every node (%.17g) for the test.
+#include "FemTech.h"
+#include "femtech_b200_ext.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+double Time, dt;
+int nSteps;
+double ExplicitTimeStepReduction = 0.8;
+double FailureTimeStep = 1e-11;
+int nPlotSteps = 50;
+bool ImplicitStatic = false;
+bool ImplicitDynamic = false;
+bool ExplicitDynamic = true;
+
+int main(int argc, char **argv) {
+  if (argc < 2) {
+    fprintf(stderr, "usage: %s mesh [tMax] [dMax] [cubeL] [energy_every]\n", argv[0]);
+    return 2;
+  }
+  const double tMax = argc > 2 ? atof(argv[2]) : 0.1, dMax = argc > 3 ? atof(argv[3]) : 0.007;
+  const double L = argc > 4 ? atof(argv[4]) : 0.005;
+  const int energy_every = argc > 5 ? atoi(argv[5]) : 1;
+  InitFemTechWoInput(argc, argv);
+  ReadInputFile(argv[1]);
+  ReadMaterials();
+  PartitionMesh();
+  AllocateArrays();
+  Time = 0.0;
+  dt = 0.0;
+  ShapeFunctions();
+  AssembleLumpedMass();
+  // the benchmark's boundary condition as a descriptor: faces x = 0, y = 0, z = 0 held in their normal direction,
+  // face y = L pulled with u_y = Time * dMax / tMax
+  const double tol = 1e-5;
+  std::vector<int> kind((size_t)nNodes * ndim, 0);
+  double rate[4] = {0.0, 0.0, dMax / tMax, 0.0};
+  for (int i = 0; i < nNodes; ++i) {
+    for (int c = 0; c < ndim; ++c)
+      if (fabs(coordinates[ndim * i + c]) < tol) kind[ndim * i + c] = 1;
+    if (fabs(coordinates[ndim * i + 1] - L) < tol) kind[ndim * i + 1] = 2;
+  }
+  femtech_b200_set_bc(kind.data(), rate, energy_every);
+  ExplicitDynamics(tMax, argv[1]);
+  const std::string out = std::string(argv[1]) + ".resident.txt";
+  FILE *f = fopen(out.c_str(), "w");
+  if (!f) return 3;
+  fprintf(f, "%d %.17g %.17g\n", nNodes, Time, dt);
+  for (int i = 0; i < nNodes * ndim; ++i) fprintf(f, "%.17g\n", displacements[i]);
+  fclose(f);
+  FreeArrays();
+  FinalizeFemTech();
+  return 0;
+}

@@ -127,3 +127,36 @@ def test_mixed_mesh_through_reference_reader_and_symbols(tmp_path):
     assert rel(o["displacements"], d["displacements"]) < 1e-9 and rel(o["mass"], d["mass"]) < 1e-13
     assert o["F"].size == d["F"].size and rel(o["F"], d["F"]) < 1e-9 and rel(o["pk2"], d["pk2"]) < 1e-9
     assert rel(o["Eavg"], d["Eavg"]) < 1e-9
+
+
+def test_resident_driver_one_explicit_dynamics_call(tmp_path):
+    """integration/resident_driver.cpp: the reference's setup calls (its own reader, partitioner and allocator), the
+    benchmark's boundary condition as a descriptor, then ONE ExplicitDynamics(tMax) through the reference's symbol --
+    the whole loop on the GPU.  End state against the oracle at 1e-9; the energy file must hold one line per step
+    (written from the records the device streams into the pinned step ring) with the oracle's running energies."""
+    exe = _need("dropin_resident")
+    from oracle import pyoracle as po
+    X, conn, pid = mesh.cube_mesh(20)
+    soft = [1040.0, 100.0, 100.0, 0, 0, 0, 0, 0, 0]
+    mesh.write_abaqus_inp(str(tmp_path / "cube10.inp"), X, conn, pid)
+    mesh.write_materials_dat(str(tmp_path / "materials.dat"), [1], soft)
+    tMax = 0.1  # the benchmark's run on a 20^3 mesh: ~290 steps, two slices of the host layer's loop
+    r = subprocess.run([exe, "cube10.inp", repr(tMax), repr(0.007 * tMax / 0.1)], cwd=tmp_path, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, (r.stdout[-1000:], r.stderr[-2000:])
+    o = po.OracleModel(X, conn, pid, [1], soft)
+    o.ShapeFunctions()
+    o.AssembleLumpedMass()
+    kind, rate = mesh.benchmark_bc(X, dMax=0.007 * tMax / 0.1, tMax=tMax)
+    n, _, eh = po.run_explicit([o], [kind], rate, tMax, 10 ** 6)
+    lines = open(tmp_path / "cube10.inp.resident.txt").read().split()
+    nN, T = int(lines[0]), float(lines[1])
+    u = np.array([float(x) for x in lines[3:]])
+    assert nN == X.shape[0] and abs(T - o.Time) <= 1e-11 * o.Time
+    assert np.abs(u - o.displacements).max() < 1e-9 * np.abs(o.displacements).max()
+    en = np.array([[float(x) for x in l.split()] for l in open(tmp_path / [f for f in os.listdir(tmp_path) if f.startswith("energy_")][0])
+                   if not l.startswith("#")])
+    assert en.shape == (n, 5)  # one line per step
+    assert np.all(np.diff(en[:, 0]) > 0) and abs(en[-1, 0] - o.Time) <= 1e-6 * o.Time
+    eh = np.asarray(eh)
+    assert np.allclose(en[:, 1:4], eh[:, :3], rtol=5e-6, atol=1e-30)
