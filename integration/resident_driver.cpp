@@ -62,7 +62,6 @@ int main(int argc, char **argv) {
   fprintf(f, "%d %.17g %.17g\n", nNodes, Time, dt);
   for (int i = 0; i < nNodes * ndim; ++i) fprintf(f, "%.17g\n", displacements[i]);
   fclose(f);
-  FreeArrays();
-  FinalizeFemTech();
+  FinalizeFemTech();  // frees the arrays (InitFinalizeFemTech.cpp:75-80)
   return 0;
 }
