@@ -449,8 +449,11 @@ struct StagedInAffine {
     }
   }
 };
+#ifndef FTB_AFF_INJ_MINBLOCKS
+#define FTB_AFF_INJ_MINBLOCKS 8  // measured at 100^3 with the criteria on: 8 blocks (128 registers, some spills) 218 us, 5-6 blocks (162-168) 238 us
+#endif
 template <int MATSEL, bool WITH_INJ>
-__global__ void __launch_bounds__(ELEM_BLOCK, MATSEL == 5 ? 4 : (WITH_INJ ? FTB_INJ_MINBLOCKS : FTB_AFF_MINBLOCKS)) k_elem_affine(const ElemArgs A) {
+__global__ void __launch_bounds__(ELEM_BLOCK, MATSEL == 5 ? 4 : (WITH_INJ ? FTB_AFF_INJ_MINBLOCKS : FTB_AFF_MINBLOCKS)) k_elem_affine(const ElemArgs A) {
   const int e = A.e0 + blockIdx.x * ELEM_BLOCK + threadIdx.x;
   const size_t E = (size_t)A.nE;
   int nd[8];

@@ -443,6 +443,120 @@ FTB_HD void face_pair(const double mD[3], const double m123[3], const double mA[
     }
   }
 }
+// largest face area A_max of the element (CalculateCharacteristicLength_C3D8.cpp:10-27 over Geometry.cpp:29-64),
+// every face evaluated in full: the straightforward form, kept as the checker of hex_face_amax below
+FTB_HD double hex_face_amax_all(const double xm[7][3]) {
+  const double* g1 = xm[0]; const double* g2 = xm[1]; const double* g3 = xm[2];
+  const double* g12 = xm[3]; const double* g23 = xm[4]; const double* g13 = xm[5]; const double* g123 = xm[6];
+  double n2max = 0.0, aslow = 0.0;
+  face_pair(g12, g123, g1, g13, g2, g23, n2max, aslow);  // zeta = -+1: faces {0,1,2,3},{4,5,6,7}
+  face_pair(g23, g123, g2, g12, g3, g13, n2max, aslow);  // xi   = -+1: faces {0,3,7,4},{1,2,6,5}
+  face_pair(g13, g123, g1, g12, g3, g23, n2max, aslow);  // eta  = -+1: faces {0,1,5,4},{3,2,6,7}
+  // parallelogram area = 4 |c1 x c2| with c = (x8 vector)/8  ->  |x8 cross| / 16
+  const double afast = sqrt(n2max) * 0.0625;
+  return afast > aslow ? afast : aslow;
+}
+
+// The same maximum with the square roots only where they can matter.  A face that takes the Gauss branch
+// (Geometry.cpp:50-63) has the area  A = sum over the four points of |v1 x v2|,  v1 = c1 + qj cD, v2 = c2 + qi cD,
+// qi, qj = +-1/sqrt(3).  With N0 = c1 x c2, N1 = c1 x cD, N2 = cD x c2 the four cross products are N0 + qi N1 + qj N2, so
+//     4 |N0|  <=  A  <=  2 sqrt( sum |.|^2 ) = 4 sqrt( |N0|^2 + (|N1|^2 + |N2|^2)/3 )
+// (triangle inequality / Cauchy-Schwarz; the mixed terms of the sum cancel over the four sign pairs).  Pass 1 computes
+// both bounds for all six faces without a square root -- for a parallelogram face (:46-48) they coincide with the exact
+// area -- and only the Gauss faces whose upper bound reaches the largest lower bound are then integrated (24 square roots
+// per distorted element become 4, sometimes 8).  The result is the reference's maximum, formed from the same four
+// norms per face; it differs from hex_face_amax_all by rounding only (tests pin 1e-13).
+// Units: mode vectors are 8 x the reference's centerD/c1/c2, cross products 64 x; areas below are 64 x the true ones.
+FTB_HD void face_pair_bounds(const double mD[3], const double m123[3], const double mA[3], const double mAn[3],
+                             const double mB[3], const double mBn[3], const int f0, double L2[6], double U2[6], unsigned& gmask) {
+  double p1[3], p2[3], q1[3], q2[3];
+  cross3(mA, mB, p1);
+  cross3(mAn, mBn, p2);
+  cross3(mA, mBn, q1);
+  cross3(mAn, mB, q2);
+  const double tol8 = 8.0e-6;
+  const double t = sqrt(3.0) / 3.0, t2 = t * t;
+#pragma unroll
+  for (int sgn = 0; sgn < 2; ++sgn) {
+    const double sg = sgn ? 1.0 : -1.0;
+    const double cD[3] = {mD[0] + sg * m123[0], mD[1] + sg * m123[1], mD[2] + sg * m123[2]};
+    const double x = (p1[0] + p2[0]) + sg * (q1[0] + q2[0]);
+    const double y = (p1[1] + p2[1]) + sg * (q1[1] + q2[1]);
+    const double z = (p1[2] + p2[2]) + sg * (q1[2] + q2[2]);
+    const double n0 = x * x + y * y + z * z;  // |c1 x c2|^2
+    L2[f0 + sgn] = 16.0 * n0;
+    if ((cD[0] < tol8) && (cD[1] < tol8) && (cD[2] < tol8)) {
+      U2[f0 + sgn] = 16.0 * n0;
+    } else {
+      double c1[3], c2[3], N1[3], N2[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { c1[i] = mA[i] + sg * mAn[i]; c2[i] = mB[i] + sg * mBn[i]; }
+      cross3(c1, cD, N1);
+      cross3(cD, c2, N2);
+      const double n12 = (N1[0] * N1[0] + N1[1] * N1[1] + N1[2] * N1[2]) + (N2[0] * N2[0] + N2[1] * N2[1] + N2[2] * N2[2]);
+      U2[f0 + sgn] = 16.0 * (n0 + t2 * n12);
+      gmask |= 1u << (f0 + sgn);
+    }
+  }
+}
+FTB_HD double sel3(const int p, const double a, const double b, const double c) { return p == 0 ? a : (p == 1 ? b : c); }
+FTB_HD double hex_face_amax(const double xm[7][3]) {
+  const double* g1 = xm[0]; const double* g2 = xm[1]; const double* g3 = xm[2];
+  const double* g12 = xm[3]; const double* g23 = xm[4]; const double* g13 = xm[5]; const double* g123 = xm[6];
+  double L2[6], U2[6];
+  unsigned gmask = 0;  // bit f: face f takes the Gauss branch
+  face_pair_bounds(g12, g123, g1, g13, g2, g23, 0, L2, U2, gmask);  // zeta = -+1
+  face_pair_bounds(g23, g123, g2, g12, g3, g13, 2, L2, U2, gmask);  // xi   = -+1
+  face_pair_bounds(g13, g123, g1, g12, g3, g23, 4, L2, U2, gmask);  // eta  = -+1
+  double M = 0.0, para2 = 0.0;
+#pragma unroll
+  for (int f = 0; f < 6; ++f) {
+    M = L2[f] > M ? L2[f] : M;
+    if (!((gmask >> f) & 1u)) para2 = L2[f] > para2 ? L2[f] : para2;
+  }
+  double best = sqrt(para2);  // exact for the parallelogram faces
+  if (gmask) {
+    unsigned cand = 0;
+#pragma unroll
+    for (int f = 0; f < 6; ++f)
+      if (((gmask >> f) & 1u) && U2[f] * (1.0 + 1e-12) >= M) cand |= 1u << f;
+    const double t = sqrt(3.0) / 3.0;
+    while (cand) {  // each lane integrates ITS next candidate: one trip for most elements, whatever the faces are
+      int f = 0;
+#if defined(__CUDA_ARCH__)
+      f = __ffs((int)cand) - 1;
+#else
+      while (!((cand >> f) & 1u)) ++f;
+#endif
+      cand &= cand - 1;
+      const int p = f >> 1;
+      const double sg = (f & 1) ? 1.0 : -1.0;
+      double cD[3], c1[3], c2[3], N0[3], N1[3], N2[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        cD[i] = sel3(p, g12[i], g23[i], g13[i]) + sg * g123[i];
+        c1[i] = sel3(p, g1[i], g2[i], g1[i]) + sg * sel3(p, g13[i], g12[i], g12[i]);
+        c2[i] = sel3(p, g2[i], g3[i], g3[i]) + sg * sel3(p, g23[i], g13[i], g23[i]);
+      }
+      cross3(c1, c2, N0);
+      cross3(c1, cD, N1);
+      cross3(cD, c2, N2);
+      double area = 0.0;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double qi = i ? t : -t, qj = j ? t : -t;
+          const double vx = N0[0] + qi * N1[0] + qj * N2[0];
+          const double vy = N0[1] + qi * N1[1] + qj * N2[1];
+          const double vz = N0[2] + qi * N1[2] + qj * N2[2];
+          area += sqrt(vx * vx + vy * vy + vz * vz);
+        }
+      best = area > best ? area : best;
+    }
+  }
+  return best * (1.0 / 64.0);
+}
 // returns V / A_max (CalculateCharacteristicLength_C3D8.cpp:3-30)
 FTB_HD double hex_char_length(const double xm[7][3]) {
   const double* g1 = xm[0]; const double* g2 = xm[1]; const double* g3 = xm[2];
@@ -590,6 +704,7 @@ FTB_HD int hex8_element_in(const In& in, int mat, const double* __restrict__ mp,
                            const Out& out, Scratch& S, double fe[8][3], double* dtElem) {
   if (MATSEL >= 0) mat = MATSEL;
   const double a = FTB_GP_A, a2 = FTB_GP_A * FTB_GP_A;
+  double dtk = 0.0;  // 1 / (512 A_max c_e)
   {
     // One space component at a time keeps the live set small: 8+8 nodal values -> 7+7 modes ->
     // 24 column entries written to the scratch; only the 21 current-configuration modes (for the
@@ -617,9 +732,13 @@ FTB_HD int hex8_element_in(const In& in, int mat, const double* __restrict__ mp,
       col_butterfly(S, 1, 1, c, gU[1], U12, U23, U123);
       col_butterfly(S, 1, 2, c, gU[2], U13, U23, U123);
     }
-    if (WITH_DT) *dtElem = hex_char_length(xm) / mp[MP_CE];  // CalculateTimeStep.cpp:19
+    // CalculateTimeStep.cpp:19: dt = (V / A_max) / c_e.  The current volume is not taken from volumeHexahedron's four
+    // triple products (Geometry.cpp:3-27) but from the Gauss loop below: V = sum_gp det F det J0, exact for the trilinear
+    // hexahedron (2 x 2 x 2 points integrate the triquadratic Jacobian exactly) and free: det F is needed anyway.
+    if (WITH_DT) dtk = 1.0 / (512.0 * hex_face_amax(xm) * mp[MP_CE]);
   }
   int status = 0;
+  double vsum = 0.0;
   double phi[7][3];
 #pragma unroll
   for (int m = 0; m < 7; ++m)
@@ -667,6 +786,7 @@ FTB_HD int hex8_element_in(const In& in, int mat, const double* __restrict__ mp,
     cofactor3(F, cF);
     const double J = F[0][0] * cF[0][0] + F[0][1] * cF[0][1] + F[0][2] * cF[0][2];
     if (!(J > 0.0) && mat != 0) status |= 4;
+    if (WITH_DT) vsum = fma(J, det, vsum);  // 512 x the current volume of this point's octant
     double P[3][3], Sv[6];
     GpHistory h;
     if (mat == 5) hist.load(gp, h);
@@ -688,6 +808,7 @@ FTB_HD int hex8_element_in(const In& in, int mat, const double* __restrict__ mp,
       phi[6][i] = fma(s23, Q0, fma(s13, Q1, fma(s12, Q2, phi[6][i])));
     }
   }
+  if (WITH_DT) *dtElem = vsum * dtk;
   // scale: 1/8 (dN/dxi) * 1/64 (cofactor of 8 J0); bilinear modes carry a, trilinear a^2
   const double w0 = 1.0 / 512.0, w1 = a / 512.0, w2 = a2 / 512.0;
 #pragma unroll
@@ -758,6 +879,7 @@ FTB_HD int hex8_element_affine_in(const In& in, int mat, const double* __restric
   if (MATSEL >= 0) mat = MATSEL;
   const double a = FTB_GP_A, a2 = FTB_GP_A * FTB_GP_A;
   int status = 0;
+  double dtk = 0.0;
   {
     double xm[7][3];
     double J0[3][3];  // 8 dX/dxi = 4 x edge vectors (exact scaling)
@@ -799,8 +921,10 @@ FTB_HD int hex8_element_affine_in(const In& in, int mat, const double* __restric
         S.st(FTB_ACJ(j, c), cJ[j][c]);
         S.st(FTB_AJI(c, j), cJ[j][c] * rdet);  // J0^-1[c][j] = cof[j][c] / det
       }
-    if (WITH_DT) *dtElem = hex_char_length(xm) / mp[MP_CE];
+    // dt = (V / A_max) / c_e with V = det J0 sum_gp det F (see hex8_element_in); det here is 512 det J0
+    if (WITH_DT) dtk = det / (512.0 * hex_face_amax(xm) * mp[MP_CE]);
   }
+  double vsum = 0.0;
   double phi[7][3];
 #pragma unroll
   for (int m = 0; m < 7; ++m)
@@ -833,6 +957,7 @@ FTB_HD int hex8_element_affine_in(const In& in, int mat, const double* __restric
     cofactor3(F, cF);
     const double J = F[0][0] * cF[0][0] + F[0][1] * cF[0][1] + F[0][2] * cF[0][2];
     if (!(J > 0.0) && mat != 0) status |= 4;
+    if (WITH_DT) vsum += J;
     double P[3][3], Sv[6];
     GpHistory h;
     if (mat == 5) hist.load(gp, h);
@@ -858,6 +983,7 @@ FTB_HD int hex8_element_affine_in(const In& in, int mat, const double* __restric
       phi[6][i] = fma(s23, Q0, fma(s13, Q1, fma(s12, Q2, phi[6][i])));
     }
   }
+  if (WITH_DT) *dtElem = vsum * dtk;
   const double w0 = 1.0 / 512.0, w1 = a / 512.0, w2 = a2 / 512.0;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {

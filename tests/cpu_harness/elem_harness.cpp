@@ -104,6 +104,19 @@ extern "C" int harness_element_affine_staged(const double* X24, const double* U2
   return st;
 }
 
+// largest face area of a hexahedron given the 8 CURRENT nodal positions: the filtered form the kernels use and the
+// every-face form it replaces
+extern "C" void harness_face_amax(const double* x24, double* out2) {
+  double xm[7][3], n[8], g[7];
+  for (int c = 0; c < 3; ++c) {
+    for (int k = 0; k < 8; ++k) n[k] = x24[3 * k + c];
+    ftb::hex_modes(n, g);
+    for (int m = 0; m < 7; ++m) xm[m][c] = g[m];
+  }
+  out2[0] = ftb::hex_face_amax(xm);
+  out2[1] = ftb::hex_face_amax_all(xm);
+}
+
 // CalculateMaximumPrincipalStrain of one element: out = max, min, shear, then the 6 sums of F^T F
 extern "C" void harness_principal(const double* X24, const double* U24, double* out9) {
   double X[8][3], U[8][3], fe[8][3], d;

@@ -32,6 +32,7 @@ def harness():
     L.harness_element_affine.restype = C.c_int
     L.harness_element_affine_staged.argtypes = L.harness_element.argtypes
     L.harness_element_affine_staged.restype = C.c_int
+    L.harness_face_amax.argtypes = [_dp, _dp]
     L.harness_mass.argtypes = [_dp, C.c_double, _dp]
     L.harness_mass.restype = C.c_double
     L.harness_principal.argtypes = [_dp, _dp, _dp]
@@ -328,3 +329,25 @@ def test_affine_hexahedron_path_equals_general_path(harness, mat):
             assert np.abs(ha - h0).max() > 0
     Xj = X + 1e-9 * rng.standard_normal((8, 3))
     assert _call_elem(harness.harness_element_affine, Xj, U, mat, mp, h0.copy())[0] == -1
+
+
+def test_filtered_face_maximum_equals_every_face_maximum(harness):
+    """hex_face_amax (bounds first, square roots only for the faces that can be the largest) against hex_face_amax_all
+    (every face integrated, the form pinned to the oracle above) on random hexahedra: regular, mildly and strongly
+    distorted, tiny (all faces below the reference's 1e-6 threshold) and with near-tied faces."""
+    rng = np.random.default_rng(11)
+    base = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    out = np.zeros(2)
+    worst = 0.0
+    for trial in range(4000):
+        h = 10.0 ** rng.uniform(-6.5, -1.0)                     # element size: around and far above the 1e-6 test
+        aspect = np.where(rng.random(3) < 0.3, 1.0, rng.uniform(0.5, 2.0, 3))  # cubes (near-tied faces) and bricks
+        jit = rng.choice([0.0, 1e-9, 1e-3, 0.05, 0.25])
+        X = (base * aspect + jit * rng.uniform(-1, 1, (8, 3))) * h
+        X = X @ np.linalg.qr(rng.standard_normal((3, 3)))[0].T if rng.random() < 0.5 else X
+        X = X + rng.uniform(-1, 1, 3) * h
+        Xc = np.ascontiguousarray(X).reshape(-1)
+        harness.harness_face_amax(Xc.ctypes.data_as(_dp), out.ctypes.data_as(_dp))
+        assert out[1] > 0
+        worst = max(worst, abs(out[0] - out[1]) / out[1])
+    assert worst <= 1e-13
