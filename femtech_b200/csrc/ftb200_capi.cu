@@ -55,6 +55,7 @@ struct ftb200_ctx {
   double* ring_host = nullptr;   // step ring (ftb200_step_ring): mapped pinned host memory, its device alias, records
   double* ring_dev = nullptr;
   long long ring_cap = 0;
+  bool pdl = false, pdl_now = false;  // programmatic dependent launch of the step's kernels (FTB200_PDL), see launch_k
   int pf_dist = 0;         // L2 prefetch distance of the element kernels in elements (elem_prefetch_begin); FTB200_PREFETCH_WAVES
   bool use_affine = true;  // FTB200_AFFINE=0: parallelepiped hexahedra go through the general kernel too
   long long nE_affine = 0;
@@ -170,11 +171,28 @@ int fail(ftb200_ctx* c, int code, const char* fmt, ...) {
                   cudaGetErrorString(e_), __FILE__, __LINE__);                                          \
   } while (0)
 
-#define LAUNCH(kern, grid, block, strm, ...)            \
-  do {                                                  \
-    auto kfn_ = kern;                                   \
-    kfn_<<<(grid), (block), 0, (strm)>>>(__VA_ARGS__);  \
-    ctx->launches++;                                    \
+// Every kernel goes through launch_k.  While ctx->pdl_now is set (launch_step, standard single-partition step with
+// FTB200_PDL=1) the launch carries the programmatic-stream-serialization attribute: the kernel may become resident while
+// its predecessor in the stream drains and synchronises itself with pdl_wait() (ftb200_kernels.cuh).
+template <class... P, class... A>
+inline void launch_k(ftb200_ctx* ctx, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t strm, A&&... args) {
+  if (ctx->pdl_now) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = strm;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+  } else {
+    kern<<<grid, block, smem, strm>>>(static_cast<P>(args)...);
+  }
+  ctx->launches++;
+}
+#define LAUNCH(kern, grid, block, strm, ...)                                              \
+  do {                                                                                    \
+    auto kfn_ = kern;                                                                     \
+    launch_k(ctx, kfn_, dim3(grid), dim3(block), (size_t)0, (strm), __VA_ARGS__);         \
   } while (0)
 
 // material-5 element kernels: the two-stage history buffer is dynamic shared memory beyond the 48 KB static limit
@@ -186,8 +204,7 @@ int fail(ftb200_ctx* c, int code, const char* fmt, ...) {
       cudaFuncSetAttribute(kfn_, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_STAGE_BYTES);         \
       attr_set_ = true;                                                                                  \
     }                                                                                                    \
-    kfn_<<<(grid), (block), HIST_STAGE_BYTES, (strm)>>>(__VA_ARGS__);                                    \
-    ctx->launches++;                                                                                     \
+    launch_k(ctx, kfn_, dim3(grid), dim3(block), (size_t)HIST_STAGE_BYTES, (strm), __VA_ARGS__);         \
   } while (0)
 
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
@@ -407,6 +424,10 @@ void launch_step(ftb200_ctx* ctx, const double* recv) {
   if (overlap_now(ctx, recv)) { launch_step_overlap(ctx); return; }
   cudaStream_t s = ctx->stream;
   size_t i0 = 0, i1 = 0;
+  // element kernel, k_adv and the node kernel chained by programmatic dependent launches (hexahedra only: k_elem_tet
+  // and the rigid-body / injury kernels have no pdl_wait)
+  const bool pdl = ctx->pdl && !recv && ctx->nranks == 1 && !ctx->rigid && !ctx->injury && !ctx->fuse_adv && !ctx->has_tet && !ctx->profile;
+  ctx->pdl_now = pdl;
   if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
   launch_elem<true, true>(ctx, s, 0, ctx->nE, 0);
   if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.elem.push_back({i0, i1}); }
@@ -426,6 +447,7 @@ void launch_step(ftb200_ctx* ctx, const double* recv) {
     else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   }
   if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.node.push_back({i0, i1}); }
+  ctx->pdl_now = false;
   if (ctx->energy && !adv_fused) {
     if (en_async) {  // K8 of this step overlaps K1 of the next one; joined before the next k_adv / at the end of the run
       cudaEventRecord(ctx->ev_nodes_done, s);
@@ -1089,6 +1111,7 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       }
     }
     {
+      if (const char* ev = getenv("FTB200_PDL")) ctx->pdl = atoi(ev) != 0;
       // element kernels: optional L2 prefetch for the blocks `waves` waves ahead (a wave = SMs x 8 resident 64-element
       // blocks).  Measured at 100^3 for 1-4 waves: no gain (k_elem_affine 170 -> 172 us, general kernel unchanged), so
       // the exposed part of the prologue is not DRAM latency of first-touch lines; off unless asked for.
@@ -1445,7 +1468,8 @@ static void join_energy(ftb200_ctx* ctx) {
 
 static int build_graph(ftb200_ctx* ctx) {
   const int sig = ctx->energy | (ctx->has_fe ? 2 : 0) | (overlap_now(ctx, nullptr) ? 4 : 0) | (ctx->energy_async ? 8 : 0) |
-                  (ctx->fuse_adv ? 16 : 0) | (ctx->node_ell ? 32 : 0) | (ctx->injury ? 64 : 0) | (ctx->rigid ? 128 : 0);
+                  (ctx->fuse_adv ? 16 : 0) | (ctx->node_ell ? 32 : 0) | (ctx->injury ? 64 : 0) | (ctx->rigid ? 128 : 0) |
+                  (ctx->pdl ? 256 : 0);
   if (ctx->graph && ctx->graph_energy == sig) return 0;
   if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
   cudaGraph_t g = nullptr;

@@ -75,6 +75,15 @@ __device__ __forceinline__ unsigned long long dt_to_bits(double v) {
   return (unsigned long long)__double_as_longlong(v);
 }
 
+// Programmatic dependent launch (opt-in on the host side, FTB200_PDL): a kernel launched with the stream-serialization
+// attribute may become resident while the kernel before it drains.  pdl_wait() blocks until every kernel this one depends
+// on has completed and its writes are visible; pdl_trigger() lets the NEXT kernel of the stream start launching once all
+// blocks of this grid have executed it.  Both are no-ops in an ordinary launch.  Rule kept by every kernel of the step:
+// before pdl_wait() only data that no kernel of the current step writes is read (connectivity; the node state written by
+// the previous step's node kernel, which has completed by the time this step's element blocks have all passed their wait).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Prony history layout: tiles of 32 consecutive elements x 144 values (3 arrays x 6 components x 8 Gauss points): one
 // contiguous 36 KB block per tile.  A warp of the thread-per-element kernels still reads 32 consecutive doubles per
 // value, but all 144 values of an element now sit in one tile (plane-major [144][E] put them 8 MB apart: one TLB entry
@@ -295,6 +304,8 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
     p = __ldg(A.pid + e);                       // with the connectivity: the parameter block is a dependent load too
     if (WITH_DT) skip = __ldg(A.eflag + e);     // element skipped by StableTimeStep (:13-19); not a late, exposed load
   }
+  pdl_wait();     // the node kernel of the previous step (u) and its scalars
+  pdl_trigger();  // k_adv may become resident; it waits for this grid itself
   if (!A.ignore_loop_flags && (A.sc->last | A.sc->done)) return;
   const int pfn = (WITH_FORCE && WITH_DT) ? elem_prefetch_begin(A, e) : -1;
   __shared__ double sm_cols[WITH_FORCE ? 72 : 1][ELEM_BLOCK];
@@ -465,6 +476,8 @@ __global__ void __launch_bounds__(ELEM_BLOCK, MATSEL == 5 ? 4 : (WITH_INJ ? FTB_
     p = __ldg(A.pid + e);
     skip = __ldg(A.eflag + e);
   }
+  pdl_wait();
+  pdl_trigger();
   if (!A.ignore_loop_flags && (A.sc->last | A.sc->done)) return;
   const int pfn = elem_prefetch_begin(A, e);
   __shared__ double sm_cols[FTB_AFFINE_SLOTS][ELEM_BLOCK];
@@ -753,6 +766,28 @@ __device__ __forceinline__ void prony_update(double* mp, int nPID, double dt, in
 template <bool FINISH, bool START, bool KICK2, bool ENERGY, bool ADV = false>
 __global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node(const NodeArgs A) {
   DevScalars* sc = A.sc;
+  const int n = blockIdx.x * NODE_BLOCK + threadIdx.x;
+  // Preamble: the node's own state (last written by the previous node kernel) and its entries of the static node ->
+  // element map.  Nothing here is written by the element kernel or k_adv of the current step, so under a programmatic
+  // dependent launch these loads are in flight while those two finish.
+  unsigned fl = 0;
+  double uu[3] = {0.0, 0.0, 0.0}, vv[3] = {0.0, 0.0, 0.0}, aa[3] = {0.0, 0.0, 0.0};
+  int ent[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+  if (n < A.nN) {
+    fl = A.flags[n];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      uu[c] = A.u[c][n];
+      vv[c] = A.v[c][n];
+      aa[c] = A.a[c][n];
+    }
+    if (FINISH && A.ell) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) ent[q] = __ldg(A.ell + (size_t)q * A.nN + n);
+    }
+  }
+  pdl_trigger();  // the next element kernel reads only the connectivity before its own wait
+  pdl_wait();
   double c_tn, c_tnp1, c_thalf;            // step being finished
   double n_tn, n_tnp1, n_thalf, n_dt;      // next step
   bool last_new;
@@ -779,17 +814,8 @@ __global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node(const N
     last_new = sc->last != 0;
   }
   const bool do_start = START && !(FINISH && last_new);
-  const int n = blockIdx.x * NODE_BLOCK + threadIdx.x;
   double wke = 0.0, wint = 0.0, wext = 0.0;
   if (n < A.nN) {
-    const unsigned fl = A.flags[n];
-    double uu[3], vv[3], aa[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      uu[c] = A.u[c][n];
-      vv[c] = A.v[c][n];
-      aa[c] = A.a[c][n];
-    }
     if (FINISH) {
       // deterministic assembly: ascending element id (GetForce_3D.cpp:15,39-44)
       double f[3] = {0.0, 0.0, 0.0};
@@ -797,9 +823,7 @@ __global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node(const N
       if (A.ell) {
         // fixed-width map [8][nN] (-1 = no entry): the 8 entries and then all 24 force loads are issued before the
         // first add, instead of a dependent load per trip of a variable-length loop; same ascending order
-        int ent[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) ent[q] = __ldg(A.ell + (size_t)q * A.nN + n);
+        // (the 8 entries were loaded in the preamble)
         double fv[8][3];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -1208,6 +1232,8 @@ template <bool INIT>
 __global__ void k_adv(DevScalars* sc, double* mp, int nPID, double Time0, double* dt_hist) {
   __shared__ double s_ndt;
   __shared__ int s_live;
+  pdl_trigger();  // the node kernel may load its (older) node state while the element kernel drains
+  pdl_wait();
   if (threadIdx.x == 0) {
     int live = 1;
     if (!INIT) {
