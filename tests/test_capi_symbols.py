@@ -69,3 +69,18 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in txt and "femtech_oracle" not in txt and "oracle/" not in txt, f
+
+
+def test_entry_points_reject_a_null_context(lib_path):
+    """Argument checks of the C-ABI run before any CUDA call: a NULL context is refused with the reference's bad-input
+    code (3) -- or the documented sentinel -- not a crash.  (No GPU needed; nothing is computed.)"""
+    from femtech_b200 import _lib
+    L = _lib.load()
+    ring = C.POINTER(C.c_double)()
+    assert L.ftb200_step_ring(None, 16, C.byref(ring)) == 3
+    assert L.ftb200_affine_element_count(None) == -1
+    assert L.ftb200_explicit_run_async(None, 1.0, 10) == 3
+    assert L.ftb200_explicit_poll(None, None, None, None, None) == 3
+    assert L.ftb200_shape_functions(None, None) == 3
+    assert L.ftb200_launch_count(None) == 0
+    assert b"null context" in L.ftb200_last_error(None)
