@@ -54,7 +54,43 @@ ELEM_FLOPS = {1: 3386.0, 4: 4296.0, 5: 6446.0}
 ELEM_FLOPS_AFFINE = {k: v - 531.0 for k, v in ELEM_FLOPS.items()}
 
 
+def _nvml_sampler(stop, out, device_index):
+    """Fast path: NVML from this process (a sample every ~2 ms, so the 25-60 ms timed regions are covered by several
+    samples).  Returns False if NVML is not usable -- the caller then falls back to polling nvidia-smi."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id of the CUDA device
+        try:
+            import torch
+            bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+            dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+            dev = torch.cuda.get_device_properties(device_index).pci_device_id
+            h = nv.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (dom, bus, dev)).encode())
+        except Exception:
+            h = nv.nvmlDeviceGetHandleByIndex(device_index)
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))  # probe once before committing to this path
+    except Exception:
+        return False
+    while not stop.is_set():
+        try:
+            sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            out.append([str(sm), str(mx)] + [("Active" if r & b else "Not Active") for b in bits.values()])
+        except Exception:
+            pass
+        stop.wait(0.002)
+    return True
+
+
 def clocks_sampler(stop, out, device_index):
+    try:
+        if _nvml_sampler(stop, out, device_index):
+            return
+    except Exception:
+        pass
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     while not stop.is_set():
