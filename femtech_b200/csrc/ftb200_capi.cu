@@ -46,17 +46,9 @@ struct ftb200_ctx {
   int nEb_hex = 0, nEi_hex = 0;   // hexahedra among the boundary / interior elements (they come first in each class)
   struct ElemRange { int e0, e1, tet, mat, affine; };
   std::vector<ElemRange> ranges;  // internal element order = runs of equal (class, element type, material, affine geometry)
-  // overlapped step (k_node_ovl beside the element kernel), see launch_step_overlap
-  bool overlap = false;            // chosen in shape_functions: FTB200_OVERLAP and a mesh that qualifies
-  unsigned *d_ovl_ctr = nullptr, *d_ovl_target = nullptr;
-  unsigned short *d_ovl_lo = nullptr, *d_ovl_hi = nullptr;
-  int ovl_chunks = 0, ovl_grid = 0, ovl_elem_dyn = 0;
-  cudaEvent_t ev_ovl_reset = nullptr, ev_ovl_n1 = nullptr;
   double* ring_host = nullptr;   // step ring (ftb200_step_ring): mapped pinned host memory, its device alias, records
   double* ring_dev = nullptr;
   long long ring_cap = 0;
-  bool pdl = false, pdl_now = false;  // programmatic dependent launch of the step's kernels (FTB200_PDL), see launch_k
-  int pf_dist = 0;         // L2 prefetch distance of the element kernels in elements (elem_prefetch_begin); FTB200_PREFETCH_WAVES
   bool use_affine = true;  // FTB200_AFFINE=0: parallelepiped hexahedra go through the general kernel too
   long long nE_affine = 0;
   // rigid-body prescribed motion (ftb200_set_rigid_bc)
@@ -81,33 +73,10 @@ struct ftb200_ctx {
   int *conn = nullptr, *pid = nullptr, *ref_of = nullptr;
   int *d_nref = nullptr, *d_nint = nullptr;  // internal node -> caller's id (-1 = padding) and back
   std::vector<int> h_nint;
-  // pipelined loop
-  PipeCtl* d_ctl = nullptr;
-  uint8_t *d_etile_chunk = nullptr, *d_ntile_group = nullptr;
-  int* d_ell = nullptr;
-  // fused step kernel
-  StepCtl* d_sctl = nullptr;
-  uint8_t *d_etile32 = nullptr, *d_ntile32 = nullptr;
-  double *d_etile_e = nullptr, *d_eblock = nullptr;
-  int nTilesE32 = 0, nTilesN32 = 0, fused_grid = 0;
-  bool fused = false;  // opt-in (FTB200_FUSED=1): measured slower than the two-kernel step, DESIGN.md §3.6
-  cudaEvent_t ev_step = nullptr, ev_energy[2] = {nullptr, nullptr};
+  int* d_ell = nullptr;  // fixed-width node -> (element, slot) map [8][nNp]
   // single-partition step: the energy reduction of step n runs on the helper stream under the element kernel of n + 1
   cudaEvent_t ev_nodes_done = nullptr, ev_energy_done = nullptr;
   bool energy_async = true, energy_pending = false, energy_async_now = true;  // _now: off for single-step calls (nothing to overlap)
-  cudaGraphExec_t fgraph = nullptr;
-  int fgraph_energy = -1;
-  double* d_etile = nullptr;
-  int nTilesE = 0, nTilesN = 0, nChunks = 0;
-  int elem_grid = 0, node_grid = 0;
-  bool pipe = false;
-  bool node_ell = true;   // k_node gathers through the fixed-width map (FTB200_NODE_ELL=0: CSR loop)
-  bool fuse_adv = false;  // opt-in FTB200_FUSE_ADV=1: k_adv + k_energy folded into k_node's last block.  Measured slower
-                          // (k_node 98 -> 115 us at 100^3: every block pays a fence + atomic round trip) than the two
-                          // tiny kernels it saves (14 us), so the four-launch step stays the default.
-  cudaEvent_t ev_elem[2] = {nullptr, nullptr};
-  cudaGraphExec_t pgraph = nullptr;
-  int pgraph_energy = -1;
   uint8_t* eflag = nullptr;
   double *felem = nullptr, *hist = nullptr, *mp = nullptr;
   int *node_off = nullptr, *node_ent = nullptr;
@@ -171,22 +140,10 @@ int fail(ftb200_ctx* c, int code, const char* fmt, ...) {
                   cudaGetErrorString(e_), __FILE__, __LINE__);                                          \
   } while (0)
 
-// Every kernel goes through launch_k.  While ctx->pdl_now is set (launch_step, standard single-partition step with
-// FTB200_PDL=1) the launch carries the programmatic-stream-serialization attribute: the kernel may become resident while
-// its predecessor in the stream drains and synchronises itself with pdl_wait() (ftb200_kernels.cuh).
+// Every kernel goes through launch_k (it counts the launches: `gpu_launches` of the bench line).
 template <class... P, class... A>
 inline void launch_k(ftb200_ctx* ctx, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t strm, A&&... args) {
-  if (ctx->pdl_now) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = strm;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
-  } else {
-    kern<<<grid, block, smem, strm>>>(static_cast<P>(args)...);
-  }
+  kern<<<grid, block, smem, strm>>>(static_cast<P>(args)...);
   ctx->launches++;
 }
 #define LAUNCH(kern, grid, block, strm, ...)                                              \
@@ -199,15 +156,19 @@ inline void launch_k(ftb200_ctx* ctx, void (*kern)(P...), dim3 grid, dim3 block,
 #define LAUNCH_HIST(kern, grid, block, strm, ...)                                                        \
   do {                                                                                                   \
     auto kfn_ = kern;                                                                                    \
-    static bool attr_set_ = false;                                                                       \
-    if (!attr_set_) {                                                                                    \
-      cudaFuncSetAttribute(kfn_, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_STAGE_BYTES);         \
-      attr_set_ = true;                                                                                  \
-    }                                                                                                    \
+    /* the attribute is per device: a process may hold contexts on several GPUs, so no process-wide cache */ \
+    cudaFuncSetAttribute(kfn_, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_STAGE_BYTES);           \
     launch_k(ctx, kfn_, dim3(grid), dim3(block), (size_t)HIST_STAGE_BYTES, (strm), __VA_ARGS__);         \
   } while (0)
 
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+// The captured step graphs bake device pointers and flags into their kernel arguments: whoever reallocates one of those
+// arrays (history, external force, injury, rigid-body state) or flips such a flag drops them; the next run rebuilds.
+void drop_graphs(ftb200_ctx* ctx) {
+  if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+  if (ctx->p2p_graph) { cudaGraphExecDestroy(ctx->p2p_graph); ctx->p2p_graph = nullptr; }
+}
 
 template <class T>
 int dalloc(ftb200_ctx* ctx, T** p, size_t n) {
@@ -234,8 +195,6 @@ ElemArgs elem_args(ftb200_ctx* c, int e0, int e1, int ignore) {
   for (int k = 0; k < 3; ++k) { A.X[k] = c->X[k]; A.u[k] = c->u[k]; }
   A.conn = c->conn; A.pid = c->pid; A.eflag = c->eflag; A.mp = c->mp; A.felem = c->felem; A.hist = c->hist;
   A.sc = c->sc; A.nE = c->nE; A.e0 = e0; A.e1 = e1; A.ignore_loop_flags = ignore;
-  A.pf_dist = c->pf_dist;
-  A.ovl_ctr = nullptr;
   A.etype = c->etype;
   A.inj_ps = c->inj_ps; A.inj_psxsr = c->inj_psxsr; A.inj_smin = c->inj_smin; A.inj_shear = c->inj_shear;
   A.inj_flags = c->inj_flags; A.inj_incl = c->inj_incl;
@@ -254,10 +213,9 @@ NodeArgs node_args(ftb200_ctx* c, const double* recv) {
   A.halo_node_idx = recv ? c->halo_node_idx : nullptr;
   A.epart = c->epart; A.sc = c->sc; A.nN = c->nNp; A.nE = c->nE;
   A.store_fi = c->energy ? 1 : 0;
-  A.dt_hist = c->dthist; A.ehist = c->ehist; A.mp_rw = c->mp; A.nPID = c->nPID;
   for (int k = 0; k < 3; ++k) { A.X[k] = c->X[k]; A.aprev[k] = c->aprev[k]; }
   A.rigid = c->rigid;
-  A.ell = c->node_ell ? c->d_ell : nullptr;
+  A.ell = c->d_ell;
   A.halo_recv_alt = nullptr;
   A.p2p_seq = nullptr;
   return A;
@@ -354,101 +312,24 @@ void launch_injury(ftb200_ctx* ctx, cudaStream_t s) {
   LAUNCH(k_injury_lists, cdiv(ctx->nE, 256), 256, s, A, ctx->inj_state);
 }
 
-// ---- overlapped step: element kernel (fp64 pipe) on the main stream with one block per SM less than it
-//      could hold; k_node_ovl (HBM) on the helper stream takes the freed slot and follows it chunk by chunk; then the scalar
-//      update and the START half of the node kernel.  Single partition, one uniform run of hexahedra of material 1 or 4.
-bool overlap_now(const ftb200_ctx* ctx, const double* recv) {
-  return ctx->overlap && !recv && ctx->nranks == 1 && !ctx->rigid && !ctx->injury && !ctx->fuse_adv && ctx->node_ell;
-}
-void launch_elem_overlap(ftb200_ctx* ctx, cudaStream_t s) {
-  const auto& r = ctx->ranges[0];
-  ElemArgs A = elem_args(ctx, 0, ctx->nE, 0);
-  A.ovl_ctr = ctx->d_ovl_ctr;
-  const int grid = cdiv(ctx->nE, ELEM_BLOCK);
-  const size_t dyn = (size_t)ctx->ovl_elem_dyn;  // unused bytes: they only cap the resident blocks per SM
-#define LAUNCH_OVL(kern)                          \
-  do {                                            \
-    auto kfn_ = kern;                             \
-    kfn_<<<grid, ELEM_BLOCK, dyn, s>>>(A);        \
-    ctx->launches++;                              \
-  } while (0)
-  if (r.affine) {
-    if (r.mat == 1) LAUNCH_OVL((k_elem_affine<1, false>));
-    else LAUNCH_OVL((k_elem_affine<4, false>));
-  } else {
-    if (r.mat == 1) LAUNCH_OVL((k_elem<1, true, true>));
-    else LAUNCH_OVL((k_elem<4, true, true>));
-  }
-#undef LAUNCH_OVL
-}
-void launch_step_overlap(ftb200_ctx* ctx) {
-  cudaStream_t s = ctx->stream, s2 = ctx->stream2;
-  size_t i0 = 0, i1 = 0;
-  cudaMemsetAsync(ctx->d_ovl_ctr, 0, ctx->ovl_chunks * sizeof(unsigned), s);
-  cudaEventRecord(ctx->ev_ovl_reset, s);
-  if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
-  launch_elem_overlap(ctx, s);
-  if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.elem.push_back({i0, i1}); }
-  cudaStreamWaitEvent(s2, ctx->ev_ovl_reset, 0);
-  OvlArgs P;
-  P.N = node_args(ctx, nullptr);
-  P.ctr = ctx->d_ovl_ctr; P.target = ctx->d_ovl_target; P.lo = ctx->d_ovl_lo; P.hi = ctx->d_ovl_hi; P.nTiles = ctx->node_blocks;
-  if (ctx->energy) LAUNCH((k_node_ovl<true>), ctx->ovl_grid, NODE_BLOCK, s2, P);
-  else LAUNCH((k_node_ovl<false>), ctx->ovl_grid, NODE_BLOCK, s2, P);
-  cudaEventRecord(ctx->ev_ovl_n1, s2);
-  // k_adv moves the step times k_node_ovl reads and the scalars the previous step's energy reduction reads: after both
-  if (ctx->energy_pending) { cudaStreamWaitEvent(s, ctx->ev_energy_done, 0); ctx->energy_pending = false; }
-  cudaStreamWaitEvent(s, ctx->ev_ovl_n1, 0);
-  LAUNCH((k_adv<false>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, 0.0, ctx->dthist);
-  if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
-  const NodeArgs N = node_args(ctx, nullptr);
-  if (ctx->energy) LAUNCH((k_node<false, true, false, true>), ctx->node_blocks, NODE_BLOCK, s, N);
-  else LAUNCH((k_node<false, true, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
-  if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.node.push_back({i0, i1}); }
-  if (ctx->energy) {
-    const bool en_async = ctx->energy_async && ctx->energy_async_now && !ctx->profile;
-    if (en_async) {
-      cudaEventRecord(ctx->ev_nodes_done, s);
-      cudaStreamWaitEvent(s2, ctx->ev_nodes_done, 0);
-      LAUNCH(k_energy, 1, 256, s2, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
-      cudaEventRecord(ctx->ev_energy_done, s2);
-      ctx->energy_pending = true;
-    } else {
-      LAUNCH(k_energy, 1, 256, s, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
-    }
-  }
-}
-
 // one loop iteration: K_elem -> K_adv -> K_node (-> K_energy) (-> injury criteria)
 void launch_step(ftb200_ctx* ctx, const double* recv) {
-  if (overlap_now(ctx, recv)) { launch_step_overlap(ctx); return; }
   cudaStream_t s = ctx->stream;
   size_t i0 = 0, i1 = 0;
-  // element kernel, k_adv and the node kernel chained by programmatic dependent launches (hexahedra only: k_elem_tet
-  // and the rigid-body / injury kernels have no pdl_wait)
-  const bool pdl = ctx->pdl && !recv && ctx->nranks == 1 && !ctx->rigid && !ctx->injury && !ctx->fuse_adv && !ctx->has_tet && !ctx->profile;
-  ctx->pdl_now = pdl;
   if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
   launch_elem<true, true>(ctx, s, 0, ctx->nE, 0);
   if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.elem.push_back({i0, i1}); }
   const NodeArgs N = node_args(ctx, recv);
-  const bool adv_fused = ctx->nranks == 1 && !recv && ctx->fuse_adv && !ctx->rigid;
-  const bool en_async = ctx->energy && ctx->energy_async && ctx->energy_async_now && ctx->nranks == 1 && !recv && !adv_fused && !ctx->profile;
+  const bool en_async = ctx->energy && ctx->energy_async && ctx->energy_async_now && ctx->nranks == 1 && !recv && !ctx->profile;
   // k_adv moves sc->step / sc->active, which the energy reduction of the previous step (helper stream) still reads
   if (ctx->energy_pending) { cudaStreamWaitEvent(s, ctx->ev_energy_done, 0); ctx->energy_pending = false; }
-  if (!adv_fused) LAUNCH((k_adv<false>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, 0.0, ctx->dthist);
+  LAUNCH((k_adv<false>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, 0.0, ctx->dthist);
   if (ctx->rigid) LAUNCH(k_rigid_step, 1, 32, s, ctx->sc, ctx->rigid, 0);
   if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
-  if (adv_fused) {
-    if (ctx->energy) LAUNCH((k_node<true, true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
-    else LAUNCH((k_node<true, true, true, false, true>), ctx->node_blocks, NODE_BLOCK, s, N);
-  } else {
-    if (ctx->energy) LAUNCH((k_node<true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
-    else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
-  }
+  if (ctx->energy) LAUNCH((k_node<true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
+  else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.node.push_back({i0, i1}); }
-  ctx->pdl_now = false;
-  if (ctx->energy && !adv_fused) {
+  if (ctx->energy) {
     if (en_async) {  // K8 of this step overlaps K1 of the next one; joined before the next k_adv / at the end of the run
       cudaEventRecord(ctx->ev_nodes_done, s);
       cudaStreamWaitEvent(ctx->stream2, ctx->ev_nodes_done, 0);
@@ -460,40 +341,6 @@ void launch_step(ftb200_ctx* ctx, const double* recv) {
     }
   }
   if (ctx->injury) launch_injury(ctx, s);
-}
-
-// ---- pipelined loop: k_elem_pipe on the main stream, k_node_pipe on the second (high priority) stream
-void launch_pipe_pair(ftb200_ctx* ctx, int i) {
-  cudaStream_t s1 = ctx->stream, s2 = ctx->stream2;
-  PipeElemArgs PE;
-  PE.E = elem_args(ctx, 0, ctx->nE, 0);
-  for (int k = 0; k < 3; ++k) { PE.v[k] = ctx->v[k]; PE.a[k] = ctx->a[k]; }
-  PE.flags = ctx->flags; PE.tile_chunk = ctx->d_etile_chunk; PE.ctl = ctx->d_ctl; PE.dt_hist = ctx->dthist; PE.nPID = ctx->nPID;
-  PipeNodeArgs PN;
-  PN.N = node_args(ctx, nullptr);
-  PN.ell = ctx->d_ell;
-  PN.tile_group = ctx->d_ntile_group; PN.ctl = ctx->d_ctl; PN.etile = ctx->d_etile; PN.ehist = ctx->ehist; PN.energy = ctx->energy;
-  size_t i0 = 0, i1 = 0;
-  if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s1);
-  switch (ctx->uniform_mat) {
-    case 1: LAUNCH((k_elem_pipe<1>), ctx->elem_grid, ELEM_BLOCK, s1, PE); break;
-    case 4: LAUNCH((k_elem_pipe<4>), ctx->elem_grid, ELEM_BLOCK, s1, PE); break;
-    case 5: LAUNCH((k_elem_pipe<5>), ctx->elem_grid, ELEM_BLOCK, s1, PE); break;
-    default: LAUNCH((k_elem_pipe<-1>), ctx->elem_grid, ELEM_BLOCK, s1, PE); break;
-  }
-  if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s1); ctx->prof.elem.push_back({i0, i1}); }
-  // k_node_pipe(i) may start once k_elem_pipe(i-1) has completely finished (counter recycling)
-  cudaStreamWaitEvent(s2, i == 0 ? ctx->ev_fork : ctx->ev_elem[(i - 1) & 1], 0);
-  if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s2);
-  LAUNCH(k_node_pipe, ctx->node_grid, NODE_TILE, s2, PN);
-  if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s2); ctx->prof.node.push_back({i0, i1}); }
-  cudaEventRecord(ctx->ev_elem[i & 1], s1);
-}
-void launch_pipe_steps(ftb200_ctx* ctx, int nsteps) {
-  cudaEventRecord(ctx->ev_fork, ctx->stream);
-  for (int i = 0; i < nsteps; ++i) launch_pipe_pair(ctx, i);
-  cudaEventRecord(ctx->ev_join, ctx->stream2);
-  cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
 }
 
 void prof_collect(ftb200_ctx* ctx) {
@@ -547,10 +394,8 @@ void free_all(ftb200_ctx* c) {
   dfree(c->p2p_window); dfree(c->d_seq); dfree(c->d_p2p_blocks);
   c->p2p_ready = false;
   if (c->p2p_graph) { cudaGraphExecDestroy(c->p2p_graph); c->p2p_graph = nullptr; }
-  dfree(c->d_nref); dfree(c->d_nint); dfree(c->d_ctl); dfree(c->d_etile_chunk); dfree(c->d_ntile_group); dfree(c->d_etile); dfree(c->d_ell); dfree(c->d_ovl_ctr); dfree(c->d_ovl_target); dfree(c->d_ovl_lo); dfree(c->d_ovl_hi); dfree(c->d_sctl); dfree(c->d_etile32); dfree(c->d_ntile32); dfree(c->d_etile_e); dfree(c->d_eblock);
+  dfree(c->d_nref); dfree(c->d_nint); dfree(c->d_ell);
   if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
-  if (c->fgraph) { cudaGraphExecDestroy(c->fgraph); c->fgraph = nullptr; }
-  if (c->pgraph) { cudaGraphExecDestroy(c->pgraph); c->pgraph = nullptr; }
   dfree(c->d_sendNodeIndex); dfree(c->halo_nodes); dfree(c->halo_off); dfree(c->halo_slot); dfree(c->halo_node_idx);
   if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
 }
@@ -582,15 +427,8 @@ int ftb200_create(int rank, int nranks, int device, ftb200_ctx** out) {
       cudaStreamCreateWithPriority(&ctx->stream_lo, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_elem[0], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_elem[1], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_step, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_nodes_done, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_energy_done, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_ovl_reset, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_ovl_n1, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_energy[0], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_energy[1], cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&ctx->ev_energy_done, cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return FTB200_ERR_CUDA;
   }
@@ -609,15 +447,8 @@ int ftb200_destroy(ftb200_ctx* ctx) {
   if (ctx->stream_lo) cudaStreamDestroy(ctx->stream_lo);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-  for (int i = 0; i < 2; ++i) {
-    if (ctx->ev_elem[i]) cudaEventDestroy(ctx->ev_elem[i]);
-    if (ctx->ev_energy[i]) cudaEventDestroy(ctx->ev_energy[i]);
-  }
-  if (ctx->ev_step) cudaEventDestroy(ctx->ev_step);
   if (ctx->ev_nodes_done) cudaEventDestroy(ctx->ev_nodes_done);
   if (ctx->ev_energy_done) cudaEventDestroy(ctx->ev_energy_done);
-  if (ctx->ev_ovl_reset) cudaEventDestroy(ctx->ev_ovl_reset);
-  if (ctx->ev_ovl_n1) cudaEventDestroy(ctx->ev_ovl_n1);
   if (ctx->ring_host) cudaFreeHost(ctx->ring_host);
   delete ctx;
   return FTB200_OK;
@@ -631,7 +462,6 @@ int ftb200_set_stream(ftb200_ctx* ctx, void* cuda_stream) {
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
-  if (ctx->pgraph) { cudaGraphExecDestroy(ctx->pgraph); ctx->pgraph = nullptr; }
   if (cuda_stream) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cuda_stream;
@@ -791,46 +621,12 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       ref_of[t] = e; int_of[e] = t;
     }
   }
-  // ---- element chunks (runs of 64-element tiles) and node groups for the pipelined loop ----------
-  const int nTilesE = cdiv(nE, ELEM_BLOCK);
-  int C = 32;
-  if (const char* ev = getenv("FTB200_CHUNKS")) C = atoi(ev);
-  C = std::max(1, std::min(std::min(C, PIPE_MAXC), nTilesE));
-  std::vector<uint8_t> etile_chunk(nTilesE);
-  std::vector<unsigned> elem_target(PIPE_MAXC, 0), node_target(PIPE_MAXC, 0), need(PIPE_MAXC, 0);
-  for (int t = 0; t < nTilesE; ++t) {
-    const int c = (int)(((long long)t * C) / nTilesE);
-    etile_chunk[t] = (uint8_t)c;
-    elem_target[c]++;
-  }
-  // node group = largest chunk among the elements of the node (0 for isolated nodes)
-  std::vector<int> ngroup(nN, 0);
-  for (int t = 0; t < nE; ++t) {
-    const int c = etile_chunk[t / ELEM_BLOCK], e = ref_of[t];
-    for (int k = 0; k < 8; ++k) { int& g = ngroup[ctx->h_conn[8 * (size_t)e + k]]; if (c > g) g = c; }
-  }
-  for (int t = 0; t < nE; ++t) {
-    const int c = etile_chunk[t / ELEM_BLOCK], e = ref_of[t];
-    for (int k = 0; k < 8; ++k) { const unsigned g = (unsigned)ngroup[ctx->h_conn[8 * (size_t)e + k]]; if (g > need[c]) need[c] = g; }
-  }
-  // internal node order: by group, caller's id inside a group; every group padded to whole node tiles
-  std::vector<int> gcount(C, 0), gstart(C + 1, 0);
-  for (int n = 0; n < nN; ++n) gcount[ngroup[n]]++;
-  for (int g = 0; g < C; ++g) gstart[g + 1] = gstart[g] + cdiv(gcount[g], NODE_TILE) * NODE_TILE;
-  const int nNp = std::max(gstart[C], NODE_TILE);
+  // ---- internal node order: the caller's order, padded to whole node tiles (brick mode: see build_patches) ------
+  const int nNp = std::max(cdiv(nN, NODE_TILE) * NODE_TILE, NODE_TILE);
   ctx->nNp = nNp;
-  const int nTilesN = nNp / NODE_TILE;
   std::vector<int> nref(nNp, -1), nint(nN, -1);
-  {
-    std::vector<int> cur(gstart.begin(), gstart.end() - 1);
-    for (int n = 0; n < nN; ++n) { const int i = cur[ngroup[n]]++; nref[i] = n; nint[n] = i; }
-  }
-  std::vector<uint8_t> ntile_group(nTilesN, (uint8_t)(C - 1));
-  for (int g = 0; g < C; ++g)
-    for (int t = gstart[g] / NODE_TILE; t < gstart[g + 1] / NODE_TILE; ++t) { ntile_group[t] = (uint8_t)g; node_target[g]++; }
-  if (gstart[C] < nNp) node_target[C - 1] += (nNp - gstart[C]) / NODE_TILE;  // tiny meshes: one padding tile
+  for (int n = 0; n < nN; ++n) { nref[n] = n; nint[n] = n; }
   ctx->h_nint = nint;
-  ctx->nTilesE = nTilesE; ctx->nTilesN = nTilesN; ctx->nChunks = C;
   // ---- shared nodes (internal ids), slots in ascending neighbour order ---------------------------
   std::vector<int> node_h(nNp, -1), halo_nodes, sendIdxInt(ctx->halo_count);
   for (int i = 0; i < ctx->halo_count; ++i) sendIdxInt[i] = nint[ctx->h_sendNodeIndex[i]];
@@ -909,15 +705,12 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       (rc = dalloc(ctx, &ctx->sc, 1)) || (rc = dalloc(ctx, &ctx->epart, 3 * (size_t)std::max(ctx->node_blocks, cdiv(nN, NODE_BLOCK)))) ||
       (rc = dalloc(ctx, &ctx->out3, 16)) || (rc = dalloc(ctx, &ctx->d_istage, 3 * (size_t)nN)) ||
       (rc = dalloc(ctx, &ctx->d_detmin, 1)) || (rc = dalloc(ctx, &ctx->d_nonpos, 1)) ||
-      (rc = dalloc(ctx, &ctx->d_nref, nNp)) || (rc = dalloc(ctx, &ctx->d_nint, nN)) || (rc = dalloc(ctx, &ctx->d_ctl, 1)) ||
-      (rc = dalloc(ctx, &ctx->d_etile_chunk, nTilesE)) || (rc = dalloc(ctx, &ctx->d_ntile_group, nTilesN)) ||
-      (rc = dalloc(ctx, &ctx->d_etile, 3 * (size_t)nTilesN)) || (rc = dalloc(ctx, &ctx->d_ell, 8 * (size_t)nNp)))
+      (rc = dalloc(ctx, &ctx->d_nref, nNp)) || (rc = dalloc(ctx, &ctx->d_nint, nN)) || (rc = dalloc(ctx, &ctx->d_ell, 8 * (size_t)nNp)))
     return rc;
   CK(cudaMemset(ctx->m, 0, nNp * sizeof(double)));
   CK(cudaMemset(ctx->eflag, 0, nE));
   CK(cudaMemset(ctx->felem, 0, 24 * 32 * (size_t)cdiv(nE, 32) * sizeof(double)));  // tiles of 32 elements (FTB_FIDX)
   CK(cudaMemset(ctx->sc, 0, sizeof(DevScalars)));
-  CK(cudaMemset(ctx->d_etile, 0, 3 * (size_t)nTilesN * sizeof(double)));
   CK(cudaMemcpy(ctx->conn, connT.data(), connT.size() * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->pid, pidI.data(), nE * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->ref_of, ref_of.data(), nE * sizeof(int), cudaMemcpyHostToDevice));
@@ -937,8 +730,6 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
   CK(cudaMemcpy(ctx->node_ent, ent.data(), ent.size() * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->d_nref, nref.data(), nNp * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->d_nint, nint.data(), nN * sizeof(int), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->d_etile_chunk, etile_chunk.data(), nTilesE, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->d_ntile_group, ntile_group.data(), nTilesN, cudaMemcpyHostToDevice));
   std::vector<char> overflow(nNp, 0);
   {
     std::vector<int> ell(8 * (size_t)nNp, -1);
@@ -948,54 +739,6 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       if (deg > 8) overflow[i] = 1;
     }
     CK(cudaMemcpy(ctx->d_ell, ell.data(), ell.size() * sizeof(int), cudaMemcpyHostToDevice));
-  }
-  {  // overlapped step: warps per element chunk, and the range of element chunks every 128-node tile gathers from
-    const int nC = cdiv(nE, OVL_CHUNK), nT = cdiv(nNp, NODE_BLOCK);
-    ctx->ovl_chunks = nC;
-    std::vector<unsigned> target(nC);
-    for (int c = 0; c < nC; ++c) target[c] = (unsigned)cdiv(std::min<long long>(nE, (long long)(c + 1) * OVL_CHUNK) - (long long)c * OVL_CHUNK, 32);
-    std::vector<unsigned short> lo(nT, 0xFFFF), hi(nT, 0);
-    for (int i = 0; i < nNp; ++i) {
-      const int t = i / NODE_BLOCK;
-      for (int j = off[i]; j < off[i + 1]; ++j) {
-        const unsigned short c = (unsigned short)((ent[j] >> 3) >> OVL_CHUNK_SHIFT);
-        lo[t] = std::min(lo[t], c); hi[t] = std::max(hi[t], c);
-      }
-    }
-    for (int t = 0; t < nT; ++t)
-      if (lo[t] == 0xFFFF) { lo[t] = 1; hi[t] = 0; }  // a tile of padding nodes waits for nothing
-    if ((rc = dalloc(ctx, &ctx->d_ovl_ctr, nC)) || (rc = dalloc(ctx, &ctx->d_ovl_target, nC)) || (rc = dalloc(ctx, &ctx->d_ovl_lo, nT)) ||
-        (rc = dalloc(ctx, &ctx->d_ovl_hi, nT)))
-      return rc;
-    CK(cudaMemset(ctx->d_ovl_ctr, 0, nC * sizeof(unsigned)));
-    CK(cudaMemcpy(ctx->d_ovl_target, target.data(), nC * sizeof(unsigned), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_ovl_lo, lo.data(), nT * sizeof(unsigned short), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_ovl_hi, hi.data(), nT * sizeof(unsigned short), cudaMemcpyHostToDevice));
-  }
-  {
-    PipeCtl h;
-    memset(&h, 0, sizeof(h));
-    for (int i = 0; i < PIPE_MAXC; ++i) { h.elem_target[i] = elem_target[i]; h.node_target[i] = node_target[i]; h.need[i] = need[i]; }
-    h.C = C; h.nTilesE = nTilesE; h.nTilesN = nTilesN;
-    h.stop_step = 0;
-    CK(cudaMemcpy(ctx->d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice));
-  }
-  {  // fused step kernel: warp-granular (32) tiles over the same chunks / groups
-    const int nTE = cdiv(nE, 32), nTN = nNp / 32;
-    ctx->nTilesE32 = nTE; ctx->nTilesN32 = nTN;
-    std::vector<uint8_t> e32(nTE), n32(nTN);
-    StepCtl h;
-    memset(&h, 0, sizeof(h));
-    for (int t = 0; t < nTE; ++t) { e32[t] = etile_chunk[(t * 32) / ELEM_BLOCK]; h.elem_target[e32[t]]++; }
-    for (int t = 0; t < nTN; ++t) n32[t] = ntile_group[(t * 32) / NODE_TILE];
-    h.C = C; h.nTilesE = nTE; h.nTilesN = nTN;
-    if ((rc = dalloc(ctx, &ctx->d_sctl, 1)) || (rc = dalloc(ctx, &ctx->d_etile32, nTE)) || (rc = dalloc(ctx, &ctx->d_ntile32, nTN)) ||
-        (rc = dalloc(ctx, &ctx->d_etile_e, 2 * 3 * (size_t)nTN)) || (rc = dalloc(ctx, &ctx->d_eblock, 3 * ENERGY_BLOCKS)))
-      return rc;
-    CK(cudaMemcpy(ctx->d_sctl, &h, sizeof(h), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_etile32, e32.data(), nTE, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_ntile32, n32.data(), nTN, cudaMemcpyHostToDevice));
-    CK(cudaMemset(ctx->d_etile_e, 0, 2 * 3 * (size_t)nTN * sizeof(double)));
   }
   if (ctx->has_visco) {  // Hn_1, Hn_2, S0n zero at t = 0 (ShapeFunctions.cpp:245-252)
     const size_t n = (size_t)144 * 32 * cdiv(nE, 32);  // tiles of 32 elements (FTB_HIDX)
@@ -1027,99 +770,7 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
     CK(cudaMemcpy(ctx->halo_slot, hslot.data(), hslot.size() * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->halo_node_idx, node_h.data(), nNp * sizeof(int), cudaMemcpyHostToDevice));
   }
-  // ---- grids of the two persistent kernels: both must be resident on every SM at the same time ----
-  // Per SM sub-partition (4 per SM, 16384 registers each) the warps of both kernels must fit, and so
-  // must the shared memory (1 KB is reserved per resident block) and the thread slots.
-  {
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, ctx->device));
-    cudaFuncAttributes fe, fn;
-    switch (ctx->uniform_mat) {
-      case 1: CK(cudaFuncGetAttributes(&fe, k_elem_pipe<1>)); break;
-      case 4: CK(cudaFuncGetAttributes(&fe, k_elem_pipe<4>)); break;
-      case 5: CK(cudaFuncGetAttributes(&fe, k_elem_pipe<5>)); break;
-      default: CK(cudaFuncGetAttributes(&fe, k_elem_pipe<-1>)); break;
-    }
-    CK(cudaFuncGetAttributes(&fn, k_node_pipe));
-    CK(cudaFuncSetAttribute(k_elem_pipe<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CK(cudaFuncSetAttribute(k_elem_pipe<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CK(cudaFuncSetAttribute(k_elem_pipe<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CK(cudaFuncSetAttribute(k_elem_pipe<-1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CK(cudaFuncSetAttribute(k_node_pipe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    auto alloc = [](int r) { return ((r + 7) / 8) * 8 * 32; };  // registers per warp, allocation unit 8 per thread
-    const int regs_smsp = prop.regsPerMultiprocessor / 4;
-    const size_t smem_sm = prop.sharedMemPerMultiprocessor;
-    int nb = 1, eb = 0;
-    if (const char* ev = getenv("FTB200_NODE_BLOCKS_PER_SM")) nb = std::max(1, atoi(ev));
-    const int node_warps_smsp = (nb * (NODE_TILE / 32) + 3) / 4;
-    for (int t = 8; t >= 1; --t) {
-      const int elem_warps_smsp = (t * (ELEM_BLOCK / 32) + 3) / 4;
-      const bool regs_ok = elem_warps_smsp * alloc(fe.numRegs) + node_warps_smsp * alloc(fn.numRegs) <= regs_smsp;
-      const bool smem_ok = t * (fe.sharedSizeBytes + 1024) + nb * (fn.sharedSizeBytes + 1024) <= smem_sm;
-      const bool thr_ok = t * ELEM_BLOCK + nb * NODE_TILE <= prop.maxThreadsPerMultiProcessor;
-      if (regs_ok && smem_ok && thr_ok) { eb = t; break; }
-    }
-    if (const char* ev = getenv("FTB200_ELEM_BLOCKS_PER_SM")) eb = std::min(eb, std::max(0, atoi(ev)));
-    // The chunk-pipelined loop (k_elem_pipe || k_node_pipe) is functional and parity-tested but not yet
-    // faster than the serial sequence (per-tile synchronisation latency); opt in with FTB200_PIPE=1.
-    ctx->pipe = false;
-    if (const char* ev = getenv("FTB200_PIPE")) ctx->pipe = eb >= 1 && atoi(ev) != 0;
-    ctx->elem_grid = std::max(1, std::min(prop.multiProcessorCount * std::max(eb, 1), nTilesE));
-    {
-      int fb = (ctx->uniform_mat == 5 || ctx->uniform_mat < 0) ? 4 : 6;  // resident 64-thread blocks of k_step per SM
-      if (const char* ev = getenv("FTB200_FUSED_BLOCKS_PER_SM")) fb = std::max(1, atoi(ev));
-      ctx->fused_grid = std::max(1, std::min(prop.multiProcessorCount * fb, cdiv(nE, ELEM_BLOCK)));
-      ctx->fused = false;
-      if (const char* ev = getenv("FTB200_FUSED")) ctx->fused = atoi(ev) != 0;
-      if (const char* ev = getenv("FTB200_FUSE_ADV")) ctx->fuse_adv = atoi(ev) != 0;
-      if (const char* ev = getenv("FTB200_NODE_ELL")) ctx->node_ell = atoi(ev) != 0;
-      if (const char* ev = getenv("FTB200_ENERGY_ASYNC")) ctx->energy_async = atoi(ev) != 0;
-      if (ctx->has_tet) { ctx->fused = false; ctx->pipe = false; }  // the one-kernel variants are hexahedra only
-    }
-    ctx->node_grid = std::max(1, std::min(prop.multiProcessorCount * nb, nTilesN));
-    {
-      // overlapped step: opt-in while it is being measured (FTB200_OVERLAP=1).  The element kernel gives up one resident
-      // block per SM (a few unused bytes of dynamic shared memory), k_node_ovl runs FTB200_OVL_NODE_BLOCKS (1) per SM.
-      bool want = false;
-      if (const char* ev = getenv("FTB200_OVERLAP")) want = atoi(ev) != 0;
-      const bool ok = ctx->nranks == 1 && ctx->halo_count == 0 && !ctx->has_tet && ctx->ranges.size() == 1 && ctx->ranges[0].e0 == 0 &&
-                      (ctx->ranges[0].mat == 1 || ctx->ranges[0].mat == 4) && ctx->ovl_chunks < 65535;
-      ctx->overlap = want && ok;
-      if (ctx->overlap) {
-        const bool aff = ctx->ranges[0].affine != 0;
-        const int stat = (aff ? FTB_AFFINE_SLOTS : 72) * ELEM_BLOCK * (int)sizeof(double) + 1024;  // static + reserved bytes per block
-        int natural = aff ? FTB_AFF_MINBLOCKS : ELEM_MINBLOCKS;
-        natural = std::min(natural, (int)(prop.sharedMemPerMultiprocessor / stat));
-        int eb2 = natural - 1;
-        if (const char* ev = getenv("FTB200_OVL_ELEM_BLOCKS")) eb2 = std::max(1, std::min(natural, atoi(ev)));
-        // smallest request that no longer lets eb2 + 1 blocks share an SM
-        int dyn = (int)(prop.sharedMemPerMultiprocessor / (eb2 + 1)) - stat + 16;
-        dyn = eb2 >= natural ? 0 : std::max(16, (dyn + 15) / 16 * 16);
-        ctx->ovl_elem_dyn = dyn;
-        int per_sm = 1;
-        if (const char* ev = getenv("FTB200_OVL_NODE_BLOCKS")) per_sm = std::max(1, atoi(ev));
-        ctx->ovl_grid = std::max(1, std::min(prop.multiProcessorCount * per_sm, ctx->node_blocks));
-        // co-residency: an SM's shared-memory carve-out is fixed while blocks live on it; every kernel of the pair asks for
-        // the same (largest) one, otherwise whichever kernel reaches an SM first locks the other out of it
-        const int co = cudaSharedmemCarveoutMaxShared;
-        CK(cudaFuncSetAttribute(k_node_ovl<true>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
-        CK(cudaFuncSetAttribute(k_node_ovl<false>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
-        CK(cudaFuncSetAttribute(k_elem_affine<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
-        CK(cudaFuncSetAttribute(k_elem_affine<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
-        CK(cudaFuncSetAttribute(k_elem<1, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
-        CK(cudaFuncSetAttribute(k_elem<4, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
-      }
-    }
-    {
-      if (const char* ev = getenv("FTB200_PDL")) ctx->pdl = atoi(ev) != 0;
-      // element kernels: optional L2 prefetch for the blocks `waves` waves ahead (a wave = SMs x 8 resident 64-element
-      // blocks).  Measured at 100^3 for 1-4 waves: no gain (k_elem_affine 170 -> 172 us, general kernel unchanged), so
-      // the exposed part of the prologue is not DRAM latency of first-touch lines; off unless asked for.
-      double waves = 0.0;
-      if (const char* ev = getenv("FTB200_PREFETCH_WAVES")) waves = atof(ev);
-      ctx->pf_dist = waves > 0.0 ? (int)(waves * prop.multiProcessorCount * 8) * ELEM_BLOCK : 0;
-    }
-  }
+  if (const char* ev = getenv("FTB200_ENERGY_ASYNC")) ctx->energy_async = atoi(ev) != 0;
   // ---- validate the reference configuration: detJ0 > 0 at every Gauss point --------------------
   {
     const unsigned long long inf = 0x7FF0000000000000ULL;
@@ -1150,6 +801,7 @@ int ftb200_lumped_mass(ftb200_ctx* ctx, double* mass_out) {
   CK(cudaMemcpyAsync(ctx->d_detmin, &inf, sizeof(inf), cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(k_mass_elem, cdiv(nE, 128), 128, ctx->stream, elem_args(ctx, 0, nE, 1), ctx->felem, ctx->d_detmin, ctx->d_nonpos);
   LAUNCH(k_mass_gather, cdiv(nN, 256), 256, ctx->stream, ctx->felem, ctx->node_off, ctx->node_ent, ctx->m, nN, nE);
+  CK(cudaGetLastError());
   if (mass_out) {
     double* src[3] = {ctx->m, ctx->m, ctx->m};  // the same value on the three dofs of a node (Mass3D.cpp:146-151)
     int rc = download_aos(ctx, src, mass_out, 0);
@@ -1174,9 +826,14 @@ static int legacy_force_local(ftb200_ctx* ctx, const double* displacements, cons
   int rc;
   if ((rc = upload_aos(ctx, displacements, ctx->u))) return rc;
   if (fe) {
+    // external-force planes live in the padded internal node order like every other nodal plane (nNp >= nN)
     for (int k = 0; k < 3; ++k)
-      if (!ctx->fe[k] && (rc = dalloc(ctx, &ctx->fe[k], ctx->nN))) return rc;
+      if (!ctx->fe[k]) {
+        if ((rc = dalloc(ctx, &ctx->fe[k], ctx->nNp))) return rc;
+        CK(cudaMemsetAsync(ctx->fe[k], 0, ctx->nNp * sizeof(double), ctx->stream));
+      }
     if ((rc = upload_aos(ctx, fe, ctx->fe))) return rc;
+    if (!ctx->has_fe) drop_graphs(ctx);  // the graphs were captured with null fe planes
     ctx->has_fe = true;
   }
   if (ctx->has_visco) LAUNCH(k_prony, 1, 128, ctx->stream, ctx->mp, ctx->nPID, dt);
@@ -1193,6 +850,7 @@ int ftb200_get_force(ftb200_ctx* ctx, const double* displacements, const double*
   LAUNCH(k_gather_force, ctx->node_blocks, NODE_BLOCK, ctx->stream, N, ctx->fnet[0], ctx->fnet[1], ctx->fnet[2]);
   if (fi && (rc = download_aos(ctx, ctx->fi, fi, 0))) return rc;
   if (f_net && (rc = download_aos(ctx, ctx->fnet, f_net, 1))) return rc;
+  CK(cudaGetLastError());  // a refused launch (bad configuration on this device) must not return stale forces
   int status = 0;
   CK(cudaMemcpyAsync(&status, &ctx->sc->status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1227,6 +885,7 @@ int ftb200_stable_time_step(ftb200_ctx* ctx, const double* displacements, const 
   const unsigned long long inf = 0x7FF0000000000000ULL;
   CK(cudaMemcpyAsync(&ctx->sc->dtmin_bits, &inf, sizeof(inf), cudaMemcpyHostToDevice, ctx->stream));
   launch_elem<false, true>(ctx, ctx->stream, 0, ctx->nE, 1);
+  CK(cudaGetLastError());
   unsigned long long bits = 0;
   CK(cudaMemcpyAsync(&bits, &ctx->sc->dtmin_bits, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1351,7 +1010,7 @@ int ftb200_record_history(ftb200_ctx* ctx, long long capacity) {
     CK(cudaMemset(ctx->ehist, 0, 4 * capacity * sizeof(double)));
   }
   CK(cudaMemcpy(&ctx->sc->hist_cap, &capacity, sizeof(long long), cudaMemcpyHostToDevice));
-  if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+  drop_graphs(ctx);  // dthist / ehist are kernel arguments of every captured loop (single-partition and peer-memory)
   dfree(ctx->inj_hist);
   if (ctx->injury && capacity > 0) {
     int rc;
@@ -1385,10 +1044,9 @@ int ftb200_explicit_begin_dt(ftb200_ctx* ctx, double Time0, double reduction, do
   // the 25-step graph of the standard loop survives a restart: its kernel arguments are device pointers and flags that
   // explicit_begin does not change (build_graph compares the ones that can; injury / rigid-body / history / stream
   // changes drop it themselves).  Rebuilding it cost 1-2 ms of every ExplicitDynamics call that starts from host state.
-  if (ctx->pgraph) { cudaGraphExecDestroy(ctx->pgraph); ctx->pgraph = nullptr; }
-  if (ctx->fgraph) { cudaGraphExecDestroy(ctx->fgraph); ctx->fgraph = nullptr; }
   // scalars: keep bc_rate / hist_cap, reset the rest
   DevScalars h;
+  CK(cudaStreamSynchronize(s));  // a run enqueued earlier may still be writing the scalars and the step ring
   CK(cudaMemcpy(&h, ctx->sc, sizeof(h), cudaMemcpyDeviceToHost));
   double rate[4];
   memcpy(rate, h.bc_rate, sizeof(rate));
@@ -1396,6 +1054,9 @@ int ftb200_explicit_begin_dt(ftb200_ctx* ctx, double Time0, double reduction, do
   memcpy(h.bc_rate, rate, sizeof(rate));
   h.hist_cap = ctx->hist_cap;
   h.ring = ctx->ring_dev; h.ring_cap = ctx->ring_cap;
+  // records are counted from this explicit_begin: a slot still holding step k of the previous run must not satisfy a
+  // wait for step k of this one (the stream is idle here)
+  for (long long i = 0; ctx->ring_host && i < ctx->ring_cap; ++i) ctx->ring_host[8 * i + 2] = -1.0;
   h.Time = Time0; h.tMax = 1e300; h.reduction = reduction; h.failure_dt = failure_dt;
   h.dtmin_bits = 0x7FF0000000000000ULL;
   h.energy_every = energy_every;
@@ -1437,13 +1098,6 @@ int ftb200_explicit_begin_finish(ftb200_ctx* ctx, const double* recv_dev) {
   const NodeArgs N = node_args(ctx, ctx->halo_count ? recv_dev : nullptr);
   LAUNCH((k_node<true, false, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   ctx->halo_recv_cur = ctx->halo_count ? recv_dev : nullptr;
-  {
-    const long long zero = 0;
-    CK(cudaMemcpyAsync(&ctx->d_ctl->elem_step, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(&ctx->d_ctl->node_step, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(&ctx->d_ctl->stop_step, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(&ctx->d_sctl->energy_step, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
-  }
   int status = 0;
   CK(cudaMemcpyAsync(&status, &ctx->sc->status, sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -1467,9 +1121,7 @@ static void join_energy(ftb200_ctx* ctx) {
 }
 
 static int build_graph(ftb200_ctx* ctx) {
-  const int sig = ctx->energy | (ctx->has_fe ? 2 : 0) | (overlap_now(ctx, nullptr) ? 4 : 0) | (ctx->energy_async ? 8 : 0) |
-                  (ctx->fuse_adv ? 16 : 0) | (ctx->node_ell ? 32 : 0) | (ctx->injury ? 64 : 0) | (ctx->rigid ? 128 : 0) |
-                  (ctx->pdl ? 256 : 0);
+  const int sig = ctx->energy | (ctx->has_fe ? 2 : 0) | (ctx->energy_async ? 8 : 0) | (ctx->injury ? 64 : 0) | (ctx->rigid ? 128 : 0);
   if (ctx->graph && ctx->graph_energy == sig) return 0;
   if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
   cudaGraph_t g = nullptr;
@@ -1557,115 +1209,6 @@ static int run_async_p2p(ftb200_ctx* ctx, double tMax, long long steps) {
   return FTB200_OK;
 }
 
-// ---- fused step: one k_step launch per time step on the main stream; the energy reduction of step n runs on
-//      the second stream concurrently with step n+1 (its partial buffer is reused by step n+2)
-static void launch_fused_steps(ftb200_ctx* ctx, int nsteps) {
-  cudaStream_t s1 = ctx->stream, s2 = ctx->stream2;
-  StepArgs P;
-  P.E = elem_args(ctx, 0, ctx->nE, 0);
-  P.N = node_args(ctx, nullptr);
-  P.ell = ctx->d_ell; P.etile_chunk = ctx->d_etile32; P.ntile_group = ctx->d_ntile32; P.ctl = ctx->d_sctl;
-  P.etile = ctx->d_etile_e; P.dt_hist = ctx->dthist; P.nPID = ctx->nPID; P.energy = ctx->energy;
-  for (int i = 0; i < nsteps; ++i) {
-    size_t i0 = 0, i1 = 0;
-    if (ctx->energy && i >= 2) cudaStreamWaitEvent(s1, ctx->ev_energy[i & 1], 0);  // buffer (i & 1) was read by step i-2's reduction
-    if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s1);
-    switch (ctx->uniform_mat) {
-      case 1: LAUNCH((k_step<1>), ctx->fused_grid, ELEM_BLOCK, s1, P); break;
-      case 4: LAUNCH((k_step<4>), ctx->fused_grid, ELEM_BLOCK, s1, P); break;
-      case 5: LAUNCH((k_step<5>), ctx->fused_grid, ELEM_BLOCK, s1, P); break;
-      default: LAUNCH((k_step<-1>), ctx->fused_grid, ELEM_BLOCK, s1, P); break;
-    }
-    if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s1); ctx->prof.elem.push_back({i0, i1}); }
-    if (ctx->energy) {
-      cudaEventRecord(ctx->ev_step, s1);
-      cudaStreamWaitEvent(s2, ctx->ev_step, 0);
-      LAUNCH(k_energy_tiles, ENERGY_BLOCKS, 256, s2, ctx->sc, ctx->d_sctl, ctx->d_etile_e, ctx->d_eblock, ctx->ehist);
-      cudaEventRecord(ctx->ev_energy[i & 1], s2);
-    }
-  }
-  if (ctx->energy) {  // join: everything of this batch is complete when the main stream continues
-    cudaStreamWaitEvent(s1, ctx->ev_energy[(nsteps - 1) & 1], 0);
-    if (nsteps >= 2) cudaStreamWaitEvent(s1, ctx->ev_energy[(nsteps - 2) & 1], 0);
-  }
-}
-
-static int run_async_fused(ftb200_ctx* ctx, double tMax, long long steps) {
-  cudaStream_t s = ctx->stream;
-  LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
-  const bool use_graph = !ctx->profile;  // built on the first run (warm-up), whatever its length
-  if (use_graph && !(ctx->fgraph && ctx->fgraph_energy == ctx->energy)) {
-    if (ctx->fgraph) { cudaGraphExecDestroy(ctx->fgraph); ctx->fgraph = nullptr; }
-    cudaGraph_t g = nullptr;
-    const long long before = ctx->launches;
-    CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    launch_fused_steps(ctx, GRAPH_STEPS);
-    cudaError_t e = cudaStreamEndCapture(s, &g);
-    ctx->launches = before;
-    if (e != cudaSuccess) return fail(ctx, FTB200_ERR_CUDA, "fused graph capture failed: %s", cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&ctx->fgraph, g, 0);
-    cudaGraphDestroy(g);
-    if (e != cudaSuccess) { ctx->fgraph = nullptr; return fail(ctx, FTB200_ERR_CUDA, "fused graph instantiate failed: %s", cudaGetErrorString(e)); }
-    ctx->fgraph_energy = ctx->energy;
-  }
-  long long left = steps;
-  const int per_step = 1 + (ctx->energy ? 1 : 0);
-  while (left > 0) {
-    if (use_graph && left >= GRAPH_STEPS) {
-      CK(cudaGraphLaunch(ctx->fgraph, s));
-      ctx->launches += (long long)per_step * GRAPH_STEPS;
-      left -= GRAPH_STEPS;
-    } else {
-      const int n = (int)std::min<long long>(left, GRAPH_STEPS);
-      launch_fused_steps(ctx, n);
-      left -= n;
-    }
-  }
-  CK(cudaGetLastError());
-  return FTB200_OK;
-}
-
-static int build_pipe_graph(ftb200_ctx* ctx) {
-  if (ctx->pgraph && ctx->pgraph_energy == ctx->energy) return 0;
-  if (ctx->pgraph) { cudaGraphExecDestroy(ctx->pgraph); ctx->pgraph = nullptr; }
-  cudaGraph_t g = nullptr;
-  const long long before = ctx->launches;
-  CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-  launch_pipe_steps(ctx, GRAPH_STEPS);
-  cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
-  ctx->launches = before;
-  if (e != cudaSuccess) return fail(ctx, FTB200_ERR_CUDA, "pipeline graph capture failed: %s", cudaGetErrorString(e));
-  e = cudaGraphInstantiate(&ctx->pgraph, g, 0);
-  cudaGraphDestroy(g);
-  if (e != cudaSuccess) { ctx->pgraph = nullptr; return fail(ctx, FTB200_ERR_CUDA, "pipeline graph instantiate failed: %s", cudaGetErrorString(e)); }
-  ctx->pgraph_energy = ctx->energy;
-  return 0;
-}
-
-static int run_async_pipe(ftb200_ctx* ctx, double tMax, long long steps) {
-  cudaStream_t s = ctx->stream;
-  LAUNCH(k_pipe_begin, 1, 1, s, ctx->sc, ctx->d_ctl, tMax, steps);
-  long long left = steps;
-  const bool use_graph = !ctx->profile;  // built on the first run (warm-up), whatever its length
-  if (use_graph) {
-    int rc = build_pipe_graph(ctx);
-    if (rc) return rc;
-  }
-  while (left > 0) {
-    if (use_graph && left >= GRAPH_STEPS) {
-      CK(cudaGraphLaunch(ctx->pgraph, s));
-      ctx->launches += 2LL * GRAPH_STEPS;
-      left -= GRAPH_STEPS;
-    } else {
-      const int n = (int)std::min<long long>(left, GRAPH_STEPS);
-      launch_pipe_steps(ctx, n);
-      left -= n;
-    }
-  }
-  CK(cudaGetLastError());
-  return FTB200_OK;
-}
-
 int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
   if (!ctx || !ctx->begun) return fail(ctx, FTB200_ERR_INPUT, "explicit_run: call explicit_begin first");
   CK(cudaSetDevice(ctx->device));
@@ -1674,11 +1217,12 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
       return fail(ctx, FTB200_ERR_INPUT, "explicit_run: multi-rank runs need the peer-memory windows (p2p_export/import) "
                                          "or the step_begin/step_join/step_end sequence");
     if (steps <= 0) return FTB200_OK;
+    if (ctx->injury)  // the selection passes need a cross-rank histogram sum: only the step_begin/step_end loop drives them
+      return fail(ctx, FTB200_ERR_INPUT, "explicit_run: the injury criteria are not carried by the peer-memory loop; "
+                                         "use the step_begin/step_join/step_end sequence");
     return run_async_p2p(ctx, tMax, steps);
   }
   if (steps <= 0) return FTB200_OK;
-  if (ctx->pipe) return run_async_pipe(ctx, tMax, steps);
-  if (ctx->fused) return run_async_fused(ctx, tMax, steps);
   cudaStream_t s = ctx->stream;
   LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
   {
@@ -1687,9 +1231,7 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
     if (ctx->energy) LAUNCH((k_node<false, true, false, true>), ctx->node_blocks, NODE_BLOCK, s, N);
     else LAUNCH((k_node<false, true, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   }
-  const bool adv_fused = ctx->nranks == 1 && ctx->fuse_adv && !ctx->rigid;
-  const int per_step = overlap_now(ctx, nullptr) ? 4 + (ctx->energy ? 1 : 0)
-                                                 : (adv_fused ? 2 : 3 + (ctx->energy ? 1 : 0)) + (ctx->injury ? INJ_LAUNCHES : 0) + (ctx->rigid ? 1 : 0);
+  const int per_step = 3 + (ctx->energy ? 1 : 0) + (ctx->injury ? INJ_LAUNCHES : 0) + (ctx->rigid ? 1 : 0);
   long long left = steps;
   const bool use_graph = !ctx->profile;  // built on the first run (warm-up), whatever its length
   if (use_graph) {
@@ -1732,7 +1274,6 @@ int ftb200_explicit_poll(ftb200_ctx* ctx, long long* steps_done, double* Time, d
   if (Time) *Time = h.Time;
   if (dt) *dt = h.ndt;
   if (status_bits) *status_bits = h.status;
-  if (h.status & 32) return fail(ctx, FTB200_ERR_CUDA, "pipelined loop stalled: element and node kernels were not co-resident");
   if (h.status & 64) return fail(ctx, FTB200_ERR_CUDA, "peer-memory exchange timed out: a neighbour rank never delivered its step");
   return FTB200_OK;
 }
@@ -1983,83 +1524,7 @@ int ftb200_profile_get(ftb200_ctx* ctx, double* elem_ms, double* node_ms, long l
   return FTB200_OK;
 }
 
-// Tuning experiment (not part of the public ABI): run the element kernel and the node kernel
-// concurrently on two streams, `reps` times, and report the elapsed time per pair.
-int ftb200_debug_overlap(ftb200_ctx* ctx, int reps, int concurrent, double* ms_per_pair) {
-  if (!ctx || !ctx->begun) return FTB200_ERR_INPUT;
-  CK(cudaSetDevice(ctx->device));
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
-  cudaStream_t s = ctx->stream, s2 = ctx->stream2;
-  const NodeArgs N = node_args(ctx, nullptr);
-  CK(cudaStreamSynchronize(s));
-  CK(cudaEventRecord(e0, s));
-  for (int r = 0; r < reps; ++r) {
-    if (concurrent) {
-      CK(cudaEventRecord(ctx->ev_fork, s));
-      CK(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
-      LAUNCH((k_node<true, false, false, false>), ctx->node_blocks, NODE_BLOCK, s2, N);
-      launch_elem<true, true>(ctx, s, 0, ctx->nE, 1);
-      CK(cudaEventRecord(ctx->ev_join, s2));
-      CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
-    } else {
-      launch_elem<true, true>(ctx, s, 0, ctx->nE, 1);
-      LAUNCH((k_node<true, false, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
-    }
-  }
-  CK(cudaEventRecord(e1, s));
-  CK(cudaEventSynchronize(e1));
-  float ms = 0;
-  CK(cudaEventElapsedTime(&ms, e0, e1));
-  *ms_per_pair = ms / reps;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  return FTB200_OK;
-}
-
-// Tuning probe (not part of the public ABI): time one of the pipe kernels alone (which = 0 element,
-// 1 node), all dependencies pre-satisfied.  Leaves the state advanced by `reps` pseudo-steps.
-int ftb200_debug_pipe(ftb200_ctx* ctx, int which, int reps, double* ms_per_launch) {
-  if (!ctx || !ctx->begun) return FTB200_ERR_INPUT;
-  CK(cudaSetDevice(ctx->device));
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
-  cudaStream_t s = ctx->stream;
-  PipeElemArgs PE;
-  PE.E = elem_args(ctx, 0, ctx->nE, 0);
-  for (int k = 0; k < 3; ++k) { PE.v[k] = ctx->v[k]; PE.a[k] = ctx->a[k]; }
-  PE.flags = ctx->flags; PE.tile_chunk = ctx->d_etile_chunk; PE.ctl = ctx->d_ctl; PE.dt_hist = nullptr; PE.nPID = ctx->nPID;
-  PipeNodeArgs PN;
-  PN.N = node_args(ctx, nullptr);
-  PN.ell = ctx->d_ell; PN.tile_group = ctx->d_ntile_group; PN.ctl = ctx->d_ctl; PN.etile = ctx->d_etile; PN.ehist = nullptr; PN.energy = ctx->energy;
-  float total = 0;
-  for (int r = 0; r < reps; ++r) {
-    LAUNCH(k_pipe_debug_arm, 1, 1, s, ctx->d_ctl, ctx->sc);
-    CK(cudaEventRecord(e0, s));
-    if (which == 0) LAUNCH((k_elem_pipe<1>), ctx->elem_grid, ELEM_BLOCK, s, PE);
-    else LAUNCH(k_node_pipe, ctx->node_grid, NODE_TILE, s, PN);
-    CK(cudaEventRecord(e1, s));
-    CK(cudaEventSynchronize(e1));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    total += ms;
-  }
-  *ms_per_launch = total / reps;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  return FTB200_OK;
-}
-
 // ----------------------------------------------------------------------------------- injury criteria
-static void drop_graphs(ftb200_ctx* ctx) {
-  if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
-  if (ctx->p2p_graph) { cudaGraphExecDestroy(ctx->p2p_graph); ctx->p2p_graph = nullptr; }
-  if (ctx->fgraph) { cudaGraphExecDestroy(ctx->fgraph); ctx->fgraph = nullptr; }
-  if (ctx->pgraph) { cudaGraphExecDestroy(ctx->pgraph); ctx->pgraph = nullptr; }
-}
-
 // ----------------------------------------------------------------------------------- rigid-body BC
 __global__ void k_rigid_mark(const int* __restrict__ ids, int n, const int* __restrict__ nint, uint16_t* flags, double* ux,
                              double* uy, double* uz, double* vx, double* vy, double* vz, double* ax, double* ay, double* az) {
@@ -2121,7 +1586,6 @@ int ftb200_set_rigid_bc(ftb200_ctx* ctx, const int sizes[6], const double* const
     LAUNCH(k_eflag, cdiv(ctx->nE, 256), 256, ctx->stream, ctx->conn, ctx->flags, ctx->eflag, ctx->nE);
     CK(cudaStreamSynchronize(ctx->stream));
   }
-  ctx->fused = false; ctx->pipe = false;
   drop_graphs(ctx);
   ctx->bc_ok = true;
   return FTB200_OK;
@@ -2188,7 +1652,6 @@ int ftb200_injury_begin(ftb200_ctx* ctx, const int* exclude_pids, int n_exclude,
     CK(cudaMemset(ctx->inj_hist, 0, 2 * ctx->hist_cap * sizeof(double)));
   }
   ctx->injury = true;
-  ctx->fused = false; ctx->pipe = false;  // the criteria live in the two-kernel step
   drop_graphs(ctx);
   return FTB200_OK;
 }

@@ -659,10 +659,9 @@ def test_brain_like_example_runs_all_next_rows_together(tmp_path):
     assert a["PartID"].size == 12 ** 3 and set(np.unique(a["PartID"])) == {0, 1, 2} and "CSDM-15" in a
 
 
-@pytest.mark.parametrize("var", ["FTB200_FUSED", "FTB200_PIPE", "FTB200_FUSE_ADV", "FTB200_ENERGY_ASYNC=0", "FTB200_NODE_ELL=0"])
-def test_opt_in_loop_variants_still_match_the_oracle(var):
-    """The experimental step organisations kept behind environment switches (fused per-step kernel,
-    chunk-pipelined kernels, k_adv/k_energy folded into k_node) and the off-switches of two defaults must stay correct:
+@pytest.mark.parametrize("var", ["FTB200_ENERGY_ASYNC=0", "FTB200_BRICK=0"])
+def test_off_switches_of_defaults_still_match_the_oracle(var):
+    """The off-switches of two defaults (energy reduction on the helper stream; the brick-fused step) must stay correct:
     the smoke run (mixed materials 1 + 5, 25 steps, checked against the oracle) under each of them."""
     import os
     import subprocess
