@@ -65,6 +65,8 @@ SIGNATURES = {
     "ftb200_upload_mesh_mixed": (C.c_int, [_vp, _dp, _ip, _ip, _ip, C.c_int, C.c_int]),
     "ftb200_gauss_point_count": (_ll, [_vp]),
     "ftb200_affine_element_count": (_ll, [_vp]),
+    "ftb200_brick_info": (C.c_int, [_vp, C.POINTER(_ll)]),
+    "ftb200_brick_maps": (C.c_int, [_vp, _ip, _ip]),
     "ftb200_set_rigid_bc": (C.c_int, [_vp, _ip, C.POINTER(_dp), C.POINTER(_dp), _ip, C.c_int]),
     "ftb200_get_rigid_state": (C.c_int, [_vp, _dp, _dp, _ip]),
     "ftb200_explicit_poll_async": (C.c_int, [_vp, _dp]),

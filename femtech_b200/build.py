@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libftb200.so")
 SOURCES = [os.path.join(CSRC, "ftb200_capi.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "ftb200_kernels.cuh"), os.path.join(CSRC, "hex8_element.cuh"),
+DEPS = SOURCES + [os.path.join(CSRC, "ftb200_kernels.cuh"), os.path.join(CSRC, "ftb200_brick.cuh"), os.path.join(CSRC, "hex8_element.cuh"),
                   os.path.join(os.path.dirname(HERE), "include", "ftb200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "ftb200_kernels.cuh"
+#include "ftb200_brick.cuh"
 
 using namespace ftb;
 
@@ -110,6 +111,15 @@ struct ftb200_ctx {
   int p2p_graph_energy = -1;
   long long p2p_graph_launches = 0;
   double Time0 = 0.0;
+  // brick-fused step (ftb200_brick.cuh): built by shape_functions when the mesh qualifies
+  bool brick_ok = false, brick_want = true, felem_stale = false;
+  int brick_dims[3] = {10, 5, 5};
+  int nB = 0, nIntTot = 0, nSurf = 0, surf_blocks = 0;
+  long long nSlots = 0;
+  BrickHdr* b_hdr = nullptr;
+  uint16_t *b_conn16 = nullptr, *b_map16 = nullptr;
+  int *b_halo = nullptr, *s_ell = nullptr, *s_ovoff = nullptr, *s_ovent = nullptr;
+  double* b_part[3] = {nullptr, nullptr, nullptr};
   // graph cache
   cudaGraphExec_t graph = nullptr;
   int graph_energy = -1;
@@ -343,6 +353,179 @@ void launch_step(ftb200_ctx* ctx, const double* recv) {
   if (ctx->injury) launch_injury(ctx, s);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Brick decomposition of an all-hexahedra mesh for k_brick / k_surf (ftb200_brick.cuh).  Elements are binned by their
+// centroid into boxes of dims[] mean element extents (a structured or voxel mesh gives exact dims[0] x dims[1] x dims[2]
+// bricks); a box with more than BRICK_NT elements or more than BRICK_NLMAX nodes is bisected at the median of its longest
+// axis until it fits.  Bricks are numbered box by box, x fastest: neighbours in the launch order share surface nodes in L2.
+struct BrickPlan {
+  int nB = 0;
+  std::vector<int> eoff;    // [nB + 1] into elems
+  std::vector<int> elems;   // caller element ids, ascending inside each brick
+};
+
+void brick_split(const ftb200_ctx* ctx, const std::vector<float>& cen, std::vector<int>& list, size_t lo, size_t hi,
+                 std::vector<int>& stamp, int& stamp_id, std::vector<std::pair<size_t, size_t>>& out) {
+  const size_t n = hi - lo;
+  bool fits = n <= (size_t)BRICK_NT;
+  if (fits) {  // count the nodes of the group
+    ++stamp_id;
+    int nl = 0;
+    for (size_t i = lo; i < hi; ++i)
+      for (int k = 0; k < 8; ++k) {
+        const int nd = ctx->h_conn[8 * (size_t)list[i] + k];
+        if (stamp[nd] != stamp_id) { stamp[nd] = stamp_id; ++nl; }
+      }
+    fits = nl <= BRICK_NLMAX;
+  }
+  if (fits || n <= 1) { out.push_back({lo, hi}); return; }
+  float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+  for (size_t i = lo; i < hi; ++i)
+    for (int c = 0; c < 3; ++c) {
+      const float v = cen[3 * (size_t)list[i] + c];
+      mn[c] = std::min(mn[c], v); mx[c] = std::max(mx[c], v);
+    }
+  int ax = 0;
+  for (int c = 1; c < 3; ++c)
+    if (mx[c] - mn[c] > mx[ax] - mn[ax]) ax = c;
+  const size_t mid = lo + n / 2;
+  std::nth_element(list.begin() + lo, list.begin() + mid, list.begin() + hi, [&](int a, int b) {
+    const float va = cen[3 * (size_t)a + ax], vb = cen[3 * (size_t)b + ax];
+    return va < vb || (va == vb && a < b);
+  });
+  brick_split(ctx, cen, list, lo, mid, stamp, stamp_id, out);
+  brick_split(ctx, cen, list, mid, hi, stamp, stamp_id, out);
+}
+
+BrickPlan plan_bricks(const ftb200_ctx* ctx) {
+  const int nE = ctx->nE, nN = ctx->nN;
+  BrickPlan P;
+  std::vector<float> cen(3 * (size_t)nE);
+  double bbmin[3] = {1e300, 1e300, 1e300}, bbmax[3] = {-1e300, -1e300, -1e300}, hsum[3] = {0, 0, 0};
+  for (int e = 0; e < nE; ++e) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, cs[3] = {0, 0, 0};
+    for (int k = 0; k < 8; ++k)
+      for (int c = 0; c < 3; ++c) {
+        const double x = ctx->h_X[3 * (size_t)ctx->h_conn[8 * (size_t)e + k] + c];
+        lo[c] = std::min(lo[c], x); hi[c] = std::max(hi[c], x); cs[c] += x;
+      }
+    for (int c = 0; c < 3; ++c) {
+      const double x = cs[c] / 8.0;
+      cen[3 * (size_t)e + c] = (float)x;
+      bbmin[c] = std::min(bbmin[c], x); bbmax[c] = std::max(bbmax[c], x);
+      hsum[c] += hi[c] - lo[c];
+    }
+  }
+  long long nc[3];
+  double cell[3];
+  for (int c = 0; c < 3; ++c) {
+    const double h = std::max(hsum[c] / std::max(nE, 1), 1e-300);
+    cell[c] = h * ctx->brick_dims[c];
+    nc[c] = std::max<long long>(1, (long long)std::floor((bbmax[c] - bbmin[c]) / cell[c]) + 1);
+  }
+  // (box, caller id) order
+  std::vector<std::pair<long long, int>> key(nE);
+  for (int e = 0; e < nE; ++e) {
+    long long ix[3];
+    for (int c = 0; c < 3; ++c) {
+      ix[c] = (long long)std::floor(((double)cen[3 * (size_t)e + c] - bbmin[c]) / cell[c] + 1e-6);
+      ix[c] = std::min(std::max(ix[c], 0LL), nc[c] - 1);
+    }
+    key[e] = {ix[0] + nc[0] * (ix[1] + nc[1] * ix[2]), e};
+  }
+  std::sort(key.begin(), key.end());
+  std::vector<int> list(nE);
+  for (int i = 0; i < nE; ++i) list[i] = key[i].second;
+  std::vector<int> stamp(nN, 0);
+  int stamp_id = 0;
+  std::vector<std::pair<size_t, size_t>> groups;
+  for (size_t i = 0; i < (size_t)nE;) {
+    size_t j = i;
+    while (j < (size_t)nE && key[j].first == key[i].first) ++j;
+    brick_split(ctx, cen, list, i, j, stamp, stamp_id, groups);
+    i = j;
+  }
+  P.nB = (int)groups.size();
+  P.eoff.assign(P.nB + 1, 0);
+  P.elems.resize(nE);
+  size_t w = 0;
+  for (int b = 0; b < P.nB; ++b) {
+    std::sort(list.begin() + groups[b].first, list.begin() + groups[b].second);
+    for (size_t i = groups[b].first; i < groups[b].second; ++i) P.elems[w++] = list[i];
+    P.eoff[b + 1] = (int)w;
+  }
+  return P;
+}
+
+// ---- brick-fused step: k_brick -> k_surf -> k_adv (-> k_energy).  The START of a step (first kick, drift, boundary
+//      condition) is the prologue of k_brick / k_surf, so the state between two steps is the full-step (u, v, a) and a run
+//      needs no separate START launch.
+bool use_brick(const ftb200_ctx* ctx) { return ctx->brick_ok && !ctx->rigid && !ctx->injury && ctx->nranks == 1; }
+
+BrickArgs brick_args(ftb200_ctx* c) {
+  BrickArgs A;
+  A.hdr = c->b_hdr; A.conn16 = c->b_conn16; A.halo = c->b_halo; A.map16 = c->b_map16;
+  for (int k = 0; k < 3; ++k) {
+    A.X[k] = c->X[k]; A.u[k] = c->u[k]; A.v[k] = c->v[k]; A.a[k] = c->a[k]; A.fi[k] = c->fi[k];
+    A.fe[k] = c->has_fe ? c->fe[k] : nullptr;
+    A.part[k] = c->b_part[k];
+  }
+  A.m = c->m; A.flags = c->flags; A.pid = c->pid; A.eflag = c->eflag; A.mp = c->mp;
+  A.epart = c->epart; A.nEpart = c->nB + c->surf_blocks; A.sc = c->sc; A.store_fi = c->energy ? 1 : 0;
+  return A;
+}
+SurfArgs surf_args(ftb200_ctx* c) {
+  SurfArgs A;
+  A.ell = c->s_ell; A.ov_off = c->s_ovoff; A.ov_ent = c->s_ovent;
+  for (int k = 0; k < 3; ++k) {
+    A.u[k] = c->u[k]; A.v[k] = c->v[k]; A.a[k] = c->a[k]; A.fi[k] = c->fi[k];
+    A.fe[k] = c->has_fe ? c->fe[k] : nullptr;
+    A.part[k] = c->b_part[k];
+  }
+  A.m = c->m; A.flags = c->flags; A.epart = c->epart; A.nEpart = c->nB + c->surf_blocks; A.eoff = c->nB;
+  A.node0 = c->nIntTot; A.nS = c->nSurf; A.sc = c->sc; A.store_fi = c->energy ? 1 : 0;
+  return A;
+}
+template <int MAT, bool EN>
+void launch_brick_k(ftb200_ctx* ctx, cudaStream_t s, const BrickArgs& A) {
+  auto kfn = k_brick<MAT, EN>;
+  cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRICK_SMEM_BYTES);  // per device
+  launch_k(ctx, kfn, dim3(ctx->nB), dim3(BRICK_NT), BRICK_SMEM_BYTES, s, A);
+}
+void launch_step_brick(ftb200_ctx* ctx) {
+  cudaStream_t s = ctx->stream;
+  size_t i0 = 0, i1 = 0;
+  const BrickArgs A = brick_args(ctx);
+  const int mat = ctx->ranges.empty() ? 1 : ctx->ranges[0].mat;
+  if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
+  if (mat == 4) { if (ctx->energy) launch_brick_k<4, true>(ctx, s, A); else launch_brick_k<4, false>(ctx, s, A); }
+  else { if (ctx->energy) launch_brick_k<1, true>(ctx, s, A); else launch_brick_k<1, false>(ctx, s, A); }
+  if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.elem.push_back({i0, i1}); }
+  if (ctx->profile) cudaEventRecord(prof_event(ctx, &i0), s);
+  if (ctx->nSurf > 0) {
+    const SurfArgs S = surf_args(ctx);
+    if (ctx->energy) LAUNCH((k_surf<true>), ctx->surf_blocks, SURF_BLOCK, s, S);
+    else LAUNCH((k_surf<false>), ctx->surf_blocks, SURF_BLOCK, s, S);
+  }
+  if (ctx->profile) { cudaEventRecord(prof_event(ctx, &i1), s); ctx->prof.node.push_back({i0, i1}); }
+  const bool en_async = ctx->energy && ctx->energy_async && ctx->energy_async_now && !ctx->profile;
+  if (ctx->energy_pending) { cudaStreamWaitEvent(s, ctx->ev_energy_done, 0); ctx->energy_pending = false; }
+  LAUNCH((k_adv<false>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, 0.0, ctx->dthist);
+  if (ctx->energy) {
+    const int nblocks = ctx->nB + ctx->surf_blocks;
+    if (en_async) {
+      cudaEventRecord(ctx->ev_nodes_done, s);
+      cudaStreamWaitEvent(ctx->stream2, ctx->ev_nodes_done, 0);
+      LAUNCH(k_energy, 1, 256, ctx->stream2, ctx->sc, ctx->epart, nblocks, ctx->ehist);
+      cudaEventRecord(ctx->ev_energy_done, ctx->stream2);
+      ctx->energy_pending = true;
+    } else {
+      LAUNCH(k_energy, 1, 256, s, ctx->sc, ctx->epart, nblocks, ctx->ehist);
+    }
+  }
+  ctx->felem_stale = true;
+}
+
 void prof_collect(ftb200_ctx* ctx) {
   ProfEvents& P = ctx->prof;
   for (auto& pr : P.elem) {
@@ -395,6 +578,9 @@ void free_all(ftb200_ctx* c) {
   c->p2p_ready = false;
   if (c->p2p_graph) { cudaGraphExecDestroy(c->p2p_graph); c->p2p_graph = nullptr; }
   dfree(c->d_nref); dfree(c->d_nint); dfree(c->d_ell);
+  dfree(c->b_hdr); dfree(c->b_conn16); dfree(c->b_map16); dfree(c->b_halo); dfree(c->s_ell); dfree(c->s_ovoff); dfree(c->s_ovent);
+  dfree(c->b_part[0]); dfree(c->b_part[1]); dfree(c->b_part[2]);
+  c->brick_ok = false;
   if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
   dfree(c->d_sendNodeIndex); dfree(c->halo_nodes); dfree(c->halo_off); dfree(c->halo_slot); dfree(c->halo_node_idx);
   if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
@@ -493,6 +679,31 @@ int ftb200_upload_mesh(ftb200_ctx* ctx, const double* coordinates, const int* co
 }
 
 long long ftb200_affine_element_count(ftb200_ctx* ctx) { return (ctx && ctx->shape_ok) ? ctx->nE_affine : -1; }
+int ftb200_brick_info(ftb200_ctx* ctx, long long* out8) {
+  if (!ctx || !ctx->shape_ok || !out8) return fail(ctx, FTB200_ERR_INPUT, "brick_info: call shape_functions first");
+  out8[0] = ctx->brick_ok ? ctx->nB : 0; out8[1] = ctx->brick_ok ? ctx->nIntTot : 0; out8[2] = ctx->brick_ok ? ctx->nSurf : 0;
+  out8[3] = ctx->brick_ok ? ctx->nSlots : 0;
+  for (int c = 0; c < 3; ++c) out8[4 + c] = ctx->brick_dims[c];
+  out8[7] = use_brick(ctx) ? 1 : 0;
+  return FTB200_OK;
+}
+int ftb200_brick_maps(ftb200_ctx* ctx, int* brick_of_element, int* interior_brick_of_node) {
+  if (!ctx || !ctx->shape_ok || !ctx->brick_ok) return fail(ctx, FTB200_ERR_INPUT, "brick_maps: no brick decomposition");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<BrickHdr> hdr(ctx->nB);
+  std::vector<int> ref_of(ctx->nE);
+  CK(cudaMemcpy(hdr.data(), ctx->b_hdr, hdr.size() * sizeof(BrickHdr), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ref_of.data(), ctx->ref_of, ref_of.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<int> bint(ctx->nNp, -1);
+  for (int b = 0; b < ctx->nB; ++b) {
+    if (brick_of_element)
+      for (int i = 0; i < hdr[b].nEl; ++i) brick_of_element[ref_of[hdr[b].e0 + i]] = b;
+    for (int i = 0; i < hdr[b].nInt; ++i) bint[hdr[b].ibase + i] = b;
+  }
+  if (interior_brick_of_node)
+    for (int n = 0; n < ctx->nN; ++n) interior_brick_of_node[n] = bint[ctx->h_nint[n]];
+  return FTB200_OK;
+}
 long long ftb200_gauss_point_count(ftb200_ctx* ctx) { return ctx ? (ctx->shape_ok ? ctx->nGP : (ctx->has_tet ? -1 : 8LL * ctx->nE)) : -1; }
 
 int ftb200_upload_mesh_mixed(ftb200_ctx* ctx, const double* coordinates, const int* connectivity, const int* eptr, const int* pid,
@@ -621,11 +832,70 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       ref_of[t] = e; int_of[e] = t;
     }
   }
-  // ---- internal node order: the caller's order, padded to whole node tiles (brick mode: see build_patches) ------
+  // ---- brick mode (ftb200_brick.cuh): a single-partition mesh of parallelepiped hexahedra of one material (1 or 4)
+  //      whose nodes have at most 8 elements.  Elements are renumbered brick by brick (the whole mesh is one run of
+  //      the internal order, so any order inside it is allowed), nodes as [interior nodes by brick | surface nodes by
+  //      owning brick].  Every other mesh keeps the two-kernel step.
+  BrickPlan plan;
+  bool brick = false;
+  {
+    if (const char* ev = getenv("FTB200_BRICK")) ctx->brick_want = atoi(ev) != 0;
+    if (const char* ev = getenv("FTB200_BRICK_DIMS")) {
+      int d[3];
+      if (sscanf(ev, "%d,%d,%d", &d[0], &d[1], &d[2]) == 3 && d[0] > 0 && d[1] > 0 && d[2] > 0 && (long long)d[0] * d[1] * d[2] <= BRICK_NT)
+        for (int c = 0; c < 3; ++c) ctx->brick_dims[c] = d[c];
+    }
+    bool ok = ctx->brick_want && ctx->nranks == 1 && ctx->halo_count == 0 && !ctx->has_tet && nE > 0 && ctx->nE_affine == nE;
+    if (ok) {
+      const int m0 = ctx->h_matid[ctx->h_pid[0]];
+      ok = (m0 == 1 || m0 == 4);
+      for (int e = 0; ok && e < nE; ++e) ok = ctx->h_matid[ctx->h_pid[e]] == m0;
+    }
+    if (ok) {
+      std::vector<unsigned char> deg(nN, 0);
+      for (size_t i = 0; ok && i < 8 * (size_t)nE; ++i) ok = ++deg[ctx->h_conn[i]] <= 8;
+    }
+    if (ok) {
+      plan = plan_bricks(ctx);
+      brick = true;
+      for (int t = 0; t < nE; ++t) { ref_of[t] = plan.elems[t]; int_of[plan.elems[t]] = t; }
+    }
+  }
+  // ---- internal node order: the caller's order (brick mode: interior nodes brick by brick, then the surface nodes
+  //      by owning brick), padded to whole node tiles ------------------------------------------------------------
   const int nNp = std::max(cdiv(nN, NODE_TILE) * NODE_TILE, NODE_TILE);
   ctx->nNp = nNp;
   std::vector<int> nref(nNp, -1), nint(nN, -1);
-  for (int n = 0; n < nN; ++n) { nref[n] = n; nint[n] = n; }
+  std::vector<int> b_ibase, b_nint;
+  int nIntTot = 0;
+  if (brick) {
+    std::vector<int> first(nN, -1);
+    std::vector<char> multi(nN, 0);
+    for (int b = 0; b < plan.nB; ++b)  // ascending brick id: first[] is the lowest brick of a node = its owner
+      for (int i = plan.eoff[b]; i < plan.eoff[b + 1]; ++i)
+        for (int k = 0; k < 8; ++k) {
+          const int nd = ctx->h_conn[8 * (size_t)plan.elems[i] + k];
+          if (first[nd] < 0) first[nd] = b;
+          else if (first[nd] != b) multi[nd] = 1;
+        }
+    b_ibase.assign(plan.nB + 1, 0); b_nint.assign(plan.nB, 0);
+    std::vector<int> scount(plan.nB + 1, 0);
+    for (int n = 0; n < nN; ++n)
+      if (first[n] >= 0) { if (multi[n]) scount[first[n]]++; else b_nint[first[n]]++; }
+    for (int b = 0; b < plan.nB; ++b) b_ibase[b + 1] = b_ibase[b] + b_nint[b];
+    nIntTot = b_ibase[plan.nB];
+    std::vector<int> curI(b_ibase.begin(), b_ibase.end() - 1), curS(plan.nB + 1, 0);
+    { int acc = nIntTot; for (int b = 0; b < plan.nB; ++b) { curS[b] = acc; acc += scount[b]; } curS[plan.nB] = acc; }
+    int orphan = curS[plan.nB];
+    for (int n = 0; n < nN; ++n) {
+      if (first[n] < 0) nint[n] = orphan++;          // node without elements: a surface node with no partial
+      else if (multi[n]) nint[n] = curS[first[n]]++;
+      else nint[n] = curI[first[n]]++;
+    }
+    for (int n = 0; n < nN; ++n) nref[nint[n]] = n;
+  } else {
+    for (int n = 0; n < nN; ++n) { nref[n] = n; nint[n] = n; }
+  }
   ctx->h_nint = nint;
   // ---- shared nodes (internal ids), slots in ascending neighbour order ---------------------------
   std::vector<int> node_h(nNp, -1), halo_nodes, sendIdxInt(ctx->halo_count);
@@ -698,11 +968,81 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
     CK(cudaMemset(ctx->fnet[k], 0, nNp * sizeof(double)));
   }
   ctx->node_blocks = cdiv(nNp, NODE_BLOCK);
+  int epart_blocks = std::max(ctx->node_blocks, cdiv(nN, NODE_BLOCK));
+  if (brick) {
+    // per-brick local numbering: interior nodes first (internal id - ibase), then the surface nodes the brick touches
+    // in ascending internal id; connectivity in local ids, local node -> (element, slot) map in ascending reference
+    // element id, one partial slot per (brick, surface local node); per surface node the slots in ascending brick id
+    const int nB = plan.nB;
+    const int nS = nN - nIntTot;
+    std::vector<BrickHdr> hdr(nB);
+    std::vector<uint16_t> conn16((size_t)nB * 8 * BRICK_NT, 0), map16((size_t)nB * 8 * BRICK_NLMAX, 0xFFFFu);
+    std::vector<int> halo((size_t)nB * BRICK_NLMAX, 0), sell(8 * (size_t)std::max(nS, 1), -1), scnt(std::max(nS, 1), 0);
+    std::vector<std::pair<int, int>> sover;
+    std::vector<int> loc(nNp, -1), surf;
+    std::vector<unsigned char> lcnt(BRICK_NLMAX);
+    long long slot = 0;
+    for (int b = 0; b < nB; ++b) {
+      const int e0 = plan.eoff[b], nEl = plan.eoff[b + 1] - e0;
+      surf.clear();
+      for (int i = 0; i < nEl; ++i)
+        for (int k = 0; k < 8; ++k) {
+          const int g = nint[ctx->h_conn[8 * (size_t)plan.elems[e0 + i] + k]];
+          if (g >= nIntTot && loc[g] != -2 - b) { loc[g] = -2 - b; surf.push_back(g); }
+        }
+      std::sort(surf.begin(), surf.end());
+      const int nInt_b = b_nint[b], nLoc = nInt_b + (int)surf.size();
+      if (nEl > BRICK_NT || nLoc > BRICK_NLMAX) return fail(ctx, FTB200_ERR_INPUT, "brick %d does not fit (%d elements, %d nodes)", b, nEl, nLoc);
+      for (size_t i = 0; i < surf.size(); ++i) { loc[surf[i]] = nInt_b + (int)i; halo[(size_t)b * BRICK_NLMAX + i] = surf[i]; }
+      std::fill(lcnt.begin(), lcnt.end(), 0);
+      for (int i = 0; i < nEl; ++i)
+        for (int k = 0; k < 8; ++k) {
+          const int g = nint[ctx->h_conn[8 * (size_t)plan.elems[e0 + i] + k]];
+          const int l = g < nIntTot ? g - b_ibase[b] : loc[g];
+          conn16[((size_t)b * 8 + k) * BRICK_NT + i] = (uint16_t)l;
+          map16[((size_t)b * 8 + lcnt[l]++) * BRICK_NLMAX + l] = (uint16_t)(i * 8 + k);
+        }
+      hdr[b] = BrickHdr{e0, nEl, b_ibase[b], nInt_b, nLoc, (int)slot, 0, 0};
+      for (size_t i = 0; i < surf.size(); ++i) {
+        const int sidx = surf[i] - nIntTot;
+        const int q = scnt[sidx]++;
+        if (q < 8) sell[(size_t)q * nS + sidx] = (int)(slot + (long long)i);
+        else sover.push_back({sidx, (int)(slot + (long long)i)});
+      }
+      slot += (long long)surf.size();
+      if (slot > 0x7fffff00LL) return fail(ctx, FTB200_ERR_INPUT, "too many surface partials for 32-bit slots");
+    }
+    ctx->nB = nB; ctx->nIntTot = nIntTot; ctx->nSurf = nS; ctx->nSlots = slot;
+    ctx->surf_blocks = cdiv(nS, SURF_BLOCK);
+    epart_blocks = std::max(epart_blocks, nB + ctx->surf_blocks);
+    if ((rc = dalloc(ctx, &ctx->b_hdr, nB)) || (rc = dalloc(ctx, &ctx->b_conn16, conn16.size())) ||
+        (rc = dalloc(ctx, &ctx->b_map16, map16.size())) || (rc = dalloc(ctx, &ctx->b_halo, halo.size())) ||
+        (rc = dalloc(ctx, &ctx->s_ell, sell.size())) || (rc = dalloc(ctx, &ctx->b_part[0], (size_t)slot + 1)) ||
+        (rc = dalloc(ctx, &ctx->b_part[1], (size_t)slot + 1)) || (rc = dalloc(ctx, &ctx->b_part[2], (size_t)slot + 1)))
+      return rc;
+    CK(cudaMemcpy(ctx->b_hdr, hdr.data(), hdr.size() * sizeof(BrickHdr), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->b_conn16, conn16.data(), conn16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->b_map16, map16.data(), map16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->b_halo, halo.data(), halo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->s_ell, sell.data(), sell.size() * sizeof(int), cudaMemcpyHostToDevice));
+    for (int c = 0; c < 3; ++c) CK(cudaMemset(ctx->b_part[c], 0, ((size_t)slot + 1) * sizeof(double)));
+    if (!sover.empty()) {
+      std::stable_sort(sover.begin(), sover.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b2) { return a.first < b2.first; });
+      std::vector<int> ooff(nS + 1, 0), oent(sover.size());
+      for (auto& pr : sover) ooff[pr.first + 1]++;
+      for (int i = 0; i < nS; ++i) ooff[i + 1] += ooff[i];
+      for (size_t i = 0; i < sover.size(); ++i) oent[i] = sover[i].second;
+      if ((rc = dalloc(ctx, &ctx->s_ovoff, ooff.size())) || (rc = dalloc(ctx, &ctx->s_ovent, oent.size()))) return rc;
+      CK(cudaMemcpy(ctx->s_ovoff, ooff.data(), ooff.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(ctx->s_ovent, oent.data(), oent.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    ctx->brick_ok = true;
+  }
   if ((rc = dalloc(ctx, &ctx->m, nNp)) || (rc = dalloc(ctx, &ctx->flags, nNp)) || (rc = dalloc(ctx, &ctx->conn, 8 * (size_t)nE)) ||
       (rc = dalloc(ctx, &ctx->pid, nE)) || (rc = dalloc(ctx, &ctx->ref_of, nE)) || (rc = dalloc(ctx, &ctx->eflag, nE)) ||
       (rc = dalloc(ctx, &ctx->felem, 24 * 32 * (size_t)cdiv(nE, 32))) || (rc = dalloc(ctx, &ctx->mp, mp.size())) ||
       (rc = dalloc(ctx, &ctx->node_off, nNp + 1)) || (rc = dalloc(ctx, &ctx->node_ent, 8 * (size_t)nE)) ||
-      (rc = dalloc(ctx, &ctx->sc, 1)) || (rc = dalloc(ctx, &ctx->epart, 3 * (size_t)std::max(ctx->node_blocks, cdiv(nN, NODE_BLOCK)))) ||
+      (rc = dalloc(ctx, &ctx->sc, 1)) || (rc = dalloc(ctx, &ctx->epart, 3 * (size_t)epart_blocks)) ||
       (rc = dalloc(ctx, &ctx->out3, 16)) || (rc = dalloc(ctx, &ctx->d_istage, 3 * (size_t)nN)) ||
       (rc = dalloc(ctx, &ctx->d_detmin, 1)) || (rc = dalloc(ctx, &ctx->d_nonpos, 1)) ||
       (rc = dalloc(ctx, &ctx->d_nref, nNp)) || (rc = dalloc(ctx, &ctx->d_nint, nN)) || (rc = dalloc(ctx, &ctx->d_ell, 8 * (size_t)nNp)))
@@ -838,6 +1178,7 @@ static int legacy_force_local(ftb200_ctx* ctx, const double* displacements, cons
   }
   if (ctx->has_visco) LAUNCH(k_prony, 1, 128, ctx->stream, ctx->mp, ctx->nPID, dt);
   launch_elem<true, false>(ctx, ctx->stream, 0, ctx->nE, 1);
+  ctx->felem_stale = false;
   return 0;
 }
 
@@ -959,6 +1300,7 @@ int ftb200_get_state(ftb200_ctx* ctx, double* displacements, double* velocities,
   if (!ctx || !ctx->shape_ok) return fail(ctx, FTB200_ERR_INPUT, "get_state: setup incomplete");
   CK(cudaSetDevice(ctx->device));
   int rc;
+  double* const* fi_src = ctx->fi;
   if (fi || f_net) {  // lazily rebuilt from the element forces of the last evaluation
     if (ctx->p2p_ready && ctx->halo_count && !ctx->halo_recv_cur) {
       unsigned long long seq = 0;
@@ -966,10 +1308,21 @@ int ftb200_get_state(ftb200_ctx* ctx, double* displacements, double* velocities,
       CK(cudaStreamSynchronize(ctx->stream));
       if (seq > 0) ctx->halo_recv_cur = p2p_recv(ctx->p2p_window, ctx->halo_count, (int)((seq - 1) & 1ULL));
     }
-    const NodeArgs N = node_args(ctx, ctx->halo_recv_cur);
+    NodeArgs N = node_args(ctx, ctx->halo_recv_cur);
+    if (ctx->felem_stale) {
+      // the brick-fused step keeps the element forces on the SM: evaluate them once more (materials 1 and 4 carry no
+      // history).  The gather goes to the du planes (unused by that step): fi holds the sums the energy check continues
+      // from, in the brick step's own summation order, and a read-back must not perturb a running calculation
+      launch_elem<true, false>(ctx, ctx->stream, 0, ctx->nE, 1);
+      ctx->felem_stale = false;
+    }
+    if (use_brick(ctx)) {
+      for (int k = 0; k < 3; ++k) N.fi[k] = ctx->du[k];
+      fi_src = ctx->du;
+    }
     LAUNCH(k_gather_force, ctx->node_blocks, NODE_BLOCK, ctx->stream, N, ctx->fnet[0], ctx->fnet[1], ctx->fnet[2]);
   }
-  double* const* src[5] = {ctx->u, ctx->v, ctx->a, ctx->fi, ctx->fnet};
+  double* const* src[5] = {ctx->u, ctx->v, ctx->a, fi_src, ctx->fnet};
   double* dst[5] = {displacements, velocities, accelerations, fi, f_net};
   for (int i = 0; i < 5; ++i)
     if (dst[i]) {
@@ -1079,6 +1432,7 @@ int ftb200_explicit_begin_force(ftb200_ctx* ctx, double* send_dev) {
   LAUNCH((k_adv<true>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, ctx->Time0, ctx->dthist);
   // GetForce() (:88)
   launch_elem<true, false>(ctx, s, 0, ctx->nE, 1);
+  ctx->felem_stale = false;
   if (ctx->halo_count) {
     // partial sums go to the f_net planes (scratch in the resident path): fi still holds the previous
     // step's total, which the energy check needs as fi_prev
@@ -1121,13 +1475,17 @@ static void join_energy(ftb200_ctx* ctx) {
 }
 
 static int build_graph(ftb200_ctx* ctx) {
-  const int sig = ctx->energy | (ctx->has_fe ? 2 : 0) | (ctx->energy_async ? 8 : 0) | (ctx->injury ? 64 : 0) | (ctx->rigid ? 128 : 0);
+  const int sig = ctx->energy | (ctx->has_fe ? 2 : 0) | (ctx->energy_async ? 8 : 0) | (ctx->injury ? 64 : 0) | (ctx->rigid ? 128 : 0) |
+                  (use_brick(ctx) ? 256 : 0);
   if (ctx->graph && ctx->graph_energy == sig) return 0;
   if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
   cudaGraph_t g = nullptr;
   const long long before = ctx->launches;
   CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-  for (int i = 0; i < GRAPH_STEPS; ++i) launch_step(ctx, nullptr);
+  for (int i = 0; i < GRAPH_STEPS; ++i) {
+    if (use_brick(ctx)) launch_step_brick(ctx);
+    else launch_step(ctx, nullptr);
+  }
   join_energy(ctx);  // the helper stream rejoins before the capture ends
   cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
   ctx->launches = before;  // captured, not launched
@@ -1225,13 +1583,15 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
   if (steps <= 0) return FTB200_OK;
   cudaStream_t s = ctx->stream;
   LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
-  {
+  const bool brick = use_brick(ctx);
+  if (!brick) {  // (the brick-fused step starts each step itself)
     const NodeArgs N = node_args(ctx, nullptr);
     if (ctx->rigid) LAUNCH(k_rigid_step, 1, 32, s, ctx->sc, ctx->rigid, 1);
     if (ctx->energy) LAUNCH((k_node<false, true, false, true>), ctx->node_blocks, NODE_BLOCK, s, N);
     else LAUNCH((k_node<false, true, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   }
-  const int per_step = 3 + (ctx->energy ? 1 : 0) + (ctx->injury ? INJ_LAUNCHES : 0) + (ctx->rigid ? 1 : 0);
+  const int per_step = brick ? (2 + (ctx->nSurf > 0 ? 1 : 0) + (ctx->energy ? 1 : 0))
+                             : 3 + (ctx->energy ? 1 : 0) + (ctx->injury ? INJ_LAUNCHES : 0) + (ctx->rigid ? 1 : 0);
   long long left = steps;
   const bool use_graph = !ctx->profile;  // built on the first run (warm-up), whatever its length
   if (use_graph) {
@@ -1246,10 +1606,12 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
       ctx->launches += (long long)per_step * GRAPH_STEPS;
       left -= GRAPH_STEPS;
     } else {
-      launch_step(ctx, nullptr);
+      if (brick) launch_step_brick(ctx);
+      else launch_step(ctx, nullptr);
       left--;
     }
   }
+  if (brick) ctx->felem_stale = true;
   join_energy(ctx);
   CK(cudaGetLastError());
   return FTB200_OK;

@@ -999,6 +999,144 @@ FTB_HD int hex8_element_affine_in(const In& in, int mat, const double* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// The parallelepiped element once more, for the brick kernel (k_brick): the same arithmetic as hex8_element_affine_in
+// with a 45-slot scratch.  cof(8 J0)[j][c] = det (8 J0)^-1[c][j], so only the inverse is kept and the determinant is
+// folded into the quadrature weights of the final butterfly (one multiplication per force mode instead of nine
+// scratch slots).  Differs from hex8_element_affine_in by rounding only (tests/test_element_math_cpu.py pins 1e-13).
+//
+// Scratch layout (45 doubles): 36 dU/dxi column entries (FTB_ACOL), then (8 J0)^-1 (9).
+#define FTB_BJI(c, j) (36 + (c) * 3 + (j))
+// staging slots of the reference nodes (nodes 0, 1, 3, 4): component 0 waits in column slots of component 1 (written
+// only after component 0 has been consumed), components 1 and 2 in the slots of the inverse (written last)
+#define FTB_BSTAGE_X(kk, c) ((c) == 0 ? (1 + 3 * (kk)) : (36 + ((c) - 1) * 4 + (kk)))
+#define FTB_BRICK_SLOTS 45
+
+struct LocalScratchBrick {
+  double v[FTB_BRICK_SLOTS];
+  FTB_HD void st(int i, double x) { v[i] = x; }
+  FTB_HD double ld(int i) const { return v[i]; }
+  FTB_HD double ld_inloop(int i) const { return v[i]; }
+};
+
+template <int MATSEL, class In, class Hist, class Out, class Scratch>
+FTB_HD int hex8_element_brick_in(const In& in, int mat, const double* __restrict__ mp, const bool updHist,
+                                 const Hist& hist, const Out& out, Scratch& S, double fe[8][3], double* dtElem) {
+  if (MATSEL >= 0) mat = MATSEL;
+  const double a = FTB_GP_A, a2 = FTB_GP_A * FTB_GP_A;
+  int status = 0;
+  double dtk = 0.0, det;
+  {
+    double xm[7][3];
+    double J0[3][3];  // 8 dX/dxi = 4 x edge vectors (exact scaling)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double x[4], nu[8], gU[7];
+      in.getX(c, x);
+      J0[c][0] = 4.0 * (x[1] - x[0]);
+      J0[c][1] = 4.0 * (x[2] - x[0]);
+      J0[c][2] = 4.0 * (x[3] - x[0]);
+      in.getU(c, nu);
+      hex_modes(nu, gU);
+      xm[0][c] = J0[c][0] + gU[0]; xm[1][c] = J0[c][1] + gU[1]; xm[2][c] = J0[c][2] + gU[2];
+      xm[3][c] = gU[3]; xm[4][c] = gU[4]; xm[5][c] = gU[5]; xm[6][c] = gU[6];
+      const double U12 = a * gU[3], U23 = a * gU[4], U13 = a * gU[5], U123 = a2 * gU[6];
+      {
+        const double A[3] = {gU[0], gU[1], gU[2]}, B[3] = {U12, U12, U13}, C[3] = {U13, U23, U23};
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const double ad = A[t] + U123, am = A[t] - U123, bc = B[t] + C[t], bm = B[t] - C[t];
+          S.st(FTB_ACOL(t, 3, c), ad + bc);
+          S.st(FTB_ACOL(t, 0, c), ad - bc);
+          S.st(FTB_ACOL(t, 1, c), am + bm);
+          S.st(FTB_ACOL(t, 2, c), am - bm);
+        }
+      }
+    }
+    double cJ[3][3];
+    cofactor3(J0, cJ);
+    det = J0[0][0] * cJ[0][0] + J0[0][1] * cJ[0][1] + J0[0][2] * cJ[0][2];  // 512 detJ0
+    if (!(det > 0.0)) status |= 2;
+    const double rdet = 1.0 / det;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) S.st(FTB_BJI(c, j), cJ[j][c] * rdet);  // J0^-1[c][j] = cof[j][c] / det
+    dtk = det / (512.0 * hex_face_amax(xm) * mp[MP_CE]);
+  }
+  double vsum = 0.0;
+  double phi[7][3];
+#pragma unroll
+  for (int m = 0; m < 7; ++m)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) phi[m][c] = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int gp = 0; gp < 8; ++gp) {
+    const int b1 = ((gp + 1) >> 1) & 1, b2 = (gp >> 1) & 1, b3 = ((gp >> 2) & 1) ^ 1;
+    const double s1 = b1 ? 1.0 : -1.0, s2 = b2 ? 1.0 : -1.0, s3 = b3 ? 1.0 : -1.0;
+    const double s23 = s2 * s3, s13 = s1 * s3, s12 = s1 * s2;
+    const int qx = b2 + 2 * b3, qe = b1 + 2 * b3, qz = b1 + 2 * b2;
+    double F[3][3];
+    {
+      double Ji[3][3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Ji[c][j] = S.ld_inloop(FTB_BJI(c, j));
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double u0 = S.ld(FTB_ACOL(0, qx, i)), u1 = S.ld(FTB_ACOL(1, qe, i)), u2 = S.ld(FTB_ACOL(2, qz, i));
+#pragma unroll
+        for (int j = 0; j < 3; ++j) F[i][j] = fma(u0, Ji[0][j], fma(u1, Ji[1][j], fma(u2, Ji[2][j], (i == j ? 1.0 : 0.0))));
+      }
+    }
+    double cF[3][3];
+    cofactor3(F, cF);
+    const double J = F[0][0] * cF[0][0] + F[0][1] * cF[0][1] + F[0][2] * cF[0][2];
+    if (!(J > 0.0) && mat != 0) status |= 4;
+    vsum += J;
+    double P[3][3], Sv[6];
+    GpHistory h;
+    if (mat == 5) hist.load(gp, h);
+    status |= material_P<Out::want_S>(mat, F, cF, J, mp, &h, updHist, P, Sv);
+    if (mat == 5 && updHist) hist.store(gp, h);
+    if (Out::enabled) out.put(gp, F, J, Sv);
+    double Ji[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Ji[c][j] = S.ld_inloop(FTB_BJI(c, j));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // Q / det = P J0^-T
+      const double Q0 = P[i][0] * Ji[0][0] + P[i][1] * Ji[0][1] + P[i][2] * Ji[0][2];
+      const double Q1 = P[i][0] * Ji[1][0] + P[i][1] * Ji[1][1] + P[i][2] * Ji[1][2];
+      const double Q2 = P[i][0] * Ji[2][0] + P[i][1] * Ji[2][1] + P[i][2] * Ji[2][2];
+      phi[0][i] += Q0;
+      phi[1][i] += Q1;
+      phi[2][i] += Q2;
+      phi[3][i] = fma(s2, Q0, fma(s1, Q1, phi[3][i]));
+      phi[4][i] = fma(s3, Q1, fma(s2, Q2, phi[4][i]));
+      phi[5][i] = fma(s3, Q0, fma(s1, Q2, phi[5][i]));
+      phi[6][i] = fma(s23, Q0, fma(s13, Q1, fma(s12, Q2, phi[6][i])));
+    }
+  }
+  *dtElem = vsum * dtk;
+  const double w0 = det * (1.0 / 512.0), w1 = det * (a / 512.0), w2 = det * (a2 / 512.0);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double p[7], f[8];
+    p[0] = phi[0][c] * w0; p[1] = phi[1][c] * w0; p[2] = phi[2][c] * w0;
+    p[3] = phi[3][c] * w1; p[4] = phi[4][c] * w1; p[5] = phi[5][c] * w1;
+    p[6] = phi[6][c] * w2;
+    hex_modes_to_nodes(p, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) fe[k][c] = f[k];
+  }
+  return status;
+}
+
+// ---------------------------------------------------------------------------------------------
 // C3D4: the reference's other solid element.  One Gauss point at the centroid with weight 1/6
 // (GaussQuadrature3D.cpp:62-69), N = (xi, eta, zeta, 1 - xi - eta - zeta), detJ = |det| (ShapeFunction_C3D4.cpp:70).
 // Same algebra as one Gauss point of the hexahedron with the edge vectors x_k - x_3 as Jacobian columns:

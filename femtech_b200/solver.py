@@ -134,6 +134,21 @@ class FemTech:
         """Hexahedra integrated by the parallelepiped kernel (after ShapeFunctions)."""
         return int(self.L.ftb200_affine_element_count(self._h))
 
+    @property
+    def brick_info(self):
+        """Brick decomposition of the brick-fused step (after ShapeFunctions): dict, bricks = 0 when the two-kernel step is used."""
+        out = (C.c_longlong * 8)()
+        self._check(self.L.ftb200_brick_info(self._h, out))
+        return {"bricks": int(out[0]), "interior_nodes": int(out[1]), "surface_nodes": int(out[2]), "partial_slots": int(out[3]),
+                "dims": (int(out[4]), int(out[5]), int(out[6])), "active": bool(out[7])}
+
+    def brick_maps(self):
+        """(brick of every element, brick that finishes every node or -1 for a surface node), caller's numbering."""
+        be = np.zeros(self.nelements, dtype=np.int32)
+        bn = np.zeros(self.nNodes, dtype=np.int32)
+        self._check(self.L.ftb200_brick_maps(self._h, be.ctypes.data_as(_ip), bn.ctypes.data_as(_ip)))
+        return be, bn
+
     # --- one-time setup ----------------------------------------------------------------------------
     def ShapeFunctions(self):
         md = C.c_double()

@@ -69,6 +69,15 @@ long long ftb200_gauss_point_count(ftb200_ctx *ctx);
  * (ShapeFunction_C3D8.cpp:60-115 stores it per point); FTB200_AFFINE=0 in the environment sends them through the
  * general kernel.  Reported by bench.py next to the throughput. */
 long long ftb200_affine_element_count(ftb200_ctx *ctx);
+/* Brick decomposition of the brick-fused step (valid after ftb200_shape_functions): out8 = bricks, interior nodes
+ * (finished inside the brick's thread block), surface nodes (finished by the second, thin pass), partial-sum slots,
+ * brick dimensions in elements (3), 1 if the resident loop will take the brick-fused step.  bricks = 0: the mesh does not
+ * qualify (several partitions, tetrahedra, distorted hexahedra, materials other than 1 and 4) or FTB200_BRICK=0, and
+ * the two-kernel step (element forces through HBM, GetForce_3D.cpp:15-51 as two passes) is used. */
+int ftb200_brick_info(ftb200_ctx *ctx, long long *out8);
+/* The decomposition itself, for inspection and tests: brick_of_element[nElements] and, per node, the brick that finishes
+ * it or -1 for a surface node (caller's numbering).  Either pointer may be NULL. */
+int ftb200_brick_maps(ftb200_ctx *ctx, int *brick_of_element, int *interior_brick_of_node);
 /* materialID, properties: src/io/input/ReadMaterials.cpp:8-138 */
 int ftb200_upload_materials(ftb200_ctx *ctx, const int *materialID, const double *properties, int nPID);
 /* sendProcessID / sendNeighbourCountCum / sendNodeIndex: PartitionMesh.cpp:566-1128 */

@@ -104,6 +104,42 @@ extern "C" int harness_element_affine_staged(const double* X24, const double* U2
   return st;
 }
 
+// hex8_element_brick_in (the element function of k_brick) with the kernel's staging plan replayed: the reference nodes
+// 0, 1, 3, 4 wait in FTB_BSTAGE_X slots of a poisoned scratch, the displacements come from a node-indexed table
+namespace {
+struct HostStagedBrick {
+  const double* v;       // scratch
+  const double* utab;    // [3][8] component-major "shared-memory" displacement table
+  void getX(const int c, double x[4]) const {
+    for (int k = 0; k < 4; ++k) x[k] = v[FTB_BSTAGE_X(k, c)];
+  }
+  void getU(const int c, double nu[8]) const {
+    for (int k = 0; k < 8; ++k) nu[k] = utab[8 * c + k];
+  }
+};
+}  // namespace
+extern "C" int harness_element_brick(const double* X24, const double* U24, int mat, const double* mp, double* hist144,
+                                     int updHist, double* fe24, double* dtElem, double* F72, double* detF8, double* pk2_48) {
+  double X[8][3], fe[8][3];
+  for (int k = 0; k < 8; ++k)
+    for (int c = 0; c < 3; ++c) X[k][c] = X24[3 * k + c];
+  if (!ftb::hex8_is_affine(X)) return -1;
+  const int nx[4] = {0, 1, 3, 4};
+  ftb::LocalScratchBrick sc;
+  for (int i = 0; i < FTB_BRICK_SLOTS; ++i) sc.v[i] = 1e300;  // poison
+  double utab[24];
+  for (int c = 0; c < 3; ++c) {
+    for (int k = 0; k < 8; ++k) utab[8 * c + k] = U24[3 * k + c];
+    for (int k = 0; k < 4; ++k) sc.v[FTB_BSTAGE_X(k, c)] = X24[3 * nx[k] + c];
+  }
+  HostHist hh{hist144};
+  HostOut ho{F72, detF8, pk2_48};
+  int st = ftb::hex8_element_brick_in<-1>(HostStagedBrick{sc.v, utab}, mat, mp, updHist != 0, hh, ho, sc, fe, dtElem);
+  for (int k = 0; k < 8; ++k)
+    for (int c = 0; c < 3; ++c) fe24[3 * k + c] = fe[k][c];
+  return st;
+}
+
 // largest face area of a hexahedron given the 8 CURRENT nodal positions: the filtered form the kernels use and the
 // every-face form it replaces
 extern "C" void harness_face_amax(const double* x24, double* out2) {

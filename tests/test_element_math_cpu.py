@@ -32,6 +32,8 @@ def harness():
     L.harness_element_affine.restype = C.c_int
     L.harness_element_affine_staged.argtypes = L.harness_element.argtypes
     L.harness_element_affine_staged.restype = C.c_int
+    L.harness_element_brick.argtypes = L.harness_element.argtypes
+    L.harness_element_brick.restype = C.c_int
     L.harness_face_amax.argtypes = [_dp, _dp]
     L.harness_mass.argtypes = [_dp, C.c_double, _dp]
     L.harness_mass.restype = C.c_double
@@ -319,6 +321,11 @@ def test_affine_hexahedron_path_equals_general_path(harness, mat):
         hs = h0.copy()
         ss, fs, dts_, Fs, dFs, pks = _call_elem(harness.harness_element_affine_staged, X, U, mat, mp, hs)
         assert ss == 0 and np.array_equal(fs, fa) and dts_ == dta and np.array_equal(Fs, Fa) and np.array_equal(hs, ha)
+        # the brick kernel's variant (45 scratch slots, det J0 folded into the weights): rounding differences only
+        hb = h0.copy()
+        sb, fb, dtb, Fb, dFb, pkb = _call_elem(harness.harness_element_brick, X, U, mat, mp, hb)
+        assert sb == 0 and np.array_equal(Fb, Fa) and np.array_equal(pkb, pka) and dtb == dta and np.array_equal(hb, ha)
+        assert np.abs(fb - fa).max() <= 1e-14 * np.abs(fa).max()
         assert np.abs(Fa - Fg).max() < 1e-14
         assert np.abs(dFa - dFg).max() < 1e-14
         assert np.abs(fa - fg).max() <= 1e-13 * np.abs(fg).max()
