@@ -44,9 +44,11 @@ struct BrickHdr {
 
 struct BrickArgs {
   const BrickHdr* hdr;
-  const uint16_t* conn16;  // [nB][8][BRICK_NT] local node index of C3D8 node k of local element t
+  const uint16_t* conn16;  // [nB][BRICK_NT][8] local node index of C3D8 node k of local element t (one 16-byte load per thread)
+  const int* xid;          // [nE][4] internal node ids of the reference nodes 0, 1, 3, 4 of every element (internal element order)
   const int* halo;         // [nB][BRICK_NLMAX] internal node ids of the surface local nodes
-  const uint16_t* map16;   // [nB][8][BRICK_NLMAX] local node -> (local element * 8 + slot), 0xFFFF = none; ascending reference element id
+  const uint16_t* map16;   // [nB][8][BRICK_NLMAX] local node -> scratch word 3 * slot * BRICK_NT + local element of the
+                           // force a local element puts on it, 0xFFFF = none; ascending reference element id
   const double* X[3];
   double* u[3];
   double* v[3];
@@ -65,8 +67,7 @@ struct BrickArgs {
   int store_fi;
 };
 
-constexpr size_t BRICK_SMEM_BYTES = (size_t)FTB_BRICK_SLOTS * BRICK_NT * 8 + 3 * BRICK_NLMAX * 8 + 8 * BRICK_NT * 2 +
-                                    8 * BRICK_NLMAX * 2 + BRICK_NLMAX * 4 + 16 + 3 * (BRICK_NT / 32) * 8;
+constexpr size_t BRICK_SMEM_BYTES = (size_t)FTB_BRICK_SLOTS * BRICK_NT * 8 + 3 * BRICK_NLMAX * 8 + 8 * BRICK_NLMAX * 2 + 16;
 
 // ---- bulk asynchronous copy global -> shared, completion on an mbarrier (SASS: UBLKCP / SYNCS) ----
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -190,87 +191,77 @@ __global__ void __launch_bounds__(BRICK_NT, 2) k_brick(const BrickArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* scr = reinterpret_cast<double*>(smem_raw);                          // [45][NT]
   double* ust = scr + FTB_BRICK_SLOTS * BRICK_NT;                            // [3][NLMAX]
-  uint16_t* s_conn = reinterpret_cast<uint16_t*>(ust + 3 * BRICK_NLMAX);     // [8][NT]
-  uint16_t* s_map = s_conn + 8 * BRICK_NT;                                   // [8][NLMAX]
-  int* s_halo = reinterpret_cast<int*>(s_map + 8 * BRICK_NLMAX);             // [NLMAX]
-  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_halo + BRICK_NLMAX);  // [2]
-  double* s_red = reinterpret_cast<double*>(s_bar + 2);                      // [3][NT / 32]
+  uint16_t* s_map = reinterpret_cast<uint16_t*>(ust + 3 * BRICK_NLMAX);      // [8][NLMAX]
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_map + 8 * BRICK_NLMAX);  // [1]
 
   const DevScalars* sc = A.sc;
   const int tid = threadIdx.x;
   const int b = blockIdx.x;
   const BrickHdr H = A.hdr[b];
-  if (sc->last | sc->done) return;
+  const int lastdone = sc->last | sc->done;
+  const StepTimes T = step_times(sc);
+  const double* bc_rate = sc->bc_rate;  // read only by nodes that carry a boundary-condition kind
+  if (lastdone) return;
+  // the local node -> (element, slot) map is needed by the epilogue only: one bulk copy, waited for after the elements
   if (tid == 0) {
     mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const unsigned nh = (unsigned)(((H.nLoc - H.nInt) * 4 + 15) & ~15);
-    mbar_expect_tx(&s_bar[0], 8 * BRICK_NT * 2 + nh);
-    bulk_g2s(s_conn, A.conn16 + (size_t)b * 8 * BRICK_NT, 8 * BRICK_NT * 2, &s_bar[0]);
-    if (nh) bulk_g2s(s_halo, A.halo + (size_t)b * BRICK_NLMAX, nh, &s_bar[0]);
-    mbar_expect_tx(&s_bar[1], 8 * BRICK_NLMAX * 2);
-    bulk_g2s(s_map, A.map16 + (size_t)b * 8 * BRICK_NLMAX, 8 * BRICK_NLMAX * 2, &s_bar[1]);
+    mbar_expect_tx(&s_bar[0], 8 * BRICK_NLMAX * 2);
+    bulk_g2s(s_map, A.map16 + (size_t)b * 8 * BRICK_NLMAX, 8 * BRICK_NLMAX * 2, &s_bar[0]);
   }
-  // element data that does not depend on the metadata
+  // ---- prologue: everything that depends on the header only is requested at once --------------------------------
   const bool has_el = tid < H.nEl;
   const int e = H.e0 + tid;
   int p = 0;
   unsigned skip = 0;
-  if (has_el) { p = __ldg(A.pid + e); skip = __ldg(A.eflag + e); }
-  const StepTimes T = step_times(sc);
-  const double* bc_rate = sc->bc_rate;  // read only by nodes that carry a boundary-condition kind
-  __syncthreads();  // the barriers are initialised
-  // ---- prologue: START of the step for the brick's local nodes; interior nodes need no index list ------------------
+  uint4 cw = make_uint4(0, 0, 0, 0);   // local node ids of the element, two per word
+  int4 xg = make_int4(0, 0, 0, 0);     // internal ids of its reference nodes 0, 1, 3, 4
+  if (has_el) {
+    cw = __ldg(reinterpret_cast<const uint4*>(A.conn16) + (size_t)b * BRICK_NT + tid);
+    xg = __ldg(reinterpret_cast<const int4*>(A.xid) + e);
+    p = __ldg(A.pid + e);
+    skip = __ldg(A.eflag + e);
+  }
   {
-    double uu[BRICK_NODE_TRIPS][3], vv[BRICK_NODE_TRIPS][3], aa[BRICK_NODE_TRIPS][3];
-    unsigned fl[BRICK_NODE_TRIPS];
     int g[BRICK_NODE_TRIPS];
-    bool waited = false;
 #pragma unroll
     for (int r = 0; r < BRICK_NODE_TRIPS; ++r) {
       const int l = tid + r * BRICK_NT;
       g[r] = -1;
-      if (l < H.nLoc) {
-        if (l < H.nInt) {
-          g[r] = H.ibase + l;
-        } else {
-          if (!waited) { mbar_wait(&s_bar[0], 0); waited = true; }
-          g[r] = s_halo[l - H.nInt];
-        }
+      if (l < H.nLoc) g[r] = l < H.nInt ? H.ibase + l : __ldg(A.halo + (size_t)b * BRICK_NLMAX + (l - H.nInt));
+    }
+    if (has_el) {  // the element's reference nodes 0, 1, 3, 4: global -> scratch, no registers
+      const int gx[4] = {xg.x, xg.y, xg.z, xg.w};
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cp_async8(scr + FTB_BSTAGE_X(kk, c) * BRICK_NT + tid, A.X[c] + gx[kk]);
+    }
+    double uu[BRICK_NODE_TRIPS][3], vv[BRICK_NODE_TRIPS][3], aa[BRICK_NODE_TRIPS][3];
+    unsigned fl[BRICK_NODE_TRIPS];
+#pragma unroll
+    for (int r = 0; r < BRICK_NODE_TRIPS; ++r)
+      if (g[r] >= 0) {
         fl[r] = A.flags[g[r]];
 #pragma unroll
         for (int c = 0; c < 3; ++c) { uu[r][c] = A.u[c][g[r]]; vv[r][c] = A.v[c][g[r]]; aa[r][c] = A.a[c][g[r]]; }
       }
-    }
-    if (!waited) mbar_wait(&s_bar[0], 0);
-    // the element's reference nodes 0, 1, 3, 4: global -> scratch, no registers
-    unsigned lnw[4] = {0, 0, 0, 0};
-    if (has_el) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) lnw[k >> 1] |= (unsigned)s_conn[k * BRICK_NT + tid] << (16 * (k & 1));
-      const int kx[4] = {0, 1, 3, 4};
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const int l = (lnw[kx[kk] >> 1] >> (16 * (kx[kk] & 1))) & 0xFFFF;
-        const int gn = l < H.nInt ? H.ibase + l : s_halo[l - H.nInt];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) cp_async8(scr + FTB_BSTAGE_X(kk, c) * BRICK_NT + tid, A.X[c] + gn);
-      }
-    }
+    // START of the step for the brick's local nodes
 #pragma unroll
     for (int r = 0; r < BRICK_NODE_TRIPS; ++r) {
       const int l = tid + r * BRICK_NT;
-      if (l < H.nLoc) {
+      if (g[r] >= 0) {
         double un[3];
         node_start_u(fl[r], T, bc_rate, uu[r], vv[r], aa[r], un);
 #pragma unroll
         for (int c = 0; c < 3; ++c) ust[c * BRICK_NLMAX + l] = un[c];
       }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();
-    // ---- elements ------------------------------------------------------------------------------------------------
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  // ---- elements ----------------------------------------------------------------------------------------------------
+  {
     double dte = 1e300;
     int status = 0;
     if (has_el) {
@@ -278,7 +269,7 @@ __global__ void __launch_bounds__(BRICK_NT, 2) k_brick(const BrickArgs A) {
       double fe[8][3];
       double d;
       SmemScratchBrick S{scr + tid};
-      BrickIn in{scr + tid, ust, {lnw[0], lnw[1], lnw[2], lnw[3]}};
+      BrickIn in{scr + tid, ust, {cw.x, cw.y, cw.z, cw.w}};
       status = hex8_element_brick_in<MATSEL>(in, MATSEL, mp, true, NoHistory(), NoOutput(), S, fe, &d);
       dte = skip ? 1e300 : d;
 #pragma unroll
@@ -295,54 +286,55 @@ __global__ void __launch_bounds__(BRICK_NT, 2) k_brick(const BrickArgs A) {
     if ((tid & 31) == 0) atomicMin(&A.sc->dtmin_bits, bits);
     if (status) atomicOr(&A.sc->status, status);
   }
-  mbar_wait(&s_bar[1], 0);
+  mbar_wait(&s_bar[0], 0);
   __syncthreads();
   // ---- epilogue: assemble the brick's contributions; finish the interior nodes, park the surface partials -------------
+  // surface nodes: one thread each, a coalesced store of the partial sum
+  for (int l = H.nInt + tid; l < H.nLoc; l += BRICK_NT) {
+    double f[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {  // ascending reference element id; + 0.0 for a missing entry is exact
+      const unsigned en = s_map[q * BRICK_NLMAX + l];
+      if (en != 0xFFFFu) { f[0] += scr[en]; f[1] += scr[en + BRICK_NT]; f[2] += scr[en + 2 * BRICK_NT]; }
+    }
+    const size_t s = (size_t)H.slot0 + (l - H.nInt);
+    A.part[0][s] = f[0]; A.part[1][s] = f[1]; A.part[2][s] = f[2];
+  }
+  // interior nodes: spread evenly over the warps (a contiguous run of nodes per warp), finished here
   double wke = 0.0, wint = 0.0, wext = 0.0;
+  {
+    const int w = tid >> 5, lane = tid & 31;
+    const int per = (H.nInt + BRICK_NT / 32 - 1) / (BRICK_NT / 32);
+    const int l1 = min((w + 1) * per, H.nInt);
+    for (int l = w * per + lane; l < l1; l += 32) {
+      const int g = H.ibase + l;
+      // the node's own state again (this block read it a few microseconds ago)
+      const unsigned fl = A.flags[g];
+      const double mm = A.m[g];
+      double uo[3], vo[3], ao[3], fprev[3] = {0.0, 0.0, 0.0}, fext[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-  for (int r = 0; r < BRICK_NODE_TRIPS; ++r) {
-    const int l = tid + r * BRICK_NT;
-    if (l < H.nLoc) {
-      const bool interior = l < H.nInt;
-      const int g = H.ibase + l;  // interior nodes only
-      // the node's own state again (L2 hits: this block read it a few microseconds ago)
-      unsigned fl = 0;
-      double uo[3], vo[3], ao[3], fprev[3] = {0.0, 0.0, 0.0}, fext[3] = {0.0, 0.0, 0.0}, mm = 1.0;
-      if (interior) {
-        fl = A.flags[g];
-        mm = A.m[g];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          uo[c] = A.u[c][g]; vo[c] = A.v[c][g]; ao[c] = A.a[c][g];
-          if (ENERGY) fprev[c] = A.fi[c][g];
-          if (A.fe[c]) fext[c] = A.fe[c][g];
-        }
+      for (int c = 0; c < 3; ++c) {
+        uo[c] = A.u[c][g]; vo[c] = A.v[c][g]; ao[c] = A.a[c][g];
+        if (ENERGY) fprev[c] = A.fi[c][g];
+        if (A.fe[c]) fext[c] = A.fe[c][g];
       }
       double f[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {  // ascending reference element id; + 0.0 for a missing entry is exact
+      for (int q = 0; q < 8; ++q) {
         const unsigned en = s_map[q * BRICK_NLMAX + l];
-        if (en != 0xFFFFu) {
-          const double* col = scr + (3 * (en & 7u)) * BRICK_NT + (en >> 3);
-          f[0] += col[0]; f[1] += col[BRICK_NT]; f[2] += col[2 * BRICK_NT];
-        }
+        if (en != 0xFFFFu) { f[0] += scr[en]; f[1] += scr[en + BRICK_NT]; f[2] += scr[en + 2 * BRICK_NT]; }
       }
-      if (interior) {
-        double un[3], vs[3], as[3], vn[3], an[3];
-        node_start(fl, T, bc_rate, uo, vo, ao, un, vs, as);
-        node_finish<ENERGY>(fl, T, mm, f, fext, fprev, uo, un, vs, as, vn, an, wke, wint, wext);
+      double un[3], vs[3], as[3], vn[3], an[3];
+      node_start(fl, T, bc_rate, uo, vo, ao, un, vs, as);
+      node_finish<ENERGY>(fl, T, mm, f, fext, fprev, uo, un, vs, as, vn, an, wke, wint, wext);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          A.u[c][g] = un[c]; A.v[c][g] = vn[c]; A.a[c][g] = an[c];
-          if (A.store_fi) A.fi[c][g] = f[c];
-        }
-      } else {
-        const size_t s = (size_t)H.slot0 + (l - H.nInt);
-        A.part[0][s] = f[0]; A.part[1][s] = f[1]; A.part[2][s] = f[2];
+      for (int c = 0; c < 3; ++c) {
+        A.u[c][g] = un[c]; A.v[c][g] = vn[c]; A.a[c][g] = an[c];
+        if (A.store_fi) A.fi[c][g] = f[c];
       }
     }
   }
-  if (ENERGY) {  // fixed-shape tree: warp shuffle, then shared memory, one partial per brick
+  if (ENERGY) {  // fixed-shape tree inside the warp, one partial per warp: no block barrier at the end of the kernel
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       wke += __shfl_down_sync(0xffffffffu, wke, o);
@@ -350,22 +342,10 @@ __global__ void __launch_bounds__(BRICK_NT, 2) k_brick(const BrickArgs A) {
       wext += __shfl_down_sync(0xffffffffu, wext, o);
     }
     if ((tid & 31) == 0) {
-      s_red[tid >> 5] = wke;
-      s_red[(BRICK_NT / 32) + (tid >> 5)] = wint;
-      s_red[2 * (BRICK_NT / 32) + (tid >> 5)] = wext;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      double s0 = 0, s1 = 0, s2 = 0;
-#pragma unroll
-      for (int w = 0; w < BRICK_NT / 32; ++w) {
-        s0 += s_red[w];
-        s1 += s_red[(BRICK_NT / 32) + w];
-        s2 += s_red[2 * (BRICK_NT / 32) + w];
-      }
-      A.epart[b] = s0;
-      A.epart[A.nEpart + b] = s1;
-      A.epart[2 * A.nEpart + b] = s2;
+      const int i = b * (BRICK_NT / 32) + (tid >> 5);
+      A.epart[i] = wke;
+      A.epart[A.nEpart + i] = wint;
+      A.epart[2 * A.nEpart + i] = wext;
     }
   }
 }
@@ -386,7 +366,7 @@ struct SurfArgs {
   const uint16_t* flags;
   const double* part[3];
   double* epart;
-  int nEpart, eoff;    // this kernel's blocks write epart[eoff + blockIdx.x]
+  int nEpart, eoff;    // this kernel's warps write epart[eoff + warp index]
   int node0, nS;
   DevScalars* sc;
   int store_fi;
@@ -447,27 +427,18 @@ __global__ void __launch_bounds__(SURF_BLOCK, 6) k_surf(const SurfArgs A) {
       if (A.store_fi) A.fi[c][g] = f[c];
     }
   }
-  if (ENERGY) {
+  if (ENERGY) {  // one partial per warp
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       wke += __shfl_down_sync(0xffffffffu, wke, o);
       wint += __shfl_down_sync(0xffffffffu, wint, o);
       wext += __shfl_down_sync(0xffffffffu, wext, o);
     }
-    __shared__ double sw[3][SURF_BLOCK / 32];
     if ((threadIdx.x & 31) == 0) {
-      sw[0][threadIdx.x >> 5] = wke;
-      sw[1][threadIdx.x >> 5] = wint;
-      sw[2][threadIdx.x >> 5] = wext;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double s0 = 0, s1 = 0, s2 = 0;
-#pragma unroll
-      for (int w = 0; w < SURF_BLOCK / 32; ++w) { s0 += sw[0][w]; s1 += sw[1][w]; s2 += sw[2][w]; }
-      A.epart[A.eoff + blockIdx.x] = s0;
-      A.epart[A.nEpart + A.eoff + blockIdx.x] = s1;
-      A.epart[2 * A.nEpart + A.eoff + blockIdx.x] = s2;
+      const int i = A.eoff + blockIdx.x * (SURF_BLOCK / 32) + (threadIdx.x >> 5);
+      A.epart[i] = wke;
+      A.epart[A.nEpart + i] = wint;
+      A.epart[2 * A.nEpart + i] = wext;
     }
   }
 }

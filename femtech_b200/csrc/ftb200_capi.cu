@@ -112,13 +112,13 @@ struct ftb200_ctx {
   long long p2p_graph_launches = 0;
   double Time0 = 0.0;
   // brick-fused step (ftb200_brick.cuh): built by shape_functions when the mesh qualifies
-  bool brick_ok = false, brick_want = true, felem_stale = false;
+  bool brick_ok = false, brick_want = false, felem_stale = false;  // FTB200_BRICK=1 selects the brick-fused step
   int brick_dims[3] = {10, 5, 5};
   int nB = 0, nIntTot = 0, nSurf = 0, surf_blocks = 0;
   long long nSlots = 0;
   BrickHdr* b_hdr = nullptr;
   uint16_t *b_conn16 = nullptr, *b_map16 = nullptr;
-  int *b_halo = nullptr, *s_ell = nullptr, *s_ovoff = nullptr, *s_ovent = nullptr;
+  int *b_halo = nullptr, *b_xid = nullptr, *s_ell = nullptr, *s_ovoff = nullptr, *s_ovent = nullptr;
   double* b_part[3] = {nullptr, nullptr, nullptr};
   // graph cache
   cudaGraphExec_t graph = nullptr;
@@ -462,16 +462,19 @@ BrickPlan plan_bricks(const ftb200_ctx* ctx) {
 //      needs no separate START launch.
 bool use_brick(const ftb200_ctx* ctx) { return ctx->brick_ok && !ctx->rigid && !ctx->injury && ctx->nranks == 1; }
 
+// energy partials of the brick-fused step: one per warp of k_brick, then one per warp of k_surf
+int brick_eparts(const ftb200_ctx* c) { return c->nB * (BRICK_NT / 32) + c->surf_blocks * (SURF_BLOCK / 32); }
+
 BrickArgs brick_args(ftb200_ctx* c) {
   BrickArgs A;
-  A.hdr = c->b_hdr; A.conn16 = c->b_conn16; A.halo = c->b_halo; A.map16 = c->b_map16;
+  A.hdr = c->b_hdr; A.conn16 = c->b_conn16; A.xid = c->b_xid; A.halo = c->b_halo; A.map16 = c->b_map16;
   for (int k = 0; k < 3; ++k) {
     A.X[k] = c->X[k]; A.u[k] = c->u[k]; A.v[k] = c->v[k]; A.a[k] = c->a[k]; A.fi[k] = c->fi[k];
     A.fe[k] = c->has_fe ? c->fe[k] : nullptr;
     A.part[k] = c->b_part[k];
   }
   A.m = c->m; A.flags = c->flags; A.pid = c->pid; A.eflag = c->eflag; A.mp = c->mp;
-  A.epart = c->epart; A.nEpart = c->nB + c->surf_blocks; A.sc = c->sc; A.store_fi = c->energy ? 1 : 0;
+  A.epart = c->epart; A.nEpart = brick_eparts(c); A.sc = c->sc; A.store_fi = c->energy ? 1 : 0;
   return A;
 }
 SurfArgs surf_args(ftb200_ctx* c) {
@@ -482,7 +485,7 @@ SurfArgs surf_args(ftb200_ctx* c) {
     A.fe[k] = c->has_fe ? c->fe[k] : nullptr;
     A.part[k] = c->b_part[k];
   }
-  A.m = c->m; A.flags = c->flags; A.epart = c->epart; A.nEpart = c->nB + c->surf_blocks; A.eoff = c->nB;
+  A.m = c->m; A.flags = c->flags; A.epart = c->epart; A.nEpart = brick_eparts(c); A.eoff = c->nB * (BRICK_NT / 32);
   A.node0 = c->nIntTot; A.nS = c->nSurf; A.sc = c->sc; A.store_fi = c->energy ? 1 : 0;
   return A;
 }
@@ -512,7 +515,7 @@ void launch_step_brick(ftb200_ctx* ctx) {
   if (ctx->energy_pending) { cudaStreamWaitEvent(s, ctx->ev_energy_done, 0); ctx->energy_pending = false; }
   LAUNCH((k_adv<false>), 1, 128, s, ctx->sc, ctx->mp, ctx->nPID, 0.0, ctx->dthist);
   if (ctx->energy) {
-    const int nblocks = ctx->nB + ctx->surf_blocks;
+    const int nblocks = brick_eparts(ctx);
     if (en_async) {
       cudaEventRecord(ctx->ev_nodes_done, s);
       cudaStreamWaitEvent(ctx->stream2, ctx->ev_nodes_done, 0);
@@ -578,7 +581,7 @@ void free_all(ftb200_ctx* c) {
   c->p2p_ready = false;
   if (c->p2p_graph) { cudaGraphExecDestroy(c->p2p_graph); c->p2p_graph = nullptr; }
   dfree(c->d_nref); dfree(c->d_nint); dfree(c->d_ell);
-  dfree(c->b_hdr); dfree(c->b_conn16); dfree(c->b_map16); dfree(c->b_halo); dfree(c->s_ell); dfree(c->s_ovoff); dfree(c->s_ovent);
+  dfree(c->b_hdr); dfree(c->b_conn16); dfree(c->b_map16); dfree(c->b_halo); dfree(c->b_xid); dfree(c->s_ell); dfree(c->s_ovoff); dfree(c->s_ovent);
   dfree(c->b_part[0]); dfree(c->b_part[1]); dfree(c->b_part[2]);
   c->brick_ok = false;
   if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
@@ -999,8 +1002,8 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
         for (int k = 0; k < 8; ++k) {
           const int g = nint[ctx->h_conn[8 * (size_t)plan.elems[e0 + i] + k]];
           const int l = g < nIntTot ? g - b_ibase[b] : loc[g];
-          conn16[((size_t)b * 8 + k) * BRICK_NT + i] = (uint16_t)l;
-          map16[((size_t)b * 8 + lcnt[l]++) * BRICK_NLMAX + l] = (uint16_t)(i * 8 + k);
+          conn16[((size_t)b * BRICK_NT + i) * 8 + k] = (uint16_t)l;
+          map16[((size_t)b * 8 + lcnt[l]++) * BRICK_NLMAX + l] = (uint16_t)(3 * k * BRICK_NT + i);
         }
       hdr[b] = BrickHdr{e0, nEl, b_ibase[b], nInt_b, nLoc, (int)slot, 0, 0};
       for (size_t i = 0; i < surf.size(); ++i) {
@@ -1012,9 +1015,16 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       slot += (long long)surf.size();
       if (slot > 0x7fffff00LL) return fail(ctx, FTB200_ERR_INPUT, "too many surface partials for 32-bit slots");
     }
+    std::vector<int> xid(4 * (size_t)nE);
+    for (int t = 0; t < nE; ++t) {
+      const int* cn = &ctx->h_conn[8 * (size_t)ref_of[t]];
+      xid[4 * (size_t)t] = nint[cn[0]]; xid[4 * (size_t)t + 1] = nint[cn[1]]; xid[4 * (size_t)t + 2] = nint[cn[3]]; xid[4 * (size_t)t + 3] = nint[cn[4]];
+    }
+    if ((rc = dalloc(ctx, &ctx->b_xid, xid.size()))) return rc;
+    CK(cudaMemcpy(ctx->b_xid, xid.data(), xid.size() * sizeof(int), cudaMemcpyHostToDevice));
     ctx->nB = nB; ctx->nIntTot = nIntTot; ctx->nSurf = nS; ctx->nSlots = slot;
     ctx->surf_blocks = cdiv(nS, SURF_BLOCK);
-    epart_blocks = std::max(epart_blocks, nB + ctx->surf_blocks);
+    epart_blocks = std::max(epart_blocks, nB * (BRICK_NT / 32) + ctx->surf_blocks * (SURF_BLOCK / 32));
     if ((rc = dalloc(ctx, &ctx->b_hdr, nB)) || (rc = dalloc(ctx, &ctx->b_conn16, conn16.size())) ||
         (rc = dalloc(ctx, &ctx->b_map16, map16.size())) || (rc = dalloc(ctx, &ctx->b_halo, halo.size())) ||
         (rc = dalloc(ctx, &ctx->s_ell, sell.size())) || (rc = dalloc(ctx, &ctx->b_part[0], (size_t)slot + 1)) ||

@@ -33,6 +33,7 @@ class env:
         self.kw = kw
 
     def __enter__(self):
+        self.kw.setdefault("FTB200_BRICK", "1")
         self.old = {k: os.environ.get(k) for k in self.kw}
         os.environ.update(self.kw)
 
@@ -120,10 +121,11 @@ def test_brick_chunked_runs_equal_one_run():
     """25-step graphs, single steps and a ragged tail: the same bits as one 60-step call."""
     X, conn, pid = mesh.cube_mesh(10)
     kind, rate = mesh.benchmark_bc(X, dMax=0.02, tMax=0.004)
-    ref = make(X, conn, pid, [1], SOFT, kind, rate, 60)
+    with env():
+        ref = make(X, conn, pid, [1], SOFT, kind, rate, 60)
+        m = make(X, conn, pid, [1], SOFT, kind, rate, 60)
     assert ref.brick_info["active"]
     assert ref.ExplicitDynamics(1.0, maxSteps=60) == 60
-    m = make(X, conn, pid, [1], SOFT, kind, rate, 60)
     done = 0
     for chunk in (1, 1, 26, 7, 25):
         done += m.ExplicitDynamics(1.0, maxSteps=chunk)
@@ -141,7 +143,8 @@ def test_brick_chunked_runs_equal_one_run():
 def test_brick_decomposition_covers_every_element_and_node_once():
     X, conn, pid = mesh.cube_mesh(12)
     kind, rate = mesh.benchmark_bc(X, dMax=0.02, tMax=0.004)
-    m = make(X, conn, pid, [1], SOFT, kind, rate, 1)
+    with env():
+        m = make(X, conn, pid, [1], SOFT, kind, rate, 1)
     info = m.brick_info
     be, bn = m.brick_maps()
     assert be.min() == 0 and be.max() == info["bricks"] - 1
@@ -181,10 +184,12 @@ def test_sheared_parallelepiped_mesh_takes_the_brick_path():
 def test_meshes_that_do_not_qualify_keep_the_two_kernel_step():
     Xj, conn, pid = mesh.cube_mesh(6, jitter=0.05)
     kind, rate = mesh.benchmark_bc(Xj, dMax=0.007, tMax=0.004)
-    m = make(Xj, conn, pid, [1], SOFT, kind, rate, 1)
+    with env():
+        m = make(Xj, conn, pid, [1], SOFT, kind, rate, 1)
     assert not m.brick_info["active"] and m.brick_info["bricks"] == 0
     m.close()
     X, conn, pid = mesh.cube_mesh(6)
-    m = make(X, conn, pid, [5], BRAIN, kind, rate, 1)
+    with env():
+        m = make(X, conn, pid, [5], BRAIN, kind, rate, 1)
     assert not m.brick_info["active"]
     m.close()
