@@ -2,26 +2,41 @@
 //
 // The two-kernel step (k_elem -> k_node) sends every element's 24 nodal forces through HBM: 192 B written and 192 B
 // read per element and step, more than half of the step's traffic.  Here the mesh is cut into BRICKS of at most
-// BRICK_NT elements (host: build_bricks in ftb200_capi.cu; geometric boxes of the element centroids), one thread block
-// per brick, and the element forces never leave the SM:
+// BRICK_NT elements (host: plan_bricks in ftb200_capi.cu; geometric boxes of the element centroids) and the element
+// forces never leave the SM:
 //
-//   k_brick   prologue  first kick + drift + boundary condition of the step for every node the brick touches
+//   k_brick   persistent thread blocks (two per SM), each walking bricks b, b + G, b + 2G, ...; per brick
+//             START     first kick + drift + boundary condition of the step for every node the brick touches
 //                       (Benchmarking-Parallel.cpp:115-135,184-244), new displacements staged in shared memory;
-//             elements  hex8_element_brick_in per thread: F, material, P cof(J0) -> 24 nodal forces, element dt
-//                       (GetForce_3D.cpp:15-46, CalculateTimeStep.cpp:7-21); the forces overwrite the thread's scratch;
-//             epilogue  per local node: fixed-order sum of the brick's contributions from shared memory
+//             SETUP     per thread = element: nodal gather, displacement modes, dU/dxi columns, (8 J0)^-1, dt factor;
+//             LOOP      eight Gauss points: F, material, P cof(J0) -> 24 nodal forces, element dt
+//                       (GetForce_3D.cpp:15-46, CalculateTimeStep.cpp:7-21);
+//             FINISH    per local node: fixed-order sum of the brick's contributions through shared memory
 //                       (GetForce_3D.cpp:39-44).  INTERIOR nodes (every element of the node lies in this brick) are
 //                       finished here: a = (fe - fi)/m, second kick, energy partial (CalculateAcclerations.cpp:4-13,
 //                       Benchmarking-Parallel.cpp:146-151, CheckEnergy.cpp:19-52), state written once.  SURFACE nodes
 //                       get one partial sum per brick (24 B) in a slot of the partial planes.
 //   k_surf    per surface node: the partials of its bricks in ascending brick order, then the same start + finish.
 //
-// Per element and step at 100^3 (10 x 5 x 5 bricks): ~50 B of brick metadata, ~120 B of nodal state read, ~45 B
-// written, ~25 B of partials each way, ~100 B in k_surf -- about half of the 717 B of the two-kernel step.
+// What makes it fast is that no warp ever waits for HBM.  A thread-per-element fp64 kernel is bound by the latency of
+// its own dependency chains: it needs all 16 warps an SM's registers allow inside the Gauss loop all the time, and a
+// block that is loading or storing nodes is not.  So the memory traffic of brick b + G runs UNDER the Gauss loop of
+// brick b (a software pipeline inside the persistent block):
+//   * the nodal state (u, v, a, flags, X) of the next brick and the metadata of the one after it are copied
+//     global -> shared with cp.async (no registers) right before the loop starts; mass and previous internal force of
+//     the current brick's interior nodes at its START; the local node -> (element, slot) map with one bulk copy
+//     (cp.async.bulk + mbarrier, SASS UBLKCP);
+//   * START, SETUP and FINISH then read shared memory only;
+//   * shared memory has room for those buffers because the element scratch does not live there: the 36 dU/dxi column
+//     entries of every thread sit in TENSOR MEMORY (tcgen05.st / tcgen05.ld, shape 32x32b: a TMEM column is one 32-bit
+//     word per thread of the warp's lane quarter, 72 columns per thread, dynamically indexed by the Gauss point; SASS
+//     STTM / LDTM).  No MMA is involved -- TMEM is used as 256 KB of per-thread scratch next to the register file.
+//     Only (8 J0)^-1 (9 doubles per thread, re-read twice per Gauss point) stays in shared memory: measured TMEM read
+//     bandwidth is 94 B/clk/SM against 128 B/clk/SM for shared memory (experiments/tmem_probe.cu), so the 27 scratch
+//     loads per Gauss point are split 9 / 18 between the two.
+//
 // Deterministic: every sum has a fixed order (interior nodes: ascending reference element id, exactly the order of
 // the two-kernel step; surface nodes: per brick, then ascending brick id), no floating-point atomics.
-// Brick metadata arrive by bulk asynchronous copies (cp.async.bulk + mbarrier): one descriptor-free TMA transfer per
-// array, issued by one thread, no registers.
 //
 // Internal node order in brick mode: [interior nodes of brick 0 | of brick 1 | ... | surface nodes by owning brick |
 // padding], so the interior nodes of a brick are one contiguous index range (coalesced loads and stores, no index list).
@@ -30,9 +45,12 @@
 
 namespace ftb {
 
-constexpr int BRICK_NT = 256;      // threads per brick = maximum number of elements of a brick
-constexpr int BRICK_NLMAX = 416;   // maximum number of local nodes of a brick (10 x 5 x 5 elements: 396)
+constexpr int BRICK_NT = 256;      // threads per block = maximum number of elements of a brick
+constexpr int BRICK_NIMAX = 160;   // maximum number of interior nodes of a brick (10 x 5 x 5 elements: 147)
+constexpr int BRICK_NSMAX = 256;   // maximum number of surface local nodes of a brick (10 x 5 x 5 elements: 249)
+constexpr int BRICK_NLMAX = BRICK_NIMAX + BRICK_NSMAX;
 constexpr int BRICK_NODE_TRIPS = (BRICK_NLMAX + BRICK_NT - 1) / BRICK_NT;
+constexpr int BRICK_TMEM_COLS = 256;  // per block; two blocks per SM use all 512 columns
 
 struct BrickHdr {
   int e0, nEl;      // elements [e0, e0 + nEl) of the internal element order
@@ -44,11 +62,12 @@ struct BrickHdr {
 
 struct BrickArgs {
   const BrickHdr* hdr;
-  const uint16_t* conn16;  // [nB][BRICK_NT][8] local node index of C3D8 node k of local element t (one 16-byte load per thread)
-  const int* xid;          // [nE][4] internal node ids of the reference nodes 0, 1, 3, 4 of every element (internal element order)
-  const int* halo;         // [nB][BRICK_NLMAX] internal node ids of the surface local nodes
-  const uint16_t* map16;   // [nB][8][BRICK_NLMAX] local node -> scratch word 3 * slot * BRICK_NT + local element of the
-                           // force a local element puts on it, 0xFFFF = none; ascending reference element id
+  const uint16_t* conn16;  // [nB][BRICK_NT][8] local node index of C3D8 node k of local element t (one 16-byte copy per thread)
+  const int* halo;         // [nB][BRICK_NSMAX] internal node ids of the surface local nodes
+  const uint16_t* map16;   // [nB][8][BRICK_NLMAX] local node -> row * BRICK_NT + local element of the force a local
+                           // element puts on it (row = its C3D8 slot), 0xFFFF = none; ascending reference element id
+  const int* pe;           // [nE] part id | (element skipped by StableTimeStep) << 30, internal element order
+  const unsigned* flags32; // node flags widened to 32 bits (cp.async moves at least 4 bytes)
   const double* X[3];
   double* u[3];
   double* v[3];
@@ -56,18 +75,39 @@ struct BrickArgs {
   double* fi[3];
   const double* fe[3];     // nullptr planes when the external force is identically zero
   const double* m;
-  const uint16_t* flags;
-  const int* pid;
-  const uint8_t* eflag;
   const double* mp;
   double* part[3];         // partial sums of the surface nodes, one slot per (brick, surface local node)
-  double* epart;           // [3][nEpart] energy partials: blocks of k_brick first, then those of k_surf
+  double* epart;           // [3][nEpart] energy partials: warps of k_brick (brick * 8 + warp) first, then those of k_surf
   int nEpart;
+  int nB;
   DevScalars* sc;
   int store_fi;
 };
 
-constexpr size_t BRICK_SMEM_BYTES = (size_t)FTB_BRICK_SLOTS * BRICK_NT * 8 + 3 * BRICK_NLMAX * 8 + 8 * BRICK_NLMAX * 2 + 16;
+// one pipeline stage of brick metadata (copied two bricks ahead)
+struct BrickMeta {
+  uint16_t conn16[BRICK_NT][8];
+  int halo[BRICK_NSMAX];
+  int pe[BRICK_NT];
+};
+struct BrickSmem {
+  double ji[9][BRICK_NT];           // (8 J0)^-1 of every thread; rows 0..7 double as the force exchange buffer of FINISH
+  double ust[3][BRICK_NLMAX];       // new displacements of the local nodes
+  double xs[3][BRICK_NLMAX];        // reference coordinates of the local nodes
+  double rawI[2][9][BRICK_NIMAX];   // u, v, a of the interior nodes (this brick's are read again by FINISH: two stages)
+  unsigned flI[2][BRICK_NIMAX];
+  double lateI[4][BRICK_NIMAX];     // m, fi_prev[3] of the current brick's interior nodes
+  double rawS[9][BRICK_NSMAX];      // u, v, a of the surface local nodes
+  unsigned flS[BRICK_NSMAX];
+  uint16_t map16[8][BRICK_NLMAX];
+  BrickMeta meta[2];
+  BrickHdr hdr[3];
+  double times[4];                  // dt1, dt2, dtn, T of the step (StepTimes), re-read behind the Gauss loop
+  unsigned long long bar;
+  unsigned tmem_base, pad;
+};
+constexpr size_t BRICK_SMEM_BYTES = sizeof(BrickSmem);
+static_assert(sizeof(BrickSmem) <= 115712, "two blocks per SM");
 
 // ---- bulk asynchronous copy global -> shared, completion on an mbarrier (SASS: UBLKCP / SYNCS) ----
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -162,192 +202,313 @@ __device__ __forceinline__ void node_finish(const unsigned fl, const StepTimes& 
   }
 }
 
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// nodal input of hex8_brick_setup: node-indexed shared-memory tables, local node ids packed two per word
 struct BrickIn {
-  const double* scr;   // &scratch[0][threadIdx.x]: reference nodes 0, 1, 3, 4 staged in FTB_BSTAGE_X slots
-  const double* ust;   // [3][BRICK_NLMAX] new displacements of the brick's local nodes
-  unsigned ln[4];      // local node ids, two per word
+  const double* xs;    // [3][BRICK_NLMAX]
+  const double* ust;   // [3][BRICK_NLMAX]
+  unsigned ln[4];
+  __device__ __forceinline__ int id(const int k) const { return (int)((ln[k >> 1] >> (16 * (k & 1))) & 0xFFFFu); }
   __device__ __forceinline__ void getX(const int c, double x[4]) const {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) x[k] = scr[FTB_BSTAGE_X(k, c) * BRICK_NT];
+    x[0] = xs[c * BRICK_NLMAX + id(0)]; x[1] = xs[c * BRICK_NLMAX + id(1)];
+    x[2] = xs[c * BRICK_NLMAX + id(3)]; x[3] = xs[c * BRICK_NLMAX + id(4)];
   }
   __device__ __forceinline__ void getU(const int c, double nu[8]) const {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) nu[k] = ust[c * BRICK_NLMAX + ((ln[k >> 1] >> (16 * (k & 1))) & 0xFFFFu)];
+    for (int k = 0; k < 8; ++k) nu[k] = ust[c * BRICK_NLMAX + id(k)];
   }
 };
-struct SmemScratchBrick {
-  double* base;  // &scratch[0][threadIdx.x]
-  __device__ __forceinline__ void st(int i, double x) { base[i * BRICK_NT] = x; }
-  __device__ __forceinline__ double ld(int i) const { return base[i * BRICK_NT]; }
-  __device__ __forceinline__ double ld_inloop(int i) const {
+// Element scratch of k_brick: the dU/dxi columns in tensor memory (this thread's lane, columns t0 + 2 i, t0 + 2 i + 1),
+// (8 J0)^-1 in shared memory.  All tcgen05 instructions are .sync.aligned: every lane of the warp executes them together.
+struct TmemScratch {
+  uint32_t t0;   // TMEM address (lane quarter of the warp << 16 | first column of the warp's slice)
+  double* ji;    // &smem.ji[0][threadIdx.x]
+  __device__ __forceinline__ void st_col(const int i, const double x) const {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(t0 + 2u * (unsigned)i), "r"((unsigned)b), "r"((unsigned)(b >> 32)) : "memory");
+  }
+  __device__ __forceinline__ void cols_written() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+  __device__ __forceinline__ void ld_cols9(const int idx[9], double out[9]) const {
+    unsigned lo[9], hi[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(lo[k]), "=r"(hi[k]) : "r"(t0 + 2u * (unsigned)idx[k]) : "memory");
+    // the loads are asynchronous: the destination registers may be read only behind the wait, so they pass through it
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(lo[0]), "+r"(hi[0]), "+r"(lo[1]), "+r"(hi[1]), "+r"(lo[2]), "+r"(hi[2]), "+r"(lo[3]), "+r"(hi[3]), "+r"(lo[4]),
+                   "+r"(hi[4]), "+r"(lo[5]), "+r"(hi[5]), "+r"(lo[6]), "+r"(hi[6]), "+r"(lo[7]), "+r"(hi[7]), "+r"(lo[8]), "+r"(hi[8])
+                 :
+                 : "memory");
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out[k] = __hiloint2double((int)hi[k], (int)lo[k]);
+  }
+  __device__ __forceinline__ void st_ji(const int i, const double x) const { ji[i * BRICK_NT] = x; }
+  __device__ __forceinline__ double ld_ji(const int i) const {  // re-read in every iteration: keeps 18 registers free
     double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(base + i * BRICK_NT)) : "memory");
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(ji + i * BRICK_NT)) : "memory");
     return v;
   }
 };
 
+// copies of one brick's metadata / nodal state into a pipeline stage (cp.async: in flight under the Gauss loop)
+__device__ __forceinline__ void brick_load_meta(const BrickArgs& A, BrickSmem& S, const int b, const int stage, const int hslot, const int tid) {
+  cp_async16(&S.meta[stage].conn16[tid][0], A.conn16 + ((size_t)b * BRICK_NT + tid) * 8);
+  cp_async4(&S.meta[stage].halo[tid], A.halo + (size_t)b * BRICK_NSMAX + tid);
+  if (tid < 2) cp_async16(reinterpret_cast<char*>(&S.hdr[hslot]) + 16 * tid, reinterpret_cast<const char*>(A.hdr + b) + 16 * tid);
+}
+__device__ __forceinline__ void brick_load_pe(const BrickArgs& A, BrickSmem& S, const BrickHdr& H, const int stage, const int tid) {
+  const int t = tid < H.nEl ? tid : H.nEl - 1;
+  cp_async4(&S.meta[stage].pe[tid], A.pe + H.e0 + t);
+}
+__device__ __forceinline__ void brick_load_nodes(const BrickArgs& A, BrickSmem& S, const BrickHdr& H, const int mstage, const int istage, const int tid) {
+#pragma unroll
+  for (int r = 0; r < BRICK_NODE_TRIPS; ++r) {
+    const int l = tid + r * BRICK_NT;
+    if (l < H.nLoc) {
+      if (l < H.nInt) {
+        const int g = H.ibase + l;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          cp_async8(&S.rawI[istage][c][l], A.u[c] + g);
+          cp_async8(&S.rawI[istage][3 + c][l], A.v[c] + g);
+          cp_async8(&S.rawI[istage][6 + c][l], A.a[c] + g);
+          cp_async8(&S.xs[c][l], A.X[c] + g);
+        }
+        cp_async4(&S.flI[istage][l], A.flags32 + g);
+      } else {
+        const int sidx = l - H.nInt;
+        const int g = S.meta[mstage].halo[sidx];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          cp_async8(&S.rawS[c][sidx], A.u[c] + g);
+          cp_async8(&S.rawS[3 + c][sidx], A.v[c] + g);
+          cp_async8(&S.rawS[6 + c][sidx], A.a[c] + g);
+          cp_async8(&S.xs[c][l], A.X[c] + g);
+        }
+        cp_async4(&S.flS[sidx], A.flags32 + g);
+      }
+    }
+  }
+}
+
+// per-run refresh of the two derived arrays k_brick copies with cp.async (4-byte granularity): node flags widened to 32 bits,
+// part id and the StableTimeStep skip flag of an element in one word
+__global__ void k_brick_prep(const uint16_t* __restrict__ flags, unsigned* flags32, int nN, const int* __restrict__ pid,
+                             const uint8_t* __restrict__ eflag, int* pe, int nE) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nN) flags32[i] = flags[i];
+  if (i < nE) pe[i] = pid[i] | ((int)(eflag[i] != 0) << 30);
+}
+
 template <int MATSEL, bool ENERGY>
 __global__ void __launch_bounds__(BRICK_NT, 2) k_brick(const BrickArgs A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* scr = reinterpret_cast<double*>(smem_raw);                          // [45][NT]
-  double* ust = scr + FTB_BRICK_SLOTS * BRICK_NT;                            // [3][NLMAX]
-  uint16_t* s_map = reinterpret_cast<uint16_t*>(ust + 3 * BRICK_NLMAX);      // [8][NLMAX]
-  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_map + 8 * BRICK_NLMAX);  // [1]
-
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  BrickSmem& S = *reinterpret_cast<BrickSmem*>(smem_raw);
   const DevScalars* sc = A.sc;
-  const int tid = threadIdx.x;
-  const int b = blockIdx.x;
-  const BrickHdr H = A.hdr[b];
-  const int lastdone = sc->last | sc->done;
-  const StepTimes T = step_times(sc);
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int G = gridDim.x;
+  int b = blockIdx.x;
+  if (sc->last | sc->done) return;
+  if (b >= A.nB) return;
   const double* bc_rate = sc->bc_rate;  // read only by nodes that carry a boundary-condition kind
-  if (lastdone) return;
-  // the local node -> (element, slot) map is needed by the epilogue only: one bulk copy, waited for after the elements
+  // ---- one-time set-up of the block: tensor memory, the barrier of the bulk copies, the first two bricks' metadata ----
+  if (tid == 32) {
+    const StepTimes T0 = step_times(sc);
+    S.times[0] = T0.dt1; S.times[1] = T0.dt2; S.times[2] = T0.dtn; S.times[3] = T0.T;
+  }
+  if (w == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&S.tmem_base)), "n"(BRICK_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
   if (tid == 0) {
-    mbar_init(&s_bar[0], 1);
+    mbar_init(&S.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(&s_bar[0], 8 * BRICK_NLMAX * 2);
-    bulk_g2s(s_map, A.map16 + (size_t)b * 8 * BRICK_NLMAX, 8 * BRICK_NLMAX * 2, &s_bar[0]);
   }
-  // ---- prologue: everything that depends on the header only is requested at once --------------------------------
-  const bool has_el = tid < H.nEl;
-  const int e = H.e0 + tid;
-  int p = 0;
-  unsigned skip = 0;
-  uint4 cw = make_uint4(0, 0, 0, 0);   // local node ids of the element, two per word
-  int4 xg = make_int4(0, 0, 0, 0);     // internal ids of its reference nodes 0, 1, 3, 4
-  if (has_el) {
-    cw = __ldg(reinterpret_cast<const uint4*>(A.conn16) + (size_t)b * BRICK_NT + tid);
-    xg = __ldg(reinterpret_cast<const int4*>(A.xid) + e);
-    p = __ldg(A.pid + e);
-    skip = __ldg(A.eflag + e);
-  }
-  {
-    int g[BRICK_NODE_TRIPS];
-#pragma unroll
-    for (int r = 0; r < BRICK_NODE_TRIPS; ++r) {
-      const int l = tid + r * BRICK_NT;
-      g[r] = -1;
-      if (l < H.nLoc) g[r] = l < H.nInt ? H.ibase + l : __ldg(A.halo + (size_t)b * BRICK_NLMAX + (l - H.nInt));
-    }
-    if (has_el) {  // the element's reference nodes 0, 1, 3, 4: global -> scratch, no registers
-      const int gx[4] = {xg.x, xg.y, xg.z, xg.w};
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) cp_async8(scr + FTB_BSTAGE_X(kk, c) * BRICK_NT + tid, A.X[c] + gx[kk]);
-    }
-    double uu[BRICK_NODE_TRIPS][3], vv[BRICK_NODE_TRIPS][3], aa[BRICK_NODE_TRIPS][3];
-    unsigned fl[BRICK_NODE_TRIPS];
-#pragma unroll
-    for (int r = 0; r < BRICK_NODE_TRIPS; ++r)
-      if (g[r] >= 0) {
-        fl[r] = A.flags[g[r]];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { uu[r][c] = A.u[c][g[r]]; vv[r][c] = A.v[c][g[r]]; aa[r][c] = A.a[c][g[r]]; }
-      }
-    // START of the step for the brick's local nodes
-#pragma unroll
-    for (int r = 0; r < BRICK_NODE_TRIPS; ++r) {
-      const int l = tid + r * BRICK_NT;
-      if (g[r] >= 0) {
-        double un[3];
-        node_start_u(fl[r], T, bc_rate, uu[r], vv[r], aa[r], un);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) ust[c * BRICK_NLMAX + l] = un[c];
-      }
-    }
-  }
-  asm volatile("cp.async.wait_all;" ::: "memory");
+  brick_load_meta(A, S, b, 0, 0, tid);
+  cp_async_commit();
+  cp_async_wait<0>();
+  asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-  // ---- elements ----------------------------------------------------------------------------------------------------
-  {
-    double dte = 1e300;
-    int status = 0;
-    if (has_el) {
-      const double* mp = A.mp + (size_t)p * FTB_MP_STRIDE;
-      double fe[8][3];
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  // warps w and w + 4 share the lanes of sub-partition w % 4: each takes half of the block's columns
+  const TmemScratch TS{S.tmem_base + ((uint32_t)((w & 3) * 32) << 16) + (uint32_t)((w >> 2) * (BRICK_TMEM_COLS / 2)), &S.ji[0][tid]};
+  brick_load_pe(A, S, S.hdr[0], 0, tid);
+  brick_load_nodes(A, S, S.hdr[0], 0, 0, tid);
+  if (b + G < A.nB) brick_load_meta(A, S, b + G, 1, 1, tid);
+  cp_async_commit();
+
+  for (int it = 0; b < A.nB; b += G, ++it) {
+    const int cur = it & 1, nxt = cur ^ 1;
+    cp_async_wait<0>();
+    __syncthreads();  // S1: this brick's nodes and metadata, the next brick's metadata have arrived; the previous FINISH is done
+    const BrickHdr H = S.hdr[it % 3];
+    // m and fi_prev of the interior nodes (needed by FINISH only), the node -> force map
+    for (int l = tid; l < H.nInt; l += BRICK_NT) {
+      cp_async8(&S.lateI[0][l], A.m + H.ibase + l);
+      if (ENERGY) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cp_async8(&S.lateI[1 + c][l], A.fi[c] + H.ibase + l);
+      }
+    }
+    cp_async_commit();
+    if (tid == 0) {
+      mbar_expect_tx(&S.bar, 8 * BRICK_NLMAX * 2);
+      bulk_g2s(&S.map16[0][0], A.map16 + (size_t)b * 8 * BRICK_NLMAX, 8 * BRICK_NLMAX * 2, &S.bar);
+    }
+    // ---- START of the step for the brick's local nodes (shared memory in, shared memory out) ------------------------
+    {
+    const StepTimes T{S.times[0], S.times[1], S.times[2], S.times[3]};
+#pragma unroll
+    for (int r = 0; r < BRICK_NODE_TRIPS; ++r) {
+      const int l = tid + r * BRICK_NT;
+      if (l < H.nLoc) {
+        double uu[3], vv[3], aa[3], un[3];
+        unsigned fl;
+        if (l < H.nInt) {
+          fl = S.flI[cur][l];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { uu[c] = S.rawI[cur][c][l]; vv[c] = S.rawI[cur][3 + c][l]; aa[c] = S.rawI[cur][6 + c][l]; }
+        } else {
+          const int sidx = l - H.nInt;
+          fl = S.flS[sidx];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { uu[c] = S.rawS[c][sidx]; vv[c] = S.rawS[3 + c][sidx]; aa[c] = S.rawS[6 + c][sidx]; }
+        }
+        node_start_u(fl, T, bc_rate, uu, vv, aa, un);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) S.ust[c][l] = un[c];
+      }
+    }
+    }
+    __syncthreads();  // S2: the new displacements are staged
+    // ---- SETUP of the element (threads beyond the brick's last element repeat it: the tcgen05 instructions are warp-wide)
+    const bool has_el = tid < H.nEl;
+    const int pe = S.meta[cur].pe[tid];
+    const double* mp = A.mp + (size_t)(pe & 0x3FFFFFFF) * FTB_MP_STRIDE;
+    double det, dtk;
+    int status;
+    {
+      const int te = has_el ? tid : H.nEl - 1;
+      const uint4 cw = *reinterpret_cast<const uint4*>(&S.meta[cur].conn16[te][0]);
+      const BrickIn in{&S.xs[0][0], &S.ust[0][0], {cw.x, cw.y, cw.z, cw.w}};
+      status = hex8_brick_setup(in, mp, TS, &det, &dtk);
+    }
+    __syncthreads();  // S3: xs, rawS, this stage's metadata are free
+    // ---- the next brick's nodes and the metadata of the one after it: in flight under the Gauss loop -------------------
+    if (b + G < A.nB) {
+      const BrickHdr Hn = S.hdr[(it + 1) % 3];
+      brick_load_pe(A, S, Hn, nxt, tid);
+      brick_load_nodes(A, S, Hn, nxt, nxt, tid);
+      if (b + 2 * G < A.nB) brick_load_meta(A, S, b + 2 * G, cur, (it + 2) % 3, tid);
+    }
+    cp_async_commit();
+    // ---- LOOP --------------------------------------------------------------------------------------------------------
+    double fe[8][3];
+    {
       double d;
-      SmemScratchBrick S{scr + tid};
-      BrickIn in{scr + tid, ust, {cw.x, cw.y, cw.z, cw.w}};
-      status = hex8_element_brick_in<MATSEL>(in, MATSEL, mp, true, NoHistory(), NoOutput(), S, fe, &d);
-      dte = skip ? 1e300 : d;
+      status |= hex8_brick_loop<MATSEL>(MATSEL, mp, true, NoHistory(), NoOutput(), TS, det, dtk, fe, &d);
+      double dte = (has_el && !(pe >> 30)) ? d : 1e300;
+      unsigned long long bits = dt_to_bits(dte);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) scr[(3 * k + c) * BRICK_NT + tid] = fe[k][c];
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t2 = __shfl_xor_sync(0xffffffffu, bits, o);
+        bits = t2 < bits ? t2 : bits;
+      }
+      if (lane == 0) atomicMin(&A.sc->dtmin_bits, bits);
+      if (has_el && status) atomicOr(&A.sc->status, status);
     }
-    unsigned long long bits = dt_to_bits(dte);
+    // ---- FINISH: the brick's contributions per local node, one force component at a time through the exchange rows ----
+    // node roles of this thread: surface local node nInt + tid, and one run of interior nodes per warp.  (The header is
+    // read again here rather than kept in registers across the loop.)
+    const volatile BrickHdr& H2 = S.hdr[it % 3];
+    const int nInt = H2.nInt, nLoc = H2.nLoc;
+    const int per = (nInt + BRICK_NT / 32 - 1) / (BRICK_NT / 32);
+    const int li = w * per + lane;                       // interior node of this thread (if lane < per and li < nInt)
+    const bool has_i = lane < per && li < nInt;          // (per <= 32: BRICK_NIMAX <= 8 * 32)
+    const int ls = nInt + tid;                           // surface node of this thread
+    const bool has_s = ls < nLoc;
+    double fI[3] = {0.0, 0.0, 0.0}, fS[3] = {0.0, 0.0, 0.0};
+    mbar_wait(&S.bar, (unsigned)(it & 1));
+    cp_async_wait<1>();  // m and fi_prev of this brick have arrived (the next brick's copies may still be in flight)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long t2 = __shfl_xor_sync(0xffffffffu, bits, o);
-      bits = t2 < bits ? t2 : bits;
-    }
-    if ((tid & 31) == 0) atomicMin(&A.sc->dtmin_bits, bits);
-    if (status) atomicOr(&A.sc->status, status);
-  }
-  mbar_wait(&s_bar[0], 0);
-  __syncthreads();
-  // ---- epilogue: assemble the brick's contributions; finish the interior nodes, park the surface partials -------------
-  // surface nodes: one thread each, a coalesced store of the partial sum
-  for (int l = H.nInt + tid; l < H.nLoc; l += BRICK_NT) {
-    double f[3] = {0.0, 0.0, 0.0};
+    for (int c = 0; c < 3; ++c) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {  // ascending reference element id; + 0.0 for a missing entry is exact
-      const unsigned en = s_map[q * BRICK_NLMAX + l];
-      if (en != 0xFFFFu) { f[0] += scr[en]; f[1] += scr[en + BRICK_NT]; f[2] += scr[en + 2 * BRICK_NT]; }
+      for (int k = 0; k < 8; ++k) S.ji[k][tid] = fe[k][c];
+      __syncthreads();
+      if (has_i) {
+        double f = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {  // ascending reference element id
+          const unsigned en = S.map16[q][li];
+          if (en != 0xFFFFu) f += (&S.ji[0][0])[en];
+        }
+        fI[c] = f;
+      }
+      if (has_s) {
+        double f = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const unsigned en = S.map16[q][ls];
+          if (en != 0xFFFFu) f += (&S.ji[0][0])[en];
+        }
+        fS[c] = f;
+      }
+      __syncthreads();
     }
-    const size_t s = (size_t)H.slot0 + (l - H.nInt);
-    A.part[0][s] = f[0]; A.part[1][s] = f[1]; A.part[2][s] = f[2];
-  }
-  // interior nodes: spread evenly over the warps (a contiguous run of nodes per warp), finished here
-  double wke = 0.0, wint = 0.0, wext = 0.0;
-  {
-    const int w = tid >> 5, lane = tid & 31;
-    const int per = (H.nInt + BRICK_NT / 32 - 1) / (BRICK_NT / 32);
-    const int l1 = min((w + 1) * per, H.nInt);
-    for (int l = w * per + lane; l < l1; l += 32) {
-      const int g = H.ibase + l;
-      // the node's own state again (this block read it a few microseconds ago)
-      const unsigned fl = A.flags[g];
-      const double mm = A.m[g];
+    double wke = 0.0, wint = 0.0, wext = 0.0;
+    if (has_s) {
+      const size_t s = (size_t)H2.slot0 + tid;
+      A.part[0][s] = fS[0]; A.part[1][s] = fS[1]; A.part[2][s] = fS[2];
+    }
+    if (has_i) {
+      const StepTimes T{S.times[0], S.times[1], S.times[2], S.times[3]};
+      const int g = H2.ibase + li;
+      const unsigned fl = S.flI[cur][li];
+      const double mm = S.lateI[0][li];
       double uo[3], vo[3], ao[3], fprev[3] = {0.0, 0.0, 0.0}, fext[3] = {0.0, 0.0, 0.0};
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        uo[c] = A.u[c][g]; vo[c] = A.v[c][g]; ao[c] = A.a[c][g];
-        if (ENERGY) fprev[c] = A.fi[c][g];
+        uo[c] = S.rawI[cur][c][li]; vo[c] = S.rawI[cur][3 + c][li]; ao[c] = S.rawI[cur][6 + c][li];
+        if (ENERGY) fprev[c] = S.lateI[1 + c][li];
         if (A.fe[c]) fext[c] = A.fe[c][g];
-      }
-      double f[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const unsigned en = s_map[q * BRICK_NLMAX + l];
-        if (en != 0xFFFFu) { f[0] += scr[en]; f[1] += scr[en + BRICK_NT]; f[2] += scr[en + 2 * BRICK_NT]; }
       }
       double un[3], vs[3], as[3], vn[3], an[3];
       node_start(fl, T, bc_rate, uo, vo, ao, un, vs, as);
-      node_finish<ENERGY>(fl, T, mm, f, fext, fprev, uo, un, vs, as, vn, an, wke, wint, wext);
+      node_finish<ENERGY>(fl, T, mm, fI, fext, fprev, uo, un, vs, as, vn, an, wke, wint, wext);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         A.u[c][g] = un[c]; A.v[c][g] = vn[c]; A.a[c][g] = an[c];
-        if (A.store_fi) A.fi[c][g] = f[c];
+        if (A.store_fi) A.fi[c][g] = fI[c];
+      }
+    }
+    if (ENERGY) {  // fixed-shape tree inside the warp, one partial per (brick, warp)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        wke += __shfl_down_sync(0xffffffffu, wke, o);
+        wint += __shfl_down_sync(0xffffffffu, wint, o);
+        wext += __shfl_down_sync(0xffffffffu, wext, o);
+      }
+      if (lane == 0) {
+        const int i = b * (BRICK_NT / 32) + w;
+        A.epart[i] = wke;
+        A.epart[A.nEpart + i] = wint;
+        A.epart[2 * A.nEpart + i] = wext;
       }
     }
   }
-  if (ENERGY) {  // fixed-shape tree inside the warp, one partial per warp: no block barrier at the end of the kernel
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      wke += __shfl_down_sync(0xffffffffu, wke, o);
-      wint += __shfl_down_sync(0xffffffffu, wint, o);
-      wext += __shfl_down_sync(0xffffffffu, wext, o);
-    }
-    if ((tid & 31) == 0) {
-      const int i = b * (BRICK_NT / 32) + (tid >> 5);
-      A.epart[i] = wke;
-      A.epart[A.nEpart + i] = wint;
-      A.epart[2 * A.nEpart + i] = wext;
-    }
-  }
+  cp_async_wait<0>();
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base), "n"(BRICK_TMEM_COLS));
 }
 
 // ---------------------------------------------------------------------------------------------

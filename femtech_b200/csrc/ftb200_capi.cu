@@ -118,7 +118,9 @@ struct ftb200_ctx {
   long long nSlots = 0;
   BrickHdr* b_hdr = nullptr;
   uint16_t *b_conn16 = nullptr, *b_map16 = nullptr;
-  int *b_halo = nullptr, *b_xid = nullptr, *s_ell = nullptr, *s_ovoff = nullptr, *s_ovent = nullptr;
+  int *b_halo = nullptr, *b_pe = nullptr, *s_ell = nullptr, *s_ovoff = nullptr, *s_ovent = nullptr;
+  unsigned* b_flags32 = nullptr;
+  int brick_grid = 0;
   double* b_part[3] = {nullptr, nullptr, nullptr};
   // graph cache
   cudaGraphExec_t graph = nullptr;
@@ -356,7 +358,7 @@ void launch_step(ftb200_ctx* ctx, const double* recv) {
 // ---------------------------------------------------------------------------------------------------------------
 // Brick decomposition of an all-hexahedra mesh for k_brick / k_surf (ftb200_brick.cuh).  Elements are binned by their
 // centroid into boxes of dims[] mean element extents (a structured or voxel mesh gives exact dims[0] x dims[1] x dims[2]
-// bricks); a box with more than BRICK_NT elements or more than BRICK_NLMAX nodes is bisected at the median of its longest
+// bricks); a box with more than BRICK_NT elements, BRICK_NIMAX interior or BRICK_NSMAX surface nodes is bisected at the median of its longest
 // axis until it fits.  Bricks are numbered box by box, x fastest: neighbours in the launch order share surface nodes in L2.
 struct BrickPlan {
   int nB = 0;
@@ -364,19 +366,21 @@ struct BrickPlan {
   std::vector<int> elems;   // caller element ids, ascending inside each brick
 };
 
-void brick_split(const ftb200_ctx* ctx, const std::vector<float>& cen, std::vector<int>& list, size_t lo, size_t hi,
-                 std::vector<int>& stamp, int& stamp_id, std::vector<std::pair<size_t, size_t>>& out) {
+void brick_split(const ftb200_ctx* ctx, const std::vector<float>& cen, const std::vector<unsigned char>& deg, std::vector<int>& list,
+                 size_t lo, size_t hi, std::vector<int>& stamp, std::vector<unsigned char>& cnt, int& stamp_id,
+                 std::vector<std::pair<size_t, size_t>>& out) {
   const size_t n = hi - lo;
   bool fits = n <= (size_t)BRICK_NT;
-  if (fits) {  // count the nodes of the group
+  if (fits) {  // interior nodes (all their elements in the group) and surface nodes of the group
     ++stamp_id;
-    int nl = 0;
+    int nl = 0, ni = 0;
     for (size_t i = lo; i < hi; ++i)
       for (int k = 0; k < 8; ++k) {
         const int nd = ctx->h_conn[8 * (size_t)list[i] + k];
-        if (stamp[nd] != stamp_id) { stamp[nd] = stamp_id; ++nl; }
+        if (stamp[nd] != stamp_id) { stamp[nd] = stamp_id; cnt[nd] = 0; ++nl; }
+        if (++cnt[nd] == deg[nd]) ++ni;
       }
-    fits = nl <= BRICK_NLMAX;
+    fits = ni <= BRICK_NIMAX && nl - ni <= BRICK_NSMAX;
   }
   if (fits || n <= 1) { out.push_back({lo, hi}); return; }
   float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
@@ -393,8 +397,8 @@ void brick_split(const ftb200_ctx* ctx, const std::vector<float>& cen, std::vect
     const float va = cen[3 * (size_t)a + ax], vb = cen[3 * (size_t)b + ax];
     return va < vb || (va == vb && a < b);
   });
-  brick_split(ctx, cen, list, lo, mid, stamp, stamp_id, out);
-  brick_split(ctx, cen, list, mid, hi, stamp, stamp_id, out);
+  brick_split(ctx, cen, deg, list, lo, mid, stamp, cnt, stamp_id, out);
+  brick_split(ctx, cen, deg, list, mid, hi, stamp, cnt, stamp_id, out);
 }
 
 BrickPlan plan_bricks(const ftb200_ctx* ctx) {
@@ -437,12 +441,14 @@ BrickPlan plan_bricks(const ftb200_ctx* ctx) {
   std::vector<int> list(nE);
   for (int i = 0; i < nE; ++i) list[i] = key[i].second;
   std::vector<int> stamp(nN, 0);
+  std::vector<unsigned char> deg(nN, 0), cnt(nN, 0);
+  for (size_t i = 0; i < 8 * (size_t)nE; ++i) ++deg[ctx->h_conn[i]];  // (at most 8 per node: checked by the caller)
   int stamp_id = 0;
   std::vector<std::pair<size_t, size_t>> groups;
   for (size_t i = 0; i < (size_t)nE;) {
     size_t j = i;
     while (j < (size_t)nE && key[j].first == key[i].first) ++j;
-    brick_split(ctx, cen, list, i, j, stamp, stamp_id, groups);
+    brick_split(ctx, cen, deg, list, i, j, stamp, cnt, stamp_id, groups);
     i = j;
   }
   P.nB = (int)groups.size();
@@ -467,13 +473,14 @@ int brick_eparts(const ftb200_ctx* c) { return c->nB * (BRICK_NT / 32) + c->surf
 
 BrickArgs brick_args(ftb200_ctx* c) {
   BrickArgs A;
-  A.hdr = c->b_hdr; A.conn16 = c->b_conn16; A.xid = c->b_xid; A.halo = c->b_halo; A.map16 = c->b_map16;
+  A.hdr = c->b_hdr; A.conn16 = c->b_conn16; A.pe = c->b_pe; A.flags32 = c->b_flags32; A.halo = c->b_halo; A.map16 = c->b_map16;
+  A.nB = c->nB;
   for (int k = 0; k < 3; ++k) {
     A.X[k] = c->X[k]; A.u[k] = c->u[k]; A.v[k] = c->v[k]; A.a[k] = c->a[k]; A.fi[k] = c->fi[k];
     A.fe[k] = c->has_fe ? c->fe[k] : nullptr;
     A.part[k] = c->b_part[k];
   }
-  A.m = c->m; A.flags = c->flags; A.pid = c->pid; A.eflag = c->eflag; A.mp = c->mp;
+  A.m = c->m; A.mp = c->mp;
   A.epart = c->epart; A.nEpart = brick_eparts(c); A.sc = c->sc; A.store_fi = c->energy ? 1 : 0;
   return A;
 }
@@ -493,7 +500,7 @@ template <int MAT, bool EN>
 void launch_brick_k(ftb200_ctx* ctx, cudaStream_t s, const BrickArgs& A) {
   auto kfn = k_brick<MAT, EN>;
   cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRICK_SMEM_BYTES);  // per device
-  launch_k(ctx, kfn, dim3(ctx->nB), dim3(BRICK_NT), BRICK_SMEM_BYTES, s, A);
+  launch_k(ctx, kfn, dim3(ctx->brick_grid), dim3(BRICK_NT), BRICK_SMEM_BYTES, s, A);
 }
 void launch_step_brick(ftb200_ctx* ctx) {
   cudaStream_t s = ctx->stream;
@@ -581,7 +588,7 @@ void free_all(ftb200_ctx* c) {
   c->p2p_ready = false;
   if (c->p2p_graph) { cudaGraphExecDestroy(c->p2p_graph); c->p2p_graph = nullptr; }
   dfree(c->d_nref); dfree(c->d_nint); dfree(c->d_ell);
-  dfree(c->b_hdr); dfree(c->b_conn16); dfree(c->b_map16); dfree(c->b_halo); dfree(c->b_xid); dfree(c->s_ell); dfree(c->s_ovoff); dfree(c->s_ovent);
+  dfree(c->b_hdr); dfree(c->b_conn16); dfree(c->b_map16); dfree(c->b_halo); dfree(c->b_pe); dfree(c->b_flags32); dfree(c->s_ell); dfree(c->s_ovoff); dfree(c->s_ovent);
   dfree(c->b_part[0]); dfree(c->b_part[1]); dfree(c->b_part[2]);
   c->brick_ok = false;
   if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
@@ -980,7 +987,7 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
     const int nS = nN - nIntTot;
     std::vector<BrickHdr> hdr(nB);
     std::vector<uint16_t> conn16((size_t)nB * 8 * BRICK_NT, 0), map16((size_t)nB * 8 * BRICK_NLMAX, 0xFFFFu);
-    std::vector<int> halo((size_t)nB * BRICK_NLMAX, 0), sell(8 * (size_t)std::max(nS, 1), -1), scnt(std::max(nS, 1), 0);
+    std::vector<int> halo((size_t)nB * BRICK_NSMAX, 0), sell(8 * (size_t)std::max(nS, 1), -1), scnt(std::max(nS, 1), 0);
     std::vector<std::pair<int, int>> sover;
     std::vector<int> loc(nNp, -1), surf;
     std::vector<unsigned char> lcnt(BRICK_NLMAX);
@@ -995,15 +1002,15 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
         }
       std::sort(surf.begin(), surf.end());
       const int nInt_b = b_nint[b], nLoc = nInt_b + (int)surf.size();
-      if (nEl > BRICK_NT || nLoc > BRICK_NLMAX) return fail(ctx, FTB200_ERR_INPUT, "brick %d does not fit (%d elements, %d nodes)", b, nEl, nLoc);
-      for (size_t i = 0; i < surf.size(); ++i) { loc[surf[i]] = nInt_b + (int)i; halo[(size_t)b * BRICK_NLMAX + i] = surf[i]; }
+      if (nEl > BRICK_NT || nInt_b > BRICK_NIMAX || (int)surf.size() > BRICK_NSMAX) return fail(ctx, FTB200_ERR_INPUT, "brick %d does not fit (%d elements, %d nodes)", b, nEl, nLoc);
+      for (size_t i = 0; i < surf.size(); ++i) { loc[surf[i]] = nInt_b + (int)i; halo[(size_t)b * BRICK_NSMAX + i] = surf[i]; }
       std::fill(lcnt.begin(), lcnt.end(), 0);
       for (int i = 0; i < nEl; ++i)
         for (int k = 0; k < 8; ++k) {
           const int g = nint[ctx->h_conn[8 * (size_t)plan.elems[e0 + i] + k]];
           const int l = g < nIntTot ? g - b_ibase[b] : loc[g];
           conn16[((size_t)b * BRICK_NT + i) * 8 + k] = (uint16_t)l;
-          map16[((size_t)b * 8 + lcnt[l]++) * BRICK_NLMAX + l] = (uint16_t)(3 * k * BRICK_NT + i);
+          map16[((size_t)b * 8 + lcnt[l]++) * BRICK_NLMAX + l] = (uint16_t)(k * BRICK_NT + i);
         }
       hdr[b] = BrickHdr{e0, nEl, b_ibase[b], nInt_b, nLoc, (int)slot, 0, 0};
       for (size_t i = 0; i < surf.size(); ++i) {
@@ -1015,13 +1022,12 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       slot += (long long)surf.size();
       if (slot > 0x7fffff00LL) return fail(ctx, FTB200_ERR_INPUT, "too many surface partials for 32-bit slots");
     }
-    std::vector<int> xid(4 * (size_t)nE);
-    for (int t = 0; t < nE; ++t) {
-      const int* cn = &ctx->h_conn[8 * (size_t)ref_of[t]];
-      xid[4 * (size_t)t] = nint[cn[0]]; xid[4 * (size_t)t + 1] = nint[cn[1]]; xid[4 * (size_t)t + 2] = nint[cn[3]]; xid[4 * (size_t)t + 3] = nint[cn[4]];
+    if ((rc = dalloc(ctx, &ctx->b_pe, nE)) || (rc = dalloc(ctx, &ctx->b_flags32, nNp))) return rc;
+    {
+      int sms = 0;
+      CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+      ctx->brick_grid = std::min(nB, 2 * std::max(sms, 1));  // persistent blocks, two per SM
     }
-    if ((rc = dalloc(ctx, &ctx->b_xid, xid.size()))) return rc;
-    CK(cudaMemcpy(ctx->b_xid, xid.data(), xid.size() * sizeof(int), cudaMemcpyHostToDevice));
     ctx->nB = nB; ctx->nIntTot = nIntTot; ctx->nSurf = nS; ctx->nSlots = slot;
     ctx->surf_blocks = cdiv(nS, SURF_BLOCK);
     epart_blocks = std::max(epart_blocks, nB * (BRICK_NT / 32) + ctx->surf_blocks * (SURF_BLOCK / 32));
@@ -1594,6 +1600,7 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
   cudaStream_t s = ctx->stream;
   LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
   const bool brick = use_brick(ctx);
+  if (brick) LAUNCH(k_brick_prep, cdiv(std::max(ctx->nNp, ctx->nE), 256), 256, s, ctx->flags, ctx->b_flags32, ctx->nNp, ctx->pid, ctx->eflag, ctx->b_pe, ctx->nE);
   if (!brick) {  // (the brick-fused step starts each step itself)
     const NodeArgs N = node_args(ctx, nullptr);
     if (ctx->rigid) LAUNCH(k_rigid_step, 1, 32, s, ctx->sc, ctx->rigid, 1);

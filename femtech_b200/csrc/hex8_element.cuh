@@ -999,70 +999,76 @@ FTB_HD int hex8_element_affine_in(const In& in, int mat, const double* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// The parallelepiped element once more, for the brick kernel (k_brick): the same arithmetic as hex8_element_affine_in
-// with a 45-slot scratch.  cof(8 J0)[j][c] = det (8 J0)^-1[c][j], so only the inverse is kept and the determinant is
-// folded into the quadrature weights of the final butterfly (one multiplication per force mode instead of nine
-// scratch slots).  Differs from hex8_element_affine_in by rounding only (tests/test_element_math_cpu.py pins 1e-13).
-//
-// Scratch layout (45 doubles): 36 dU/dxi column entries (FTB_ACOL), then (8 J0)^-1 (9).
-#define FTB_BJI(c, j) (36 + (c) * 3 + (j))
-// staging slots of the reference nodes (nodes 0, 1, 3, 4): component 0 waits in column slots of component 1 (written
-// only after component 0 has been consumed), components 1 and 2 in the slots of the inverse (written last)
-#define FTB_BSTAGE_X(kk, c) ((c) == 0 ? (1 + 3 * (kk)) : (36 + ((c) - 1) * 4 + (kk)))
-#define FTB_BRICK_SLOTS 45
-
+// The parallelepiped element once more, for the brick kernel (k_brick): the same arithmetic as hex8_element_affine_in,
+// cut into the two phases of that kernel's software pipeline and with the scratch split by access pattern:
+//   hex8_brick_setup  nodal gather -> displacement modes -> the 36 dU/dxi column entries (st_col: the kernel keeps them
+//                     in TENSOR MEMORY, 72 columns of the thread's own lane), (8 J0)^-1 (st_ji: 9 shared-memory slots
+//                     that are re-read inside the loop), and the loop-invariant part of the element's stable dt;
+//   hex8_brick_loop   the eight Gauss points and the inverse butterfly.
+// cof(8 J0)[j][c] = det (8 J0)^-1[c][j], so only the inverse is kept and the determinant is folded into the quadrature
+// weights of the final butterfly.  Differs from hex8_element_affine_in by rounding only (tests/test_element_math_cpu.py).
 struct LocalScratchBrick {
-  double v[FTB_BRICK_SLOTS];
-  FTB_HD void st(int i, double x) { v[i] = x; }
-  FTB_HD double ld(int i) const { return v[i]; }
-  FTB_HD double ld_inloop(int i) const { return v[i]; }
+  double col[36], ji[9];
+  FTB_HD void st_col(int i, double x) { col[i] = x; }
+  FTB_HD void cols_written() const {}
+  FTB_HD void ld_cols9(const int idx[9], double out[9]) const {  // the nine column entries of one Gauss point
+    for (int k = 0; k < 9; ++k) out[k] = col[idx[k]];
+  }
+  FTB_HD void st_ji(int i, double x) { ji[i] = x; }
+  FTB_HD double ld_ji(int i) const { return ji[i]; }
 };
 
-template <int MATSEL, class In, class Hist, class Out, class Scratch>
-FTB_HD int hex8_element_brick_in(const In& in, int mat, const double* __restrict__ mp, const bool updHist,
-                                 const Hist& hist, const Out& out, Scratch& S, double fe[8][3], double* dtElem) {
+template <class In, class Scratch>
+FTB_HD int hex8_brick_setup(const In& in, const double* __restrict__ mp, Scratch& S, double* det_out, double* dtk_out) {
+  const double a = FTB_GP_A, a2 = FTB_GP_A * FTB_GP_A;
+  int status = 0;
+  double xm[7][3];
+  double J0[3][3];  // 8 dX/dxi = 4 x edge vectors (exact scaling)
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double x[4], nu[8], gU[7];
+    in.getX(c, x);
+    J0[c][0] = 4.0 * (x[1] - x[0]);
+    J0[c][1] = 4.0 * (x[2] - x[0]);
+    J0[c][2] = 4.0 * (x[3] - x[0]);
+    in.getU(c, nu);
+    hex_modes(nu, gU);
+    xm[0][c] = J0[c][0] + gU[0]; xm[1][c] = J0[c][1] + gU[1]; xm[2][c] = J0[c][2] + gU[2];
+    xm[3][c] = gU[3]; xm[4][c] = gU[4]; xm[5][c] = gU[5]; xm[6][c] = gU[6];
+    const double U12 = a * gU[3], U23 = a * gU[4], U13 = a * gU[5], U123 = a2 * gU[6];
+    {
+      const double A[3] = {gU[0], gU[1], gU[2]}, B[3] = {U12, U12, U13}, C[3] = {U13, U23, U23};
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const double ad = A[t] + U123, am = A[t] - U123, bc = B[t] + C[t], bm = B[t] - C[t];
+        S.st_col(FTB_ACOL(t, 3, c), ad + bc);
+        S.st_col(FTB_ACOL(t, 0, c), ad - bc);
+        S.st_col(FTB_ACOL(t, 1, c), am + bm);
+        S.st_col(FTB_ACOL(t, 2, c), am - bm);
+      }
+    }
+  }
+  S.cols_written();
+  double cJ[3][3];
+  cofactor3(J0, cJ);
+  const double det = J0[0][0] * cJ[0][0] + J0[0][1] * cJ[0][1] + J0[0][2] * cJ[0][2];  // 512 detJ0
+  if (!(det > 0.0)) status |= 2;
+  const double rdet = 1.0 / det;
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) S.st_ji(c * 3 + j, cJ[j][c] * rdet);  // J0^-1[c][j] = cof[j][c] / det
+  *det_out = det;
+  *dtk_out = det / (512.0 * hex_face_amax(xm) * mp[MP_CE]);  // dt = (V / A_max) / c_e with V = det J0 sum_gp det F
+  return status;
+}
+
+template <int MATSEL, class Hist, class Out, class Scratch>
+FTB_HD int hex8_brick_loop(int mat, const double* __restrict__ mp, const bool updHist, const Hist& hist, const Out& out,
+                           const Scratch& S, const double det, const double dtk, double fe[8][3], double* dtElem) {
   if (MATSEL >= 0) mat = MATSEL;
   const double a = FTB_GP_A, a2 = FTB_GP_A * FTB_GP_A;
   int status = 0;
-  double dtk = 0.0, det;
-  {
-    double xm[7][3];
-    double J0[3][3];  // 8 dX/dxi = 4 x edge vectors (exact scaling)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      double x[4], nu[8], gU[7];
-      in.getX(c, x);
-      J0[c][0] = 4.0 * (x[1] - x[0]);
-      J0[c][1] = 4.0 * (x[2] - x[0]);
-      J0[c][2] = 4.0 * (x[3] - x[0]);
-      in.getU(c, nu);
-      hex_modes(nu, gU);
-      xm[0][c] = J0[c][0] + gU[0]; xm[1][c] = J0[c][1] + gU[1]; xm[2][c] = J0[c][2] + gU[2];
-      xm[3][c] = gU[3]; xm[4][c] = gU[4]; xm[5][c] = gU[5]; xm[6][c] = gU[6];
-      const double U12 = a * gU[3], U23 = a * gU[4], U13 = a * gU[5], U123 = a2 * gU[6];
-      {
-        const double A[3] = {gU[0], gU[1], gU[2]}, B[3] = {U12, U12, U13}, C[3] = {U13, U23, U23};
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-          const double ad = A[t] + U123, am = A[t] - U123, bc = B[t] + C[t], bm = B[t] - C[t];
-          S.st(FTB_ACOL(t, 3, c), ad + bc);
-          S.st(FTB_ACOL(t, 0, c), ad - bc);
-          S.st(FTB_ACOL(t, 1, c), am + bm);
-          S.st(FTB_ACOL(t, 2, c), am - bm);
-        }
-      }
-    }
-    double cJ[3][3];
-    cofactor3(J0, cJ);
-    det = J0[0][0] * cJ[0][0] + J0[0][1] * cJ[0][1] + J0[0][2] * cJ[0][2];  // 512 detJ0
-    if (!(det > 0.0)) status |= 2;
-    const double rdet = 1.0 / det;
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) S.st(FTB_BJI(c, j), cJ[j][c] * rdet);  // J0^-1[c][j] = cof[j][c] / det
-    dtk = det / (512.0 * hex_face_amax(xm) * mp[MP_CE]);
-  }
   double vsum = 0.0;
   double phi[7][3];
 #pragma unroll
@@ -1079,17 +1085,20 @@ FTB_HD int hex8_element_brick_in(const In& in, int mat, const double* __restrict
     const int qx = b2 + 2 * b3, qe = b1 + 2 * b3, qz = b1 + 2 * b2;
     double F[3][3];
     {
+      const int idx[9] = {FTB_ACOL(0, qx, 0), FTB_ACOL(1, qe, 0), FTB_ACOL(2, qz, 0), FTB_ACOL(0, qx, 1), FTB_ACOL(1, qe, 1),
+                          FTB_ACOL(2, qz, 1), FTB_ACOL(0, qx, 2), FTB_ACOL(1, qe, 2), FTB_ACOL(2, qz, 2)};
       double Ji[3][3];
 #pragma unroll
       for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) Ji[c][j] = S.ld_inloop(FTB_BJI(c, j));
+        for (int j = 0; j < 3; ++j) Ji[c][j] = S.ld_ji(c * 3 + j);
+      double uc[9];
+      S.ld_cols9(idx, uc);  // (issued behind the shared-memory loads: their latency passes under the tensor-memory round trip)
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const double u0 = S.ld(FTB_ACOL(0, qx, i)), u1 = S.ld(FTB_ACOL(1, qe, i)), u2 = S.ld(FTB_ACOL(2, qz, i));
+      for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) F[i][j] = fma(u0, Ji[0][j], fma(u1, Ji[1][j], fma(u2, Ji[2][j], (i == j ? 1.0 : 0.0))));
-      }
+        for (int j = 0; j < 3; ++j)
+          F[i][j] = fma(uc[3 * i], Ji[0][j], fma(uc[3 * i + 1], Ji[1][j], fma(uc[3 * i + 2], Ji[2][j], (i == j ? 1.0 : 0.0))));
     }
     double cF[3][3];
     cofactor3(F, cF);
@@ -1106,7 +1115,7 @@ FTB_HD int hex8_element_brick_in(const In& in, int mat, const double* __restrict
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int j = 0; j < 3; ++j) Ji[c][j] = S.ld_inloop(FTB_BJI(c, j));
+      for (int j = 0; j < 3; ++j) Ji[c][j] = S.ld_ji(c * 3 + j);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {  // Q / det = P J0^-T
       const double Q0 = P[i][0] * Ji[0][0] + P[i][1] * Ji[0][1] + P[i][2] * Ji[0][2];
@@ -1133,6 +1142,15 @@ FTB_HD int hex8_element_brick_in(const In& in, int mat, const double* __restrict
 #pragma unroll
     for (int k = 0; k < 8; ++k) fe[k][c] = f[k];
   }
+  return status;
+}
+
+template <int MATSEL, class In, class Hist, class Out, class Scratch>
+FTB_HD int hex8_element_brick_in(const In& in, int mat, const double* __restrict__ mp, const bool updHist,
+                                 const Hist& hist, const Out& out, Scratch& S, double fe[8][3], double* dtElem) {
+  double det, dtk;
+  int status = hex8_brick_setup(in, mp, S, &det, &dtk);
+  status |= hex8_brick_loop<MATSEL>(mat, mp, updHist, hist, out, S, det, dtk, fe, dtElem);
   return status;
 }
 

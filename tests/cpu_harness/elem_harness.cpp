@@ -104,14 +104,14 @@ extern "C" int harness_element_affine_staged(const double* X24, const double* U2
   return st;
 }
 
-// hex8_element_brick_in (the element function of k_brick) with the kernel's staging plan replayed: the reference nodes
-// 0, 1, 3, 4 wait in FTB_BSTAGE_X slots of a poisoned scratch, the displacements come from a node-indexed table
+// hex8_brick_setup + hex8_brick_loop (the element function of k_brick, cut where the kernel's pipeline cuts it): the
+// reference nodes 0, 1, 3, 4 and the displacements come from node-indexed tables like the kernel's shared-memory staging
 namespace {
 struct HostStagedBrick {
-  const double* v;       // scratch
-  const double* utab;    // [3][8] component-major "shared-memory" displacement table
+  const double* xtab;    // [3][4] component-major reference coordinates of nodes 0, 1, 3, 4
+  const double* utab;    // [3][8] component-major displacement table
   void getX(const int c, double x[4]) const {
-    for (int k = 0; k < 4; ++k) x[k] = v[FTB_BSTAGE_X(k, c)];
+    for (int k = 0; k < 4; ++k) x[k] = xtab[4 * c + k];
   }
   void getU(const int c, double nu[8]) const {
     for (int k = 0; k < 8; ++k) nu[k] = utab[8 * c + k];
@@ -126,15 +126,18 @@ extern "C" int harness_element_brick(const double* X24, const double* U24, int m
   if (!ftb::hex8_is_affine(X)) return -1;
   const int nx[4] = {0, 1, 3, 4};
   ftb::LocalScratchBrick sc;
-  for (int i = 0; i < FTB_BRICK_SLOTS; ++i) sc.v[i] = 1e300;  // poison
-  double utab[24];
+  for (int i = 0; i < 36; ++i) sc.col[i] = 1e300;  // poison
+  for (int i = 0; i < 9; ++i) sc.ji[i] = 1e300;
+  double utab[24], xtab[12];
   for (int c = 0; c < 3; ++c) {
     for (int k = 0; k < 8; ++k) utab[8 * c + k] = U24[3 * k + c];
-    for (int k = 0; k < 4; ++k) sc.v[FTB_BSTAGE_X(k, c)] = X24[3 * nx[k] + c];
+    for (int k = 0; k < 4; ++k) xtab[4 * c + k] = X24[3 * nx[k] + c];
   }
   HostHist hh{hist144};
   HostOut ho{F72, detF8, pk2_48};
-  int st = ftb::hex8_element_brick_in<-1>(HostStagedBrick{sc.v, utab}, mat, mp, updHist != 0, hh, ho, sc, fe, dtElem);
+  double det, dtk;
+  int st = ftb::hex8_brick_setup(HostStagedBrick{xtab, utab}, mp, sc, &det, &dtk);
+  st |= ftb::hex8_brick_loop<-1>(mat, mp, updHist != 0, hh, ho, sc, det, dtk, fe, dtElem);
   for (int k = 0; k < 8; ++k)
     for (int c = 0; c < 3; ++c) fe24[3 * k + c] = fe[k][c];
   return st;
