@@ -477,10 +477,17 @@ class LocalGroup:
     def run_p2p(self, tMax, steps):
         # direct launches (no graph capture/instantiate while a peer's wait kernel may be spinning: all the
         # ranks share one CUDA context here; separate processes use the captured graph)
+        # Enqueued in chunks of a few steps, rank by rank: a rank's wait kernel spins until its neighbours' steps arrive, and
+        # the host cannot enqueue those while it is blocked on a full launch queue behind the first rank's whole run
+        # (mixed-material partitions launch a dozen kernels per step).
         for m in self.models:
             m.profile(True)
-        for m in self.models:
-            m.run_async(tMax, steps)
+        left = int(steps)
+        while left > 0:
+            c = min(left, 8)
+            for m in self.models:
+                m.run_async(tMax, c)
+            left -= c
         self._sync()
         for m in self.models:
             m._poll()

@@ -44,6 +44,24 @@ def cube_mesh(n, L=CUBE_L, jitter=0.0, seed=1234, nparts_z=1):
     return np.ascontiguousarray(X), np.ascontiguousarray(conn), pid
 
 
+def box_mesh(Nx, Ny, Nz, h):
+    """Structured Nx x Ny x Nz hex8 box with spacing h, numbered like cube_mesh (node id = i + (Nx+1) j + (Nx+1)(Ny+1) k,
+    element id = i + Nx j + Nx Ny k): the global mesh of femtech_b200.dist.brick_partition's per-rank bricks."""
+    kk, jj, ii = np.meshgrid(np.arange(Nz + 1), np.arange(Ny + 1), np.arange(Nx + 1), indexing="ij")
+    X = np.stack([ii.reshape(-1) * h, jj.reshape(-1) * h, kk.reshape(-1) * h], axis=-1).astype(np.float64)
+    ek, ej, ei = np.meshgrid(np.arange(Nz), np.arange(Ny), np.arange(Nx), indexing="ij")
+    ei, ej, ek = ei.reshape(-1), ej.reshape(-1), ek.reshape(-1)
+    nx1, nxy = Nx + 1, (Nx + 1) * (Ny + 1)
+
+    def nid(i, j, k):
+        return (i + nx1 * j + nxy * k).astype(np.int32)
+
+    conn = np.stack([nid(ei, ej, ek), nid(ei + 1, ej, ek), nid(ei + 1, ej + 1, ek), nid(ei, ej + 1, ek),
+                     nid(ei, ej, ek + 1), nid(ei + 1, ej, ek + 1), nid(ei + 1, ej + 1, ek + 1),
+                     nid(ei, ej + 1, ek + 1)], axis=1).astype(np.int32)
+    return np.ascontiguousarray(X), np.ascontiguousarray(conn), np.zeros(conn.shape[0], np.int32)
+
+
 KUHN_TETS = ((0, 1, 2, 6), (0, 2, 3, 6), (0, 3, 7, 6), (0, 7, 4, 6), (0, 4, 5, 6), (0, 5, 1, 6))
 
 

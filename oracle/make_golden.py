@@ -98,6 +98,10 @@ def main():
         group_g(tmp)
         shutil.rmtree(tmp, ignore_errors=True)
         return
+    if only == "long":
+        group_h(tmp)
+        shutil.rmtree(tmp, ignore_errors=True)
+        return
     if only in ("injury", "rigid"):
         X, conn, pid = mesh.cube_mesh(6, jitter=0.05, nparts_z=3)
         f6 = os.path.join(tmp, "cube6mix.inp")
@@ -110,6 +114,7 @@ def main():
         group_f(tmp, f6)
     if only == "":
         group_g(tmp)
+        group_h(tmp)
     shutil.rmtree(tmp, ignore_errors=True)
 
 
@@ -189,6 +194,20 @@ def group_g(tmp):
         d, en, _ = run_ref(f, mats, props, 1, 150, 0.005, 0.0009, injury_exclude=[])
         save(name, d, en[-1:], dict(tMax=0.005, dMax=0.0009, exclude=[]),
              MESH_KEYS + ["eptr"] + STATE_KEYS + GP_KEYS + INJ_KEYS)
+
+
+def group_h(tmp):
+    # (H) the north-star bar itself: 1000 steps on a jittered mesh for the three materials the kernels specialise
+    #     (neo-Hookean, HGO, HGO + Prony), ramp chosen so that the pull reaches ~14 % of the edge after 1000 steps
+    X, conn, pid = mesh.cube_mesh(4, jitter=0.1)
+    f4 = os.path.join(tmp, "cube4j_long.inp")
+    mesh.write_abaqus_inp(f4, X, conn, pid)
+    HGO = list(BRAIN[:4]) + [10.0, 0, 0, 0, 0]
+    for name, mid, props, tMax, dMax in (("cube4j_m1_1k", 1, SOFT, 4.0, 0.002), ("cube4j_m4_1k", 4, HGO, 0.004, 0.0016),
+                                         ("cube4j_m5_1k", 5, BRAIN, 0.004, 0.0016)):
+        d, en, _ = run_ref(f4, [mid], props, 1, 1000, tMax, dMax)
+        assert int(d[0]["steps"][0]) == 1000, d[0]["steps"]
+        save(name, d, en[-1:], dict(tMax=tMax, dMax=dMax), MESH_KEYS + STATE_KEYS + GP_KEYS)
 
 
 def group_e(tmp, f6):

@@ -32,7 +32,8 @@ def make_model(d, **kw):
     return m
 
 
-CASES = ["ex9_1elt", "cube4j_m1", "cube4j_m2", "cube4j_m3", "cube4j_m4", "cube4j_m5", "cube6mix_p1", "bench10_p1"]
+CASES = ["ex9_1elt", "cube4j_m1", "cube4j_m2", "cube4j_m3", "cube4j_m4", "cube4j_m5", "cube6mix_p1", "bench10_p1",
+         "cube4j_m1_1k", "cube4j_m4_1k", "cube4j_m5_1k"]  # _1k: the reference's own state after 1000 steps, materials 1, 4, 5, jittered mesh
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -659,10 +660,11 @@ def test_brain_like_example_runs_all_next_rows_together(tmp_path):
     assert a["PartID"].size == 12 ** 3 and set(np.unique(a["PartID"])) == {0, 1, 2} and "CSDM-15" in a
 
 
-@pytest.mark.parametrize("var", ["FTB200_ENERGY_ASYNC=0", "FTB200_BRICK=0"])
+@pytest.mark.parametrize("var", ["FTB200_ENERGY_ASYNC=0", "FTB200_BRICK=1"])
 def test_off_switches_of_defaults_still_match_the_oracle(var):
-    """The off-switches of two defaults (energy reduction on the helper stream; the brick-fused step) must stay correct:
-    the smoke run (mixed materials 1 + 5, 25 steps, checked against the oracle) under each of them."""
+    """The switches must leave a correct path: the energy reduction on the main stream, and the brick-fused step asked for
+    on a mesh that does not qualify (the two-kernel step must take over silently): the smoke run (mixed materials 1 + 5,
+    25 steps, checked against the oracle) under each of them."""
     import os
     import subprocess
     import sys

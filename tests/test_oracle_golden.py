@@ -13,7 +13,8 @@ from conftest import golden, rank_dict
 from femtech_b200 import mesh
 from oracle import pyoracle as po
 
-SINGLE = ["ex9_1elt", "bench10_p1", "cube4j_m1", "cube4j_m2", "cube4j_m3", "cube4j_m4", "cube4j_m5", "cube6mix_p1"]
+SINGLE = ["ex9_1elt", "bench10_p1", "cube4j_m1", "cube4j_m2", "cube4j_m3", "cube4j_m4", "cube4j_m5", "cube6mix_p1",
+          "cube4j_m1_1k", "cube4j_m4_1k", "cube4j_m5_1k"]  # _1k: 1000 steps (the north-star bar), oracle/make_golden.py group H
 MULTI = ["bench10_p2", "bench10_p4", "bench10_p8", "cube6mix_p3"]
 
 
