@@ -66,6 +66,17 @@ SIGNATURES = {
     "ftb200_gauss_point_count": (_ll, [_vp]),
     "ftb200_affine_element_count": (_ll, [_vp]),
     "ftb200_brick_info": (C.c_int, [_vp, C.POINTER(_ll)]),
+    "ftb200_device_count": (C.c_int, []),
+    "ftb200_halo_pack_host": (C.c_int, [_vp, C.c_int, _dp]),
+    "ftb200_halo_add_host": (C.c_int, [_vp, C.c_int, _dp]),
+    "ftb200_get_force_begin": (C.c_int, [_vp, _dp, _dp, C.c_double, _dp]),
+    "ftb200_get_force_end": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "ftb200_get_dtmin": (C.c_int, [_vp, _dp]),
+    "ftb200_set_dtmin": (C.c_int, [_vp, C.c_double]),
+    "ftb200_explicit_begin_force_host": (C.c_int, [_vp, _dp]),
+    "ftb200_explicit_begin_finish_host": (C.c_int, [_vp, _dp]),
+    "ftb200_step_begin_host": (C.c_int, [_vp, _dp, _dp]),
+    "ftb200_step_end_host": (C.c_int, [_vp, _dp, C.c_double]),
     "ftb200_brick_maps": (C.c_int, [_vp, _ip, _ip]),
     "ftb200_set_rigid_bc": (C.c_int, [_vp, _ip, C.POINTER(_dp), C.POINTER(_dp), _ip, C.c_int]),
     "ftb200_get_rigid_state": (C.c_int, [_vp, _dp, _dp, _ip]),

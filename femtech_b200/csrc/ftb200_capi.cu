@@ -99,6 +99,7 @@ struct ftb200_ctx {
   int *d_sendNodeIndex = nullptr, *halo_nodes = nullptr, *halo_off = nullptr, *halo_slot = nullptr,
       *halo_node_idx = nullptr;
   const double* halo_recv_cur = nullptr;
+  double *d_xsend = nullptr, *d_xrecv = nullptr;  // exchange windows of the host-buffer (MPI host) entry points
   // peer-memory transport
   char* p2p_window = nullptr;
   size_t p2p_bytes = 0;
@@ -592,6 +593,7 @@ void free_all(ftb200_ctx* c) {
   dfree(c->b_part[0]); dfree(c->b_part[1]); dfree(c->b_part[2]);
   c->brick_ok = false;
   if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+  dfree(c->d_xsend); dfree(c->d_xrecv);
   dfree(c->d_sendNodeIndex); dfree(c->halo_nodes); dfree(c->halo_off); dfree(c->halo_slot); dfree(c->halo_node_idx);
   if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
 }
@@ -1798,6 +1800,122 @@ int ftb200_step_end(ftb200_ctx* ctx, const double* recv_dev) {
   ctx->halo_recv_cur = ctx->halo_count ? recv_dev : nullptr;
   return FTB200_OK;
 }
+// ---------------------------------------------------------------------------------------------------------------
+// Host-buffer variants of the exchange entry points, for a host that moves the shared-node windows itself (the
+// reference's MPI_Isend / MPI_Irecv of sendNodeDisplacement / recvNodeDisplacement, GetForce_3D.cpp:54-102,
+// Mass3D.cpp:77-125) and has no CUDA of its own: the device windows live inside the context.
+static int ensure_xwin(ftb200_ctx* ctx) {
+  if (ctx->d_xsend || !ctx->halo_count) return 0;
+  int rc;
+  if ((rc = dalloc(ctx, &ctx->d_xsend, 3 * (size_t)ctx->halo_count)) || (rc = dalloc(ctx, &ctx->d_xrecv, 3 * (size_t)ctx->halo_count))) return rc;
+  return 0;
+}
+static int xsend_to_host(ftb200_ctx* ctx, double* send_host) {
+  if (!ctx->halo_count) return 0;
+  CK(cudaMemcpyAsync(send_host, ctx->d_xsend, 3 * (size_t)ctx->halo_count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+static int xrecv_from_host(ftb200_ctx* ctx, const double* recv_host) {
+  if (!ctx->halo_count) return 0;
+  CK(cudaMemcpyAsync(ctx->d_xrecv, recv_host, 3 * (size_t)ctx->halo_count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+int ftb200_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+int ftb200_halo_pack_host(ftb200_ctx* ctx, int field, double* send_host) {
+  if (!ctx || !ctx->shape_ok || (ctx->halo_count && !send_host)) return fail(ctx, FTB200_ERR_INPUT, "halo_pack_host: bad arguments");
+  int rc;
+  if ((rc = ensure_xwin(ctx)) || (ctx->halo_count && (rc = ftb200_halo_pack(ctx, field, ctx->d_xsend)))) return rc;
+  return xsend_to_host(ctx, send_host);
+}
+int ftb200_halo_add_host(ftb200_ctx* ctx, int field, const double* recv_host) {
+  if (!ctx || !ctx->shape_ok || (ctx->halo_count && !recv_host)) return fail(ctx, FTB200_ERR_INPUT, "halo_add_host: bad arguments");
+  int rc;
+  if (!ctx->halo_count) return FTB200_OK;
+  if ((rc = ensure_xwin(ctx)) || (rc = xrecv_from_host(ctx, recv_host)) || (rc = ftb200_halo_add(ctx, field, ctx->d_xrecv))) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return FTB200_OK;
+}
+// legacy GetForce on several ranks: local element forces and the packed partial sums of the shared nodes ...
+int ftb200_get_force_begin(ftb200_ctx* ctx, const double* displacements, const double* fe, double dt, double* send_host) {
+  if (!ctx || !ctx->shape_ok || !displacements || (ctx->halo_count && !send_host)) return fail(ctx, FTB200_ERR_INPUT, "get_force_begin: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ensure_xwin(ctx)) || (rc = legacy_force_local(ctx, displacements, fe, dt))) return rc;
+  if (ctx->halo_count) {
+    LAUNCH(k_gather_shared, cdiv(ctx->nshared, 128), 128, ctx->stream, ctx->felem, ctx->node_off, ctx->node_ent, ctx->halo_nodes,
+           ctx->fnet[0], ctx->fnet[1], ctx->fnet[2], ctx->nshared, ctx->nE);
+    LAUNCH(k_halo_pack, cdiv(ctx->halo_count, 256), 256, ctx->stream, ctx->fnet[0], ctx->fnet[1], ctx->fnet[2], ctx->d_sendNodeIndex,
+           ctx->d_xsend, ctx->halo_count);
+  }
+  return xsend_to_host(ctx, send_host);
+}
+// ... and, once the host has exchanged them, the assembled fi (+ neighbours in ascending neighbour order) and f_net
+int ftb200_get_force_end(ftb200_ctx* ctx, const double* recv_host, double* fi, double* f_net) {
+  if (!ctx || !ctx->shape_ok || (ctx->halo_count && !recv_host)) return fail(ctx, FTB200_ERR_INPUT, "get_force_end: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = xrecv_from_host(ctx, recv_host))) return rc;
+  const NodeArgs N = node_args(ctx, ctx->halo_count ? ctx->d_xrecv : nullptr);
+  LAUNCH(k_gather_force, ctx->node_blocks, NODE_BLOCK, ctx->stream, N, ctx->fnet[0], ctx->fnet[1], ctx->fnet[2]);
+  ctx->halo_recv_cur = ctx->halo_count ? ctx->d_xrecv : nullptr;
+  if (fi && (rc = download_aos(ctx, ctx->fi, fi, 0))) return rc;
+  if (f_net && (rc = download_aos(ctx, ctx->fnet, f_net, 1))) return rc;
+  CK(cudaGetLastError());
+  int status = 0;
+  CK(cudaMemcpyAsync(&status, &ctx->sc->status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (status & 1) return fail(ctx, FTB200_ERR_MATERIAL, "Unknown material type");
+  return FTB200_OK;
+}
+// the cross-rank MIN of the stable time step: read this rank's candidate, write the global one (StableTimeStep.cpp:33)
+int ftb200_get_dtmin(ftb200_ctx* ctx, double* dtmin_local) {
+  if (!ctx || !ctx->shape_ok || !dtmin_local) return fail(ctx, FTB200_ERR_INPUT, "get_dtmin: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // the interior elements of a split step (no-op otherwise)
+  CK(cudaMemcpyAsync(dtmin_local, &ctx->sc->dtmin_bits, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return FTB200_OK;
+}
+int ftb200_set_dtmin(ftb200_ctx* ctx, double dtmin_global) {
+  if (!ctx || !ctx->shape_ok) return fail(ctx, FTB200_ERR_INPUT, "set_dtmin: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(&ctx->sc->dtmin_bits, &dtmin_global, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // the source is the caller's stack
+  return FTB200_OK;
+}
+int ftb200_explicit_begin_force_host(ftb200_ctx* ctx, double* send_host) {
+  if (!ctx || !ctx->shape_ok || (ctx->halo_count && !send_host)) return fail(ctx, FTB200_ERR_INPUT, "explicit_begin_force_host: bad arguments");
+  int rc;
+  if ((rc = ensure_xwin(ctx)) || (rc = ftb200_explicit_begin_force(ctx, ctx->halo_count ? ctx->d_xsend : nullptr))) return rc;
+  return xsend_to_host(ctx, send_host);
+}
+int ftb200_explicit_begin_finish_host(ftb200_ctx* ctx, const double* recv_host) {
+  if (!ctx || !ctx->shape_ok || (ctx->halo_count && !recv_host)) return fail(ctx, FTB200_ERR_INPUT, "explicit_begin_finish_host: bad arguments");
+  int rc;
+  if ((rc = xrecv_from_host(ctx, recv_host))) return rc;
+  return ftb200_explicit_begin_finish(ctx, ctx->halo_count ? ctx->d_xrecv : nullptr);
+}
+// one step of the loop with the exchange on the host: elements + packed partials out, this rank's dt candidate out ...
+int ftb200_step_begin_host(ftb200_ctx* ctx, double* send_host, double* dtmin_local) {
+  if (!ctx || !ctx->begun || (ctx->halo_count && !send_host) || !dtmin_local) return fail(ctx, FTB200_ERR_INPUT, "step_begin_host: bad arguments");
+  int rc;
+  if ((rc = ensure_xwin(ctx)) || (rc = ftb200_step_begin(ctx, ctx->halo_count ? ctx->d_xsend : nullptr, nullptr)) ||
+      (rc = xsend_to_host(ctx, send_host)))
+    return rc;
+  return ftb200_get_dtmin(ctx, dtmin_local);
+}
+// ... neighbours' partials and the global dt in, scalar update + node kernel
+int ftb200_step_end_host(ftb200_ctx* ctx, const double* recv_host, double dtmin_global) {
+  if (!ctx || !ctx->begun || (ctx->halo_count && !recv_host)) return fail(ctx, FTB200_ERR_INPUT, "step_end_host: bad arguments");
+  int rc;
+  if ((rc = ftb200_set_dtmin(ctx, dtmin_global)) || (rc = xrecv_from_host(ctx, recv_host))) return rc;
+  return ftb200_step_end(ctx, ctx->halo_count ? ctx->d_xrecv : nullptr);
+}
+
 int ftb200_p2p_export(ftb200_ctx* ctx, void* handle_out, void** window_out) {
   if (!ctx || !ctx->shape_ok) return fail(ctx, FTB200_ERR_INPUT, "p2p_export: call shape_functions first");
   CK(cudaSetDevice(ctx->device));

@@ -164,6 +164,31 @@ int ftb200_halo_count(const ftb200_ctx *ctx);
  * slice of recv.  field: 0 = internal force, 1 = lumped mass. */
 int ftb200_halo_pack(ftb200_ctx *ctx, int field, double *send_dev);
 int ftb200_halo_add(ftb200_ctx *ctx, int field, const double *recv_dev);
+/* HOST-buffer variants for a host that moves the windows itself and has no CUDA of its own -- the reference's MPI ranks:
+ * send_host / recv_host are the reference's sendNodeDisplacement / recvNodeDisplacement arrays (3*halo_count doubles),
+ * exchanged by the caller with the very MPI_Isend / MPI_Irecv loop of GetForce_3D.cpp:63-91 / Mass3D.cpp:86-114.
+ * The device-side windows live inside the context.  (integration/femtech_host.cpp under mpirun -np N.) */
+int ftb200_device_count(void);
+int ftb200_halo_pack_host(ftb200_ctx *ctx, int field, double *send_host);
+int ftb200_halo_add_host(ftb200_ctx *ctx, int field, const double *recv_host);
+/* GetForce_3D.cpp:5-102 on a rank with neighbours, around the exchange: element loop + local scatter + the partial sums
+ * of the shared nodes packed (:15-61), then -- after the caller's exchange -- neighbour sum in ascending neighbour
+ * order and f_net (:92-97, :49-51). */
+int ftb200_get_force_begin(ftb200_ctx *ctx, const double *displacements, const double *fe, double dt, double *send_host);
+int ftb200_get_force_end(ftb200_ctx *ctx, const double *recv_host, double *fi, double *f_net);
+/* StableTimeStep.cpp:33: this rank's candidate out, MPI_Allreduce(MIN) by the caller, the global value back in. */
+int ftb200_get_dtmin(ftb200_ctx *ctx, double *dtmin_local);
+int ftb200_set_dtmin(ftb200_ctx *ctx, double dtmin_global);
+/* explicit_begin and the time step of the resident loop with the exchange on the host (the sequence of
+ * ftb200_explicit_begin_dt/_force/_finish and ftb200_step_begin/_join/_end below, host buffers instead of device ones):
+ *   ftb200_explicit_begin_dt(.., NULL); ftb200_get_dtmin; [Allreduce MIN]; ftb200_set_dtmin;
+ *   ftb200_explicit_begin_force_host(send); [exchange]; ftb200_explicit_begin_finish_host(recv);
+ *   ftb200_run_begin(tMax, steps); per step: ftb200_step_begin_host(send, &dt_local); [exchange, Allreduce MIN];
+ *   ftb200_step_end_host(recv, dt_global). */
+int ftb200_explicit_begin_force_host(ftb200_ctx *ctx, double *send_host);
+int ftb200_explicit_begin_finish_host(ftb200_ctx *ctx, const double *recv_host);
+int ftb200_step_begin_host(ftb200_ctx *ctx, double *send_host, double *dtmin_local);
+int ftb200_step_end_host(ftb200_ctx *ctx, const double *recv_host, double dtmin_global);
 /* Resident path for a rank with shared nodes, split around the exchange (one call sequence per time step):
  *   ftb200_run_begin(tMax, steps)   once per run: arms the loop and performs the first kick + drift + BC
  *   ftb200_step_begin(send_dev, &dtmin_dev)

@@ -61,12 +61,32 @@ static void ensure_ctx() {
       TerminateFemTech(3);
     }
   }
-  int ndev_rank = world_rank;  /* one rank per GPU */
+  /* one rank per GPU; with fewer GPUs than ranks (a test box) the ranks share the devices round robin */
+  const int ndev = ftb200_device_count();
   const char *ev = getenv("FTB200_DEVICE");
-  check(ftb200_create(world_rank, world_size, ev ? atoi(ev) : ndev_rank, &g_ctx));
+  check(ftb200_create(world_rank, world_size, ev ? atoi(ev) : (ndev > 0 ? world_rank % ndev : 0), &g_ctx));
   check(ftb200_upload_mesh_mixed(g_ctx, coordinates, connectivity, eptr, pid, nNodes, nelements));
   check(ftb200_upload_materials(g_ctx, materialID, properties, nPIDglobal));
   check(ftb200_upload_comm(g_ctx, sendProcessCount, sendProcessID, sendNeighbourCountCum, sendNodeIndex));
+}
+
+/* ---- the shared-node exchange of the reference, kept as it is: sendNodeDisplacement -> neighbours -> recvNodeDisplacement
+ * with one MPI_Isend / MPI_Irecv per neighbour (GetForce_3D.cpp:63-91, Mass3D.cpp:86-114).  The device packs and adds
+ * (ftb200_*_host entry points); the transport is the host's MPI. ------------------------------------------------------ */
+static void exchange_shared_nodes(int tag) {
+  if (world_size == 1 || sendProcessCount == 0) return;
+  MPI_Request *req = (MPI_Request *)malloc(sizeof(MPI_Request) * 2 * sendProcessCount);
+  for (int i = 0; i < sendProcessCount; ++i) {
+    const int location = sendNeighbourCountCum[i] * ndim, size = ndim * sendNeighbourCount[i];
+    MPI_Isend(&sendNodeDisplacement[location], size, MPI_DOUBLE, sendProcessID[i], tag, MPI_COMM_WORLD, &req[i]);
+  }
+  for (int i = 0; i < sendProcessCount; ++i) {
+    const int location = sendNeighbourCountCum[i] * ndim, size = ndim * sendNeighbourCount[i];
+    MPI_Irecv(&recvNodeDisplacement[location], size, MPI_DOUBLE, sendProcessID[i], tag, MPI_COMM_WORLD, &req[sendProcessCount + i]);
+  }
+  MPI_Status status;
+  for (int i = 0; i < 2 * sendProcessCount; ++i) MPI_Wait(&req[i], &status);
+  free(req);
 }
 
 /* ---- src/fem/AllocateArrays.cpp:29-153 ----------------------------------------------------------- */
@@ -130,11 +150,16 @@ void AssembleLumpedMass(void) {
   ensure_ctx();
   mass = (double *)calloc(nDOF, sizeof(double));
   if (!mass) { FILE_LOG_SINGLE(ERROR, "Allocation of mass matrix failed"); TerminateFemTech(12); }
-  if (world_size > 1) {
-    FILE_LOG_SINGLE(ERROR, "femtech_b200 legacy mode is single rank; multi-GPU runs use the resident path (femtech_b200.dist)");
-    TerminateFemTech(3);
+  if (world_size == 1) {
+    check(ftb200_lumped_mass(g_ctx, mass));
+    return;
   }
-  check(ftb200_lumped_mass(g_ctx, mass));
+  /* Mass3D.cpp:77-125 updateMassMatrixNeighbour: the shared nodes receive their neighbours' share */
+  check(ftb200_lumped_mass(g_ctx, NULL));
+  check(ftb200_halo_pack_host(g_ctx, 1, sendNodeDisplacement));
+  exchange_shared_nodes(7132);
+  check(ftb200_halo_add_host(g_ctx, 1, recvNodeDisplacement));
+  check(ftb200_get_mass(g_ctx, mass));
 }
 static void implicit_only(const char *what) {
   FILE_LOG_SINGLE(ERROR, "%s belongs to the dense implicit solvers, which femtech_b200 does not replace", what);
@@ -150,7 +175,17 @@ void GetForce_3D() {
   g_state_gen++;
   bool anyFe = false;
   for (int i = 0; i < nDOF && !anyFe; ++i) anyFe = fe[i] != 0.0;
-  check(ftb200_get_force(g_ctx, displacements, anyFe ? fe : NULL, dt, fi, f_net));
+  if (world_size == 1) {
+    check(ftb200_get_force(g_ctx, displacements, anyFe ? fe : NULL, dt, fi, f_net));
+    return;
+  }
+  /* GetForce_3D.cpp:54-102 updateInternalForceNeighbour around the reference's own MPI exchange.  fe is uploaded on every
+   * rank as soon as one rank has any (the captured kernels' arguments must agree across the step). */
+  int anyGlobal = anyFe ? 1 : 0;
+  MPI_Allreduce(MPI_IN_PLACE, &anyGlobal, 1, MPI_INT, MPI_MAX, MPI_COMM_WORLD);
+  check(ftb200_get_force_begin(g_ctx, displacements, anyGlobal ? fe : NULL, dt, sendNodeDisplacement));
+  exchange_shared_nodes(2169);
+  check(ftb200_get_force_end(g_ctx, recvNodeDisplacement, fi, f_net));
 }
 void GetForce() {
   if (ndim != 3) { FILE_LOG_SINGLE(ERROR, "GetForce function not yet implemented for %dD", ndim); TerminateFemTech(3); }
@@ -251,6 +286,54 @@ void femtech_b200_set_rigid_bc(const int sizes[6], const double *const t[6], con
   g_rigid = true;
   g_energy_every = energy_every;
 }
+/* Several ranks: one partition per GPU, the reference's ParMETIS split (PartitionMesh.cpp:23-83) as it stands in the
+ * globals.  Two transports for the shared-node sum and the dt MIN of every step:
+ *   p2p   peer-memory windows over NVLink (CUDA IPC handles exchanged once with MPI_Allgather, then no MPI and no host in
+ *         the loop: the whole step is a CUDA graph) -- the default when every rank has its own GPU;
+ *   host  the reference's own MPI_Isend / MPI_Irecv exchange and MPI_Allreduce(MIN), one round per step, the device packing
+ *         and adding -- the default when ranks share a GPU (processes on one device time-slice: a kernel that waits for a
+ *         peer's flag would wait for the peer's time slice), FTB200_MPI_TRANSPORT=host|p2p overrides. */
+static bool g_p2p = false, g_p2p_ready = false;
+static void setup_p2p() {
+  if (g_p2p_ready) return;
+  unsigned char handle[64];
+  check(ftb200_p2p_export(g_ctx, handle, NULL));
+  unsigned char *all = (unsigned char *)malloc((size_t)64 * world_size);
+  MPI_Allgather(handle, 64, MPI_BYTE, all, 64, MPI_BYTE, MPI_COMM_WORLD);
+  /* where this rank's slice sits in each neighbour's window: the neighbour tells (its cumulative count for us, our index
+   * in its list, its total) -- the send lists are symmetric (PartitionMesh.cpp:566-1128) */
+  const int nb = sendProcessCount;
+  int *mine = (int *)malloc(sizeof(int) * 3 * (nb + 1)), *theirs = (int *)malloc(sizeof(int) * 3 * (nb + 1));
+  MPI_Request *req = (MPI_Request *)malloc(sizeof(MPI_Request) * 2 * (nb + 1));
+  for (int i = 0; i < nb; ++i) {
+    mine[3 * i] = sendNeighbourCountCum[i]; mine[3 * i + 1] = i; mine[3 * i + 2] = sendNeighbourCountCum[nb];
+    MPI_Isend(&mine[3 * i], 3, MPI_INT, sendProcessID[i], 2170, MPI_COMM_WORLD, &req[i]);
+    MPI_Irecv(&theirs[3 * i], 3, MPI_INT, sendProcessID[i], 2170, MPI_COMM_WORLD, &req[nb + i]);
+  }
+  MPI_Status status;
+  for (int i = 0; i < 2 * nb; ++i) MPI_Wait(&req[i], &status);
+  int *off = (int *)malloc(sizeof(int) * (nb + 1)), *idx = (int *)malloc(sizeof(int) * (nb + 1)), *tot = (int *)malloc(sizeof(int) * (nb + 1));
+  for (int i = 0; i < nb; ++i) { off[i] = theirs[3 * i]; idx[i] = theirs[3 * i + 1]; tot[i] = theirs[3 * i + 2]; }
+  check(ftb200_p2p_import(g_ctx, all, 0, off, idx, tot));
+  MPI_Barrier(MPI_COMM_WORLD);
+  free(all); free(mine); free(theirs); free(req); free(off); free(idx); free(tot);
+  g_p2p_ready = true;
+}
+/* `n` steps of the loop (fewer if timeFinal is reached: the remaining iterations are no-ops on the device) */
+static void run_steps(double timeFinal, long long n) {
+  if (world_size == 1 || g_p2p) {
+    check(ftb200_explicit_run_async(g_ctx, timeFinal, n));
+    return;
+  }
+  check(ftb200_run_begin(g_ctx, timeFinal, n));
+  for (long long i = 0; i < n; ++i) {
+    double dtl = 0.0;
+    check(ftb200_step_begin_host(g_ctx, sendNodeDisplacement, &dtl));
+    exchange_shared_nodes(2169);
+    MPI_Allreduce(MPI_IN_PLACE, &dtl, 1, MPI_DOUBLE, MPI_MIN, MPI_COMM_WORLD);  /* StableTimeStep.cpp:33 */
+    check(ftb200_step_end_host(g_ctx, recvNodeDisplacement, dtl));
+  }
+}
 void ExplicitDynamics(double timeFinal, char *name) {
   (void)name;
   ensure_ctx();
@@ -259,32 +342,61 @@ void ExplicitDynamics(double timeFinal, char *name) {
     g_bc_kind = (int *)calloc(nDOF, sizeof(int));
   }
   if (!g_bc_kind) { FILE_LOG_SINGLE(ERROR, "ExplicitDynamics: call femtech_b200_set_bc() or femtech_b200_set_rigid_bc() first"); TerminateFemTech(3); }
-  if (world_size > 1) { FILE_LOG_SINGLE(ERROR, "ExplicitDynamics: multi-GPU runs are driven by femtech_b200.dist"); TerminateFemTech(3); }
   check(ftb200_set_state(g_ctx, displacements, velocities, accelerations, boundary));
   check(ftb200_set_bc(g_ctx, g_bc_kind, g_bc_rate));
-  check(ftb200_explicit_begin(g_ctx, Time, ExplicitTimeStepReduction, FailureTimeStep, g_energy_every));
+  if (world_size == 1) {
+    check(ftb200_explicit_begin(g_ctx, Time, ExplicitTimeStepReduction, FailureTimeStep, g_energy_every));
+  } else {
+    const char *tr = getenv("FTB200_MPI_TRANSPORT");
+    g_p2p = tr ? strcmp(tr, "p2p") == 0 : ftb200_device_count() >= world_size;
+    /* step 0 of the drivers (Benchmarking-Parallel.cpp:83-91) with the two cross-rank operations on the host's MPI */
+    check(ftb200_explicit_begin_dt(g_ctx, Time, ExplicitTimeStepReduction, FailureTimeStep, g_energy_every, NULL));
+    double dtl = 0.0;
+    check(ftb200_get_dtmin(g_ctx, &dtl));
+    MPI_Allreduce(MPI_IN_PLACE, &dtl, 1, MPI_DOUBLE, MPI_MIN, MPI_COMM_WORLD);
+    check(ftb200_set_dtmin(g_ctx, dtl));
+    check(ftb200_explicit_begin_force_host(g_ctx, sendNodeDisplacement));
+    exchange_shared_nodes(2169);
+    check(ftb200_explicit_begin_finish_host(g_ctx, recvNodeDisplacement));
+    if (g_p2p) setup_p2p();
+  }
   /* The loop runs in slices of RING/2 steps; every finished step's record (Time, dt, step, status, energies) is written by
    * the device into the pinned host ring of ftb200_step_ring, and the energy file gets the line CheckEnergy would have
    * written for that step (CheckEnergy.cpp:66-83: "%12.6e %12.6e  %12.6e  %12.6e %12.6e") -- one line per step, as in the
-   * reference's drivers, without a host round trip per step. */
+   * reference's drivers, without a host round trip per step.  Several ranks: the records carry this rank's share of the
+   * sums (owner rule of CheckEnergy.cpp:21-33 on the device); rank 0 adds the shares of a slice with one MPI_Reduce. */
   const long long RING = 512;
   double *ring = NULL;
   check(ftb200_step_ring(g_ctx, RING, &ring));
   long long steps = 0, done = 0;
   int st = 0;
+  double *part = (double *)malloc(sizeof(double) * 3 * RING), *sum = (double *)malloc(sizeof(double) * 3 * RING);
   for (;;) {
-    check(ftb200_explicit_run_async(g_ctx, timeFinal, RING / 2));
+    run_steps(timeFinal, RING / 2);
     long long now = 0;
     check(ftb200_explicit_poll(g_ctx, &now, &Time, &dt, &st));
+    const long long cnt = now - done;
     for (long long k = done + 1; k <= now; ++k) {
       const volatile double *r = ring + 8 * ((k - 1) % RING);
       if (r[2] != (double)k) { FILE_LOG_SINGLE(ERROR, "ExplicitDynamics: step ring out of sequence at step %lld", k); TerminateFemTech(3); }
-      if (g_energy_every && world_rank == 0) fprintf(energyFile, "%12.6e %12.6e  %12.6e  %12.6e %12.6e\n", r[0], r[4], r[5], r[6], r[7]);
+      part[3 * (k - done - 1)] = r[4]; part[3 * (k - done - 1) + 1] = r[5]; part[3 * (k - done - 1) + 2] = r[6];
     }
-    steps += now - done;
+    if (world_size > 1) {
+      if (cnt > 0) MPI_Reduce(part, sum, (int)(3 * cnt), MPI_DOUBLE, MPI_SUM, 0, MPI_COMM_WORLD);
+    } else {
+      memcpy(sum, part, sizeof(double) * 3 * cnt);
+    }
+    if (g_energy_every && world_rank == 0)
+      for (long long k = done + 1; k <= now; ++k) {
+        const volatile double *r = ring + 8 * ((k - 1) % RING);
+        const double *e = sum + 3 * (k - done - 1);
+        fprintf(energyFile, "%12.6e %12.6e  %12.6e  %12.6e %12.6e\n", r[0], e[0], e[1], e[2], fabs(e[2] + e[0] - e[1]));
+      }
+    steps += cnt;
     if (now == done || !(Time < timeFinal) || (st & 16)) break;
     done = now;
   }
+  free(part); free(sum);
   check(ftb200_step_ring(g_ctx, 0, NULL));
   if (st & 1) { FILE_LOG_SINGLE(ERROR, "Unknown material type"); TerminateFemTech(1); }
   if (st & 16) { FILE_LOG_SINGLE(ERROR, "Timestep too small, dt below FailureTimeStep"); TerminateFemTech(19); }

@@ -56,11 +56,17 @@ int main(int argc, char **argv) {
   }
   femtech_b200_set_bc(kind.data(), rate, energy_every);
   ExplicitDynamics(tMax, argv[1]);
-  const std::string out = std::string(argv[1]) + ".resident.txt";
+  // one file per rank when there are several (with the global node ids of PartitionMesh.cpp, so that a test can place them)
+  std::string out = std::string(argv[1]) + ".resident.txt";
+  if (world_size > 1) out = std::string(argv[1]) + ".resident.rank" + std::to_string(world_rank) + ".txt";
   FILE *f = fopen(out.c_str(), "w");
   if (!f) return 3;
   fprintf(f, "%d %.17g %.17g\n", nNodes, Time, dt);
   for (int i = 0; i < nNodes * ndim; ++i) fprintf(f, "%.17g\n", displacements[i]);
+  if (world_size > 1) {
+    for (int i = 0; i < nNodes; ++i) fprintf(f, "%d\n", globalNodeID[i]);
+    for (int i = 0; i < nNodes * ndim; ++i) fprintf(f, "%.17g\n", velocities[i]);
+  }
   fclose(f);
   FinalizeFemTech();  // frees the arrays (InitFinalizeFemTech.cpp:75-80)
   return 0;
