@@ -303,6 +303,16 @@ def ours_single(args):
             # (profiles/r01_k_elem_final_ncu_full.csv: dram__bytes_read.sum + dram__bytes_write.sum); other configs: null
             "traffic": NCU_TRAFFIC_BYTES.get((n, mat, bool(energy), bool(args.injury), n_affine == E)),
             "traffic_unit": "bytes per launch (algorithmic: %d)" % int(b_elem * E),
+            "traffic_source": "PINNED CONSTANT, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                              "launch from the ncu --set full capture profiles/r01_k_elem_affine_ncu_full.csv (commit f34820f; "
+                              "general kernel: r01_k_elem_general_ncu_full.csv); null for configurations without a capture",
+            # what north_star scores is the STEP: both roofs and the step's fraction of the slower one, first
+            "step_frac_of_min_roof": value / min(fp64_peak * 1e12 / flops, hbm_peak * 1e9 / (b_elem + b_node)),
+            "step_roof_fp64": fp64_peak * 1e12 / flops, "step_roof_hbm": hbm_peak * 1e9 / (b_elem + b_node),
+            "step_frac_of_hbm_roof_survey_bytes": value / (hbm_peak * 1e9 / 717.0),
+            "step_note": "roofs in element-steps/s: fp64 = measured DFMA peak / executed flops per element, hbm = measured copy "
+                         "bandwidth / algorithmic bytes per element-step of this design (%.0f B; SURVEY 8(d) counts 717 B: "
+                         "step_frac_of_hbm_roof_survey_bytes)" % (b_elem + b_node),
             "peak_source": "fp64: DFMA microbenchmark measured in this run; hbm: " + hbm_src,
             "launch_ms": prof["elem_ms"], "launches_timed": prof["elem_launches"],
             "algorithmic_flops_per_element": flops, "algorithmic_bytes_per_element": b_elem,
@@ -364,6 +374,9 @@ def ours_single(args):
     m.step_ring(0)
     e2e = {"value": E * e2e_steps / e2e_ring_s, "unit": "element-steps/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": (5 * 24 * N + 12 * N) / e2e_steps + 64, "steps": e2e_steps, "records_consistent": ok_recs,
+           "amortised_over_steps": e2e_steps,
+           "amortisation": "the state upload (%.0f MB) and download (%.0f MB) cross PCIe ONCE per call and are spread over the %d "
+                           "steps of the call: e2e approaches `value` as the call gets longer" % (h2d * e2e_steps / 1e6, (5 * 24 * N + 12 * N) / 1e6, e2e_steps),
            "api": "ExplicitDynamics (resident), one call for the %d steps: pinned host state in, every step's scalars "
                   "(Time, dt, status, energies) written by the device into a pinned host ring and consumed by the host "
                   "as they arrive, host state out; all copies inside the timed region" % e2e_steps}
@@ -404,6 +417,29 @@ def ours_single(args):
                   "api": "legacy drop-in: GetForce + CalculateAccelerations + CheckEnergy + StableTimeStep on host arrays "
                          "(driver host loops not included)", "steps": leg_steps}
 
+    # (c) N = 1 through the loop the multi-GPU runs take (split element launches, pack, dt through the peer-memory window,
+    #     k_adv_p2p), zero neighbours: separates the cost of that loop from the cost of scaling in the N > 1 lines
+    part_path = None
+    try:
+        m.Time = 0.0
+        m.displacements[:] = 0.0; m.velocities[:] = 0.0; m.accelerations[:] = 0.0; m.boundary[:] = 0
+        m.enable_partitioned_loop()
+        m.explicit_begin(energy_every=energy)
+        m.run_async(tMax, max(args.warmup, 3))
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev4.record(stream)
+            m.run_async(tMax, args.steps)
+            ev5.record(stream)
+        torch.cuda.synchronize()
+        ms_p = ev4.elapsed_time(ev5)
+        part_path = {"value": E * args.steps / (ms_p * 1e-3), "unit": "element-steps/s", "ms_per_step": ms_p / args.steps,
+                     "what": "the same mesh on 1 GPU through the partitioned (peer-memory) loop of bench.py --gpus N > 1 with no "
+                             "neighbour: the N > 1 lines should be compared with this, `value` is the single-partition loop"}
+    except Exception as ex:  # never fail the headline over the extra leg
+        part_path = {"error": str(ex)[:200]}
+
     cpu = None
     if not args.no_cpu:
         cpu = run_reference_cpu(args.ref_n, mat, 40, 5, max(1, min(host_cores(), 32)))
@@ -424,7 +460,7 @@ def ours_single(args):
                            ("one fused kernel per step" if prof["node_launches"] == 0 else "element + node kernels per step"),
                    "l2": "per-step working set %.2f GB > 126 MB L2, no flush needed" % ((b_elem + b_node) * E / 1e9)},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_per_step_calls": e2e_calls, "e2e_async": e2e_async,
-        "e2e_legacy": e2e_legacy,
+        "e2e_legacy": e2e_legacy, "n1_partitioned_loop": part_path,
         "gpu_launches": launches, "clocks": summarize_clocks(samples),
         "ms_per_step_with_kernel_events": ms_total_prof / args.steps,
         "fp64_peak_tflops_measured": fp64_peak,

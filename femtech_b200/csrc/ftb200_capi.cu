@@ -467,7 +467,7 @@ BrickPlan plan_bricks(const ftb200_ctx* ctx) {
 // ---- brick-fused step: k_brick -> k_surf -> k_adv (-> k_energy).  The START of a step (first kick, drift, boundary
 //      condition) is the prologue of k_brick / k_surf, so the state between two steps is the full-step (u, v, a) and a run
 //      needs no separate START launch.
-bool use_brick(const ftb200_ctx* ctx) { return ctx->brick_ok && !ctx->rigid && !ctx->injury && ctx->nranks == 1; }
+bool use_brick(const ftb200_ctx* ctx) { return ctx->brick_ok && !ctx->rigid && !ctx->injury && ctx->nranks == 1 && !ctx->p2p_ready; }
 
 // energy partials of the brick-fused step: one per warp of k_brick, then one per warp of k_surf
 int brick_eparts(const ftb200_ctx* c) { return c->nB * (BRICK_NT / 32) + c->surf_blocks * (SURF_BLOCK / 32); }
@@ -1588,7 +1588,7 @@ static int run_async_p2p(ftb200_ctx* ctx, double tMax, long long steps) {
 int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
   if (!ctx || !ctx->begun) return fail(ctx, FTB200_ERR_INPUT, "explicit_run: call explicit_begin first");
   CK(cudaSetDevice(ctx->device));
-  if (ctx->nranks > 1) {
+  if (ctx->nranks > 1 || ctx->p2p_ready) {  // (a single rank that imported its own window runs the partitioned loop too: bench)
     if (!ctx->p2p_ready)
       return fail(ctx, FTB200_ERR_INPUT, "explicit_run: multi-rank runs need the peer-memory windows (p2p_export/import) "
                                          "or the step_begin/step_join/step_end sequence");

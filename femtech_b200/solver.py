@@ -343,6 +343,15 @@ class FemTech:
                 raise FemTechB200Error(100, "step %d did not arrive in the step ring" % k)
         return row.copy()
 
+    def enable_partitioned_loop(self):
+        """Single rank only: export this context's peer-memory window and import it as the only rank, so that run_async
+        takes the loop of the multi-GPU runs (split element launches, dt through the window, k_adv_p2p) with zero
+        neighbours.  bench.py uses it to separate the cost of that loop from the cost of scaling."""
+        w = C.c_void_p()
+        self._check(self.L.ftb200_p2p_export(self._h, None, C.byref(w)))
+        arr = (C.c_void_p * 1)(w.value)
+        self._check(self.L.ftb200_p2p_import(self._h, arr, 1, None, None, None))
+
     def run_async(self, timeFinal, steps):
         self._check(self.L.ftb200_explicit_run_async(self._h, float(timeFinal), int(steps)))
 
