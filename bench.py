@@ -480,6 +480,8 @@ def main():
     ap.add_argument("--ref-n", type=int, default=40, help="edge of the bounded CPU sample")
     ap.add_argument("--no-energy", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="multi-GPU: weak = n^3 elements per GPU (default), "
+                    "strong = one n^3 cube cut over the GPUs (BASELINE configs 3 and 4)")
     ap.add_argument("--no-validate", action="store_true", help="multi-GPU: skip the state check against the single-GPU run of the global mesh")
     ap.add_argument("--injury", action="store_true", help="also evaluate the injury criteria every step (ex5.cpp:240)")
     ap.add_argument("--jitter", type=float, default=0.0, help="move the interior nodes by this fraction of the spacing: "

@@ -1530,6 +1530,8 @@ static void launch_step_p2p(ftb200_ctx* ctx) {
     LAUNCH(k_p2p_pack, cdiv(ctx->halo_count, 128), 128, s, ctx->p2p, ctx->felem, ctx->node_off, ctx->node_ent,
            ctx->d_sendNodeIndex, ctx->sc, ctx->nE);
   cudaStreamWaitEvent(s, ctx->ev_join, 0);
+  // k_adv_p2p moves sc->step / sc->active, which the energy reduction of the previous step (helper stream) still reads
+  if (ctx->energy_pending) { cudaStreamWaitEvent(s, ctx->ev_energy_done, 0); ctx->energy_pending = false; }
   LAUNCH(k_adv_p2p, 1, 128, s, ctx->p2p, ctx->sc, ctx->mp, ctx->nPID, ctx->dthist);
   if (ctx->rigid) LAUNCH(k_rigid_step, 1, 32, s, ctx->sc, ctx->rigid, 0);
   NodeArgs N = node_args(ctx, ctx->halo_count ? p2p_recv(ctx->p2p_window, ctx->halo_count, 0) : nullptr);
@@ -1539,9 +1541,20 @@ static void launch_step_p2p(ftb200_ctx* ctx) {
   }
   if (ctx->energy) LAUNCH((k_node<true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
   else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
-  if (ctx->energy) LAUNCH(k_energy, 1, 256, s, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
+  if (ctx->energy) {
+    if (ctx->energy_async && !ctx->profile) {  // K8 of this step under the element kernels of the next one, like the single-partition loop
+      cudaEventRecord(ctx->ev_nodes_done, s);
+      cudaStreamWaitEvent(ctx->stream2, ctx->ev_nodes_done, 0);
+      LAUNCH(k_energy, 1, 256, ctx->stream2, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
+      cudaEventRecord(ctx->ev_energy_done, ctx->stream2);
+      ctx->energy_pending = true;
+    } else {
+      LAUNCH(k_energy, 1, 256, s, ctx->sc, ctx->epart, ctx->node_blocks, ctx->ehist);
+    }
+  }
 }
 
+static void join_energy(ftb200_ctx* ctx);
 static int run_async_p2p(ftb200_ctx* ctx, double tMax, long long steps) {
   cudaStream_t s = ctx->stream;
   LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
@@ -1558,6 +1571,7 @@ static int run_async_p2p(ftb200_ctx* ctx, double tMax, long long steps) {
     const long long before = ctx->launches;
     CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < GRAPH_STEPS; ++i) launch_step_p2p(ctx);
+    join_energy(ctx);  // the helper stream rejoins before the capture ends
     cudaError_t e = cudaStreamEndCapture(s, &g);
     const long long per_graph = ctx->launches - before;
     ctx->launches = before;
@@ -1579,6 +1593,7 @@ static int run_async_p2p(ftb200_ctx* ctx, double tMax, long long steps) {
       left--;
     }
   }
+  join_energy(ctx);
   // the receive window of the last step, for a later get_state
   ctx->halo_recv_cur = nullptr;
   CK(cudaGetLastError());

@@ -723,17 +723,24 @@ __global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node(const N
         // fixed-width map [8][nN] (-1 = no entry): the 8 entries and then all 24 force loads are issued before the
         // first add, instead of a dependent load per trip of a variable-length loop; same ascending order
         // (the 8 entries were loaded in the preamble)
-        double fv[8][3];
+#ifndef FTB_NODE_GATHER_BATCH
+#define FTB_NODE_GATHER_BATCH 4  // measured at 100^3: 8 in flight (64 registers, 64 B of spills) 92.3 us, 4 (16 B) 90.1 us, 2 89.9 us
+#endif
+        // FTB_NODE_GATHER_BATCH entries (x 3 components) in flight at a time; the additions keep the ascending order
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int en = ent[q] < 0 ? 0 : ent[q];
+        for (int q0 = 0; q0 < 8; q0 += FTB_NODE_GATHER_BATCH) {
+          double fv[FTB_NODE_GATHER_BATCH][3];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) fv[q][c] = (ent[q] >= 0) ? __ldg(A.felem + FTB_FIDX(3 * (en & 7) + c, en >> 3)) : 0.0;
+          for (int q = 0; q < FTB_NODE_GATHER_BATCH; ++q) {
+            const int en = ent[q0 + q] < 0 ? 0 : ent[q0 + q];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) fv[q][c] = (ent[q0 + q] >= 0) ? __ldg(A.felem + FTB_FIDX(3 * (en & 7) + c, en >> 3)) : 0.0;
+          }
+#pragma unroll
+          for (int q = 0; q < FTB_NODE_GATHER_BATCH; ++q)  // + 0.0 for a missing entry is exact
+#pragma unroll
+            for (int c = 0; c < 3; ++c) f[c] += fv[q][c];
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q)  // + 0.0 for a missing entry is exact
-#pragma unroll
-          for (int c = 0; c < 3; ++c) f[c] += fv[q][c];
         if (fl & FTB_FLAG_OVERFLOW)
           for (int j = A.node_off[n] + 8, j1 = A.node_off[n + 1]; j < j1; ++j) {
             const int en = __ldg(A.node_ent + j);

@@ -76,30 +76,31 @@ def proc_grid(P):
 
 
 def brick_partition(n_local, pgrid, rank, L_local=0.005):
-    """Rank `rank`'s brick of a structured hex8 box made of pgrid = (px,py,pz) bricks of n_local^3
-    elements each (weak scaling: the global mesh grows with the rank count).  Node and element
-    numbering, C3D8 ordering and spacing follow femtech_b200.mesh.cube_mesh; the maps follow the
-    reference's rules (see maps_from_elements) but are built analytically, without the global mesh.
+    """Rank `rank`'s brick of a structured hex8 box made of pgrid = (px,py,pz) bricks of n_local^3 elements each
+    (n_local may be a triple (nx, ny, nz) for bricks that are not cubes: strong scaling of a fixed global cube).  Weak
+    scaling: the global mesh grows with the rank count.  Node and element numbering, C3D8 ordering and spacing follow
+    femtech_b200.mesh.cube_mesh / box_mesh; the maps follow the reference's rules (see maps_from_elements) but are built
+    analytically, without the global mesh.  The spacing is L_local / nx.
 
     Returns dict(coordinates[N,3], connectivity[E,8] local ids, pid[E], node_gids[N], comm{...},
                  box=(Lx,Ly,Lz), dims=(Nx,Ny,Nz)).
     """
     px, py, pz = pgrid
-    n = n_local
+    nx, ny, nz = (n_local, n_local, n_local) if np.isscalar(n_local) else tuple(int(v) for v in n_local)
     rx, ry, rz = rank % px, (rank // px) % py, rank // (px * py)
-    Nx, Ny, Nz = n * px, n * py, n * pz
-    h = L_local / n
-    ox, oy, oz = rx * n, ry * n, rz * n
-    n1 = n + 1
-    kk, jj, ii = np.meshgrid(np.arange(n1), np.arange(n1), np.arange(n1), indexing="ij")
+    Nx, Ny, Nz = nx * px, ny * py, nz * pz
+    h = L_local / nx
+    ox, oy, oz = rx * nx, ry * ny, rz * nz
+    kk, jj, ii = np.meshgrid(np.arange(nz + 1), np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
     gi, gj, gk = (ii + ox).reshape(-1), (jj + oy).reshape(-1), (kk + oz).reshape(-1)
     X = np.stack([gi * h, gj * h, gk * h], axis=-1).astype(np.float64)
     gids = gi.astype(np.int64) + (Nx + 1) * gj.astype(np.int64) + (Nx + 1) * (Ny + 1) * gk.astype(np.int64)
-    ek, ej, ei = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    ek, ej, ei = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
     ei, ej, ek = ei.reshape(-1), ej.reshape(-1), ek.reshape(-1)
+    nx1, nxy = nx + 1, (nx + 1) * (ny + 1)
 
     def nid(i, j, k):
-        return (i + n1 * j + n1 * n1 * k).astype(np.int32)
+        return (i + nx1 * j + nxy * k).astype(np.int32)
 
     conn = np.stack([nid(ei, ej, ek), nid(ei + 1, ej, ek), nid(ei + 1, ej + 1, ek), nid(ei, ej + 1, ek),
                      nid(ei, ej, ek + 1), nid(ei + 1, ej, ek + 1), nid(ei + 1, ej + 1, ek + 1),
@@ -107,7 +108,7 @@ def brick_partition(n_local, pgrid, rank, L_local=0.005):
     # neighbours: every brick that shares at least one node (faces, edges, corners), ascending rank;
     # shared nodes of a pair = a face/edge/corner of the local node box, ascending global id == ascending local id
     pids, counts, idx = [], [], []
-    local_ids = np.arange(n1 ** 3, dtype=np.int32).reshape(n1, n1, n1)  # [k, j, i]
+    local_ids = np.arange((nx + 1) * (ny + 1) * (nz + 1), dtype=np.int32).reshape(nz + 1, ny + 1, nx + 1)  # [k, j, i]
     for q in range(px * py * pz):
         if q == rank:
             continue
@@ -116,8 +117,8 @@ def brick_partition(n_local, pgrid, rank, L_local=0.005):
         if max(abs(dx), abs(dy), abs(dz)) > 1:
             continue
         sel = []
-        for d in (dz, dy, dx):
-            sel.append(slice(None) if d == 0 else (slice(n, n + 1) if d > 0 else slice(0, 1)))
+        for d, nn in ((dz, nz), (dy, ny), (dx, nx)):
+            sel.append(slice(None) if d == 0 else (slice(nn, nn + 1) if d > 0 else slice(0, 1)))
         shared = local_ids[sel[0], sel[1], sel[2]].reshape(-1)
         pids.append(q)
         counts.append(shared.size)

@@ -70,7 +70,14 @@ def run(args):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, mat = args.n, args.material
     pg = fdist.proc_grid(world)
-    part = fdist.brick_partition(n, pg, rank)
+    strong = getattr(args, "scaling", "weak") == "strong"
+    if strong:  # a FIXED n^3 cube cut into px x py x pz bricks (BASELINE configs 3 and 4); spacing as in the 100^3 cube
+        if n % pg[0] or n % pg[1] or n % pg[2]:
+            raise SystemExit("--scaling strong: %d is not divisible by the process grid %s" % (n, pg))
+        loc = (n // pg[0], n // pg[1], n // pg[2])
+        part = fdist.brick_partition(loc, pg, rank, L_local=loc[0] * 5e-5)
+    else:
+        part = fdist.brick_partition(n, pg, rank)
     E_local, N_local = part["connectivity"].shape[0], part["coordinates"].shape[0]
     energy = 0 if args.no_energy else 1
     rate_v = 0.07 if mat == 1 else 1.75
@@ -148,12 +155,16 @@ def run(args):
         out = {
             "metric": "hex8 element-steps/sec fp64", "value": E_total * args.steps / (ms_total * 1e-3),
             "unit": "element-steps/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic structured hex8 box of %dx%dx%d bricks, %d^3 elements per GPU (%d elements "
-                                   "total), %s, benchmark BC, %s, dt recomputed every step" %
-                                   (pg[0], pg[1], pg[2], n, E_total, bench.MAT_NAME[mat],
-                                    "CheckEnergy every step" if energy else "no energy check"),
+            "config": {"workload": ("synthetic %d^3 structured hex8 cube (%d elements) cut into %dx%dx%d bricks of %s elements, one "
+                                    "per GPU, %s, benchmark BC, %s, dt recomputed every step" %
+                                    (n, E_total, pg[0], pg[1], pg[2], "x".join(str(v // g) for v, g in zip(part["dims"], pg)),
+                                     bench.MAT_NAME[mat], "CheckEnergy every step" if energy else "no energy check")) if strong else
+                                   ("synthetic structured hex8 box of %dx%dx%d bricks, %d^3 elements per GPU (%d elements "
+                                    "total), %s, benchmark BC, %s, dt recomputed every step" %
+                                    (pg[0], pg[1], pg[2], n, E_total, bench.MAT_NAME[mat],
+                                     "CheckEnergy every step" if energy else "no energy check")),
                        "partition": "structured brick split, one partition per GPU (ParMETIS part[] accepted as input; "
                                     "node maps follow PartitionMesh.cpp, tests/test_partition_host.py)",
                        "exchange": ("peer-memory transport: pack kernel stores the shared-node partials into the neighbours' "
