@@ -475,7 +475,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=100, help="cube edge in elements per GPU (BASELINE config 2: 100)")
+    ap.add_argument("--n", "--edge", dest="n", type=int, default=100, help="cube edge in elements per GPU (BASELINE config 2: 100)")
     ap.add_argument("--material", type=int, default=1, choices=[1, 4, 5])
     ap.add_argument("--ref-n", type=int, default=40, help="edge of the bounded CPU sample")
     ap.add_argument("--no-energy", action="store_true")

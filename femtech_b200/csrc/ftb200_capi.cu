@@ -1324,7 +1324,7 @@ int ftb200_get_state(ftb200_ctx* ctx, double* displacements, double* velocities,
       unsigned long long seq = 0;
       CK(cudaMemcpyAsync(&seq, ctx->d_seq, sizeof(seq), cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
-      if (seq > 0) ctx->halo_recv_cur = p2p_recv(ctx->p2p_window, ctx->halo_count, (int)((seq - 1) & 1ULL));
+      if (seq > 0) ctx->halo_recv_cur = p2p_recv(ctx->p2p_window, ctx->halo_count, (int)((seq - 1) & 1ULL), ctx->nranks);
     }
     NodeArgs N = node_args(ctx, ctx->halo_recv_cur);
     if (ctx->felem_stale) {
@@ -1534,13 +1534,30 @@ static void launch_step_p2p(ftb200_ctx* ctx) {
   if (ctx->energy_pending) { cudaStreamWaitEvent(s, ctx->ev_energy_done, 0); ctx->energy_pending = false; }
   LAUNCH(k_adv_p2p, 1, 128, s, ctx->p2p, ctx->sc, ctx->mp, ctx->nPID, ctx->dthist);
   if (ctx->rigid) LAUNCH(k_rigid_step, 1, 32, s, ctx->sc, ctx->rigid, 0);
-  NodeArgs N = node_args(ctx, ctx->halo_count ? p2p_recv(ctx->p2p_window, ctx->halo_count, 0) : nullptr);
+  NodeArgs N = node_args(ctx, ctx->halo_count ? p2p_recv(ctx->p2p_window, ctx->halo_count, 0, ctx->nranks) : nullptr);
   if (ctx->halo_count) {
-    N.halo_recv_alt = p2p_recv(ctx->p2p_window, ctx->halo_count, 1);
+    N.halo_recv_alt = p2p_recv(ctx->p2p_window, ctx->halo_count, 1, ctx->nranks);
     N.p2p_seq = ctx->d_seq;
   }
   if (ctx->energy) LAUNCH((k_node<true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
   else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+  if (ctx->injury) {
+    // CalculateInjuryCriterions across partitions inside the loop: running extrema per rank, then the six radix passes of
+    // the two GLOBAL 95th-percentile selections, each with its histogram summed over the ranks through the windows
+    launch_injury(ctx, s);  // one rank: everything; several ranks: the extrema only
+    if (ctx->nranks > 1) {
+      const ElemArgs A = elem_args(ctx, 0, ctx->nE, 0);
+      double* h0 = ctx->inj_hist;
+      double* h1 = ctx->inj_hist ? ctx->inj_hist + ctx->hist_cap : nullptr;
+      for (int pass = 0; pass < INJ_PASSES; ++pass) {
+        LAUNCH(k_injury_select, dim3(std::min(INJ_BLOCKS, cdiv(ctx->nE, INJ_THREADS * INJ_ITEMS)), 2), INJ_THREADS, s, A, ctx->inj_state,
+               pass, nullptr, nullptr, 1);
+        LAUNCH(k_injury_xchg, 1, INJ_THREADS, s, ctx->p2p, ctx->sc, ctx->inj_state, pass);
+        LAUNCH(k_injury_pick, dim3(1, 2), INJ_THREADS, s, ctx->sc, ctx->inj_state, pass, h0, h1);
+      }
+      LAUNCH(k_injury_lists, cdiv(ctx->nE, 256), 256, s, A, ctx->inj_state);
+    }
+  }
   if (ctx->energy) {
     if (ctx->energy_async && !ctx->profile) {  // K8 of this step under the element kernels of the next one, like the single-partition loop
       cudaEventRecord(ctx->ev_nodes_done, s);
@@ -1565,7 +1582,8 @@ static int run_async_p2p(ftb200_ctx* ctx, double tMax, long long steps) {
     else LAUNCH((k_node<false, true, false, false>), ctx->node_blocks, NODE_BLOCK, s, N);
   }
   const bool use_graph = !ctx->profile;  // built on the first run (warm-up), whatever its length
-  if (use_graph && !(ctx->p2p_graph && ctx->p2p_graph_energy == ctx->energy)) {
+  const int p2p_sig = ctx->energy | (ctx->has_fe ? 2 : 0) | (ctx->injury ? 64 : 0) | (ctx->rigid ? 128 : 0);
+  if (use_graph && !(ctx->p2p_graph && ctx->p2p_graph_energy == p2p_sig)) {
     if (ctx->p2p_graph) { cudaGraphExecDestroy(ctx->p2p_graph); ctx->p2p_graph = nullptr; }
     cudaGraph_t g = nullptr;
     const long long before = ctx->launches;
@@ -1579,7 +1597,7 @@ static int run_async_p2p(ftb200_ctx* ctx, double tMax, long long steps) {
     e = cudaGraphInstantiate(&ctx->p2p_graph, g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) { ctx->p2p_graph = nullptr; return fail(ctx, FTB200_ERR_CUDA, "p2p graph instantiate failed: %s", cudaGetErrorString(e)); }
-    ctx->p2p_graph_energy = ctx->energy;
+    ctx->p2p_graph_energy = p2p_sig;
     ctx->p2p_graph_launches = per_graph;
   }
   long long left = steps;
@@ -1608,9 +1626,6 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
       return fail(ctx, FTB200_ERR_INPUT, "explicit_run: multi-rank runs need the peer-memory windows (p2p_export/import) "
                                          "or the step_begin/step_join/step_end sequence");
     if (steps <= 0) return FTB200_OK;
-    if (ctx->injury)  // the selection passes need a cross-rank histogram sum: only the step_begin/step_end loop drives them
-      return fail(ctx, FTB200_ERR_INPUT, "explicit_run: the injury criteria are not carried by the peer-memory loop; "
-                                         "use the step_begin/step_join/step_end sequence");
     return run_async_p2p(ctx, tMax, steps);
   }
   if (steps <= 0) return FTB200_OK;
@@ -1937,7 +1952,7 @@ int ftb200_p2p_export(ftb200_ctx* ctx, void* handle_out, void** window_out) {
   if ((int)ctx->h_sendProcessID.size() > P2P_MAXNB || ctx->nranks > P2P_MAXP)
     return fail(ctx, FTB200_ERR_INPUT, "p2p_export: more than %d neighbours or %d ranks", P2P_MAXNB, P2P_MAXP);
   if (!ctx->p2p_window) {
-    ctx->p2p_bytes = sizeof(P2PHeader) + 2 * 3 * (size_t)std::max(ctx->halo_count, 1) * sizeof(double);
+    ctx->p2p_bytes = p2p_recv_off(ctx->nranks) + 2 * 3 * (size_t)std::max(ctx->halo_count, 1) * sizeof(double);
     CK(cudaMalloc((void**)&ctx->p2p_window, ctx->p2p_bytes));
     CK(cudaMemset(ctx->p2p_window, 0, ctx->p2p_bytes));
     int rc;
@@ -1997,6 +2012,11 @@ int ftb200_p2p_import(ftb200_ctx* ctx, const void* all_handles, int handles_are_
     cudaFuncAttributes fa;
     CK(cudaFuncGetAttributes(&fa, k_p2p_pack));
     CK(cudaFuncGetAttributes(&fa, k_adv_p2p));
+    CK(cudaFuncGetAttributes(&fa, k_injury_xchg));
+    CK(cudaFuncGetAttributes(&fa, k_injury_pick));
+    CK(cudaFuncGetAttributes(&fa, k_injury_select));
+    CK(cudaFuncGetAttributes(&fa, k_injury_reduce));
+    CK(cudaFuncGetAttributes(&fa, k_injury_lists));
     CK(cudaFuncGetAttributes(&fa, k_begin_run));
     CK(cudaFuncGetAttributes(&fa, k_energy));
     CK(cudaFuncGetAttributes(&fa, k_gather_force));

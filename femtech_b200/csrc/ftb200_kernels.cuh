@@ -1418,6 +1418,7 @@ struct P2PHeader {
   unsigned long long hflag[P2P_MAXNB];
   unsigned long long dflag[P2P_MAXP];
   double dtslot[2][P2P_MAXP];
+  unsigned long long iflag[P2P_MAXP];  // per source rank: (step sequence * 8 + radix pass + 1) of its last injury histogram
 };
 struct P2PArgs {
   char* self;                    // this rank's window
@@ -1431,8 +1432,15 @@ struct P2PArgs {
   unsigned long long* seq;       // monotone step sequence (device), never reset
   unsigned* blocks_done;
 };
-__host__ __device__ __forceinline__ double* p2p_recv(char* win, int H, int buf) {
-  return reinterpret_cast<double*>(win + sizeof(P2PHeader)) + (size_t)buf * 3 * (size_t)H;
+// window layout: header | injury histograms [2][n_ranks][P2P_IHIST counters] | receive buffers [2][3 H]; the first two
+// parts have the same size on every rank, so a peer's histogram area is found without knowing its halo count
+constexpr int P2P_IHIST = 2 * 2048;  // = 2 * INJ_BINS (static_assert below)
+__host__ __device__ __forceinline__ size_t p2p_ihist_off() { return (sizeof(P2PHeader) + 255) & ~(size_t)255; }
+__host__ __device__ __forceinline__ size_t p2p_recv_off(int n_ranks) {
+  return p2p_ihist_off() + (size_t)2 * (size_t)n_ranks * P2P_IHIST * sizeof(unsigned);
+}
+__host__ __device__ __forceinline__ double* p2p_recv(char* win, int H, int buf, int n_ranks) {
+  return reinterpret_cast<double*>(win + p2p_recv_off(n_ranks)) + (size_t)buf * 3 * (size_t)H;
 }
 
 __global__ void k_p2p_pack(const P2PArgs P, const double* felem, const int* node_off, const int* node_ent,
@@ -1453,7 +1461,7 @@ __global__ void k_p2p_pack(const P2PArgs P, const double* felem, const int* node
 #pragma unroll
       for (int c = 0; c < 3; ++c) f[c] += felem[FTB_FIDX(3 * sl + c, e)];
     }
-    double* dst = p2p_recv(P.peer_nb[nb], P.peer_H[nb], buf) + 3 * (size_t)(P.peer_slot_off[nb] + (i - P.nb_cum[nb]));
+    double* dst = p2p_recv(P.peer_nb[nb], P.peer_H[nb], buf, P.n_ranks) + 3 * (size_t)(P.peer_slot_off[nb] + (i - P.nb_cum[nb]));
     dst[0] = f[0]; dst[1] = f[1]; dst[2] = f[2];  // peer store over NVLink
   }
   __shared__ int s_last;
@@ -1535,6 +1543,7 @@ constexpr int NODE_TILE = 128;  // internal node order is padded to whole tiles 
 // and the element lists of the percentile maxima.
 constexpr int INJ_BINS = 2048;    // 11-bit digits: 6 passes over the 64-bit keys (the top pass has 9 bits)
 constexpr int INJ_PASSES = 6;
+static_assert(P2P_IHIST == 2 * INJ_BINS, "peer-memory window layout");
 struct InjState {
   double scal[12];  // maxStrain, maxT, minStrain, minT, maxShear, maxShearT, maxPSxSR, maxTimePSxSR, MPS95, t, MPSxSR95, t
   int elems[4];     // reference element ids of the four extrema (ex5.cpp:63,74)
@@ -1794,6 +1803,46 @@ __global__ void __launch_bounds__(INJ_THREADS) k_injury_pick(const DevScalars* s
     } else {
       st->upd[arr] = 0;
     }
+  }
+}
+
+// Sum of the per-rank histograms of one radix pass through the peer-memory windows (the percentile is a GLOBAL order
+// statistic, math.cpp:160-199 gathers all ranks): every rank stores its 2 x 2048 counters into its slot of every rank's
+// window (buffer = pass parity), raises a flag, waits for all ranks' flags of this (step, pass) and replaces its own
+// histogram by the sum in rank order.  Two buffers suffice: a rank reaches pass p + 2 only after every rank has
+// announced pass p + 1, i.e. has finished reading pass p.  One block; k_injury_pick follows.
+__global__ void __launch_bounds__(INJ_THREADS) k_injury_xchg(const P2PArgs P, const DevScalars* sc, InjState* st, const int pass) {
+  if (!sc->active) return;
+  __shared__ int s_ok;
+  const unsigned long long want = (*P.seq) * 8ULL + (unsigned long long)pass + 1ULL;  // seq was advanced by k_adv_p2p of this step
+  const int buf = pass & 1;
+  const size_t slot = (size_t)2 * INJ_BINS;
+  const unsigned* mine = &st->hist[0][0];
+  for (int r = 0; r < P.n_ranks; ++r) {
+    unsigned* dst = reinterpret_cast<unsigned*>(P.peer_rank[r] + p2p_ihist_off()) + ((size_t)buf * P.n_ranks + P.rank) * slot;
+    for (int i = threadIdx.x; i < 2 * INJ_BINS; i += INJ_THREADS) dst[i] = mine[i];
+  }
+  if (threadIdx.x == 0) s_ok = 1;
+  __threadfence_system();
+  __syncthreads();
+  for (int r = threadIdx.x; r < P.n_ranks; r += INJ_THREADS)
+    *(volatile unsigned long long*)&reinterpret_cast<P2PHeader*>(P.peer_rank[r])->iflag[P.rank] = want;
+  const unsigned long long t0 = now_ns();
+  for (int r = threadIdx.x; r < P.n_ranks; r += INJ_THREADS) {
+    volatile unsigned long long* fl = &reinterpret_cast<P2PHeader*>(P.self)->iflag[r];
+    while (*fl < want) {
+      __nanosleep(100);
+      if (now_ns() - t0 > 5000000000ULL) { s_ok = 0; break; }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (!s_ok) { if (threadIdx.x == 0) atomicOr(&const_cast<DevScalars*>(sc)->status, 64); return; }
+  const unsigned* all = reinterpret_cast<const unsigned*>(P.self + p2p_ihist_off()) + (size_t)buf * P.n_ranks * slot;
+  for (int i = threadIdx.x; i < 2 * INJ_BINS; i += INJ_THREADS) {
+    unsigned sum = 0;
+    for (int r = 0; r < P.n_ranks; ++r) sum += __ldcg(all + (size_t)r * slot + i);
+    (&st->hist[0][0])[i] = sum;
   }
 }
 

@@ -591,9 +591,9 @@ def test_mixed_hex_tet_mesh_matches_reference(name):
     m.close()
 
 
-def test_injury_criteria_three_partitions_match_reference():
-    """ex5's injury loop on the reference's own 3-rank ParMETIS partition (fixture inj6_p3): per-rank flags, strains,
-    extrema and lists, and the GLOBAL 95th percentile (math.cpp:160-199 gathers all ranks) through per-pass histogram sums."""
+def _injury_p3_case(p2p):
+    """ex5's injury loop on the reference's own 3-rank ParMETIS partition (fixture inj6_p3), one context per rank on one
+    device; asserts inside (a failure surfaces as the subprocess' traceback when run through the peer-memory loop)."""
     from femtech_b200 import dist as fdist
     g = golden("inj6_p3")
     P = int(g["nranks"])
@@ -613,7 +613,11 @@ def test_injury_criteria_three_partitions_match_reference():
         m._check(m.L.ftb200_record_history(m._h, nsteps + 8))
     grp.explicit_begin(energy_every=1)
     grp.InitInjuryCriterion(exclude_pids=g["param_exclude"])
-    grp.run(float(g["param_tMax"]), nsteps)
+    if p2p:
+        grp.enable_p2p()
+        grp.run_p2p(float(g["param_tMax"]), nsteps)
+    else:
+        grp.run(float(g["param_tMax"]), nsteps)
     for r, m in enumerate(grp.models):
         d = rank_dict(g, r)
         m.sync_out()
@@ -634,6 +638,27 @@ def test_injury_criteria_three_partitions_match_reference():
         assert rel(h95, d["inj_hist95"]) < TOL and rel(hx95, d["inj_histx95"]) < 1e-6
         assert rel(res["volumes"], d["inj_volumes"]) < 1e-12
     grp.close()
+    return True
+
+
+def test_injury_criteria_three_partitions_match_reference():
+    """Per-rank flags, strains, extrema and lists, and the GLOBAL 95th percentile (math.cpp:160-199 gathers all ranks) through
+    per-pass histogram sums; the split-step sequence with the sums done by the caller."""
+    assert _injury_p3_case(False)
+
+
+def test_injury_criteria_inside_the_peer_memory_loop():
+    """The same inside the graph-capturable peer-memory loop: the histograms of every radix pass are summed through the
+    ranks' windows by k_injury_xchg (no host, no NCCL).  Fresh process: P ranks x 2 streams share one device."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_parity as t; "
+            "print('RESULT', t._injury_p3_case(True))" % (here, os.path.dirname(here)))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "RESULT True" in r.stdout, (r.stdout[-1500:], r.stderr[-2500:])
 
 
 def test_brain_like_example_runs_all_next_rows_together(tmp_path):
