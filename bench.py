@@ -35,7 +35,7 @@ def algorithmic_bytes(n, mat, energy):
     elem = 36 + 1 + 48 * rho_n + 192            # K_elem: conn+pid+eflag, X and u (unique nodes), f_e write
     node = 192 + (4 + 32) * rho_n + (8 + 2 + 72 + 72) * rho_n  # K_node: f_e read, CSR, m, flags, u v a read + write
     if energy:
-        node += 96 * rho_n                       # du and fi: write + read next step
+        node += 48 * rho_n                       # fi: write + read next step (the displacement increment is rebuilt, not stored)
     hist = 2304 if mat == 5 else 0
     return elem + hist, node
 

@@ -195,6 +195,17 @@ void dfree(T*& p) {
   p = nullptr;
 }
 
+// Every copy and fill of the set-up code is ordered on the context's OWN stream.  The streams are non-blocking (several
+// contexts may live in one process, some with kernels that wait for a peer), so they do not synchronise with the legacy
+// default stream -- and a plain cudaMemcpy from pageable memory returns once the data are staged, before the DMA has
+// landed, a plain cudaMemset is asynchronous altogether: a kernel launched on the context's stream right behind them
+// could read the old contents (seen: the node list of the rigid-body condition on a first, cold context).
+cudaError_t ftb_memcpy(ftb200_ctx* ctx, void* dst, const void* src, size_t n, cudaMemcpyKind kind) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, n, kind, ctx->stream);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(ctx->stream);
+}
+cudaError_t ftb_memset(ftb200_ctx* ctx, void* p, int v, size_t n) { return cudaMemsetAsync(p, v, n, ctx->stream); }
+
 int ensure_big(ftb200_ctx* ctx, size_t bytes) {
   if (ctx->d_big_bytes >= bytes) return 0;
   dfree(ctx->d_big);
@@ -704,8 +715,8 @@ int ftb200_brick_maps(ftb200_ctx* ctx, int* brick_of_element, int* interior_bric
   CK(cudaSetDevice(ctx->device));
   std::vector<BrickHdr> hdr(ctx->nB);
   std::vector<int> ref_of(ctx->nE);
-  CK(cudaMemcpy(hdr.data(), ctx->b_hdr, hdr.size() * sizeof(BrickHdr), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(ref_of.data(), ctx->ref_of, ref_of.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(ftb_memcpy(ctx, hdr.data(), ctx->b_hdr, hdr.size() * sizeof(BrickHdr), cudaMemcpyDeviceToHost));
+  CK(ftb_memcpy(ctx, ref_of.data(), ctx->ref_of, ref_of.size() * sizeof(int), cudaMemcpyDeviceToHost));
   std::vector<int> bint(ctx->nNp, -1);
   for (int b = 0; b < ctx->nB; ++b) {
     if (brick_of_element)
@@ -971,13 +982,13 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
         (rc = dalloc(ctx, &ctx->a[k], nNp)) || (rc = dalloc(ctx, &ctx->fi[k], nNp)) || (rc = dalloc(ctx, &ctx->du[k], nNp)) ||
         (rc = dalloc(ctx, &ctx->fnet[k], nNp)) || (rc = dalloc(ctx, &ctx->d_stage[k], 3 * (size_t)std::max(nN, nNp))))
       return rc;
-    CK(cudaMemcpy(ctx->X[k], &Xs[(size_t)k * nNp], nNp * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemset(ctx->u[k], 0, nNp * sizeof(double)));
-    CK(cudaMemset(ctx->v[k], 0, nNp * sizeof(double)));
-    CK(cudaMemset(ctx->a[k], 0, nNp * sizeof(double)));
-    CK(cudaMemset(ctx->fi[k], 0, nNp * sizeof(double)));
-    CK(cudaMemset(ctx->du[k], 0, nNp * sizeof(double)));
-    CK(cudaMemset(ctx->fnet[k], 0, nNp * sizeof(double)));
+    CK(ftb_memcpy(ctx, ctx->X[k], &Xs[(size_t)k * nNp], nNp * sizeof(double), cudaMemcpyHostToDevice));
+    CK(ftb_memset(ctx, ctx->u[k], 0, nNp * sizeof(double)));
+    CK(ftb_memset(ctx, ctx->v[k], 0, nNp * sizeof(double)));
+    CK(ftb_memset(ctx, ctx->a[k], 0, nNp * sizeof(double)));
+    CK(ftb_memset(ctx, ctx->fi[k], 0, nNp * sizeof(double)));
+    CK(ftb_memset(ctx, ctx->du[k], 0, nNp * sizeof(double)));
+    CK(ftb_memset(ctx, ctx->fnet[k], 0, nNp * sizeof(double)));
   }
   ctx->node_blocks = cdiv(nNp, NODE_BLOCK);
   int epart_blocks = std::max(ctx->node_blocks, cdiv(nN, NODE_BLOCK));
@@ -1038,12 +1049,12 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
         (rc = dalloc(ctx, &ctx->s_ell, sell.size())) || (rc = dalloc(ctx, &ctx->b_part[0], (size_t)slot + 1)) ||
         (rc = dalloc(ctx, &ctx->b_part[1], (size_t)slot + 1)) || (rc = dalloc(ctx, &ctx->b_part[2], (size_t)slot + 1)))
       return rc;
-    CK(cudaMemcpy(ctx->b_hdr, hdr.data(), hdr.size() * sizeof(BrickHdr), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->b_conn16, conn16.data(), conn16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->b_map16, map16.data(), map16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->b_halo, halo.data(), halo.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->s_ell, sell.data(), sell.size() * sizeof(int), cudaMemcpyHostToDevice));
-    for (int c = 0; c < 3; ++c) CK(cudaMemset(ctx->b_part[c], 0, ((size_t)slot + 1) * sizeof(double)));
+    CK(ftb_memcpy(ctx, ctx->b_hdr, hdr.data(), hdr.size() * sizeof(BrickHdr), cudaMemcpyHostToDevice));
+    CK(ftb_memcpy(ctx, ctx->b_conn16, conn16.data(), conn16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CK(ftb_memcpy(ctx, ctx->b_map16, map16.data(), map16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CK(ftb_memcpy(ctx, ctx->b_halo, halo.data(), halo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(ftb_memcpy(ctx, ctx->s_ell, sell.data(), sell.size() * sizeof(int), cudaMemcpyHostToDevice));
+    for (int c = 0; c < 3; ++c) CK(ftb_memset(ctx, ctx->b_part[c], 0, ((size_t)slot + 1) * sizeof(double)));
     if (!sover.empty()) {
       std::stable_sort(sover.begin(), sover.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b2) { return a.first < b2.first; });
       std::vector<int> ooff(nS + 1, 0), oent(sover.size());
@@ -1051,8 +1062,8 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       for (int i = 0; i < nS; ++i) ooff[i + 1] += ooff[i];
       for (size_t i = 0; i < sover.size(); ++i) oent[i] = sover[i].second;
       if ((rc = dalloc(ctx, &ctx->s_ovoff, ooff.size())) || (rc = dalloc(ctx, &ctx->s_ovent, oent.size()))) return rc;
-      CK(cudaMemcpy(ctx->s_ovoff, ooff.data(), ooff.size() * sizeof(int), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(ctx->s_ovent, oent.data(), oent.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CK(ftb_memcpy(ctx, ctx->s_ovoff, ooff.data(), ooff.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CK(ftb_memcpy(ctx, ctx->s_ovent, oent.data(), oent.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     ctx->brick_ok = true;
   }
@@ -1065,13 +1076,13 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       (rc = dalloc(ctx, &ctx->d_detmin, 1)) || (rc = dalloc(ctx, &ctx->d_nonpos, 1)) ||
       (rc = dalloc(ctx, &ctx->d_nref, nNp)) || (rc = dalloc(ctx, &ctx->d_nint, nN)) || (rc = dalloc(ctx, &ctx->d_ell, 8 * (size_t)nNp)))
     return rc;
-  CK(cudaMemset(ctx->m, 0, nNp * sizeof(double)));
-  CK(cudaMemset(ctx->eflag, 0, nE));
-  CK(cudaMemset(ctx->felem, 0, 24 * 32 * (size_t)cdiv(nE, 32) * sizeof(double)));  // tiles of 32 elements (FTB_FIDX)
-  CK(cudaMemset(ctx->sc, 0, sizeof(DevScalars)));
-  CK(cudaMemcpy(ctx->conn, connT.data(), connT.size() * sizeof(int), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->pid, pidI.data(), nE * sizeof(int), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->ref_of, ref_of.data(), nE * sizeof(int), cudaMemcpyHostToDevice));
+  CK(ftb_memset(ctx, ctx->m, 0, nNp * sizeof(double)));
+  CK(ftb_memset(ctx, ctx->eflag, 0, nE));
+  CK(ftb_memset(ctx, ctx->felem, 0, 24 * 32 * (size_t)cdiv(nE, 32) * sizeof(double)));  // tiles of 32 elements (FTB_FIDX)
+  CK(ftb_memset(ctx, ctx->sc, 0, sizeof(DevScalars)));
+  CK(ftb_memcpy(ctx, ctx->conn, connT.data(), connT.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CK(ftb_memcpy(ctx, ctx->pid, pidI.data(), nE * sizeof(int), cudaMemcpyHostToDevice));
+  CK(ftb_memcpy(ctx, ctx->ref_of, ref_of.data(), nE * sizeof(int), cudaMemcpyHostToDevice));
   ctx->nGP = 8LL * nE;
   if (ctx->has_tet) {  // element types (internal order) and the packed Gauss-point offsets (reference order)
     std::vector<uint8_t> etI(nE);
@@ -1080,14 +1091,14 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
     for (int e = 0; e < nE; ++e) gpoff[e + 1] = gpoff[e] + (ctx->h_etype[e] ? 1 : 8);
     ctx->nGP = gpoff[nE];
     if ((rc = dalloc(ctx, &ctx->etype, nE)) || (rc = dalloc(ctx, &ctx->gpoff, nE + 1))) return rc;
-    CK(cudaMemcpy(ctx->etype, etI.data(), nE, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->gpoff, gpoff.data(), (nE + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    CK(ftb_memcpy(ctx, ctx->etype, etI.data(), nE, cudaMemcpyHostToDevice));
+    CK(ftb_memcpy(ctx, ctx->gpoff, gpoff.data(), (nE + 1) * sizeof(int), cudaMemcpyHostToDevice));
   }
-  CK(cudaMemcpy(ctx->mp, mp.data(), mp.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->node_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->node_ent, ent.data(), ent.size() * sizeof(int), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->d_nref, nref.data(), nNp * sizeof(int), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->d_nint, nint.data(), nN * sizeof(int), cudaMemcpyHostToDevice));
+  CK(ftb_memcpy(ctx, ctx->mp, mp.data(), mp.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(ftb_memcpy(ctx, ctx->node_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CK(ftb_memcpy(ctx, ctx->node_ent, ent.data(), ent.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CK(ftb_memcpy(ctx, ctx->d_nref, nref.data(), nNp * sizeof(int), cudaMemcpyHostToDevice));
+  CK(ftb_memcpy(ctx, ctx->d_nint, nint.data(), nN * sizeof(int), cudaMemcpyHostToDevice));
   std::vector<char> overflow(nNp, 0);
   {
     std::vector<int> ell(8 * (size_t)nNp, -1);
@@ -1096,12 +1107,12 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
       for (int q = 0; q < std::min(deg, 8); ++q) ell[(size_t)q * nNp + i] = ent[off[i] + q];
       if (deg > 8) overflow[i] = 1;
     }
-    CK(cudaMemcpy(ctx->d_ell, ell.data(), ell.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(ftb_memcpy(ctx, ctx->d_ell, ell.data(), ell.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
   if (ctx->has_visco) {  // Hn_1, Hn_2, S0n zero at t = 0 (ShapeFunctions.cpp:245-252)
     const size_t n = (size_t)144 * 32 * cdiv(nE, 32);  // tiles of 32 elements (FTB_HIDX)
     if ((rc = dalloc(ctx, &ctx->hist, n))) return rc;
-    CK(cudaMemset(ctx->hist, 0, n * sizeof(double)));
+    CK(ftb_memset(ctx, ctx->hist, 0, n * sizeof(double)));
   }
   // flags: padding nodes are fully constrained and never counted; shared / not-owned bits
   // (CheckEnergy.cpp:21-33: a shared node is counted by the lowest rank sharing it)
@@ -1115,25 +1126,25 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
     for (size_t p = 0; p < ctx->h_sendProcessID.size(); ++p)
       if (ctx->h_sendProcessID[p] < ctx->rank)
         for (int i = ctx->h_sendCum[p]; i < ctx->h_sendCum[p + 1]; ++i) fl[sendIdxInt[i]] |= FTB_FLAG_NOTOWNED;
-    CK(cudaMemcpy(ctx->flags, fl.data(), nNp * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CK(ftb_memcpy(ctx, ctx->flags, fl.data(), nNp * sizeof(uint16_t), cudaMemcpyHostToDevice));
   }
   if (ctx->halo_count) {
     if ((rc = dalloc(ctx, &ctx->d_sendNodeIndex, ctx->halo_count)) || (rc = dalloc(ctx, &ctx->halo_nodes, ctx->nshared)) ||
         (rc = dalloc(ctx, &ctx->halo_off, ctx->nshared + 1)) || (rc = dalloc(ctx, &ctx->halo_slot, ctx->halo_count)) ||
         (rc = dalloc(ctx, &ctx->halo_node_idx, nNp)))
       return rc;
-    CK(cudaMemcpy(ctx->d_sendNodeIndex, sendIdxInt.data(), ctx->halo_count * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->halo_nodes, halo_nodes.data(), ctx->nshared * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->halo_off, hoff.data(), hoff.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->halo_slot, hslot.data(), hslot.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->halo_node_idx, node_h.data(), nNp * sizeof(int), cudaMemcpyHostToDevice));
+    CK(ftb_memcpy(ctx, ctx->d_sendNodeIndex, sendIdxInt.data(), ctx->halo_count * sizeof(int), cudaMemcpyHostToDevice));
+    CK(ftb_memcpy(ctx, ctx->halo_nodes, halo_nodes.data(), ctx->nshared * sizeof(int), cudaMemcpyHostToDevice));
+    CK(ftb_memcpy(ctx, ctx->halo_off, hoff.data(), hoff.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(ftb_memcpy(ctx, ctx->halo_slot, hslot.data(), hslot.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(ftb_memcpy(ctx, ctx->halo_node_idx, node_h.data(), nNp * sizeof(int), cudaMemcpyHostToDevice));
   }
   if (const char* ev = getenv("FTB200_ENERGY_ASYNC")) ctx->energy_async = atoi(ev) != 0;
   // ---- validate the reference configuration: detJ0 > 0 at every Gauss point --------------------
   {
     const unsigned long long inf = 0x7FF0000000000000ULL;
-    CK(cudaMemcpy(ctx->d_detmin, &inf, sizeof(inf), cudaMemcpyHostToDevice));
-    CK(cudaMemset(ctx->d_nonpos, 0, sizeof(int)));
+    CK(ftb_memcpy(ctx, ctx->d_detmin, &inf, sizeof(inf), cudaMemcpyHostToDevice));
+    CK(ftb_memset(ctx, ctx->d_nonpos, 0, sizeof(int)));
     // the per-element masses land in the first 8 planes of felem (scratch until the first force call)
     LAUNCH(k_mass_elem, cdiv(nE, 128), 128, ctx->stream, elem_args(ctx, 0, nE, 1), ctx->felem, ctx->d_detmin, ctx->d_nonpos);
     LAUNCH(k_mass_gather, cdiv(nNp, 256), 256, ctx->stream, ctx->felem, ctx->node_off, ctx->node_ent, ctx->m, nNp, nE);
@@ -1377,16 +1388,16 @@ int ftb200_record_history(ftb200_ctx* ctx, long long capacity) {
   if (capacity > 0) {
     int rc;
     if ((rc = dalloc(ctx, &ctx->dthist, (size_t)capacity)) || (rc = dalloc(ctx, &ctx->ehist, 4 * (size_t)capacity))) return rc;
-    CK(cudaMemset(ctx->dthist, 0, capacity * sizeof(double)));
-    CK(cudaMemset(ctx->ehist, 0, 4 * capacity * sizeof(double)));
+    CK(ftb_memset(ctx, ctx->dthist, 0, capacity * sizeof(double)));
+    CK(ftb_memset(ctx, ctx->ehist, 0, 4 * capacity * sizeof(double)));
   }
-  CK(cudaMemcpy(&ctx->sc->hist_cap, &capacity, sizeof(long long), cudaMemcpyHostToDevice));
+  CK(ftb_memcpy(ctx, &ctx->sc->hist_cap, &capacity, sizeof(long long), cudaMemcpyHostToDevice));
   drop_graphs(ctx);  // dthist / ehist are kernel arguments of every captured loop (single-partition and peer-memory)
   dfree(ctx->inj_hist);
   if (ctx->injury && capacity > 0) {
     int rc;
     if ((rc = dalloc(ctx, &ctx->inj_hist, 2 * (size_t)capacity))) return rc;
-    CK(cudaMemset(ctx->inj_hist, 0, 2 * capacity * sizeof(double)));
+    CK(ftb_memset(ctx, ctx->inj_hist, 0, 2 * capacity * sizeof(double)));
   }
   return FTB200_OK;
 }
@@ -1395,8 +1406,8 @@ int ftb200_get_history(ftb200_ctx* ctx, long long first, long long count, double
   if (!ctx || first < 0 || count < 0 || first + count > ctx->hist_cap) return fail(ctx, FTB200_ERR_INPUT, "get_history: range");
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
-  if (dt_hist && count) CK(cudaMemcpy(dt_hist, ctx->dthist + first, count * sizeof(double), cudaMemcpyDeviceToHost));
-  if (energy_hist4 && count) CK(cudaMemcpy(energy_hist4, ctx->ehist + 4 * first, 4 * count * sizeof(double), cudaMemcpyDeviceToHost));
+  if (dt_hist && count) CK(ftb_memcpy(ctx, dt_hist, ctx->dthist + first, count * sizeof(double), cudaMemcpyDeviceToHost));
+  if (energy_hist4 && count) CK(ftb_memcpy(ctx, energy_hist4, ctx->ehist + 4 * first, 4 * count * sizeof(double), cudaMemcpyDeviceToHost));
   return FTB200_OK;
 }
 
@@ -1418,7 +1429,7 @@ int ftb200_explicit_begin_dt(ftb200_ctx* ctx, double Time0, double reduction, do
   // scalars: keep bc_rate / hist_cap, reset the rest
   DevScalars h;
   CK(cudaStreamSynchronize(s));  // a run enqueued earlier may still be writing the scalars and the step ring
-  CK(cudaMemcpy(&h, ctx->sc, sizeof(h), cudaMemcpyDeviceToHost));
+  CK(ftb_memcpy(ctx, &h, ctx->sc, sizeof(h), cudaMemcpyDeviceToHost));
   double rate[4];
   memcpy(rate, h.bc_rate, sizeof(rate));
   memset(&h, 0, sizeof(h));
@@ -1730,8 +1741,8 @@ int ftb200_step_ring(ftb200_ctx* ctx, long long capacity, double** host_ring) {
     ctx->ring_cap = capacity;
     for (long long i = 0; i < 8 * capacity; ++i) ctx->ring_host[i] = (i % 8 == 2) ? -1.0 : 0.0;
   }
-  CK(cudaMemcpy(&ctx->sc->ring, &ctx->ring_dev, sizeof(double*), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(&ctx->sc->ring_cap, &ctx->ring_cap, sizeof(long long), cudaMemcpyHostToDevice));
+  CK(ftb_memcpy(ctx, &ctx->sc->ring, &ctx->ring_dev, sizeof(double*), cudaMemcpyHostToDevice));
+  CK(ftb_memcpy(ctx, &ctx->sc->ring_cap, &ctx->ring_cap, sizeof(long long), cudaMemcpyHostToDevice));
   if (host_ring) *host_ring = ctx->ring_host;
   return FTB200_OK;
 }
@@ -1954,11 +1965,11 @@ int ftb200_p2p_export(ftb200_ctx* ctx, void* handle_out, void** window_out) {
   if (!ctx->p2p_window) {
     ctx->p2p_bytes = p2p_recv_off(ctx->nranks) + 2 * 3 * (size_t)std::max(ctx->halo_count, 1) * sizeof(double);
     CK(cudaMalloc((void**)&ctx->p2p_window, ctx->p2p_bytes));
-    CK(cudaMemset(ctx->p2p_window, 0, ctx->p2p_bytes));
+    CK(ftb_memset(ctx, ctx->p2p_window, 0, ctx->p2p_bytes));
     int rc;
     if ((rc = dalloc(ctx, &ctx->d_seq, 1)) || (rc = dalloc(ctx, &ctx->d_p2p_blocks, 1))) return rc;
-    CK(cudaMemset(ctx->d_seq, 0, sizeof(unsigned long long)));
-    CK(cudaMemset(ctx->d_p2p_blocks, 0, sizeof(unsigned)));
+    CK(ftb_memset(ctx, ctx->d_seq, 0, sizeof(unsigned long long)));
+    CK(ftb_memset(ctx, ctx->d_p2p_blocks, 0, sizeof(unsigned)));
     CK(cudaDeviceSynchronize());
   }
   if (handle_out) {
@@ -2097,22 +2108,22 @@ int ftb200_set_rigid_bc(ftb200_ctx* ctx, const int sizes[6], const double* const
   int rc;
   dfree(ctx->rigid_tab);
   if ((rc = dalloc(ctx, &ctx->rigid_tab, 2 * (size_t)total))) return rc;
-  CK(cudaMemcpy(ctx->rigid_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(ftb_memcpy(ctx, ctx->rigid_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
   h.tab_t = ctx->rigid_tab; h.tab_v = ctx->rigid_tab + total;
   h.R[0] = h.Rinv[0] = 1.0;
   if (!ctx->rigid && (rc = dalloc(ctx, &ctx->rigid, 1))) return rc;
-  CK(cudaMemcpy(ctx->rigid, &h, sizeof(h), cudaMemcpyHostToDevice));
+  CK(ftb_memcpy(ctx, ctx->rigid, &h, sizeof(h), cudaMemcpyHostToDevice));
   for (int k = 0; k < 3; ++k) {
     if (!ctx->aprev[k] && (rc = dalloc(ctx, &ctx->aprev[k], (size_t)ctx->nNp))) return rc;
-    CK(cudaMemset(ctx->aprev[k], 0, (size_t)ctx->nNp * sizeof(double)));
+    CK(ftb_memset(ctx, ctx->aprev[k], 0, (size_t)ctx->nNp * sizeof(double)));
   }
   ctx->rigid_count = (int)ids.size();
   if (!ids.empty()) {
     if ((rc = ensure_big(ctx, (ids.size() + (size_t)ctx->nN) * sizeof(int) + 16))) return rc;
     int* d_ids = reinterpret_cast<int*>(ctx->d_big);
     int* d_nint = d_ids + ids.size();
-    CK(cudaMemcpy(d_ids, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_nint, ctx->h_nint.data(), (size_t)ctx->nN * sizeof(int), cudaMemcpyHostToDevice));
+    CK(ftb_memcpy(ctx, d_ids, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(ftb_memcpy(ctx, d_nint, ctx->h_nint.data(), (size_t)ctx->nN * sizeof(int), cudaMemcpyHostToDevice));
     LAUNCH(k_rigid_mark, cdiv((int)ids.size(), 256), 256, ctx->stream, d_ids, (int)ids.size(), d_nint, ctx->flags, ctx->u[0], ctx->u[1],
            ctx->u[2], ctx->v[0], ctx->v[1], ctx->v[2], ctx->a[0], ctx->a[1], ctx->a[2]);
     LAUNCH(k_eflag, cdiv(ctx->nE, 256), 256, ctx->stream, ctx->conn, ctx->flags, ctx->eflag, ctx->nE);
@@ -2128,7 +2139,7 @@ int ftb200_get_rigid_state(ftb200_ctx* ctx, double* y12, double* ydot12, int* bo
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   DevRigid h;
-  CK(cudaMemcpy(&h, ctx->rigid, sizeof(h), cudaMemcpyDeviceToHost));
+  CK(ftb_memcpy(ctx, &h, ctx->rigid, sizeof(h), cudaMemcpyDeviceToHost));
   if (y12) for (int i = 0; i < 12; ++i) y12[i] = h.y[i];
   if (ydot12) for (int i = 0; i < 12; ++i) ydot12[i] = h.ydot[i];
   if (boundary_count) *boundary_count = ctx->rigid_count;
@@ -2144,7 +2155,7 @@ int ftb200_injury_begin(ftb200_ctx* ctx, const int* exclude_pids, int n_exclude,
   const size_t nE = ctx->nE;
   // InitInjuryCriterion (ex5.cpp:1251-1281): elements whose part is not excluded, internal element order
   std::vector<int> ref_of(nE);
-  CK(cudaMemcpy(ref_of.data(), ctx->ref_of, nE * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(ftb_memcpy(ctx, ref_of.data(), ctx->ref_of, nE * sizeof(int), cudaMemcpyDeviceToHost));
   std::vector<uint8_t> incl(nE, 1);
   int n = 0;
   for (size_t t = 0; t < nE; ++t) {
@@ -2165,23 +2176,23 @@ int ftb200_injury_begin(ftb200_ctx* ctx, const int* exclude_pids, int n_exclude,
       return rc;
   }
   // PS_Old starts at zero (the reference mallocs it uninitialised, ex5.cpp:1285; fresh pages read as zero)
-  CK(cudaMemset(ctx->inj_ps, 0, nE * sizeof(double)));
-  CK(cudaMemset(ctx->inj_psxsr, 0, nE * sizeof(double)));
-  CK(cudaMemset(ctx->inj_smin, 0, nE * sizeof(double)));
-  CK(cudaMemset(ctx->inj_shear, 0, nE * sizeof(double)));
-  CK(cudaMemset(ctx->inj_flags, 0, nE));
-  CK(cudaMemcpy(ctx->inj_incl, incl.data(), nE, cudaMemcpyHostToDevice));
+  CK(ftb_memset(ctx, ctx->inj_ps, 0, nE * sizeof(double)));
+  CK(ftb_memset(ctx, ctx->inj_psxsr, 0, nE * sizeof(double)));
+  CK(ftb_memset(ctx, ctx->inj_smin, 0, nE * sizeof(double)));
+  CK(ftb_memset(ctx, ctx->inj_shear, 0, nE * sizeof(double)));
+  CK(ftb_memset(ctx, ctx->inj_flags, 0, nE));
+  CK(ftb_memcpy(ctx, ctx->inj_incl, incl.data(), nE, cudaMemcpyHostToDevice));
   InjState st;
   memset(&st, 0, sizeof(st));
   st.kth0 = (unsigned)std::max(index95, 0);  // several partitions: ftb200_injury_global_count sets the global rank
   st.nIncluded = n;
-  CK(cudaMemcpy(ctx->inj_state, &st, sizeof(st), cudaMemcpyHostToDevice));
+  CK(ftb_memcpy(ctx, ctx->inj_state, &st, sizeof(st), cudaMemcpyHostToDevice));
   if (thresholds4) for (int k = 0; k < 4; ++k) ctx->inj_thr[k] = thresholds4[k];
   else { ctx->inj_thr[0] = 0.15; ctx->inj_thr[1] = 0.30; ctx->inj_thr[2] = 120.0; ctx->inj_thr[3] = 28.0; }
   dfree(ctx->inj_hist);
   if (ctx->hist_cap > 0) {
     if ((rc = dalloc(ctx, &ctx->inj_hist, 2 * (size_t)ctx->hist_cap))) return rc;
-    CK(cudaMemset(ctx->inj_hist, 0, 2 * ctx->hist_cap * sizeof(double)));
+    CK(ftb_memset(ctx, ctx->inj_hist, 0, 2 * ctx->hist_cap * sizeof(double)));
   }
   ctx->injury = true;
   drop_graphs(ctx);
@@ -2223,26 +2234,26 @@ int ftb200_injury_get(ftb200_ctx* ctx, double* scalars12, int* extreme_elems4, u
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   InjState st;
-  CK(cudaMemcpy(&st, ctx->inj_state, sizeof(st), cudaMemcpyDeviceToHost));
+  CK(ftb_memcpy(ctx, &st, ctx->inj_state, sizeof(st), cudaMemcpyDeviceToHost));
   if (scalars12) for (int k = 0; k < 12; ++k) scalars12[k] = st.scal[k];
   if (extreme_elems4) for (int k = 0; k < 4; ++k) extreme_elems4[k] = st.elems[k];
   if (!(flags || ps || psxsr || volumes5)) return FTB200_OK;
   const size_t nE = ctx->nE;
   std::vector<int> ref_of(nE);
   std::vector<uint8_t> f(nE), incl(nE);
-  CK(cudaMemcpy(ref_of.data(), ctx->ref_of, nE * sizeof(int), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(f.data(), ctx->inj_flags, nE, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(incl.data(), ctx->inj_incl, nE, cudaMemcpyDeviceToHost));
+  CK(ftb_memcpy(ctx, ref_of.data(), ctx->ref_of, nE * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(ftb_memcpy(ctx, f.data(), ctx->inj_flags, nE, cudaMemcpyDeviceToHost));
+  CK(ftb_memcpy(ctx, incl.data(), ctx->inj_incl, nE, cudaMemcpyDeviceToHost));
   std::vector<uint8_t> fr(nE);
   for (size_t t = 0; t < nE; ++t) fr[ref_of[t]] = (uint8_t)(f[t] | (incl[t] ? 0x80u : 0u));
   if (flags) memcpy(flags, fr.data(), nE);
   std::vector<double> tmp(nE);
   if (ps) {
-    CK(cudaMemcpy(tmp.data(), ctx->inj_ps, nE * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(ftb_memcpy(ctx, tmp.data(), ctx->inj_ps, nE * sizeof(double), cudaMemcpyDeviceToHost));
     for (size_t t = 0; t < nE; ++t) ps[ref_of[t]] = tmp[t];
   }
   if (psxsr) {
-    CK(cudaMemcpy(tmp.data(), ctx->inj_psxsr, nE * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(ftb_memcpy(ctx, tmp.data(), ctx->inj_psxsr, nE * sizeof(double), cudaMemcpyDeviceToHost));
     for (size_t t = 0; t < nE; ++t) psxsr[ref_of[t]] = tmp[t];
   }
   if (volumes5) {  // ex5.cpp:1049-1066: summed in the reference's element order
@@ -2266,8 +2277,8 @@ int ftb200_injury_history(ftb200_ctx* ctx, long long first, long long count, dou
     return fail(ctx, FTB200_ERR_INPUT, "injury_history: no history recorded (record_history before injury_begin) or bad range");
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
-  if (mps95 && count) CK(cudaMemcpy(mps95, ctx->inj_hist + first, count * sizeof(double), cudaMemcpyDeviceToHost));
-  if (mpsxsr95 && count) CK(cudaMemcpy(mpsxsr95, ctx->inj_hist + ctx->hist_cap + first, count * sizeof(double), cudaMemcpyDeviceToHost));
+  if (mps95 && count) CK(ftb_memcpy(ctx, mps95, ctx->inj_hist + first, count * sizeof(double), cudaMemcpyDeviceToHost));
+  if (mpsxsr95 && count) CK(ftb_memcpy(ctx, mpsxsr95, ctx->inj_hist + ctx->hist_cap + first, count * sizeof(double), cudaMemcpyDeviceToHost));
   return FTB200_OK;
 }
 
@@ -2276,7 +2287,7 @@ int ftb200_injury_local_count(ftb200_ctx* ctx, long long* n_included) {
   if (!ctx || !ctx->inj_state || !n_included) return fail(ctx, FTB200_ERR_INPUT, "injury_local_count: call injury_begin first");
   CK(cudaSetDevice(ctx->device));
   InjState st;
-  CK(cudaMemcpy(&st, ctx->inj_state, sizeof(st), cudaMemcpyDeviceToHost));
+  CK(ftb_memcpy(ctx, &st, ctx->inj_state, sizeof(st), cudaMemcpyDeviceToHost));
   *n_included = st.nIncluded;
   return FTB200_OK;
 }
@@ -2286,7 +2297,7 @@ int ftb200_injury_global_count(ftb200_ctx* ctx, long long n_total) {
   if (index95 < 0) return fail(ctx, FTB200_ERR_INPUT, "injury_global_count: %lld participating elements, the 95th percentile needs >= 2", n_total);
   CK(cudaSetDevice(ctx->device));
   const unsigned k = (unsigned)index95;
-  CK(cudaMemcpy(&ctx->inj_state->kth0, &k, sizeof(k), cudaMemcpyHostToDevice));
+  CK(ftb_memcpy(ctx, &ctx->inj_state->kth0, &k, sizeof(k), cudaMemcpyHostToDevice));
   return FTB200_OK;
 }
 int ftb200_injury_select_hist(ftb200_ctx* ctx, int pass, unsigned** hist_dev, int* hist_len) {

@@ -782,12 +782,21 @@ __global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node(const N
         const double a_old = (A.rigid && (fl & FTB_FLAG_RIGID)) ? A.aprev[c][n] : aa[c];
         if (!b) aa[c] = fnet / m;  // CalculateAcclerations.cpp:7-11
         if (KICK2) {
+          // displacement increment of the step for the energy check (displacements - displacements_prev, CheckEnergy.cpp:35):
+          // rebuilt from what the START of this step did instead of being carried through HBM (48 B per node and step) --
+          // a free dof moved by dt * v_half, a prescribed one by rate * (t_np1 - t_n) as the difference of the two stored
+          // values, a held one not at all; only rigid-body nodes (arbitrary kinematics) keep their stored increment
+          double dd = 0.0;
           if (!b) {
             const double vhalf = vv[c] + dt1 * a_old;  // Benchmarking-Parallel.cpp:115-122
             vv[c] = vhalf + dt2 * aa[c];               // :146-151
+            if (ENERGY) dd = sc->dt * vhalf;
+          } else if (ENERGY) {
+            const unsigned kind = (fl >> (4 + 2 * c)) & 3u;
+            if (A.rigid && (fl & FTB_FLAG_RIGID)) dd = A.du[c][n];
+            else if (kind) dd = sc->t_np1 * sc->bc_rate[kind] - sc->t_n * sc->bc_rate[kind];
           }
           if (ENERGY && !(fl & FTB_FLAG_NOTOWNED)) {   // CheckEnergy.cpp:19-52
-            const double dd = A.du[c][n];
             const double fprev = A.fi[c][n];
             wke += m * vv[c] * vv[c];
             if (b) wext += dd * (fprev + f[c] + m * (aa[c] + a_old));
@@ -815,7 +824,6 @@ __global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node(const N
           vv[c] = r;
           aa[c] = 0.0;
         }
-        if (ENERGY && !(A.rigid && (fl & FTB_FLAG_RIGID))) A.du[c][n] = uu[c] - u_old;
       }
       if (A.rigid && (fl & FTB_FLAG_RIGID)) {  // ApplyAccBoundaryConditions, ex5.cpp:352-371
         const DevRigid* rb = A.rigid;
@@ -1825,8 +1833,10 @@ __global__ void __launch_bounds__(INJ_THREADS) k_injury_xchg(const P2PArgs P, co
   if (threadIdx.x == 0) s_ok = 1;
   __threadfence_system();
   __syncthreads();
-  for (int r = threadIdx.x; r < P.n_ranks; r += INJ_THREADS)
+  for (int r = threadIdx.x; r < P.n_ranks; r += INJ_THREADS) {
+    __threadfence_system();  // release by the thread that raises the flag: the block's stores (ordered by the barrier) first
     *(volatile unsigned long long*)&reinterpret_cast<P2PHeader*>(P.peer_rank[r])->iflag[P.rank] = want;
+  }
   const unsigned long long t0 = now_ns();
   for (int r = threadIdx.x; r < P.n_ranks; r += INJ_THREADS) {
     volatile unsigned long long* fl = &reinterpret_cast<P2PHeader*>(P.self)->iflag[r];
