@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """BASELINE config 5 on several GPUs: the brain-simulation-shaped run of examples/brain_like.py (rigid outer shell, soft
 neo-Hookean layer, viscoelastic HGO core; prescribed rigid-body motion of the shell, ex5.cpp:339-371; injury criteria
-every step, ex5.cpp:1311-1430) with one partition per GPU inside the graph-captured peer-memory loop:
+every step, ex5.cpp:1311-1430) with one partition per GPU:
 
   * every rank integrates the same 12 rigid-body states (k_rigid_step) and moves its own shell nodes;
-  * the shared-node force sums and the dt MIN go through the peer-memory windows (k_p2p_pack / k_adv_p2p);
-  * the two 95th-percentile strains are GLOBAL order statistics: the histogram of every radix pass is summed over the
-    ranks through the same windows (k_injury_xchg) -- no NCCL call and no host work per step.
+  * the two 95th-percentile strains are GLOBAL order statistics: the histogram of every radix pass is summed over the ranks;
+  * default transport: the split-step sequence -- shared-node force sums by NCCL send/recv, dt MIN and the per-pass
+    histograms by NCCL all-reduce, interior elements overlapping the exchange (no host synchronisation in the loop);
+  * --windows (FTB200_INJURY_WINDOWS=1): everything through the peer-memory windows inside the graph-captured loop
+    (k_p2p_pack / k_adv_p2p / k_injury_xchg).  Exact in emulation and at small sizes, intermittently wrong percentiles at
+    >= 500 k elements per rank on real NVLink -- hence opt-in; --check exposes it.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 examples/brain_like_dist.py --edge 128
 
@@ -48,6 +51,7 @@ def main():
     ap.add_argument("--t-end", type=float, default=0.002)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--no-injury", action="store_true")
+    ap.add_argument("--windows", action="store_true", help="peer-memory loop also for the injury histograms (opt-in, see above)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
@@ -69,14 +73,19 @@ def main():
     d.explicit_begin(energy_every=1)
     if not args.no_injury:
         d.InitInjuryCriterion(exclude_pids=[0, 1])
-    d.enable_p2p(part["comm"])
-    d.run_p2p(args.t_end, 5)  # warm-up: builds the CUDA graph of the loop
+    use_windows = args.windows or args.no_injury
+    if args.windows:
+        os.environ["FTB200_INJURY_WINDOWS"] = "1"
+    if use_windows:
+        d.enable_p2p(part["comm"])
+    run = d.run_p2p if use_windows else d.run
+    run(args.t_end, 5)  # warm-up (peer-memory loop: builds the CUDA graph)
     torch.cuda.synchronize()
     dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(d.stream):
         ev0.record(d.stream)
-    d.run_p2p(args.t_end, args.steps)
+    run(args.t_end, args.steps)
     with torch.cuda.stream(d.stream):
         ev1.record(d.stream)
     torch.cuda.synchronize()
@@ -128,7 +137,10 @@ def main():
             rs = s.injury_results() if not args.no_injury else {"scalars": np.zeros(12)}
             r95 = float(np.abs(h95 - g95).max() / max(np.abs(g95).max(), 1e-300))
             rx95 = float(np.abs(hx95 - gx95).max() / max(np.abs(gx95).max(), 1e-300))
+            bad = np.nonzero(np.abs(h95 - g95) > 1e-9 * max(np.abs(g95).max(), 1e-300))[0]
             check = {"against": "single-GPU run of the same %d^3 mesh, %d steps" % (n, done), "steps_single": int(sd), "u_rel_err": eu,
+                     "mps95_first_bad_step": (int(bad[0]) if bad.size else None), "mps95_bad_steps": int(bad.size),
+                     "mps95_sample": [[int(i), float(h95[i]), float(g95[i])] for i in bad[:4]],
                      "mps95_hist_rel_err": r95, "mpsxsr95_hist_rel_err": rx95, "worst": worst if eu > 1e-9 else None,
                      "mps95_single": float(rs["scalars"][8]), "ok": bool(sd == done and eu < 1e-9 and r95 < 1e-9 and rx95 < 1e-6)}
             s.close()
@@ -137,7 +149,7 @@ def main():
         y, _, nb = m.rigid_state()
         print(json.dumps({
             "what": "brain-shaped multi-part mesh (rigid shell / neo-Hookean layer / HGO + Prony core), rigid-body motion of the shell, "
-                    "injury criteria every step, peer-memory loop",
+                    "injury criteria every step; transport: " + ("peer-memory windows" if use_windows else "NCCL split step"),
             "n_gpus": world, "elements": E_total, "steps": done - 5, "ms_per_step": float(ms[0]) / args.steps,
             "element_steps_per_s": E_total * args.steps / (float(ms[0]) * 1e-3), "Time": m.Time, "dt": m.dt,
             "status_bits": int(m.status_bits), "mps95": float(res["scalars"][8]), "mpsxsr95": float(res["scalars"][10]),

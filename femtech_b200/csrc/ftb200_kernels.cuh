@@ -1847,11 +1847,12 @@ __global__ void __launch_bounds__(INJ_THREADS) k_injury_xchg(const P2PArgs P, co
   }
   __threadfence_system();
   __syncthreads();
+  __threadfence_system();  // acquire in every reading thread too (the flags were observed by other threads of the block)
   if (!s_ok) { if (threadIdx.x == 0) atomicOr(&const_cast<DevScalars*>(sc)->status, 64); return; }
-  const unsigned* all = reinterpret_cast<const unsigned*>(P.self + p2p_ihist_off()) + (size_t)buf * P.n_ranks * slot;
+  const volatile unsigned* all = reinterpret_cast<const volatile unsigned*>(P.self + p2p_ihist_off()) + (size_t)buf * P.n_ranks * slot;
   for (int i = threadIdx.x; i < 2 * INJ_BINS; i += INJ_THREADS) {
     unsigned sum = 0;
-    for (int r = 0; r < P.n_ranks; ++r) sum += __ldcg(all + (size_t)r * slot + i);
+    for (int r = 0; r < P.n_ranks; ++r) sum += all[(size_t)r * slot + i];  // written by the peers: system-scope loads
     (&st->hist[0][0])[i] = sum;
   }
 }

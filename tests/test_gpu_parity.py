@@ -653,7 +653,7 @@ def test_injury_criteria_inside_the_peer_memory_loop():
     import os
     import subprocess
     import sys
-    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", FTB200_INJURY_WINDOWS="1")
     here = os.path.dirname(os.path.abspath(__file__))
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_parity as t; "
             "print('RESULT', t._injury_p3_case(True))" % (here, os.path.dirname(here)))
@@ -700,3 +700,66 @@ def test_off_switches_of_defaults_still_match_the_oracle(var):
     r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=env, capture_output=True,
                        text=True, timeout=300)
     assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
+
+
+def _injury_bricks_case(P, n_local):
+    """P in-process ranks (brick split of a structured box), injury criteria inside the peer-memory loop, against ONE context
+    on the global mesh: displacement 1e-9, the two global 95th-percentile histories 1e-9 / 1e-6."""
+    from femtech_b200 import dist as fdist
+    from femtech_b200 import solver
+    pg = fdist.proc_grid(P)
+    parts = [fdist.brick_partition(n_local, pg, r) for r in range(P)]
+    Nx, Ny, Nz = parts[0]["dims"]
+    h = parts[0]["box"][0] / Nx
+    props = [1040.0, 2.0e3, 2.0e4, 0, 0, 0, 0, 0, 0]
+    nsteps, tMax, dMax = 60, 1.0, 0.24  # the pull rate of the injury fixtures (0.0012 m in 0.005 s)
+    Ly = parts[0]["box"][1]
+    X, conn, pid = mesh.box_mesh(Nx, Ny, Nz, h)
+    kind, rate = mesh.benchmark_bc(X, L=Ly, dMax=dMax, tMax=tMax)
+    s = solver.FemTech(X, conn, pid, [1], props)
+    s.ShapeFunctions(); s.AssembleLumpedMass(); s.set_bc(kind, rate)
+    s._check(s.L.ftb200_record_history(s._h, nsteps + 8))
+    s.explicit_begin(energy_every=1)
+    s.InitInjuryCriterion()
+    assert s.ExplicitDynamics(tMax, maxSteps=nsteps) == nsteps
+    g95, gx95 = s.injury_history(0, nsteps)
+    U = s.displacements.reshape(-1, 3).copy()
+    s.close()
+    grp = fdist.LocalGroup(parts, [1], props)
+    grp.setup()
+    for m, p in zip(grp.models, parts):
+        k, rate = mesh.benchmark_bc(p["coordinates"], L=Ly, dMax=dMax, tMax=tMax)
+        m.set_bc(k, rate)
+        m._check(m.L.ftb200_record_history(m._h, nsteps + 8))
+    grp.explicit_begin(energy_every=1)
+    grp.InitInjuryCriterion()
+    grp.enable_p2p()
+    grp.run_p2p(tMax, nsteps)
+    out = {"u": 0.0, "h95": 0.0, "hx95": 0.0}
+    for m, p in zip(grp.models, parts):
+        m.sync_out()
+        assert int(m.steps_done) == nsteps
+        out["u"] = max(out["u"], rel(m.displacements.reshape(-1, 3), U[p["node_gids"]]))
+        h95, hx95 = m.injury_history(0, nsteps)
+        out["h95"] = max(out["h95"], rel(h95, g95))
+        out["hx95"] = max(out["hx95"], rel(hx95, gx95))
+    grp.close()
+    return out
+
+
+def test_injury_percentiles_eight_ranks_peer_memory_loop():
+    """Eight partitions (2 x 2 x 2 bricks, every rank a neighbour of every other) exchanging the radix histograms through
+    their windows.  Fresh process: 8 ranks x 2 streams share one device."""
+    import json
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", FTB200_INJURY_WINDOWS="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ("import json,sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_parity as t; "
+            "print('RESULT ' + json.dumps(t._injury_bricks_case(8, 8)))" % (here, os.path.dirname(here)))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+    assert r.returncode == 0 and line, (r.stdout[-1500:], r.stderr[-2500:])
+    o = json.loads(line[-1][7:])
+    assert o["u"] < TOL and o["h95"] < TOL and o["hx95"] < 1e-6, o
