@@ -5,11 +5,10 @@ every step, ex5.cpp:1311-1430) with one partition per GPU:
 
   * every rank integrates the same 12 rigid-body states (k_rigid_step) and moves its own shell nodes;
   * the two 95th-percentile strains are GLOBAL order statistics: the histogram of every radix pass is summed over the ranks;
-  * default transport: the split-step sequence -- shared-node force sums by NCCL send/recv, dt MIN and the per-pass
-    histograms by NCCL all-reduce, interior elements overlapping the exchange (no host synchronisation in the loop);
-  * --windows (FTB200_INJURY_WINDOWS=1): everything through the peer-memory windows inside the graph-captured loop
-    (k_p2p_pack / k_adv_p2p / k_injury_xchg).  Exact in emulation and at small sizes, intermittently wrong percentiles at
-    >= 500 k elements per rank on real NVLink -- hence opt-in; --check exposes it.
+  * default transport: everything through the peer-memory windows inside the graph-captured loop -- shared-node force
+    sums and dt MIN (k_p2p_pack / k_adv_p2p), the per-pass histograms (k_injury_xchg); no NCCL call, no host work per step;
+  * --nccl: the split-step sequence instead (NCCL send/recv of the shared-node windows, NCCL all-reduce of dt and of the
+    histograms, interior elements overlapping the exchange).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 examples/brain_like_dist.py --edge 128
 
@@ -51,7 +50,7 @@ def main():
     ap.add_argument("--t-end", type=float, default=0.002)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--no-injury", action="store_true")
-    ap.add_argument("--windows", action="store_true", help="peer-memory loop also for the injury histograms (opt-in, see above)")
+    ap.add_argument("--nccl", action="store_true", help="split-step sequence over NCCL instead of the peer-memory loop")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
@@ -73,9 +72,7 @@ def main():
     d.explicit_begin(energy_every=1)
     if not args.no_injury:
         d.InitInjuryCriterion(exclude_pids=[0, 1])
-    use_windows = args.windows or args.no_injury
-    if args.windows:
-        os.environ["FTB200_INJURY_WINDOWS"] = "1"
+    use_windows = not args.nccl
     if use_windows:
         d.enable_p2p(part["comm"])
     run = d.run_p2p if use_windows else d.run

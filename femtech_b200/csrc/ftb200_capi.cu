@@ -1637,17 +1637,6 @@ int ftb200_explicit_run_async(ftb200_ctx* ctx, double tMax, long long steps) {
       return fail(ctx, FTB200_ERR_INPUT, "explicit_run: multi-rank runs need the peer-memory windows (p2p_export/import) "
                                          "or the step_begin/step_join/step_end sequence");
     if (steps <= 0) return FTB200_OK;
-    if (ctx->injury && ctx->nranks > 1) {
-      // The per-pass histogram exchange through the windows (k_injury_xchg) is exact in the in-process emulation (3-rank
-      // reference partition, 8-rank bricks) and on 2-4 real GPUs at <= 65 k elements per rank, but the global percentile
-      // came out wrong intermittently at >= 500 k elements per rank over real NVLink: it stays
-      // opt-in until that is understood.  The split-step sequence (ftb200_step_begin/_join/_end with the caller's
-      // all-reduce of ftb200_injury_select_hist) is the checked multi-GPU path for the injury criteria.
-      const char* ev = getenv("FTB200_INJURY_WINDOWS");
-      if (!ev || atoi(ev) == 0)
-        return fail(ctx, FTB200_ERR_INPUT, "explicit_run: the injury criteria inside the peer-memory loop are opt-in "
-                                           "(FTB200_INJURY_WINDOWS=1); use the step_begin/step_join/step_end sequence");
-    }
     return run_async_p2p(ctx, tMax, steps);
   }
   if (steps <= 0) return FTB200_OK;

@@ -283,7 +283,11 @@ class DistFemTech:
         with torch.cuda.stream(self.stream):
             t = torch.tensor([n.value], dtype=torch.int64, device=self.device)
             self.dist.all_reduce(t)
-        m._check(m.L.ftb200_injury_global_count(m._h, int(t.item())))
+            # read back on the SAME stream: torch's streams do not synchronise with the default stream, and a .item()
+            # issued there could return this rank's own count before the all-reduce has run (seen on 8 GPUs: the global
+            # 95th percentile then used a local rank index and came out too low)
+            total = int(t.item())
+        m._check(m.L.ftb200_injury_global_count(m._h, total))
         self.injury = True
 
     def _injury_select(self):

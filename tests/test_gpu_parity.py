@@ -653,7 +653,7 @@ def test_injury_criteria_inside_the_peer_memory_loop():
     import os
     import subprocess
     import sys
-    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", FTB200_INJURY_WINDOWS="1")
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
     here = os.path.dirname(os.path.abspath(__file__))
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_parity as t; "
             "print('RESULT', t._injury_p3_case(True))" % (here, os.path.dirname(here)))
@@ -754,7 +754,7 @@ def test_injury_percentiles_eight_ranks_peer_memory_loop():
     import os
     import subprocess
     import sys
-    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", FTB200_INJURY_WINDOWS="1")
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
     here = os.path.dirname(os.path.abspath(__file__))
     code = ("import json,sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_parity as t; "
             "print('RESULT ' + json.dumps(t._injury_bricks_case(8, 8)))" % (here, os.path.dirname(here)))
