@@ -843,6 +843,9 @@ FTB_HD int hex8_element_in(const In& in, int mat, const double* __restrict__ mp,
 #define FTB_ASTAGE_U(k, c) FTB_ACOL((k) >> 2, (k) & 3, c)
 #define FTB_ASTAGE_X(kk, c) (36 + ((c) - 1) * 4 + (kk))
 #define FTB_AFFINE_SLOTS 54
+#ifndef FTB_AFF_GP_UNROLL
+#define FTB_AFF_GP_UNROLL 4
+#endif
 
 struct LocalScratchAffine {
   double v[FTB_AFFINE_SLOTS];
@@ -930,7 +933,10 @@ FTB_HD int hex8_element_affine_in(const In& in, int mat, const double* __restric
   for (int m = 0; m < 7; ++m)
 #pragma unroll
     for (int c = 0; c < 3; ++c) phi[m][c] = 0.0;
-  constexpr int kGpUnroll = FTB_GP_UNROLL;
+  // neo-Hookean without outputs: unrolled by FTB_AFF_GP_UNROLL -- measured at 100^3 rolled 163.9 us, by 2 161.9, by 4 159.7,
+  // by 8 167.8.  Rolled for the other variants (by 4: HGO 206.7 against 212.7 us but the same step time, HGO + Prony 531
+  // against 513, with the injury criteria 216 against 210)
+  constexpr int kGpUnroll = (MATSEL == 1 && !Out::enabled) ? FTB_AFF_GP_UNROLL : 1;
 #if defined(__CUDA_ARCH__)
 #pragma unroll kGpUnroll
 #endif
