@@ -52,6 +52,53 @@ FTB_HD double ftb_rcbrt(const double x) {
 #endif
 }
 
+// ln J and 1/J of the neo-Hookean stress, and the reciprocal of the HGO stresses, without the library's special-case
+// handling.  One Gauss point of k_elem_affine spends 172 fp64 and ~125 other instructions, and the kernel is bound by the
+// issue port: `log(J)` and `1.0 / J` alone were ~35 fp64 and ~45 other instructions of those
+// (exponent extraction, polynomial coefficients moved through uniform registers, slow-path tests and calls).  Here:
+//   1/x    MUFU.RCP64H seed + two Newton steps (x is a positive normal number: J > 0 is checked by the caller);
+//   ln J   = 2 atanh(s), s = (J - 1)/(J + 1), as 2 s (1 + z (1/3 + z (1/5 + ... + z/27))), z = s^2, for |s| <= 1/4
+//          (0.6 <= J <= 1.667; truncation < 1e-17 relative), coefficients as constant-bank operands of the DFMAs;
+//          outside that range the library functions.
+// Agreement with log / division: a few ulp (the parity tests hold the kernels to 1e-9 against the oracle over 1000 steps).
+#if defined(__CUDACC__)
+__constant__ double FTB_LN_C[13] = {1.0 / 3.0,  1.0 / 5.0,  1.0 / 7.0,  1.0 / 9.0,  1.0 / 11.0, 1.0 / 13.0, 1.0 / 15.0,
+                                    1.0 / 17.0, 1.0 / 19.0, 1.0 / 21.0, 1.0 / 23.0, 1.0 / 25.0, 1.0 / 27.0};
+#endif
+FTB_HD double ftb_rcp(const double x) {
+#if defined(__CUDA_ARCH__) && !defined(FTB_LIBM_MATERIAL)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+FTB_HD void ftb_ln_rcp(const double J, double* lnJ, double* rJ) {
+#if defined(__CUDA_ARCH__) && !defined(FTB_LIBM_MATERIAL)
+  const double w = J - 1.0, t = J + 1.0;
+  const double rt = ftb_rcp(t);
+  double s = w * rt;
+  s = fma(rt, fma(-s, t, w), s);  // one correction: s = (J - 1)/(J + 1) to within an ulp
+  *rJ = ftb_rcp(J);
+  if (fabs(s) <= 0.25) {
+    const double z = s * s;
+    double p = FTB_LN_C[12];
+#pragma unroll
+    for (int k = 11; k >= 0; --k) p = fma(p, z, FTB_LN_C[k]);
+    const double s2 = s + s;
+    *lnJ = fma(s2 * z, p, s2);
+  } else {
+    *lnJ = log(J);
+  }
+#else
+  *lnJ = log(J);
+  *rJ = 1.0 / J;
+#endif
+}
+
 // Per-part parameter block (device memory, FTB_MP_STRIDE doubles per part).
 // [0..8] are properties[9*pid + k] (src/io/input/ReadMaterials.cpp:43-122).
 enum {
@@ -185,7 +232,8 @@ FTB_HD void pullback_sym(const double cofF[3][3], const double sig[6], const dou
 // (src/materials/HGOIsotropic.cpp:44-84): sigma = pref*dev(B) + hydro*I.
 FTB_HD void hgo_cauchy(const double F[3][3], const double J, const double* __restrict__ mp, double sig[6]) {
   const double mu = mp[MP_MU], k1 = mp[MP_K1], k2 = mp[MP_K2], K = mp[MP_KBULK];
-  const double hydro = 0.5 * K * (J * J - 1.0) / J;
+  const double rJ = ftb_rcp(J);
+  const double hydro = 0.5 * K * (J * J - 1.0) * rJ;
   double B[6];  // B = F F^T, Voigt
   B[0] = F[0][0] * F[0][0] + F[0][1] * F[0][1] + F[0][2] * F[0][2];
   B[1] = F[1][0] * F[1][0] + F[1][1] * F[1][1] + F[1][2] * F[1][2];
@@ -204,8 +252,8 @@ FTB_HD void hgo_cauchy(const double F[3][3], const double J, const double* __res
     const double ex = (k2 == 0.0) ? 1.0 : exp(k2 * Ea * Ea);
     fiber = 2.0 * k1 * ex * Ea * kappa;
   }
-  const double pref = Jm23 * (mu + fiber) / J;
-  const double t3 = trB / 3.0;
+  const double pref = Jm23 * (mu + fiber) * rJ;
+  const double t3 = trB * (1.0 / 3.0);
   sig[0] = (B[0] - t3) * pref + hydro;
   sig[1] = (B[1] - t3) * pref + hydro;
   sig[2] = (B[2] - t3) * pref + hydro;
@@ -234,8 +282,9 @@ FTB_HD int material_P(const int mat, const double F[3][3], const double cofF[3][
     case 1: {  // compressible neo-Hookean (CompressibleNeoHookean.cpp:43-55)
       // S = mu (I - C^-1) + lambda ln J C^-1  =>  P = mu F + (lambda ln J - mu) F^-T,  F^-T = cof F / J
       // the reciprocal runs concurrently with the logarithm (two independent serial chains)
-      const double rJ = 1.0 / J;
-      const double c = (lambda * log(J) - mu) * rJ;
+      double lnJ, rJ;
+      ftb_ln_rcp(J, &lnJ, &rJ);
+      const double c = (lambda * lnJ - mu) * rJ;
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -774,7 +823,7 @@ FTB_HD int hex8_element_in(const In& in, int mat, const double* __restrict__ mp,
     cofactor3(J0, cJ);
     const double det = J0[0][0] * cJ[0][0] + J0[0][1] * cJ[0][1] + J0[0][2] * cJ[0][2];  // 512 detJ0
     if (!(det > 0.0)) status |= 2;
-    const double rdet = 1.0 / det;
+    const double rdet = ftb_rcp(det);
     // F = I + Uh * J0^-1 ,  J0^-1[c][j] = cJ[j][c] / det
     double F[3][3];
 #pragma unroll
@@ -844,7 +893,7 @@ FTB_HD int hex8_element_in(const In& in, int mat, const double* __restrict__ mp,
 #define FTB_ASTAGE_X(kk, c) (36 + ((c) - 1) * 4 + (kk))
 #define FTB_AFFINE_SLOTS 54
 #ifndef FTB_AFF_GP_UNROLL
-#define FTB_AFF_GP_UNROLL 4
+#define FTB_AFF_GP_UNROLL 1
 #endif
 
 struct LocalScratchAffine {
@@ -916,7 +965,7 @@ FTB_HD int hex8_element_affine_in(const In& in, int mat, const double* __restric
     cofactor3(J0, cJ);
     const double det = J0[0][0] * cJ[0][0] + J0[0][1] * cJ[0][1] + J0[0][2] * cJ[0][2];  // 512 detJ0
     if (!(det > 0.0)) status |= 2;
-    const double rdet = 1.0 / det;
+    const double rdet = ftb_rcp(det);
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
@@ -925,7 +974,7 @@ FTB_HD int hex8_element_affine_in(const In& in, int mat, const double* __restric
         S.st(FTB_AJI(c, j), cJ[j][c] * rdet);  // J0^-1[c][j] = cof[j][c] / det
       }
     // dt = (V / A_max) / c_e with V = det J0 sum_gp det F (see hex8_element_in); det here is 512 det J0
-    if (WITH_DT) dtk = det / (512.0 * hex_face_amax(xm) * mp[MP_CE]);
+    if (WITH_DT) dtk = det * ftb_rcp(512.0 * hex_face_amax(xm) * mp[MP_CE]);
   }
   double vsum = 0.0;
   double phi[7][3];
@@ -933,9 +982,9 @@ FTB_HD int hex8_element_affine_in(const In& in, int mat, const double* __restric
   for (int m = 0; m < 7; ++m)
 #pragma unroll
     for (int c = 0; c < 3; ++c) phi[m][c] = 0.0;
-  // neo-Hookean without outputs: unrolled by FTB_AFF_GP_UNROLL -- measured at 100^3 rolled 163.9 us, by 2 161.9, by 4 159.7,
-  // by 8 167.8.  Rolled for the other variants (by 4: HGO 206.7 against 212.7 us but the same step time, HGO + Prony 531
-  // against 513, with the injury criteria 216 against 210)
+  // The loop stays rolled (FTB_AFF_GP_UNROLL = 1).  Measured at 100^3, neo-Hookean: with the library log / division rolled
+  // 164.0 us, unrolled by 2 161.9, by 4 159.8, by 8 167.8; with ftb_ln_rcp rolled **155.6**, by 2 176, by 4 180 (spills).
+  // HGO, HGO + Prony and the injury variant lose with any unrolling.
   constexpr int kGpUnroll = (MATSEL == 1 && !Out::enabled) ? FTB_AFF_GP_UNROLL : 1;
 #if defined(__CUDA_ARCH__)
 #pragma unroll kGpUnroll
@@ -1059,13 +1108,13 @@ FTB_HD int hex8_brick_setup(const In& in, const double* __restrict__ mp, Scratch
   cofactor3(J0, cJ);
   const double det = J0[0][0] * cJ[0][0] + J0[0][1] * cJ[0][1] + J0[0][2] * cJ[0][2];  // 512 detJ0
   if (!(det > 0.0)) status |= 2;
-  const double rdet = 1.0 / det;
+  const double rdet = ftb_rcp(det);
 #pragma unroll
   for (int j = 0; j < 3; ++j)
 #pragma unroll
     for (int c = 0; c < 3; ++c) S.st_ji(c * 3 + j, cJ[j][c] * rdet);  // J0^-1[c][j] = cof[j][c] / det
   *det_out = det;
-  *dtk_out = det / (512.0 * hex_face_amax(xm) * mp[MP_CE]);  // dt = (V / A_max) / c_e with V = det J0 sum_gp det F
+  *dtk_out = det * ftb_rcp(512.0 * hex_face_amax(xm) * mp[MP_CE]);  // dt = (V / A_max) / c_e with V = det J0 sum_gp det F
   return status;
 }
 
@@ -1182,7 +1231,7 @@ FTB_HD int tet4_element(const double X[4][3], const double U[4][3], int mat, con
   cofactor3(J0, cJ);
   const double det = J0[0][0] * cJ[0][0] + J0[0][1] * cJ[0][1] + J0[0][2] * cJ[0][2];
   if (det == 0.0 || !(det == det)) status |= 2;
-  const double rdet = 1.0 / det;
+  const double rdet = ftb_rcp(det);
   double F[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
