@@ -47,6 +47,8 @@ NCU_TRAFFIC_BYTES = {(100, 1, True, False, False): 86507008 + 138745344,   # pro
 # executed fp64 flops per element in K_elem (FMA = 2).  Material 1 from ncu (general kernel: 1208 DFMA + 463 DADD + 507 DMUL
 # per element, profiles/r01_k_elem_general_ncu_full.csv); materials 4 and 5 = material 1 + the SASS difference of their
 # material code
+# Round 2 check (profiles/r02_k_elem_affine_ncu_full.csv, ftb_ln_rcp in the material code): 1082 DFMA + 320 DADD + 373 DMUL
+# per element = 2857 flops -- the same work in 14 % fewer instructions (88.4 M instead of 102.4 M warp instructions)
 ELEM_FLOPS = {1: 3386.0, 4: 4296.0, 5: 6446.0}
 # k_elem_affine (parallelepiped reference geometry): no cofactor / determinant / reciprocal of J0 per Gauss point, F in 27
 # FMAs, no coordinate modes and columns: 1060 DFMA + 357 DADD + 378 DMUL per element for material 1
