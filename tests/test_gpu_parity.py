@@ -763,3 +763,50 @@ def test_injury_percentiles_eight_ranks_peer_memory_loop():
     assert r.returncode == 0 and line, (r.stdout[-1500:], r.stderr[-2500:])
     o = json.loads(line[-1][7:])
     assert o["u"] < TOL and o["h95"] < TOL and o["hx95"] < 1e-6, o
+
+
+def test_external_force_through_legacy_call_and_resident_loop():
+    """A non-zero external force (fe): f_net = fe - fi of the legacy GetForce, and the resident loop with fe in the node
+    kernel (a = (fe - fi)/m) and in the external work of the energy check, against the oracle.  The fe planes live in the
+    padded internal node order (an 11^3-node mesh pads to 1408 nodes): the write past nN that the advisor found would
+    corrupt the neighbouring allocation here."""
+    from femtech_b200 import solver
+    from oracle import pyoracle as po
+    X, conn, pid = mesh.cube_mesh(10, jitter=0.05)
+    props = [1040.0, 2.0e5, 4.0e5, 0, 0, 0, 0, 0, 0]
+    kind, rate = mesh.benchmark_bc(X, dMax=0.007, tMax=0.1)
+    rng = np.random.default_rng(11)
+    fe = 2.0e-3 * rng.standard_normal(3 * X.shape[0])
+    fe[kind > 0] = 0.0  # (loads on prescribed dofs only enter the external work)
+    nsteps = 80
+    o = po.OracleModel(X, conn, pid, [1], props)
+    o.ShapeFunctions()
+    o.AssembleLumpedMass()
+    o.fe[:] = fe
+    o.fe_prev[:] = fe
+    m = solver.FemTech(X, conn, pid, [1], props)
+    m.ShapeFunctions()
+    m.AssembleLumpedMass()
+    m.fe[:] = fe
+    # legacy call on a deformed state
+    u0 = 1e-5 * rng.standard_normal(3 * X.shape[0])
+    o.displacements[:] = u0
+    m.displacements[:] = u0
+    o.GetForce()
+    m.GetForce()
+    assert rel(m.fi, o.fi) < 1e-11 and rel(m.f_net, o.f_net) < 1e-11
+    assert np.abs(m.f_net + m.fi - fe).max() <= 1e-12 * np.abs(m.fi).max()
+    # resident loop from rest with the same load
+    o.displacements[:] = 0.0
+    m.displacements[:] = 0.0
+    n, dth_o, eh_o = po.run_explicit([o], [kind], rate, 1.0, nsteps)
+    assert n == nsteps
+    m.set_bc(kind, rate)
+    m.explicit_begin(energy_every=1, record_steps=nsteps)
+    assert m.ExplicitDynamics(1.0, maxSteps=nsteps) == nsteps
+    dth, eh = m.history(0, nsteps)
+    assert np.allclose(dth, dth_o, rtol=1e-11, atol=0)
+    assert rel(m.displacements, o.displacements) < TOL and rel(m.velocities, o.velocities) < TOL
+    assert rel(m.f_net, o.f_net) < 1e-6
+    assert np.allclose(eh[-1][:3], eh_o[-1][:3], rtol=1e-8, atol=1e-14 * np.abs(eh_o[-1]).max())
+    m.close()
