@@ -29,4 +29,9 @@ void femtech_b200_set_rigid_bc(const int sizes[6], const double *const t[6], con
                                int boundarySize, int energy_every);
 void femtech_b200_injury_results(double scalars12[12], int extreme_elems4[4], unsigned char *flags, double *PS_Old,
                                  double *PSxSRArray, double volumes5[5]);
+/* Steps executed and seconds spent inside the last ExplicitDynamics() call (set-up of step 0 and the final read-back
+ * included), the transport used on several ranks ("single", "p2p", "host"): what a driver prints as its throughput. */
+long long femtech_b200_last_steps(void);
+double femtech_b200_last_seconds(void);
+const char *femtech_b200_last_transport(void);
 #endif

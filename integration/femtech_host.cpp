@@ -294,6 +294,11 @@ void femtech_b200_set_rigid_bc(const int sizes[6], const double *const t[6], con
  *         and adding -- the default when ranks share a GPU (processes on one device time-slice: a kernel that waits for a
  *         peer's flag would wait for the peer's time slice), FTB200_MPI_TRANSPORT=host|p2p overrides. */
 static bool g_p2p = false, g_p2p_ready = false;
+static long long g_last_steps = 0;
+static double g_last_seconds = 0.0;
+long long femtech_b200_last_steps(void) { return g_last_steps; }
+double femtech_b200_last_seconds(void) { return g_last_seconds; }
+const char *femtech_b200_last_transport(void) { return world_size == 1 ? "single" : (g_p2p ? "p2p" : "host"); }
 static void setup_p2p() {
   if (g_p2p_ready) return;
   unsigned char handle[64];
@@ -338,6 +343,7 @@ void ExplicitDynamics(double timeFinal, char *name) {
   (void)name;
   ensure_ctx();
   g_state_gen++;
+  const double wall0 = MPI_Wtime();
   if (!g_bc_kind && g_rigid) {  /* only the rigid-body condition: no other dof is prescribed */
     g_bc_kind = (int *)calloc(nDOF, sizeof(int));
   }
@@ -401,6 +407,8 @@ void ExplicitDynamics(double timeFinal, char *name) {
   if (st & 1) { FILE_LOG_SINGLE(ERROR, "Unknown material type"); TerminateFemTech(1); }
   if (st & 16) { FILE_LOG_SINGLE(ERROR, "Timestep too small, dt below FailureTimeStep"); TerminateFemTech(19); }
   check(ftb200_get_state(g_ctx, displacements, velocities, accelerations, boundary, fi, f_net));
+  g_last_steps = steps;
+  g_last_seconds = MPI_Wtime() - wall0;
   FILE_LOG_MASTER(INFO, "ExplicitDynamics: %lld steps on the GPU, Time = %15.6e", steps, Time);
 }
 

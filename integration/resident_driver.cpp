@@ -68,6 +68,16 @@ int main(int argc, char **argv) {
     for (int i = 0; i < nNodes * ndim; ++i) fprintf(f, "%.17g\n", velocities[i]);
   }
   fclose(f);
+  {  // throughput of the call, summed over the ranks' elements (every element belongs to exactly one rank)
+    long long eLocal = nelements, eTotal = 0;
+    MPI_Reduce(&eLocal, &eTotal, 1, MPI_LONG_LONG, MPI_SUM, 0, MPI_COMM_WORLD);
+    double sec = femtech_b200_last_seconds(), secMax = 0.0;
+    MPI_Reduce(&sec, &secMax, 1, MPI_DOUBLE, MPI_MAX, 0, MPI_COMM_WORLD);
+    if (world_rank == 0)
+      printf("RESIDENT ranks %d transport %s elements %lld steps %lld seconds %.6f element_steps_per_s %.6e\n", world_size,
+             femtech_b200_last_transport(), eTotal, femtech_b200_last_steps(), secMax,
+             (double)eTotal * (double)femtech_b200_last_steps() / secMax);
+  }
   FinalizeFemTech();  // frees the arrays (InitFinalizeFemTech.cpp:75-80)
   return 0;
 }
