@@ -51,6 +51,7 @@ struct ftb200_ctx {
   double* ring_dev = nullptr;
   long long ring_cap = 0;
   bool use_affine = true;  // FTB200_AFFINE=0: parallelepiped hexahedra go through the general kernel too
+  bool use_nh = true;      // FTB200_NH=0: neo-Hookean parallelepipeds through k_elem_affine<1, false> instead of k_elem_affine_nh
   long long nE_affine = 0;
   // rigid-body prescribed motion (ftb200_set_rigid_bc)
   DevRigid* rigid = nullptr;
@@ -282,6 +283,7 @@ void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore
     switch (mat) {
       case 1:
         if (inj) LAUNCH((k_elem_affine<1, true>), grid, ELEM_BLOCK, s, A);
+        else if (ctx->use_nh) LAUNCH(k_elem_affine_nh, grid, ELEM_BLOCK, s, A);
         else LAUNCH((k_elem_affine<1, false>), grid, ELEM_BLOCK, s, A);
         return;
       case 4:
@@ -816,6 +818,7 @@ int ftb200_shape_functions(ftb200_ctx* ctx, double* min_detJ) {
     std::vector<char> aff(nE, 0);
     ctx->nE_affine = 0;
     if (const char* ev = getenv("FTB200_AFFINE")) ctx->use_affine = atoi(ev) != 0;
+    if (const char* ev = getenv("FTB200_NH")) ctx->use_nh = atoi(ev) != 0;
     if (ctx->use_affine)
       for (int e = 0; e < nE; ++e) {
         if (mixed && ctx->h_etype[e]) continue;

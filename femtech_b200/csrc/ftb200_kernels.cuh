@@ -477,6 +477,65 @@ __global__ void __launch_bounds__(ELEM_BLOCK, MATSEL == 5 ? 4 : (WITH_INJ ? FTB_
   if (status) atomicOr(&A.sc->status, status);
 }
 
+// K_elem for runs of neo-Hookean parallelepipeds without the strain outputs (the headline configuration): the element
+// in current-Jacobian form (hex8_element_affine_nh: the linear part of the stress summed over the Gauss points in closed
+// form, 9 shared loads and ~95 fp64 instructions per point).  Same gather plan, same outputs and step semantics as
+// k_elem_affine<1, false>; 44 scratch slots per thread.  FTB200_NH=0 sends such runs through k_elem_affine again.
+#ifndef FTB_NH_MINBLOCKS
+#define FTB_NH_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(ELEM_BLOCK, FTB_NH_MINBLOCKS) k_elem_affine_nh(const ElemArgs A) {
+  const int e = A.e0 + blockIdx.x * ELEM_BLOCK + threadIdx.x;
+  const size_t E = (size_t)A.nE;
+  int nd[8];
+  int p = 0;
+  unsigned skip = 0;
+  if (e < A.e1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) nd[k] = __ldg(A.conn + (size_t)k * E + e);
+    p = __ldg(A.pid + e);
+    skip = __ldg(A.eflag + e);
+  }
+  if (!A.ignore_loop_flags && (A.sc->last | A.sc->done)) return;
+  __shared__ double sm_cols[FTB_NH_SLOTS][ELEM_BLOCK];
+  double dte = 1e300;
+  int status = 0;
+  if (e < A.e1) {
+    double X0[4], U0[8];
+    double* colbase = &sm_cols[0][threadIdx.x];
+    const int nx[4] = {nd[0], nd[1], nd[3], nd[4]};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) U0[k] = __ldg(A.u[0] + nd[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) X0[k] = __ldg(A.X[0] + nx[k]);
+#pragma unroll
+    for (int c = 1; c < 3; ++c) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cp_async8(colbase + FTB_ASTAGE_U(k, c) * ELEM_BLOCK, A.u[c] + nd[k]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cp_async8(colbase + FTB_ASTAGE_X(k, c) * ELEM_BLOCK, A.X[c] + nx[k]);
+    }
+    const double* mp = A.mp + (size_t)p * FTB_MP_STRIDE;
+    double fe[8][3];
+    double d;
+    SmemScratchAffine S{colbase};
+    status = hex8_element_affine_nh<true>(StagedInAffine{X0, U0, colbase}, mp, S, fe, &d);
+    dte = skip ? 1e300 : d;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) A.felem[FTB_FIDX(3 * k + c, e)] = fe[k][c];
+  }
+  unsigned long long b = dt_to_bits(dte);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o);
+    b = t < b ? t : b;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMin(&A.sc->dtmin_bits, b);
+  if (status) atomicOr(&A.sc->status, status);
+}
+
 // The C3D4 elements of a mixed mesh: they sit in their own index ranges of the internal element
 // order, so this kernel sees only tetrahedra and k_elem only hexahedra.  One thread per element, generic material.
 constexpr int TET_BLOCK = 128;

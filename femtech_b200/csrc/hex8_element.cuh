@@ -1059,6 +1059,171 @@ FTB_HD int hex8_element_affine_in(const In& in, int mat, const double* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// The neo-Hookean parallelepiped in CURRENT-JACOBIAN form (round 2; the default for runs of material-1 parallelepipeds
+// without the strain outputs).  Same element, same Gauss rule, algebra rearranged so that the Gauss loop only carries
+// what is nonlinear:
+//   Ft = dx/dxi = J0 + dU/dxi (the Jacobian of the CURRENT configuration; F = Ft J0^-1 is never formed),
+//   cof F = cof(Ft) cof(J0)^-1,  J = det Ft / det J0,
+//   Q = P cof(J0) = mu Ft M + c cof(Ft),   M = J0^-1 cof(J0) = cof(J0)^T cof(J0) / det J0 (symmetric, one per element),
+//   c = (lambda ln J - mu) / J   (CompressibleNeoHookean.cpp:43-55 pushed through P = F S).
+// The first term is LINEAR in the nodal positions and M is the same at all eight points, so its sum over the Gauss
+// points is taken in closed form in the mode basis (sign patterns of different modes are orthogonal over the 2x2x2
+// rule): linear modes 8 mu xm_t M, bilinear 8 a mu (...), trilinear 8 a^2 mu xm_123 tr M -- about 60 flops per element
+// instead of 63 per point.  What stays in the loop is cof(Ft), det, ln J, 1/J and 36 accumulations of c cof(Ft): 9 shared
+// loads and ~95 fp64 instructions per point against 27 loads and ~172 for hex8_element_affine_in, no J0^-1 / cof(J0)
+// slots.  The rest state is no longer an exact zero (8 mu J0 M and sum c cof(Ft) cancel to rounding, a spurious
+// strain of ~1e-16 -- the reference, which builds F from coordinates, has the same noise); differs from
+// hex8_element_affine_in by rounding only (tests/test_element_math_cpu.py pins 1e-12 of the force maximum at 0.4 %
+// strain).
+//
+// ln J with a short series first: |s| <= 1/16 (0.882 <= J <= 1.133) needs 6 terms for 1e-18.
+FTB_HD void ftb_ln_rcp_tiered(const double J, double* lnJ, double* rJ) {
+#if defined(__CUDA_ARCH__) && !defined(FTB_LIBM_MATERIAL)
+  const double w = J - 1.0, t = J + 1.0;
+  const double rt = ftb_rcp(t);
+  double s = w * rt;
+  s = fma(rt, fma(-s, t, w), s);
+  *rJ = ftb_rcp(J);
+  const double z = s * s, zz = z * z, s2 = s + s;
+  if (fabs(s) <= 0.0625) {
+    // 1/3 + z/5 + z^2/7 + z^3/9 + z^4/11 + z^5/13: even and odd powers as two chains
+    const double pe = fma(fma(FTB_LN_C[4], zz, FTB_LN_C[2]), zz, FTB_LN_C[0]);
+    const double po = fma(fma(FTB_LN_C[5], zz, FTB_LN_C[3]), zz, FTB_LN_C[1]);
+    *lnJ = fma(s2 * z, fma(po, z, pe), s2);
+  } else if (fabs(s) <= 0.25) {
+    double pe = FTB_LN_C[12], po = FTB_LN_C[11];
+#pragma unroll
+    for (int k = 10; k >= 0; k -= 2) pe = fma(pe, zz, FTB_LN_C[k]);
+#pragma unroll
+    for (int k = 9; k >= 1; k -= 2) po = fma(po, zz, FTB_LN_C[k]);
+    *lnJ = fma(s2 * z, fma(po, z, pe), s2);
+  } else {
+    *lnJ = log(J);
+  }
+#else
+  *lnJ = log(J);
+  *rJ = 1.0 / J;
+#endif
+}
+#define FTB_NH_SLOTS 44  // 36 column entries + the staging slots of the reference nodes (FTB_ASTAGE_X)
+#ifndef FTB_NH_GP_UNROLL
+#define FTB_NH_GP_UNROLL 8
+#endif
+template <bool WITH_DT, class In, class Scratch>
+FTB_HD int hex8_element_affine_nh(const In& in, const double* __restrict__ mp, Scratch& S, double fe[8][3], double* dtElem) {
+  const double a = FTB_GP_A, a2 = FTB_GP_A * FTB_GP_A;
+  const double mu = mp[MP_MU], lambda = mp[MP_LAMBDA];
+  int status = 0;
+  double dtk = 0.0, rdet0;
+  double phi[7][3];
+  {
+    double xm[7][3];  // modes of the current coordinates (8 dx/dxi scaling): linear ones J0 + gU, the rest gU
+    double J0[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double x[4], nu[8], gU[7];
+      in.getX(c, x);
+      J0[c][0] = 4.0 * (x[1] - x[0]);
+      J0[c][1] = 4.0 * (x[2] - x[0]);
+      J0[c][2] = 4.0 * (x[3] - x[0]);
+      in.getU(c, nu);
+      hex_modes(nu, gU);
+      xm[0][c] = J0[c][0] + gU[0]; xm[1][c] = J0[c][1] + gU[1]; xm[2][c] = J0[c][2] + gU[2];
+      xm[3][c] = gU[3]; xm[4][c] = gU[4]; xm[5][c] = gU[5]; xm[6][c] = gU[6];
+      const double U12 = a * gU[3], U23 = a * gU[4], U13 = a * gU[5], U123 = a2 * gU[6];
+      const double A[3] = {xm[0][c], xm[1][c], xm[2][c]}, B[3] = {U12, U12, U13}, C[3] = {U13, U23, U23};
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {  // column t of 8 dx/dxi at its four sign pairs (layout of hex8_element_affine_in)
+        const double ad = A[t] + U123, am = A[t] - U123, bc = B[t] + C[t], bm = B[t] - C[t];
+        S.st(FTB_ACOL(t, 3, c), ad + bc);
+        S.st(FTB_ACOL(t, 0, c), ad - bc);
+        S.st(FTB_ACOL(t, 1, c), am + bm);
+        S.st(FTB_ACOL(t, 2, c), am - bm);
+      }
+    }
+    double cJ[3][3];
+    cofactor3(J0, cJ);
+    const double det = J0[0][0] * cJ[0][0] + J0[0][1] * cJ[0][1] + J0[0][2] * cJ[0][2];  // 512 det J0
+    if (!(det > 0.0)) status |= 2;
+    rdet0 = ftb_rcp(det);
+    // dt = (V / A_max) / c_e with V = det J0 sum_gp det F = sum_gp det Ft (see hex8_element_in); before the linear term,
+    // which turns the modes into the force accumulators component by component
+    if (WITH_DT) dtk = det * ftb_rcp(512.0 * hex_face_amax(xm) * mp[MP_CE]);
+    // 8 mu M, M = cof^T cof / det
+    const double k8 = 8.0 * mu * rdet0;
+    const double M00 = k8 * (cJ[0][0] * cJ[0][0] + cJ[1][0] * cJ[1][0] + cJ[2][0] * cJ[2][0]);
+    const double M11 = k8 * (cJ[0][1] * cJ[0][1] + cJ[1][1] * cJ[1][1] + cJ[2][1] * cJ[2][1]);
+    const double M22 = k8 * (cJ[0][2] * cJ[0][2] + cJ[1][2] * cJ[1][2] + cJ[2][2] * cJ[2][2]);
+    const double M01 = k8 * (cJ[0][0] * cJ[0][1] + cJ[1][0] * cJ[1][1] + cJ[2][0] * cJ[2][1]);
+    const double M02 = k8 * (cJ[0][0] * cJ[0][2] + cJ[1][0] * cJ[1][2] + cJ[2][0] * cJ[2][2]);
+    const double M12 = k8 * (cJ[0][1] * cJ[0][2] + cJ[1][1] * cJ[1][2] + cJ[2][1] * cJ[2][2]);
+    const double aM3 = a * (M00 + M11), aM4 = a * (M11 + M22), aM5 = a * (M00 + M22), aM6 = a2 * (M00 + M11 + M22);
+    const double aM01 = a * M01, aM02 = a * M02, aM12 = a * M12;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // sum over the Gauss points of mu Ft M against the mode gradients, in closed form
+      phi[0][i] = xm[0][i] * M00 + xm[1][i] * M01 + xm[2][i] * M02;
+      phi[1][i] = xm[0][i] * M01 + xm[1][i] * M11 + xm[2][i] * M12;
+      phi[2][i] = xm[0][i] * M02 + xm[1][i] * M12 + xm[2][i] * M22;
+      phi[3][i] = xm[3][i] * aM3 + xm[4][i] * aM02 + xm[5][i] * aM12;
+      phi[4][i] = xm[4][i] * aM4 + xm[5][i] * aM01 + xm[3][i] * aM02;
+      phi[5][i] = xm[5][i] * aM5 + xm[4][i] * aM01 + xm[3][i] * aM12;
+      phi[6][i] = xm[6][i] * aM6;
+    }
+  }
+  double vsum = 0.0;
+  constexpr int kGpUnroll = FTB_NH_GP_UNROLL;
+#if defined(__CUDA_ARCH__)
+#pragma unroll kGpUnroll
+#endif
+  for (int gp = 0; gp < 8; ++gp) {
+    const int b1 = ((gp + 1) >> 1) & 1, b2 = (gp >> 1) & 1, b3 = ((gp >> 2) & 1) ^ 1;
+    const int qx = b2 + 2 * b3, qe = b1 + 2 * b3, qz = b1 + 2 * b2;
+    double Ft[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      // ld_inloop: a load the compiler cannot replace by the value stored above (it would keep all 36 in registers)
+      Ft[i][0] = S.ld_inloop(FTB_ACOL(0, qx, i));
+      Ft[i][1] = S.ld_inloop(FTB_ACOL(1, qe, i));
+      Ft[i][2] = S.ld_inloop(FTB_ACOL(2, qz, i));
+    }
+    double cF[3][3];
+    cofactor3(Ft, cF);
+    const double det = Ft[0][0] * cF[0][0] + Ft[0][1] * cF[0][1] + Ft[0][2] * cF[0][2];
+    if (!(det > 0.0)) status |= 4;
+    const double J = det * rdet0;
+    if (WITH_DT) vsum += J;
+    double lnJ, rJ;
+    ftb_ln_rcp_tiered(J, &lnJ, &rJ);
+    const double cc = (lambda * lnJ - mu) * rJ;
+    const double c1 = b1 ? cc : -cc, c2 = b2 ? cc : -cc, c3 = b3 ? cc : -cc;
+    const double c23 = (b2 == b3) ? cc : -cc, c13 = (b1 == b3) ? cc : -cc, c12 = (b1 == b2) ? cc : -cc;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      phi[0][i] = fma(cc, cF[i][0], phi[0][i]);
+      phi[1][i] = fma(cc, cF[i][1], phi[1][i]);
+      phi[2][i] = fma(cc, cF[i][2], phi[2][i]);
+      phi[3][i] = fma(c2, cF[i][0], fma(c1, cF[i][1], phi[3][i]));
+      phi[4][i] = fma(c3, cF[i][1], fma(c2, cF[i][2], phi[4][i]));
+      phi[5][i] = fma(c3, cF[i][0], fma(c1, cF[i][2], phi[5][i]));
+      phi[6][i] = fma(c23, cF[i][0], fma(c13, cF[i][1], fma(c12, cF[i][2], phi[6][i])));
+    }
+  }
+  if (WITH_DT) *dtElem = vsum * dtk;
+  const double w0 = 1.0 / 512.0, w1 = a / 512.0, w2 = a2 / 512.0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double p[7], f[8];
+    p[0] = phi[0][c] * w0; p[1] = phi[1][c] * w0; p[2] = phi[2][c] * w0;
+    p[3] = phi[3][c] * w1; p[4] = phi[4][c] * w1; p[5] = phi[5][c] * w1;
+    p[6] = phi[6][c] * w2;
+    hex_modes_to_nodes(p, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) fe[k][c] = f[k];
+  }
+  return status;
+}
+
+// ---------------------------------------------------------------------------------------------
 // The parallelepiped element once more, for the brick kernel (k_brick): the same arithmetic as hex8_element_affine_in,
 // cut into the two phases of that kernel's software pipeline and with the scratch split by access pattern:
 //   hex8_brick_setup  nodal gather -> displacement modes -> the 36 dU/dxi column entries (st_col: the kernel keeps them

@@ -104,6 +104,36 @@ extern "C" int harness_element_affine_staged(const double* X24, const double* U2
   return st;
 }
 
+// hex8_element_affine_nh (neo-Hookean parallelepiped, current-Jacobian form: what k_elem_affine_nh runs), direct and through
+// the staging-slot plan of the kernel (components 1, 2 of the input wait in slots the function later overwrites)
+extern "C" int harness_element_affine_nh(const double* X24, const double* U24, const double* mp, int staged, double* fe24, double* dtElem) {
+  double X[8][3], U[8][3], fe[8][3];
+  for (int k = 0; k < 8; ++k)
+    for (int c = 0; c < 3; ++c) { X[k][c] = X24[3 * k + c]; U[k][c] = U24[3 * k + c]; }
+  if (!ftb::hex8_is_affine(X)) return -1;
+  ftb::LocalScratchAffine sc;
+  for (int i = 0; i < FTB_AFFINE_SLOTS; ++i) sc.v[i] = 1e300;  // poison
+  int st;
+  if (staged) {
+    const int nx[4] = {0, 1, 3, 4};
+    double x0[4], u0[8];
+    for (int k = 0; k < 8; ++k) u0[k] = U24[3 * k];
+    for (int k = 0; k < 4; ++k) x0[k] = X24[3 * nx[k]];
+    for (int c = 1; c < 3; ++c) {
+      for (int k = 0; k < 8; ++k) sc.v[FTB_ASTAGE_U(k, c)] = U24[3 * k + c];
+      for (int k = 0; k < 4; ++k) sc.v[FTB_ASTAGE_X(k, c)] = X24[3 * nx[k] + c];
+    }
+    st = ftb::hex8_element_affine_nh<true>(HostStagedAffine{x0, u0, sc.v}, mp, sc, fe, dtElem);
+    for (int i = FTB_NH_SLOTS; i < FTB_AFFINE_SLOTS; ++i)
+      if (sc.v[i] != 1e300) return -2;  // the function must stay inside its 44 slots
+  } else {
+    st = ftb::hex8_element_affine_nh<true>(ftb::ArrayInAffine{X, U}, mp, sc, fe, dtElem);
+  }
+  for (int k = 0; k < 8; ++k)
+    for (int c = 0; c < 3; ++c) fe24[3 * k + c] = fe[k][c];
+  return st;
+}
+
 // hex8_brick_setup + hex8_brick_loop (the element function of k_brick, cut where the kernel's pipeline cuts it): the
 // reference nodes 0, 1, 3, 4 and the displacements come from node-indexed tables like the kernel's shared-memory staging
 namespace {
