@@ -51,7 +51,7 @@ struct ftb200_ctx {
   double* ring_dev = nullptr;
   long long ring_cap = 0;
   bool use_affine = true;  // FTB200_AFFINE=0: parallelepiped hexahedra go through the general kernel too
-  bool use_nh = true;      // FTB200_NH=0: neo-Hookean parallelepipeds through k_elem_affine<1, false> instead of k_elem_affine_nh
+  bool use_nh = true;      // FTB200_NH=0: neo-Hookean / HGO parallelepipeds through k_elem_affine<MAT, false> instead of k_elem_affine_cj<MAT>
   long long nE_affine = 0;
   // rigid-body prescribed motion (ftb200_set_rigid_bc)
   DevRigid* rigid = nullptr;
@@ -283,11 +283,12 @@ void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore
     switch (mat) {
       case 1:
         if (inj) LAUNCH((k_elem_affine<1, true>), grid, ELEM_BLOCK, s, A);
-        else if (ctx->use_nh) LAUNCH(k_elem_affine_nh, grid, ELEM_BLOCK, s, A);
+        else if (ctx->use_nh) LAUNCH(k_elem_affine_cj<1>, grid, ELEM_BLOCK, s, A);
         else LAUNCH((k_elem_affine<1, false>), grid, ELEM_BLOCK, s, A);
         return;
       case 4:
         if (inj) LAUNCH((k_elem_affine<4, true>), grid, ELEM_BLOCK, s, A);
+        else if (ctx->use_nh) LAUNCH(k_elem_affine_cj<4>, grid, ELEM_BLOCK, s, A);
         else LAUNCH((k_elem_affine<4, false>), grid, ELEM_BLOCK, s, A);
         return;
       case 5:

@@ -477,14 +477,16 @@ __global__ void __launch_bounds__(ELEM_BLOCK, MATSEL == 5 ? 4 : (WITH_INJ ? FTB_
   if (status) atomicOr(&A.sc->status, status);
 }
 
-// K_elem for runs of neo-Hookean parallelepipeds without the strain outputs (the headline configuration): the element
-// in current-Jacobian form (hex8_element_affine_nh: the linear part of the stress summed over the Gauss points in closed
-// form, 9 shared loads and ~95 fp64 instructions per point).  Same gather plan, same outputs and step semantics as
-// k_elem_affine<1, false>; 44 scratch slots per thread.  FTB200_NH=0 sends such runs through k_elem_affine again.
+// K_elem for runs of neo-Hookean (MAT 1, the headline configuration) or HGO (MAT 4) parallelepipeds without the strain
+// outputs: the element in current-Jacobian form (hex8_element_affine_cj; MAT 1: the linear part of the stress summed over
+// the Gauss points in closed form, 9 shared loads and ~95 fp64 instructions per point).  Same gather plan, same outputs
+// and step semantics as k_elem_affine<MAT, false>; 44 scratch slots per thread.  FTB200_NH=0 sends such runs through
+// k_elem_affine again.
 #ifndef FTB_NH_MINBLOCKS
 #define FTB_NH_MINBLOCKS 8
 #endif
-__global__ void __launch_bounds__(ELEM_BLOCK, FTB_NH_MINBLOCKS) k_elem_affine_nh(const ElemArgs A) {
+template <int MAT>
+__global__ void __launch_bounds__(ELEM_BLOCK, FTB_NH_MINBLOCKS) k_elem_affine_cj(const ElemArgs A) {
   const int e = A.e0 + blockIdx.x * ELEM_BLOCK + threadIdx.x;
   const size_t E = (size_t)A.nE;
   int nd[8];
@@ -519,7 +521,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, FTB_NH_MINBLOCKS) k_elem_affine_nh
     double fe[8][3];
     double d;
     SmemScratchAffine S{colbase};
-    status = hex8_element_affine_nh<true>(StagedInAffine{X0, U0, colbase}, mp, S, fe, &d);
+    status = hex8_element_affine_cj<MAT, true>(StagedInAffine{X0, U0, colbase}, mp, S, fe, &d);
     dte = skip ? 1e300 : d;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
@@ -748,7 +750,15 @@ __device__ __forceinline__ void prony_update(double* mp, int nPID, double dt, in
 template <bool FINISH, bool START, bool KICK2, bool ENERGY>
 __global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node(const NodeArgs A) {
   DevScalars* sc = A.sc;
-  const int n = blockIdx.x * NODE_BLOCK + threadIdx.x;
+  // Blocks walk the nodes from the END of the internal order (FTB_NODE_REVERSE): the element kernel before this launch
+  // wrote the force tiles in ascending element order, so the tiles of the last elements are the ones still in the
+  // 126 MB L2 when this kernel starts -- and the displacements this kernel writes last (the first nodes) are the ones
+  // the next element kernel gathers first.  Results are bit-identical: lb is only the block's place in the node order.
+#ifndef FTB_NODE_REVERSE
+#define FTB_NODE_REVERSE 1
+#endif
+  const int lb = FTB_NODE_REVERSE ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int n = lb * NODE_BLOCK + threadIdx.x;
   // Preamble: the node's own state (last written by the previous node kernel) and its entries of the static node ->
   // element map.  Nothing here is written by the element kernel or k_adv of the current step, so under a programmatic
   // dependent launch these loads are in flight while those two finish.
@@ -936,9 +946,9 @@ __global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node(const N
         s1 += sw[1][w];
         s2 += sw[2][w];
       }
-      A.epart[blockIdx.x] = s0;
-      A.epart[gridDim.x + blockIdx.x] = s1;
-      A.epart[2 * gridDim.x + blockIdx.x] = s2;
+      A.epart[lb] = s0;
+      A.epart[gridDim.x + lb] = s1;
+      A.epart[2 * gridDim.x + lb] = s2;
     }
   }
 }

@@ -1107,10 +1107,21 @@ FTB_HD void ftb_ln_rcp_tiered(const double J, double* lnJ, double* rJ) {
 }
 #define FTB_NH_SLOTS 44  // 36 column entries + the staging slots of the reference nodes (FTB_ASTAGE_X)
 #ifndef FTB_NH_GP_UNROLL
-#define FTB_NH_GP_UNROLL 8
+#define FTB_NH_GP_UNROLL 8  // measured at 100^3: rolled 121.0 us, by 2 116.6, by 4 113.6, by 8 112.5 (profiles/r02_k_elem_affine_nh_variants.txt)
 #endif
-template <bool WITH_DT, class In, class Scratch>
-FTB_HD int hex8_element_affine_nh(const In& in, const double* __restrict__ mp, Scratch& S, double fe[8][3], double* dtElem) {
+#ifndef FTB_CJ4_GP_UNROLL
+#define FTB_CJ4_GP_UNROLL 1
+#endif
+// MAT = 1: as above.  MAT = 4 (HGO with isotropic fibre dispersion, HGOIsotropic.cpp:44-84): the Cauchy stress is
+// sigma = pref dev(B) + hydro I with B = F F^T, and B cof F = F (F^T cof F) = J F, so
+//   P = sigma cof F = (pref J) F + (hydro - pref tr B / 3) cof F,    Q = alpha Ft M + gamma cof(Ft)
+// -- the neo-Hookean structure with coefficients that vary from point to point (alpha through J and I1), hence no
+// closed-form sum: G = Ft M is formed per point (M in 6 scratch slots) and also delivers tr B = (G : Ft) / det J0.
+// 63 multiply-adds per point for F, B, P and Q become 45, and the 18 loads of cof(J0), J0^-1 become 6.
+#define FTB_CJ_M(k) (36 + (k))  // M00 M11 M22 M12 M02 M01 (Voigt) in the staging slots of the reference nodes, free by then
+template <int MAT, bool WITH_DT, class In, class Scratch>
+FTB_HD int hex8_element_affine_cj(const In& in, const double* __restrict__ mp, Scratch& S, double fe[8][3], double* dtElem) {
+  static_assert(MAT == 1 || MAT == 4, "current-Jacobian form: neo-Hookean and HGO");
   const double a = FTB_GP_A, a2 = FTB_GP_A * FTB_GP_A;
   const double mu = mp[MP_MU], lambda = mp[MP_LAMBDA];
   int status = 0;
@@ -1149,29 +1160,38 @@ FTB_HD int hex8_element_affine_nh(const In& in, const double* __restrict__ mp, S
     // dt = (V / A_max) / c_e with V = det J0 sum_gp det F = sum_gp det Ft (see hex8_element_in); before the linear term,
     // which turns the modes into the force accumulators component by component
     if (WITH_DT) dtk = det * ftb_rcp(512.0 * hex_face_amax(xm) * mp[MP_CE]);
-    // 8 mu M, M = cof^T cof / det
-    const double k8 = 8.0 * mu * rdet0;
+    // MAT 1: 8 mu M;  MAT 4: M itself (M = cof^T cof / det)
+    const double k8 = (MAT == 1 ? 8.0 * mu : 1.0) * rdet0;
     const double M00 = k8 * (cJ[0][0] * cJ[0][0] + cJ[1][0] * cJ[1][0] + cJ[2][0] * cJ[2][0]);
     const double M11 = k8 * (cJ[0][1] * cJ[0][1] + cJ[1][1] * cJ[1][1] + cJ[2][1] * cJ[2][1]);
     const double M22 = k8 * (cJ[0][2] * cJ[0][2] + cJ[1][2] * cJ[1][2] + cJ[2][2] * cJ[2][2]);
     const double M01 = k8 * (cJ[0][0] * cJ[0][1] + cJ[1][0] * cJ[1][1] + cJ[2][0] * cJ[2][1]);
     const double M02 = k8 * (cJ[0][0] * cJ[0][2] + cJ[1][0] * cJ[1][2] + cJ[2][0] * cJ[2][2]);
     const double M12 = k8 * (cJ[0][1] * cJ[0][2] + cJ[1][1] * cJ[1][2] + cJ[2][1] * cJ[2][2]);
-    const double aM3 = a * (M00 + M11), aM4 = a * (M11 + M22), aM5 = a * (M00 + M22), aM6 = a2 * (M00 + M11 + M22);
-    const double aM01 = a * M01, aM02 = a * M02, aM12 = a * M12;
+    if (MAT == 1) {
+      const double aM3 = a * (M00 + M11), aM4 = a * (M11 + M22), aM5 = a * (M00 + M22), aM6 = a2 * (M00 + M11 + M22);
+      const double aM01 = a * M01, aM02 = a * M02, aM12 = a * M12;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {  // sum over the Gauss points of mu Ft M against the mode gradients, in closed form
-      phi[0][i] = xm[0][i] * M00 + xm[1][i] * M01 + xm[2][i] * M02;
-      phi[1][i] = xm[0][i] * M01 + xm[1][i] * M11 + xm[2][i] * M12;
-      phi[2][i] = xm[0][i] * M02 + xm[1][i] * M12 + xm[2][i] * M22;
-      phi[3][i] = xm[3][i] * aM3 + xm[4][i] * aM02 + xm[5][i] * aM12;
-      phi[4][i] = xm[4][i] * aM4 + xm[5][i] * aM01 + xm[3][i] * aM02;
-      phi[5][i] = xm[5][i] * aM5 + xm[4][i] * aM01 + xm[3][i] * aM12;
-      phi[6][i] = xm[6][i] * aM6;
+      for (int i = 0; i < 3; ++i) {  // sum over the Gauss points of mu Ft M against the mode gradients, in closed form
+        phi[0][i] = xm[0][i] * M00 + xm[1][i] * M01 + xm[2][i] * M02;
+        phi[1][i] = xm[0][i] * M01 + xm[1][i] * M11 + xm[2][i] * M12;
+        phi[2][i] = xm[0][i] * M02 + xm[1][i] * M12 + xm[2][i] * M22;
+        phi[3][i] = xm[3][i] * aM3 + xm[4][i] * aM02 + xm[5][i] * aM12;
+        phi[4][i] = xm[4][i] * aM4 + xm[5][i] * aM01 + xm[3][i] * aM02;
+        phi[5][i] = xm[5][i] * aM5 + xm[4][i] * aM01 + xm[3][i] * aM12;
+        phi[6][i] = xm[6][i] * aM6;
+      }
+    } else {
+      S.st(FTB_CJ_M(0), M00); S.st(FTB_CJ_M(1), M11); S.st(FTB_CJ_M(2), M22);
+      S.st(FTB_CJ_M(3), M12); S.st(FTB_CJ_M(4), M02); S.st(FTB_CJ_M(5), M01);
+#pragma unroll
+      for (int m = 0; m < 7; ++m)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) phi[m][i] = 0.0;
     }
   }
   double vsum = 0.0;
-  constexpr int kGpUnroll = FTB_NH_GP_UNROLL;
+  constexpr int kGpUnroll = MAT == 1 ? FTB_NH_GP_UNROLL : FTB_CJ4_GP_UNROLL;
 #if defined(__CUDA_ARCH__)
 #pragma unroll kGpUnroll
 #endif
@@ -1192,20 +1212,66 @@ FTB_HD int hex8_element_affine_nh(const In& in, const double* __restrict__ mp, S
     if (!(det > 0.0)) status |= 4;
     const double J = det * rdet0;
     if (WITH_DT) vsum += J;
-    double lnJ, rJ;
-    ftb_ln_rcp_tiered(J, &lnJ, &rJ);
-    const double cc = (lambda * lnJ - mu) * rJ;
-    const double c1 = b1 ? cc : -cc, c2 = b2 ? cc : -cc, c3 = b3 ? cc : -cc;
-    const double c23 = (b2 == b3) ? cc : -cc, c13 = (b1 == b3) ? cc : -cc, c12 = (b1 == b2) ? cc : -cc;
+    if (MAT == 1) {
+      double lnJ, rJ;
+      ftb_ln_rcp_tiered(J, &lnJ, &rJ);
+      const double cc = (lambda * lnJ - mu) * rJ;
+      const double c1 = b1 ? cc : -cc, c2 = b2 ? cc : -cc, c3 = b3 ? cc : -cc;
+      const double c23 = (b2 == b3) ? cc : -cc, c13 = (b1 == b3) ? cc : -cc, c12 = (b1 == b2) ? cc : -cc;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      phi[0][i] = fma(cc, cF[i][0], phi[0][i]);
-      phi[1][i] = fma(cc, cF[i][1], phi[1][i]);
-      phi[2][i] = fma(cc, cF[i][2], phi[2][i]);
-      phi[3][i] = fma(c2, cF[i][0], fma(c1, cF[i][1], phi[3][i]));
-      phi[4][i] = fma(c3, cF[i][1], fma(c2, cF[i][2], phi[4][i]));
-      phi[5][i] = fma(c3, cF[i][0], fma(c1, cF[i][2], phi[5][i]));
-      phi[6][i] = fma(c23, cF[i][0], fma(c13, cF[i][1], fma(c12, cF[i][2], phi[6][i])));
+      for (int i = 0; i < 3; ++i) {
+        phi[0][i] = fma(cc, cF[i][0], phi[0][i]);
+        phi[1][i] = fma(cc, cF[i][1], phi[1][i]);
+        phi[2][i] = fma(cc, cF[i][2], phi[2][i]);
+        phi[3][i] = fma(c2, cF[i][0], fma(c1, cF[i][1], phi[3][i]));
+        phi[4][i] = fma(c3, cF[i][1], fma(c2, cF[i][2], phi[4][i]));
+        phi[5][i] = fma(c3, cF[i][0], fma(c1, cF[i][2], phi[5][i]));
+        phi[6][i] = fma(c23, cF[i][0], fma(c13, cF[i][1], fma(c12, cF[i][2], phi[6][i])));
+      }
+    } else {
+      const double M00 = S.ld_inloop(FTB_CJ_M(0)), M11 = S.ld_inloop(FTB_CJ_M(1)), M22 = S.ld_inloop(FTB_CJ_M(2));
+      const double M12 = S.ld_inloop(FTB_CJ_M(3)), M02 = S.ld_inloop(FTB_CJ_M(4)), M01 = S.ld_inloop(FTB_CJ_M(5));
+      double G[3][3];
+      double trB = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        G[i][0] = Ft[i][0] * M00 + Ft[i][1] * M01 + Ft[i][2] * M02;
+        G[i][1] = Ft[i][0] * M01 + Ft[i][1] * M11 + Ft[i][2] * M12;
+        G[i][2] = Ft[i][0] * M02 + Ft[i][1] * M12 + Ft[i][2] * M22;
+        trB += G[i][0] * Ft[i][0] + G[i][1] * Ft[i][1] + G[i][2] * Ft[i][2];
+      }
+      trB *= rdet0;
+      // the scalars of hgo_cauchy (HGOIsotropic.cpp:44-84), same expressions
+      const double k1 = mp[MP_K1], k2 = mp[MP_K2], K = mp[MP_KBULK];
+      const double rJ = ftb_rcp(J);
+      const double hydro = 0.5 * K * (J * J - 1.0) * rJ;
+      const double rc = ftb_rcbrt(J);
+      const double Jm23 = rc * rc;
+      const double I1 = Jm23 * trB;
+      const double kappa = 1.0 / 3.0;
+      const double Ea = kappa * (I1 - 3.0);
+      double fiber = 0.0;
+      if (Ea > 0.0) {
+        const double ex = (k2 == 0.0) ? 1.0 : exp(k2 * Ea * Ea);
+        fiber = 2.0 * k1 * ex * Ea * kappa;
+      }
+      const double pref = Jm23 * (mu + fiber) * rJ;
+      const double alpha = pref * J, gamma = hydro - pref * (trB * (1.0 / 3.0));
+      const double s1 = b1 ? 1.0 : -1.0, s2 = b2 ? 1.0 : -1.0, s3 = b3 ? 1.0 : -1.0;
+      const double s23 = s2 * s3, s13 = s1 * s3, s12 = s1 * s2;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double Q0 = fma(alpha, G[i][0], gamma * cF[i][0]);
+        const double Q1 = fma(alpha, G[i][1], gamma * cF[i][1]);
+        const double Q2 = fma(alpha, G[i][2], gamma * cF[i][2]);
+        phi[0][i] += Q0;
+        phi[1][i] += Q1;
+        phi[2][i] += Q2;
+        phi[3][i] = fma(s2, Q0, fma(s1, Q1, phi[3][i]));
+        phi[4][i] = fma(s3, Q1, fma(s2, Q2, phi[4][i]));
+        phi[5][i] = fma(s3, Q0, fma(s1, Q2, phi[5][i]));
+        phi[6][i] = fma(s23, Q0, fma(s13, Q1, fma(s12, Q2, phi[6][i])));
+      }
     }
   }
   if (WITH_DT) *dtElem = vsum * dtk;
@@ -1221,6 +1287,11 @@ FTB_HD int hex8_element_affine_nh(const In& in, const double* __restrict__ mp, S
     for (int k = 0; k < 8; ++k) fe[k][c] = f[k];
   }
   return status;
+}
+
+template <bool WITH_DT, class In, class Scratch>
+FTB_HD int hex8_element_affine_nh(const In& in, const double* __restrict__ mp, Scratch& S, double fe[8][3], double* dtElem) {
+  return hex8_element_affine_cj<1, WITH_DT>(in, mp, S, fe, dtElem);
 }
 
 // ---------------------------------------------------------------------------------------------

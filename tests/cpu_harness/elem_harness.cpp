@@ -104,9 +104,10 @@ extern "C" int harness_element_affine_staged(const double* X24, const double* U2
   return st;
 }
 
-// hex8_element_affine_nh (neo-Hookean parallelepiped, current-Jacobian form: what k_elem_affine_nh runs), direct and through
+// hex8_element_affine_cj (neo-Hookean / HGO parallelepiped, current-Jacobian form: what k_elem_affine_cj runs), direct and through
 // the staging-slot plan of the kernel (components 1, 2 of the input wait in slots the function later overwrites)
-extern "C" int harness_element_affine_nh(const double* X24, const double* U24, const double* mp, int staged, double* fe24, double* dtElem) {
+template <int MAT>
+static int affine_cj(const double* X24, const double* U24, const double* mp, int staged, double* fe24, double* dtElem) {
   double X[8][3], U[8][3], fe[8][3];
   for (int k = 0; k < 8; ++k)
     for (int c = 0; c < 3; ++c) { X[k][c] = X24[3 * k + c]; U[k][c] = U24[3 * k + c]; }
@@ -123,15 +124,21 @@ extern "C" int harness_element_affine_nh(const double* X24, const double* U24, c
       for (int k = 0; k < 8; ++k) sc.v[FTB_ASTAGE_U(k, c)] = U24[3 * k + c];
       for (int k = 0; k < 4; ++k) sc.v[FTB_ASTAGE_X(k, c)] = X24[3 * nx[k] + c];
     }
-    st = ftb::hex8_element_affine_nh<true>(HostStagedAffine{x0, u0, sc.v}, mp, sc, fe, dtElem);
+    st = ftb::hex8_element_affine_cj<MAT, true>(HostStagedAffine{x0, u0, sc.v}, mp, sc, fe, dtElem);
     for (int i = FTB_NH_SLOTS; i < FTB_AFFINE_SLOTS; ++i)
       if (sc.v[i] != 1e300) return -2;  // the function must stay inside its 44 slots
   } else {
-    st = ftb::hex8_element_affine_nh<true>(ftb::ArrayInAffine{X, U}, mp, sc, fe, dtElem);
+    st = ftb::hex8_element_affine_cj<MAT, true>(ftb::ArrayInAffine{X, U}, mp, sc, fe, dtElem);
   }
   for (int k = 0; k < 8; ++k)
     for (int c = 0; c < 3; ++c) fe24[3 * k + c] = fe[k][c];
   return st;
+}
+
+extern "C" int harness_element_affine_cj(const double* X24, const double* U24, int mat, const double* mp, int staged, double* fe24, double* dtElem) {
+  if (mat == 1) return affine_cj<1>(X24, U24, mp, staged, fe24, dtElem);
+  if (mat == 4) return affine_cj<4>(X24, U24, mp, staged, fe24, dtElem);
+  return -3;
 }
 
 // hex8_brick_setup + hex8_brick_loop (the element function of k_brick, cut where the kernel's pipeline cuts it): the

@@ -135,10 +135,12 @@ def test_affine_kernel_agrees_with_general_kernel(mat, injury):
         assert np.allclose(ia["scalars"][[0, 2, 4]], ig["scalars"][[0, 2, 4]], rtol=1e-9, atol=1e-14)  # max/min strain, max shear
 
 
-def test_current_jacobian_kernel_agrees_with_displacement_gradient_kernel():
-    """k_elem_affine_nh (neo-Hookean parallelepipeds in current-Jacobian form, the default) against k_elem_affine<1>
-    (FTB200_NH=0) on the same structured mesh: the two differ by rounding only -- state and stresses after 200 steps to
-    1e-11, the recorded dt history to 1e-12 -- and the new kernel alone matches the oracle at 1e-9 in the tests above."""
+@pytest.mark.parametrize("mat", [1, 4])
+def test_current_jacobian_kernel_agrees_with_displacement_gradient_kernel(mat):
+    """k_elem_affine_cj<MAT> (neo-Hookean / HGO parallelepipeds in current-Jacobian form, the default) against
+    k_elem_affine<MAT> (FTB200_NH=0) on the same structured mesh: the two differ by rounding only -- state and stresses
+    after 200 steps to 1e-11, the recorded dt history to 1e-12 -- and the new kernel alone matches the oracle at 1e-9 in
+    the tests above."""
     X, conn, pid = mesh.cube_mesh(8)
     kind, rate = mesh.benchmark_bc(X, dMax=0.02, tMax=0.004)
     nsteps = 200
@@ -146,7 +148,7 @@ def test_current_jacobian_kernel_agrees_with_displacement_gradient_kernel():
     for flag in ("1", "0"):
         os.environ["FTB200_NH"] = flag
         try:
-            m = run_gpu(X, conn, pid, [1], PROPS[1], kind, rate, nsteps)
+            m = run_gpu(X, conn, pid, [mat], PROPS[mat], kind, rate, nsteps)
         finally:
             del os.environ["FTB200_NH"]
         assert m.affine_elements == conn.shape[0]
