@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "ftb200_kernels.cuh"
@@ -107,6 +108,8 @@ struct ftb200_ctx {
   P2PArgs p2p;
   bool p2p_ready = false;
   unsigned long long* d_seq = nullptr;
+  unsigned long long* trace = nullptr;  // FTB200_P2P_TRACE: [TRACE_STEPS][TRACE_SLOTS] time stamps of the partitioned step
+  std::string trace_prefix;
   unsigned* d_p2p_blocks = nullptr;
   std::vector<void*> p2p_opened;
   cudaGraphExec_t p2p_graph = nullptr;
@@ -652,6 +655,24 @@ int ftb200_destroy(ftb200_ctx* ctx) {
   if (!ctx) return FTB200_OK;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  if (ctx->trace) {  // diagnostic dump of the partitioned step's time stamps
+    std::vector<unsigned long long> h((size_t)TRACE_STEPS * TRACE_SLOTS);
+    cudaMemcpy(h.data(), ctx->trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    char path[512];
+    snprintf(path, sizeof path, "%s_rank%d.txt", ctx->trace_prefix.c_str(), ctx->rank);
+    if (FILE* f = fopen(path, "w")) {
+      for (int st = 0; st < TRACE_STEPS; ++st) {
+        const unsigned long long* r = &h[(size_t)st * TRACE_SLOTS];
+        if (!r[0]) continue;
+        fprintf(f, "%d", st);
+        for (int k = 0; k < TRACE_SLOTS; ++k) fprintf(f, " %llu", r[k]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+    dfree(ctx->trace);
+    ctx->trace = nullptr;
+  }
   free_all(ctx);
   for (auto e : ctx->prof.pool) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1536,18 +1557,23 @@ static void launch_step_p2p(ftb200_ctx* ctx) {
   cudaStream_t s = ctx->stream, s2 = ctx->stream_lo;
   const int nEb = ctx->nE_boundary;
   // elements touching shared nodes first, on the high-priority main stream; the interior fills the machine behind them
+  unsigned long long* tr = ctx->trace;
+  if (tr) LAUNCH(k_stamp, 1, 1, s, tr, ctx->sc, 0, 0);
   cudaEventRecord(ctx->ev_fork, s);
   launch_elem<true, true>(ctx, s, 0, nEb, 0);
+  if (tr) LAUNCH(k_stamp, 1, 1, s, tr, ctx->sc, 1, 0);
   cudaStreamWaitEvent(s2, ctx->ev_fork, 0);
   launch_elem<true, true>(ctx, s2, nEb, ctx->nE, 0);
+  if (tr) LAUNCH(k_stamp, 1, 1, s2, tr, ctx->sc, 7, 0);
   cudaEventRecord(ctx->ev_join, s2);
   if (ctx->halo_count)
     LAUNCH(k_p2p_pack, cdiv(ctx->halo_count, 128), 128, s, ctx->p2p, ctx->felem, ctx->node_off, ctx->node_ent,
            ctx->d_sendNodeIndex, ctx->sc, ctx->nE);
+  if (tr) LAUNCH(k_stamp, 1, 1, s, tr, ctx->sc, 2, 0);
   cudaStreamWaitEvent(s, ctx->ev_join, 0);
   // k_adv_p2p moves sc->step / sc->active, which the energy reduction of the previous step (helper stream) still reads
   if (ctx->energy_pending) { cudaStreamWaitEvent(s, ctx->ev_energy_done, 0); ctx->energy_pending = false; }
-  LAUNCH(k_adv_p2p, 1, 128, s, ctx->p2p, ctx->sc, ctx->mp, ctx->nPID, ctx->dthist);
+  LAUNCH(k_adv_p2p, 1, 128, s, ctx->p2p, ctx->sc, ctx->mp, ctx->nPID, ctx->dthist, tr);
   if (ctx->rigid) LAUNCH(k_rigid_step, 1, 32, s, ctx->sc, ctx->rigid, 0);
   NodeArgs N = node_args(ctx, ctx->halo_count ? p2p_recv(ctx->p2p_window, ctx->halo_count, 0, ctx->nranks) : nullptr);
   if (ctx->halo_count) {
@@ -1556,6 +1582,7 @@ static void launch_step_p2p(ftb200_ctx* ctx) {
   }
   if (ctx->energy) LAUNCH((k_node<true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
   else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+  if (tr) LAUNCH(k_stamp, 1, 1, s, tr, ctx->sc, 6, -1);  // k_adv_p2p has advanced sc->step
   if (ctx->injury) {
     // CalculateInjuryCriterions across partitions inside the loop: running extrema per rank, then the six radix passes of
     // the two GLOBAL 95th-percentile selections, each with its histogram summed over the ranks through the windows
@@ -1589,6 +1616,13 @@ static void launch_step_p2p(ftb200_ctx* ctx) {
 static void join_energy(ftb200_ctx* ctx);
 static int run_async_p2p(ftb200_ctx* ctx, double tMax, long long steps) {
   cudaStream_t s = ctx->stream;
+  if (!ctx->trace)
+    if (const char* ev = getenv("FTB200_P2P_TRACE")) {
+      if (*ev && dalloc(ctx, &ctx->trace, (size_t)TRACE_STEPS * TRACE_SLOTS) == 0) {
+        ftb_memset(ctx, ctx->trace, 0, sizeof(unsigned long long) * TRACE_STEPS * TRACE_SLOTS);
+        ctx->trace_prefix = ev;
+      }
+    }
   LAUNCH(k_begin_run, 1, 1, s, ctx->sc, tMax, steps);
   {
     const NodeArgs N = node_args(ctx, nullptr);

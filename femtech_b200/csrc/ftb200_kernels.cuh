@@ -108,6 +108,29 @@ struct DevHist {
 #ifndef FTB_ELEM_BLOCK
 #define FTB_ELEM_BLOCK 64
 #endif
+// Cache policy of the streams (FTB_STREAM_HINTS): everything the node kernel touches once per step (its own state, the
+// node map) and the connectivity of the element kernel is loaded / stored with the evict-first policy (ld.global.cs /
+// st.global.cs), so that the lines that ARE reused across the kernel boundary -- the force tiles the element kernel
+// wrote last and the node kernel (walking backwards) reads first -- survive longer in the 126 MB L2.
+#ifndef FTB_STREAM_HINTS
+#define FTB_STREAM_HINTS 1
+#endif
+template <class T>
+__device__ __forceinline__ T ld_stream(const T* p) {
+#if FTB_STREAM_HINTS
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
+template <class T>
+__device__ __forceinline__ void st_stream(T* p, const T v) {
+#if FTB_STREAM_HINTS
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
@@ -485,8 +508,15 @@ __global__ void __launch_bounds__(ELEM_BLOCK, MATSEL == 5 ? 4 : (WITH_INJ ? FTB_
 #ifndef FTB_NH_MINBLOCKS
 #define FTB_NH_MINBLOCKS 8
 #endif
+#ifndef FTB_ELEM_PREFETCH
+#define FTB_ELEM_PREFETCH (148 * FTB_NH_MINBLOCKS * ELEM_BLOCK)  // elements ahead (0 = off): one resident wave
+#endif
 template <int MAT>
+#ifdef FTB_NH_MAXNREG
+__global__ void __maxnreg__(FTB_NH_MAXNREG) k_elem_affine_cj(const ElemArgs A) {
+#else
 __global__ void __launch_bounds__(ELEM_BLOCK, FTB_NH_MINBLOCKS) k_elem_affine_cj(const ElemArgs A) {
+#endif
   const int e = A.e0 + blockIdx.x * ELEM_BLOCK + threadIdx.x;
   const size_t E = (size_t)A.nE;
   int nd[8];
@@ -494,9 +524,24 @@ __global__ void __launch_bounds__(ELEM_BLOCK, FTB_NH_MINBLOCKS) k_elem_affine_cj
   unsigned skip = 0;
   if (e < A.e1) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) nd[k] = __ldg(A.conn + (size_t)k * E + e);
-    p = __ldg(A.pid + e);
-    skip = __ldg(A.eflag + e);
+    for (int k = 0; k < 8; ++k) nd[k] = ld_stream(A.conn + (size_t)k * E + e);
+    p = ld_stream(A.pid + e);
+    // the flag is only needed at the very end; as an ordinary load the compiler sinks it there and the warp then waits a
+    // full DRAM latency per element (6 % of the stall samples, profiles/r02_k_elem_affine_cj_line_profile.txt)
+    asm volatile("ld.global.cs.u8 %0, [%1];" : "=r"(skip) : "l"(A.eflag + e));
+#if FTB_ELEM_PREFETCH
+    // connectivity of the elements one resident wave ahead, into L2: lanes 0-7 / 8-15 fetch the line of plane k that holds
+    // the first / last element of this warp's successor, lanes 16-18 its pid and eflag lines
+    {
+      const int lane = threadIdx.x & 31;
+      const size_t ef = (size_t)(e - lane) + FTB_ELEM_PREFETCH + ((lane & 8) ? 31 : 0);
+      if (ef < (size_t)A.e1) {
+        if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.conn + (size_t)(lane & 7) * E + ef));
+        else if (lane < 18) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.pid + ef + (lane & 1) * 31));
+        else if (lane == 18) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.eflag + ef));
+      }
+    }
+#endif
   }
   if (!A.ignore_loop_flags && (A.sc->last | A.sc->done)) return;
   __shared__ double sm_cols[FTB_NH_SLOTS][ELEM_BLOCK];
@@ -766,16 +811,16 @@ __global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node(const N
   double uu[3] = {0.0, 0.0, 0.0}, vv[3] = {0.0, 0.0, 0.0}, aa[3] = {0.0, 0.0, 0.0};
   int ent[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
   if (n < A.nN) {
-    fl = A.flags[n];
+    fl = ld_stream(A.flags + n);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      uu[c] = A.u[c][n];
-      vv[c] = A.v[c][n];
-      aa[c] = A.a[c][n];
+      uu[c] = ld_stream(A.u[c] + n);
+      vv[c] = ld_stream(A.v[c] + n);
+      aa[c] = ld_stream(A.a[c] + n);
     }
     if (FINISH && A.ell) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) ent[q] = __ldg(A.ell + (size_t)q * A.nN + n);
+      for (int q = 0; q < 8; ++q) ent[q] = ld_stream(A.ell + (size_t)q * A.nN + n);
     }
   }
   if (FINISH && !sc->active) return;
@@ -839,7 +884,7 @@ __global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node(const N
           }
         }
       }
-      const double m = A.m[n];
+      const double m = ld_stream(A.m + n);
       const double dt1 = sc->t_half - sc->t_n, dt2 = sc->t_np1 - sc->t_half;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -866,14 +911,14 @@ __global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node(const N
             else if (kind) dd = sc->t_np1 * sc->bc_rate[kind] - sc->t_n * sc->bc_rate[kind];
           }
           if (ENERGY && !(fl & FTB_FLAG_NOTOWNED)) {   // CheckEnergy.cpp:19-52
-            const double fprev = A.fi[c][n];
+            const double fprev = ld_stream(A.fi[c] + n);
             wke += m * vv[c] * vv[c];
             if (b) wext += dd * (fprev + f[c] + m * (aa[c] + a_old));
             wint += dd * (fprev + f[c]);
             wext += dd * (fext + fext);  // fe_prev == fe: the reference never updates fe
           }
         }
-        if (A.store_fi) A.fi[c][n] = f[c];
+        if (A.store_fi) st_stream(A.fi[c] + n, f[c]);
       }
     }
     if (do_start) {
@@ -918,9 +963,9 @@ __global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node(const N
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      if (do_start) A.u[c][n] = uu[c];
-      A.v[c][n] = vv[c];
-      A.a[c][n] = aa[c];
+      if (do_start) A.u[c][n] = uu[c];  // default policy: the next element kernel gathers it
+      st_stream(A.v[c] + n, vv[c]);
+      st_stream(A.a[c] + n, aa[c]);
     }
   }
   if (FINISH && KICK2 && ENERGY) {
@@ -1558,10 +1603,23 @@ __global__ void k_p2p_pack(const P2PArgs P, const double* felem, const int* node
   }
 }
 
+// Diagnostic trace of the partitioned step (FTB200_P2P_TRACE=<file prefix>; off by default, no kernel of the default path
+// changes): TRACE_SLOTS time stamps (%globaltimer, ns) per step, written by one-thread marker kernels between the
+// launches of the step and by k_adv_p2p around its publish / wait phases; dumped per rank when the context is destroyed.
+//   0 step start | 1 boundary elements done | 2 partial sums packed and flagged | 3 k_adv_p2p starts (interior joined)
+//   4 dt published to every rank | 5 every rank's dt and every neighbour's flag seen | 6 node kernel done | 7 interior done
+constexpr int TRACE_SLOTS = 8, TRACE_STEPS = 2048;
+__global__ void k_stamp(unsigned long long* tr, const DevScalars* sc, int slot, int step_offset) {
+  const long long st = (long long)sc->step + step_offset;
+  if (st >= 0 && st < TRACE_STEPS) tr[st * TRACE_SLOTS + slot] = now_ns();
+}
+
 // dt exchange + waits + the scalar update of k_adv<false>
-__global__ void k_adv_p2p(const P2PArgs P, DevScalars* sc, double* mp, int nPID, double* dt_hist) {
+__global__ void k_adv_p2p(const P2PArgs P, DevScalars* sc, double* mp, int nPID, double* dt_hist, unsigned long long* trace) {
   __shared__ double s_ndt;
   __shared__ int s_live, s_ok;
+  unsigned long long* tr = nullptr;
+  if (trace && threadIdx.x == 0 && sc->step < TRACE_STEPS) { tr = trace + (size_t)sc->step * TRACE_SLOTS; tr[3] = now_ns(); }
   if (threadIdx.x == 0) {
     int live = 1;
     if (sc->done) live = 0;
@@ -1583,6 +1641,7 @@ __global__ void k_adv_p2p(const P2PArgs P, DevScalars* sc, double* mp, int nPID,
     __threadfence_system();
     *(volatile unsigned long long*)&w->dflag[P.rank] = seq + 1;
   }
+  if (tr) tr[4] = now_ns();
   // wait for every rank's dt and every neighbour's partials of this step
   const unsigned long long t0 = now_ns();
   for (int r = threadIdx.x; r < P.n_ranks + P.n_nb; r += blockDim.x) {
@@ -1594,6 +1653,7 @@ __global__ void k_adv_p2p(const P2PArgs P, DevScalars* sc, double* mp, int nPID,
   }
   __threadfence_system();
   __syncthreads();
+  if (tr) tr[5] = now_ns();
   if (threadIdx.x == 0) {
     if (!s_ok) { sc->status |= 64; sc->last = 1; }  // a peer never arrived: stop instead of hanging
     double dtmin = 1e300;

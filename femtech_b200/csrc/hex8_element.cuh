@@ -56,7 +56,7 @@ FTB_HD double ftb_rcbrt(const double x) {
 // handling.  One Gauss point of k_elem_affine spends 172 fp64 and ~125 other instructions, and the kernel is bound by the
 // issue port: `log(J)` and `1.0 / J` alone were ~35 fp64 and ~45 other instructions of those
 // (exponent extraction, polynomial coefficients moved through uniform registers, slow-path tests and calls).  Here:
-//   1/x    MUFU.RCP64H seed + two Newton steps (x is a positive normal number: J > 0 is checked by the caller);
+//   1/x    MUFU.RCP64H seed + one cubic correction step (x is a positive normal number: J > 0 is checked by the caller);
 //   ln J   = 2 atanh(s), s = (J - 1)/(J + 1), as 2 s (1 + z (1/3 + z (1/5 + ... + z/27))), z = s^2, for |s| <= 1/4
 //          (0.6 <= J <= 1.667; truncation < 1e-17 relative), coefficients as constant-bank operands of the DFMAs;
 //          outside that range the library functions.
@@ -69,9 +69,10 @@ FTB_HD double ftb_rcp(const double x) {
 #if defined(__CUDA_ARCH__) && !defined(FTB_LIBM_MATERIAL)
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  r = fma(r, fma(-x, r, 1.0), r);
-  r = fma(r, fma(-x, r, 1.0), r);
-  return r;
+  // one cubic step instead of two Newton steps: 1/x = r (1 + e + e^2 + ...), e = 1 - x r; the seed is good to ~2^-20
+  // (MUFU.RCP64H reads the upper word of x), so dropping e^3 leaves 2^-60 relative
+  const double e = fma(-x, r, 1.0);
+  return fma(r, fma(e, e, e), r);
 #else
   return 1.0 / x;
 #endif

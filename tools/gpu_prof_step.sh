@@ -4,7 +4,7 @@
 TAG=${1:-r02}
 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 48 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 6 --warmup 3 --no-cpu > gpurun_out/${TAG}_launches_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k "regex:^k_elem_affine$" -s 4 -c 1 -f -o gpurun_out/${TAG}_k_elem_affine \
+ncu --set full --clock-control none --import-source on -k "regex:^k_elem_affine_cj$" -s 4 -c 1 -f -o gpurun_out/${TAG}_k_elem_affine \
     python bench.py --steps 6 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_elem.log 2>&1
 ncu --set full --clock-control none --import-source on -k "regex:^k_node$" -s 5 -c 1 -f -o gpurun_out/${TAG}_k_node \
     python bench.py --steps 6 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_node.log 2>&1
