@@ -108,6 +108,16 @@ struct ftb200_ctx {
   P2PArgs p2p;
   bool p2p_ready = false;
   unsigned long long* d_seq = nullptr;
+  // exchange fused into the element kernels (PackArgs): device copy of the arguments, counters, and the switch that
+  // elem_args consults while launch_step_p2p launches the step's element kernels
+  PackArgs* d_pk = nullptr;
+  unsigned* d_pk_ctr = nullptr;
+  bool p2p_fused = false, pk_on = false;
+  // launch attributes of the partitioned step (launch_k): 0 none, 1 priority la_prio, 2 programmatic event la_event
+  int la_kind = 0, la_prio = 0, la_err = 0;
+  cudaEvent_t la_event = nullptr, ev_prog = nullptr;
+  int prio_hi = 0, prio_lo = 0;
+  int p2p_order = 0;  // FTB200_P2P_ORDER: how the boundary elements get ahead of the interior (launch_step_p2p)
   unsigned long long* trace = nullptr;  // FTB200_P2P_TRACE: [TRACE_STEPS][TRACE_SLOTS] time stamps of the partitioned step
   std::string trace_prefix;
   unsigned* d_p2p_blocks = nullptr;
@@ -160,7 +170,27 @@ int fail(ftb200_ctx* c, int code, const char* fmt, ...) {
 // Every kernel goes through launch_k (it counts the launches: `gpu_launches` of the bench line).
 template <class... P, class... A>
 inline void launch_k(ftb200_ctx* ctx, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t strm, A&&... args) {
-  kern<<<grid, block, smem, strm>>>(static_cast<P>(args)...);
+  if (ctx->la_kind) {
+    // launch attributes of the partitioned step (launch_step_p2p): an explicit priority, or a programmatic event that
+    // fires when every block of this grid has STARTED (the interior elements wait for it on their own stream)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = strm;
+    cudaLaunchAttribute at[1];
+    if (ctx->la_kind == 1) {
+      at[0].id = cudaLaunchAttributePriority;
+      at[0].val.priority = ctx->la_prio;
+    } else {
+      at[0].id = cudaLaunchAttributeProgrammaticEvent;
+      at[0].val.programmaticEvent.event = ctx->la_event;
+      at[0].val.programmaticEvent.flags = 0;
+      at[0].val.programmaticEvent.triggerAtBlockStart = 1;
+    }
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+    if (e != cudaSuccess && !ctx->la_err) ctx->la_err = (int)e;
+  } else {
+    kern<<<grid, block, smem, strm>>>(static_cast<P>(args)...);
+  }
   ctx->launches++;
 }
 #define LAUNCH(kern, grid, block, strm, ...)                                              \
@@ -220,6 +250,8 @@ int ensure_big(ftb200_ctx* ctx, size_t bytes) {
 
 ElemArgs elem_args(ftb200_ctx* c, int e0, int e1, int ignore) {
   ElemArgs A;
+  A.pk = c->pk_on ? c->d_pk : nullptr;
+  A.pk_nEb = c->pk_on ? c->nE_boundary : 0;
   for (int k = 0; k < 3; ++k) { A.X[k] = c->X[k]; A.u[k] = c->u[k]; }
   A.conn = c->conn; A.pid = c->pid; A.eflag = c->eflag; A.mp = c->mp; A.felem = c->felem; A.hist = c->hist;
   A.sc = c->sc; A.nE = c->nE; A.e0 = e0; A.e1 = e1; A.ignore_loop_flags = ignore;
@@ -286,11 +318,13 @@ void launch_elem_hex(ftb200_ctx* ctx, cudaStream_t s, int e0, int e1, int ignore
     switch (mat) {
       case 1:
         if (inj) LAUNCH((k_elem_affine<1, true>), grid, ELEM_BLOCK, s, A);
+        else if (ctx->use_nh && A.pk) LAUNCH((k_elem_affine_cj<1, true>), grid, ELEM_BLOCK, s, A);
         else if (ctx->use_nh) LAUNCH(k_elem_affine_cj<1>, grid, ELEM_BLOCK, s, A);
         else LAUNCH((k_elem_affine<1, false>), grid, ELEM_BLOCK, s, A);
         return;
       case 4:
         if (inj) LAUNCH((k_elem_affine<4, true>), grid, ELEM_BLOCK, s, A);
+        else if (ctx->use_nh && A.pk) LAUNCH((k_elem_affine_cj<4, true>), grid, ELEM_BLOCK, s, A);
         else if (ctx->use_nh) LAUNCH(k_elem_affine_cj<4>, grid, ELEM_BLOCK, s, A);
         else LAUNCH((k_elem_affine<4, false>), grid, ELEM_BLOCK, s, A);
         return;
@@ -611,6 +645,7 @@ void free_all(ftb200_ctx* c) {
   c->brick_ok = false;
   if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
   dfree(c->d_xsend); dfree(c->d_xrecv);
+  dfree(c->d_pk); dfree(c->d_pk_ctr);
   dfree(c->d_sendNodeIndex); dfree(c->halo_nodes); dfree(c->halo_off); dfree(c->halo_slot); dfree(c->halo_node_idx);
   if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
 }
@@ -643,10 +678,13 @@ int ftb200_create(int rank, int nranks, int device, ftb200_ctx** out) {
       cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_nodes_done, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_energy_done, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&ctx->ev_energy_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_prog, cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return FTB200_ERR_CUDA;
   }
+  ctx->prio_hi = prio_hi; ctx->prio_lo = prio_lo;
+  if (const char* ev = getenv("FTB200_P2P_ORDER")) ctx->p2p_order = atoi(ev);
   *out = ctx;
   return FTB200_OK;
 }
@@ -682,6 +720,7 @@ int ftb200_destroy(ftb200_ctx* ctx) {
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->ev_nodes_done) cudaEventDestroy(ctx->ev_nodes_done);
   if (ctx->ev_energy_done) cudaEventDestroy(ctx->ev_energy_done);
+  if (ctx->ev_prog) cudaEventDestroy(ctx->ev_prog);
   if (ctx->ring_host) cudaFreeHost(ctx->ring_host);
   delete ctx;
   return FTB200_OK;
@@ -1559,21 +1598,52 @@ static void launch_step_p2p(ftb200_ctx* ctx) {
   // elements touching shared nodes first, on the high-priority main stream; the interior fills the machine behind them
   unsigned long long* tr = ctx->trace;
   if (tr) LAUNCH(k_stamp, 1, 1, s, tr, ctx->sc, 0, 0);
+  // The boundary elements must reach the SMs BEFORE the interior ones (their partial sums then cross NVLink while the
+  // interior is integrated).  Stream priorities alone do not achieve that inside the captured graph: the trace
+  // (profiles/r02_p2p_trace_2gpu_before.txt) shows the boundary grid finishing 103 us into the step, behind the
+  // interior's blocks.  p2p_order: 0 stream priorities only (round 1), 1 explicit priority attribute on every launch,
+  // 2 the interior waits for a programmatic event that fires once every boundary block has started, 3 the interior
+  // waits for the boundary grid to finish.
+  const int order = nEb > 0 ? ctx->p2p_order : 0;
+  // Fused exchange on a mesh that one hexahedron kernel covers (one material, one geometry class): ONE launch over all
+  // elements.  Blocks are handed out in element order, so the boundary elements -- first in the internal order -- run
+  // first and their epilogue sends under the interior blocks of the same grid; no second stream, no fork / join.
+  bool one_launch = false;
+  if (ctx->p2p_fused && !ctx->ranges.empty() && ctx->ranges.size() <= 2 && ctx->ranges.front().e0 == 0 && ctx->ranges.back().e1 == ctx->nE) {
+    const auto &r0 = ctx->ranges.front(), &r1 = ctx->ranges.back();
+    one_launch = !r0.tet && !r1.tet && r0.mat == r1.mat && r0.affine == r1.affine;
+  }
+  if (one_launch) {
+    ctx->pk_on = true;
+    launch_elem_hex<true, true>(ctx, s, 0, ctx->nE, 0, ctx->ranges.front().mat, ctx->ranges.front().affine);
+    ctx->pk_on = false;
+    if (tr) { LAUNCH(k_stamp, 1, 1, s, tr, ctx->sc, 1, 0); LAUNCH(k_stamp, 1, 1, s, tr, ctx->sc, 2, 0); LAUNCH(k_stamp, 1, 1, s, tr, ctx->sc, 7, 0); }
+  } else {
   cudaEventRecord(ctx->ev_fork, s);
+  if (order == 1) { ctx->la_kind = 1; ctx->la_prio = ctx->prio_hi; }
+  if (order == 2) { ctx->la_kind = 2; ctx->la_event = ctx->ev_prog; }
+  ctx->pk_on = ctx->p2p_fused;  // only this launch carries the exchange epilogue
   launch_elem<true, true>(ctx, s, 0, nEb, 0);
+  ctx->pk_on = false;
+  ctx->la_kind = 0;
   if (tr) LAUNCH(k_stamp, 1, 1, s, tr, ctx->sc, 1, 0);
-  cudaStreamWaitEvent(s2, ctx->ev_fork, 0);
+  if (order == 3) cudaEventRecord(ctx->ev_prog, s);
+  cudaStreamWaitEvent(s2, (order == 2 || order == 3) ? ctx->ev_prog : ctx->ev_fork, 0);
+  if (order == 1) { ctx->la_kind = 1; ctx->la_prio = ctx->prio_lo; }
   launch_elem<true, true>(ctx, s2, nEb, ctx->nE, 0);
+  ctx->la_kind = 0;
   if (tr) LAUNCH(k_stamp, 1, 1, s2, tr, ctx->sc, 7, 0);
   cudaEventRecord(ctx->ev_join, s2);
-  if (ctx->halo_count)
+  if (order == 1) { ctx->la_kind = 1; ctx->la_prio = ctx->prio_hi; }
+  if (ctx->halo_count && !ctx->p2p_fused)
     LAUNCH(k_p2p_pack, cdiv(ctx->halo_count, 128), 128, s, ctx->p2p, ctx->felem, ctx->node_off, ctx->node_ent,
            ctx->d_sendNodeIndex, ctx->sc, ctx->nE);
   if (tr) LAUNCH(k_stamp, 1, 1, s, tr, ctx->sc, 2, 0);
   cudaStreamWaitEvent(s, ctx->ev_join, 0);
+  }
   // k_adv_p2p moves sc->step / sc->active, which the energy reduction of the previous step (helper stream) still reads
   if (ctx->energy_pending) { cudaStreamWaitEvent(s, ctx->ev_energy_done, 0); ctx->energy_pending = false; }
-  LAUNCH(k_adv_p2p, 1, 128, s, ctx->p2p, ctx->sc, ctx->mp, ctx->nPID, ctx->dthist, tr);
+  LAUNCH(k_adv_p2p, 1, 128, s, ctx->p2p, ctx->sc, ctx->mp, ctx->nPID, ctx->dthist, tr, 0);
   if (ctx->rigid) LAUNCH(k_rigid_step, 1, 32, s, ctx->sc, ctx->rigid, 0);
   NodeArgs N = node_args(ctx, ctx->halo_count ? p2p_recv(ctx->p2p_window, ctx->halo_count, 0, ctx->nranks) : nullptr);
   if (ctx->halo_count) {
@@ -1582,6 +1652,7 @@ static void launch_step_p2p(ftb200_ctx* ctx) {
   }
   if (ctx->energy) LAUNCH((k_node<true, true, true, true>), ctx->node_blocks, NODE_BLOCK, s, N);
   else LAUNCH((k_node<true, true, true, false>), ctx->node_blocks, NODE_BLOCK, s, N);
+  ctx->la_kind = 0;
   if (tr) LAUNCH(k_stamp, 1, 1, s, tr, ctx->sc, 6, -1);  // k_adv_p2p has advanced sc->step
   if (ctx->injury) {
     // CalculateInjuryCriterions across partitions inside the loop: running extrema per rank, then the six radix passes of
@@ -1643,6 +1714,8 @@ static int run_async_p2p(ftb200_ctx* ctx, double tMax, long long steps) {
     const long long per_graph = ctx->launches - before;
     ctx->launches = before;
     if (e != cudaSuccess) return fail(ctx, FTB200_ERR_CUDA, "p2p graph capture failed: %s", cudaGetErrorString(e));
+    if (ctx->la_err) return fail(ctx, FTB200_ERR_CUDA, "p2p graph capture: a launch with attributes failed: %s (FTB200_P2P_ORDER=%d)",
+                                 cudaGetErrorString((cudaError_t)ctx->la_err), ctx->p2p_order);
     e = cudaGraphInstantiate(&ctx->p2p_graph, g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) { ctx->p2p_graph = nullptr; return fail(ctx, FTB200_ERR_CUDA, "p2p graph instantiate failed: %s", cudaGetErrorString(e)); }
@@ -2054,6 +2127,23 @@ int ftb200_p2p_import(ftb200_ctx* ctx, const void* all_handles, int handles_are_
     P.nb_cum[i] = ctx->h_sendCum[i];
   }
   P.nb_cum[nnb] = ctx->h_sendCum[nnb];
+  // ---- exchange fused into the element kernels (all-hexahedra meshes; FTB200_P2P_FUSED=0: separate pack kernel) ----
+  ctx->p2p_fused = !ctx->has_tet;
+  if (const char* ev = getenv("FTB200_P2P_FUSED")) ctx->p2p_fused = ctx->p2p_fused && atoi(ev) != 0;
+  if (ctx->p2p_fused) {
+    PackArgs K;
+    memset(&K, 0, sizeof(K));
+    K.P = P;
+    K.halo_node_idx = ctx->halo_node_idx; K.halo_off = ctx->halo_off; K.halo_slot = ctx->halo_slot;
+    K.node_off = ctx->node_off; K.node_ent = ctx->node_ent;
+    int rc;
+    if ((rc = dalloc(ctx, &ctx->d_pk_ctr, (size_t)ctx->nshared + 2)) || (rc = dalloc(ctx, &ctx->d_pk, 1))) return rc;
+    CK(ftb_memset(ctx, ctx->d_pk_ctr, 0, ((size_t)ctx->nshared + 2) * sizeof(unsigned)));
+    K.node_ctr = ctx->d_pk_ctr + 2; K.packed = ctx->d_pk_ctr;
+    K.n_shared = ctx->nshared; K.nEb = ctx->nE_boundary;
+    CK(ftb_memcpy(ctx, ctx->d_pk, &K, sizeof(K), cudaMemcpyHostToDevice));
+    CK(cudaStreamSynchronize(ctx->stream));  // K lives on this stack frame
+  }
   // Load every kernel of the loop NOW: with lazy module loading the first launch of a kernel may
   // synchronise the context, which would deadlock against a peer's spinning wait kernel when several
   // ranks live in one process.
@@ -2077,6 +2167,14 @@ int ftb200_p2p_import(ftb200_ctx* ctx, const void* all_handles, int handles_are_
     CK(cudaFuncGetAttributes(&fa, k_elem<4, true, true>));
     CK(cudaFuncGetAttributes(&fa, k_elem<5, true, true>));
     CK(cudaFuncGetAttributes(&fa, k_elem<-1, true, true>));
+    CK(cudaFuncGetAttributes(&fa, k_elem_affine_cj<1>));
+    CK(cudaFuncGetAttributes(&fa, k_elem_affine_cj<4>));
+    CK(cudaFuncGetAttributes(&fa, (k_elem_affine_cj<1, true>)));
+    CK(cudaFuncGetAttributes(&fa, (k_elem_affine_cj<4, true>)));
+    CK(cudaFuncGetAttributes(&fa, (k_elem_affine<1, false>)));
+    CK(cudaFuncGetAttributes(&fa, (k_elem_affine<4, false>)));
+    CK(cudaFuncGetAttributes(&fa, (k_elem_affine<5, false>)));
+    CK(cudaFuncGetAttributes(&fa, k_stamp));
   }
   ctx->p2p_ready = true;
   return FTB200_OK;

@@ -181,7 +181,10 @@ struct HistSel<true> {
 };
 constexpr int HIST_STAGE_BYTES = 2 * 18 * FTB_ELEM_BLOCK * (int)sizeof(double);
 
+struct PackArgs;  // peer-memory exchange fused into the element kernels (below, next to P2PArgs)
 struct ElemArgs {
+  const PackArgs* pk;  // nullptr outside the partitioned loop
+  int pk_nEb;          // elements [0, pk_nEb) of the internal order touch shared nodes
   const double* X[3];
   const double* u[3];
   const int* conn;  // 8 planes
@@ -214,6 +217,8 @@ struct ElemArgs {
 #ifndef FTB_ELEM_BLOCK
 #define FTB_ELEM_BLOCK 64
 #endif
+// epilogue of the hexahedron kernels inside the partitioned loop (A.pk != nullptr); every thread of the block calls it
+__device__ void elem_p2p_epilogue(const PackArgs* pk, const int* conn, const int nE, const double* felem, const int e, const bool valid);
 #ifndef FTB_ELEM_MINBLOCKS
 #define FTB_ELEM_MINBLOCKS 6
 #endif
@@ -365,6 +370,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, (MATSEL == 5 || MATSEL < 0) ? 4 : 
     if ((threadIdx.x & 31) == 0) atomicMin(&A.sc->dtmin_bits, b);
   }
   if (status) atomicOr(&A.sc->status, status);
+  if (A.pk && e < A.pk_nEb) elem_p2p_epilogue(A.pk, A.conn, A.nE, A.felem, e, e < A.e1);
 }
 
 // K_elem for runs of hexahedra whose reference geometry is affine (hex8_element_affine_in: parallelepipeds, e.g. every
@@ -498,6 +504,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, MATSEL == 5 ? 4 : (WITH_INJ ? FTB_
   }
   if ((threadIdx.x & 31) == 0) atomicMin(&A.sc->dtmin_bits, b);
   if (status) atomicOr(&A.sc->status, status);
+  if (A.pk && e < A.pk_nEb) elem_p2p_epilogue(A.pk, A.conn, A.nE, A.felem, e, e < A.e1);
 }
 
 // K_elem for runs of neo-Hookean (MAT 1, the headline configuration) or HGO (MAT 4) parallelepipeds without the strain
@@ -511,7 +518,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, MATSEL == 5 ? 4 : (WITH_INJ ? FTB_
 #ifndef FTB_ELEM_PREFETCH
 #define FTB_ELEM_PREFETCH (148 * FTB_NH_MINBLOCKS * ELEM_BLOCK)  // elements ahead (0 = off): one resident wave
 #endif
-template <int MAT>
+template <int MAT, bool P2P = false>  // P2P: the boundary elements of the partitioned loop (fused exchange, elem_p2p_epilogue)
 #ifdef FTB_NH_MAXNREG
 __global__ void __maxnreg__(FTB_NH_MAXNREG) k_elem_affine_cj(const ElemArgs A) {
 #else
@@ -581,6 +588,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, FTB_NH_MINBLOCKS) k_elem_affine_cj
   }
   if ((threadIdx.x & 31) == 0) atomicMin(&A.sc->dtmin_bits, b);
   if (status) atomicOr(&A.sc->status, status);
+  if (P2P && e < A.pk_nEb) elem_p2p_epilogue(A.pk, A.conn, A.nE, A.felem, e, e < A.e1);
 }
 
 // The C3D4 elements of a mixed mesh: they sit in their own index ranges of the internal element
@@ -1565,6 +1573,91 @@ __host__ __device__ __forceinline__ double* p2p_recv(char* win, int H, int buf, 
   return reinterpret_cast<double*>(win + p2p_recv_off(n_ranks)) + (size_t)buf * 3 * (size_t)H;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The exchange of the partitioned step FUSED INTO THE ELEMENT KERNELS (default; FTB200_P2P_FUSED=0 restores the separate
+// k_p2p_pack launch and the publish phase of k_adv_p2p).  Why: a kernel launched behind the interior elements cannot get
+// a block onto an SM before the interior grid has handed out all of its blocks -- k_elem_affine_cj allocates every
+// register of an SM, and neither stream priorities nor explicit launch priorities change the order in which the block
+// scheduler serves the two grids (profiles/r02_p2p_trace_2gpu_*.txt: the pack kernel, launched 10 us into the step,
+// started after 103 us).  So nothing is launched: the boundary elements themselves send.
+//   * shared-node partial sums: every boundary element, after its force stores, counts itself in at each of its shared
+//     nodes; the LAST element to arrive at a node sums the node's local contributions in the node map's order (the same
+//     order, so the same bits, as k_p2p_pack / the reference's scatter) and stores the sum into the neighbours' receive
+//     windows over NVLink; the thread that packs the last shared node raises this rank's flag in every neighbour's
+//     header.  The partial sums leave ~10 us into the step, under the interior elements.
+// Only the launch of the boundary elements carries the epilogue (ElemArgs::pk); the dt MIN stays in k_adv_p2p: having the
+// last element block of the step publish it was measured -- the fence + counter of every block costs the element phase
+// 10 us at 100^3 (a block that has just streamed out 12 KB of forces waits for them instead of retiring).
+// No spinning inside the element kernels.
+struct PackArgs {
+  P2PArgs P;
+  const int* halo_node_idx;  // node -> shared-node index, -1 for the others
+  const int* halo_off;       // shared node -> its send positions (CSR), ascending neighbour
+  const int* halo_slot;      // send position i = position in sendNodeIndex = position in the neighbour's slice of its window
+  const int* node_off;       // node -> (element, slot) map
+  const int* node_ent;
+  unsigned* node_ctr;        // [n_shared] arrivals, back to zero when the node is packed
+  unsigned* packed;          // shared nodes packed this step
+  int n_shared, nEb;
+};
+__device__ __noinline__ void elem_p2p_epilogue(const PackArgs* pk, const int* conn, const int nE, const double* felem, const int e,
+                                               const bool valid) {
+  const PackArgs& K = *pk;
+  if (!(valid && e < K.nEb)) return;  // only elements touching shared nodes (they come first in the internal order)
+  const P2PArgs& P = K.P;
+  __threadfence();  // this element's force stores, device-wide, before it counts itself in
+  const size_t E = (size_t)nE;
+  const unsigned long long seq = *P.seq;
+  const int buf = (int)(seq & 1ULL);
+  unsigned mine = 0;  // bit k: this thread is the last contributor of its node k
+  int nd[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) nd[k] = conn[(size_t)k * E + e];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int h = K.halo_node_idx[nd[k]];
+    if (h < 0) continue;
+    const unsigned deg = (unsigned)(K.node_off[nd[k] + 1] - K.node_off[nd[k]]);
+    if (atomicAdd(&K.node_ctr[h], 1u) == deg - 1) {
+      K.node_ctr[h] = 0;  // every contributor has arrived: nobody touches the counter again in this step
+      mine |= 1u << k;
+    }
+  }
+  if (!mine) return;
+  __threadfence();
+  unsigned count = 0;
+  for (int k = 0; k < 8; ++k) {
+    if (!((mine >> k) & 1u)) continue;
+    const int n = nd[k];
+    const int h = K.halo_node_idx[n];
+    double f[3] = {0.0, 0.0, 0.0};
+    for (int j = K.node_off[n], j1 = K.node_off[n + 1]; j < j1; ++j) {
+      const int ent = K.node_ent[j];
+      const size_t el = (size_t)(ent >> 3);
+      const int sl = ent & 7;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) f[c] += __ldcg(felem + FTB_FIDX(3 * sl + c, el));  // L2: written by other SMs in this launch
+    }
+    for (int q = K.halo_off[h]; q < K.halo_off[h + 1]; ++q) {
+      const int i = K.halo_slot[q];
+      int nb = 0;
+      while (i >= P.nb_cum[nb + 1]) ++nb;
+      double* dst = p2p_recv(P.peer_nb[nb], P.peer_H[nb], buf, P.n_ranks) + 3 * (size_t)(P.peer_slot_off[nb] + (i - P.nb_cum[nb]));
+      dst[0] = f[0]; dst[1] = f[1]; dst[2] = f[2];  // peer store over NVLink
+    }
+    ++count;
+  }
+  __threadfence_system();  // one system-scope fence per thread, after all of its peer stores
+  if (atomicAdd(K.packed, count) + count == (unsigned)K.n_shared) {
+    *K.packed = 0;
+    __threadfence_system();
+    for (int nb = 0; nb < P.n_nb; ++nb) {
+      volatile unsigned long long* fl = &reinterpret_cast<P2PHeader*>(P.peer_nb[nb])->hflag[P.peer_my_index[nb]];
+      *fl = seq + 1;
+    }
+  }
+}
+
 __global__ void k_p2p_pack(const P2PArgs P, const double* felem, const int* node_off, const int* node_ent,
                            const int* sendNodeIndex, const DevScalars* sc, int nE) {
   if (sc->last | sc->done) return;
@@ -1615,7 +1708,8 @@ __global__ void k_stamp(unsigned long long* tr, const DevScalars* sc, int slot, 
 }
 
 // dt exchange + waits + the scalar update of k_adv<false>
-__global__ void k_adv_p2p(const P2PArgs P, DevScalars* sc, double* mp, int nPID, double* dt_hist, unsigned long long* trace) {
+__global__ void k_adv_p2p(const P2PArgs P, DevScalars* sc, double* mp, int nPID, double* dt_hist, unsigned long long* trace,
+                          const int published) {
   __shared__ double s_ndt;
   __shared__ int s_live, s_ok;
   unsigned long long* tr = nullptr;
@@ -1635,6 +1729,7 @@ __global__ void k_adv_p2p(const P2PArgs P, DevScalars* sc, double* mp, int nPID,
   P2PHeader* self = reinterpret_cast<P2PHeader*>(P.self);
   // publish this rank's dt to every rank (its own window included)
   const double mydt = __longlong_as_double((long long)*(volatile unsigned long long*)&sc->dtmin_bits);
+  if (!published)  // (fused exchange: the last element block of the step has published it already)
   for (int r = threadIdx.x; r < P.n_ranks; r += blockDim.x) {
     P2PHeader* w = reinterpret_cast<P2PHeader*>(P.peer_rank[r]);
     *(volatile double*)&w->dtslot[buf][P.rank] = mydt;
