@@ -43,7 +43,8 @@ def algorithmic_bytes(n, mat, energy):
 # (n, material, energy, injury) -> measured DRAM bytes per k_elem launch (ncu, see profiles/)
 # key: (n, material, energy, injury, affine kernel)
 NCU_TRAFFIC_BYTES = {(100, 1, True, False, False): 86507008 + 138745344,   # profiles/r01_k_elem_general_ncu_full.csv
-                     (100, 1, True, False, True): 86602752 + 136579840}    # profiles/r01_k_elem_affine_ncu_full.csv
+                     (100, 1, True, False, True): 86602752 + 136579840,    # profiles/r01_k_elem_affine_ncu_full.csv
+                     (100, 1, True, False, "cj"): 86509312 + 133839360}    # profiles/r02_k_elem_affine_cj_ncu_full.csv
 # executed fp64 flops per element in K_elem (FMA = 2).  Material 1 from ncu (general kernel: 1208 DFMA + 463 DADD + 507 DMUL
 # per element, profiles/r01_k_elem_general_ncu_full.csv); materials 4 and 5 = material 1 + the SASS difference of their
 # material code
@@ -54,6 +55,11 @@ ELEM_FLOPS = {1: 3386.0, 4: 4296.0, 5: 6446.0}
 # FMAs, no coordinate modes and columns: 1060 DFMA + 357 DADD + 378 DMUL per element for material 1
 # (profiles/r01_k_elem_affine_ncu_full.csv), i.e. 531 flops less than the general kernel
 ELEM_FLOPS_AFFINE = {k: v - 531.0 for k, v in ELEM_FLOPS.items()}
+# k_elem_affine_cj (round 2, current-Jacobian form of the parallelepiped element; the default for
+# materials 1 and 4 without the strain outputs): material 1 from ncu -- 707 DFMA + 248 DADD + 251 DMUL per element
+# (profiles/r02_k_elem_affine_cj_ncu_full.csv) = 1914 flops; material 4 = k_elem_affine<4> minus the SASS difference of
+# the Gauss loop (47 DFMA + 4 DMUL fewer, 1 DADD more per point) plus the per-element M
+ELEM_FLOPS_CJ = {1: 1914.0, 4: 3030.0}
 
 
 def _nvml_sampler(stop, out, device_index):
@@ -263,7 +269,10 @@ def ours_single(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    flops = (n_affine * ELEM_FLOPS_AFFINE[mat] + (E - n_affine) * ELEM_FLOPS[mat]) / E
+    # which kernel the parallelepipeds run: the current-Jacobian form unless switched off or the strain outputs are on
+    cj = mat in ELEM_FLOPS_CJ and not args.injury and os.environ.get("FTB200_NH", "1") != "0"
+    flops_aff = ELEM_FLOPS_CJ[mat] if cj else ELEM_FLOPS_AFFINE[mat]
+    flops = (n_affine * flops_aff + (E - n_affine) * ELEM_FLOPS[mat]) / E
     fused = prof["node_launches"] == 0  # one fused kernel per step (k_step): element and node work in the same launch
     elem_s = prof["elem_ms"] * 1e-3
     if fused:
@@ -295,7 +304,8 @@ def ours_single(args):
         node_gbs = b_node * E / node_s / 1e9
         fp64_bound = elem_tf / fp64_peak >= elem_gbs / hbm_peak
         roofline = {
-            "kernel": ("k_elem_affine" if n_affine == E else "k_elem") + " (fused gather, F, material, B^T sigma, element dt)",
+            "kernel": (("k_elem_affine_cj" if cj else "k_elem_affine") if n_affine == E else "k_elem") +
+                      " (fused gather, F, material, B^T sigma, element dt)",
             "bound": "fp64" if fp64_bound else "hbm",
             "achieved": elem_tf if fp64_bound else elem_gbs,
             "peak": fp64_peak if fp64_bound else hbm_peak,
@@ -303,11 +313,12 @@ def ours_single(args):
             "frac": (elem_tf / fp64_peak) if fp64_bound else (elem_gbs / hbm_peak),
             # DRAM bytes of one k_elem launch from the ncu --set full capture of this configuration
             # (profiles/r01_k_elem_final_ncu_full.csv: dram__bytes_read.sum + dram__bytes_write.sum); other configs: null
-            "traffic": NCU_TRAFFIC_BYTES.get((n, mat, bool(energy), bool(args.injury), n_affine == E)),
+            "traffic": NCU_TRAFFIC_BYTES.get((n, mat, bool(energy), bool(args.injury), ("cj" if cj else True) if n_affine == E else False)),
             "traffic_unit": "bytes per launch (algorithmic: %d)" % int(b_elem * E),
             "traffic_source": "PINNED CONSTANT, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one "
-                              "launch from the ncu --set full capture profiles/r01_k_elem_affine_ncu_full.csv (commit f34820f; "
-                              "general kernel: r01_k_elem_general_ncu_full.csv); null for configurations without a capture",
+                              "launch from the ncu --set full capture profiles/r02_k_elem_affine_cj_ncu_full.csv (round 2; "
+                              "k_elem_affine: r01_k_elem_affine_ncu_full.csv, general kernel: r01_k_elem_general_ncu_full.csv); "
+                              "null for configurations without a capture",
             # what north_star scores is the STEP: both roofs and the step's fraction of the slower one, first
             "step_frac_of_min_roof": value / min(fp64_peak * 1e12 / flops, hbm_peak * 1e9 / (b_elem + b_node)),
             "step_roof_fp64": fp64_peak * 1e12 / flops, "step_roof_hbm": hbm_peak * 1e9 / (b_elem + b_node),
@@ -455,8 +466,9 @@ def ours_single(args):
                                "(Benchmarking-Parallel.cpp:184-244), %s, dt recomputed every step"
                                % (n, ("structured, nodes jittered by %g of the spacing" % args.jitter) if args.jitter else "structured",
                                   E, N, MAT_NAME[mat], "CheckEnergy every step" if energy else "no energy check"),
-                   "element_kernel": "%d of %d hexahedra have a parallelepiped reference geometry and run k_elem_affine "
-                                     "(dN/dX once per element); the rest run the general k_elem" % (n_affine, E),
+                   "element_kernel": "%d of %d hexahedra have a parallelepiped reference geometry and run %s; the rest run the "
+                                     "general k_elem" % (n_affine, E, "k_elem_affine_cj (current-Jacobian form)" if cj else
+                                                         "k_elem_affine (dN/dX once per element)"),
                    "injury_criteria": bool(args.injury),
                    "mode": "resident ExplicitDynamics loop, CUDA graph of 25 steps, " +
                            ("one fused kernel per step" if prof["node_launches"] == 0 else "element + node kernels per step"),

@@ -2077,6 +2077,12 @@ int ftb200_p2p_export(ftb200_ctx* ctx, void* handle_out, void** window_out) {
     ctx->p2p_bytes = p2p_recv_off(ctx->nranks) + 2 * 3 * (size_t)std::max(ctx->halo_count, 1) * sizeof(double);
     CK(cudaMalloc((void**)&ctx->p2p_window, ctx->p2p_bytes));
     CK(ftb_memset(ctx, ctx->p2p_window, 0, ctx->p2p_bytes));
+    {  // the dt slots start out empty (P2PHeader)
+      std::vector<unsigned long long> empty(4 * P2P_MAXP, P2P_DT_EMPTY);
+      CK(cudaMemcpyAsync(ctx->p2p_window + offsetof(P2PHeader, dtslot), empty.data(), empty.size() * sizeof(unsigned long long),
+                         cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
     int rc;
     if ((rc = dalloc(ctx, &ctx->d_seq, 1)) || (rc = dalloc(ctx, &ctx->d_p2p_blocks, 1))) return rc;
     CK(ftb_memset(ctx, ctx->d_seq, 0, sizeof(unsigned long long)));

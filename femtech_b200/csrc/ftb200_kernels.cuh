@@ -879,8 +879,8 @@ __global__ void __launch_bounds__(NODE_BLOCK, FTB_NODE_MINBLOCKS) k_node(const N
           for (int c = 0; c < 3; ++c) f[c] += __ldg(A.felem + FTB_FIDX(3 * s + c, e));
         }
       }
-      if (A.halo_node_idx) {  // shared node: add the neighbours' partial sums, ascending neighbour (:92-97)
-        const int h = A.halo_node_idx[n];
+      if (A.halo_node_idx && (fl & FTB_FLAG_SHARED)) {  // shared node: add the neighbours' partial sums, ascending neighbour (:92-97)
+        const int h = A.halo_node_idx[n];  // (only the ~3 % shared nodes pay for this dependent load)
         if (h >= 0) {
           // peer-memory transport: the window that was filled during this step ((seq - 1) & 1, seq already advanced)
           const double* rv = A.halo_recv;
@@ -1544,10 +1544,14 @@ __global__ void k_sum3(const double* epart, int nblocks, double* out3) {
 // neighbour because it needs that neighbour's dt to finish each step.  Everything is graph-capturable.
 constexpr int P2P_MAXNB = 64;
 constexpr int P2P_MAXP = 64;
+constexpr unsigned long long P2P_DT_EMPTY = 0x7FF8000000000001ULL;  // a NaN: dt_to_bits never produces one
 struct P2PHeader {
   unsigned long long hflag[P2P_MAXNB];
   unsigned long long dflag[P2P_MAXP];
-  double dtslot[2][P2P_MAXP];
+  // dt of every rank for step seq in dtslot[seq & 3]: the value is its own arrival flag (a slot holds P2P_DT_EMPTY until
+  // the rank's store lands; the reader re-arms slot (seq + 2) & 3 after consuming slot seq & 3 -- a peer can only write
+  // that slot after it has seen this rank's dt of step seq + 1, which is published after the re-arm)
+  double dtslot[4][P2P_MAXP];
   unsigned long long iflag[P2P_MAXP];  // per source rank: (step sequence * 8 + radix pass + 1) of its last injury histogram
 };
 struct P2PArgs {
@@ -1727,21 +1731,18 @@ __global__ void k_adv_p2p(const P2PArgs P, DevScalars* sc, double* mp, int nPID,
   const unsigned long long seq = *P.seq;
   const int buf = (int)(seq & 1ULL);
   P2PHeader* self = reinterpret_cast<P2PHeader*>(P.self);
-  // publish this rank's dt to every rank (its own window included)
-  const double mydt = __longlong_as_double((long long)*(volatile unsigned long long*)&sc->dtmin_bits);
-  if (!published)  // (fused exchange: the last element block of the step has published it already)
-  for (int r = threadIdx.x; r < P.n_ranks; r += blockDim.x) {
-    P2PHeader* w = reinterpret_cast<P2PHeader*>(P.peer_rank[r]);
-    *(volatile double*)&w->dtslot[buf][P.rank] = mydt;
-    __threadfence_system();
-    *(volatile unsigned long long*)&w->dflag[P.rank] = seq + 1;
-  }
+  // publish this rank's dt to every rank (its own window included): ONE 8-byte store per rank, no fence and no flag
+  const unsigned long long mybits = *(volatile unsigned long long*)&sc->dtmin_bits;
+  const int slot = (int)(seq & 3ULL);
+  if (!published)
+    for (int r = threadIdx.x; r < P.n_ranks; r += blockDim.x)
+      *(volatile unsigned long long*)&reinterpret_cast<P2PHeader*>(P.peer_rank[r])->dtslot[slot][P.rank] = mybits;
   if (tr) tr[4] = now_ns();
   // wait for every rank's dt and every neighbour's partials of this step
   const unsigned long long t0 = now_ns();
   for (int r = threadIdx.x; r < P.n_ranks + P.n_nb; r += blockDim.x) {
-    volatile unsigned long long* fl = r < P.n_ranks ? &self->dflag[r] : &self->hflag[r - P.n_ranks];
-    while (*fl < seq + 1) {
+    volatile unsigned long long* fl = r < P.n_ranks ? (volatile unsigned long long*)&self->dtslot[slot][r] : &self->hflag[r - P.n_ranks];
+    while (r < P.n_ranks ? (*fl == P2P_DT_EMPTY) : (*fl < seq + 1)) {
       __nanosleep(100);
       if (now_ns() - t0 > 5000000000ULL) { s_ok = 0; break; }
     }
@@ -1753,8 +1754,9 @@ __global__ void k_adv_p2p(const P2PArgs P, DevScalars* sc, double* mp, int nPID,
     if (!s_ok) { sc->status |= 64; sc->last = 1; }  // a peer never arrived: stop instead of hanging
     double dtmin = 1e300;
     for (int r = 0; r < P.n_ranks; ++r) {
-      const double d = *(volatile double*)&self->dtslot[buf][r];
+      const double d = *(volatile double*)&self->dtslot[slot][r];
       if (d < dtmin) dtmin = d;
+      *(volatile unsigned long long*)&self->dtslot[(slot + 2) & 3][r] = P2P_DT_EMPTY;  // re-arm (see P2PHeader)
     }
     sc->dtmin_bits = (unsigned long long)__double_as_longlong(dtmin);
     *P.seq = seq + 1;
