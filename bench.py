@@ -44,7 +44,7 @@ def algorithmic_bytes(n, mat, energy):
 # key: (n, material, energy, injury, affine kernel)
 NCU_TRAFFIC_BYTES = {(100, 1, True, False, False): 86507008 + 138745344,   # profiles/r01_k_elem_general_ncu_full.csv
                      (100, 1, True, False, True): 86602752 + 136579840,    # profiles/r01_k_elem_affine_ncu_full.csv
-                     (100, 1, True, False, "cj"): 86509312 + 133839360}    # profiles/r02_k_elem_affine_cj_ncu_full.csv
+                     (100, 1, True, False, "cj"): 86508544 + 133630464}    # profiles/r02_k_elem_affine_cj_ncu_full.csv
 # executed fp64 flops per element in K_elem (FMA = 2).  Material 1 from ncu (general kernel: 1208 DFMA + 463 DADD + 507 DMUL
 # per element, profiles/r01_k_elem_general_ncu_full.csv); materials 4 and 5 = material 1 + the SASS difference of their
 # material code
@@ -56,10 +56,10 @@ ELEM_FLOPS = {1: 3386.0, 4: 4296.0, 5: 6446.0}
 # (profiles/r01_k_elem_affine_ncu_full.csv), i.e. 531 flops less than the general kernel
 ELEM_FLOPS_AFFINE = {k: v - 531.0 for k, v in ELEM_FLOPS.items()}
 # k_elem_affine_cj (round 2, current-Jacobian form of the parallelepiped element; the default for
-# materials 1 and 4 without the strain outputs): material 1 from ncu -- 707 DFMA + 248 DADD + 251 DMUL per element
-# (profiles/r02_k_elem_affine_cj_ncu_full.csv) = 1914 flops; material 4 = k_elem_affine<4> minus the SASS difference of
+# materials 1 and 4 without the strain outputs): material 1 from ncu -- 689 DFMA + 248 DADD + 251 DMUL per element
+# (profiles/r02_k_elem_affine_cj_ncu_full.csv) = 1876 flops; material 4 = k_elem_affine<4> minus the SASS difference of
 # the Gauss loop (47 DFMA + 4 DMUL fewer, 1 DADD more per point) plus the per-element M
-ELEM_FLOPS_CJ = {1: 1914.0, 4: 3030.0}
+ELEM_FLOPS_CJ = {1: 1876.0, 4: 3030.0}
 
 
 def _nvml_sampler(stop, out, device_index):
