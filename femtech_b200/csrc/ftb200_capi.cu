@@ -2105,6 +2105,10 @@ int ftb200_p2p_import(ftb200_ctx* ctx, const void* all_handles, int handles_are_
   const int nnb = (int)ctx->h_sendProcessID.size();
   if (nnb && (!peer_slot_offset || !peer_my_index || !peer_halo_count)) return fail(ctx, FTB200_ERR_INPUT, "p2p_import: null metadata");
   CK(cudaSetDevice(ctx->device));
+  // a loop graph captured after an earlier import has the old windows and the old PackArgs block baked into its kernel
+  // arguments: drop it (the next run captures again)
+  CK(cudaStreamSynchronize(ctx->stream));
+  drop_graphs(ctx);
   P2PArgs& P = ctx->p2p;
   memset(&P, 0, sizeof(P));
   P.self = ctx->p2p_window;
