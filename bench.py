@@ -30,14 +30,37 @@ MAT_NAME = {1: "compressible neo-Hookean (mat 1)", 4: "HGO isotropic (mat 4)", 5
 
 # Algorithmic work per element-step (DESIGN.md "Work model"): bytes = compulsory HBM traffic of the
 # design, flops = fp64 operations of the mode-basis formulation actually executed (FMA = 2).
-def algorithmic_bytes(n, mat, energy):
-    rho_n = ((n + 1.0) / n) ** 3
+def algorithmic_bytes(n, mat, energy, rho_n=None):
+    if rho_n is None:
+        rho_n = ((n + 1.0) / n) ** 3
     elem = 36 + 1 + 48 * rho_n + 192            # K_elem: conn+pid+eflag, X and u (unique nodes), f_e write
     node = 192 + (4 + 32) * rho_n + (8 + 2 + 72 + 72) * rho_n  # K_node: f_e read, CSR, m, flags, u v a read + write
     if energy:
         node += 48 * rho_n                       # fi: write + read next step (the displacement increment is rebuilt, not stored)
     hist = 2304 if mat == 5 else 0
     return elem + hist, node
+
+
+def hbm_peak_gbs():
+    """Measured copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the profiling recipe's fallback."""
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def step_roofline(value_total, n_gpus, mat, energy, rho_n):
+    """`roofline` of a multi-GPU line: the STEP of one GPU against the HBM roof (the binding one since the current-Jacobian
+    element kernel): algorithmic bytes per element-step x this GPU's element-steps/s."""
+    b_elem, b_node = algorithmic_bytes(0, mat, energy, rho_n=rho_n)
+    peak, src = hbm_peak_gbs()
+    gbs = (b_elem + b_node) * (value_total / n_gpus) / 1e9
+    return {"kernel": "whole step of one GPU (element kernel + node kernel + exchange)", "bound": "hbm", "achieved": gbs, "peak": peak,
+            "unit": "GB/s", "frac": gbs / peak, "traffic": None, "peak_source": "hbm: " + src,
+            "algorithmic_bytes_per_element": b_elem + b_node,
+            "step_frac_of_hbm_roof_survey_bytes": 717.0 * (value_total / n_gpus) / 1e9 / peak,
+            "note": "per-kernel fp64 / HBM views are in the N = 1 line; ncu cannot attach to a multi-process run"}
 
 
 # (n, material, energy, injury) -> measured DRAM bytes per k_elem launch (ncu, see profiles/)

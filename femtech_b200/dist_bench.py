@@ -176,7 +176,8 @@ def run(args):
                        "l2": "per-step working set > 126 MB L2 per GPU, no flush needed",
                        "valid": "state check: u, v of every rank after warm-up + timed steps vs the single-GPU resident run of "
                                 "the same global mesh, 1e-9 relative (validation key)"},
-            "roofline": None, "cpu_baseline": None,
+            "roofline": bench.step_roofline(E_total * args.steps / (ms_total * 1e-3), world, mat, bool(energy), N_local / float(E_local)),
+            "cpu_baseline": None,
             "e2e": {"value": E_total * e2e_steps / float(e2e_s[0]), "unit": "element-steps/s",
                     "h2d_bytes_per_step": (3 * 24 + 12) * N_local * world / e2e_steps,
                     "d2h_bytes_per_step": (5 * 24 + 12) * N_local * world / e2e_steps + 64 * world,

@@ -24,3 +24,19 @@ def test_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"]
+
+
+def test_multi_gpu_roofline_object():
+    """The `roofline` object of the N > 1 lines (bench.step_roofline, called by femtech_b200/dist_bench.py): the step of one
+    GPU against the HBM roof, from the same byte model as the N = 1 line."""
+    sys.path.insert(0, ROOT)
+    import bench
+    rho = (101.0 / 100.0) ** 3
+    r = bench.step_roofline(8 * 4.46e9, 8, 1, True, rho)
+    be, bn = bench.algorithmic_bytes(100, 1, True)
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["traffic"] is None
+    assert r["algorithmic_bytes_per_element"] == pytest.approx(be + bn)
+    assert r["achieved"] == pytest.approx((be + bn) * 4.46e9 / 1e9)
+    assert r["frac"] == pytest.approx(r["achieved"] / r["peak"]) and 0 < r["frac"] < 1
+    assert r["step_frac_of_hbm_roof_survey_bytes"] == pytest.approx(717.0 * 4.46 / r["peak"])
+    json.dumps(r)
