@@ -1595,15 +1595,15 @@ static int build_graph(ftb200_ctx* ctx) {
 static void launch_step_p2p(ftb200_ctx* ctx) {
   cudaStream_t s = ctx->stream, s2 = ctx->stream_lo;
   const int nEb = ctx->nE_boundary;
-  // elements touching shared nodes first, on the high-priority main stream; the interior fills the machine behind them
   unsigned long long* tr = ctx->trace;
   if (tr) LAUNCH(k_stamp, 1, 1, s, tr, ctx->sc, 0, 0);
-  // The boundary elements must reach the SMs BEFORE the interior ones (their partial sums then cross NVLink while the
-  // interior is integrated).  Stream priorities alone do not achieve that inside the captured graph: the trace
-  // (profiles/r02_p2p_trace_2gpu_before.txt) shows the boundary grid finishing 103 us into the step, behind the
-  // interior's blocks.  p2p_order: 0 stream priorities only (round 1), 1 explicit priority attribute on every launch,
-  // 2 the interior waits for a programmatic event that fires once every boundary block has started, 3 the interior
-  // waits for the boundary grid to finish.
+  // The partial sums of the shared nodes should cross NVLink while the interior is integrated.  With a separate pack
+  // kernel they do not: whatever is launched behind the interior grid gets its first block only when that grid has
+  // handed out all of its blocks (the element kernel allocates every register of an SM) -- the trace
+  // (profiles/r02_p2p_trace_2gpu_before.txt) shows the marker behind the boundary elements 103 us into the step and the
+  // pack kernel done at 123 us.  p2p_order (two-stream form, measured, none helps): 0 stream priorities only, 1 explicit
+  // priority attribute on every launch, 2 the interior waits for a programmatic event that fires once every boundary
+  // block has started, 3 the interior waits for the boundary grid to finish.  Hence the fused exchange below.
   const int order = nEb > 0 ? ctx->p2p_order : 0;
   // Fused exchange on a mesh that one hexahedron kernel covers (one material, one geometry class): ONE launch over all
   // elements.  Blocks are handed out in element order, so the boundary elements -- first in the internal order -- run
@@ -1619,6 +1619,7 @@ static void launch_step_p2p(ftb200_ctx* ctx) {
     ctx->pk_on = false;
     if (tr) { LAUNCH(k_stamp, 1, 1, s, tr, ctx->sc, 1, 0); LAUNCH(k_stamp, 1, 1, s, tr, ctx->sc, 2, 0); LAUNCH(k_stamp, 1, 1, s, tr, ctx->sc, 7, 0); }
   } else {
+  // two-stream form: elements touching shared nodes on the main stream, the interior behind them on its own stream
   cudaEventRecord(ctx->ev_fork, s);
   if (order == 1) { ctx->la_kind = 1; ctx->la_prio = ctx->prio_hi; }
   if (order == 2) { ctx->la_kind = 2; ctx->la_event = ctx->ev_prog; }
