@@ -516,7 +516,8 @@ __global__ void __launch_bounds__(ELEM_BLOCK, MATSEL == 5 ? 4 : (WITH_INJ ? FTB_
 #define FTB_NH_MINBLOCKS 8
 #endif
 #ifndef FTB_ELEM_PREFETCH
-#define FTB_ELEM_PREFETCH (148 * FTB_NH_MINBLOCKS * ELEM_BLOCK)  // elements ahead (0 = off): one resident wave
+#define FTB_ELEM_PREFETCH 0  // L2 prefetch of the connectivity this many elements ahead (one resident wave = 148 * 8 * 64):
+                             // measured 110.8 us on against 110.7 us off (profiles/r02_k_elem_affine_cj_prefetch_register_variants.txt) -- off
 #endif
 template <int MAT, bool P2P = false>  // P2P: the boundary elements of the partitioned loop (fused exchange, elem_p2p_epilogue)
 #ifdef FTB_NH_MAXNREG
@@ -544,7 +545,7 @@ __global__ void __launch_bounds__(ELEM_BLOCK, FTB_NH_MINBLOCKS) k_elem_affine_cj
       const size_t ef = (size_t)(e - lane) + FTB_ELEM_PREFETCH + ((lane & 8) ? 31 : 0);
       if (ef < (size_t)A.e1) {
         if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.conn + (size_t)(lane & 7) * E + ef));
-        else if (lane < 18) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.pid + ef + (lane & 1) * 31));
+        else if (lane < 18) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.pid + min(ef + (size_t)((lane & 1) * 31), (size_t)A.e1 - 1)));
         else if (lane == 18) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.eflag + ef));
       }
     }
